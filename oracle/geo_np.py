@@ -1,0 +1,282 @@
+"""
+ORACLE (test infrastructure, never imported by the product): numpy
+restatement of the planar-rupture geometry on the classical-PSHA hot path:
+rupture construction (corners -> planar record) and the rupture-to-site
+distance metrics rrup / rjb / rx / ry0 / repi / rhypo / azimuth.
+
+Follows openquake/hazardlib/geo/surface/planar.py (build_planar :209-251,
+_build_corners :107-185, build_planar_array :261-320, project :324-403,
+get_rjb :460-529, get_rx :533-545, get_ry0 :549-568, get_rhypo/repi/azimuth
+:572-621), openquake/hazardlib/geo/geodetic.py (distances :38-48,
+distances_to_arc :51-66, fast_point_at :483-517) and
+openquake/hazardlib/geo/utils.py (cartesian_to_spherical :688-707,
+min_distance :710-720).  Pinned by tests/golden/planar_*.npz (reference
+outputs) and by the reference's own known-answer test
+hazardlib/tests/contexts_test.py:347-360.
+
+A "planar" here is a dict of arrays with the same fields as the reference's
+planar_array_dt (planar.py:45-53), leading dimension U (ruptures):
+corners (U,3,4) [lon,lat,dep x TL,TR,BL,BR], xyz (U,3,4), normal/uv1/uv2
+(U,3), wlr (U,3) [width,length,rate], sdr (U,3), hypo (U,3).
+"""
+import math
+import numpy as np
+
+EARTH_RADIUS = 6371.0  # geodetic.py:32
+
+
+def spherical_to_cartesian(lons, lats, deps):
+    # geodetic.py:445-480
+    phi, theta = np.radians(lons), np.radians(lats)
+    rr = EARTH_RADIUS - np.asarray(deps, float)
+    ctr = rr * np.cos(theta)
+    return np.stack([ctr * np.cos(phi), ctr * np.sin(phi),
+                     rr * np.sin(theta)], axis=-1)
+
+
+def cartesian_to_spherical(xyz):
+    # geo/utils.py:688-707; xyz (N, 3) -> lons, lats, deps
+    rr = np.sqrt(np.sum(xyz * xyz, axis=-1))
+    x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
+    return (np.degrees(np.arctan2(y, x)),
+            np.degrees(np.arcsin(np.clip(z / rr, -1., 1.))),
+            EARTH_RADIUS - rr)
+
+
+def distances(lon, lat, lons, lats):
+    # geodetic.py:38-48, radians in, km out
+    d = np.arcsin(np.sqrt(
+        np.sin((lat - lats) / 2.0) ** 2 +
+        np.cos(lat) * np.cos(lats) * np.sin((lon - lons) / 2.0) ** 2))
+    return d * 2. * EARTH_RADIUS
+
+
+def distances_to_arc(lon, lat, azi, lons, lats):
+    # geodetic.py:51-66, degrees in, km out (signed: + on the left of the arc
+    # ... as the reference defines it)
+    lon, lat, azi = np.radians(lon), np.radians(lat), np.radians(azi)
+    lons, lats = np.radians(lons), np.radians(lats)
+    coss = np.cos(lats)
+    azi_to_target = - np.arctan2(
+        np.sin(lon - lons) * coss,
+        np.cos(lat) * np.sin(lats) - np.sin(lat) * coss * np.cos(lon - lons))
+    dist = distances(lon, lat, lons, lats)
+    s = np.sin(azi_to_target - azi)
+    angle = np.arccos(s * np.sin(dist / EARTH_RADIUS))
+    return (np.pi / 2. - angle) * EARTH_RADIUS
+
+
+def fast_point_at(lon, lat, azimuth, distance):
+    # geodetic.py:483-517, scalars
+    lon, lat = math.radians(lon), math.radians(lat)
+    tc = - math.radians(azimuth)
+    sd, cd = math.sin(distance / EARTH_RADIUS), math.cos(distance / EARTH_RADIUS)
+    sl, cl = math.sin(lat), math.cos(lat)
+    sin_lats = sl * cd + cl * sd * math.cos(tc)
+    dlon = math.atan2(math.sin(tc) * sd * cl, cd - sl * sin_lats)
+    lons = (lon - dlon + math.pi) % (2 * math.pi) - math.pi
+    return math.degrees(lons), math.degrees(math.asin(sin_lats))
+
+
+# ----------------------------------------------------------------------- #
+#                         rupture construction                             #
+# ----------------------------------------------------------------------- #
+
+def rupdims(usd, lsd, rar, area, dip):
+    # get_rupdims planar.py:68-95 -> length, horizontal width, height
+    rdip = math.radians(dip)
+    sd, cd = math.sin(rdip), math.cos(rdip)
+    max_width = (lsd - usd) / sd
+    length = math.sqrt(area * rar)
+    width = area / length
+    if width > max_width:
+        width = max_width
+        length = area / width
+    return length, width * cd, width * sd
+
+
+def rupture_corners(usd, lsd, rar, area, strike, dip, clon, clat, cdep,
+                    dip_frac=0.5):
+    """
+    _build_corners planar.py:107-185 for a single hypocentral depth:
+    returns corners (4, 3) [TL, TR, BL, BR] x [lon, lat, dep] and the
+    (possibly shifted) centre depth.
+    """
+    length, width, height = rupdims(usd, lsd, rar, area, dip)
+    hl, hw, hh = length / 2., width / 2., height / 2.
+    theta = math.degrees(math.atan(hw / hl))
+    hor = math.sqrt(hl ** 2 + hw ** 2)
+    shift = (1. - 2. * dip_frac) * hh
+    top, bot = cdep + shift - hh, cdep + shift + hh
+    v = usd - top
+    if v < 0:
+        v = lsd - bot
+        if v > 0:
+            v = 0.
+    v = shift + v
+    lon, lat = clon, clat
+    if v != 0:
+        azi = (strike + 90 + 90 + 90) if v < 0 else (strike + 90)
+        lon, lat = fast_point_at(clon, clat, azi, abs(v / hh * hw))
+        cdep = cdep + v
+    out = np.zeros((4, 3))
+    out[0, :2] = fast_point_at(lon, lat, strike + 180 + theta, hor)
+    out[1, :2] = fast_point_at(lon, lat, strike - theta, hor)
+    out[2, :2] = fast_point_at(lon, lat, strike + 180 - theta, hor)
+    out[3, :2] = fast_point_at(lon, lat, strike + theta, hor)
+    out[0:2, 2] = cdep - hh
+    out[2:4, 2] = cdep + hh
+    return out, cdep
+
+
+def planar_from_corners(corners, sdr, hypo, rate=None):
+    """
+    build_planar_array planar.py:261-320; corners (U, 4, 3) -> planar dict
+    """
+    corners = np.asarray(corners, float)
+    U = len(corners)
+    xyz = spherical_to_cartesian(
+        corners[..., 0], corners[..., 1], corners[..., 2])  # (U, 4, 3)
+    tl, tr, bl = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+
+    def unit(v):
+        return v / np.sqrt(np.sum(v * v, axis=-1))[:, None]
+    n = unit(np.cross(tl - tr, tl - bl))
+    uv1 = unit(tr - tl)
+    uv2 = np.cross(n, uv1)
+    delta = xyz - xyz[:, :1]
+    def dot(a, b):  # same association as planar.py:253-256
+        return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1] +
+                a[..., 2] * b[..., 2])
+    xx = dot(delta, uv1[:, None, :]).T   # (4, U)
+    yy = dot(delta, uv2[:, None, :]).T
+    # xx[0] = yy[0] = 0 by construction in the reference (zeros, not dots)
+    xx[0] = 0.
+    yy[0] = 0.
+    length = ((xx[1] - xx[0]) + (xx[3] - xx[2])) / 2.0
+    width = ((yy[2] - yy[0]) + (yy[3] - yy[1])) / 2.0
+    wlr = np.zeros((U, 3))
+    wlr[:, 0], wlr[:, 1] = width, length
+    if rate is not None:
+        wlr[:, 2] = rate
+    return dict(corners=np.transpose(corners, (0, 2, 1)).copy(),
+                xyz=np.transpose(xyz, (0, 2, 1)).copy(),
+                normal=n, uv1=uv1, uv2=uv2, wlr=wlr,
+                sdr=np.asarray(sdr, float).reshape(U, 3).copy(),
+                hypo=np.asarray(hypo, float).reshape(U, 3).copy())
+
+
+def build_planar(mag, strike, dip, rake, rate, area, hypo_lon, hypo_lat,
+                 hypo_dep, usd, lsd, rar):
+    """
+    build_planar planar.py:209-251 for U independent single-depth ruptures
+    (each with its own hypocentre), shift_hypo=False, dip_frac 0.5.
+    """
+    U = len(mag)
+    corners = np.zeros((U, 4, 3))
+    for u in range(U):
+        corners[u], _ = rupture_corners(
+            usd, lsd, rar, area[u], strike[u], dip[u],
+            hypo_lon[u], hypo_lat[u], hypo_dep[u])
+    sdr = np.stack([strike, dip, rake], axis=1)
+    hypo = np.stack([hypo_lon, hypo_lat, hypo_dep], axis=1)
+    return planar_from_corners(corners, sdr, hypo, rate)
+
+
+# ----------------------------------------------------------------------- #
+#                               distances                                  #
+# ----------------------------------------------------------------------- #
+
+def project(planar, points):
+    """planar.py:324-403: (rrup, xx, yy) each (U, N); points (N, 3) xyz"""
+    mat = points[None, :, :] - planar['xyz'][:, None, :, 0]   # (U, N, 3)
+
+    def dot(v):
+        return (mat[..., 0] * v[:, None, 0] + mat[..., 1] * v[:, None, 1] +
+                mat[..., 2] * v[:, None, 2])
+    dists, xx, yy = dot(planar['normal']), dot(planar['uv1']), dot(planar['uv2'])
+    width, length = planar['wlr'][:, None, 0], planar['wlr'][:, None, 1]
+    mxx = np.where(xx < 0, xx, np.where(xx > length, xx - length, 0.))
+    myy = np.where(yy < 0, yy, np.where(yy > width, yy - width, 0.))
+    return np.sqrt(dists ** 2 + mxx ** 2 + myy ** 2), xx, yy
+
+
+def _arcs(planar, lons, lats):
+    """the four signed arc distances of get_rjb, each (U, N)"""
+    c = planar['corners']
+    strike = planar['sdr'][:, 0, None]
+    downdip = (strike + 90) % 360
+    clon, clat = c[:, 0, :, None], c[:, 1, :, None]   # (U, 4, 1)
+    a0 = distances_to_arc(clon[:, 2], clat[:, 2], strike, lons, lats)
+    a1 = distances_to_arc(clon[:, 0], clat[:, 0], strike, lons, lats)
+    a2 = distances_to_arc(clon[:, 0], clat[:, 0], downdip, lons, lats)
+    a3 = distances_to_arc(clon[:, 1], clat[:, 1], downdip, lons, lats)
+    return a0, a1, a2, a3
+
+
+def get_rjb(planar, points):
+    """planar.py:460-529"""
+    lons, lats, _ = cartesian_to_spherical(points)
+    a0, a1, a2, a3 = _arcs(planar, lons, lats)
+    c = planar['corners']
+    cxyz = spherical_to_cartesian(c[:, 0], c[:, 1], np.zeros_like(c[:, 0]))
+    d2 = ((cxyz[:, None, :, :] - points[None, :, None, :]) ** 2).sum(axis=-1)
+    dcorner = np.sqrt(d2.min(axis=-1))
+    s0, s1, s2, s3 = np.sign(a0), np.sign(a1), np.sign(a2), np.sign(a3)
+    d01 = np.minimum(np.abs(a0), np.abs(a1))
+    d23 = np.minimum(np.abs(a2), np.abs(a3))
+    return np.where((s0 == s1) & (s2 == s3), dcorner,
+                    np.where(s0 == s1, d01, np.where(s2 == s3, d23, 0.)))
+
+
+def get_rx(planar, points):
+    """planar.py:533-545"""
+    lons, lats, _ = cartesian_to_spherical(points)
+    c = planar['corners']
+    return distances_to_arc(c[:, 0, 0, None], c[:, 1, 0, None],
+                            planar['sdr'][:, 0, None], lons, lats)
+
+
+def get_ry0(planar, points):
+    """planar.py:549-568"""
+    lons, lats, _ = cartesian_to_spherical(points)
+    c = planar['corners']
+    azi = (planar['sdr'][:, 0, None] + 90.) % 360.
+    d1 = distances_to_arc(c[:, 0, 0, None], c[:, 1, 0, None], azi, lons, lats)
+    d2 = distances_to_arc(c[:, 0, 1, None], c[:, 1, 1, None], azi, lons, lats)
+    return np.where(np.sign(d1) == np.sign(d2),
+                    np.fmin(np.abs(d1), np.abs(d2)), 0.)
+
+
+def get_repi(planar, points):
+    """planar.py:589-602"""
+    lons, lats, _ = cartesian_to_spherical(points)
+    h = planar['hypo']
+    return distances(np.radians(h[:, 0, None]), np.radians(h[:, 1, None]),
+                     np.radians(lons), np.radians(lats))
+
+
+def get_rhypo(planar, points):
+    """planar.py:572-586"""
+    _, _, deps = cartesian_to_spherical(points)
+    hdist = get_repi(planar, points)
+    vdist = planar['hypo'][:, 2, None] - deps
+    return np.sqrt(hdist ** 2 + vdist ** 2)
+
+
+def get_azimuth(planar, points):
+    """planar.py:605-621 with geodetic.fast_azimuth :117-130"""
+    lons, lats, _ = cartesian_to_spherical(points)
+    h = planar['hypo']
+    lon, lat = np.radians(h[:, 0, None]), np.radians(h[:, 1, None])
+    lons, lats = np.radians(lons), np.radians(lats)
+    cl = np.cos(lats)
+    tc = np.arctan2(np.sin(lon - lons) * cl,
+                    np.cos(lat) * np.sin(lats) -
+                    np.sin(lat) * cl * np.cos(lon - lons))
+    return (-np.degrees(tc) - planar['sdr'][:, 0, None]) % 360
+
+
+DIST = {'rjb': get_rjb, 'rx': get_rx, 'ry0': get_ry0, 'repi': get_repi,
+        'rhypo': get_rhypo, 'azimuth': get_azimuth,
+        'rrup': lambda p, x: project(p, x)[0]}
