@@ -1,0 +1,193 @@
+/*
+ * oqg.h -- C ABI of the B200-native classical-PSHA hot path.
+ *
+ * The reference (gem/oq-engine, openquake/hazardlib) has no FFI layer: its
+ * boundary for this path is a Python operator surface.
+ * Each entry point below names the reference operator it replaces
+ * (paths relative to the reference checkout):
+ *
+ *   oqg_distances      planar.project / get_rjb / get_rx / get_ry0 / get_repi /
+ *                      get_rhypo / get_azimuth
+ *                      (hazardlib/geo/surface/planar.py:324-403, 460-621),
+ *                      the distance part of ContextMaker.get_ctxs
+ *                      (hazardlib/contexts.py:374-440, 1051-1099)
+ *   oqg_mean_stds      ContextMaker.get_mean_stds / get_4MN -> GMPE.compute
+ *                      (hazardlib/contexts.py:1250-1303, gsim/base.py:389-401)
+ *   oqg_poes           _set_poes / set_poes / truncnorm_sf / ndtr
+ *                      (hazardlib/contexts.py:482-489, 1415-1475,
+ *                      hazardlib/stats.py:27-73)
+ *   oqg_update         MapArray.update_indep -> update_pmap_i / update_pmap_r
+ *                      with tom.get_pnes (hazardlib/map_array.py:238-260,
+ *                      443-455, hazardlib/tom.py:185-217)
+ *   oqg_hazard_planar  the whole chain ContextMaker.get_ctxs -> update for
+ *                      planar ruptures, fused, with no context rows
+ *                      materialised (hazardlib/contexts.py:1232-1247 driven by
+ *                      RmapMaker._make_src_indep :1548-1579)
+ *   oqg_hazard_planar_host  the same call taking HOST buffers (copies inside)
+ *
+ * Conventions: every function returns 0 on success, non-zero on error with a
+ * message available from oqg_last_error(); all `dev` pointers are device
+ * pointers on the handle's device (any allocator: cudaMalloc, a torch CUDA
+ * tensor's data_ptr()); all work is queued on the handle's stream and the
+ * functions do NOT synchronise unless stated; a handle is not thread-safe.
+ * There is no CPU fallback: without a CUDA device oqg_create fails.
+ */
+#ifndef OQG_H
+#define OQG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oqg_handle oqg_handle;
+
+/* GMPE families with a device implementation (reference module) */
+enum {
+  OQG_BSSA14 = 0,  /* gsim/boore_2014.py BooreEtAl2014 (+HighQ/LowQ tables) */
+  OQG_CY14 = 1,    /* gsim/chiou_youngs_2014.py ChiouYoungs2014 */
+  OQG_ASK14 = 2,   /* gsim/abrahamson_2014.py AbrahamsonEtAl2014 */
+  OQG_CB14 = 3,    /* gsim/campbell_bozorgnia_2014.py CampbellBozorgnia2014 */
+  OQG_BA08 = 4,    /* gsim/boore_atkinson_2008.py BooreAtkinson2008 */
+  OQG_AB06 = 5,    /* gsim/atkinson_boore_2006.py AtkinsonBoore2006 */
+  OQG_AKKAR14 = 6, /* gsim/akkar_2014.py AkkarEtAl{Rjb,Repi,Rhyp}2014 */
+  OQG_NFAMILIES = 7
+};
+
+/* distance metrics: bit positions for masks and order of output planes */
+enum {
+  OQG_RRUP = 0, OQG_RJB = 1, OQG_RX = 2, OQG_RY0 = 3, OQG_REPI = 4,
+  OQG_RHYPO = 5, OQG_AZIMUTH = 6, OQG_NDIST = 7
+};
+
+#define OQG_KMAX 56       /* doubles per coefficient row */
+#define OQG_PLANAR_LEN 42 /* doubles per planar rupture: the memory of one
+                             (3,) record array of planar_array_dt
+                             (planar.py:45-53), i.e. [k][14] with k = lon/lat/
+                             dep (or x/y/z) and 14 = corners[4] xyz[4] normal
+                             uv1 uv2 wlr sdr hypo; a reference planar array
+                             .view(float) uploads as it is */
+#define OQG_MAX_OCC 16    /* max length of probs_occur */
+
+/* per-model configuration; `flags` and `par` meaning per family:
+ *  BSSA14 : flags bit0-1 region (0 nobasin, 1 CAL, 2 JPN), bit4 sof;
+ *           par[0] sigma_mu_epsilon
+ *  CY14   : flags bit0-1 region (0 CAL, 1 JPN, 2 ITA, 3 WEN), bit4 use_hw,
+ *           bit5 peer; par[0] sigma_mu_epsilon, par[1] alpha_nm
+ *  ASK14  : flags bit0-1 region (0 none/CAL, 1 JPN, 2 TWN, 3 CHN);
+ *           par[0] sigma_mu_epsilon
+ *  CB14   : flags bit0 SJ; par[0] sigma_mu_epsilon
+ *  BA08   : -
+ *  AB06   : flags bit0-1 mag_eq (0 NA, 1 Mblg87, 2 Mblg96); par[0] scale_fac
+ *  AKKAR14: flags bit0-1 distance (0 rjb, 1 repi, 2 rhypo);
+ *           par[0] log(adjustment_factor)
+ */
+typedef struct {
+  int32_t family;
+  int32_t flags;
+  double par[4];
+} oqg_gsim;
+
+/* context rows as a struct of device arrays of length P (the columns of the
+ * reference's ctx recarray, contexts.py:660-678); pointers of columns that
+ * no configured model reads may be NULL */
+typedef struct {
+  const double *mag, *rake, *dip, *ztor, *width, *hypo_depth;
+  const double *rrup, *rjb, *rx, *ry0, *repi, *rhypo;
+  const double *vs30, *z1pt0, *z2pt5;
+  const uint8_t *vs30measured;
+} oqg_ctx;
+
+/* site collection as a struct of arrays of length N (site.py:249-324) */
+typedef struct {
+  const double *lon, *lat, *depth;       /* degrees, degrees, km */
+  const double *vs30, *z1pt0, *z2pt5;    /* may be NULL if unused */
+  const uint8_t *vs30measured;           /* may be NULL if unused */
+} oqg_sites;
+
+int oqg_create(oqg_handle **out, int device);
+void oqg_destroy(oqg_handle *h);
+/* message of the last error (h may be NULL for errors of oqg_create) */
+const char *oqg_last_error(oqg_handle *h);
+/* queue the work on an existing cudaStream_t (e.g. torch's current stream;
+ * NULL is the legacy default stream) / back on the handle's own stream */
+int oqg_set_stream(oqg_handle *h, void *cuda_stream);
+int oqg_use_own_stream(oqg_handle *h);
+int oqg_synchronize(oqg_handle *h);
+
+/* comma separated names of the coefficient row of a family, in the order the
+ * device expects them; names of the form table.column; NULL if unknown */
+const char *oqg_family_fields(int family);
+/* bit mask (1 << OQG_RRUP ...) of the distances / a string of context
+ * columns a configured model reads */
+int oqg_required_distances(const oqg_gsim *g);
+
+/* models: coeffs[G][M+1][OQG_KMAX] (host), row M = the PGA row of the model.
+ * An unknown family or flag is an error (there is no fallback). */
+int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
+                  const double *coeffs);
+/* levels: loglevels[M][L1] (host), as ContextMaker.loglevels
+ * (contexts.py:718-724); phi_b = ndtr(truncation_level) (contexts.py:628) */
+int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
+                   double truncation_level);
+
+/* distances of U planar ruptures x N sites: out[k][U][N] (dev) for the k-th
+ * set bit of `mask` in the order of the OQG_R* enum; planar is dev [U][42] */
+int oqg_distances(oqg_handle *h, const double *planar_dev, int U,
+                  const oqg_sites *sites_dev, int N, int mask,
+                  double *out_dev);
+
+/* out[4][G][M][P] (dev) = mean, sig, tau, phi */
+int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx_dev, int64_t P,
+                  double *out_dev);
+
+/* poes[P][L][G] float32 (dev) from mean_std[4][G][M][P] (dev), L = M*L1 */
+int oqg_poes(oqg_handle *h, const double *mean_std_dev, int64_t P,
+             float *poes_dev);
+
+/* fold rows into the map: map[N][L][G] float32 (dev), poes[P][L][G] float32
+ * (dev); the rows of site row s are order[seg[s] .. seg[s+1]) (dev; a stable
+ * grouping of the context rows by site row, seg has N+1 entries);
+ * rate[P]; probs_occur[P][K] or NULL with K = 0 (Poisson);
+ * rates_mode 0: map *= pne, 1: map += -log(pne) (update_pmap_i / _r) */
+int oqg_update(oqg_handle *h, float *map_dev, int N, const float *poes_dev,
+               int64_t P, const int64_t *order_dev, const int64_t *seg_dev,
+               const double *rate_dev, const double *probs_occur_dev, int K,
+               double itime, int rates_mode);
+
+/* the fused path.  planar dev [U][42] (wlr[2] is the occurrence rate),
+ * mag[U], magdist[U] (rows with rrup >= magdist are dropped,
+ * contexts.py:472), probs_occur [U][K] or NULL, sites dev arrays, sidx[N] the
+ * map row of each site (NULL: identity); map dev [Nmap][L][G] float32 is
+ * updated in place: rates_mode 0: *= prod pne, 1: += sum rates.
+ * counters (dev, may be NULL): [0] += number of rupture-site pairs kept */
+int oqg_hazard_planar(oqg_handle *h, const double *planar_dev,
+                      const double *mag_dev, const double *magdist_dev,
+                      const double *probs_occur_dev, int K, int U,
+                      const oqg_sites *sites_dev, const uint32_t *sidx_dev,
+                      int N, double minimum_distance, double itime,
+                      int rates_mode, float *map_dev,
+                      unsigned long long *counters_dev);
+
+/* same with HOST buffers: copies the ruptures and sites in, the map in and
+ * out, and synchronises; map is host [N][L][G] float32 (sidx = identity) */
+int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
+                           const double *mag, const double *magdist,
+                           const double *probs_occur, int K, int U,
+                           const oqg_sites *sites, int N,
+                           double minimum_distance, double itime,
+                           int rates_mode, float *map,
+                           unsigned long long *pairs_kept);
+
+/* number of kernels launched by this handle so far (for bench accounting) */
+unsigned long long oqg_launch_count(oqg_handle *h);
+/* average device milliseconds of the last fused kernel launches measured
+ * with CUDA events on the handle's stream: fills ms[G], returns G or <0 */
+int oqg_last_fused_ms(oqg_handle *h, float *ms, int cap);
+/* FP64 FMA microbenchmark: measured DFMA rate of the device in TFLOP/s
+ * (2 flop per FMA); synchronises */
+int oqg_measure_fp64_peak(oqg_handle *h, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OQG_H */

@@ -1,0 +1,20 @@
+"""oq-engine_b200: a B200-native (sm_100a) implementation of OpenQuake's
+classical-PSHA hot path behind the reference's operator surface
+(ContextMaker / GMPE.compute / MapArray).  The computation runs in
+hand-written CUDA kernels (csrc/) called through the C ABI of include/oqg.h;
+there is no CPU fallback."""
+from . import _lib, _build  # noqa
+from .imt import from_string  # noqa
+from .coeffs import CoeffsTable  # noqa
+from .gsim import (  # noqa
+    GMPE, BooreEtAl2014, ChiouYoungs2014, AbrahamsonEtAl2014,
+    CampbellBozorgnia2014, BooreAtkinson2008, AtkinsonBoore2006,
+    AkkarEtAlRjb2014, AkkarEtAlRepi2014, AkkarEtAlRhyp2014, get_gsim,
+    registry)
+from .tom import PoissonTOM, NegativeBinomialTOM  # noqa
+from .map_array import MapArray  # noqa
+from .planar import build_planar, planar_array_dt, wc1994_median_area  # noqa
+from .site import SiteCollection  # noqa
+from .contexts import ContextMaker, IntegrationDistance  # noqa
+
+__version__ = '0.1.0'

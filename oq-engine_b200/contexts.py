@@ -1,0 +1,603 @@
+"""ContextMaker: the reference's operator surface for the classical-PSHA hot
+path (openquake/hazardlib/contexts.py:507-1303) over the CUDA kernels.
+
+    get_ctxs        :1051-1099 (planar ruptures, :374-474)
+    get_mean_stds   :1250-1303
+    gen_poes        :1155-1203
+    update/get_pmap :1206-1247
+    hazard_planar   the fused equivalent of RmapMaker._make_src_indep
+                    (:1548-1579): ruptures x sites -> map with no context rows
+                    materialised
+
+The host side is Python as in the reference; PyTorch tensors are used only as
+device buffers.  There is no CPU fallback: an unsupported GMPE, a missing
+library or a missing CUDA device raises.
+"""
+import os
+import ctypes
+import numpy
+from scipy.special import ndtr
+
+from . import _lib
+from .imt import from_string
+from .gsim import GMPE, get_gsim
+from .map_array import MapArray
+from .tom import PoissonTOM
+from .planar import planar_array_dt, as_flat
+
+U32 = numpy.uint32
+F32 = numpy.float32
+MINMAG, MAXMAG = 2.5, 10.2   # calc/filters.py
+
+_handles = {}
+
+
+def default_device():
+    return int(os.environ.get('OQ_GPU_DEVICE',
+                              os.environ.get('LOCAL_RANK', 0)))
+
+
+def get_handle(device=None):
+    """One oqg handle per process and device, bound to torch's current
+    stream on that device so that torch copies and kernels are ordered"""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('no CUDA device: oq-engine_b200 has no CPU path')
+    device = default_device() if device is None else device
+    if device not in _handles:
+        _handles[device] = _lib.Handle(device)
+    h = _handles[device]
+    stream = torch.cuda.current_stream(device).cuda_stream
+    _lib.lib().oqg_set_stream(h._h, ctypes.c_void_p(stream))
+    return h
+
+
+def _device_index(device):
+    """None | int | 'cuda:1' -> None | int"""
+    if device is None or isinstance(device, int):
+        return device
+    s = str(device)
+    return int(s.split(':')[1]) if ':' in s else 0
+
+
+def _dev(arr, device, dtype=None):
+    """numpy array (or torch tensor) -> contiguous torch CUDA tensor"""
+    import torch
+    if isinstance(arr, torch.Tensor):
+        t = arr.to('cuda:%d' % device)
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.contiguous()
+    arr = numpy.array(arr, order='C')   # copy: fields of records are strided
+    if arr.dtype == bool:
+        arr = arr.view(numpy.uint8)
+    if arr.dtype == numpy.uint32:
+        arr = arr.view(numpy.int32)
+    t = torch.from_numpy(arr).to('cuda:%d' % device, non_blocking=False)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else None)
+
+
+class IntegrationDistance(dict):
+    """trt -> [(mag, dist), ...] (calc/filters.py:196-225); calling it with a
+    TRT gives a function mag -> maximum distance"""
+    @classmethod
+    def new(cls, value):
+        self = cls()
+        if value == 'magdist':
+            self['default'] = [(3, 0), (6, 150), (10, 600)]
+            return self
+        if isinstance(value, str):
+            value = eval(value, {}, {})   # '300' or '[(4., 50), (8., 200.)]'
+        if isinstance(value, dict):
+            items = value
+        else:
+            items = {'default': value}
+        for trt, val in items.items():
+            if isinstance(val, (list, tuple)):
+                self[trt] = sorted(set(tuple(it) for it in val))
+            else:
+                assert val >= 0, val
+                self[trt] = [(MINMAG, val), (MAXMAG, val)]
+        return self
+
+    def __call__(self, trt):
+        pairs = self.get(trt, self.get('default'))
+        return magdepdist(pairs)
+
+
+class magdepdist(object):
+    """Linear interpolation mag -> distance (calc/filters.py magdepdist)"""
+    def __init__(self, pairs):
+        self.mags = numpy.array([m for m, d in pairs], float)
+        self.dists = numpy.array([d for m, d in pairs], float)
+
+    def __call__(self, mag):
+        return numpy.interp(mag, self.mags, self.dists)
+
+
+def _interp(param, name, trt):
+    mdd = param.get(name)
+    if mdd is None:
+        return magdepdist([(MINMAG, 1000), (MAXMAG, 1000)])
+    if isinstance(mdd, IntegrationDistance):
+        return mdd(trt)
+    if isinstance(mdd, dict):
+        return IntegrationDistance.new(mdd)(trt)
+    if callable(mdd):
+        return mdd
+    return magdepdist([(MINMAG, float(mdd)), (MAXMAG, float(mdd))])
+
+
+class PlanarRuptures(object):
+    """
+    The rupture side of the path: U planar ruptures with their magnitudes
+    (what `src.get_planar()` feeds to genctxs_Pp, contexts.py:443-474).
+
+    :param planar: (U, 3) record array of planar_array_dt (wlr[:, 2] is the
+        occurrence rate)
+    :param mag: (U,) magnitudes
+    """
+    def __init__(self, planar, mag, src_id=0):
+        assert planar.dtype == planar_array_dt, planar.dtype
+        self.planar = planar
+        self.mag = numpy.asarray(mag, float)
+        self.src_id = src_id
+        assert len(self.mag) == len(planar)
+
+    def __len__(self):
+        return len(self.mag)
+
+    @property
+    def rate(self):
+        return self.planar['wlr'][:, 2]
+
+
+def _gsim_structs(gsims, imts):
+    """ctypes arrays (oqg_gsim[G], coeffs[G][M+1][KMAX]) for the models"""
+    G, M = len(gsims), len(imts)
+    arr = (_lib.OqgGsim * G)()
+    coeffs = numpy.zeros((G, M + 1, _lib.KMAX))
+    for g, gsim in enumerate(gsims):
+        fam, flags, par = gsim.device_spec()
+        arr[g].family, arr[g].flags = fam, flags
+        for k in range(4):
+            arr[g].par[k] = par[k]
+        for m, imt in enumerate(imts):
+            coeffs[g, m] = gsim.coeff_row(imt)   # KeyError if undefined
+        try:
+            coeffs[g, M] = gsim.pga_row()
+        except KeyError:
+            pass
+    return arr, coeffs
+
+
+CTX_COLUMNS = ('mag', 'rake', 'dip', 'ztor', 'width', 'hypo_depth', 'rrup',
+               'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'vs30', 'z1pt0', 'z2pt5',
+               'vs30measured')
+
+
+def _ctx_struct(ctx, device):
+    """OqgCtx of device pointers for a recarray-like ctx; returns the
+    struct and the tensors to keep alive"""
+    names = (ctx.dtype.names if hasattr(ctx, 'dtype') and ctx.dtype.names
+             else list(vars(ctx)))
+    st, keep = _lib.OqgCtx(), []
+    for col in CTX_COLUMNS:
+        if col in names:
+            a = ctx[col] if hasattr(ctx, 'dtype') else getattr(ctx, col)
+            if col == 'vs30measured':
+                t = _dev(numpy.asarray(a, bool), device)
+            else:
+                t = _dev(numpy.asarray(a, float), device)
+            keep.append(t)
+            setattr(st, col, t.data_ptr())
+    return st, keep
+
+
+def mean_stds_device(gsims, ctx, imts, device=None, handle=None,
+                     configure=True):
+    """(4, G, M, N) float64 numpy array computed on the GPU"""
+    import torch
+    h = handle or get_handle(device)
+    if configure:
+        arr, coeffs = _gsim_structs(gsims, imts)
+        h.call('oqg_set_gsims', len(gsims), arr, len(imts),
+               coeffs.ctypes.data_as(_lib.c_double_p))
+        h.owner = h.cfg = None
+    N = len(ctx)
+    out = torch.empty((4, len(gsims), len(imts), N), dtype=torch.float64,
+                      device='cuda:%d' % h.device)
+    if N:
+        st, keep = _ctx_struct(ctx, h.device)
+        h.call('oqg_mean_stds', ctypes.byref(st), N, _ptr(out))
+    return out.cpu().numpy()
+
+
+def _group_by_site(sidxs, N):
+    order = numpy.argsort(sidxs, kind='stable').astype(numpy.int64)
+    seg = numpy.searchsorted(sidxs[order], numpy.arange(N + 1)).astype(
+        numpy.int64)
+    return order, seg
+
+
+def update_device(pmap, poes, rates, probs_occur, sidxs, itime, handle=None):
+    """MapArray.update_indep on the GPU: poes (n, L, G) host or device"""
+    import torch
+    h = handle or get_handle(_device_index(pmap.device))
+    dev = h.device
+    n = len(sidxs)
+    if n == 0:
+        return
+    N, L, G = pmap.shape
+    # the kernel reads its shapes from the handle configuration
+    if getattr(h, 'cfg', None) != (L, G):
+        _configure_shapes(h, L, G)
+    tpoes = _dev(poes, dev, torch.float32)
+    order, seg = _group_by_site(numpy.asarray(sidxs, numpy.int64), N)
+    probs = numpy.asarray(probs_occur, float)
+    K = probs.shape[1] if probs.ndim == 2 else 0
+    t_order, t_seg = _dev(order, dev), _dev(seg, dev)
+    t_rate = _dev(numpy.asarray(rates, float), dev)
+    t_probs = _dev(probs, dev) if K else None
+    on_host = pmap.device is None
+    t_map = _dev(pmap.array, dev) if on_host else pmap.array
+    h.call('oqg_update', _ptr(t_map), N, _ptr(tpoes), n, _ptr(t_order),
+           _ptr(t_seg), _ptr(t_rate), _ptr(t_probs), K, float(itime),
+           int(pmap.rates))
+    if on_host:
+        pmap.array[:] = t_map.cpu().numpy()
+
+
+def _configure_shapes(h, L, G):
+    """Minimal configuration for oqg_update when no ContextMaker set the
+    handle up: G dummy models, one IMT with L levels"""
+    arr = (_lib.OqgGsim * G)()
+    for g in range(G):
+        arr[g].family = _lib.FAMILIES['BA08']
+    coeffs = numpy.zeros((G, 2, _lib.KMAX))
+    h.call('oqg_set_gsims', G, arr, 1, coeffs.ctypes.data_as(_lib.c_double_p))
+    lev = numpy.zeros(L)
+    h.call('oqg_set_levels', 1, L, lev.ctypes.data_as(_lib.c_double_p), 99.)
+    h.cfg = (L, G)
+    h.owner = None
+
+
+class ContextMaker(object):
+    """
+    :param trt: tectonic region type string
+    :param gsims: list of GMPE instances (or class names)
+    :param oq: dictionary with imtls, truncation_level, investigation_time,
+        maximum_distance, minimum_distance (same keys as the reference)
+    """
+    tom = None
+
+    def __init__(self, trt, gsims, oq, device=None):
+        param = dict(oq)
+        self.trt = trt
+        self.gsims = [get_gsim(g) for g in gsims]
+        for g in self.gsims:
+            if not isinstance(g, GMPE):
+                raise NotImplementedError('%r has no device implementation'
+                                          % g)
+        self.gid = numpy.arange(len(self.gsims), dtype=numpy.uint16)
+        if 'imtls' not in param:
+            raise KeyError('Missing imtls in ContextMaker!')
+        for imt in param['imtls']:
+            if not isinstance(imt, str):
+                raise TypeError('Expected string, got %s' % type(imt))
+        self.imtls = {imt: numpy.asarray(imls, float)
+                      for imt, imls in param['imtls'].items()}
+        self.maximum_distance = _interp(param, 'maximum_distance', trt)
+        self.minimum_distance = param.get('minimum_distance', 0)
+        self.investigation_time = param.get('investigation_time')
+        self.truncation_level = param.get('truncation_level', 99.)
+        self.phi_b = float(ndtr(self.truncation_level))
+        self.device = device
+        self.cfactor = numpy.zeros(2)
+        self.set_imts_conv()
+        for req in ('DISTANCES', 'SITES_PARAMETERS', 'RUPTURE_PARAMETERS'):
+            reqset = set()
+            for gsim in self.gsims:
+                reqset.update(getattr(gsim, 'REQUIRES_' + req))
+            setattr(self, 'REQUIRES_' + req, reqset)
+        # validate models and IMTs now: unsupported -> error at construction
+        self._structs = _gsim_structs(self.gsims, self.imts)
+
+    def set_imts_conv(self):
+        self.imts = tuple(from_string(im) for im in self.imtls)
+        lens = {len(v) for v in self.imtls.values()}
+        if len(lens) != 1:
+            raise ValueError('all IMTs must have the same number of levels')
+        self.L1 = lens.pop()
+        with numpy.errstate(divide='ignore'):
+            self.loglevels = {
+                imt: (numpy.log(imls) if imt != 'MMI' else imls)
+                for imt, imls in self.imtls.items()}
+
+    @property
+    def M(self):
+        return len(self.imts)
+
+    @property
+    def G(self):
+        return len(self.gsims)
+
+    @property
+    def L(self):
+        return self.M * self.L1
+
+    # ------------------------------------------------------------- device
+    def handle(self):
+        """The configured device handle (created lazily in the worker
+        process, like init_monitoring in the reference)"""
+        h = get_handle(_device_index(self.device))
+        if getattr(h, 'owner', None) is not self:
+            arr, coeffs = self._structs
+            h.call('oqg_set_gsims', self.G, arr, self.M,
+                   coeffs.ctypes.data_as(_lib.c_double_p))
+            lev = numpy.ascontiguousarray(
+                [self.loglevels[im] for im in self.imtls], float)
+            h.call('oqg_set_levels', self.M, self.L1,
+                   lev.ctypes.data_as(_lib.c_double_p),
+                   float(self.truncation_level))
+            h.owner = self
+            h.cfg = (self.L, self.G)
+        return h
+
+    def __getstate__(self):
+        # ctypes arrays do not pickle: rebuild them in the worker
+        dic = self.__dict__.copy()
+        dic.pop('_structs', None)
+        return dic
+
+    def __setstate__(self, dic):
+        self.__dict__.update(dic)
+        self._structs = _gsim_structs(self.gsims, self.imts)
+
+    # --------------------------------------------------------------- ctxs
+    def ctx_dtype(self, K=0):
+        """The dtype of the context rows (contexts.py:660-678)"""
+        dists = self.REQUIRES_DISTANCES | {'rrup'}
+        fields = []
+        for name in sorted(self.REQUIRES_RUPTURE_PARAMETERS):
+            fields.append((name, float))
+        for name in sorted(self.REQUIRES_SITES_PARAMETERS):
+            fields.append((name, bool if name == 'vs30measured' else float))
+        for name in sorted(dists):
+            fields.append((name, float))
+        fields += [('src_id', numpy.int32), ('rup_id', U32), ('sids', U32),
+                   ('occurrence_rate', float), ('probs_occur', float, (K,))]
+        return numpy.dtype(fields)
+
+    def new_ctx(self, size, K=0):
+        return numpy.zeros(size, self.ctx_dtype(K)).view(numpy.recarray)
+
+    def get_ctxs(self, src, sitecol, src_id=0, step=1):
+        """
+        Context rows of the ruptures of `src` (a PlanarRuptures) on the
+        sites, one recarray per unique magnitude like genctxs_Pp
+        (contexts.py:443-474): rows with rrup >= maximum_distance(mag) are
+        dropped, required distances are clamped by minimum_distance.
+        """
+        import torch
+        if not isinstance(src, PlanarRuptures):
+            raise NotImplementedError(
+                'only planar ruptures (PlanarRuptures) have a device path')
+        h = self.handle()
+        U, N = len(src), len(sitecol)
+        if U == 0 or N == 0:
+            return []
+        dists = sorted(self.REQUIRES_DISTANCES | {'rrup'})
+        mask = 0
+        for d in dists:
+            mask |= 1 << _lib.DIST.index(d)
+        order = [d for d in _lib.DIST if d in dists]
+        dev = h.device
+        t_pla = _dev(as_flat(src.planar), dev)
+        st, keep = self._sites_struct(sitecol, dev)
+        out = torch.empty((len(order), U, N), dtype=torch.float64,
+                          device='cuda:%d' % dev)
+        h.call('oqg_distances', _ptr(t_pla), U, ctypes.byref(st), N, mask,
+               _ptr(out))
+        dd = dict(zip(order, out.cpu().numpy()))
+        tom = self.tom
+        K = 0
+        probs = None
+        if tom is not None and hasattr(tom, 'get_pmf'):
+            probs = tom.get_pmf(src.rate)
+            K = probs.shape[1]
+        ctxs = []
+        mags = src.mag
+        for mag in numpy.unique(mags)[::step]:
+            idx = numpy.flatnonzero(mags == mag)
+            ctx = self.new_ctx(len(idx) * N, K).reshape(len(idx), N)
+            for name in dists:
+                arr = dd[name][idx]
+                if self.minimum_distance and name in self.REQUIRES_DISTANCES:
+                    arr = numpy.where(arr < self.minimum_distance,
+                                      self.minimum_distance, arr)
+                ctx[name] = arr
+            pla = src.planar[idx]
+            par = dict(mag=mags[idx], width=pla['wlr'][:, 0],
+                       dip=pla['sdr'][:, 1], rake=pla['sdr'][:, 2],
+                       strike=pla['sdr'][:, 0], ztor=pla['corners'][:, 2, 0],
+                       hypo_depth=pla['hypo'][:, 2])
+            for name in self.REQUIRES_RUPTURE_PARAMETERS:
+                ctx[name] = par[name][:, None]
+            for name in self.REQUIRES_SITES_PARAMETERS:
+                ctx[name] = sitecol.array[name][None, :]
+            ctx['occurrence_rate'] = pla['wlr'][:, 2][:, None]
+            ctx['rup_id'] = idx[:, None]
+            ctx['src_id'] = src_id
+            ctx['sids'] = sitecol.sids[None, :]
+            if K:
+                ctx['probs_occur'] = probs[idx][:, None, :]
+            ctx = ctx.flatten()
+            ctx = ctx[ctx['rrup'] < self.maximum_distance(mag)]
+            if len(ctx):
+                ctxs.append(ctx.view(numpy.recarray))
+        return ctxs
+
+    def _sites_struct(self, sitecol, dev):
+        st, keep = _lib.OqgSites(), []
+        arr = sitecol.array
+        for name in ('lon', 'lat', 'depth', 'vs30', 'z1pt0', 'z2pt5',
+                     'vs30measured'):
+            if name in arr.dtype.names:
+                a = arr[name]
+                t = _dev(numpy.asarray(a, bool if name == 'vs30measured'
+                                       else float), dev)
+                keep.append(t)
+                setattr(st, name, t.data_ptr())
+        return st, keep
+
+    def recarray(self, ctxs):
+        """Concatenate context arrays"""
+        if len(ctxs) == 1:
+            return ctxs[0]
+        return numpy.concatenate(ctxs).view(numpy.recarray)
+
+    # --------------------------------------------------------- mean, stds
+    def get_mean_stds(self, ctxs, split_by_mag=True):
+        """
+        :returns: (4, G, M, N) float64: mean, sig, tau, phi
+        (contexts.py:1250-1279); with split_by_mag the rows are reordered by
+        magnitude exactly as the reference does
+        """
+        ctx = self.recarray(list(ctxs))
+        if split_by_mag:
+            ctx = ctx[numpy.argsort(numpy.round(ctx.mag, 3), kind='stable')]
+        h = self.handle()
+        return mean_stds_device(self.gsims, ctx, self.imts, handle=h,
+                                configure=False)
+
+    # --------------------------------------------------------------- poes
+    def _device_poes(self, h, ctx):
+        """device tensors (poes (n, L, G) f32, mean_stds (4, G, M, n))"""
+        import torch
+        n = len(ctx)
+        dev = 'cuda:%d' % h.device
+        ms = torch.empty((4, self.G, self.M, n), dtype=torch.float64,
+                         device=dev)
+        st, keep = _ctx_struct(ctx, h.device)
+        h.call('oqg_mean_stds', ctypes.byref(st), n, _ptr(ms))
+        poes = torch.empty((n, self.L, self.G), dtype=torch.float32,
+                           device=dev)
+        h.call('oqg_poes', _ptr(ms), n, _ptr(poes))
+        return poes, ms
+
+    def gen_poes(self, ctx):
+        """
+        :yields: poes (n, L, G) float64, mea, sig, tau (G, M, n) and the
+            context rows, one block per unique magnitude rounded to 3 digits
+            in increasing order (contexts.py:1190-1203)
+        """
+        h = self.handle()
+        ctx.mag = numpy.round(ctx.mag, 3)
+        order = numpy.argsort(ctx.mag, kind='stable')
+        sctx = ctx[order]
+        if len(sctx) == 0:
+            return
+        poes, ms = self._device_poes(h, sctx)
+        poes = poes.cpu().numpy().astype(numpy.float64)
+        ms = ms.cpu().numpy()
+        mags, starts = numpy.unique(sctx.mag, return_index=True)
+        stops = list(starts[1:]) + [len(sctx)]
+        self.cfactor += [len(sctx), len(mags)]
+        for a, b in zip(starts, stops):
+            yield (poes[a:b], ms[0, :, :, a:b], ms[1, :, :, a:b],
+                   ms[2, :, :, a:b], sctx[a:b])
+
+    # ---------------------------------------------------------------- map
+    def update(self, pmap, ctx, rup_mutex=None):
+        """
+        Update the map in place (contexts.py:1232-1247): mean/stds, PoEs and
+        the fold into the map all stay on the device.
+        """
+        if rup_mutex:
+            raise NotImplementedError('mutex ruptures have no device path')
+        if len(ctx) == 0:
+            return
+        h = self.handle()
+        itime = self.tom.time_span if self.tom is not None else (
+            self.investigation_time)
+        poes, _ms = self._device_poes(h, ctx)
+        update_device(pmap, poes, ctx.occurrence_rate, ctx.probs_occur,
+                      pmap.sidx[ctx.sids], itime, handle=h)
+        self.cfactor += [len(ctx), len(numpy.unique(numpy.round(ctx.mag, 3)))]
+
+    def get_pmap(self, ctx, tom=None, rup_mutex={}):
+        """PoE map (contexts.py:1206-1218)"""
+        if rup_mutex:
+            raise NotImplementedError('mutex ruptures have no device path')
+        self.tom = tom or self.tom or PoissonTOM(self.investigation_time)
+        sids = numpy.unique(ctx.sids)
+        pmap = MapArray(sids, self.L, self.G).fill(1)
+        self.update(pmap, ctx)
+        return ~pmap
+
+    # -------------------------------------------------------------- fused
+    def magdist(self, mags):
+        """maximum distance for each magnitude"""
+        return numpy.array([float(self.maximum_distance(m)) for m in mags])
+
+    def hazard_planar(self, pmap, src, sitecol, count=False):
+        """
+        Fold all the ruptures of `src` (PlanarRuptures) on the sites into
+        `pmap` in one fused pass: the equivalent of
+        ``for ctx in get_ctxs(src, sitecol): update(pmap, ctx)`` without
+        materialising the context rows.  Returns the number of rupture-site
+        pairs kept by the distance filter if `count`.
+        """
+        import torch
+        h = self.handle()
+        dev = h.device
+        tom = self.tom or PoissonTOM(self.investigation_time)
+        self.tom = tom
+        U, N = len(src), len(sitecol)
+        if U == 0 or N == 0:
+            return 0
+        K, t_probs = 0, None
+        if hasattr(tom, 'get_pmf'):
+            probs = numpy.ascontiguousarray(tom.get_pmf(src.rate))
+            K = probs.shape[1]
+            t_probs = _dev(probs, dev)
+        t_pla = _dev(as_flat(src.planar), dev)
+        t_mag = _dev(src.mag, dev)
+        t_md = _dev(self.magdist(src.mag), dev)
+        st, keep = self._sites_struct(sitecol, dev)
+        t_sidx = _dev(pmap.sidx[sitecol.sids].astype(numpy.uint32), dev)
+        on_host = pmap.device is None
+        t_map = _dev(pmap.array, dev) if on_host else pmap.array
+        t_cnt = torch.zeros(2, dtype=torch.int64, device='cuda:%d' % dev) \
+            if count else None
+        h.call('oqg_hazard_planar', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
+               _ptr(t_probs), K, U, ctypes.byref(st), _ptr(t_sidx), N,
+               float(self.minimum_distance), float(tom.time_span),
+               int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
+        if on_host:
+            pmap.array[:] = t_map.cpu().numpy()
+        if count:
+            return int(t_cnt[0].item())
+
+    def get_pmap_planar(self, src, sitecol):
+        """PoE map of planar ruptures on the sites through the fused path"""
+        pmap = MapArray(sitecol.sids, self.L, self.G).fill(1)
+        self.hazard_planar(pmap, src, sitecol)
+        return ~pmap
+
+
+def get_mean_stds(gsim, ctx, imts, **kw):
+    """
+    Module-level helper of the reference (contexts.py:1723): (4, M, N) array
+    for a single model
+    """
+    imtls = {from_string(i).string: [0] for i in imts}
+    cm = ContextMaker('*', [gsim], dict(imtls=imtls, **kw))
+    return cm.get_mean_stds([ctx], split_by_mag=False)[:, 0]

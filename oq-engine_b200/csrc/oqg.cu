@@ -1,0 +1,924 @@
+// liboqg: kernels and C ABI of the B200-native classical-PSHA hot path.
+// See include/oqg.h for the boundary and DESIGN.md for the layout.
+//
+// Kernels (all FP64 arithmetic for distances / GMPE / PoE like the
+// reference; float32 only where the reference stores float32):
+//   k_prep_ruptures  planar records -> prepared rupture SoA [NF_RUP][U]
+//   k_prep_sites     lon/lat/depth -> site SoA [NF_SITE][N]
+//   k_distances      (U, N) distance planes (unfused API, get_ctxs)
+//   k_mean_stds<F>   context rows -> (4, G, M, P) (unfused API)
+//   k_poes           (4, G, M, P) -> (P, L, G) float32 (unfused API)
+//   k_update         fold (P, L, G) PoEs into the map, one thread per map
+//                    element looping over the rows of its site (no atomics)
+//   k_fused<F,NB>    ruptures x sites -> partial sums of rate*poe*T per
+//                    (site, level) with distances, GMPE and PoEs in
+//                    registers / shared memory, nothing materialised
+//   k_finalize       partial sums -> float32 pne / rate map
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/oqg.h"
+#include "oqg_gmpe.cuh"
+#include "oqg_geo.cuh"
+#include "oqg_poe.cuh"
+
+using namespace oqg;
+
+#define OQG_MAX_SLOTS 112
+#define OQG_MAX_G 16
+#define OQG_MAX_LEVELS 1024
+#define NL 20          // level accumulators per thread in the fused kernel
+#define RT 32          // ruptures per shared-memory tile
+#define NWMAX 8        // warps (units) per CTA in the fused kernel
+#define MAXPLANES 6
+
+__constant__ double c_coef[OQG_MAX_SLOTS][OQG_KMAX];
+__constant__ double c_loglev[OQG_MAX_LEVELS];
+__constant__ oqg_gsim c_gsim[OQG_MAX_G];
+
+// ------------------------------------------------------------------ handle
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct oqg_handle {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  int G = 0, M = 0, L1 = 0;
+  std::vector<oqg_gsim> gsims;
+  std::vector<double> coef, loglev;
+  double truncation_level = 0, phi_b = 0;
+  bool const_dirty = true;
+  unsigned long long launches = 0;
+  Buf rup, site, part, stage[12];
+  int *flag_dev = nullptr;
+  cudaEvent_t ev[2 * OQG_MAX_G + 2];
+  int n_fused_ev = 0;
+  int sm_count = 148;
+};
+
+static std::string g_create_err;
+static oqg_handle *g_const_owner = nullptr;
+
+static int fail(oqg_handle *h, const std::string &msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return 1;
+}
+
+#define CK(call)                                                          \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess)                                                \
+      return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+static int reserve(oqg_handle *h, Buf &b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+
+static int upload_const(oqg_handle *h) {
+  if (!h->const_dirty && g_const_owner == h) return 0;
+  if (h->G && !h->coef.empty()) {
+    CK(cudaMemcpyToSymbolAsync(c_coef, h->coef.data(),
+                               h->coef.size() * sizeof(double), 0,
+                               cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyToSymbolAsync(c_gsim, h->gsims.data(),
+                               h->gsims.size() * sizeof(oqg_gsim), 0,
+                               cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!h->loglev.empty())
+    CK(cudaMemcpyToSymbolAsync(c_loglev, h->loglev.data(),
+                               h->loglev.size() * sizeof(double), 0,
+                               cudaMemcpyHostToDevice, h->stream));
+  // the host vectors must stay alive until the copies ran: they are members
+  // and only replaced by set_* calls, which synchronise first
+  h->const_dirty = false;
+  g_const_owner = h;
+  return 0;
+}
+
+// ----------------------------------------------------------- prep kernels
+__global__ void k_prep_ruptures(const double *__restrict__ planar,
+                                const double *__restrict__ mag,
+                                const double *__restrict__ magdist, int64_t U,
+                                double *__restrict__ out) {
+  int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  double pl[OQG_PLANAR_LEN];
+  for (int k = 0; k < OQG_PLANAR_LEN; k++) pl[k] = planar[u * OQG_PLANAR_LEN + k];
+  prep_rupture(pl, mag[u], magdist ? magdist[u] : INFINITY, out + u, U);
+}
+
+__global__ void k_prep_sites(const double *__restrict__ lon,
+                             const double *__restrict__ lat,
+                             const double *__restrict__ dep, int N,
+                             double *__restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  prep_site(lon[n], lat[n], dep ? dep[n] : 0., out + n, N);
+}
+
+// -------------------------------------------------------------- distances
+// out[k][U][N]; one thread per site, blockIdx.y strides over the ruptures
+__global__ void k_distances(const double *__restrict__ rup, int U,
+                            const double *__restrict__ site, int N, int mask,
+                            double *__restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double sx[3], sq[3], sdep;
+  for (int k = 0; k < 3; k++) {
+    sx[k] = site[(int64_t)(SF_XYZ + k) * N + n];
+    sq[k] = site[(int64_t)(SF_Q + k) * N + n];
+  }
+  sdep = site[(int64_t)SF_DEPTH * N + n];
+  for (int u = blockIdx.y; u < U; u += gridDim.y) {
+    Dist d;
+    pair_distances(rup + u, U, sx, sq, sdep, mask, d);
+    const double vals[OQG_NDIST] = {d.rrup, d.rjb, d.rx, d.ry0, d.repi,
+                                    d.rhypo, d.azimuth};
+    int plane = 0;
+#pragma unroll
+    for (int k = 0; k < OQG_NDIST; k++)
+      if (mask & (1 << k)) {
+        out[((int64_t)plane * U + u) * N + n] = vals[k];
+        plane++;
+      }
+  }
+}
+
+// -------------------------------------------------------------- mean_stds
+struct CtxDev {
+  oqg_ctx c;
+};
+
+__device__ __forceinline__ double ld(const double *p, int64_t i) {
+  return p ? p[i] : 0.;
+}
+
+template <int F>
+__global__ void __launch_bounds__(128)
+k_mean_stds(int g, int G, int M, CtxDev cd, int64_t P,
+            double *__restrict__ out, int *__restrict__ flag) {
+  typedef typename Fam<F>::C CT;
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const oqg_ctx &c = cd.c;
+  Row r;
+  r.mag = ld(c.mag, p); r.rake = ld(c.rake, p); r.dip = ld(c.dip, p);
+  r.ztor = ld(c.ztor, p); r.width = ld(c.width, p);
+  r.hypo_depth = ld(c.hypo_depth, p);
+  r.rrup = ld(c.rrup, p); r.rjb = ld(c.rjb, p); r.rx = ld(c.rx, p);
+  r.ry0 = ld(c.ry0, p); r.repi = ld(c.repi, p); r.rhypo = ld(c.rhypo, p);
+  r.vs30 = ld(c.vs30, p); r.z1pt0 = ld(c.z1pt0, p); r.z2pt5 = ld(c.z2pt5, p);
+  r.vs30measured = c.vs30measured ? c.vs30measured[p] != 0 : false;
+  const oqg_gsim &gs = c_gsim[g];
+  const CT &Cp = *reinterpret_cast<const CT *>(c_coef[g * (M + 1) + M]);
+  typename Fam<F>::R st = Fam<F>::row(gs, Cp, r);
+  const int64_t plane = (int64_t)G * M * P;
+  for (int m = 0; m < M; m++) {
+    const CT &C = *reinterpret_cast<const CT *>(c_coef[g * (M + 1) + m]);
+    Out o = Fam<F>::imt(gs, C, Cp, r, st);
+    int64_t idx = ((int64_t)g * M + m) * P + p;
+    out[idx] = o.mean;
+    out[plane + idx] = o.sig;
+    out[2 * plane + idx] = o.tau;
+    out[3 * plane + idx] = o.phi;
+    if (o.sig == 0.) *flag = 1;  // benign race: every writer stores 1
+  }
+}
+
+// ------------------------------------------------------------------- poes
+// one thread per output element poes[p][l][g] (coalesced float32 stores)
+__global__ void k_poes(const double *__restrict__ ms, int64_t P, int G, int M,
+                       int L1, double phi_b, double inv_norm,
+                       float *__restrict__ out) {
+  const int64_t LG = (int64_t)M * L1 * G;
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= P * LG) return;
+  int64_t p = e / LG;
+  int rem = (int)(e - p * LG);
+  int l = rem / G, g = rem - l * G;
+  int m = l / L1;
+  int64_t idx = ((int64_t)g * M + m) * P + p;
+  double mean = ms[idx], sig = ms[(int64_t)G * M * P + idx];
+  double z = (c_loglev[l] - mean) / sig;
+  out[e] = (float)truncnorm_sf(phi_b, inv_norm, z);
+}
+
+// ----------------------------------------------------------------- update
+// one thread per map element (s, l, g); loops over the rows of site row s
+__global__ void k_update(float *__restrict__ map, int N, int LG, int G,
+                         const float *__restrict__ poes,
+                         const int64_t *__restrict__ order,
+                         const int64_t *__restrict__ seg,
+                         const double *__restrict__ rate,
+                         const double *__restrict__ probs, int K, double itime,
+                         int rates_mode) {
+  int s = blockIdx.y;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= LG) return;
+  int64_t a = seg[s], b = seg[s + 1];
+  if (a == b) return;
+  double sum = 0., prod = 1.;
+  for (int64_t i = a; i < b; i++) {
+    int64_t row = order[i];
+    double poe = (double)poes[row * LG + e];
+    if (K == 0) {
+      sum += rate[row] * poe * itime;
+    } else {
+      double pne = itime == 0. ? 1. - poe
+                               : pne_from_pmf(probs + row * K, K, poe);
+      if (rates_mode) sum += -log(pne); else prod *= pne;
+    }
+  }
+  int64_t at = (int64_t)s * LG + e;
+  if (rates_mode) map[at] = (float)((double)map[at] + sum);
+  else map[at] = (float)((double)map[at] * (exp(-sum) * prod));
+}
+
+// ------------------------------------------------------------------ fused
+struct FusedArgs {
+  const double *rup;      // [NF_RUP][U]
+  const double *probs;    // [U][K] or null
+  const double *site;     // [NF_SITE][N]
+  const double *vs30, *z1pt0, *z2pt5;
+  const uint8_t *vs30measured;
+  double *part;           // [RC][G][N][L]
+  unsigned long long *counters;
+  int64_t U;
+  int N, K;
+  int g, G, M, L1;
+  int nlc;                // level chunks per IMT
+  int lpc;                // levels per chunk (<= NL)
+  int nunits;             // M * nlc
+  int rup_per_chunk;
+  int dmask;              // distances to compute
+  int clampmask;          // distances clamped by minimum_distance
+  int nplanes;
+  int plane_of[OQG_NDIST];
+  int count_pairs;
+  double mindist, itime, phi_b, inv_norm;
+};
+
+template <int F, bool NEGBIN>
+__global__ void __launch_bounds__(32 * NWMAX, 2)
+k_fused(const FusedArgs A) {
+  typedef typename Fam<F>::C CT;
+  extern __shared__ double smem[];
+  double *s_rup = smem;                       // [NF_RUP][RT]
+  double *s_dist = s_rup + NF_RUP * RT;       // [nplanes][RT][32]
+  double *s_site = s_dist + A.nplanes * RT * 32;  // [NF_SITE][32]
+  double *s_probs = s_site + NF_SITE * 32;    // [RT][K]
+  unsigned *s_valid = (unsigned *)(s_probs + (NEGBIN ? RT * A.K : 0));
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int site0 = blockIdx.x * 32;
+  const int n = site0 + lane;
+  const bool site_ok = n < A.N;
+  const int unit = blockIdx.z * nw + warp;     // (m, level chunk)
+  const bool unit_ok = unit < A.nunits;
+  const int m = unit_ok ? unit / A.nlc : 0;
+  const int lc = unit_ok ? unit - m * A.nlc : 0;
+  const int l0 = lc * A.lpc;
+  const int nl = min(A.lpc, A.L1 - l0);
+
+  // site tile to shared memory (geometry) and registers (site parameters)
+  for (int i = threadIdx.x; i < NF_SITE * 32; i += blockDim.x) {
+    int f = i >> 5, j = i & 31;
+    s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
+  }
+  Row row;
+  row.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
+  row.z1pt0 = site_ok && A.z1pt0 ? A.z1pt0[n] : -999.;
+  row.z2pt5 = site_ok && A.z2pt5 ? A.z2pt5[n] : -999.;
+  row.vs30measured = site_ok && A.vs30measured ? A.vs30measured[n] != 0 : false;
+
+  const oqg_gsim &gs = c_gsim[A.g];
+  const CT &C = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + m]);
+  const CT &Cp = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + A.M]);
+  const double *ll = c_loglev + m * A.L1 + l0;
+
+  double acc[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) acc[l] = NEGBIN ? 1. : 0.;
+  unsigned long long kept = 0;
+
+  const int64_t r_begin = (int64_t)blockIdx.y * A.rup_per_chunk;
+  const int64_t r_end = min(A.U, r_begin + A.rup_per_chunk);
+
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += RT) {
+    const int nr = (int)min((int64_t)RT, r_end - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NF_RUP * RT; i += blockDim.x) {
+      int f = i / RT, j = i - f * RT;
+      s_rup[i] = j < nr ? A.rup[(int64_t)f * A.U + r0 + j] : 0.;
+    }
+    if (NEGBIN)
+      for (int i = threadIdx.x; i < nr * A.K; i += blockDim.x)
+        s_probs[i] = A.probs[r0 * A.K + i];
+    __syncthreads();
+    // ---- distances: rupture i of the tile by warp i % nw, lane = site
+    for (int i = warp; i < nr; i += nw) {
+      double sx[3], sq[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        sx[k] = s_site[(SF_XYZ + k) * 32 + lane];
+        sq[k] = s_site[(SF_Q + k) * 32 + lane];
+      }
+      Dist d;
+      pair_distances(s_rup + i, RT, sx, sq, s_site[SF_DEPTH * 32 + lane],
+                     A.dmask, d);
+      double vals[OQG_NDIST] = {d.rrup, d.rjb, d.rx, d.ry0, d.repi, d.rhypo,
+                                0.};
+      // minimum_distance clamp of the required distances, contexts.py:391
+      if (A.mindist != 0.) {
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          if ((A.clampmask >> k) & 1)
+            if (vals[k] < A.mindist) vals[k] = A.mindist;
+      }
+      bool ok = site_ok && vals[0] < s_rup[RF_MAGDIST * RT + i];
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        if ((A.dmask >> k) & 1)
+          s_dist[(A.plane_of[k] * RT + i) * 32 + lane] = vals[k];
+      unsigned b = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_valid[i] = b;
+      if (A.count_pairs && lane == 0 && blockIdx.z == 0) kept += __popc(b);
+    }
+    __syncthreads();
+    // ---- GMPE + PoEs + accumulation: this warp's (IMT, level chunk)
+    if (!unit_ok) continue;
+    for (int i = 0; i < nr; i++) {
+      unsigned vm = s_valid[i];
+      if (!((vm >> lane) & 1)) continue;
+      row.mag = s_rup[RF_MAG * RT + i];
+      row.rake = s_rup[RF_RAKE * RT + i];
+      row.dip = s_rup[RF_DIP * RT + i];
+      row.ztor = s_rup[RF_ZTOR * RT + i];
+      row.width = s_rup[RF_WIDTH * RT + i];
+      row.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];
+#define DGET(k) (((A.dmask >> (k)) & 1) ? s_dist[(A.plane_of[k] * RT + i) * 32 + lane] : 0.)
+      row.rrup = DGET(OQG_RRUP);
+      row.rjb = DGET(OQG_RJB);
+      row.rx = DGET(OQG_RX);
+      row.ry0 = DGET(OQG_RY0);
+      row.repi = DGET(OQG_REPI);
+      row.rhypo = DGET(OQG_RHYPO);
+#undef DGET
+      typename Fam<F>::R st = Fam<F>::row(gs, Cp, row);
+      Out o = Fam<F>::imt(gs, C, Cp, row, st);
+      const double inv = 1. / o.sig;
+      if (NEGBIN) {
+        const double *pr = s_probs + i * A.K;
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+          if (l < nl) {
+            double poe = truncnorm_sf(A.phi_b, A.inv_norm,
+                                      (ll[l] - o.mean) * inv);
+            acc[l] *= A.itime == 0. ? 1. - poe : pne_from_pmf(pr, A.K, poe);
+          }
+      } else {
+        const double rt = s_rup[RF_RATE * RT + i] * A.itime;
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+          if (l < nl) {
+            double poe = truncnorm_sf(A.phi_b, A.inv_norm,
+                                      (ll[l] - o.mean) * inv);
+            acc[l] = fma(rt, poe, acc[l]);
+          }
+      }
+    }
+  }
+  if (A.count_pairs && lane == 0 && kept)
+    atomicAdd(A.counters, kept);  // statistics only, not the map
+  if (!unit_ok || !site_ok) return;
+  const int L = A.M * A.L1;
+  double *dst = A.part + (((int64_t)blockIdx.y * A.G + A.g) * A.N + n) * L +
+                m * A.L1 + l0;
+#pragma unroll
+  for (int l = 0; l < NL; l++)
+    if (l < nl) dst[l] = NEGBIN ? -log(acc[l]) : acc[l];
+}
+
+// partial sums -> map[sidx[n]][l][g]
+__global__ void k_finalize(const double *__restrict__ part, int RC, int G,
+                           int N, int L, const uint32_t *__restrict__ sidx,
+                           int rates_mode, float *__restrict__ map) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)N * L * G;
+  if (e >= tot) return;
+  int n = (int)(e / ((int64_t)L * G));
+  int rem = (int)(e - (int64_t)n * L * G);
+  int l = rem / G, g = rem - l * G;
+  double s = 0.;
+  for (int rc = 0; rc < RC; rc++)
+    s += part[(((int64_t)rc * G + g) * N + n) * L + l];
+  int64_t at = ((int64_t)(sidx ? sidx[n] : n) * L + l) * G + g;
+  if (rates_mode) map[at] = (float)((double)map[at] + s);
+  else map[at] = (float)((double)map[at] * exp(-s));
+}
+
+// FP64 FMA microbenchmark (8 independent chains per thread)
+__global__ void k_dfma(double *out, int iters) {
+  double a[8];
+  double x = 1.0000001 + threadIdx.x * 1e-9, y = 1e-9;
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = k * 0.1 + threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = fma(a[k], x, y);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 12345.678) out[0] = s;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int oqg_create(oqg_handle **out, int device) {
+  oqg_handle *h = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, std::string("no CUDA device: ") +
+                             cudaGetErrorString(e) +
+                             " (liboqg has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, "bad device index");
+  h = new oqg_handle();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) !=
+          cudaSuccess) {
+    delete h;
+    return fail(nullptr, "cannot initialise the device");
+  }
+  h->stream = h->own_stream;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  for (auto &ev : h->ev) cudaEventCreate(&ev);
+  cudaMalloc((void **)&h->flag_dev, sizeof(int));
+  cudaMemset(h->flag_dev, 0, sizeof(int));
+  *out = h;
+  return 0;
+}
+
+void oqg_destroy(oqg_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (Buf *b : {&h->rup, &h->site, &h->part}) if (b->p) cudaFree(b->p);
+  for (auto &b : h->stage) if (b.p) cudaFree(b.p);
+  if (h->flag_dev) cudaFree(h->flag_dev);
+  for (auto &ev : h->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(h->own_stream);
+  if (g_const_owner == h) g_const_owner = nullptr;
+  delete h;
+}
+
+const char *oqg_last_error(oqg_handle *h) {
+  return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+int oqg_set_stream(oqg_handle *h, void *s) {
+  h->stream = (cudaStream_t)s;  // NULL is the legacy default stream
+  return 0;
+}
+
+int oqg_use_own_stream(oqg_handle *h) {
+  h->stream = h->own_stream;
+  return 0;
+}
+
+int oqg_synchronize(oqg_handle *h) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+const char *oqg_family_fields(int family) {
+  switch (family) {
+    case OQG_BSSA14: return Fam<OQG_BSSA14>::fields();
+    case OQG_CY14: return Fam<OQG_CY14>::fields();
+    case OQG_ASK14: return Fam<OQG_ASK14>::fields();
+    case OQG_CB14: return Fam<OQG_CB14>::fields();
+    case OQG_BA08: return Fam<OQG_BA08>::fields();
+    case OQG_AB06: return Fam<OQG_AB06>::fields();
+    case OQG_AKKAR14: return Fam<OQG_AKKAR14>::fields();
+  }
+  return nullptr;
+}
+
+int oqg_required_distances(const oqg_gsim *g) { return required_distances(*g); }
+
+int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
+                  const double *coeffs) {
+  if (G < 1 || G > OQG_MAX_G) return fail(h, "G must be in 1..16");
+  if (M < 1 || G * (M + 1) > OQG_MAX_SLOTS)
+    return fail(h, "too many (gsim, IMT) pairs for the coefficient table "
+                   "(G * (M + 1) <= 112)");
+  for (int g = 0; g < G; g++) {
+    const oqg_gsim &s = gsims[g];
+    if (s.family < 0 || s.family >= OQG_NFAMILIES)
+      return fail(h, "unsupported GMPE family " + std::to_string(s.family) +
+                         " (no fallback)");
+    int reg = s.flags & 3;
+    bool bad = false;
+    if (s.family == OQG_BSSA14 && reg > 2) bad = true;
+    if (s.family == OQG_AB06 && reg > 2) bad = true;
+    if (s.family == OQG_AKKAR14 && reg > 2) bad = true;
+    if (bad) return fail(h, "unsupported flags for GMPE family");
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->G = G; h->M = M;
+  h->gsims.assign(gsims, gsims + G);
+  h->coef.assign(coeffs, coeffs + (size_t)G * (M + 1) * OQG_KMAX);
+  h->const_dirty = true;
+  return 0;
+}
+
+int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
+                   double truncation_level) {
+  if (M < 1 || L1 < 1 || M * L1 > OQG_MAX_LEVELS)
+    return fail(h, "M * L1 must be in 1..1024");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->M && h->M != M) return fail(h, "set_levels: M differs from set_gsims");
+  h->M = M; h->L1 = L1;
+  h->loglev.assign(loglevels, loglevels + (size_t)M * L1);
+  h->truncation_level = truncation_level;
+  h->phi_b = 0.5 * (1.0 + erf(truncation_level * sqrt(0.5)));
+  h->const_dirty = true;
+  return 0;
+}
+
+static int prep_sites(oqg_handle *h, const oqg_sites *s, int N) {
+  if (!s->lon || !s->lat) return fail(h, "sites need lon and lat");
+  if (reserve(h, h->site, (size_t)NF_SITE * N * 8)) return 1;
+  k_prep_sites<<<(N + 127) / 128, 128, 0, h->stream>>>(
+      s->lon, s->lat, s->depth, N, (double *)h->site.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int prep_ruptures(oqg_handle *h, const double *planar,
+                         const double *mag, const double *magdist, int64_t U) {
+  if (reserve(h, h->rup, (size_t)NF_RUP * U * 8)) return 1;
+  k_prep_ruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
+      planar, mag, magdist, U, (double *)h->rup.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_distances(oqg_handle *h, const double *planar, int U,
+                  const oqg_sites *sites, int N, int mask, double *out) {
+  CK(cudaSetDevice(h->device));
+  if (U <= 0 || N <= 0) return 0;
+  if (mask <= 0 || mask >= (1 << OQG_NDIST)) return fail(h, "bad distance mask");
+  // mag is not used by the distances: pass the planar pointer as a dummy
+  if (reserve(h, h->stage[11], (size_t)U * 8)) return 1;
+  CK(cudaMemsetAsync(h->stage[11].p, 0, (size_t)U * 8, h->stream));
+  if (prep_ruptures(h, planar, (const double *)h->stage[11].p, nullptr, U))
+    return 1;
+  if (prep_sites(h, sites, N)) return 1;
+  dim3 grid((N + 127) / 128, std::min(U, 4096));
+  k_distances<<<grid, 128, 0, h->stream>>>((const double *)h->rup.p, U,
+                                           (const double *)h->site.p, N, mask,
+                                           out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+template <int F>
+static void launch_mean_stds(oqg_handle *h, int g, const oqg_ctx *ctx,
+                             int64_t P, double *out) {
+  CtxDev cd;
+  cd.c = *ctx;
+  k_mean_stds<F><<<(unsigned)((P + 127) / 128), 128, 0, h->stream>>>(
+      g, h->G, h->M, cd, P, out, h->flag_dev);
+}
+
+extern "C" {
+
+static const char *missing_column(const oqg_gsim &g, const oqg_ctx *c) {
+  int d = required_distances(g);
+  if ((d >> OQG_RRUP & 1) && !c->rrup) return "rrup";
+  if ((d >> OQG_RJB & 1) && !c->rjb) return "rjb";
+  if ((d >> OQG_RX & 1) && !c->rx) return "rx";
+  if ((d >> OQG_RY0 & 1) && !c->ry0) return "ry0";
+  if ((d >> OQG_REPI & 1) && !c->repi) return "repi";
+  if ((d >> OQG_RHYPO & 1) && !c->rhypo) return "rhypo";
+  if (!c->mag) return "mag";
+  if (!c->vs30) return "vs30";
+  int f = g.family;
+  if (f != OQG_AB06 && !c->rake) return "rake";
+  if (f == OQG_CY14 || f == OQG_ASK14 || f == OQG_CB14) {
+    if (!c->dip) return "dip";
+    if (!c->ztor) return "ztor";
+  }
+  if ((f == OQG_ASK14 || f == OQG_CB14) && !c->width) return "width";
+  if (f == OQG_CB14 && !c->hypo_depth) return "hypo_depth";
+  if (f == OQG_CB14 && !c->z2pt5) return "z2pt5";
+  if ((f == OQG_CY14 || f == OQG_ASK14) && (!c->z1pt0 || !c->vs30measured))
+    return "z1pt0/vs30measured";
+  if (f == OQG_BSSA14 && (g.flags & 3) && !c->z1pt0) return "z1pt0";
+  if (g.par[0] != 0. && f <= OQG_CB14 && !c->rrup) return "rrup";
+  return nullptr;
+}
+
+int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx, int64_t P, double *out) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G) return fail(h, "oqg_set_gsims not called");
+  if (P <= 0) return 0;
+  for (int g = 0; g < h->G; g++)
+    if (const char *m = missing_column(h->gsims[g], ctx))
+      return fail(h, std::string("context column missing: ") + m);
+  if (upload_const(h)) return 1;
+  CK(cudaMemsetAsync(h->flag_dev, 0, sizeof(int), h->stream));
+  for (int g = 0; g < h->G; g++) {
+    switch (h->gsims[g].family) {
+      case OQG_BSSA14: launch_mean_stds<OQG_BSSA14>(h, g, ctx, P, out); break;
+      case OQG_CY14: launch_mean_stds<OQG_CY14>(h, g, ctx, P, out); break;
+      case OQG_ASK14: launch_mean_stds<OQG_ASK14>(h, g, ctx, P, out); break;
+      case OQG_CB14: launch_mean_stds<OQG_CB14>(h, g, ctx, P, out); break;
+      case OQG_BA08: launch_mean_stds<OQG_BA08>(h, g, ctx, P, out); break;
+      case OQG_AB06: launch_mean_stds<OQG_AB06>(h, g, ctx, P, out); break;
+      case OQG_AKKAR14: launch_mean_stds<OQG_AKKAR14>(h, g, ctx, P, out); break;
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  // zero total stddev with a real truncation is an error in the reference
+  // (contexts.py:1297)
+  double tl = h->truncation_level;
+  if (h->L1 && !(tl == 0. || tl == 1e-9 || tl == 99.)) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->flag_dev, sizeof(int), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) return fail(h, "Total StdDev is zero");
+  }
+  return 0;
+}
+
+int oqg_poes(oqg_handle *h, const double *ms, int64_t P, float *poes) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
+  if (P <= 0) return 0;
+  if (upload_const(h)) return 1;
+  int64_t tot = P * h->M * h->L1 * h->G;
+  double inv_norm = 1. / (h->phi_b * 2. - 1.);
+  k_poes<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+      ms, P, h->G, h->M, h->L1, h->phi_b, inv_norm, poes);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_update(oqg_handle *h, float *map, int N, const float *poes, int64_t P,
+               const int64_t *order, const int64_t *seg, const double *rate,
+               const double *probs, int K, double itime, int rates_mode) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
+  if (P <= 0 || N <= 0) return 0;
+  if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
+  int LG = h->M * h->L1 * h->G;
+  dim3 grid((LG + 127) / 128, N);
+  k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
+                                        rate, K ? probs : nullptr, K, itime,
+                                        rates_mode);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+template <int F>
+static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
+                                size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (A.K) {
+    e = cudaFuncSetAttribute(k_fused<F, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+    if (e != cudaSuccess) return e;
+    k_fused<F, true><<<grid, threads, smem, st>>>(A);
+  } else {
+    e = cudaFuncSetAttribute(k_fused<F, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+    if (e != cudaSuccess) return e;
+    k_fused<F, false><<<grid, threads, smem, st>>>(A);
+  }
+  return cudaGetLastError();
+}
+
+extern "C" {
+
+int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
+                      const double *magdist, const double *probs, int K,
+                      int U, const oqg_sites *sites, const uint32_t *sidx,
+                      int N, double mindist, double itime, int rates_mode,
+                      float *map, unsigned long long *counters) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
+  if (U <= 0 || N <= 0) return 0;
+  if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
+  if (K && !probs) return fail(h, "probs_occur missing");
+  const int G = h->G, M = h->M, L1 = h->L1, L = M * L1;
+  if (upload_const(h)) return 1;
+  if (prep_ruptures(h, planar, mag, magdist, U)) return 1;
+  if (prep_sites(h, sites, N)) return 1;
+
+  FusedArgs A;
+  memset(&A, 0, sizeof(A));
+  A.rup = (const double *)h->rup.p;
+  A.probs = K ? probs : nullptr;
+  A.site = (const double *)h->site.p;
+  A.vs30 = sites->vs30; A.z1pt0 = sites->z1pt0; A.z2pt5 = sites->z2pt5;
+  A.vs30measured = sites->vs30measured;
+  A.counters = counters;
+  A.U = U; A.N = N; A.K = K; A.G = G; A.M = M; A.L1 = L1;
+  A.nlc = (L1 + NL - 1) / NL;
+  A.lpc = (L1 + A.nlc - 1) / A.nlc;
+  A.nunits = M * A.nlc;
+  A.mindist = mindist; A.itime = itime; A.phi_b = h->phi_b;
+  A.inv_norm = 1. / (h->phi_b * 2. - 1.);
+
+  // CTA shape: nw warps (units) per CTA, unit groups on blockIdx.z
+  int ugroups = (A.nunits + NWMAX - 1) / NWMAX;
+  int nw = (A.nunits + ugroups - 1) / ugroups;
+  int tiles = (N + 31) / 32;
+  // rupture chunks: enough CTAs for ~8 waves of 2 CTAs per SM, rounded to
+  // whole shared-memory tiles, so that the tail wave is small
+  int64_t ctas_wanted = (int64_t)h->sm_count * 2 * 8;
+  int64_t rc = (ctas_wanted + (int64_t)tiles * ugroups - 1) /
+               ((int64_t)tiles * ugroups);
+  int64_t max_rc = (U + RT - 1) / RT;
+  rc = std::max<int64_t>(1, std::min<int64_t>(rc, std::min<int64_t>(max_rc, 64)));
+  int64_t rpc = (U + rc - 1) / rc;
+  rpc = (rpc + RT - 1) / RT * RT;
+  rc = (U + rpc - 1) / rpc;
+  A.rup_per_chunk = (int)rpc;
+  if (reserve(h, h->part, (size_t)rc * G * N * L * 8)) return 1;
+  A.part = (double *)h->part.p;
+
+  for (int g = 0; g < G; g++) {
+    const oqg_gsim &gs = h->gsims[g];
+    if (gs.family == OQG_CB14 && !sites->z2pt5) return fail(h, "sites need z2pt5");
+    if (!sites->vs30) return fail(h, "sites need vs30");
+    if ((gs.family == OQG_CY14 || gs.family == OQG_ASK14) &&
+        (!sites->z1pt0 || !sites->vs30measured))
+      return fail(h, "sites need z1pt0 and vs30measured");
+    A.g = g;
+    A.clampmask = required_distances(gs);
+    A.dmask = A.clampmask | (1 << OQG_RRUP);
+    if (A.dmask & (1 << OQG_RHYPO)) A.dmask |= 1 << OQG_REPI;
+    A.nplanes = 0;
+    for (int k = 0; k < 6; k++)
+      if ((A.dmask >> k) & 1) A.plane_of[k] = A.nplanes++;
+    A.count_pairs = counters && g == 0;  // blockIdx.z == 0 only
+    size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
+                   NF_SITE * 32 + (K ? RT * K : 0)) * 8 + RT * 4;
+    dim3 grid(tiles, (unsigned)rc, ugroups);
+    // only blockIdx.z == 0 counts pairs
+    cudaError_t e = cudaSuccess;
+    CK(cudaEventRecord(h->ev[2 * g], h->stream));
+    switch (gs.family) {
+      case OQG_BSSA14: e = launch_fused<OQG_BSSA14>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_CY14: e = launch_fused<OQG_CY14>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_ASK14: e = launch_fused<OQG_ASK14>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_CB14: e = launch_fused<OQG_CB14>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_BA08: e = launch_fused<OQG_BA08>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_AB06: e = launch_fused<OQG_AB06>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_AKKAR14: e = launch_fused<OQG_AKKAR14>(A, grid, 32 * nw, smem, h->stream); break;
+    }
+    CK(cudaEventRecord(h->ev[2 * g + 1], h->stream));
+    h->launches++;
+    if (e != cudaSuccess)
+      return fail(h, std::string("fused launch: ") + cudaGetErrorString(e));
+  }
+  h->n_fused_ev = G;
+  int64_t tot = (int64_t)N * L * G;
+  k_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+      A.part, (int)rc, G, N, L, sidx, rates_mode, map);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int h2d(oqg_handle *h, Buf &b, const void *src, size_t bytes,
+               const void **dev) {
+  if (!src) { *dev = nullptr; return 0; }
+  if (reserve(h, b, bytes)) return 1;
+  CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  *dev = b.p;
+  return 0;
+}
+
+int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
+                           const double *mag, const double *magdist,
+                           const double *probs, int K, int U,
+                           const oqg_sites *s, int N, double mindist,
+                           double itime, int rates_mode, float *map,
+                           unsigned long long *pairs_kept) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
+  const void *d[11];
+  oqg_sites sd;
+  if (h2d(h, h->stage[0], planar, (size_t)U * OQG_PLANAR_LEN * 8, &d[0])) return 1;
+  if (h2d(h, h->stage[1], mag, (size_t)U * 8, &d[1])) return 1;
+  if (h2d(h, h->stage[2], magdist, (size_t)U * 8, &d[2])) return 1;
+  if (h2d(h, h->stage[3], K ? probs : nullptr, (size_t)U * K * 8, &d[3])) return 1;
+  if (h2d(h, h->stage[4], s->lon, (size_t)N * 8, &d[4])) return 1;
+  if (h2d(h, h->stage[5], s->lat, (size_t)N * 8, &d[5])) return 1;
+  if (h2d(h, h->stage[6], s->depth, (size_t)N * 8, &d[6])) return 1;
+  if (h2d(h, h->stage[7], s->vs30, (size_t)N * 8, &d[7])) return 1;
+  if (h2d(h, h->stage[8], s->z1pt0, (size_t)N * 8, &d[8])) return 1;
+  if (h2d(h, h->stage[9], s->z2pt5, (size_t)N * 8, &d[9])) return 1;
+  if (h2d(h, h->stage[10], s->vs30measured, (size_t)N, &d[10])) return 1;
+  sd.lon = (const double *)d[4]; sd.lat = (const double *)d[5];
+  sd.depth = (const double *)d[6]; sd.vs30 = (const double *)d[7];
+  sd.z1pt0 = (const double *)d[8]; sd.z2pt5 = (const double *)d[9];
+  sd.vs30measured = (const uint8_t *)d[10];
+  size_t mbytes = (size_t)N * h->M * h->L1 * h->G * 4;
+  // the map and the pair counter share one staging buffer
+  if (reserve(h, h->stage[11], mbytes + 16)) return 1;
+  float *map_dev = (float *)h->stage[11].p;
+  unsigned long long *cnt =
+      (unsigned long long *)((char *)h->stage[11].p + (mbytes + 7) / 8 * 8);
+  CK(cudaMemcpyAsync(map_dev, map, mbytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(cnt, 0, 8, h->stream));
+  if (oqg_hazard_planar(h, (const double *)d[0], (const double *)d[1],
+                        (const double *)d[2], (const double *)d[3], K, U, &sd,
+                        nullptr, N, mindist, itime, rates_mode, map_dev,
+                        pairs_kept ? cnt : nullptr))
+    return 1;
+  CK(cudaMemcpyAsync(map, map_dev, mbytes, cudaMemcpyDeviceToHost, h->stream));
+  if (pairs_kept)
+    CK(cudaMemcpyAsync(pairs_kept, cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+unsigned long long oqg_launch_count(oqg_handle *h) { return h->launches; }
+
+int oqg_last_fused_ms(oqg_handle *h, float *ms, int cap) {
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+  int n = std::min(cap, h->n_fused_ev);
+  for (int g = 0; g < n; g++)
+    if (cudaEventElapsedTime(&ms[g], h->ev[2 * g], h->ev[2 * g + 1]) !=
+        cudaSuccess)
+      return -1;
+  return n;
+}
+
+int oqg_measure_fp64_peak(oqg_handle *h, double *tflops) {
+  CK(cudaSetDevice(h->device));
+  double *out = nullptr;
+  CK(cudaMalloc((void **)&out, 8));
+  const int iters = 4096, threads = 256, blocks = h->sm_count * 8;
+  cudaEvent_t a = h->ev[2 * OQG_MAX_G], b = h->ev[2 * OQG_MAX_G + 1];
+  k_dfma<<<blocks, threads, 0, h->stream>>>(out, 64);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(a, h->stream));
+    k_dfma<<<blocks, threads, 0, h->stream>>>(out, iters);
+    CK(cudaEventRecord(b, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    best = std::min(best, ms);
+  }
+  h->launches += 6;
+  CK(cudaFree(out));
+  double flops = 2.0 * 8 * iters * (double)threads * blocks;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// Rupture-to-site distance metrics for planar ruptures as device functions.
+//
+// Reference: openquake/hazardlib/geo/surface/planar.py (project :324-403,
+// get_rjb :460-529, get_rx :533-545, get_ry0 :549-568, get_rhypo :572-586,
+// get_repi :589-602, get_azimuth :605-621), geo/geodetic.py (distances
+// :38-48, distances_to_arc :51-66) and geo/utils.py (min_distance :710-720).
+//
+// The reference evaluates the cross-track distance to a great-circle arc as
+//    (pi/2 - acos(sin(azimuth_to_target - azimuth) * sin(dist / R))) * R
+// with ~20 transcendental calls.  Here the same quantity is computed from
+// unit vectors: with p the arc origin, q the site and w = e_p cos(azi) -
+// n_p sin(azi) (e_p, n_p the local east / north unit vectors at p) one has
+//    sin(azimuth_to_target - azimuth) * sin(dist / R) == (q - p) . w
+// exactly, so the distance is R * asin((q - p) . w): one dot product and one
+// asin, better conditioned than the reference formula (which loses ~1e-12
+// relative to cancellation in lon - lons).  The great-circle distance comes
+// from the chord: sin(dist / 2R) = |q - p| / 2.
+//
+// A rupture is prepared once (prep_rupture) into NF_RUP doubles stored
+// field-major in HBM (rup[field][R]) so that rupture tiles load coalesced.
+#pragma once
+#include <math.h>
+#include "../../include/oqg.h"
+
+namespace oqg {
+
+#define OQG_EARTH_RADIUS 6371.0  // geodetic.py:32
+#define OQG_R2D 57.29577951308232
+
+// fields of a prepared rupture
+enum {
+  RF_TL = 0,       // xyz of the top-left corner, km (3)
+  RF_NRM = 3,      // unit normal (3)
+  RF_UV1 = 6,      // unit vector along strike (3)
+  RF_UV2 = 9,      // unit vector down dip (3)
+  RF_WIDTH = 12,
+  RF_LENGTH = 13,
+  RF_W0 = 14,      // arc normals: BL/strike, TL/strike, TL/downdip, TR/downdip
+  RF_P0 = 26,      // arc origins as unit vectors BL, TL, TL, TR -> only 3
+                   // distinct: BL (26), TL (29), TR (32)
+  RF_CS = 35,      // surface projections of the corners TL TR BL BR, km (12)
+  RF_HYP = 47,     // hypocentre unit vector (3)
+  RF_HDEP = 50,    // hypocentre depth
+  RF_HE = 51,      // east unit vector at the hypocentre (3)
+  RF_HN = 54,      // north unit vector at the hypocentre (3)
+  RF_STRIKE = 57,
+  RF_MAG = 58, RF_RAKE = 59, RF_DIP = 60, RF_ZTOR = 61, RF_HYPO_DEPTH = 62,
+  RF_RATE = 63, RF_MAGDIST = 64,
+  NF_RUP = 65
+};
+
+// fields of a prepared site
+enum {
+  SF_XYZ = 0,   // km (3)
+  SF_Q = 3,     // unit vector (3)
+  SF_DEPTH = 6, // EARTH_RADIUS - |xyz|
+  NF_SITE = 7
+};
+
+struct Dist {
+  double rrup, rjb, rx, ry0, repi, rhypo, azimuth;
+};
+
+__device__ __forceinline__ void unit_from_lonlat(double lon_deg, double lat_deg,
+                                                 double *p, double *e,
+                                                 double *n) {
+  double sl, cl, sp, cp;
+  sincos(lon_deg * 0.017453292519943295, &sl, &cl);
+  sincos(lat_deg * 0.017453292519943295, &sp, &cp);
+  p[0] = cp * cl; p[1] = cp * sl; p[2] = sp;
+  if (e) { e[0] = -sl; e[1] = cl; e[2] = 0.; }
+  if (n) { n[0] = -sp * cl; n[1] = -sp * sl; n[2] = cp; }
+}
+
+// planar: 42 doubles, the memory of one (3,) record array of
+// planar_array_dt (planar.py:45-53);
+// writes field f of the prepared rupture to out[f * stride]
+__device__ inline void prep_rupture(const double *pl, double mag,
+                                    double magdist, double *out,
+                                    int64_t stride) {
+  // memory layout of a (3,) record array of planar_array_dt: [k][14] with
+  // k = lon/lat/dep (x/y/z) and 14 = corners[4] xyz[4] normal uv1 uv2 wlr
+  // sdr hypo
+#define CORNER(k, c) pl[(k) * 14 + (c)]
+#define XYZ(k, c) pl[(k) * 14 + 4 + (c)]
+  const double wlr[3] = {pl[11], pl[14 + 11], pl[28 + 11]};
+  const double sdr[3] = {pl[12], pl[14 + 12], pl[28 + 12]};
+  const double hypo[3] = {pl[13], pl[14 + 13], pl[28 + 13]};
+#define PUT(f, v) out[(int64_t)(f) * stride] = (v)
+  for (int k = 0; k < 3; k++) {
+    PUT(RF_TL + k, XYZ(k, 0));
+    PUT(RF_NRM + k, pl[k * 14 + 8]);
+    PUT(RF_UV1 + k, pl[k * 14 + 9]);
+    PUT(RF_UV2 + k, pl[k * 14 + 10]);
+  }
+  PUT(RF_WIDTH, wlr[0]);
+  PUT(RF_LENGTH, wlr[1]);
+  const double strike = sdr[0];
+  const double downdip = fmod(strike + 90., 360.);
+  double ss, cs, sd, cd;
+  sincos(strike * 0.017453292519943295, &ss, &cs);
+  sincos(downdip * 0.017453292519943295, &sd, &cd);
+  // corner order TL TR BL BR; arcs: (BL, strike) (TL, strike) (TL, downdip)
+  // (TR, downdip), planar.py:481-498
+  const int arc_corner[4] = {2, 0, 0, 1};
+  for (int a = 0; a < 4; a++) {
+    int c = arc_corner[a];
+    double p[3], e[3], n[3];
+    unit_from_lonlat(CORNER(0, c), CORNER(1, c), p, e, n);
+    double sa = a < 2 ? ss : sd, ca = a < 2 ? cs : cd;
+    for (int k = 0; k < 3; k++) PUT(RF_W0 + 3 * a + k, e[k] * ca - n[k] * sa);
+  }
+  const int origin_corner[3] = {2, 0, 1};  // BL, TL, TR
+  for (int j = 0; j < 3; j++) {
+    double p[3];
+    int c = origin_corner[j];
+    unit_from_lonlat(CORNER(0, c), CORNER(1, c), p, 0, 0);
+    for (int k = 0; k < 3; k++) PUT(RF_P0 + 3 * j + k, p[k]);
+  }
+  for (int c = 0; c < 4; c++) {
+    double p[3];
+    unit_from_lonlat(CORNER(0, c), CORNER(1, c), p, 0, 0);
+    for (int k = 0; k < 3; k++)
+      PUT(RF_CS + 3 * c + k, p[k] * OQG_EARTH_RADIUS);
+  }
+  {
+    double p[3], e[3], n[3];
+    unit_from_lonlat(hypo[0], hypo[1], p, e, n);
+    for (int k = 0; k < 3; k++) {
+      PUT(RF_HYP + k, p[k]);
+      PUT(RF_HE + k, e[k]);
+      PUT(RF_HN + k, n[k]);
+    }
+  }
+  PUT(RF_HDEP, hypo[2]);
+  PUT(RF_STRIKE, strike);
+  PUT(RF_MAG, mag);
+  PUT(RF_RAKE, sdr[2]);
+  PUT(RF_DIP, sdr[1]);
+  PUT(RF_ZTOR, CORNER(2, 0));
+  PUT(RF_HYPO_DEPTH, hypo[2]);
+  PUT(RF_RATE, wlr[2]);
+  PUT(RF_MAGDIST, magdist);
+#undef PUT
+#undef CORNER
+#undef XYZ
+}
+
+// site: lon/lat in degrees, depth km -> xyz (geodetic.py:445-480), the unit
+// vector and the depth recovered from xyz (geo/utils.py:688-707)
+__device__ inline void prep_site(double lon, double lat, double depth,
+                                 double *out, int64_t stride) {
+  double p[3];
+  unit_from_lonlat(lon, lat, p, 0, 0);
+  double rr = OQG_EARTH_RADIUS - depth;
+  double x = rr * p[0], y = rr * p[1], z = rr * p[2];
+  double nrm = sqrt(x * x + y * y + z * z);
+  out[(SF_XYZ + 0) * stride] = x;
+  out[(SF_XYZ + 1) * stride] = y;
+  out[(SF_XYZ + 2) * stride] = z;
+  out[(SF_Q + 0) * stride] = x / nrm;
+  out[(SF_Q + 1) * stride] = y / nrm;
+  out[(SF_Q + 2) * stride] = z / nrm;
+  out[SF_DEPTH * stride] = OQG_EARTH_RADIUS - nrm;
+}
+
+// Distances of one rupture-site pair.  `rup` points to field 0 of the
+// rupture, fields are `rs` doubles apart (shared or global memory); the site
+// is given by its xyz (km), unit vector q and depth.  `mask` selects what to
+// compute (rrup always).
+template <typename RupPtr>
+__device__ __forceinline__ void pair_distances(RupPtr rup, int rs,
+                                               const double *sx,
+                                               const double *sq, double sdep,
+                                               int mask, Dist &d) {
+#define RUP(f) rup[(f) * rs]
+  // --- rrup, planar.py:324-403
+  {
+    double m0 = sx[0] - RUP(RF_TL), m1 = sx[1] - RUP(RF_TL + 1),
+           m2 = sx[2] - RUP(RF_TL + 2);
+    double dn = m0 * RUP(RF_NRM) + m1 * RUP(RF_NRM + 1) + m2 * RUP(RF_NRM + 2);
+    double xx = m0 * RUP(RF_UV1) + m1 * RUP(RF_UV1 + 1) + m2 * RUP(RF_UV1 + 2);
+    double yy = m0 * RUP(RF_UV2) + m1 * RUP(RF_UV2 + 1) + m2 * RUP(RF_UV2 + 2);
+    double len = RUP(RF_LENGTH), wid = RUP(RF_WIDTH);
+    double mxx = xx < 0. ? xx : (xx > len ? xx - len : 0.);
+    double myy = yy < 0. ? yy : (yy > wid ? yy - wid : 0.);
+    d.rrup = sqrt(dn * dn + mxx * mxx + myy * myy);
+  }
+  if (mask & ((1 << OQG_RJB) | (1 << OQG_RX) | (1 << OQG_RY0))) {
+    // signed sines of the four cross-track angles
+    double s[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int po = a == 0 ? 0 : (a == 3 ? 2 : 1);  // BL TL TL TR
+      double e0 = sq[0] - RUP(RF_P0 + 3 * po), e1 = sq[1] - RUP(RF_P0 + 3 * po + 1),
+             e2 = sq[2] - RUP(RF_P0 + 3 * po + 2);
+      s[a] = e0 * RUP(RF_W0 + 3 * a) + e1 * RUP(RF_W0 + 3 * a + 1) +
+             e2 * RUP(RF_W0 + 3 * a + 2);
+    }
+    if (mask & (1 << OQG_RX)) d.rx = asin(s[1]) * OQG_EARTH_RADIUS;
+    bool same23 = (s[2] > 0.) == (s[3] > 0.) && (s[2] < 0.) == (s[3] < 0.);
+    if (mask & (1 << OQG_RY0)) {
+      d.ry0 = same23 ? asin(fmin(fabs(s[2]), fabs(s[3]))) * OQG_EARTH_RADIUS
+                     : 0.;
+    }
+    if (mask & (1 << OQG_RJB)) {
+      bool same01 = (s[0] > 0.) == (s[1] > 0.) && (s[0] < 0.) == (s[1] < 0.);
+      if (same01 && same23) {
+        // min distance to the surface projections of the corners
+        double best = 1e300;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          double e0 = sx[0] - RUP(RF_CS + 3 * c), e1 = sx[1] - RUP(RF_CS + 3 * c + 1),
+                 e2 = sx[2] - RUP(RF_CS + 3 * c + 2);
+          best = fmin(best, e0 * e0 + e1 * e1 + e2 * e2);
+        }
+        d.rjb = sqrt(best);
+      } else if (same01) {
+        d.rjb = asin(fmin(fabs(s[0]), fabs(s[1]))) * OQG_EARTH_RADIUS;
+      } else if (same23) {
+        d.rjb = asin(fmin(fabs(s[2]), fabs(s[3]))) * OQG_EARTH_RADIUS;
+      } else {
+        d.rjb = 0.;
+      }
+    }
+  }
+  if (mask & ((1 << OQG_REPI) | (1 << OQG_RHYPO) | (1 << OQG_AZIMUTH))) {
+    double e0 = sq[0] - RUP(RF_HYP), e1 = sq[1] - RUP(RF_HYP + 1),
+           e2 = sq[2] - RUP(RF_HYP + 2);
+    double half = 0.5 * sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+    d.repi = asin(fmin(half, 1.)) * 2. * OQG_EARTH_RADIUS;
+    double vd = RUP(RF_HDEP) - sdep;
+    d.rhypo = sqrt(d.repi * d.repi + vd * vd);
+    if (mask & (1 << OQG_AZIMUTH)) {
+      double E = e0 * RUP(RF_HE) + e1 * RUP(RF_HE + 1) + e2 * RUP(RF_HE + 2);
+      double N = e0 * RUP(RF_HN) + e1 * RUP(RF_HN + 1) + e2 * RUP(RF_HN + 2);
+      // fast_azimuth (geodetic.py:117-130) then (azimuth - strike) % 360
+      double az = atan2(E, N) * OQG_R2D - RUP(RF_STRIKE);
+      az = fmod(az, 360.);
+      if (az < 0.) az += 360.;
+      d.azimuth = az;
+    }
+  }
+#undef RUP
+}
+
+}  // namespace oqg

@@ -1,0 +1,443 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): the CUDA path, called
+through the C ABI (ctypes) and through the reference-like Python operators,
+against the golden fixtures produced by the reference and against the numpy
+oracle on seeded inputs.
+
+Tolerances: mean/sig/tau/phi float64 rtol 1e-10 (the device uses CUDA's
+libm, 1-2 ulp per call); distances rtol 1e-9 / atol 1e-8 km (the reference's
+own formulas are conditioned to ~1e-12 relative); PoEs float32 rtol 1e-5
+where PoE >= 1e-8 (BASELINE.json north_star); maps rtol 1e-5 against a
+float64 re-accumulation of the oracle's PoEs and rtol 2e-5 against the
+reference's float32 read-modify-write maps.
+"""
+import json
+import ctypes
+import numpy as np
+import pytest
+
+import geo_np
+import hazard_np
+import poe_np
+from helpers import (GOLDEN, load, gmpe_cases, pipeline_cases, ctx_of, rup_of,
+                     sites_of, json_kwargs, synth_ruptures, synth_sites, Bag)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def oq():
+    import oq_engine_b200
+    oq_engine_b200._lib.lib()   # fails loudly if the extension is missing
+    return oq_engine_b200
+
+
+def make_gsims(oq, pairs):
+    return [oq.get_gsim(name, **kw) for name, kw in pairs]
+
+
+def to_recarray(bag):
+    names = list(vars(bag))
+    dt = [(n, vars(bag)[n].dtype, vars(bag)[n].shape[1:]) for n in names]
+    arr = np.zeros(len(bag), dt)
+    for n in names:
+        arr[n] = vars(bag)[n]
+    return arr.view(np.recarray)
+
+
+def planar_of(oq, d):
+    r = rup_of(d)
+    pla = oq.build_planar(
+        r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+        r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], float(d['usd']),
+        float(d['lsd']), float(d['rar']))
+    return r, pla
+
+
+def sitecol_of(oq, d):
+    s = sites_of(d)
+    return oq.SiteCollection.from_points(s['lon'], s['lat'], s['depth'], s)
+
+
+# ------------------------------------------------------------------ GMPEs
+@pytest.mark.parametrize('tag', gmpe_cases())
+def test_gmpe_golden(oq, tag):
+    d = load('gmpe_' + tag)
+    gsim = oq.get_gsim(str(d['name']), **json_kwargs(d))
+    ctx = to_recarray(ctx_of(d))
+    imts = [str(i) for i in d['imts']]
+    M, N = len(imts), len(ctx)
+    out = np.zeros((4, M, N))
+    gsim.compute(ctx, imts, *out)       # the reference operator
+    np.testing.assert_allclose(out, d['mean_stds'], rtol=1e-10, atol=1e-12)
+
+
+def test_gmpe_unsupported_is_an_error(oq):
+    with pytest.raises(NotImplementedError):
+        oq.get_gsim('ToroEtAl2002')
+    with pytest.raises(NotImplementedError):
+        oq.BooreEtAl2014(usgs_basin_scaling=True)
+    with pytest.raises(KeyError):   # IMT outside the table
+        oq.ContextMaker('*', [oq.AtkinsonBoore2006()],
+                        dict(imtls={'SA(9.0)': [0.1]}))
+
+
+# -------------------------------------------------------------- distances
+def test_planar_golden(oq):
+    d = load('planar')
+    r, pla = planar_of(oq, d)
+    for f in ('corners', 'xyz', 'normal', 'uv1', 'uv2', 'wlr', 'sdr', 'hypo'):
+        np.testing.assert_allclose(pla[f], d['planar_' + f], rtol=0,
+                                   atol=1e-10, err_msg=f)
+    sc = sitecol_of(oq, d)
+    gsims = [oq.AbrahamsonEtAl2014(), oq.AkkarEtAlRepi2014(),
+             oq.AkkarEtAlRhyp2014()]
+    cm = oq.ContextMaker('*', gsims, dict(imtls={'PGA': [0.1]}))
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    ctxs = cm.get_ctxs(src, sc)
+    ctx = cm.recarray(ctxs)
+    assert len(ctx) == len(r['mag']) * len(sc)
+    for name in ('rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo'):
+        got = np.zeros((len(r['mag']), len(sc)))
+        got[ctx.rup_id, ctx.sids] = ctx[name]
+        np.testing.assert_allclose(got, d['dist_' + name], rtol=1e-9,
+                                   atol=1e-8, err_msg=name)
+
+
+def test_distances_c_abi_all_metrics(oq):
+    import torch
+    d = load('planar')
+    r, pla = planar_of(oq, d)
+    s = sites_of(d)
+    h = oq.contexts.get_handle()
+    dev = 'cuda:%d' % h.device
+    U, N = len(pla), len(s['lon'])
+    t_pla = torch.from_numpy(oq.planar.as_flat(pla)).to(dev)
+    st = oq._lib.OqgSites()
+    keep = []
+    for name in ('lon', 'lat', 'depth'):
+        t = torch.from_numpy(np.ascontiguousarray(s[name])).to(dev)
+        keep.append(t)
+        setattr(st, name, t.data_ptr())
+    out = torch.empty((7, U, N), dtype=torch.float64, device=dev)
+    h.call('oqg_distances', ctypes.c_void_p(t_pla.data_ptr()), U,
+           ctypes.byref(st), N, 0x7f, ctypes.c_void_p(out.data_ptr()))
+    out = out.cpu().numpy()
+    for k, name in enumerate(oq._lib.DIST):
+        exp = d['dist_' + name]
+        if name == 'azimuth':   # circular quantity
+            diff = np.abs((out[k] - exp + 180) % 360 - 180)
+            assert diff.max() < 1e-6, diff.max()
+        else:
+            np.testing.assert_allclose(out[k], exp, rtol=1e-9, atol=1e-8,
+                                       err_msg=name)
+
+
+def test_distances_random_vs_oracle(oq):
+    rng = np.random.default_rng(11)
+    r = synth_ruptures(300, rng, box=3.0)
+    sites = synth_sites(500, rng, box=3.0)
+    sites['depth'] = rng.uniform(0, 2, 500) * (rng.random(500) < .3)
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    opla = geo_np.build_planar(
+        r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+        r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+    for f in ('corners', 'xyz', 'normal', 'uv1', 'uv2', 'wlr'):
+        np.testing.assert_allclose(pla[f], opla[f], rtol=0, atol=1e-9)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    cm = oq.ContextMaker('*', [oq.AbrahamsonEtAl2014(),
+                               oq.AkkarEtAlRhyp2014(),
+                               oq.AkkarEtAlRepi2014()],
+                         dict(imtls={'PGA': [0.1]}))
+    ctx = cm.recarray(cm.get_ctxs(oq.contexts.PlanarRuptures(pla, r['mag']),
+                                  sc))
+    xyz = hazard_np.site_xyz(sites)
+    for name in ('rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo'):
+        exp = geo_np.DIST[name](opla, xyz)
+        got = np.zeros_like(exp)
+        got[ctx.rup_id, ctx.sids] = ctx[name]
+        np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-8,
+                                   err_msg=name)
+
+
+# ------------------------------------------------- unfused pipeline pieces
+def cmaker_of(oq, d, **extra):
+    gsims = make_gsims(oq, [tuple(g) for g in json.loads(str(d['gsims']))])
+    imtls = {str(i): d['imls'] for i in d['imts']}
+    nb = json.loads(str(d['negbin']))
+    cm = oq.ContextMaker('*', gsims, dict(
+        imtls=imtls, truncation_level=float(d['truncation_level']),
+        investigation_time=float(d['investigation_time']),
+        maximum_distance=float(d['maxdist']),
+        minimum_distance=float(d['mindist']), **extra))
+    itime = float(d['investigation_time'])
+    cm.tom = (oq.NegativeBinomialTOM(itime, **nb) if nb
+              else oq.PoissonTOM(itime))
+    return cm
+
+
+@pytest.mark.parametrize('tag', pipeline_cases())
+def test_pipeline_unfused_golden(oq, tag):
+    d = load('pipeline_' + tag)
+    cm = cmaker_of(oq, d)
+    r, pla = planar_of(oq, d)
+    sc = sitecol_of(oq, d)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    ctx = cm.recarray(cm.get_ctxs(src, sc))
+    ref = to_recarray(ctx_of(d))
+    assert len(ctx) == len(ref)
+    # same order: by magnitude, then rupture, then site
+    np.testing.assert_array_equal(ctx.sids, ref.sids)
+    for name in ctx.dtype.names:
+        if name in ('src_id', 'rup_id', 'sids'):
+            continue
+        np.testing.assert_allclose(ctx[name], ref[name], rtol=1e-9,
+                                   atol=1e-8, err_msg=name)
+    # mean and stds on the reference's rows
+    ms = cm.get_mean_stds([ref], split_by_mag=False)
+    np.testing.assert_allclose(ms, d['mean_stds'], rtol=1e-10, atol=1e-12)
+    # PoEs
+    poes = np.concatenate([p for p, *_ in cm.gen_poes(ref.copy().view(
+        np.recarray))])
+    exp = d['poes']
+    big = exp > 1e-8
+    np.testing.assert_allclose(poes[big], exp[big], rtol=1e-5)
+    assert np.abs(poes - exp).max() < 1e-7
+    # maps
+    N, L, G = d['pmap'].shape
+    pmap = oq.MapArray(sc.sids, L, G).fill(1)
+    cm.update(pmap, ref)
+    np.testing.assert_allclose(pmap.array, d['pmap'], rtol=2e-5, atol=1e-7)
+    rmap = oq.MapArray(sc.sids, L, G, rates=True).fill(0)
+    cm.update(rmap, ref)
+    np.testing.assert_allclose(rmap.array, d['rmap'], rtol=2e-5, atol=1e-9)
+    # get_pmap = 1 - pne map
+    # 1 - pne in float32: absolute error 2e-5 * pne
+    np.testing.assert_allclose(cm.get_pmap(ref).array, 1. - d['pmap'],
+                               rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize('tag', pipeline_cases())
+def test_pipeline_fused_golden(oq, tag):
+    d = load('pipeline_' + tag)
+    cm = cmaker_of(oq, d)
+    r, pla = planar_of(oq, d)
+    sc = sitecol_of(oq, d)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    N, L, G = d['pmap'].shape
+    pmap = oq.MapArray(sc.sids, L, G).fill(1)
+    kept = cm.hazard_planar(pmap, src, sc, count=True)
+    assert kept == len(d['ctx_sids'])
+    np.testing.assert_allclose(pmap.array, d['pmap'], rtol=2e-5, atol=1e-7)
+    rmap = oq.MapArray(sc.sids, L, G, rates=True).fill(0)
+    cm.hazard_planar(rmap, src, sc)
+    np.testing.assert_allclose(rmap.array, d['rmap'], rtol=2e-5, atol=1e-9)
+    if not json.loads(str(d['negbin'])):
+        # order independent check against the float64 sum of the
+        # reference's own float32 PoEs
+        ref = ctx_of(d)
+        acc = np.zeros((N, L, G))
+        x = ref.occurrence_rate[:, None, None] * d['poes'] * float(
+            d['investigation_time'])
+        np.add.at(acc, ref.sids, x)
+        big = acc > 1e-12
+        np.testing.assert_allclose(rmap.array[big], acc[big], rtol=1e-5)
+
+
+def test_truncnorm_edges(oq):
+    """truncnorm_sf edge cases of the reference through oqg_poes"""
+    import torch
+    with open(GOLDEN + '/truncnorm.json') as f:
+        cases = json.load(f)
+    h = oq.contexts.get_handle()
+    dev = 'cuda:%d' % h.device
+    for c in cases:
+        z = np.array(c['z'])
+        exp = np.array([np.nan if x is None else x for x in c['sf']])
+        n = len(z)
+        cm = oq.ContextMaker('*', [oq.BooreAtkinson2008()], dict(
+            imtls={'PGA': [1.0]}, truncation_level=c['truncation_level']))
+        hh = cm.handle()
+        # mean = -z, sig = 1, level log(1) = 0  ->  (0 - mean) / sig = z
+        ms = np.zeros((4, 1, 1, n))
+        ms[0, 0, 0] = -z
+        ms[1, 0, 0] = 1.
+        t_ms = torch.from_numpy(ms).to(dev)
+        out = torch.empty((n, 1, 1), dtype=torch.float32, device=dev)
+        hh.call('oqg_poes', ctypes.c_void_p(t_ms.data_ptr()), n,
+                ctypes.c_void_p(out.data_ptr()))
+        got = out.cpu().numpy().ravel()
+        ok = np.isfinite(exp)
+        np.testing.assert_allclose(got[ok], exp[ok].astype(np.float32),
+                                   rtol=2e-6, atol=1e-30)
+        assert np.isnan(got[~ok]).all()
+
+
+# ------------------------------------------ random larger cases vs oracle
+CFG = {
+    'cfg3': [('BooreEtAl2014', {}), ('ChiouYoungs2014', {})],
+    'cfg4': [('BooreEtAl2014', {}), ('ChiouYoungs2014', {}),
+             ('AbrahamsonEtAl2014', {}), ('CampbellBozorgnia2014', {})],
+    'mixed': [('BooreAtkinson2008', {}), ('AkkarEtAlRjb2014', {}),
+              ('AtkinsonBoore2006', {}), ('AkkarEtAlRhyp2014', {}),
+              ('AkkarEtAlRepi2014', {}),
+              ('BooreEtAl2014', dict(region='CAL', sigma_mu_epsilon=1.)),
+              ('ChiouYoungs2014', dict(region='JPN'))],
+}
+IMTS = ['PGA', 'SA(0.1)', 'SA(0.2)', 'SA(0.5)', 'SA(1.0)', 'SA(2.0)',
+        'SA(3.0)']
+
+
+@pytest.mark.parametrize('cfg,U,N,maxdist,mindist,L1', [
+    ('cfg3', 257, 333, 1000., 0., 20),
+    ('cfg4', 130, 190, 1000., 0., 20),
+    ('cfg3', 200, 100, 80., 3., 20),      # distance filter + clamp
+    ('mixed', 96, 65, 150., 0., 20),
+    ('cfg3', 64, 70, 1000., 0., 45),      # three level chunks per IMT
+    ('cfg3', 33, 31, 1000., 0., 7),       # short level grid, ragged tiles
+    ('cfg4', 1, 1, 1000., 0., 20),        # single pair
+])
+def test_fused_vs_oracle(oq, cfg, U, N, maxdist, mindist, L1):
+    rng = np.random.default_rng(U * 1000 + N)
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng, sentinels=True)
+    imls = np.logspace(-2, 0.3, L1)
+    imtls = {imt: imls for imt in IMTS}
+    pairs = CFG[cfg]
+    cm = oq.ContextMaker('*', make_gsims(oq, pairs), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.,
+        maximum_distance=maxdist, minimum_distance=mindist))
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    L, G = len(IMTS) * L1, len(pairs)
+    rmap = oq.MapArray(sc.sids, L, G, rates=True).fill(0)
+    kept = cm.hazard_planar(rmap, src, sc, count=True)
+    # oracle
+    opla = geo_np.build_planar(
+        r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+        r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+    octx = hazard_np.get_ctx(pairs, opla, r['mag'], sites,
+                             np.full(U, maxdist), mindist)
+    assert kept == len(octx)
+    acc = hazard_np.exact_rate_sum(pairs, octx, sites['sids'], imtls, 3., 50.)
+    big = acc > 1e-10
+    np.testing.assert_allclose(rmap.array[big], acc[big], rtol=1e-5)
+    assert np.abs(rmap.array - acc).max() <= 1e-5 * acc.max() + 1e-12
+    # pne mode and host-buffer entry point give the same map
+    pmap = oq.MapArray(sc.sids, L, G).fill(1)
+    cm.hazard_planar(pmap, src, sc)
+    np.testing.assert_allclose(pmap.array, np.exp(-acc), rtol=1e-5)
+    # the unfused operators agree with the fused kernel
+    ctx = cm.recarray(cm.get_ctxs(src, sc)) if len(octx) else None
+    if ctx is not None:
+        rmap2 = oq.MapArray(sc.sids, L, G, rates=True).fill(0)
+        cm.update(rmap2, ctx)
+        np.testing.assert_allclose(rmap2.array, rmap.array, rtol=2e-6,
+                                   atol=1e-12)
+
+
+def test_fused_host_entry_point(oq):
+    """oqg_hazard_planar_host: host buffers in, host map out"""
+    rng = np.random.default_rng(5)
+    U, N = 100, 77
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1)
+    cm.hazard_planar(pmap, src, sc)
+    h = cm.handle()
+    flat = oq.planar.as_flat(pla)
+    mag = np.ascontiguousarray(r['mag'])
+    md = cm.magdist(r['mag'])
+    st = oq._lib.OqgSites()
+    keep = {}
+    for name in ('lon', 'lat', 'depth', 'vs30', 'z1pt0', 'z2pt5'):
+        keep[name] = np.ascontiguousarray(sites[name], float)
+        setattr(st, name, keep[name].ctypes.data)
+    keep['m'] = np.ascontiguousarray(sites['vs30measured']).view(np.uint8)
+    st.vs30measured = keep['m'].ctypes.data
+    out = np.ones((N, cm.L, cm.G), np.float32)
+    kept = ctypes.c_ulonglong(0)
+    h.call('oqg_hazard_planar_host', flat.ctypes.data, mag.ctypes.data,
+           md.ctypes.data, None, 0, U, ctypes.byref(st), N, 0., 50., 0,
+           out.ctypes.data, ctypes.byref(kept))
+    assert kept.value == U * N
+    np.testing.assert_array_equal(out, pmap.array)
+
+
+def test_fused_negbin_vs_oracle(oq):
+    rng = np.random.default_rng(77)
+    U, N = 60, 50
+    r = synth_ruptures(U, rng)
+    r['rate'] = r['rate'] * 50   # make the non-Poissonian part visible
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    pairs = CFG['cfg3']
+    cm = oq.ContextMaker('*', make_gsims(oq, pairs), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    cm.tom = oq.NegativeBinomialTOM(50., mu=1., alpha=0.5)
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1)
+    cm.hazard_planar(pmap, src, sc)
+    opla = geo_np.build_planar(
+        r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+        r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+    po = cm.tom.get_pmf(opla['wlr'][:, 2])
+    octx = hazard_np.get_ctx(pairs, opla, r['mag'], sites, None, 0, po)
+    poes, _ = hazard_np.get_poes(pairs, octx, imtls, 3.)
+    logp = np.zeros((N, cm.L, cm.G))
+    for i in range(len(octx)):
+        pne = poe_np.get_pnes(octx.occurrence_rate[i], octx.probs_occur[i],
+                              poes[i].astype(float), 50.)
+        logp[octx.sids[i]] += np.log(pne)
+    np.testing.assert_allclose(pmap.array, np.exp(logp), rtol=1e-5)
+    assert pmap.array.min() < 0.9
+
+
+def test_map_on_device_and_sidx(oq):
+    """MapArray on the device, sites given as a subset with their own sids"""
+    rng = np.random.default_rng(3)
+    U, N = 50, 64
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    full = oq.MapArray(sc.sids, cm.L, cm.G).fill(1)
+    cm.hazard_planar(full, src, sc)
+    # two tiles (sids % 2) into a device-resident map
+    dmap = oq.MapArray(sc.sids, cm.L, cm.G, device='cuda:0').fill(1)
+    for tile in sc.split(2):
+        cm.hazard_planar(dmap, src, tile)
+    np.testing.assert_array_equal(dmap.numpy(), full.array)
+    # two halves of the ruptures multiply
+    half = oq.MapArray(sc.sids, cm.L, cm.G).fill(1)
+    for sl in (slice(0, 20), slice(20, U)):
+        cm.hazard_planar(half, oq.contexts.PlanarRuptures(
+            pla[sl], r['mag'][sl]), sc)
+    np.testing.assert_allclose(half.array, full.array, rtol=1e-6)
