@@ -178,6 +178,15 @@ int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
                            int rates_mode, float *map,
                            unsigned long long *pairs_kept);
 
+/* The fused kernel evaluates the PoEs from a float32 polynomial table of
+ * the truncated-normal survival function (argument in float64) when the
+ * table built for the truncation level reproduces the exact formula to 2e-6
+ * relative for PoE >= 1e-9; otherwise, or after oqg_set_exact_poe(h, 1), it
+ * uses the reference formula with FP64 erf.  oqg_poe_table_info reports
+ * whether the table is in use and its measured maximum relative error. */
+int oqg_set_exact_poe(oqg_handle *h, int on);
+int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err);
+
 /* number of kernels launched by this handle so far (for bench accounting) */
 unsigned long long oqg_launch_count(oqg_handle *h);
 /* average device milliseconds of the last fused kernel launches measured

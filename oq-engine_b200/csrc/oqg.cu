@@ -58,7 +58,9 @@ struct oqg_handle {
   double truncation_level = 0, phi_b = 0;
   bool const_dirty = true;
   unsigned long long launches = 0;
-  Buf rup, site, part, stage[12];
+  Buf rup, site, part, ptab, stage[12];
+  bool fast_ok = false, exact_poe = false;
+  double ptab_err = 0., xscale = 0.;
   int *flag_dev = nullptr;
   cudaEvent_t ev[2 * OQG_MAX_G + 2];
   int n_fused_ev = 0;
@@ -251,12 +253,24 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 }
 
 // ------------------------------------------------------------------ fused
+// Fast PoE: poe as a function of x = (tl - z) * PT_NODES_M1 / (2 tl) in
+// [0, PT_NODES - 1] is tabulated as one degree-5 polynomial per node k =
+// round(x) in u = x - k in [-.5, .5] (float32 coefficients built in float64
+// by oqg_set_levels); node 0 has a zero constant term, so that the relative
+// accuracy is kept as poe -> 0 (z -> truncation level), where the textbook
+// formula cancels.  x itself is computed in float64.  The table is
+// [PT_DEG + 1][PT_NODES] floats in shared memory: lanes with different nodes
+// hit different banks, lanes with the same node broadcast.
+#define PT_NODES 32
+#define PT_DEG 5
+
 struct FusedArgs {
   const double *rup;      // [NF_RUP][U]
   const double *probs;    // [U][K] or null
   const double *site;     // [NF_SITE][N]
   const double *vs30, *z1pt0, *z2pt5;
   const uint8_t *vs30measured;
+  const float *ptab;      // [PT_DEG + 1][PT_NODES] or null (exact FP64 PoEs)
   double *part;           // [RC][G][N][L]
   unsigned long long *counters;
   int64_t U;
@@ -271,19 +285,39 @@ struct FusedArgs {
   int nplanes;
   int plane_of[OQG_NDIST];
   int count_pairs;
-  double mindist, itime, phi_b, inv_norm;
+  double mindist, itime, phi_b, inv_norm, tl, xscale;
 };
 
-template <int F, bool NEGBIN>
+__device__ __forceinline__ float poe_table(const float *s_tab, double x64) {
+  float x = (float)x64;
+  x = fminf(fmaxf(x, 0.f), (float)(PT_NODES - 1));
+  float y = x + 8388608.f;              // 2^23: round to nearest integer
+  float u = x - (y - 8388608.f);
+  const float *c = s_tab + (__float_as_int(y) & (PT_NODES - 1));
+  float p = c[5 * PT_NODES];
+  p = fmaf(p, u, c[4 * PT_NODES]);
+  p = fmaf(p, u, c[3 * PT_NODES]);
+  p = fmaf(p, u, c[2 * PT_NODES]);
+  p = fmaf(p, u, c[1 * PT_NODES]);
+  return __saturatef(fmaf(p, u, c[0]));
+}
+
+template <int F, bool NEGBIN, bool FAST>
 __global__ void __launch_bounds__(32 * NWMAX, 2)
 k_fused(const FusedArgs A) {
   typedef typename Fam<F>::C CT;
+  typedef typename Fam<F>::R RS;
+  constexpr bool SHARED_ROW = sizeof(RS) >= 8;
   extern __shared__ double smem[];
-  double *s_rup = smem;                       // [NF_RUP][RT]
-  double *s_dist = s_rup + NF_RUP * RT;       // [nplanes][RT][32]
-  double *s_site = s_dist + A.nplanes * RT * 32;  // [NF_SITE][32]
-  double *s_probs = s_site + NF_SITE * 32;    // [RT][K]
-  unsigned *s_valid = (unsigned *)(s_probs + (NEGBIN ? RT * A.K : 0));
+  const int nthreads = blockDim.x;
+  double *s_rup = smem;                            // [NF_RUP][RT]
+  double *s_dist = s_rup + NF_RUP * RT;            // [nplanes][RT][32]
+  double *s_site = s_dist + A.nplanes * RT * 32;   // [NF_SITE][32]
+  double *s_acc = s_site + NF_SITE * 32;           // [NL][nthreads]
+  double *s_probs = s_acc + (FAST ? NL * nthreads : 0);   // [RT][K]
+  RS *s_row = (RS *)(s_probs + (NEGBIN ? RT * A.K : 0));  // [RT][32]
+  float *s_tab = (float *)(s_row + (SHARED_ROW ? RT * 32 : 0));
+  unsigned *s_valid = (unsigned *)(s_tab + (FAST ? (PT_DEG + 1) * PT_NODES : 0));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -302,6 +336,12 @@ k_fused(const FusedArgs A) {
     int f = i >> 5, j = i & 31;
     s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
   }
+  if (FAST) {
+    for (int i = threadIdx.x; i < (PT_DEG + 1) * PT_NODES; i += blockDim.x)
+      s_tab[i] = A.ptab[i];
+#pragma unroll
+    for (int l = 0; l < NL; l++) s_acc[l * nthreads + threadIdx.x] = 0.;
+  }
   Row row;
   row.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
   row.z1pt0 = site_ok && A.z1pt0 ? A.z1pt0[n] : -999.;
@@ -313,13 +353,30 @@ k_fused(const FusedArgs A) {
   const CT &Cp = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + A.M]);
   const double *ll = c_loglev + m * A.L1 + l0;
 
-  double acc[NL];
+  // exact path: FP64 accumulators (sum of rate*poe*T, or product of pnes);
+  // fast path: float32 accumulators per tile, flushed to FP64 in s_acc
+  double acc[FAST ? 1 : NL];
+  float facc[FAST ? NL : 1];
+  if (!FAST) {
 #pragma unroll
-  for (int l = 0; l < NL; l++) acc[l] = NEGBIN ? 1. : 0.;
+    for (int l = 0; l < NL; l++) acc[l] = NEGBIN ? 1. : 0.;
+  }
   unsigned long long kept = 0;
 
   const int64_t r_begin = (int64_t)blockIdx.y * A.rup_per_chunk;
   const int64_t r_end = min(A.U, r_begin + A.rup_per_chunk);
+
+#define LOAD_ROW(i)                                                        \
+  row.mag = s_rup[RF_MAG * RT + i];                                        \
+  row.rake = s_rup[RF_RAKE * RT + i];                                      \
+  row.dip = s_rup[RF_DIP * RT + i];                                        \
+  row.ztor = s_rup[RF_ZTOR * RT + i];                                      \
+  row.width = s_rup[RF_WIDTH * RT + i];                                    \
+  row.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];                          \
+  row.rrup = DGET(OQG_RRUP); row.rjb = DGET(OQG_RJB);                      \
+  row.rx = DGET(OQG_RX); row.ry0 = DGET(OQG_RY0);                          \
+  row.repi = DGET(OQG_REPI); row.rhypo = DGET(OQG_RHYPO);
+#define DGET(k) (((A.dmask >> (k)) & 1) ? s_dist[(A.plane_of[k] * RT + i) * 32 + lane] : 0.)
 
   for (int64_t r0 = r_begin; r0 < r_end; r0 += RT) {
     const int nr = (int)min((int64_t)RT, r_end - r0);
@@ -362,29 +419,41 @@ k_fused(const FusedArgs A) {
       if (A.count_pairs && lane == 0 && blockIdx.z == 0) kept += __popc(b);
     }
     __syncthreads();
+    // ---- the IMT-independent part of the model, once per pair, shared by
+    // the IMT warps through shared memory
+    if (SHARED_ROW) {
+      for (int i = warp; i < nr; i += nw) {
+        if (!((s_valid[i] >> lane) & 1)) continue;
+        LOAD_ROW(i)
+        s_row[i * 32 + lane] = Fam<F>::row(gs, Cp, row);
+      }
+      __syncthreads();
+    }
     // ---- GMPE + PoEs + accumulation: this warp's (IMT, level chunk)
     if (!unit_ok) continue;
+    if (FAST) {
+#pragma unroll
+      for (int l = 0; l < NL; l++) facc[l] = 0.f;
+    }
     for (int i = 0; i < nr; i++) {
       unsigned vm = s_valid[i];
       if (!((vm >> lane) & 1)) continue;
-      row.mag = s_rup[RF_MAG * RT + i];
-      row.rake = s_rup[RF_RAKE * RT + i];
-      row.dip = s_rup[RF_DIP * RT + i];
-      row.ztor = s_rup[RF_ZTOR * RT + i];
-      row.width = s_rup[RF_WIDTH * RT + i];
-      row.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];
-#define DGET(k) (((A.dmask >> (k)) & 1) ? s_dist[(A.plane_of[k] * RT + i) * 32 + lane] : 0.)
-      row.rrup = DGET(OQG_RRUP);
-      row.rjb = DGET(OQG_RJB);
-      row.rx = DGET(OQG_RX);
-      row.ry0 = DGET(OQG_RY0);
-      row.repi = DGET(OQG_REPI);
-      row.rhypo = DGET(OQG_RHYPO);
-#undef DGET
-      typename Fam<F>::R st = Fam<F>::row(gs, Cp, row);
+      LOAD_ROW(i)
+      RS st;
+      if (SHARED_ROW) st = s_row[i * 32 + lane];
+      else st = Fam<F>::row(gs, Cp, row);
       Out o = Fam<F>::imt(gs, C, Cp, row, st);
       const double inv = 1. / o.sig;
-      if (NEGBIN) {
+      if (FAST) {
+        // x = (tl - (l - mean) / sig) * xscale
+        const double xa = -inv * A.xscale;
+        const double xb = (A.tl + o.mean * inv) * A.xscale;
+        const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+          if (l < nl)
+            facc[l] = fmaf(rt, poe_table(s_tab, fma(ll[l], xa, xb)), facc[l]);
+      } else if (NEGBIN) {
         const double *pr = s_probs + i * A.K;
 #pragma unroll
         for (int l = 0; l < NL; l++)
@@ -404,7 +473,14 @@ k_fused(const FusedArgs A) {
           }
       }
     }
+    if (FAST) {
+#pragma unroll
+      for (int l = 0; l < NL; l++)
+        s_acc[l * nthreads + threadIdx.x] += (double)facc[l];
+    }
   }
+#undef DGET
+#undef LOAD_ROW
   if (A.count_pairs && lane == 0 && kept)
     atomicAdd(A.counters, kept);  // statistics only, not the map
   if (!unit_ok || !site_ok) return;
@@ -413,7 +489,9 @@ k_fused(const FusedArgs A) {
                 m * A.L1 + l0;
 #pragma unroll
   for (int l = 0; l < NL; l++)
-    if (l < nl) dst[l] = NEGBIN ? -log(acc[l]) : acc[l];
+    if (l < nl)
+      dst[l] = FAST ? s_acc[l * nthreads + threadIdx.x]
+                    : (NEGBIN ? -log(acc[l]) : acc[l]);
 }
 
 // partial sums -> map[sidx[n]][l][g]
@@ -450,6 +528,85 @@ __global__ void k_dfma(double *out, int iters) {
   if (s == 12345.678) out[0] = s;
 }
 
+// ---------------------------------------------------------- PoE table
+// F(t) = (Q(tl - t) - Q(tl)) / (1 - 2 Q(tl)), Q the upper tail of the normal
+static double poe_exact(double tl, double t) {
+  double qtl = 0.5 * erfc(tl * sqrt(0.5));
+  return (0.5 * erfc((tl - t) * sqrt(0.5)) - qtl) / (1. - 2. * qtl);
+}
+
+// least-squares-free polynomial interpolation: solve V c = f (n <= 6)
+static void solve_vandermonde(int n, const long double *u,
+                              const long double *f, long double *c) {
+  long double a[6][7];
+  for (int i = 0; i < n; i++) {
+    long double p = 1;
+    for (int j = 0; j < n; j++) { a[i][j] = p; p *= u[i]; }
+    a[i][n] = f[i];
+  }
+  for (int col = 0; col < n; col++) {
+    int piv = col;
+    for (int r = col + 1; r < n; r++)
+      if (fabsl(a[r][col]) > fabsl(a[piv][col])) piv = r;
+    for (int j = 0; j <= n; j++) std::swap(a[col][j], a[piv][j]);
+    for (int r = 0; r < n; r++) {
+      if (r == col) continue;
+      long double fct = a[r][col] / a[col][col];
+      for (int j = col; j <= n; j++) a[r][j] -= fct * a[col][j];
+    }
+  }
+  for (int i = 0; i < n; i++) c[i] = a[i][n] / a[i][i];
+}
+
+static float poe_table_host(const float *tab, double x64) {
+  float x = (float)x64;
+  x = fminf(fmaxf(x, 0.f), (float)(PT_NODES - 1));
+  int k = (int)nearbyintf(x);
+  float u = x - (float)k;
+  const float *c = tab + k;
+  float p = c[5 * PT_NODES];
+  for (int d = 4; d >= 0; d--) p = fmaf(p, u, c[d * PT_NODES]);
+  return fminf(fmaxf(p, 0.f), 1.f);
+}
+
+// builds the table for truncation level tl; returns the maximum relative
+// error over poe >= 1e-9 (absolute error below that), sampled densely
+static double build_poe_table(double tl, float *tab, double *xscale) {
+  const double pi = 3.14159265358979323846;
+  const double s = (PT_NODES - 1) / (2. * tl);
+  *xscale = s;
+  for (int k = 0; k < PT_NODES; k++) {
+    long double u[6], f[6], c[6] = {0, 0, 0, 0, 0, 0};
+    if (k == 0) {
+      // F(u / s) = u * G(u) on [0, .5]: zero constant term
+      for (int j = 0; j < 5; j++) {
+        u[j] = 0.25L + 0.25L * cosl((2 * j + 1) * pi / 10);
+        f[j] = poe_exact(tl, (double)u[j] / s) / u[j];
+      }
+      solve_vandermonde(5, u, f, c + 1);
+    } else {
+      for (int j = 0; j < 6; j++) {
+        u[j] = 0.5L * cosl((2 * j + 1) * pi / 12);
+        f[j] = poe_exact(tl, (k + (double)u[j]) / s);
+      }
+      solve_vandermonde(6, u, f, c);
+    }
+    for (int d = 0; d <= PT_DEG; d++) tab[d * PT_NODES + k] = (float)c[d];
+  }
+  double worst = 0.;
+  const int NS = 40000;
+  for (int i = 0; i <= NS; i++) {
+    double x = (PT_NODES - 1) * (double)i / NS;
+    // finer sampling near the truncation point
+    if (i < 2000) x = 0.5 * pow(10., -8. + 8. * i / 2000.);
+    double ex = poe_exact(tl, x / s);
+    double got = poe_table_host(tab, x);
+    double err = ex >= 1e-9 ? fabs(got / ex - 1.) : fabs(got - ex) / 1e-9;
+    worst = std::max(worst, err);
+  }
+  return worst;
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -483,7 +640,7 @@ void oqg_destroy(oqg_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (Buf *b : {&h->rup, &h->site, &h->part}) if (b->p) cudaFree(b->p);
+  for (Buf *b : {&h->rup, &h->site, &h->part, &h->ptab}) if (b->p) cudaFree(b->p);
   for (auto &b : h->stage) if (b.p) cudaFree(b.p);
   if (h->flag_dev) cudaFree(h->flag_dev);
   for (auto &ev : h->ev) cudaEventDestroy(ev);
@@ -566,6 +723,17 @@ int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
   h->truncation_level = truncation_level;
   h->phi_b = 0.5 * (1.0 + erf(truncation_level * sqrt(0.5)));
   h->const_dirty = true;
+  // fast PoE table: used when it reproduces the exact formula to 2e-6
+  h->fast_ok = false;
+  if (truncation_level >= 0.5 && truncation_level <= 8.) {
+    float tab[(PT_DEG + 1) * PT_NODES];
+    h->ptab_err = build_poe_table(truncation_level, tab, &h->xscale);
+    if (h->ptab_err <= 2e-6) {
+      if (reserve(h, h->ptab, sizeof(tab))) return 1;
+      CK(cudaMemcpy(h->ptab.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+      h->fast_ok = true;
+    }
+  }
   return 0;
 }
 
@@ -716,24 +884,30 @@ int oqg_update(oqg_handle *h, float *map, int N, const float *poes, int64_t P,
 
 }  // extern "C"
 
+template <int F, bool NB, bool FAST>
+static cudaError_t launch_fused2(const FusedArgs &A, dim3 grid, int threads,
+                                 size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(
+      k_fused<F, NB, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      (int)smem);
+  if (e != cudaSuccess) return e;
+  k_fused<F, NB, FAST><<<grid, threads, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
 template <int F>
 static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
-                                size_t smem, cudaStream_t st) {
-  cudaError_t e;
-  if (A.K) {
-    e = cudaFuncSetAttribute(k_fused<F, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-    if (e != cudaSuccess) return e;
-    k_fused<F, true><<<grid, threads, smem, st>>>(A);
-  } else {
-    e = cudaFuncSetAttribute(k_fused<F, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-    if (e != cudaSuccess) return e;
-    k_fused<F, false><<<grid, threads, smem, st>>>(A);
-  }
-  return cudaGetLastError();
+                                cudaStream_t st) {
+  typedef typename Fam<F>::R RS;
+  const bool fast = A.ptab != nullptr && A.K == 0;
+  size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
+                 NF_SITE * 32 + (fast ? NL * threads : 0) +
+                 (A.K ? RT * A.K : 0)) * 8 +
+                (sizeof(RS) >= 8 ? RT * 32 * sizeof(RS) : 0) +
+                (fast ? (PT_DEG + 1) * PT_NODES * 4 : 0) + RT * 4;
+  if (A.K) return launch_fused2<F, true, false>(A, grid, threads, smem, st);
+  if (fast) return launch_fused2<F, false, true>(A, grid, threads, smem, st);
+  return launch_fused2<F, false, false>(A, grid, threads, smem, st);
 }
 
 extern "C" {
@@ -765,6 +939,8 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
   A.nlc = (L1 + NL - 1) / NL;
   A.lpc = (L1 + A.nlc - 1) / A.nlc;
   A.nunits = M * A.nlc;
+  A.ptab = (h->fast_ok && !h->exact_poe) ? (const float *)h->ptab.p : nullptr;
+  A.tl = h->truncation_level; A.xscale = h->xscale;
   A.mindist = mindist; A.itime = itime; A.phi_b = h->phi_b;
   A.inv_norm = 1. / (h->phi_b * 2. - 1.);
 
@@ -801,20 +977,18 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
     for (int k = 0; k < 6; k++)
       if ((A.dmask >> k) & 1) A.plane_of[k] = A.nplanes++;
     A.count_pairs = counters && g == 0;  // blockIdx.z == 0 only
-    size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
-                   NF_SITE * 32 + (K ? RT * K : 0)) * 8 + RT * 4;
     dim3 grid(tiles, (unsigned)rc, ugroups);
     // only blockIdx.z == 0 counts pairs
     cudaError_t e = cudaSuccess;
     CK(cudaEventRecord(h->ev[2 * g], h->stream));
     switch (gs.family) {
-      case OQG_BSSA14: e = launch_fused<OQG_BSSA14>(A, grid, 32 * nw, smem, h->stream); break;
-      case OQG_CY14: e = launch_fused<OQG_CY14>(A, grid, 32 * nw, smem, h->stream); break;
-      case OQG_ASK14: e = launch_fused<OQG_ASK14>(A, grid, 32 * nw, smem, h->stream); break;
-      case OQG_CB14: e = launch_fused<OQG_CB14>(A, grid, 32 * nw, smem, h->stream); break;
-      case OQG_BA08: e = launch_fused<OQG_BA08>(A, grid, 32 * nw, smem, h->stream); break;
-      case OQG_AB06: e = launch_fused<OQG_AB06>(A, grid, 32 * nw, smem, h->stream); break;
-      case OQG_AKKAR14: e = launch_fused<OQG_AKKAR14>(A, grid, 32 * nw, smem, h->stream); break;
+      case OQG_BSSA14: e = launch_fused<OQG_BSSA14>(A, grid, 32 * nw, h->stream); break;
+      case OQG_CY14: e = launch_fused<OQG_CY14>(A, grid, 32 * nw, h->stream); break;
+      case OQG_ASK14: e = launch_fused<OQG_ASK14>(A, grid, 32 * nw, h->stream); break;
+      case OQG_CB14: e = launch_fused<OQG_CB14>(A, grid, 32 * nw, h->stream); break;
+      case OQG_BA08: e = launch_fused<OQG_BA08>(A, grid, 32 * nw, h->stream); break;
+      case OQG_AB06: e = launch_fused<OQG_AB06>(A, grid, 32 * nw, h->stream); break;
+      case OQG_AKKAR14: e = launch_fused<OQG_AKKAR14>(A, grid, 32 * nw, h->stream); break;
     }
     CK(cudaEventRecord(h->ev[2 * g + 1], h->stream));
     h->launches++;
@@ -885,6 +1059,17 @@ int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
 }
 
 unsigned long long oqg_launch_count(oqg_handle *h) { return h->launches; }
+
+int oqg_set_exact_poe(oqg_handle *h, int on) {
+  h->exact_poe = on != 0;
+  return 0;
+}
+
+int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err) {
+  *in_use = h->fast_ok && !h->exact_poe;
+  *max_rel_err = h->ptab_err;
+  return 0;
+}
 
 int oqg_last_fused_ms(oqg_handle *h, float *ms, int cap) {
   if (cudaSetDevice(h->device) != cudaSuccess) return -1;

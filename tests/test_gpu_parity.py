@@ -441,3 +441,43 @@ def test_map_on_device_and_sidx(oq):
         cm.hazard_planar(half, oq.contexts.PlanarRuptures(
             pla[sl], r['mag'][sl]), sc)
     np.testing.assert_allclose(half.array, full.array, rtol=1e-6)
+
+
+def test_fast_poe_table_vs_exact(oq):
+    """The float32 polynomial table of the truncated-normal survival
+    function used by the fused kernel against the FP64 erf formula: the
+    table is in use for truncation_level=3 with a measured error <= 2e-6,
+    both paths agree on the map, and an untabulated truncation level (99)
+    falls back to the exact formula"""
+    rng = np.random.default_rng(99)
+    U, N = 150, 130
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng, sentinels=True)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    L_ = oq._lib.lib()
+    for tl, expect_table in ((3., True), (2., True), (99., False)):
+        cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+            imtls=imtls, truncation_level=tl, investigation_time=50.))
+        h = cm.handle()
+        in_use, err = ctypes.c_int(0), ctypes.c_double(0)
+        L_.oqg_poe_table_info(h._h, ctypes.byref(in_use), ctypes.byref(err))
+        assert bool(in_use.value) == expect_table, (tl, err.value)
+        if expect_table:
+            assert err.value <= 2e-6
+        fast = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+        cm.hazard_planar(fast, src, sc)
+        L_.oqg_set_exact_poe(h._h, 1)
+        try:
+            exact = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+            cm.hazard_planar(exact, src, sc)
+        finally:
+            L_.oqg_set_exact_poe(h._h, 0)
+        big = exact.array > 1e-12
+        np.testing.assert_allclose(fast.array[big], exact.array[big],
+                                   rtol=5e-6)
