@@ -4,7 +4,8 @@ import os
 import ctypes as C
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, 'liboqg.so')
+# OQG_LIB selects another build of the same library (A/B experiments)
+LIBPATH = os.environ.get('OQG_LIB') or os.path.join(HERE, 'liboqg.so')
 
 KMAX = 56
 PLANAR_LEN = 42

@@ -27,19 +27,25 @@
 #include "oqg_gmpe.cuh"
 #include "oqg_geo.cuh"
 #include "oqg_poe.cuh"
+#include "oqg_fast.cuh"
 
 using namespace oqg;
 
-#define OQG_MAX_SLOTS 112
+#define OQG_MAX_SLOTS 96
 #define OQG_MAX_G 16
 #define OQG_MAX_LEVELS 1024
 #define NL 20          // level accumulators per thread in the fused kernel
-#define RT 32          // ruptures per shared-memory tile
-#define NWMAX 8        // warps (units) per CTA in the fused kernel
+#define RT 16          // ruptures per shared-memory tile
+#define NWMAX 7        // warps (units) per CTA in the fused kernel
+#ifndef MINB
+#define MINB 3         // CTAs per SM the fused kernel is compiled for
+#endif
 #define MAXPLANES 6
 
 __constant__ double c_coef[OQG_MAX_SLOTS][OQG_KMAX];
-__constant__ double c_loglev[OQG_MAX_LEVELS];
+// [0, MAX_LEVELS): loglevels[M][L1]; [MAX_LEVELS, 2 MAX_LEVELS): the same by
+// fused-kernel unit, [unit][NL] padded with +inf
+__constant__ double c_loglev[2 * OQG_MAX_LEVELS];
 __constant__ oqg_gsim c_gsim[OQG_MAX_G];
 
 // ------------------------------------------------------------------ handle
@@ -54,7 +60,7 @@ struct oqg_handle {
   std::string err;
   int G = 0, M = 0, L1 = 0;
   std::vector<oqg_gsim> gsims;
-  std::vector<double> coef, loglev;
+  std::vector<double> coef, loglev, loglev_pad;
   double truncation_level = 0, phi_b = 0;
   bool const_dirty = true;
   unsigned long long launches = 0;
@@ -105,6 +111,11 @@ static int upload_const(oqg_handle *h) {
   if (!h->loglev.empty())
     CK(cudaMemcpyToSymbolAsync(c_loglev, h->loglev.data(),
                                h->loglev.size() * sizeof(double), 0,
+                               cudaMemcpyHostToDevice, h->stream));
+  if (!h->loglev_pad.empty())
+    CK(cudaMemcpyToSymbolAsync(c_loglev, h->loglev_pad.data(),
+                               h->loglev_pad.size() * sizeof(double),
+                               OQG_MAX_LEVELS * sizeof(double),
                                cudaMemcpyHostToDevice, h->stream));
   // the host vectors must stay alive until the copies ran: they are members
   // and only replaced by set_* calls, which synchronise first
@@ -293,7 +304,9 @@ __device__ __forceinline__ float poe_table(const float *s_tab, double x64) {
   x = fminf(fmaxf(x, 0.f), (float)(PT_NODES - 1));
   float y = x + 8388608.f;              // 2^23: round to nearest integer
   float u = x - (y - 8388608.f);
-  const float *c = s_tab + (__float_as_int(y) & (PT_NODES - 1));
+  // the low mantissa bits of y are the node: s_tab + node, with the bits of
+  // 2^23 (0x4b000000) folded into the base pointer (one LEA)
+  const float *c = (s_tab - 0x4b000000) + __float_as_int(y);
   float p = c[5 * PT_NODES];
   p = fmaf(p, u, c[4 * PT_NODES]);
   p = fmaf(p, u, c[3 * PT_NODES]);
@@ -302,25 +315,44 @@ __device__ __forceinline__ float poe_table(const float *s_tab, double x64) {
   return __saturatef(fmaf(p, u, c[0]));
 }
 
+template <typename T>
+__device__ __forceinline__ void st_soa(double *base, int stride, const T &v) {
+  const double *a = reinterpret_cast<const double *>(&v);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 8); k++) base[k * stride] = a[k];
+}
+
+template <typename T>
+__device__ __forceinline__ T ld_soa(const double *base, int stride) {
+  T v;
+  double *a = reinterpret_cast<double *>(&v);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 8); k++) a[k] = base[k * stride];
+  return v;
+}
+
 template <int F, bool NEGBIN, bool FAST>
-__global__ void __launch_bounds__(32 * NWMAX, 2)
+__global__ void __launch_bounds__(32 * NWMAX, MINB)
 k_fused(const FusedArgs A) {
-  typedef typename Fam<F>::C CT;
-  typedef typename Fam<F>::R RS;
-  constexpr bool SHARED_ROW = sizeof(RS) >= 8;
+  typedef Fast<F> FF;
+  typedef typename FF::C CT;
+  typedef typename FF::S ST;
+  typedef typename FF::Q QT;
+  typedef typename FF::P PT;
+  constexpr int QW = FF::HAS_Q ? sizeof(QT) / 8 : 0;   // doubles
+  constexpr int PW = FF::HAS_P ? sizeof(PT) / 8 : 0;
   extern __shared__ double smem[];
-  const int nthreads = blockDim.x;
+  const int nw = blockDim.x >> 5;
   double *s_rup = smem;                            // [NF_RUP][RT]
   double *s_dist = s_rup + NF_RUP * RT;            // [nplanes][RT][32]
   double *s_site = s_dist + A.nplanes * RT * 32;   // [NF_SITE][32]
-  double *s_acc = s_site + NF_SITE * 32;           // [NL][nthreads]
-  double *s_probs = s_acc + (FAST ? NL * nthreads : 0);   // [RT][K]
-  RS *s_row = (RS *)(s_probs + (NEGBIN ? RT * A.K : 0));  // [RT][32]
-  float *s_tab = (float *)(s_row + (SHARED_ROW ? RT * 32 : 0));
+  double *s_q = s_site + NF_SITE * 32;             // [nw + 1][RT][QW]
+  double *s_p = s_q + (nw + 1) * RT * QW;          // [PW][RT][32]
+  double *s_probs = s_p + PW * RT * 32;            // [RT][K]
+  float *s_tab = (float *)(s_probs + (NEGBIN ? RT * A.K : 0));
   unsigned *s_valid = (unsigned *)(s_tab + (FAST ? (PT_DEG + 1) * PT_NODES : 0));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = blockDim.x >> 5;
   const int site0 = blockIdx.x * 32;
   const int n = site0 + lane;
   const bool site_ok = n < A.N;
@@ -336,28 +368,36 @@ k_fused(const FusedArgs A) {
     int f = i >> 5, j = i & 31;
     s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
   }
-  if (FAST) {
+  if (FAST)
     for (int i = threadIdx.x; i < (PT_DEG + 1) * PT_NODES; i += blockDim.x)
       s_tab[i] = A.ptab[i];
-#pragma unroll
-    for (int l = 0; l < NL; l++) s_acc[l * nthreads + threadIdx.x] = 0.;
-  }
-  Row row;
-  row.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
-  row.z1pt0 = site_ok && A.z1pt0 ? A.z1pt0[n] : -999.;
-  row.z2pt5 = site_ok && A.z2pt5 ? A.z2pt5[n] : -999.;
-  row.vs30measured = site_ok && A.vs30measured ? A.vs30measured[n] != 0 : false;
+  SiteIn si;
+  si.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
+  si.z1pt0 = site_ok && A.z1pt0 ? A.z1pt0[n] : -999.;
+  si.z2pt5 = site_ok && A.z2pt5 ? A.z2pt5[n] : -999.;
+  si.vs30measured = site_ok && A.vs30measured ? A.vs30measured[n] != 0 : false;
 
   const oqg_gsim &gs = c_gsim[A.g];
   const CT &C = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + m]);
   const CT &Cp = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + A.M]);
-  const double *ll = c_loglev + m * A.L1 + l0;
+  // log levels of this unit, padded to NL with +inf (poe = 0)
+  const double *ll = c_loglev + OQG_MAX_LEVELS + (unit_ok ? unit : 0) * NL;
+  const ST ss = FF::site(gs, C, si);      // this IMT
+  const ST sp = FF::site(gs, Cp, si);     // PGA, for the shared pair state
 
   // exact path: FP64 accumulators (sum of rate*poe*T, or product of pnes);
-  // fast path: float32 accumulators per tile, flushed to FP64 in s_acc
+  // fast path: float32 accumulators per tile, flushed to the FP64 partial
+  // sums of this thread in global memory (L2 resident)
   double acc[FAST ? 1 : NL];
   float facc[FAST ? NL : 1];
-  if (!FAST) {
+  const int L = A.M * A.L1;
+  double *dst = A.part + (((int64_t)blockIdx.y * A.G + A.g) * A.N +
+                          (site_ok ? n : 0)) * L + m * A.L1 + l0;
+  const bool writer = unit_ok && site_ok;
+  if (FAST) {
+    if (writer)
+      for (int l = 0; l < nl; l++) dst[l] = 0.;
+  } else {
 #pragma unroll
     for (int l = 0; l < NL; l++) acc[l] = NEGBIN ? 1. : 0.;
   }
@@ -366,17 +406,19 @@ k_fused(const FusedArgs A) {
   const int64_t r_begin = (int64_t)blockIdx.y * A.rup_per_chunk;
   const int64_t r_end = min(A.U, r_begin + A.rup_per_chunk);
 
-#define LOAD_ROW(i)                                                        \
-  row.mag = s_rup[RF_MAG * RT + i];                                        \
-  row.rake = s_rup[RF_RAKE * RT + i];                                      \
-  row.dip = s_rup[RF_DIP * RT + i];                                        \
-  row.ztor = s_rup[RF_ZTOR * RT + i];                                      \
-  row.width = s_rup[RF_WIDTH * RT + i];                                    \
-  row.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];                          \
-  row.rrup = DGET(OQG_RRUP); row.rjb = DGET(OQG_RJB);                      \
-  row.rx = DGET(OQG_RX); row.ry0 = DGET(OQG_RY0);                          \
-  row.repi = DGET(OQG_REPI); row.rhypo = DGET(OQG_RHYPO);
 #define DGET(k) (((A.dmask >> (k)) & 1) ? s_dist[(A.plane_of[k] * RT + i) * 32 + lane] : 0.)
+#define LOAD_PAIR(i)                                                       \
+  RupIn ri;                                                                \
+  ri.mag = s_rup[RF_MAG * RT + i];                                         \
+  ri.rake = s_rup[RF_RAKE * RT + i];                                       \
+  ri.dip = s_rup[RF_DIP * RT + i];                                         \
+  ri.ztor = s_rup[RF_ZTOR * RT + i];                                       \
+  ri.width = s_rup[RF_WIDTH * RT + i];                                     \
+  ri.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];                           \
+  Dist dd;                                                                 \
+  dd.rrup = DGET(OQG_RRUP); dd.rjb = DGET(OQG_RJB);                        \
+  dd.rx = DGET(OQG_RX); dd.ry0 = DGET(OQG_RY0);                            \
+  dd.repi = DGET(OQG_REPI); dd.rhypo = DGET(OQG_RHYPO);
 
   for (int64_t r0 = r_begin; r0 < r_end; r0 += RT) {
     const int nr = (int)min((int64_t)RT, r_end - r0);
@@ -418,14 +460,32 @@ k_fused(const FusedArgs A) {
       if (lane == 0) s_valid[i] = b;
       if (A.count_pairs && lane == 0 && blockIdx.z == 0) kept += __popc(b);
     }
+    // ---- rupture-only part of the model: lane = rupture, one IMT per
+    // warp; the last warp also does the PGA row
+    if (FF::HAS_Q && lane < nr) {
+      const int i = lane;
+      RupIn ri;
+      ri.mag = s_rup[RF_MAG * RT + i];
+      ri.rake = s_rup[RF_RAKE * RT + i];
+      ri.dip = s_rup[RF_DIP * RT + i];
+      ri.ztor = s_rup[RF_ZTOR * RT + i];
+      ri.width = s_rup[RF_WIDTH * RT + i];
+      ri.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];
+      st_soa(s_q + (warp * RT + i) * QW, 1, FF::rup(gs, C, ri));
+      if (warp == nw - 1)
+        st_soa(s_q + (nw * RT + i) * QW, 1, FF::rup(gs, Cp, ri));
+    }
     __syncthreads();
     // ---- the IMT-independent part of the model, once per pair, shared by
     // the IMT warps through shared memory
-    if (SHARED_ROW) {
+    if (FF::HAS_P) {
       for (int i = warp; i < nr; i += nw) {
         if (!((s_valid[i] >> lane) & 1)) continue;
-        LOAD_ROW(i)
-        s_row[i * 32 + lane] = Fam<F>::row(gs, Cp, row);
+        LOAD_PAIR(i)
+        QT qp;
+        if (FF::HAS_Q) qp = ld_soa<QT>(s_q + (nw * RT + i) * QW, 1);
+        st_soa(s_p + i * 32 + lane, RT * 32,
+               FF::pair(gs, Cp, sp, qp, ri, si, dd));
       }
       __syncthreads();
     }
@@ -438,60 +498,53 @@ k_fused(const FusedArgs A) {
     for (int i = 0; i < nr; i++) {
       unsigned vm = s_valid[i];
       if (!((vm >> lane) & 1)) continue;
-      LOAD_ROW(i)
-      RS st;
-      if (SHARED_ROW) st = s_row[i * 32 + lane];
-      else st = Fam<F>::row(gs, Cp, row);
-      Out o = Fam<F>::imt(gs, C, Cp, row, st);
-      const double inv = 1. / o.sig;
+      LOAD_PAIR(i)
+      QT q;
+      PT pp;
+      if (FF::HAS_Q) q = ld_soa<QT>(s_q + (warp * RT + i) * QW, 1);
+      if (FF::HAS_P) pp = ld_soa<PT>(s_p + i * 32 + lane, RT * 32);
+      else pp = FF::pair(gs, Cp, sp, q, ri, si, dd);
+      double mean, sig;
+      FF::eval(gs, C, Cp, ss, q, pp, ri, si, dd, mean, sig);
+      const double inv = 1. / sig;
       if (FAST) {
         // x = (tl - (l - mean) / sig) * xscale
         const double xa = -inv * A.xscale;
-        const double xb = (A.tl + o.mean * inv) * A.xscale;
+        const double xb = (A.tl + mean * inv) * A.xscale;
         const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
 #pragma unroll
         for (int l = 0; l < NL; l++)
-          if (l < nl)
-            facc[l] = fmaf(rt, poe_table(s_tab, fma(ll[l], xa, xb)), facc[l]);
+          facc[l] = fmaf(rt, poe_table(s_tab, fma(ll[l], xa, xb)), facc[l]);
       } else if (NEGBIN) {
         const double *pr = s_probs + i * A.K;
 #pragma unroll
-        for (int l = 0; l < NL; l++)
-          if (l < nl) {
-            double poe = truncnorm_sf(A.phi_b, A.inv_norm,
-                                      (ll[l] - o.mean) * inv);
-            acc[l] *= A.itime == 0. ? 1. - poe : pne_from_pmf(pr, A.K, poe);
-          }
+        for (int l = 0; l < NL; l++) {
+          double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
+          acc[l] *= A.itime == 0. ? 1. - poe : pne_from_pmf(pr, A.K, poe);
+        }
       } else {
         const double rt = s_rup[RF_RATE * RT + i] * A.itime;
 #pragma unroll
-        for (int l = 0; l < NL; l++)
-          if (l < nl) {
-            double poe = truncnorm_sf(A.phi_b, A.inv_norm,
-                                      (ll[l] - o.mean) * inv);
-            acc[l] = fma(rt, poe, acc[l]);
-          }
+        for (int l = 0; l < NL; l++) {
+          double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
+          acc[l] = fma(rt, poe, acc[l]);
+        }
       }
     }
-    if (FAST) {
+    if (FAST && site_ok) {
 #pragma unroll
       for (int l = 0; l < NL; l++)
-        s_acc[l * nthreads + threadIdx.x] += (double)facc[l];
+        if (l < nl) dst[l] += (double)facc[l];
     }
   }
 #undef DGET
-#undef LOAD_ROW
+#undef LOAD_PAIR
   if (A.count_pairs && lane == 0 && kept)
     atomicAdd(A.counters, kept);  // statistics only, not the map
-  if (!unit_ok || !site_ok) return;
-  const int L = A.M * A.L1;
-  double *dst = A.part + (((int64_t)blockIdx.y * A.G + A.g) * A.N + n) * L +
-                m * A.L1 + l0;
+  if (FAST || !writer) return;
 #pragma unroll
   for (int l = 0; l < NL; l++)
-    if (l < nl)
-      dst[l] = FAST ? s_acc[l * nthreads + threadIdx.x]
-                    : (NEGBIN ? -log(acc[l]) : acc[l]);
+    if (l < nl) dst[l] = NEGBIN ? -log(acc[l]) : acc[l];
 }
 
 // partial sums -> map[sidx[n]][l][g]
@@ -689,7 +742,7 @@ int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
   if (G < 1 || G > OQG_MAX_G) return fail(h, "G must be in 1..16");
   if (M < 1 || G * (M + 1) > OQG_MAX_SLOTS)
     return fail(h, "too many (gsim, IMT) pairs for the coefficient table "
-                   "(G * (M + 1) <= 112)");
+                   "(G * (M + 1) <= 96)");
   for (int g = 0; g < G; g++) {
     const oqg_gsim &s = gsims[g];
     if (s.family < 0 || s.family >= OQG_NFAMILIES)
@@ -720,6 +773,16 @@ int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
   if (h->M && h->M != M) return fail(h, "set_levels: M differs from set_gsims");
   h->M = M; h->L1 = L1;
   h->loglev.assign(loglevels, loglevels + (size_t)M * L1);
+  {
+    int nlc = (L1 + NL - 1) / NL, lpc = (L1 + nlc - 1) / nlc;
+    if (M * nlc * NL > OQG_MAX_LEVELS)
+      return fail(h, "too many levels for the fused kernel");
+    h->loglev_pad.assign((size_t)M * nlc * NL, INFINITY);
+    for (int m = 0; m < M; m++)
+      for (int l = 0; l < L1; l++)
+        h->loglev_pad[(size_t)(m * nlc + l / lpc) * NL + l % lpc] =
+            loglevels[m * L1 + l];
+  }
   h->truncation_level = truncation_level;
   h->phi_b = 0.5 * (1.0 + erf(truncation_level * sqrt(0.5)));
   h->const_dirty = true;
@@ -898,12 +961,14 @@ static cudaError_t launch_fused2(const FusedArgs &A, dim3 grid, int threads,
 template <int F>
 static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
                                 cudaStream_t st) {
-  typedef typename Fam<F>::R RS;
+  typedef Fast<F> FF;
   const bool fast = A.ptab != nullptr && A.K == 0;
+  const int nw = threads / 32;
+  const int QW = FF::HAS_Q ? sizeof(typename FF::Q) / 8 : 0;
+  const int PW = FF::HAS_P ? sizeof(typename FF::P) / 8 : 0;
   size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
-                 NF_SITE * 32 + (fast ? NL * threads : 0) +
-                 (A.K ? RT * A.K : 0)) * 8 +
-                (sizeof(RS) >= 8 ? RT * 32 * sizeof(RS) : 0) +
+                 NF_SITE * 32 + (size_t)(nw + 1) * RT * QW +
+                 (size_t)PW * RT * 32 + (A.K ? RT * A.K : 0)) * 8 +
                 (fast ? (PT_DEG + 1) * PT_NODES * 4 : 0) + RT * 4;
   if (A.K) return launch_fused2<F, true, false>(A, grid, threads, smem, st);
   if (fast) return launch_fused2<F, false, true>(A, grid, threads, smem, st);
@@ -950,7 +1015,7 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
   int tiles = (N + 31) / 32;
   // rupture chunks: enough CTAs for ~8 waves of 2 CTAs per SM, rounded to
   // whole shared-memory tiles, so that the tail wave is small
-  int64_t ctas_wanted = (int64_t)h->sm_count * 2 * 8;
+  int64_t ctas_wanted = (int64_t)h->sm_count * MINB * 8;
   int64_t rc = (ctas_wanted + (int64_t)tiles * ugroups - 1) /
                ((int64_t)tiles * ugroups);
   int64_t max_rc = (U + RT - 1) / RT;
