@@ -38,7 +38,7 @@ using namespace oqg;
 #define RT 16          // ruptures per shared-memory tile
 #define NWMAX 7        // warps (units) per CTA in the fused kernel
 #ifndef MINB
-#define MINB 3         // CTAs per SM the fused kernel is compiled for
+#define MINB 4         // CTAs per SM the fused kernel is compiled for
 #endif
 #define MAXPLANES 6
 
@@ -65,7 +65,8 @@ struct oqg_handle {
   bool const_dirty = true;
   unsigned long long launches = 0;
   Buf rup, site, part, ptab, stage[12];
-  bool fast_ok = false, exact_poe = false;
+  bool fast_ok = false, exact_poe = false, sorted = false;
+  int pt_nodes = 0;
   double ptab_err = 0., xscale = 0.;
   int *flag_dev = nullptr;
   cudaEvent_t ev[2 * OQG_MAX_G + 2];
@@ -264,16 +265,24 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 }
 
 // ------------------------------------------------------------------ fused
-// Fast PoE: poe as a function of x = (tl - z) * PT_NODES_M1 / (2 tl) in
-// [0, PT_NODES - 1] is tabulated as one degree-5 polynomial per node k =
+// Fast PoE: poe as a function of x = (tl - z) * (nodes - 1) / (2 tl) in
+// [0, nodes - 1] is tabulated as one degree-4 polynomial per node k =
 // round(x) in u = x - k in [-.5, .5] (float32 coefficients built in float64
-// by oqg_set_levels); node 0 has a zero constant term, so that the relative
-// accuracy is kept as poe -> 0 (z -> truncation level), where the textbook
-// formula cancels.  x itself is computed in float64.  The table is
-// [PT_DEG + 1][PT_NODES] floats in shared memory: lanes with different nodes
-// hit different banks, lanes with the same node broadcast.
-#define PT_NODES 32
-#define PT_DEG 5
+// by oqg_set_levels; 64 or 128 nodes, whichever reproduces the exact formula
+// to 2e-6); node 0 has a zero constant term, so that the relative accuracy
+// is kept as poe -> 0 (z -> truncation level), where the textbook formula
+// cancels.  x itself is computed in float64.  The table is [nodes][9] floats
+// in shared memory: lanes whose nodes are less than 32 apart hit different
+// banks, lanes with the same node broadcast.
+#define PT_DEG 4
+#define PT_STRIDE 9       // floats per node: odd, so that 32 consecutive
+                          // nodes fall in 32 different banks
+#define PT_MAXNODES 128
+#ifndef FLUSH_TILES
+#define FLUSH_TILES 4
+#endif
+//    // float32 partial sums are flushed to FP64 every
+                          // FLUSH_TILES * RT ruptures
 
 struct FusedArgs {
   const double *rup;      // [NF_RUP][U]
@@ -281,7 +290,9 @@ struct FusedArgs {
   const double *site;     // [NF_SITE][N]
   const double *vs30, *z1pt0, *z2pt5;
   const uint8_t *vs30measured;
-  const float *ptab;      // [PT_DEG + 1][PT_NODES] or null (exact FP64 PoEs)
+  const float *ptab;      // [nodes][PT_STRIDE] or null (exact FP64 PoEs)
+  int pt_nodes;
+  unsigned pt_bias;
   double *part;           // [RC][G][N][L]
   unsigned long long *counters;
   int64_t U;
@@ -296,23 +307,29 @@ struct FusedArgs {
   int nplanes;
   int plane_of[OQG_NDIST];
   int count_pairs;
+  int sorted;             // the levels of every IMT are increasing
   double mindist, itime, phi_b, inv_norm, tl, xscale;
 };
 
-__device__ __forceinline__ float poe_table(const float *s_tab, double x64) {
+// tab32: shared-window address of the table minus (0x4b000000 * 36), so
+// that tab32 + bits(x + 2^23) * 36 is the address of node round(x)
+__device__ __forceinline__ float poe_table(unsigned tab32, float xmax,
+                                           double x64) {
   float x = (float)x64;
-  x = fminf(fmaxf(x, 0.f), (float)(PT_NODES - 1));
+  x = fminf(fmaxf(x, 0.f), xmax);
   float y = x + 8388608.f;              // 2^23: round to nearest integer
   float u = x - (y - 8388608.f);
-  // the low mantissa bits of y are the node: s_tab + node, with the bits of
-  // 2^23 (0x4b000000) folded into the base pointer (one LEA)
-  const float *c = (s_tab - 0x4b000000) + __float_as_int(y);
-  float p = c[5 * PT_NODES];
-  p = fmaf(p, u, c[4 * PT_NODES]);
-  p = fmaf(p, u, c[3 * PT_NODES]);
-  p = fmaf(p, u, c[2 * PT_NODES]);
-  p = fmaf(p, u, c[1 * PT_NODES]);
-  return __saturatef(fmaf(p, u, c[0]));
+  unsigned a = tab32 + __float_as_uint(y) * (PT_STRIDE * 4);
+  float c0, c1, c2, c3, c4;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(c0) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+4];" : "=f"(c1) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+8];" : "=f"(c2) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+12];" : "=f"(c3) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+16];" : "=f"(c4) : "r"(a));
+  float p = fmaf(c4, u, c3);
+  p = fmaf(p, u, c2);
+  p = fmaf(p, u, c1);
+  return __saturatef(fmaf(p, u, c0));
 }
 
 template <typename T>
@@ -350,7 +367,7 @@ k_fused(const FusedArgs A) {
   double *s_p = s_q + (nw + 1) * RT * QW;          // [PW][RT][32]
   double *s_probs = s_p + PW * RT * 32;            // [RT][K]
   float *s_tab = (float *)(s_probs + (NEGBIN ? RT * A.K : 0));
-  unsigned *s_valid = (unsigned *)(s_tab + (FAST ? (PT_DEG + 1) * PT_NODES : 0));
+  unsigned *s_valid = (unsigned *)(s_tab + (FAST ? A.pt_nodes * PT_STRIDE : 0));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int site0 = blockIdx.x * 32;
@@ -369,8 +386,13 @@ k_fused(const FusedArgs A) {
     s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
   }
   if (FAST)
-    for (int i = threadIdx.x; i < (PT_DEG + 1) * PT_NODES; i += blockDim.x)
+    for (int i = threadIdx.x; i < A.pt_nodes * PT_STRIDE; i += blockDim.x)
       s_tab[i] = A.ptab[i];
+  // pt_bias = -(0x4b000000 * 36) mod 2^32 comes in as a kernel argument: as
+  // a literal the compiler splits it off again and adds it back before
+  // every load
+  const unsigned tab32 = (unsigned)__cvta_generic_to_shared(s_tab) + A.pt_bias;
+  const float xmax = (float)(A.pt_nodes - 1);
   SiteIn si;
   si.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
   si.z1pt0 = site_ok && A.z1pt0 ? A.z1pt0[n] : -999.;
@@ -402,6 +424,11 @@ k_fused(const FusedArgs A) {
     for (int l = 0; l < NL; l++) acc[l] = NEGBIN ? 1. : 0.;
   }
   unsigned long long kept = 0;
+  if (FAST) {
+#pragma unroll
+    for (int l = 0; l < NL; l++) facc[l] = 0.f;
+  }
+  int tiles_left = FLUSH_TILES;
 
   const int64_t r_begin = (int64_t)blockIdx.y * A.rup_per_chunk;
   const int64_t r_end = min(A.U, r_begin + A.rup_per_chunk);
@@ -491,10 +518,6 @@ k_fused(const FusedArgs A) {
     }
     // ---- GMPE + PoEs + accumulation: this warp's (IMT, level chunk)
     if (!unit_ok) continue;
-    if (FAST) {
-#pragma unroll
-      for (int l = 0; l < NL; l++) facc[l] = 0.f;
-    }
     for (int i = 0; i < nr; i++) {
       unsigned vm = s_valid[i];
       if (!((vm >> lane) & 1)) continue;
@@ -504,17 +527,30 @@ k_fused(const FusedArgs A) {
       if (FF::HAS_Q) q = ld_soa<QT>(s_q + (warp * RT + i) * QW, 1);
       if (FF::HAS_P) pp = ld_soa<PT>(s_p + i * 32 + lane, RT * 32);
       else pp = FF::pair(gs, Cp, sp, q, ri, si, dd);
-      double mean, sig;
-      FF::eval(gs, C, Cp, ss, q, pp, ri, si, dd, mean, sig);
-      const double inv = 1. / sig;
+      double mean, sig, inv;
+      FF::eval(gs, C, Cp, ss, q, pp, ri, si, dd, mean, sig, inv);
       if (FAST) {
         // x = (tl - (l - mean) / sig) * xscale
         const double xa = -inv * A.xscale;
         const double xb = (A.tl + mean * inv) * A.xscale;
         const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
+        // levels are sorted: from the first one at or above mean + tl * sig
+        // for every lane of the warp on, all the PoEs are zero (the padding
+        // levels are +inf).  The threshold is reduced over the warp in
+        // float32, rounded up.
+        // (one REDUX over the active lanes on the order-preserving integer
+        // image of the float)
+        int key = __float_as_int(__double2float_ru(fma(A.tl, sig, mean)));
+        key ^= (key >> 31) & 0x7fffffff;
+        key = __reduce_max_sync(vm, key);
+        key ^= (key >> 31) & 0x7fffffff;
+        const double thr_w = A.sorted ? (double)__int_as_float(key) : INFINITY;
 #pragma unroll
-        for (int l = 0; l < NL; l++)
-          facc[l] = fmaf(rt, poe_table(s_tab, fma(ll[l], xa, xb)), facc[l]);
+        for (int l = 0; l < NL; l++) {
+          const double lv = ll[l];
+          if (lv >= thr_w) break;
+          facc[l] = fmaf(rt, poe_table(tab32, xmax, fma(lv, xa, xb)), facc[l]);
+        }
       } else if (NEGBIN) {
         const double *pr = s_probs + i * A.K;
 #pragma unroll
@@ -531,10 +567,15 @@ k_fused(const FusedArgs A) {
         }
       }
     }
-    if (FAST && site_ok) {
+    if (FAST && (--tiles_left == 0 || r0 + RT >= r_end)) {
+      tiles_left = FLUSH_TILES;
+      if (site_ok) {
 #pragma unroll
-      for (int l = 0; l < NL; l++)
-        if (l < nl) dst[l] += (double)facc[l];
+        for (int l = 0; l < NL; l++)
+          if (l < nl) dst[l] += (double)facc[l];
+      }
+#pragma unroll
+      for (int l = 0; l < NL; l++) facc[l] = 0.f;
     }
   }
 #undef DGET
@@ -611,49 +652,51 @@ static void solve_vandermonde(int n, const long double *u,
   for (int i = 0; i < n; i++) c[i] = a[i][n] / a[i][i];
 }
 
-static float poe_table_host(const float *tab, double x64) {
+static float poe_table_host(const float *tab, int nodes, double x64) {
   float x = (float)x64;
-  x = fminf(fmaxf(x, 0.f), (float)(PT_NODES - 1));
+  x = fminf(fmaxf(x, 0.f), (float)(nodes - 1));
   int k = (int)nearbyintf(x);
   float u = x - (float)k;
-  const float *c = tab + k;
-  float p = c[5 * PT_NODES];
-  for (int d = 4; d >= 0; d--) p = fmaf(p, u, c[d * PT_NODES]);
+  const float *c = tab + k * PT_STRIDE;
+  float p = c[PT_DEG];
+  for (int d = PT_DEG - 1; d >= 0; d--) p = fmaf(p, u, c[d]);
   return fminf(fmaxf(p, 0.f), 1.f);
 }
 
 // builds the table for truncation level tl; returns the maximum relative
-// error over poe >= 1e-9 (absolute error below that), sampled densely
-static double build_poe_table(double tl, float *tab, double *xscale) {
+// error over poe >= 1e-9 (absolute error / 1e-9 below that), sampled densely
+static double build_poe_table(double tl, int nodes, float *tab,
+                              double *xscale) {
   const double pi = 3.14159265358979323846;
-  const double s = (PT_NODES - 1) / (2. * tl);
+  const double s = (nodes - 1) / (2. * tl);
   *xscale = s;
-  for (int k = 0; k < PT_NODES; k++) {
+  for (int k = 0; k < nodes; k++) {
     long double u[6], f[6], c[6] = {0, 0, 0, 0, 0, 0};
     if (k == 0) {
       // F(u / s) = u * G(u) on [0, .5]: zero constant term
-      for (int j = 0; j < 5; j++) {
-        u[j] = 0.25L + 0.25L * cosl((2 * j + 1) * pi / 10);
+      for (int j = 0; j < PT_DEG; j++) {
+        u[j] = 0.25L + 0.25L * cosl((2 * j + 1) * pi / (2 * PT_DEG));
         f[j] = poe_exact(tl, (double)u[j] / s) / u[j];
       }
-      solve_vandermonde(5, u, f, c + 1);
+      solve_vandermonde(PT_DEG, u, f, c + 1);
     } else {
-      for (int j = 0; j < 6; j++) {
-        u[j] = 0.5L * cosl((2 * j + 1) * pi / 12);
+      for (int j = 0; j <= PT_DEG; j++) {
+        u[j] = 0.5L * cosl((2 * j + 1) * pi / (2 * (PT_DEG + 1)));
         f[j] = poe_exact(tl, (k + (double)u[j]) / s);
       }
-      solve_vandermonde(6, u, f, c);
+      solve_vandermonde(PT_DEG + 1, u, f, c);
     }
-    for (int d = 0; d <= PT_DEG; d++) tab[d * PT_NODES + k] = (float)c[d];
+    for (int d = 0; d < PT_STRIDE; d++)
+      tab[k * PT_STRIDE + d] = d <= PT_DEG ? (float)c[d] : 0.f;
   }
   double worst = 0.;
-  const int NS = 40000;
+  const int NS = 60000;
   for (int i = 0; i <= NS; i++) {
-    double x = (PT_NODES - 1) * (double)i / NS;
+    double x = (nodes - 1) * (double)i / NS;
     // finer sampling near the truncation point
-    if (i < 2000) x = 0.5 * pow(10., -8. + 8. * i / 2000.);
+    if (i < 3000) x = 0.5 * pow(10., -8. + 8. * i / 3000.);
     double ex = poe_exact(tl, x / s);
-    double got = poe_table_host(tab, x);
+    double got = poe_table_host(tab, nodes, x);
     double err = ex >= 1e-9 ? fabs(got / ex - 1.) : fabs(got - ex) / 1e-9;
     worst = std::max(worst, err);
   }
@@ -773,6 +816,11 @@ int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
   if (h->M && h->M != M) return fail(h, "set_levels: M differs from set_gsims");
   h->M = M; h->L1 = L1;
   h->loglev.assign(loglevels, loglevels + (size_t)M * L1);
+  h->sorted = true;
+  for (int m = 0; m < M; m++)
+    for (int l = 1; l < L1; l++)
+      if (!(loglevels[m * L1 + l] > loglevels[m * L1 + l - 1]))
+        h->sorted = false;
   {
     int nlc = (L1 + NL - 1) / NL, lpc = (L1 + nlc - 1) / nlc;
     if (M * nlc * NL > OQG_MAX_LEVELS)
@@ -789,12 +837,15 @@ int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
   // fast PoE table: used when it reproduces the exact formula to 2e-6
   h->fast_ok = false;
   if (truncation_level >= 0.5 && truncation_level <= 8.) {
-    float tab[(PT_DEG + 1) * PT_NODES];
-    h->ptab_err = build_poe_table(truncation_level, tab, &h->xscale);
-    if (h->ptab_err <= 2e-6) {
-      if (reserve(h, h->ptab, sizeof(tab))) return 1;
-      CK(cudaMemcpy(h->ptab.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
-      h->fast_ok = true;
+    float tab[PT_MAXNODES * PT_STRIDE];
+    for (int nodes = 64; nodes <= PT_MAXNODES && !h->fast_ok; nodes *= 2) {
+      h->ptab_err = build_poe_table(truncation_level, nodes, tab, &h->xscale);
+      if (h->ptab_err <= 2e-6) {
+        if (reserve(h, h->ptab, sizeof(tab))) return 1;
+        CK(cudaMemcpy(h->ptab.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+        h->fast_ok = true;
+        h->pt_nodes = nodes;
+      }
     }
   }
   return 0;
@@ -969,7 +1020,7 @@ static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
   size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
                  NF_SITE * 32 + (size_t)(nw + 1) * RT * QW +
                  (size_t)PW * RT * 32 + (A.K ? RT * A.K : 0)) * 8 +
-                (fast ? (PT_DEG + 1) * PT_NODES * 4 : 0) + RT * 4;
+                (fast ? A.pt_nodes * PT_STRIDE * 4 : 0) + RT * 4;
   if (A.K) return launch_fused2<F, true, false>(A, grid, threads, smem, st);
   if (fast) return launch_fused2<F, false, true>(A, grid, threads, smem, st);
   return launch_fused2<F, false, false>(A, grid, threads, smem, st);
@@ -1006,6 +1057,9 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
   A.nunits = M * A.nlc;
   A.ptab = (h->fast_ok && !h->exact_poe) ? (const float *)h->ptab.p : nullptr;
   A.tl = h->truncation_level; A.xscale = h->xscale;
+  A.pt_nodes = h->pt_nodes;
+  A.sorted = h->sorted;
+  A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_STRIDE * 4);
   A.mindist = mindist; A.itime = itime; A.phi_b = h->phi_b;
   A.inv_norm = 1. / (h->phi_b * 2. - 1.);
 

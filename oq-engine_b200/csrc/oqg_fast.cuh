@@ -22,6 +22,15 @@
 #include "oqg_gmpe.cuh"
 #include "oqg_geo.cuh"
 
+#ifndef OQG_CY_NOINLINE
+#define OQG_CY_NOINLINE 0
+#endif
+#if OQG_CY_NOINLINE
+#define OQG_CY_INLINE __noinline__
+#else
+#define OQG_CY_INLINE __forceinline__
+#endif
+
 namespace oqg {
 
 struct SiteIn {
@@ -70,10 +79,11 @@ template <int F> struct Fast {
                                               const Q &, const P &p,
                                               const RupIn &r, const SiteIn &s,
                                               const Dist &d, double &mean,
-                                              double &sig) {
+                                              double &sig, double &inv) {
     Out o = Fam<F>::imt(g, c, Cp, make_row(r, s, d), p);
     mean = o.mean;
     sig = o.sig;
+    inv = 1. / o.sig;
   }
 };
 
@@ -145,7 +155,7 @@ template <> struct Fast<OQG_BSSA14> {
                                               const Q &q, const P &p,
                                               const RupIn &r, const SiteIn &,
                                               const Dist &d, double &mean,
-                                              double &sig) {
+                                              double &sig, double &inv) {
     double rr = sqrt(d.rjb * d.rjb + c.h * c.h);
     double fp = q.c12 * log(rr / 1.0) + (c.c3 + c.Dc3) * (rr - 1.0);
     mean = (q.fm + fp) + (s.lin + s.f2 * p.lnp);
@@ -154,7 +164,9 @@ template <> struct Fast<OQG_BSSA14> {
     if (d.rjb > c.R2) phi += c.DfR;
     else if (d.rjb > c.R1) phi += c.DfR * ((p.lrjb - q.lR1) * q.ilR);
     phi += s.dphi;
-    sig = sqrt(q.tau * q.tau + phi * phi);
+    double var = q.tau * q.tau + phi * phi;
+    inv = rsqrt(var);
+    sig = var * inv;
   }
 };
 
@@ -226,12 +238,14 @@ template <> struct Fast<OQG_CY14> {
     return q;
   }
 
-  // mean (before floor and epistemic term) and sigma for one IMT
-  static __device__ __forceinline__ void one(const oqg_gsim &g, const C &c,
+  // mean (before floor and epistemic term) and sigma for one IMT; not
+  // inlined: shared by the pair stage (PGA) and the IMT stage to keep the
+  // kernel within the instruction cache
+  static __device__ OQG_CY_INLINE void one(const oqg_gsim &g, const C &c,
                                              const S &s, const Q &q,
                                              double fr, double hwd,
                                              const Dist &d, double &mean,
-                                             double &sig) {
+                                             double &sig, double &inv) {
     const double C4 = -2.1;
     double ln_yref = q.a + C4 * log(d.rrup + q.b) + (fr + q.gam * d.rrup) + 0.;
     if (((g.flags >> 4) & 1) && d.rx >= 0.0) {
@@ -241,11 +255,13 @@ template <> struct Fast<OQG_CY14> {
     double yref = exp(ln_yref);
     double fnl = log((yref + c.phi4) / c.phi4) * s.nls;
     mean = ln_yref + fnl + s.lin;
-    if ((g.flags >> 5) & 1) { sig = 0.65; return; }  // peer
+    if ((g.flags >> 5) & 1) { sig = 0.65; inv = 1. / 0.65; return; }  // peer
     double nl0 = s.nls * (yref / (yref + c.phi4));
     double nl1 = (1.0 + nl0) * (1.0 + nl0);
-    double phi = q.mdep * sqrt(s.phis + nl1);
-    sig = sqrt(nl1 * (q.tau * q.tau) + phi * phi);
+    double phi2 = (q.mdep * q.mdep) * (s.phis + nl1);
+    double var = nl1 * (q.tau * q.tau) + phi2;
+    inv = rsqrt(var);
+    sig = var * inv;
   }
 
   static __device__ __forceinline__ P pair(const oqg_gsim &g, const C &Cp,
@@ -256,8 +272,8 @@ template <> struct Fast<OQG_CY14> {
     P p;
     p.fr = (C4A - C4) * log(sqrt(d.rrup * d.rrup + CRB * CRB));
     p.hwd = 1.0 - (sqrt(d.rjb * d.rjb + r.ztor * r.ztor) / (d.rrup + 1.0));
-    double sig;
-    one(g, Cp, sp, qp, p.fr, p.hwd, d, p.pga_mean, sig);
+    double sig, inv;
+    one(g, Cp, sp, qp, p.fr, p.hwd, d, p.pga_mean, sig, inv);
     return p;
   }
 
@@ -266,8 +282,8 @@ template <> struct Fast<OQG_CY14> {
                                               const Q &q, const P &p,
                                               const RupIn &r, const SiteIn &,
                                               const Dist &d, double &mean,
-                                              double &sig) {
-    one(g, c, s, q, p.fr, p.hwd, d, mean, sig);
+                                              double &sig, double &inv) {
+    one(g, c, s, q, p.fr, p.hwd, d, mean, sig, inv);
     if (c.period > 0. && c.period <= 0.3 && mean < p.pga_mean)
       mean = p.pga_mean;
     mean = mean + g.par[0] * epistemic_sigma(d.rrup, r.mag);

@@ -40,13 +40,13 @@ def line_table(func_substr):
     return table
 
 
-def main(rep, func, top=40):
+def main(rep, func, top=40, stall=None):
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     ia, ii, isamp = (hdr.index('Address'), hdr.index('Instructions Executed'),
-                     hdr.index('# Samples'))
+                     hdr.index(stall or '# Samples'))
     sass = [(int(r[ia], 16), float(r[ii] or 0), float(r[isamp] or 0), r[1])
             for r in rows[2:] if len(r) == len(hdr)]
     table = line_table(func)
