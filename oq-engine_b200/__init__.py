@@ -15,6 +15,7 @@ from .tom import PoissonTOM, NegativeBinomialTOM  # noqa
 from .map_array import MapArray  # noqa
 from .planar import build_planar, planar_array_dt, wc1994_median_area  # noqa
 from .site import SiteCollection  # noqa
-from .contexts import ContextMaker, IntegrationDistance  # noqa
+from .contexts import ContextMaker, IntegrationDistance, PlanarRuptures  # noqa
+from . import sharding  # noqa
 
 __version__ = '0.1.0'

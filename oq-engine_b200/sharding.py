@@ -1,0 +1,127 @@
+"""Multi-GPU decomposition of the hot path: one process per GPU.
+
+The reference parallelises the classical calculator as a map-reduce over
+(source block x site tile) tasks whose results are summed in the master
+(openquake/calculators/classical.py:386-432, 591-650; site tiles by
+``sids % ntiles``, openquake/hazardlib/site.py:133-161).  Here
+
+* **site sharding** gives every rank a site tile and all the ruptures: map
+  rows are independent, so there is NO data-path collective; the tiles are
+  only gathered at the end if the caller wants the whole map;
+* **source-group sharding** gives every rank whole source groups and a map
+  over all the sites; the maps are combined once, pne maps multiplicatively
+  (``all_reduce(PRODUCT)``) and rate maps additively (``all_reduce(SUM)``),
+  exactly the reductions the reference master performs
+  (classical.py:431, hazard_curve.py:156).  Over NCCL this is one
+  NVLink/NVSwitch all-reduce of N x L x G float32.
+
+torch.distributed provides the process group (nccl on GPUs, gloo in the CPU
+tests); nothing here launches kernels by itself.
+"""
+import numpy
+
+
+def site_tile(sitecol, rank, world, mode='modulo'):
+    """
+    The site tile of `rank`: ``sids % world == rank`` like the reference's
+    TileGetter, or a contiguous block (mode='block')
+    """
+    if world == 1:
+        return sitecol
+    if mode == 'modulo':
+        return sitecol.filter(sitecol.sids % world == rank)
+    n = len(sitecol)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    mask = numpy.zeros(n, bool)
+    mask[lo:hi] = True
+    return sitecol.filter(mask)
+
+
+def groups_of(rank, world, n_groups):
+    """Round-robin assignment of source groups to ranks"""
+    return [g for g in range(n_groups) if g % world == rank]
+
+
+def combine_maps(array, rates, group=None):
+    """
+    Combine per-rank maps over ALL the sites in place: product of the
+    probabilities of no exceedance, or sum of the rates.
+
+    :param array: torch tensor (N, L, G) float32 (CUDA with nccl, CPU with
+        gloo)
+    """
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return array
+    op = dist.ReduceOp.SUM if rates else dist.ReduceOp.PRODUCT
+    dist.all_reduce(array, op=op, group=group)
+    return array
+
+
+def gather_tiles(tile_array, tile_sids, n_sites, group=None):
+    """
+    Assemble the whole (n_sites, L, G) map from the site tiles of the ranks
+    (all_gather of equally padded tiles); returns a tensor on every rank
+    """
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out = torch.empty((n_sites,) + tuple(tile_array.shape[1:]),
+                          dtype=tile_array.dtype, device=tile_array.device)
+        out[torch.as_tensor(numpy.asarray(tile_sids, numpy.int64),
+                            device=tile_array.device)] = tile_array
+        return out
+    world = dist.get_world_size(group)
+    nmax = (n_sites + world - 1) // world
+    L, G = tile_array.shape[1:]
+    pad = torch.zeros((nmax, L, G), dtype=tile_array.dtype,
+                      device=tile_array.device)
+    pad[:len(tile_array)] = tile_array
+    sids = torch.full((nmax,), -1, dtype=torch.int64,
+                      device=tile_array.device)
+    sids[:len(tile_sids)] = torch.as_tensor(
+        numpy.asarray(tile_sids, numpy.int64), device=tile_array.device)
+    tiles = [torch.empty_like(pad) for _ in range(world)]
+    allsids = [torch.empty_like(sids) for _ in range(world)]
+    dist.all_gather(tiles, pad, group=group)
+    dist.all_gather(allsids, sids, group=group)
+    out = torch.empty((n_sites, L, G), dtype=tile_array.dtype,
+                      device=tile_array.device)
+    for t, s in zip(tiles, allsids):
+        ok = s >= 0
+        out[s[ok]] = t[ok]
+    return out
+
+
+def hazard_site_sharded(cmaker, src, sitecol, rank, world, rates=False,
+                        mode='modulo'):
+    """
+    Fused pass of all the ruptures of `src` over this rank's site tile;
+    returns (MapArray of the tile on the device, tile)
+    """
+    from .map_array import MapArray
+    tile = site_tile(sitecol, rank, world, mode)
+    pmap = MapArray(tile.sids, cmaker.L, cmaker.G, rates=rates,
+                    device='cuda:%d' % cmaker.handle().device)
+    pmap.fill(0 if rates else 1)
+    cmaker.hazard_planar(pmap, src, tile)
+    return pmap, tile
+
+
+def hazard_group_sharded(cmakers, srcs, sitecol, rank, world, rates=False,
+                         group=None):
+    """
+    Source-group sharding: `cmakers[g]`, `srcs[g]` describe group g; this
+    rank folds its groups into a map over all the sites, then the maps are
+    combined with one all-reduce (PRODUCT of pnes / SUM of rates).
+    All the groups must share L and G (same `g` columns).
+    """
+    from .map_array import MapArray
+    cm0 = cmakers[0]
+    pmap = MapArray(sitecol.sids, cm0.L, cm0.G, rates=rates,
+                    device='cuda:%d' % cm0.handle().device)
+    pmap.fill(0 if rates else 1)
+    for g in groups_of(rank, world, len(srcs)):
+        cmakers[g].hazard_planar(pmap, srcs[g], sitecol)
+    combine_maps(pmap.array, rates, group)
+    return pmap
