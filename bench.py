@@ -121,7 +121,8 @@ def _cpu_worker(args):
     arr = np.ones((len(idx), L, len(pairs)), np.float32)
     sid_to_row = np.zeros(int(sub['sids'].max()) + 1, np.uint32)
     sid_to_row[sub['sids']] = np.arange(len(idx))
-    hazard_np.update(arr, sid_to_row, pairs, ctx, imtls, tl, itime)
+    hazard_np.update(arr, sid_to_row, pairs, ctx, imtls, tl, itime,
+                     chunk=50_000)
     return len(ctx), time.time() - t0, float(arr.sum())
 
 
@@ -379,7 +380,8 @@ def main():
     ap.add_argument('--workload', default='cfg3', choices=list(WORKLOADS))
     ap.add_argument('--ruptures', type=int, default=0)
     ap.add_argument('--sites', type=int, default=0)
-    ap.add_argument('--cpu-ruptures', type=int, default=16)
+    ap.add_argument('--cpu-ruptures', type=int, default=768,
+                    help='ruptures of the bounded CPU sample (x all sites)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -481,3 +481,61 @@ def test_fast_poe_table_vs_exact(oq):
         big = exact.array > 1e-12
         np.testing.assert_allclose(fast.array[big], exact.array[big],
                                    rtol=5e-6)
+
+
+def test_sharding_on_one_gpu(oq):
+    """The multi-GPU decompositions executed rank after rank on one GPU:
+    site tiles assemble to the unsharded map; the product of per-rank pne
+    maps (sum of rate maps) over source groups equals one pass over all
+    the groups"""
+    import torch
+    rng = np.random.default_rng(21)
+    N = 90
+    sites = synth_sites(N, rng)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    srcs = []
+    for g in range(4):
+        r = synth_ruptures(40, np.random.default_rng(50 + g))
+        pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                              r['rate'], r['area'], r['hypo_lon'],
+                              r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+        srcs.append(oq.PlanarRuptures(pla, r['mag']))
+    full = oq.MapArray(sc.sids, cm.L, cm.G).fill(1)
+    for src in srcs:
+        cm.hazard_planar(full, src, sc)
+    world = 3
+    # site sharding
+    out = np.zeros_like(full.array)
+    for rank in range(world):
+        tmap = None
+        for src in srcs:
+            if tmap is None:
+                tmap, tile = oq.sharding.hazard_site_sharded(
+                    cm, src, sc, rank, world)
+            else:
+                cm.hazard_planar(tmap, src, tile)
+        gathered = oq.sharding.gather_tiles(tmap.array, tile.sids, N)
+        out[tile.sids] = gathered.cpu().numpy()[tile.sids]
+    np.testing.assert_array_equal(out, full.array)
+    # source-group sharding (the all-reduce is the identity at world 1)
+    prod = torch.ones_like(tmap.array.new_empty(full.array.shape))
+    rates = torch.zeros_like(prod)
+    for rank in range(world):
+        for mode, acc in ((False, prod), (True, rates)):
+            pm = oq.MapArray(sc.sids, cm.L, cm.G, rates=mode,
+                             device='cuda:0').fill(0 if mode else 1)
+            for g in oq.sharding.groups_of(rank, world, len(srcs)):
+                cm.hazard_planar(pm, srcs[g], sc)
+            if mode:
+                acc += pm.array
+            else:
+                acc *= pm.array
+    np.testing.assert_allclose(prod.cpu().numpy(), full.array, rtol=1e-6)
+    np.testing.assert_allclose(np.exp(-rates.cpu().numpy()), full.array,
+                               rtol=1e-5)
+    pm = oq.sharding.hazard_group_sharded([cm] * 4, srcs, sc, 0, 1)
+    np.testing.assert_allclose(pm.numpy(), full.array, rtol=1e-6)
