@@ -140,6 +140,12 @@ int oqg_distances(oqg_handle *h, const double *planar_dev, int U,
 int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx_dev, int64_t P,
                   double *out_dev);
 
+/* verification entry point: out[2][G][M][P] (dev) = mean, sig as evaluated
+ * by the staged model code of the fused kernel (per-site / per-rupture /
+ * per-pair / per-IMT stages) on the same context rows */
+int oqg_mean_stds_staged(oqg_handle *h, const oqg_ctx *ctx_dev, int64_t P,
+                         double *out_dev);
+
 /* poes[P][L][G] float32 (dev) from mean_std[4][G][M][P] (dev), L = M*L1 */
 int oqg_poes(oqg_handle *h, const double *mean_std_dev, int64_t P,
              float *poes_dev);

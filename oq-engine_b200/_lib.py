@@ -65,6 +65,8 @@ def lib():
         'oqg_distances': (C.c_int, [H, c_void, C.c_int, C.POINTER(OqgSites),
                                     C.c_int, C.c_int, c_void]),
         'oqg_mean_stds': (C.c_int, [H, C.POINTER(OqgCtx), C.c_int64, c_void]),
+        'oqg_mean_stds_staged': (C.c_int, [H, C.POINTER(OqgCtx), C.c_int64,
+                                           c_void]),
         'oqg_poes': (C.c_int, [H, c_void, C.c_int64, c_void]),
         'oqg_update': (C.c_int, [H, c_void, C.c_int, c_void, C.c_int64,
                                  c_void, c_void, c_void, c_void, C.c_int,

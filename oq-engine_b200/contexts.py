@@ -219,6 +219,24 @@ def mean_stds_device(gsims, ctx, imts, device=None, handle=None,
     return out.cpu().numpy()
 
 
+def mean_stds_staged_device(gsims, ctx, imts, device=None, handle=None):
+    """(2, G, M, N) float64 = mean, sig as evaluated by the staged model
+    code of the fused kernel (verification of csrc/oqg_fast.cuh)"""
+    import torch
+    h = handle or get_handle(device)
+    arr, coeffs = _gsim_structs(gsims, imts)
+    h.call('oqg_set_gsims', len(gsims), arr, len(imts),
+           coeffs.ctypes.data_as(_lib.c_double_p))
+    h.owner = h.cfg = None
+    N = len(ctx)
+    out = torch.empty((2, len(gsims), len(imts), N), dtype=torch.float64,
+                      device='cuda:%d' % h.device)
+    if N:
+        st, keep = _ctx_struct(ctx, h.device)
+        h.call('oqg_mean_stds_staged', ctypes.byref(st), N, _ptr(out))
+    return out.cpu().numpy()
+
+
 def _group_by_site(sidxs, N):
     order = numpy.argsort(sidxs, kind='stable').astype(numpy.int64)
     seg = numpy.searchsorted(sidxs[order], numpy.arange(N + 1)).astype(

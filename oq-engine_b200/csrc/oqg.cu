@@ -215,6 +215,50 @@ k_mean_stds(int g, int G, int M, CtxDev cd, int64_t P,
   }
 }
 
+// the staged model code of the fused kernel (oqg_fast.cuh) on context rows:
+// out[2][G][M][P] = mean, sig.  Verification entry point: the parity tests
+// compare it with the reference fixtures to the same tolerance as
+// k_mean_stds, so that the staging is pinned independently of the PoEs.
+template <int F>
+__global__ void __launch_bounds__(128)
+k_mean_stds_staged(int g, int G, int M, CtxDev cd, int64_t P,
+                   double *__restrict__ out) {
+  typedef Fast<F> FF;
+  typedef typename FF::C CT;
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const oqg_ctx &c = cd.c;
+  RupIn ri;
+  ri.mag = ld(c.mag, p); ri.rake = ld(c.rake, p); ri.dip = ld(c.dip, p);
+  ri.ztor = ld(c.ztor, p); ri.width = ld(c.width, p);
+  ri.hypo_depth = ld(c.hypo_depth, p);
+  Dist dd;
+  dd.rrup = ld(c.rrup, p); dd.rjb = ld(c.rjb, p); dd.rx = ld(c.rx, p);
+  dd.ry0 = ld(c.ry0, p); dd.repi = ld(c.repi, p); dd.rhypo = ld(c.rhypo, p);
+  dd.azimuth = 0.;
+  SiteIn si;
+  si.vs30 = ld(c.vs30, p);
+  si.z1pt0 = c.z1pt0 ? c.z1pt0[p] : -999.;
+  si.z2pt5 = c.z2pt5 ? c.z2pt5[p] : -999.;
+  si.vs30measured = c.vs30measured ? c.vs30measured[p] != 0 : false;
+  const oqg_gsim &gs = c_gsim[g];
+  const CT &Cp = *reinterpret_cast<const CT *>(c_coef[g * (M + 1) + M]);
+  const typename FF::S sp = FF::site(gs, Cp, si);
+  const typename FF::Q qp = FF::rup(gs, Cp, ri);
+  const typename FF::P pp = FF::pair(gs, Cp, sp, qp, ri, si, dd);
+  const int64_t plane = (int64_t)G * M * P;
+  for (int m = 0; m < M; m++) {
+    const CT &C = *reinterpret_cast<const CT *>(c_coef[g * (M + 1) + m]);
+    const typename FF::S ss = FF::site(gs, C, si);
+    const typename FF::Q q = FF::rup(gs, C, ri);
+    double mean, sig, inv;
+    FF::eval(gs, C, Cp, ss, q, qp, pp, ri, si, dd, mean, sig, inv);
+    int64_t idx = ((int64_t)g * M + m) * P + p;
+    out[idx] = mean;
+    out[plane + idx] = sig;
+  }
+}
+
 // ------------------------------------------------------------------- poes
 // one thread per output element poes[p][l][g] (coalesced float32 stores)
 __global__ void k_poes(const double *__restrict__ ms, int64_t P, int G, int M,
@@ -522,13 +566,14 @@ k_fused(const FusedArgs A) {
       unsigned vm = s_valid[i];
       if (!((vm >> lane) & 1)) continue;
       LOAD_PAIR(i)
-      QT q;
+      QT q, qp;
       PT pp;
       if (FF::HAS_Q) q = ld_soa<QT>(s_q + (warp * RT + i) * QW, 1);
+      if (FF::EVAL_QP) qp = ld_soa<QT>(s_q + (nw * RT + i) * QW, 1);
       if (FF::HAS_P) pp = ld_soa<PT>(s_p + i * 32 + lane, RT * 32);
       else pp = FF::pair(gs, Cp, sp, q, ri, si, dd);
       double mean, sig, inv;
-      FF::eval(gs, C, Cp, ss, q, pp, ri, si, dd, mean, sig, inv);
+      FF::eval(gs, C, Cp, ss, q, qp, pp, ri, si, dd, mean, sig, inv);
       if (FAST) {
         // x = (tl - (l - mean) / sig) * xscale
         const double xa = -inv * A.xscale;
@@ -902,6 +947,15 @@ static void launch_mean_stds(oqg_handle *h, int g, const oqg_ctx *ctx,
       g, h->G, h->M, cd, P, out, h->flag_dev);
 }
 
+template <int F>
+static void launch_mean_stds_staged(oqg_handle *h, int g, const oqg_ctx *ctx,
+                                    int64_t P, double *out) {
+  CtxDev cd;
+  cd.c = *ctx;
+  k_mean_stds_staged<F><<<(unsigned)((P + 127) / 128), 128, 0, h->stream>>>(
+      g, h->G, h->M, cd, P, out);
+}
+
 extern "C" {
 
 static const char *missing_column(const oqg_gsim &g, const oqg_ctx *c) {
@@ -961,6 +1015,31 @@ int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx, int64_t P, double *out) {
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (flag) return fail(h, "Total StdDev is zero");
+  }
+  return 0;
+}
+
+int oqg_mean_stds_staged(oqg_handle *h, const oqg_ctx *ctx, int64_t P,
+                         double *out) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G) return fail(h, "oqg_set_gsims not called");
+  if (P <= 0) return 0;
+  for (int g = 0; g < h->G; g++)
+    if (const char *m = missing_column(h->gsims[g], ctx))
+      return fail(h, std::string("context column missing: ") + m);
+  if (upload_const(h)) return 1;
+  for (int g = 0; g < h->G; g++) {
+    switch (h->gsims[g].family) {
+      case OQG_BSSA14: launch_mean_stds_staged<OQG_BSSA14>(h, g, ctx, P, out); break;
+      case OQG_CY14: launch_mean_stds_staged<OQG_CY14>(h, g, ctx, P, out); break;
+      case OQG_ASK14: launch_mean_stds_staged<OQG_ASK14>(h, g, ctx, P, out); break;
+      case OQG_CB14: launch_mean_stds_staged<OQG_CB14>(h, g, ctx, P, out); break;
+      case OQG_BA08: launch_mean_stds_staged<OQG_BA08>(h, g, ctx, P, out); break;
+      case OQG_AB06: launch_mean_stds_staged<OQG_AB06>(h, g, ctx, P, out); break;
+      case OQG_AKKAR14: launch_mean_stds_staged<OQG_AKKAR14>(h, g, ctx, P, out); break;
+    }
+    h->launches++;
+    CK(cudaGetLastError());
   }
   return 0;
 }

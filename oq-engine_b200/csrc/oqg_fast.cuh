@@ -62,7 +62,7 @@ template <int F> struct Fast {
   typedef Empty S;
   typedef Empty Q;
   typedef typename Fam<F>::R P;
-  static constexpr bool HAS_S = false, HAS_Q = false;
+  static constexpr bool HAS_S = false, HAS_Q = false, EVAL_QP = false;
   static constexpr bool HAS_P = sizeof(P) >= 8;
   static __device__ __forceinline__ S site(const oqg_gsim &, const C &,
                                            const SiteIn &) { return S(); }
@@ -76,7 +76,7 @@ template <int F> struct Fast {
   }
   static __device__ __forceinline__ void eval(const oqg_gsim &g, const C &c,
                                               const C &Cp, const S &,
-                                              const Q &, const P &p,
+                                              const Q &, const Q &, const P &p,
                                               const RupIn &r, const SiteIn &s,
                                               const Dist &d, double &mean,
                                               double &sig, double &inv) {
@@ -94,6 +94,7 @@ template <> struct Fast<OQG_BSSA14> {
   struct Q { double fm, c12, tau, phi0, lR1, ilR; };
   struct P { double lnp, lrjb; };
   static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
+  static constexpr bool EVAL_QP = false;
 
   static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
                                            const SiteIn &s) {
@@ -152,7 +153,7 @@ template <> struct Fast<OQG_BSSA14> {
 
   static __device__ __forceinline__ void eval(const oqg_gsim &g, const C &c,
                                               const C &, const S &s,
-                                              const Q &q, const P &p,
+                                              const Q &q, const Q &, const P &p,
                                               const RupIn &r, const SiteIn &,
                                               const Dist &d, double &mean,
                                               double &sig, double &inv) {
@@ -177,6 +178,7 @@ template <> struct Fast<OQG_CY14> {
   struct Q { double a, b, gam, hw, tau, mdep; };
   struct P { double fr, hwd, pga_mean; };
   static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
+  static constexpr bool EVAL_QP = false;
 
   static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
                                            const SiteIn &s) {
@@ -279,7 +281,7 @@ template <> struct Fast<OQG_CY14> {
 
   static __device__ __forceinline__ void eval(const oqg_gsim &g, const C &c,
                                               const C &, const S &s,
-                                              const Q &q, const P &p,
+                                              const Q &q, const Q &, const P &p,
                                               const RupIn &r, const SiteIn &,
                                               const Dist &d, double &mean,
                                               double &sig, double &inv) {
@@ -287,6 +289,296 @@ template <> struct Fast<OQG_CY14> {
     if (c.period > 0. && c.period <= 0.3 && mean < p.pga_mean)
       mean = p.pga_mean;
     mean = mean + g.par[0] * epistemic_sigma(d.rrup, r.mag);
+  }
+};
+
+// --------------------------------------------------------------- ASK14 --
+// abrahamson_2014.py:62-438 split by dependency.  Rearrangements with
+// respect to oqg_gmpe.cuh (all exact identities, ~1e-16 relative):
+//   b log(sa + c rat^1.5) - b log(sa + c) = b log((sa + c rat^1.5)/(sa + c))
+//   sig^2 = (phi_al^2 - phi_amp^2 + tau_al^2) (1 + der)^2 + phi_amp^2
+// and the rock spectral acceleration sa1180 is only evaluated for the sites
+// with vs30 < vlin, the only ones whose mean or sigma depend on it.
+template <> struct Fast<OQG_ASK14> {
+  typedef Ask14C C;
+  struct S { double lin, crat, add, s1180, rcoef; };
+  struct Q { double a0, klr, c4m2, sofz, hwq, r1, tau, pm, pe; };
+  struct P { double hwp; };
+  static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
+  static constexpr bool EVAL_QP = false;
+
+  static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
+                                           const SiteIn &s) {
+    const int region = g.flags & 3;
+    S o;
+    double vstar = s.vs30 >= c.v1 ? c.v1 : s.vs30;
+    double rat = vstar / c.vlin;
+    if (s.vs30 >= c.vlin) {
+      o.lin = (c.a10 + c.b * 1.5) * log(rat);
+      o.crat = -1.;                       // linear site: no sa1180 needed
+    } else {
+      o.lin = c.a10 * log(rat);
+      o.crat = c.c * pow(rat, 1.5);
+    }
+    Row w;
+    w.vs30 = s.vs30; w.z1pt0 = s.z1pt0;
+    // the rrup-independent part of the regional term, for the site and for
+    // the 1180 m/s rock pass
+    o.add = ask_basin_soil(c, w, region) + ask_regional(c, region, s.vs30, 0.);
+    o.s1180 = ask_site(c, 1180., 0.) + ask_regional(c, region, 1180., 0.);
+    o.rcoef = region == 2 ? c.a25 : (region == 3 ? c.a28
+                                                 : (region == 1 ? c.a29 : 0.));
+    return o;
+  }
+
+  static __device__ __forceinline__ Q rup(const oqg_gsim &, const C &c,
+                                          const RupIn &r) {
+    Q q;
+    const double mag = r.mag, m1 = c.m1, m2 = 5.0;
+    double c4m = c.c4 - (c.c4 - 1.) * (5. - mag);
+    if (mag > 5.) c4m = c.c4;
+    if (mag < 4.) c4m = 1.;
+    q.c4m2 = c4m * c4m;
+    double t;
+    if (mag >= m1) {
+      t = c.a5 * (mag - m1) + c.a8 * ((8.5 - mag) * (8.5 - mag));
+      q.klr = c.a2 + c.a3 * (mag - m1);
+    } else if (mag >= m2) {
+      t = c.a4 * (mag - m1) + c.a8 * ((8.5 - mag) * (8.5 - mag));
+      q.klr = c.a2 + c.a3 * (mag - m1);
+    } else {
+      t = c.a4 * (m2 - m1) + c.a8 * ((8.5 - m2) * (8.5 - m2)) +
+          c.a6 * (mag - m2) + c.a7 * ((mag - m2) * (mag - m2));
+      q.klr = c.a2 + c.a3 * (m2 - m1);
+    }
+    q.a0 = c.a1 * 1.0 + t;
+    Row w;
+    w.mag = mag; w.rake = r.rake;
+    q.sofz = ask_sof(c, w) + c.a15 * fmin(r.ztor / 20.0, 1.);
+    // rupture-only factors of the hanging-wall term :201-257
+    const double dip = r.dip;
+    double t1 = dip <= 30. ? 60. / 45. : (90. - dip) / 45.0;
+    double m65 = mag - 6.5;
+    double t2 = (1. + 0.2 * m65 - (1. - 0.2) * (m65 * m65));
+    if (mag > 6.5) t2 = 1. + 0.2 * m65;
+    if (mag <= 5.5) t2 = 0.;
+    double t4 = r.ztor <= 10. ? 1. - (r.ztor * r.ztor) / 100. : 0.;
+    q.hwq = dip == 90. ? 0. : c.a13 * t1 * t2 * t4;
+    q.r1 = r.width * cos(dip * OQG_D2R);
+    // aleatory terms :61-90, 180-199
+    double tau_al = c.s3 + (c.s4 - c.s3) / 2. * (mag - 5.);
+    if (mag < 5.) tau_al = c.s3;
+    if (mag >= 7.) tau_al = c.s4;
+    q.tau = tau_al;
+    double pm = c.s1m + (c.s2m - c.s1m) / 2. * (mag - 4.);
+    double pe = c.s1e + (c.s2e - c.s1e) / 2. * (mag - 4.);
+    if (mag < 4.) { pm = c.s1m; pe = c.s1e; }
+    if (mag >= 6.) { pm = c.s2m; pe = c.s2e; }
+    q.pm = pm; q.pe = pe;
+    return q;
+  }
+
+  // distance tapers of the hanging-wall term (T3 and T5), IMT independent
+  static __device__ __forceinline__ P pair(const oqg_gsim &, const C &,
+                                           const S &, const Q &qp,
+                                           const RupIn &, const SiteIn &,
+                                           const Dist &d) {
+    P p;
+    const double rx = d.rx, r1 = qp.r1, r2 = 3. * r1;
+    double t3;
+    if (rx < r1) {
+      double q = rx / r1;
+      t3 = 0.25 + 1.50 * q + (-0.75) * (q * q);
+    } else if (rx <= r2) {
+      t3 = 1. - (rx - r1) / (r2 - r1);
+    } else {
+      t3 = 0.;
+    }
+    double ry1 = rx * tan(20. * OQG_D2R);
+    double dd = d.ry0 - ry1;
+    double t5 = dd <= 0.0 ? 1. : (dd < 5.0 ? 1. - dd / 5.0 : 0.);
+    p.hwp = rx > 0. ? t3 * t5 : 0.;
+    return p;
+  }
+
+  static __device__ __forceinline__ void eval(const oqg_gsim &g, const C &c,
+                                              const C &, const S &s,
+                                              const Q &q, const Q &, const P &p,
+                                              const RupIn &r, const SiteIn &si,
+                                              const Dist &d, double &mean,
+                                              double &sig, double &inv) {
+    const int region = g.flags & 3;
+    const double rrup = d.rrup;
+    double R = sqrt(rrup * rrup + q.c4m2);
+    double basic = (q.a0 + c.a17 * rrup) + q.klr * log(R);
+    double common = basic + q.sofz + q.hwq * p.hwp;
+    double rr = s.rcoef * rrup;
+    double site = s.lin, der = 0.;
+    if (s.crat >= 0.) {
+      double sa1180 = exp(common + s.s1180 + rr);
+      double t1 = sa1180 + s.crat, t2 = sa1180 + c.c;
+      double w = 1. / (t1 * t2);
+      site += c.b * log((t1 * t1) * w);
+      der = c.b * sa1180 * ((t2 - t1) * w);
+    }
+    mean = common + site + s.add + rr;
+    mean = mean + g.par[0] * epistemic_sigma(rrup, r.mag);
+    double phi_al;
+    if (region == 1)
+      phi_al = rrup < 30. ? c.s5
+                          : (rrup <= 80. ? c.s5 + (c.s6 - c.s5) / 50. * (rrup - 30.)
+                                         : c.s6);
+    else
+      phi_al = si.vs30measured ? q.pm : q.pe;
+    double phi_amp = phi_al < 0.4 ? 0.99 * phi_al : 0.4;
+    double pa2 = phi_amp * phi_amp;
+    double d1 = 1. + der;
+    double var = ((phi_al * phi_al - pa2) + q.tau * q.tau) * (d1 * d1) + pa2;
+    inv = rsqrt(var);
+    sig = var * inv;
+  }
+};
+
+// ---------------------------------------------------------------- CB14 --
+// campbell_bozorgnia_2014.py:54-463 split by dependency.  Rearrangements
+// (exact identities): log(sqrt(x)) = log(x) / 2;
+//   k2 (log(a + c v^n) - log(a + c)) = k2 log((a + c v^n) / (a + c));
+//   sig^2 = tau^2 + phi^2 expanded, no intermediate square roots.
+template <> struct Fast<OQG_CB14> {
+  typedef Cb14C C;
+  struct S { double lin, cvn, rock; };
+  struct Q { double a0, kdis, hngq, r1, r2, taub, phib, varb; };
+  struct P { double a1100, pga_mean, hx, hrr; };
+  static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
+  static constexpr bool EVAL_QP = true;
+
+  static __device__ __forceinline__ double site_lin(const C &c, int SJ,
+                                                    double vs30, bool rock,
+                                                    double z2pt5) {
+    const double CB_N = 1.18;
+    double lv = log(vs30 / c.k1);
+    double fsite = c.c11 * lv;
+    if (vs30 > c.k1) fsite = fsite + (c.k2 * CB_N * lv);
+    if (SJ) {
+      double fj = (c.c13 + c.k2 * CB_N) * lv;
+      double soft = (c.c12 + c.k2 * CB_N) * (lv - log(200.0 / c.k1));
+      fsite = fsite + (vs30 <= 200.0 ? fj + soft : fj);
+    }
+    double z25;
+    if (rock) z25 = cb_z25ref(SJ, 1100.0);
+    else z25 = z2pt5 == -999. ? cb_z25ref(SJ, vs30) : z2pt5;
+    double fsed = 0.;
+    if (z25 < 1.0) fsed = (c.c14 + c.c15 * SJ) * (z25 - 1.0);
+    if (z25 > 3.0)
+      fsed = (c.c16 * c.k3) * exp(-0.75) * (1. - exp(-0.25 * (z25 - 3.)));
+    return fsite + fsed;
+  }
+
+  static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
+                                           const SiteIn &s) {
+    const int SJ = g.flags & 1;
+    S o;
+    o.lin = site_lin(c, SJ, s.vs30, false, s.z2pt5);
+    o.rock = site_lin(c, SJ, 1100., true, 0.);
+    o.cvn = s.vs30 > c.k1 ? -1. : 1.88 * pow(s.vs30 / c.k1, 1.18);
+    return o;
+  }
+
+  static __device__ __forceinline__ Q rup(const oqg_gsim &, const C &c,
+                                          const RupIn &r) {
+    Q q;
+    const double mag = r.mag;
+    double fmag = c.c0 + c.c1 * mag, t;
+    if (mag > 6.5)
+      t = c.c2 * (mag - 4.5) + c.c3 * (mag - 5.5) + c.c4 * (mag - 6.5);
+    else if (mag > 5.5) t = c.c2 * (mag - 4.5) + c.c3 * (mag - 5.5);
+    else if (mag > 4.5) t = c.c2 * (mag - 4.5);
+    else t = 0.;
+    fmag = fmag + t;
+    double frv = (r.rake > 30. && r.rake < 150.) ? 1. : 0.;
+    double fnm = (r.rake > -150. && r.rake < -30.) ? 1. : 0.;
+    double fflt_m = mag <= 4.5 ? 0. : (mag > 5.5 ? 1. : mag - 4.5);
+    double fflt = (c.c8 * frv + c.c9 * fnm) * fflt_m;
+    double fh = fmin(fmax(r.hypo_depth - 7.0, 0.), 13.);
+    double fm = c.c17 + (c.c18 - c.c17) * (mag - 5.5);
+    if (mag <= 5.5) fm = c.c17;
+    if (mag > 6.5) fm = c.c18;
+    double fdip = c.c19 * (5.5 - mag) * r.dip;
+    if (mag < 4.5) fdip = c.c19 * r.dip;
+    if (mag > 5.5) fdip = 0.0;
+    q.a0 = fmag + fflt + fh * fm + fdip;
+    q.kdis = 0.5 * (c.c5 + c.c6 * mag);
+    double fhng_m = (mag - 5.5) * (1.0 + c.a2 * (mag - 6.5));
+    if (mag < 5.5) fhng_m = 0.0;
+    if (mag > 6.5) fhng_m = 1.0 + c.a2 * (mag - 6.5);
+    double fhng_z = r.ztor > 16.66 ? 0. : 1. - 0.06 * r.ztor;
+    double fhng_d = (90.0 - r.dip) / 45.0;
+    q.hngq = c.c10 * fhng_m * fhng_z * fhng_d;
+    q.r1 = r.width * cos(r.dip * OQG_D2R);
+    q.r2 = 62.0 * mag - 350.0;
+    q.taub = cb_lin(mag, c.tau1, c.tau2);
+    double pl = cb_lin(mag, c.phi1, c.phi2);
+    q.phib = sqrt(pl * pl - c.philnAF * c.philnAF);
+    q.varb = q.taub * q.taub + pl * pl;
+    return q;
+  }
+
+  // the part of the mean without the nonlinear soil term
+  static __device__ __forceinline__ double base(const C &c, const Q &q,
+                                                const P &p, const Dist &d) {
+    const double rrup = d.rrup;
+    double fdis = q.kdis * log(rrup * rrup + c.c7 * c.c7);
+    double fhng_rx;
+    if (d.rx >= q.r1) fhng_rx = fmax(1.0 + c.h5 * p.hx + c.h6 * (p.hx * p.hx), 0.0);
+    else if (d.rx >= 0.) fhng_rx = c.h1 + c.h2 * p.hx + c.h3 * (p.hx * p.hx);
+    else fhng_rx = 0.;
+    double fatn = rrup >= 80.0 ? (c.c20 + c.Dc20) * (rrup - 80.0) : 0.;
+    return (q.a0 + fdis) + (q.hngq * fhng_rx) * p.hrr + fatn;
+  }
+
+  static __device__ __forceinline__ P pair(const oqg_gsim &, const C &Cp,
+                                           const S &sp, const Q &qp,
+                                           const RupIn &, const SiteIn &,
+                                           const Dist &d) {
+    P p;
+    if (d.rx >= qp.r1) p.hx = (d.rx - qp.r1) / (qp.r2 - qp.r1);
+    else p.hx = d.rx / qp.r1;
+    p.hrr = d.rrup > 0.0 ? (d.rrup - d.rjb) / d.rrup : 1.;
+    double b = base(Cp, qp, p, d);
+    p.a1100 = exp(b + sp.rock);
+    double nl = 0.;
+    if (sp.cvn >= 0.)
+      nl = Cp.k2 * log((p.a1100 + sp.cvn) / (p.a1100 + 1.88));
+    p.pga_mean = b + sp.lin + nl;
+    return p;
+  }
+
+  static __device__ __forceinline__ void eval(const oqg_gsim &g, const C &c,
+                                              const C &, const S &s,
+                                              const Q &q, const Q &qp,
+                                              const P &p, const RupIn &r,
+                                              const SiteIn &, const Dist &d,
+                                              double &mean, double &sig,
+                                              double &inv) {
+    double eps = g.par[0] * epistemic_sigma(d.rrup, r.mag);
+    double nl = 0., alpha = 0.;
+    if (s.cvn >= 0.) {
+      double af1 = p.a1100 + s.cvn, af2 = p.a1100 + 1.88;
+      double w = 1. / (af1 * af2);
+      nl = c.k2 * log((af1 * af1) * w);
+      alpha = c.k2 * p.a1100 * ((af2 - af1) * w);
+    }
+    mean = base(c, q, p, d) + s.lin + nl;
+    mean = mean + eps;
+    if (c.period > 0. && c.period < 0.25) {  // :554-564
+      if (mean <= p.pga_mean) mean = p.pga_mean;
+      mean = mean + eps;  // added a second time in the reference
+    }
+    double var = q.varb +
+                 (alpha * alpha) * (qp.taub * qp.taub + qp.phib * qp.phib) +
+                 (2.0 * alpha * c.rholny) * (q.taub * qp.taub + q.phib * qp.phib);
+    inv = rsqrt(var);
+    sig = var * inv;
   }
 };
 

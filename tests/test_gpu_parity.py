@@ -71,6 +71,19 @@ def test_gmpe_golden(oq, tag):
     np.testing.assert_allclose(out, d['mean_stds'], rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize('tag', gmpe_cases())
+def test_gmpe_staged_golden(oq, tag):
+    """the per-site / per-rupture / per-pair / per-IMT staging used inside
+    the fused kernel reproduces the reference's mean and total sigma"""
+    d = load('gmpe_' + tag)
+    gsim = oq.get_gsim(str(d['name']), **json_kwargs(d))
+    ctx = to_recarray(ctx_of(d))
+    imts = [str(i) for i in d['imts']]
+    out = oq.contexts.mean_stds_staged_device([gsim], ctx, imts)
+    np.testing.assert_allclose(out[:, 0], d['mean_stds'][:2], rtol=1e-10,
+                               atol=1e-12)
+
+
 def test_gmpe_unsupported_is_an_error(oq):
     with pytest.raises(NotImplementedError):
         oq.get_gsim('ToroEtAl2002')
