@@ -226,6 +226,8 @@ k_mean_stds_staged(int g, int G, int M, CtxDev cd, int64_t P,
   typedef Fast<F> FF;
   typedef typename FF::C CT;
   int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  math_tables_init();
+  __syncthreads();
   if (p >= P) return;
   const oqg_ctx &c = cd.c;
   RupIn ri;
@@ -309,19 +311,19 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 }
 
 // ------------------------------------------------------------------ fused
-// Fast PoE: poe as a function of x = (tl - z) * (nodes - 1) / (2 tl) in
-// [0, nodes - 1] is tabulated as one degree-4 polynomial per node k =
-// round(x) in u = x - k in [-.5, .5] (float32 coefficients built in float64
-// by oqg_set_levels; 64 or 128 nodes, whichever reproduces the exact formula
-// to 2e-6); node 0 has a zero constant term, so that the relative accuracy
-// is kept as poe -> 0 (z -> truncation level), where the textbook formula
-// cancels.  x itself is computed in float64.  The table is [nodes][9] floats
-// in shared memory: lanes whose nodes are less than 32 apart hit different
-// banks, lanes with the same node broadcast.
-#define PT_DEG 4
-#define PT_STRIDE 9       // floats per node: odd, so that 32 consecutive
-                          // nodes fall in 32 different banks
-#define PT_MAXNODES 128
+// Fast PoE: poe as a function of x = (tl - z) / (2 tl) in [0, 1] is tabulated
+// as one cubic per node k = round(x (nodes - 1)) in u = x (nodes - 1) - k in
+// [-.5, .5] (float32 coefficients built in float64 by oqg_set_levels; 256 or
+// 512 nodes, whichever reproduces the exact formula to 2e-6); node 0 has a
+// zero constant term, so that the relative accuracy is kept as poe -> 0
+// (z -> truncation level), where the textbook formula cancels.  x itself is
+// computed in float64.  The table is [nodes][4] floats in shared memory, one
+// 16-byte load per evaluation: lanes with the same node broadcast, the lanes
+// of a quarter warp (neighbouring sites) hit nodes less than 8 apart, i.e.
+// different banks.
+#define PT_DEG 3
+#define PT_STRIDE 4       // floats per node: one LDS.128
+#define PT_MAXNODES 512
 #ifndef FLUSH_TILES
 #define FLUSH_TILES 4
 #endif
@@ -355,23 +357,20 @@ struct FusedArgs {
   double mindist, itime, phi_b, inv_norm, tl, xscale;
 };
 
-// tab32: shared-window address of the table minus (0x4b000000 * 36), so
-// that tab32 + bits(x + 2^23) * 36 is the address of node round(x)
-__device__ __forceinline__ float poe_table(unsigned tab32, float xmax,
+// tab32: shared-window address of the table minus (0x4b000000 * 16), so
+// that tab32 + bits(k + 2^23) * 16 is the address of node k.  12 instructions
+// per evaluation with the DFMA of x and the FFMA into the accumulator: F2F,
+// FADD.SAT, FFMA (round), FADD, FFMA (u), IMAD (address), LDS.128, 3 FFMA.
+__device__ __forceinline__ float poe_table(unsigned tab32, float nm1,
                                            double x64) {
-  float x = (float)x64;
-  x = fminf(fmaxf(x, 0.f), xmax);
-  float y = x + 8388608.f;              // 2^23: round to nearest integer
-  float u = x - (y - 8388608.f);
+  float x = __saturatef((float)x64);    // NaN -> 0 -> poe 0
+  float y = fmaf(x, nm1, 8388608.f);    // 2^23: round to nearest integer
+  float u = fmaf(x, nm1, -(y - 8388608.f));
   unsigned a = tab32 + __float_as_uint(y) * (PT_STRIDE * 4);
-  float c0, c1, c2, c3, c4;
-  asm("ld.shared.f32 %0, [%1];" : "=f"(c0) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+4];" : "=f"(c1) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+8];" : "=f"(c2) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+12];" : "=f"(c3) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+16];" : "=f"(c4) : "r"(a));
-  float p = fmaf(c4, u, c3);
-  p = fmaf(p, u, c2);
+  float c0, c1, c2, c3;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(c0), "=f"(c1), "=f"(c2), "=f"(c3) : "r"(a));
+  float p = fmaf(c3, u, c2);
   p = fmaf(p, u, c1);
   return __saturatef(fmaf(p, u, c0));
 }
@@ -402,16 +401,16 @@ k_fused(const FusedArgs A) {
   typedef typename FF::P PT;
   constexpr int QW = FF::HAS_Q ? sizeof(QT) / 8 : 0;   // doubles
   constexpr int PW = FF::HAS_P ? sizeof(PT) / 8 : 0;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int nw = blockDim.x >> 5;
-  double *s_rup = smem;                            // [NF_RUP][RT]
+  float *s_tab = (float *)smem;                    // [nodes][PT_STRIDE]
+  double *s_rup = smem + (FAST ? A.pt_nodes * PT_STRIDE / 2 : 0);  // [NF_RUP][RT]
   double *s_dist = s_rup + NF_RUP * RT;            // [nplanes][RT][32]
   double *s_site = s_dist + A.nplanes * RT * 32;   // [NF_SITE][32]
   double *s_q = s_site + NF_SITE * 32;             // [nw + 1][RT][QW]
   double *s_p = s_q + (nw + 1) * RT * QW;          // [PW][RT][32]
   double *s_probs = s_p + PW * RT * 32;            // [RT][K]
-  float *s_tab = (float *)(s_probs + (NEGBIN ? RT * A.K : 0));
-  unsigned *s_valid = (unsigned *)(s_tab + (FAST ? A.pt_nodes * PT_STRIDE : 0));
+  unsigned *s_valid = (unsigned *)(s_probs + (NEGBIN ? RT * A.K : 0));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int site0 = blockIdx.x * 32;
@@ -432,11 +431,12 @@ k_fused(const FusedArgs A) {
   if (FAST)
     for (int i = threadIdx.x; i < A.pt_nodes * PT_STRIDE; i += blockDim.x)
       s_tab[i] = A.ptab[i];
-  // pt_bias = -(0x4b000000 * 36) mod 2^32 comes in as a kernel argument: as
+  math_tables_init();   // log / exp tables of oqg_math.cuh
+  // pt_bias = -(0x4b000000 * 16) mod 2^32 comes in as a kernel argument: as
   // a literal the compiler splits it off again and adds it back before
   // every load
   const unsigned tab32 = (unsigned)__cvta_generic_to_shared(s_tab) + A.pt_bias;
-  const float xmax = (float)(A.pt_nodes - 1);
+  const float nm1 = (float)(A.pt_nodes - 1);
   SiteIn si;
   si.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
   si.z1pt0 = site_ok && A.z1pt0 ? A.z1pt0[n] : -999.;
@@ -575,7 +575,7 @@ k_fused(const FusedArgs A) {
       double mean, sig, inv;
       FF::eval(gs, C, Cp, ss, q, qp, pp, ri, si, dd, mean, sig, inv);
       if (FAST) {
-        // x = (tl - (l - mean) / sig) * xscale
+        // x = (tl - (l - mean) / sig) * xscale, xscale = 1 / (2 tl)
         const double xa = -inv * A.xscale;
         const double xb = (A.tl + mean * inv) * A.xscale;
         const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
@@ -594,7 +594,7 @@ k_fused(const FusedArgs A) {
         for (int l = 0; l < NL; l++) {
           const double lv = ll[l];
           if (lv >= thr_w) break;
-          facc[l] = fmaf(rt, poe_table(tab32, xmax, fma(lv, xa, xb)), facc[l]);
+          facc[l] = fmaf(rt, poe_table(tab32, nm1, fma(lv, xa, xb)), facc[l]);
         }
       } else if (NEGBIN) {
         const double *pr = s_probs + i * A.K;
@@ -697,11 +697,13 @@ static void solve_vandermonde(int n, const long double *u,
   for (int i = 0; i < n; i++) c[i] = a[i][n] / a[i][i];
 }
 
-static float poe_table_host(const float *tab, int nodes, double x64) {
-  float x = (float)x64;
-  x = fminf(fmaxf(x, 0.f), (float)(nodes - 1));
-  int k = (int)nearbyintf(x);
-  float u = x - (float)k;
+static float poe_table_host(const float *tab, int nodes, double x01) {
+  float x = (float)x01;                 // the device sequence of poe_table()
+  x = fminf(fmaxf(x, 0.f), 1.f);
+  float nm1 = (float)(nodes - 1);
+  float y = fmaf(x, nm1, 8388608.f);
+  int k = (int)(y - 8388608.f);
+  float u = fmaf(x, nm1, -(y - 8388608.f));
   const float *c = tab + k * PT_STRIDE;
   float p = c[PT_DEG];
   for (int d = PT_DEG - 1; d >= 0; d--) p = fmaf(p, u, c[d]);
@@ -714,7 +716,7 @@ static double build_poe_table(double tl, int nodes, float *tab,
                               double *xscale) {
   const double pi = 3.14159265358979323846;
   const double s = (nodes - 1) / (2. * tl);
-  *xscale = s;
+  *xscale = 1. / (2. * tl);
   for (int k = 0; k < nodes; k++) {
     long double u[6], f[6], c[6] = {0, 0, 0, 0, 0, 0};
     if (k == 0) {
@@ -741,7 +743,7 @@ static double build_poe_table(double tl, int nodes, float *tab,
     // finer sampling near the truncation point
     if (i < 3000) x = 0.5 * pow(10., -8. + 8. * i / 3000.);
     double ex = poe_exact(tl, x / s);
-    double got = poe_table_host(tab, nodes, x);
+    double got = poe_table_host(tab, nodes, x / (nodes - 1));
     double err = ex >= 1e-9 ? fabs(got / ex - 1.) : fabs(got - ex) / 1e-9;
     worst = std::max(worst, err);
   }
@@ -848,6 +850,16 @@ int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
   h->G = G; h->M = M;
   h->gsims.assign(gsims, gsims + G);
   h->coef.assign(coeffs, coeffs + (size_t)G * (M + 1) * OQG_KMAX);
+  // derived per-IMT constants of the staged model code (oqg_fast.cuh)
+  for (int g = 0; g < G; g++)
+    for (int m = 0; m <= M; m++) {
+      double *row = h->coef.data() + ((size_t)g * (M + 1) + m) * OQG_KMAX;
+      if (gsims[g].family == OQG_CY14) {
+        const Cy14C *c = reinterpret_cast<const Cy14C *>(row);
+        row[OQG_DER + CY_LOG_PHI4] = log(c->phi4);
+        row[OQG_DER + CY_INV_C9B] = 1. / c->c9b;
+      }
+    }
   h->const_dirty = true;
   return 0;
 }
@@ -883,7 +895,7 @@ int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,
   h->fast_ok = false;
   if (truncation_level >= 0.5 && truncation_level <= 8.) {
     float tab[PT_MAXNODES * PT_STRIDE];
-    for (int nodes = 64; nodes <= PT_MAXNODES && !h->fast_ok; nodes *= 2) {
+    for (int nodes = 256; nodes <= PT_MAXNODES && !h->fast_ok; nodes *= 2) {
       h->ptab_err = build_poe_table(truncation_level, nodes, tab, &h->xscale);
       if (h->ptab_err <= 2e-6) {
         if (reserve(h, h->ptab, sizeof(tab))) return 1;

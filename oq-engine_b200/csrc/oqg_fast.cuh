@@ -15,12 +15,17 @@
 // so that the innermost stage keeps only the transcendental calls that
 // really depend on the triple.  The arithmetic is the same as in
 // oqg_gmpe.cuh (which follows the reference term by term) up to the
-// association of a few additions; results agree to ~1e-15.  Families
+// association of a few additions and the table-driven log / exp / tanh /
+// reciprocal of oqg_math.cuh in the per-pair and per-IMT stages; results
+// agree to ~1e-15.  Per-IMT constants that would cost a transcendental or a
+// divide per evaluation (log phi4, 1 / c9b ...) are precomputed on the host
+// into the tail of the coefficient row (OQG_DER, filled by oqg_set_gsims).  Families
 // without a specialisation go through the generic Fast<F>, which calls the
 // unstaged functions (P = the row state of oqg_gmpe.cuh).
 #pragma once
 #include "oqg_gmpe.cuh"
 #include "oqg_geo.cuh"
+#include "oqg_math.cuh"
 
 #ifndef OQG_CY_NOINLINE
 #define OQG_CY_NOINLINE 0
@@ -43,6 +48,14 @@ struct RupIn {
 };
 
 struct Empty {};
+
+// derived per-IMT constants in the tail of a coefficient row (filled on the
+// host by oqg_set_gsims from the packed coefficients)
+enum { CY_LOG_PHI4 = 0, CY_INV_C9B = 1 };
+template <typename CT>
+__device__ __forceinline__ double der(const CT &c, int k) {
+  return reinterpret_cast<const double *>(&c)[OQG_DER + k];
+}
 
 __device__ __forceinline__ Row make_row(const RupIn &r, const SiteIn &s,
                                         const Dist &d) {
@@ -144,10 +157,10 @@ template <> struct Fast<OQG_BSSA14> {
                                            const Dist &d) {
     P p;
     double rr = sqrt(d.rjb * d.rjb + Cp.h * Cp.h);
-    double pga_rock = exp(qp.fm + (qp.c12 * log(rr / 1.0) +
-                                   (Cp.c3 + Cp.Dc3) * (rr - 1.0)));
-    p.lnp = log((pga_rock + 0.1) / 0.1);
-    p.lrjb = log(d.rjb);
+    double pga_rock = fast_exp(qp.fm + (qp.c12 * fast_log(rr) +
+                                        (Cp.c3 + Cp.Dc3) * (rr - 1.0)));
+    p.lnp = fast_log((pga_rock + 0.1) * 10.);
+    p.lrjb = log(d.rjb);   // rjb may be 0: the library function
     return p;
   }
 
@@ -157,8 +170,9 @@ template <> struct Fast<OQG_BSSA14> {
                                               const RupIn &r, const SiteIn &,
                                               const Dist &d, double &mean,
                                               double &sig, double &inv) {
-    double rr = sqrt(d.rjb * d.rjb + c.h * c.h);
-    double fp = q.c12 * log(rr / 1.0) + (c.c3 + c.Dc3) * (rr - 1.0);
+    double rr2 = d.rjb * d.rjb + c.h * c.h;
+    double rr = sqrt(rr2);
+    double fp = q.c12 * (0.5 * fast_log(rr2)) + (c.c3 + c.Dc3) * (rr - 1.0);
     mean = (q.fm + fp) + (s.lin + s.f2 * p.lnp);
     if (g.par[0] != 0.) mean += g.par[0] * epistemic_sigma(d.rrup, r.mag);
     double phi = q.phi0;
@@ -249,16 +263,19 @@ template <> struct Fast<OQG_CY14> {
                                              const Dist &d, double &mean,
                                              double &sig, double &inv) {
     const double C4 = -2.1;
-    double ln_yref = q.a + C4 * log(d.rrup + q.b) + (fr + q.gam * d.rrup) + 0.;
+    double ln_yref = q.a + C4 * fast_log(d.rrup + q.b) +
+                     (fr + q.gam * d.rrup) + 0.;
     if (((g.flags >> 4) & 1) && d.rx >= 0.0) {
-      double fd = hwd * (c.c9a + (1.0 - c.c9a) * tanh(d.rx / c.c9b));
+      double fd = hwd * (c.c9a + (1.0 - c.c9a) *
+                                     fast_tanh_pos(d.rx * der(c, CY_INV_C9B)));
       ln_yref += q.hw * fd;
     }
-    double yref = exp(ln_yref);
-    double fnl = log((yref + c.phi4) / c.phi4) * s.nls;
+    double yref = fast_exp(ln_yref);
+    double yp = yref + c.phi4;
+    double fnl = (fast_log(yp) - der(c, CY_LOG_PHI4)) * s.nls;
     mean = ln_yref + fnl + s.lin;
     if ((g.flags >> 5) & 1) { sig = 0.65; inv = 1. / 0.65; return; }  // peer
-    double nl0 = s.nls * (yref / (yref + c.phi4));
+    double nl0 = s.nls * (yref * fast_rcp(yp));
     double nl1 = (1.0 + nl0) * (1.0 + nl0);
     double phi2 = (q.mdep * q.mdep) * (s.phis + nl1);
     double var = nl1 * (q.tau * q.tau) + phi2;
@@ -272,7 +289,7 @@ template <> struct Fast<OQG_CY14> {
                                            const Dist &d) {
     const double C4 = -2.1, C4A = -0.5, CRB = 50.0;
     P p;
-    p.fr = (C4A - C4) * log(sqrt(d.rrup * d.rrup + CRB * CRB));
+    p.fr = (C4A - C4) * (0.5 * fast_log(d.rrup * d.rrup + CRB * CRB));
     p.hwd = 1.0 - (sqrt(d.rjb * d.rjb + r.ztor * r.ztor) / (d.rrup + 1.0));
     double sig, inv;
     one(g, Cp, sp, qp, p.fr, p.hwd, d, p.pga_mean, sig, inv);
@@ -288,7 +305,7 @@ template <> struct Fast<OQG_CY14> {
     one(g, c, s, q, p.fr, p.hwd, d, mean, sig, inv);
     if (c.period > 0. && c.period <= 0.3 && mean < p.pga_mean)
       mean = p.pga_mean;
-    mean = mean + g.par[0] * epistemic_sigma(d.rrup, r.mag);
+    if (g.par[0] != 0.) mean = mean + g.par[0] * epistemic_sigma(d.rrup, r.mag);
   }
 };
 
@@ -409,20 +426,20 @@ template <> struct Fast<OQG_ASK14> {
                                               double &sig, double &inv) {
     const int region = g.flags & 3;
     const double rrup = d.rrup;
-    double R = sqrt(rrup * rrup + q.c4m2);
-    double basic = (q.a0 + c.a17 * rrup) + q.klr * log(R);
+    double basic = (q.a0 + c.a17 * rrup) +
+                   q.klr * (0.5 * fast_log(rrup * rrup + q.c4m2));
     double common = basic + q.sofz + q.hwq * p.hwp;
     double rr = s.rcoef * rrup;
     double site = s.lin, der = 0.;
     if (s.crat >= 0.) {
-      double sa1180 = exp(common + s.s1180 + rr);
+      double sa1180 = fast_exp(common + s.s1180 + rr);
       double t1 = sa1180 + s.crat, t2 = sa1180 + c.c;
-      double w = 1. / (t1 * t2);
-      site += c.b * log((t1 * t1) * w);
+      double w = fast_rcp(t1 * t2);
+      site += c.b * fast_log((t1 * t1) * w);
       der = c.b * sa1180 * ((t2 - t1) * w);
     }
     mean = common + site + s.add + rr;
-    mean = mean + g.par[0] * epistemic_sigma(rrup, r.mag);
+    if (g.par[0] != 0.) mean = mean + g.par[0] * epistemic_sigma(rrup, r.mag);
     double phi_al;
     if (region == 1)
       phi_al = rrup < 30. ? c.s5
@@ -527,7 +544,7 @@ template <> struct Fast<OQG_CB14> {
   static __device__ __forceinline__ double base(const C &c, const Q &q,
                                                 const P &p, const Dist &d) {
     const double rrup = d.rrup;
-    double fdis = q.kdis * log(rrup * rrup + c.c7 * c.c7);
+    double fdis = q.kdis * fast_log(rrup * rrup + c.c7 * c.c7);
     double fhng_rx;
     if (d.rx >= q.r1) fhng_rx = fmax(1.0 + c.h5 * p.hx + c.h6 * (p.hx * p.hx), 0.0);
     else if (d.rx >= 0.) fhng_rx = c.h1 + c.h2 * p.hx + c.h3 * (p.hx * p.hx);
@@ -545,10 +562,10 @@ template <> struct Fast<OQG_CB14> {
     else p.hx = d.rx / qp.r1;
     p.hrr = d.rrup > 0.0 ? (d.rrup - d.rjb) / d.rrup : 1.;
     double b = base(Cp, qp, p, d);
-    p.a1100 = exp(b + sp.rock);
+    p.a1100 = fast_exp(b + sp.rock);
     double nl = 0.;
     if (sp.cvn >= 0.)
-      nl = Cp.k2 * log((p.a1100 + sp.cvn) / (p.a1100 + 1.88));
+      nl = Cp.k2 * fast_log((p.a1100 + sp.cvn) * fast_rcp(p.a1100 + 1.88));
     p.pga_mean = b + sp.lin + nl;
     return p;
   }
@@ -560,12 +577,13 @@ template <> struct Fast<OQG_CB14> {
                                               const SiteIn &, const Dist &d,
                                               double &mean, double &sig,
                                               double &inv) {
-    double eps = g.par[0] * epistemic_sigma(d.rrup, r.mag);
+    double eps = 0.;
+    if (g.par[0] != 0.) eps = g.par[0] * epistemic_sigma(d.rrup, r.mag);
     double nl = 0., alpha = 0.;
     if (s.cvn >= 0.) {
       double af1 = p.a1100 + s.cvn, af2 = p.a1100 + 1.88;
-      double w = 1. / (af1 * af2);
-      nl = c.k2 * log((af1 * af1) * w);
+      double w = fast_rcp(af1 * af2);
+      nl = c.k2 * fast_log((af1 * af1) * w);
       alpha = c.k2 * p.a1100 * ((af2 - af1) * w);
     }
     mean = base(c, q, p, d) + s.lin + nl;

@@ -80,6 +80,11 @@ struct Ba08C { BA08_FIELDS(OQG_DECL) };
 struct Ab06C { AB06_FIELDS(OQG_DECL) };
 struct Akkar14C { AKKAR14_FIELDS(OQG_DECL) };
 
+// the last OQG_KMAX - OQG_DER doubles of a row hold constants derived on the
+// host from the packed coefficients (oqg_set_gsims; read by oqg_fast.cuh)
+#define OQG_DER 48
+static_assert(sizeof(Ask14C) <= OQG_DER * 8 && sizeof(Cb14C) <= OQG_DER * 8 &&
+              sizeof(Cy14C) <= OQG_DER * 8, "derived slots overlap the row");
 static_assert(sizeof(Bssa14C) <= OQG_KMAX * 8, "row too long");
 static_assert(sizeof(Cy14C) <= OQG_KMAX * 8, "row too long");
 static_assert(sizeof(Ask14C) <= OQG_KMAX * 8, "row too long");

@@ -3,6 +3,7 @@ kernel: joins the SASS page of an ncu report with the line table of the
 cubin inside liboqg.so (nvdisasm -g; needs -lineinfo).
 
     python tools/ncu_lines.py gpurun_out/prof.ncu-rep <mangled-substring> [top]
+        [stall-column|''] [kernel-name-substring]
 """
 import os
 import re
@@ -40,10 +41,16 @@ def line_table(func_substr):
     return table
 
 
-def main(rep, func, top=40, stall=None):
+def main(rep, func, top=40, stall=None, kernel=None):
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    # one section per (kernel, view): keep the first section of the kernel
+    # whose name holds `kernel` (default: the first)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+    pick = [i for i in starts if kernel is None or kernel in rows[i][1]][0]
+    end = min([i for i in starts if i > pick] + [len(rows)])
+    rows = rows[pick:end]
     hdr = rows[1]
     ia, ii, isamp = (hdr.index('Address'), hdr.index('Instructions Executed'),
                      hdr.index(stall or '# Samples'))
