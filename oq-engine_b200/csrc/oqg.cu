@@ -35,7 +35,17 @@ using namespace oqg;
 #define OQG_MAX_G 16
 #define OQG_MAX_LEVELS 1024
 #define NL 20          // level accumulators per thread in the fused kernel
+#ifndef RT
 #define RT 16          // ruptures per shared-memory tile
+#endif
+#ifndef NLR
+#define NLR 10         // level accumulators kept in registers (fast path); the
+                       // upper NL - NLR levels, which the level skipping
+                       // reaches rarely, accumulate in shared memory
+#endif
+#ifndef LGRP
+#define LGRP 1         // levels evaluated per level-skipping test (NL % LGRP == 0)
+#endif
 #define NWMAX 7        // warps (units) per CTA in the fused kernel
 #ifndef MINB
 #define MINB 4         // CTAs per SM the fused kernel is compiled for
@@ -411,6 +421,8 @@ k_fused(const FusedArgs A) {
   double *s_p = s_q + (nw + 1) * RT * QW;          // [PW][RT][32]
   double *s_probs = s_p + PW * RT * 32;            // [RT][K]
   unsigned *s_valid = (unsigned *)(s_probs + (NEGBIN ? RT * A.K : 0));
+  float *s_hi = (float *)(s_valid + RT) + threadIdx.x;  // [NL - NLR][threads]
+  const int hs = blockDim.x;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int site0 = blockIdx.x * 32;
@@ -455,7 +467,7 @@ k_fused(const FusedArgs A) {
   // fast path: float32 accumulators per tile, flushed to the FP64 partial
   // sums of this thread in global memory (L2 resident)
   double acc[FAST ? 1 : NL];
-  float facc[FAST ? NL : 1];
+  float facc[FAST ? NLR : 1];
   const int L = A.M * A.L1;
   double *dst = A.part + (((int64_t)blockIdx.y * A.G + A.g) * A.N +
                           (site_ok ? n : 0)) * L + m * A.L1 + l0;
@@ -470,7 +482,9 @@ k_fused(const FusedArgs A) {
   unsigned long long kept = 0;
   if (FAST) {
 #pragma unroll
-    for (int l = 0; l < NL; l++) facc[l] = 0.f;
+    for (int l = 0; l < NLR; l++) facc[l] = 0.f;
+#pragma unroll
+    for (int l = NLR; l < NL; l++) s_hi[(l - NLR) * hs] = 0.f;
   }
   int tiles_left = FLUSH_TILES;
 
@@ -590,11 +604,25 @@ k_fused(const FusedArgs A) {
         key = __reduce_max_sync(vm, key);
         key ^= (key >> 31) & 0x7fffffff;
         const double thr_w = A.sorted ? (double)__int_as_float(key) : INFINITY;
+        // The test is made once per LGRP levels: the evaluations of a group
+        // are independent instruction chains in one basic block (a level
+        // past the threshold evaluates to exactly 0: x saturates to node 0)
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
+        for (int l = 0; l < NLR; l += LGRP) {
+          if (ll[l] >= thr_w) break;
+#pragma unroll
+          for (int j = 0; j < LGRP; j++)
+            facc[l + j] = fmaf(rt, poe_table(tab32, nm1, fma(ll[l + j], xa, xb)),
+                               facc[l + j]);
+        }
+        // the levels are sorted: if the loop above stopped early, this one
+        // stops at once
+#pragma unroll
+        for (int l = NLR; l < NL; l++) {
           const double lv = ll[l];
           if (lv >= thr_w) break;
-          facc[l] = fmaf(rt, poe_table(tab32, nm1, fma(lv, xa, xb)), facc[l]);
+          s_hi[(l - NLR) * hs] = fmaf(rt, poe_table(tab32, nm1, fma(lv, xa, xb)),
+                                      s_hi[(l - NLR) * hs]);
         }
       } else if (NEGBIN) {
         const double *pr = s_probs + i * A.K;
@@ -616,11 +644,16 @@ k_fused(const FusedArgs A) {
       tiles_left = FLUSH_TILES;
       if (site_ok) {
 #pragma unroll
-        for (int l = 0; l < NL; l++)
+        for (int l = 0; l < NLR; l++)
           if (l < nl) dst[l] += (double)facc[l];
+#pragma unroll
+        for (int l = NLR; l < NL; l++)
+          if (l < nl) dst[l] += (double)s_hi[(l - NLR) * hs];
       }
 #pragma unroll
-      for (int l = 0; l < NL; l++) facc[l] = 0.f;
+      for (int l = 0; l < NLR; l++) facc[l] = 0.f;
+#pragma unroll
+      for (int l = NLR; l < NL; l++) s_hi[(l - NLR) * hs] = 0.f;
     }
   }
 #undef DGET
@@ -1111,7 +1144,8 @@ static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
   size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
                  NF_SITE * 32 + (size_t)(nw + 1) * RT * QW +
                  (size_t)PW * RT * 32 + (A.K ? RT * A.K : 0)) * 8 +
-                (fast ? A.pt_nodes * PT_STRIDE * 4 : 0) + RT * 4;
+                (fast ? A.pt_nodes * PT_STRIDE * 4 : 0) + RT * 4 +
+                (fast ? (size_t)(NL - NLR) * threads * 4 : 0);
   if (A.K) return launch_fused2<F, true, false>(A, grid, threads, smem, st);
   if (fast) return launch_fused2<F, false, true>(A, grid, threads, smem, st);
   return launch_fused2<F, false, false>(A, grid, threads, smem, st);
