@@ -184,6 +184,47 @@ int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
                            int rates_mode, float *map,
                            unsigned long long *pairs_kept);
 
+/* ---- rupture generation of point sources on the device --
+ * replaces PointSource.get_planar / get_planin (source/point.py:192-289) and
+ * build_planar / _build_corners (geo/surface/planar.py:107-251) for a batch
+ * of S point sources given as a struct of DEVICE arrays.  The magnitude
+ * frequency distribution, nodal plane distribution and hypocentral depth
+ * distribution of source s are the slices [beg, beg + cnt) of the shared
+ * lists below (area sources: all the points share one slice).  The ruptures
+ * of a source are ordered (magnitude, nodal plane, depth) as in the
+ * reference; rup_off[s] is the index of the first rupture of source s,
+ * rup_off[S] = U = sum of mag_cnt * np_cnt * hd_cnt. */
+enum { OQG_MSR_WC1994 = 0,   /* scalerel/wc1994.py get_median_area */
+       OQG_MSR_POINT = 1 };  /* scalerel/point.py PointMSR */
+typedef struct {
+  const double *lon, *lat;            /* [S] location, degrees */
+  const double *usd, *lsd, *rar;      /* [S] upper / lower seismogenic depth
+                                         (km), rupture aspect ratio */
+  const int32_t *mag_beg, *mag_cnt;   /* [S] */
+  const int32_t *np_beg, *np_cnt;     /* [S] */
+  const int32_t *hd_beg, *hd_cnt;     /* [S] */
+  const int64_t *rup_off;             /* [S + 1] */
+  const double *mag, *mag_rate;       /* magnitudes and annual rates
+                                         (get_annual_occurrence_rates) */
+  const double *mag_dist;             /* integration distance of each
+                                         magnitude, km; may be NULL */
+  const double *np_strike, *np_dip, *np_rake, *np_prob;
+  const double *hd_depth, *hd_prob;
+  const double *hd_frac;              /* hypo_dip_fracs; NULL = 0.5 */
+  int32_t msr;                        /* OQG_MSR_* */
+  int32_t shift_hypo;                 /* ContextMaker.shift_hypo */
+} oqg_point_sources;
+
+/* planar_dev[U][42] in the planar_array_dt record layout, except that wlr[2]
+ * holds the occurrence rate mag_rate * (np_prob * hd_prob) (the convention
+ * of oqg_hazard_planar; the reference keeps the weight there and multiplies
+ * by the magnitude rate in _get_ctx_planar, contexts.py:416);
+ * mag_dev[U]; magdist_dev[U] (NULL if mag_dist is NULL).  An unknown msr is
+ * an error. */
+int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
+                       int64_t U, double *planar_dev, double *mag_dev,
+                       double *magdist_dev);
+
 /* The fused kernel evaluates the PoEs from a float32 polynomial table of
  * the truncated-normal survival function (argument in float64) when the
  * table built for the truncation level reproduces the exact formula to 2e-6

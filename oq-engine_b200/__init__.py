@@ -16,6 +16,9 @@ from .map_array import MapArray  # noqa
 from .planar import build_planar, planar_array_dt, wc1994_median_area  # noqa
 from .site import SiteCollection  # noqa
 from .contexts import ContextMaker, IntegrationDistance, PlanarRuptures  # noqa
+from .source import (  # noqa
+    PointSource, PointSourceBatch, TruncatedGRMFD, EvenlyDiscretizedMFD,
+    ArbitraryMFD, point_ruptures_device)
 from . import sharding  # noqa
 
 __version__ = '0.1.0'

@@ -314,6 +314,9 @@ class ContextMaker(object):
         self.maximum_distance = _interp(param, 'maximum_distance', trt)
         self.minimum_distance = param.get('minimum_distance', 0)
         self.investigation_time = param.get('investigation_time')
+        self.shift_hypo = param.get('shift_hypo', False)
+        self.pointsource_distance = float(
+            param.get('pointsource_distance') or 0)
         self.truncation_level = param.get('truncation_level', 99.)
         self.phi_b = float(ndtr(self.truncation_level))
         self.device = device
@@ -589,6 +592,16 @@ class ContextMaker(object):
         t_pla = _dev(as_flat(src.planar), dev)
         t_mag = _dev(src.mag, dev)
         t_md = _dev(self.magdist(src.mag), dev)
+        return self._hazard_planar_dev(pmap, t_pla, t_mag, t_md, t_probs, K,
+                                       U, sitecol, count)
+
+    def _hazard_planar_dev(self, pmap, t_pla, t_mag, t_md, t_probs, K, U,
+                           sitecol, count):
+        # ruptures already on the device -> oqg_hazard_planar
+        import torch
+        h = self.handle()
+        dev = h.device
+        N = len(sitecol)
         st, keep = self._sites_struct(sitecol, dev)
         t_sidx = _dev(pmap.sidx[sitecol.sids].astype(numpy.uint32), dev)
         on_host = pmap.device is None
@@ -597,12 +610,51 @@ class ContextMaker(object):
             if count else None
         h.call('oqg_hazard_planar', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
                _ptr(t_probs), K, U, ctypes.byref(st), _ptr(t_sidx), N,
-               float(self.minimum_distance), float(tom.time_span),
+               float(self.minimum_distance), float(self.tom.time_span),
                int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
         if on_host:
             pmap.array[:] = t_map.cpu().numpy()
         if count:
             return int(t_cnt[0].item())
+
+    def hazard_point_sources(self, pmap, sources, sitecol, count=False):
+        """
+        Fold all the ruptures of a list of point sources (source.PointSource,
+        or a source.PointSourceBatch) into `pmap`: the equivalent of
+        ``for src in sources: for ctx in get_ctxs(src, sitecol):
+        update(pmap, ctx)`` (genctxs_Pp, contexts.py:443-474) with the
+        ruptures built on the device (oqg_point_ruptures) and no context
+        rows materialised.  As in the reference with the default
+        pointsource_distance, every rupture of every (magnitude, nodal
+        plane, depth) combination is used; the pointsource_distance
+        approximation of _quintets (contexts.py:321-370) is not applied.
+        """
+        from .source import PointSourceBatch, point_ruptures_device
+        batch = sources if isinstance(sources, PointSourceBatch) \
+            else PointSourceBatch(sources)
+        # the reference's default (1000 km) keeps every site "close", i.e.
+        # no approximation; a smaller value replaces, for far sites, the
+        # nodal planes / depths by one average rupture (_quintets)
+        if 0 < self.pointsource_distance < 1000 and (
+                batch.cnt['np'] * batch.cnt['hd'] > 1).any():
+            raise NotImplementedError(
+                'the pointsource_distance approximation has no device '
+                'implementation')
+        h = self.handle()
+        tom = self.tom or PoissonTOM(self.investigation_time)
+        self.tom = tom
+        if batch.U == 0 or len(sitecol) == 0:
+            return 0
+        K, t_probs = 0, None
+        if hasattr(tom, 'get_pmf'):
+            _mag, rate = batch.expand()
+            probs = numpy.ascontiguousarray(tom.get_pmf(rate))
+            K = probs.shape[1]
+            t_probs = _dev(probs, h.device)
+        t_pla, t_mag, t_md = point_ruptures_device(
+            batch, h, self.magdist(batch.mag), self.shift_hypo)
+        return self._hazard_planar_dev(pmap, t_pla, t_mag, t_md, t_probs, K,
+                                       batch.U, sitecol, count)
 
     def get_pmap_planar(self, src, sitecol):
         """PoE map of planar ruptures on the sites through the fused path"""

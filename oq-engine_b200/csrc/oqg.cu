@@ -28,6 +28,7 @@
 #include "oqg_geo.cuh"
 #include "oqg_poe.cuh"
 #include "oqg_fast.cuh"
+#include "oqg_source.cuh"
 
 using namespace oqg;
 
@@ -145,6 +146,37 @@ __global__ void k_prep_ruptures(const double *__restrict__ planar,
   double pl[OQG_PLANAR_LEN];
   for (int k = 0; k < OQG_PLANAR_LEN; k++) pl[k] = planar[u * OQG_PLANAR_LEN + k];
   prep_rupture(pl, mag[u], magdist ? magdist[u] : INFINITY, out + u, U);
+}
+
+// one thread per rupture of a batch of point sources (oqg_source.cuh)
+__global__ void k_point_ruptures(const oqg_point_sources P, int S, int64_t U,
+                                 double *__restrict__ planar,
+                                 double *__restrict__ mag_out,
+                                 double *__restrict__ magdist_out) {
+  int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  int lo = 0, hi = S;   // last s with rup_off[s] <= u
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (P.rup_off[mid] <= u) lo = mid; else hi = mid;
+  }
+  const int s = lo;
+  const int64_t r = u - P.rup_off[s];
+  const int N = P.np_cnt[s], D = P.hd_cnt[s];
+  const int m = (int)(r / ((int64_t)N * D));
+  const int n = (int)((r / D) % N), d = (int)(r % D);
+  const int im = P.mag_beg[s] + m, in = P.np_beg[s] + n, id = P.hd_beg[s] + d;
+  const double mag = P.mag[im], rake = P.np_rake[in];
+  const double weight = P.np_prob[in] * P.hd_prob[id];
+  double pl[OQG_PLANAR_LEN];
+  build_planar_rupture(P.usd[s], P.lsd[s], P.rar[s],
+                       median_area(P.msr, mag, rake), P.np_strike[in],
+                       P.np_dip[in], rake, P.lon[s], P.lat[s], P.hd_depth[id],
+                       P.hd_frac ? P.hd_frac[id] : 0.5,
+                       P.mag_rate[im] * weight, P.shift_hypo, pl);
+  for (int k = 0; k < OQG_PLANAR_LEN; k++) planar[u * OQG_PLANAR_LEN + k] = pl[k];
+  mag_out[u] = mag;
+  if (magdist_out) magdist_out[u] = P.mag_dist[im];
 }
 
 __global__ void k_prep_sites(const double *__restrict__ lon,
@@ -956,6 +988,29 @@ static int prep_ruptures(oqg_handle *h, const double *planar,
   if (reserve(h, h->rup, (size_t)NF_RUP * U * 8)) return 1;
   k_prep_ruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
       planar, mag, magdist, U, (double *)h->rup.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
+                       int64_t U, double *planar, double *mag,
+                       double *magdist) {
+  CK(cudaSetDevice(h->device));
+  if (S <= 0 || U <= 0) return 0;
+  if (src->msr != OQG_MSR_WC1994 && src->msr != OQG_MSR_POINT)
+    return fail(h, "unsupported magnitude-scaling relationship (no fallback)");
+  if (!src->lon || !src->lat || !src->usd || !src->lsd || !src->rar ||
+      !src->mag_beg || !src->mag_cnt || !src->np_beg || !src->np_cnt ||
+      !src->hd_beg || !src->hd_cnt || !src->rup_off || !src->mag ||
+      !src->mag_rate || !src->np_strike || !src->np_dip || !src->np_rake ||
+      !src->np_prob || !src->hd_depth || !src->hd_prob)
+    return fail(h, "point sources: missing array");
+  if (!planar || !mag) return fail(h, "point sources: missing output");
+  if (magdist && !src->mag_dist)
+    return fail(h, "point sources: magdist output without mag_dist");
+  k_point_ruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
+      *src, S, U, planar, mag, magdist);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

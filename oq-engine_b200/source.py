@@ -1,0 +1,282 @@
+"""Point sources: the host-side description the rupture generator on the
+device consumes.
+
+Mirrors the slice of the reference a classical calculation touches before the
+hot path: the magnitude-frequency distributions
+(openquake/hazardlib/mfd/truncated_gr.py:103-164, evenly_discretized.py,
+arbitrary_mfd.py), `PointSource` with its nodal-plane and hypocentral-depth
+distributions (source/point.py:60-196) and `get_annual_occurrence_rates`
+(source/base.py:459-477).  The ruptures themselves (`get_planar`,
+point.py:258-289) are built on the device by `oqg_point_ruptures`; nothing
+here loops over ruptures.
+"""
+import math
+import ctypes
+import numpy
+
+from . import _lib
+
+MSR = {'WC1994': 0, 'PointMSR': 1}
+
+
+def _round(x):
+    # baselib/general.py:566-571: the Python-2 rounding the MFDs use
+    return float(math.floor(x + math.copysign(0.5, x)))
+
+
+class TruncatedGRMFD(object):
+    """mfd/truncated_gr.py: rates of a doubly truncated Gutenberg-Richter
+    distribution evenly discretised in bins of `bin_width`"""
+    def __init__(self, min_mag, max_mag, bin_width, a_val, b_val):
+        if not bin_width > 0:
+            raise ValueError('bin width %g must be positive' % bin_width)
+        if not min_mag >= 0:
+            raise ValueError('minimum magnitude %g must be non-negative'
+                             % min_mag)
+        if not max_mag >= min_mag + bin_width:
+            raise ValueError('maximum magnitude %g must be higher than '
+                             'minimum magnitude %g by bin width %g at least'
+                             % (max_mag, min_mag, bin_width))
+        if b_val <= 0:
+            raise ValueError('b-value %g must be non-negative' % b_val)
+        self.min_mag, self.max_mag, self.bin_width = min_mag, max_mag, bin_width
+        self.a_val, self.b_val = a_val, b_val
+
+    def get_annual_occurrence_rates(self):
+        bw = self.bin_width
+        lo = _round(self.min_mag / bw) * bw
+        hi = _round(self.max_mag / bw) * bw
+        if lo != hi:
+            lo += bw / 2.0
+            hi -= bw / 2.0
+        nbins = int(_round((hi - lo) / bw)) + 1
+        out, mag = [], lo
+        for _ in range(nbins):
+            out.append((mag, 10 ** (self.a_val - self.b_val * (mag - bw / 2.0))
+                        - 10 ** (self.a_val - self.b_val * (mag + bw / 2.0))))
+            mag += bw
+        return out
+
+
+class EvenlyDiscretizedMFD(object):
+    """mfd/evenly_discretized.py"""
+    def __init__(self, min_mag, bin_width, occurrence_rates):
+        if not bin_width > 0:
+            raise ValueError('bin width must be positive')
+        if not len(occurrence_rates):
+            raise ValueError('at least one bin must be specified')
+        if not all(r >= 0 for r in occurrence_rates):
+            raise ValueError('all occurrence rates must not be negative')
+        self.min_mag, self.bin_width = min_mag, bin_width
+        self.occurrence_rates = list(occurrence_rates)
+
+    def get_annual_occurrence_rates(self):
+        return [(self.min_mag + i * self.bin_width, r)
+                for i, r in enumerate(self.occurrence_rates)]
+
+
+class ArbitraryMFD(object):
+    """mfd/arbitrary_mfd.py"""
+    def __init__(self, magnitudes, occurrence_rates):
+        if len(magnitudes) != len(occurrence_rates):
+            raise ValueError('magnitudes and rates of different length')
+        self.magnitudes = list(magnitudes)
+        self.occurrence_rates = list(occurrence_rates)
+
+    def get_annual_occurrence_rates(self):
+        return list(zip(self.magnitudes, self.occurrence_rates))
+
+
+class PointSource(object):
+    """
+    source/point.py PointSource, the attributes the rupture generation reads.
+
+    :param mfd: an object with get_annual_occurrence_rates()
+    :param msr: 'WC1994' or 'PointMSR' (anything else is an error: there is
+        no device implementation to fall back from)
+    :param nodal_plane_distribution: [(prob, strike, dip, rake), ...]
+    :param hypocenter_distribution: [(prob, depth), ...]
+    :param hypo_dip_fracs: optional, one down-dip fraction per depth
+    """
+    def __init__(self, source_id, lon, lat, mfd, msr, rupture_aspect_ratio,
+                 upper_seismogenic_depth, lower_seismogenic_depth,
+                 nodal_plane_distribution, hypocenter_distribution,
+                 hypo_dip_fracs=None, tectonic_region_type='*'):
+        if msr not in MSR:
+            raise NotImplementedError(
+                'magnitude-scaling relationship %s has no device '
+                'implementation' % msr)
+        if not lower_seismogenic_depth > upper_seismogenic_depth:
+            raise ValueError('lower seismogenic depth must be below '
+                             'upper seismogenic depth')
+        for _p, depth in hypocenter_distribution:
+            if depth > lower_seismogenic_depth:
+                raise ValueError('source_id=%r depth=%r is below '
+                                 'lower_seismogenic_depth=%r' % (
+                                     source_id, depth,
+                                     lower_seismogenic_depth))
+            elif depth < upper_seismogenic_depth:
+                raise ValueError('source_id=%r depth=%r is over '
+                                 'upper_seismogenic_depth=%r' % (
+                                     source_id, depth,
+                                     upper_seismogenic_depth))
+        self.source_id, self.lon, self.lat = source_id, lon, lat
+        self.mfd, self.msr = mfd, msr
+        self.rupture_aspect_ratio = rupture_aspect_ratio
+        self.upper_seismogenic_depth = upper_seismogenic_depth
+        self.lower_seismogenic_depth = lower_seismogenic_depth
+        self.nodal_plane_distribution = list(nodal_plane_distribution)
+        self.hypocenter_distribution = list(hypocenter_distribution)
+        self.hypo_dip_fracs = hypo_dip_fracs
+        self.tectonic_region_type = tectonic_region_type
+
+    def get_annual_occurrence_rates(self, min_rate=0):
+        # source/base.py:459-477
+        return [(m, r) for m, r in self.mfd.get_annual_occurrence_rates()
+                if min_rate is None or r > min_rate]
+
+    def count_nphc(self):
+        return len(self.nodal_plane_distribution) * len(
+            self.hypocenter_distribution)
+
+    def count_ruptures(self):
+        return len(self.get_annual_occurrence_rates()) * self.count_nphc()
+
+
+class OqgPointSources(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        'lon', 'lat', 'usd', 'lsd', 'rar', 'mag_beg', 'mag_cnt', 'np_beg',
+        'np_cnt', 'hd_beg', 'hd_cnt', 'rup_off', 'mag', 'mag_rate',
+        'mag_dist', 'np_strike', 'np_dip', 'np_rake', 'np_prob', 'hd_depth',
+        'hd_prob', 'hd_frac')] + [('msr', ctypes.c_int32),
+                                  ('shift_hypo', ctypes.c_int32)]
+
+
+class PointSourceBatch(object):
+    """
+    S point sources as the struct of arrays of `oqg_point_sources`
+    (include/oqg.h).  Sources sharing the same MFD object or equal nodal-plane /
+    depth distributions (the points of an area source) share one slice of
+    the lists.
+    """
+    def __init__(self, sources):
+        sources = list(sources)
+        if not sources:
+            raise ValueError('no sources')
+        msrs = {s.msr for s in sources}
+        if len(msrs) != 1:
+            raise ValueError('one magnitude-scaling relationship per batch, '
+                             'got %s' % sorted(msrs))
+        self.msr = MSR[msrs.pop()]
+        S = self.S = len(sources)
+        f = lambda name: numpy.array([getattr(s, name) for s in sources],  # noqa
+                                     float)
+        self.lon, self.lat = f('lon'), f('lat')
+        self.usd, self.lsd = (f('upper_seismogenic_depth'),
+                              f('lower_seismogenic_depth'))
+        self.rar = f('rupture_aspect_ratio')
+        lists = {k: [] for k in ('mag', 'mag_rate', 'np', 'hd', 'frac')}
+        slices = {'mag': {}, 'np': {}, 'hd': {}}
+        beg = {k: numpy.zeros(S, numpy.int32) for k in slices}
+        cnt = {k: numpy.zeros(S, numpy.int32) for k in slices}
+        any_frac = any(s.hypo_dip_fracs is not None for s in sources)
+        for i, s in enumerate(sources):
+            key = id(s.mfd)
+            if key not in slices['mag']:
+                mr = s.get_annual_occurrence_rates()
+                slices['mag'][key] = (len(lists['mag']), len(mr))
+                lists['mag'] += [m for m, _ in mr]
+                lists['mag_rate'] += [r for _, r in mr]
+            npkey = tuple(tuple(x) for x in s.nodal_plane_distribution)
+            if npkey not in slices['np']:
+                slices['np'][npkey] = (len(lists['np']), len(npkey))
+                lists['np'] += list(npkey)
+            fr = s.hypo_dip_fracs
+            fracs = tuple(0.5 if fr is None or fr[d] is None else fr[d]
+                          for d in range(len(s.hypocenter_distribution)))
+            hdkey = (tuple(tuple(x) for x in s.hypocenter_distribution), fracs)
+            if hdkey not in slices['hd']:
+                slices['hd'][hdkey] = (len(lists['hd']), len(fracs))
+                lists['hd'] += list(hdkey[0])
+                lists['frac'] += list(fracs)
+            for k, key in (('mag', id(s.mfd)), ('np', npkey), ('hd', hdkey)):
+                beg[k][i], cnt[k][i] = slices[k][key]
+        self.beg, self.cnt = beg, cnt
+        self.mag = numpy.array(lists['mag'], float)
+        self.mag_rate = numpy.array(lists['mag_rate'], float)
+        npd = numpy.array(lists['np'], float).reshape(-1, 4)
+        self.np_prob, self.np_strike, self.np_dip, self.np_rake = (
+            numpy.ascontiguousarray(npd[:, k]) for k in range(4))
+        hdd = numpy.array(lists['hd'], float).reshape(-1, 2)
+        self.hd_prob, self.hd_depth = (
+            numpy.ascontiguousarray(hdd[:, k]) for k in range(2))
+        self.hd_frac = numpy.array(lists['frac'], float) if any_frac else None
+        n = (cnt['mag'].astype(numpy.int64) * cnt['np'] * cnt['hd'])
+        self.rup_off = numpy.concatenate([[0], numpy.cumsum(n)]).astype(
+            numpy.int64)
+        self.U = int(self.rup_off[-1])
+
+    def __len__(self):
+        return self.U
+
+    def expand(self):
+        """(mag, occurrence_rate) of every rupture in device order, on the
+        host (needed only for non-Poissonian temporal occurrence models)"""
+        mags, rates = [], []
+        for s in range(self.S):
+            mb, mc = self.beg['mag'][s], self.cnt['mag'][s]
+            nb, nc = self.beg['np'][s], self.cnt['np'][s]
+            hb, hc = self.beg['hd'][s], self.cnt['hd'][s]
+            w = (self.np_prob[nb:nb + nc, None] *
+                 self.hd_prob[None, hb:hb + hc]).ravel()
+            mags.append(numpy.repeat(self.mag[mb:mb + mc], nc * hc))
+            rates.append((self.mag_rate[mb:mb + mc, None] * w[None]).ravel())
+        return numpy.concatenate(mags), numpy.concatenate(rates)
+
+    def to_device(self, dev, mag_dist=None, shift_hypo=False):
+        """:returns: (OqgPointSources struct, list of tensors kept alive)"""
+        from .contexts import _dev
+        keep = {}
+
+        def up(name, arr):
+            if arr is None:
+                return None
+            keep[name] = _dev(arr, dev)
+            return keep[name].data_ptr()
+        st = OqgPointSources()
+        for name in ('lon', 'lat', 'usd', 'lsd', 'rar', 'rup_off', 'mag',
+                     'mag_rate', 'np_strike', 'np_dip', 'np_rake', 'np_prob',
+                     'hd_depth', 'hd_prob', 'hd_frac'):
+            setattr(st, name, up(name, getattr(self, name)))
+        for k in ('mag', 'np', 'hd'):
+            setattr(st, k + '_beg', up(k + '_beg', self.beg[k]))
+            setattr(st, k + '_cnt', up(k + '_cnt', self.cnt[k]))
+        st.mag_dist = up('mag_dist', mag_dist)
+        st.msr = self.msr
+        st.shift_hypo = int(bool(shift_hypo))
+        return st, keep
+
+
+def point_ruptures_device(batch, handle, mag_dist=None, shift_hypo=False):
+    """
+    Build the planar ruptures of a PointSourceBatch on the handle's device:
+    returns torch CUDA tensors (planar (U, 42), mag (U,), magdist (U,) or
+    None).  The equivalent of PointSource.get_planar for every source.
+    """
+    import torch
+    dev = handle.device
+    st, keep = batch.to_device(dev, mag_dist, shift_hypo)
+    U = batch.U
+    cuda = 'cuda:%d' % dev
+    t_pla = torch.empty((U, _lib.PLANAR_LEN), dtype=torch.float64, device=cuda)
+    t_mag = torch.empty(U, dtype=torch.float64, device=cuda)
+    t_md = torch.empty(U, dtype=torch.float64, device=cuda) \
+        if mag_dist is not None else None
+    handle.call('oqg_point_ruptures', ctypes.byref(st), batch.S, U,
+                ctypes.c_void_p(t_pla.data_ptr()),
+                ctypes.c_void_p(t_mag.data_ptr()),
+                ctypes.c_void_p(t_md.data_ptr() if t_md is not None else None))
+    # the source arrays must outlive the kernel: the launch is asynchronous
+    torch.cuda.current_stream(dev).synchronize()
+    del keep
+    return t_pla, t_mag, t_md

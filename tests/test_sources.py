@@ -1,0 +1,271 @@
+"""Rupture generation of point sources and
+BASELINE.json configs[0] (the AreaSourceClassicalPSHA demo).
+
+CPU part: the oracle (oracle/source_np.py) and the host-side MFD / batch
+logic against the fixtures produced by the reference
+(oracle/make_golden_sources.py).  GPU part (-m gpu): oqg_point_ruptures
+against the reference's PointSource.get_planar output, and the demo's hazard
+curves through ContextMaker.hazard_point_sources against the reference's
+ContextMaker.get_ctxs -> update.
+"""
+import os
+import numpy as np
+import pytest
+
+import source_np
+import hazard_np
+from helpers import GOLDEN
+
+PS = np.load(os.path.join(GOLDEN, 'point_sources.npz'))
+NAMES = [str(n) for n in PS['names']]
+
+
+def case(name):
+    g = lambda k: PS[name + '__' + k]  # noqa
+    sc = g('scalars')
+    d = dict(lon=sc[0], lat=sc[1], usd=sc[2], lsd=sc[3], rar=sc[4],
+             shift=bool(sc[5]), msr=str(g('msr')), mags=g('mags'),
+             mag_rates=g('mag_rates'), npd=[tuple(x) for x in g('npd')],
+             hdd=[tuple(x) for x in g('hdd')],
+             dip_fracs=(list(g('dip_fracs'))
+                        if name + '__dip_fracs' in PS.files else None),
+             planar=g('planar'), mag=g('mag'), rate=g('rate'))
+    if name + '__gr' in PS.files:
+        d['gr'] = g('gr')
+    return d
+
+
+def flat(pla):
+    U = len(pla['wlr'])
+    out = np.zeros((U, 3, 14))
+    out[:, :, 0:4] = pla['corners']
+    out[:, :, 4:8] = pla['xyz']
+    for k, name in enumerate(('normal', 'uv1', 'uv2', 'wlr', 'sdr', 'hypo')):
+        out[:, :, 8 + k] = pla[name]
+    return out.reshape(U, 42)
+
+
+def as_source(oq, d, sid='1'):
+    mfd = oq.ArbitraryMFD(d['mags'], d['mag_rates'])
+    return oq.PointSource(sid, d['lon'], d['lat'], mfd, d['msr'], d['rar'],
+                          d['usd'], d['lsd'], d['npd'], d['hdd'],
+                          d['dip_fracs'])
+
+
+# ------------------------------------------------------------------ CPU
+@pytest.mark.parametrize('name', NAMES)
+def test_oracle_point_ruptures_golden(name):
+    d = case(name)
+    pla, mag, rate = source_np.point_source_ruptures(d, d['shift'])
+    np.testing.assert_allclose(flat(pla), d['planar'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(mag, d['mag'])
+    np.testing.assert_allclose(rate, d['rate'], rtol=1e-15)
+
+
+@pytest.mark.parametrize('name', [n for n in NAMES if n + '__gr' in PS.files])
+def test_truncated_gr_matches_reference(name):
+    import oq_engine_b200 as oq
+    d = case(name)
+    # the area source spreads its MFD evenly over its points
+    # (source/area.py: rates scaled by 1 / number of points)
+    total = oq.TruncatedGRMFD(*d['gr'])
+    mags, rates = zip(*total.get_annual_occurrence_rates())
+    np.testing.assert_allclose(mags, d['mags'], rtol=1e-15)
+    np.testing.assert_allclose(np.array(rates) / len(d['src_lon']),
+                               d['mag_rates'], rtol=1e-14)
+    mfd = oq.ArbitraryMFD(d['mags'], d['mag_rates'])
+    m, r = source_np.truncated_gr_rates(*d['gr'])
+    np.testing.assert_allclose(m, d['mags'], rtol=1e-15)
+    np.testing.assert_allclose(r, d['mag_rates'], rtol=1e-15)
+
+
+def test_mfd_validation_errors():
+    import oq_engine_b200 as oq
+    with pytest.raises(ValueError):
+        oq.TruncatedGRMFD(5., 5.05, 0.1, 4., 1.)   # narrower than a bin
+    with pytest.raises(ValueError):
+        oq.TruncatedGRMFD(5., 6., 0., 4., 1.)
+    with pytest.raises(ValueError):
+        oq.EvenlyDiscretizedMFD(5., 0.1, [])
+    e = oq.EvenlyDiscretizedMFD(5.05, 0.1, [1e-2, 1e-3])
+    assert e.get_annual_occurrence_rates() == [(5.05, 1e-2),
+                                               (5.05 + 1 * 0.1, 1e-3)]
+
+
+def test_point_source_validation_errors():
+    import oq_engine_b200 as oq
+    mfd = oq.ArbitraryMFD([5.], [1e-2])
+    ok = dict(nodal_plane_distribution=[(1., 0., 90., 0.)],
+              hypocenter_distribution=[(1., 5.)])
+    with pytest.raises(NotImplementedError):   # no device implementation
+        oq.PointSource('1', 0., 0., mfd, 'Leonard2014_SCR', 1., 0., 10., **ok)
+    with pytest.raises(ValueError):            # lsd above usd
+        oq.PointSource('1', 0., 0., mfd, 'WC1994', 1., 10., 5., **ok)
+    with pytest.raises(ValueError):            # depth below lsd
+        oq.PointSource('1', 0., 0., mfd, 'WC1994', 1., 0., 4., **ok)
+
+
+def test_batch_layout_and_expand():
+    import oq_engine_b200 as oq
+    srcs = [as_source(oq, case(n), n) for n in NAMES if n != 'pointmsr']
+    # two sources sharing the same distributions share one slice
+    d = case('multi')
+    twin = oq.PointSource('twin', 1., 2., srcs[1].mfd, 'WC1994', 2., 0., 12.,
+                          srcs[1].nodal_plane_distribution,
+                          srcs[1].hypocenter_distribution)
+    b = oq.PointSourceBatch(srcs + [twin])
+    assert b.S == 4 and b.U == 8 + 54 + 32 + 54
+    assert list(b.rup_off) == [0, 8, 62, 94, 148]
+    assert b.beg['mag'][1] == b.beg['mag'][3]
+    assert b.beg['np'][1] == b.beg['np'][3]
+    assert len(b.mag) == 8 + 9 + 8   # the twin adds nothing
+    mag, rate = b.expand()
+    want_mag = np.concatenate([case(n)['mag'] for n in
+                               ('single', 'multi', 'dipfrac_shift', 'multi')])
+    want_rate = np.concatenate([case(n)['rate'] for n in
+                                ('single', 'multi', 'dipfrac_shift', 'multi')])
+    np.testing.assert_array_equal(mag, want_mag)
+    np.testing.assert_allclose(rate, want_rate, rtol=1e-15)
+    assert b.hd_frac is not None and b.hd_frac[-2] == 0.25
+    with pytest.raises(ValueError):            # mixed scaling relationships
+        oq.PointSourceBatch(srcs + [as_source(oq, case('pointmsr'))])
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.fixture(scope='module')
+def oq():
+    import oq_engine_b200
+    oq_engine_b200._lib.lib()
+    return oq_engine_b200
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', NAMES)
+def test_device_point_ruptures_golden(oq, name):
+    d = case(name)
+    h = oq.contexts.get_handle()
+    b = oq.PointSourceBatch([as_source(oq, d)])
+    md = np.linspace(100., 300., len(b.mag))
+    t_pla, t_mag, t_md = oq.point_ruptures_device(b, h, md, d['shift'])
+    pla = t_pla.cpu().numpy()
+    want = d['planar'].copy()
+    # wlr[2] of the device ruptures is the occurrence rate, of the
+    # reference's planar array the (nodal plane x depth) weight
+    got_rate, pla[:, 2 * 14 + 11] = pla[:, 2 * 14 + 11].copy(), 0.
+    want[:, 2 * 14 + 11] = 0.
+    # PointMSR ruptures are 10 m x 10 m: their unit vectors and sizes come
+    # from differences of corner coordinates of magnitude 6371 km that agree
+    # to 6 digits, conditioned to ~1e-9 relative in the reference itself
+    tol = 5e-9 if d['msr'] == 'PointMSR' else 1e-11
+    np.testing.assert_allclose(pla, want, rtol=tol, atol=tol)
+    np.testing.assert_allclose(got_rate, d['rate'], rtol=1e-15)
+    np.testing.assert_array_equal(t_mag.cpu().numpy(), d['mag'])
+    nphc = len(d['npd']) * len(d['hdd'])
+    np.testing.assert_array_equal(t_md.cpu().numpy(), np.repeat(md, nphc))
+
+
+@pytest.mark.gpu
+def test_device_point_ruptures_many_sources(oq):
+    """a batch of sources with shared and own distributions against the
+    oracle, source by source"""
+    rng = np.random.default_rng(5)
+    mfd = oq.TruncatedGRMFD(4.7, 7.2, 0.1, 3.9, 0.95)
+    npd = [(0.25, 0., 90., 0.), (0.25, 45., 60., 90.), (0.5, 200., 35., -90.)]
+    hdd = [(0.2, 3.), (0.5, 8.), (0.3, 17.)]
+    srcs, descs = [], []
+    for i in range(40):
+        lon, lat = rng.uniform(-180, 180), rng.uniform(-70, 70)
+        own = i % 5 == 0
+        m = oq.EvenlyDiscretizedMFD(5.05, 0.2, list(rng.uniform(1e-4, 1e-2, 6))
+                                    ) if own else mfd
+        srcs.append(oq.PointSource(str(i), lon, lat, m, 'WC1994', 1.5, 0., 20.,
+                                   npd, hdd))
+        mags, rates = zip(*m.get_annual_occurrence_rates())
+        descs.append(dict(lon=lon, lat=lat, usd=0., lsd=20., rar=1.5,
+                          msr='WC1994', mags=mags, mag_rates=rates, npd=npd,
+                          hdd=hdd))
+    b = oq.PointSourceBatch(srcs)
+    t_pla, t_mag, _ = oq.point_ruptures_device(b, oq.contexts.get_handle())
+    pla, mag = t_pla.cpu().numpy(), t_mag.cpu().numpy()
+    for s, d in enumerate(descs):
+        opla, omag, orate = source_np.point_source_ruptures(d)
+        want = flat(opla)
+        want[:, 2 * 14 + 11] = orate
+        sl = slice(b.rup_off[s], b.rup_off[s + 1])
+        np.testing.assert_allclose(pla[sl], want, rtol=1e-11, atol=1e-11)
+        np.testing.assert_array_equal(mag[sl], omag)
+
+
+@pytest.mark.gpu
+def test_cfg1_area_source_demo(oq):
+    """BASELINE.json configs[0]: demos/hazard/AreaSourceClassicalPSHA
+    (BooreAtkinson2008, 8 IMTs x 45 levels, 200 km) -- hazard curves of the
+    reference's ContextMaker path on the same point sources and sites"""
+    d = np.load(os.path.join(GOLDEN, 'cfg1_area_demo.npz'))
+    # the area source spreads its MFD evenly over its points
+    # (source/area.py: rates scaled by 1 / number of points)
+    total = oq.TruncatedGRMFD(*d['gr'])
+    mags, rates = zip(*total.get_annual_occurrence_rates())
+    np.testing.assert_allclose(mags, d['mags'], rtol=1e-15)
+    np.testing.assert_allclose(np.array(rates) / len(d['src_lon']),
+                               d['mag_rates'], rtol=1e-14)
+    mfd = oq.ArbitraryMFD(d['mags'], d['mag_rates'])
+    npd = [tuple(x) for x in d['npd']]
+    hdd = [tuple(x) for x in d['hdd']]
+    srcs = [oq.PointSource(str(i), lon, lat, mfd, 'WC1994', float(d['rar']),
+                           float(d['usd']), float(d['lsd']), npd, hdd)
+            for i, (lon, lat) in enumerate(zip(d['src_lon'], d['src_lat']))]
+    N = len(d['site_lon'])
+    sites = dict(vs30=np.full(N, float(d['vs30'])))
+    sc = oq.SiteCollection.from_points(d['site_lon'], d['site_lat'],
+                                       np.zeros(N), sites)
+    imtls = {str(imt): d['levels'] for imt in d['imts']}
+    cm = oq.ContextMaker('Active Shallow Crust',
+                         [oq.get_gsim('BooreAtkinson2008')], dict(
+        imtls=imtls, truncation_level=float(d['truncation_level']),
+        investigation_time=float(d['investigation_time']),
+        maximum_distance=oq.IntegrationDistance.new(
+            str(float(d['maximum_distance'])))))
+    pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1.)
+    kept = cm.hazard_point_sources(pmap, srcs, sc, count=True)
+    assert kept == int(d['nrows'])      # the same rows survive rrup < 200 km
+    poes = (~pmap).array
+    want = d['poes']
+    assert poes.shape == want.shape == (N, 8 * 45, 1)
+    # (1) against the reference's map.  The reference multiplies its
+    # float32 pne map 416 times per site (one rounding of ~3e-8 each, order
+    # dependent); the device rounds once.  In pne
+    # space that is the rtol 2e-5 of the other pipeline tests; as PoE
+    # = 1 - pne it is an absolute 1.5e-6.
+    np.testing.assert_allclose(1. - poes, 1. - want, rtol=2e-5, atol=1.5e-7)
+    np.testing.assert_allclose(poes, want, atol=1.5e-6)
+    top = want >= 1e-2
+    np.testing.assert_allclose(poes[top], want[top], rtol=1e-4)
+    # hazard curves are non increasing in the level
+    assert (np.diff(poes.reshape(N, 8, 45), axis=2) <= 1e-7).all()
+    # (2) tight check in rate space (no float32 pne cancellation): the
+    # device rate map against a float64 accumulation of the oracle's PoEs
+    # over the oracle's own ruptures of the 52 point sources
+    rmap = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0.)
+    cm.hazard_point_sources(rmap, srcs, sc)
+    plas, omags = [], []
+    for lon, lat in zip(d['src_lon'], d['src_lat']):
+        desc = dict(lon=lon, lat=lat, usd=float(d['usd']), lsd=float(d['lsd']),
+                    rar=float(d['rar']), msr='WC1994', mags=d['mags'],
+                    mag_rates=d['mag_rates'], npd=npd, hdd=hdd)
+        pla, mag, rate = source_np.point_source_ruptures(desc)
+        pla['wlr'][:, 2] = rate
+        plas.append(pla)
+        omags.append(mag)
+    pla = {k: np.concatenate([p[k] for p in plas]) for k in plas[0]}
+    mag = np.concatenate(omags)
+    osites = dict(sids=sc.sids, lon=d['site_lon'], lat=d['site_lat'],
+                  depth=np.zeros(N), vs30=sites['vs30'])
+    pairs = [('BooreAtkinson2008', {})]
+    octx = hazard_np.get_ctx(pairs, pla, mag, osites,
+                             np.full(len(mag), float(d['maximum_distance'])))
+    assert len(octx) == kept
+    acc = hazard_np.exact_rate_sum(pairs, octx, sc.sids, imtls, 3., 50.)
+    big = acc > 1e-10
+    np.testing.assert_allclose(rmap.array[big], acc[big], rtol=1e-5)
+    np.testing.assert_allclose(rmap.array, acc, rtol=1e-5, atol=1e-10)
