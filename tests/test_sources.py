@@ -66,14 +66,10 @@ def test_oracle_point_ruptures_golden(name):
 def test_truncated_gr_matches_reference(name):
     import oq_engine_b200 as oq
     d = case(name)
-    # the area source spreads its MFD evenly over its points
-    # (source/area.py: rates scaled by 1 / number of points)
-    total = oq.TruncatedGRMFD(*d['gr'])
-    mags, rates = zip(*total.get_annual_occurrence_rates())
+    mfd = oq.TruncatedGRMFD(*d['gr'])
+    mags, rates = zip(*mfd.get_annual_occurrence_rates())
     np.testing.assert_allclose(mags, d['mags'], rtol=1e-15)
-    np.testing.assert_allclose(np.array(rates) / len(d['src_lon']),
-                               d['mag_rates'], rtol=1e-14)
-    mfd = oq.ArbitraryMFD(d['mags'], d['mag_rates'])
+    np.testing.assert_allclose(rates, d['mag_rates'], rtol=1e-15)
     m, r = source_np.truncated_gr_rates(*d['gr'])
     np.testing.assert_allclose(m, d['mags'], rtol=1e-15)
     np.testing.assert_allclose(r, d['mag_rates'], rtol=1e-15)
