@@ -225,6 +225,39 @@ int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        int64_t U, double *planar_dev, double *mag_dev,
                        double *magdist_dev);
 
+/* ---- post-processing of the rates map -------------------
+ * oqg_postclassical replaces, for all the sites at once, the loop of
+ * postclassical (calculators/classical.py:258-325): MapGetter.get_hcurve
+ * (calculators/getters.py:351-364) and build_stat_curve (getters.py:47-76)
+ * with mean_curve / std_curve / quantile_curve (hazardlib/stats.py:156-214)
+ * and, if use_rates, to_rates / to_probs (calc/mean_rates.py:28-50).
+ *   rates_dev   [N][L][Gt] float32, the array of a rates MapArray
+ *   g_off_dev   [Gt + 1], g_rlz_dev: the realizations (trt_rlzs % 2^24) of
+ *               each gsim column g are g_rlz[g_off[g] .. g_off[g + 1])
+ *   weights_dev [W][R] float64, W = 1 (one weight per realization) or M
+ *               (IMT-dependent weights, one row per IMT); an IMT whose
+ *               weights sum to zero gives zero curves (getters.py:61-63)
+ *   kinds, qs   S statistics (host arrays): OQG_STAT_MEAN, OQG_STAT_STD,
+ *               OQG_STAT_QUANTILE with its quantile in qs[s]
+ *   rlz_out_dev [R][N][L] float32 or NULL ('hcurves-rlzs')
+ *   stat_out_dev[S][N][L] float32 or NULL ('hcurves-stats')
+ * R <= 256, S <= 16, W <= 64 (an error otherwise). */
+enum { OQG_STAT_MEAN = 0, OQG_STAT_STD = 1, OQG_STAT_QUANTILE = 2 };
+int oqg_postclassical(oqg_handle *h, const float *rates_dev, int N, int L,
+                      int Gt, int M, const int32_t *g_off_dev,
+                      const int32_t *g_rlz_dev, int R,
+                      const double *weights_dev, int W,
+                      const double *weight_sums, int S, const int32_t *kinds,
+                      const double *qs, int use_rates, float *rlz_out_dev,
+                      float *stat_out_dev);
+/* compute_hazard_maps (hazardlib/map_array.py:94-141) for K curves:
+ * curves_dev [K][M][L1] float32 PoEs, imls_dev [M][L1], poes_dev [P]
+ * -> out_dev [K][M][P] float32 intensity levels (0 where the PoE is above
+ * the curve) */
+int oqg_hazard_maps(oqg_handle *h, const float *curves_dev, int64_t K, int M,
+                    int L1, const double *imls_dev, int P,
+                    const double *poes_dev, float *out_dev);
+
 /* The fused kernel evaluates the PoEs from a float32 polynomial table of
  * the truncated-normal survival function (argument in float64) when the
  * table built for the truncation level reproduces the exact formula to 2e-6

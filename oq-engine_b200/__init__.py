@@ -19,6 +19,8 @@ from .contexts import ContextMaker, IntegrationDistance, PlanarRuptures  # noqa
 from .source import (  # noqa
     PointSource, PointSourceBatch, TruncatedGRMFD, EvenlyDiscretizedMFD,
     ArbitraryMFD, point_ruptures_device)
+from .postproc import (  # noqa
+    postclassical, compute_hazard_maps, compute_hmaps)
 from . import sharding  # noqa
 
 __version__ = '0.1.0'

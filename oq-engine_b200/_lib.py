@@ -81,6 +81,12 @@ def lib():
             c_void, C.POINTER(C.c_ulonglong)]),
         'oqg_point_ruptures': (C.c_int, [H, c_void, C.c_int, C.c_int64,
                                          c_void, c_void, c_void]),
+        'oqg_postclassical': (C.c_int, [
+            H, c_void, C.c_int, C.c_int, C.c_int, C.c_int, c_void, c_void,
+            C.c_int, c_void, C.c_int, c_double_p, C.c_int,
+            C.POINTER(C.c_int32), c_double_p, C.c_int, c_void, c_void]),
+        'oqg_hazard_maps': (C.c_int, [H, c_void, C.c_int64, C.c_int, C.c_int,
+                                      c_void, C.c_int, c_void, c_void]),
         'oqg_set_exact_poe': (C.c_int, [H, C.c_int]),
         'oqg_poe_table_info': (C.c_int, [H, C.POINTER(C.c_int), c_double_p]),
         'oqg_launch_count': (C.c_ulonglong, [H]),

@@ -29,6 +29,7 @@
 #include "oqg_poe.cuh"
 #include "oqg_fast.cuh"
 #include "oqg_source.cuh"
+#include "oqg_post.cuh"
 
 using namespace oqg;
 
@@ -988,6 +989,55 @@ static int prep_ruptures(oqg_handle *h, const double *planar,
   if (reserve(h, h->rup, (size_t)NF_RUP * U * 8)) return 1;
   k_prep_ruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
       planar, mag, magdist, U, (double *)h->rup.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
+                      int M, const int32_t *g_off, const int32_t *g_rlz, int R,
+                      const double *weights, int W, const double *weight_sums,
+                      int S, const int32_t *kinds, const double *qs,
+                      int use_rates, float *rlz_out, float *stat_out) {
+  CK(cudaSetDevice(h->device));
+  if (N <= 0 || L <= 0) return 0;
+  if (R < 1 || R > OQG_RMAX) return fail(h, "postclassical: R must be in 1..256");
+  if (S < 0 || S > OQG_SMAX) return fail(h, "postclassical: at most 16 statistics");
+  if (M < 1 || L % M) return fail(h, "postclassical: L must be a multiple of M");
+  if (W != 1 && W != M) return fail(h, "postclassical: W must be 1 or M");
+  if (W > 64) return fail(h, "postclassical: at most 64 weight columns");
+  if (!rates || !g_off || !g_rlz) return fail(h, "postclassical: missing input");
+  if (S && (!weights || !weight_sums || !kinds || !qs || !stat_out))
+    return fail(h, "postclassical: missing weights / statistics / output");
+  PostArgs A;
+  memset(&A, 0, sizeof(A));
+  A.rates = rates; A.g_off = g_off; A.g_rlz = g_rlz; A.weights = weights;
+  A.rlz_out = rlz_out; A.stat_out = stat_out;
+  A.n_elems = (int64_t)N * L; A.L = L; A.L1 = L / M; A.Gt = Gt; A.R = R; A.W = W;
+  A.S = S; A.use_rates = use_rates;
+  for (int w = 0; w < W && S; w++) A.wsum[w] = weight_sums[w];
+  for (int s = 0; s < S; s++) {
+    if (kinds[s] < OQG_STAT_MEAN || kinds[s] > OQG_STAT_QUANTILE)
+      return fail(h, "postclassical: unknown statistic");
+    A.kind[s] = kinds[s];
+    A.q[s] = qs[s];
+  }
+  k_postclassical<<<(unsigned)((A.n_elems + 127) / 128), 128, 0, h->stream>>>(A);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_hazard_maps(oqg_handle *h, const float *curves, int64_t K, int M,
+                    int L1, const double *imls, int P, const double *poes,
+                    float *out) {
+  CK(cudaSetDevice(h->device));
+  if (K <= 0 || P <= 0) return 0;
+  if (M < 1 || L1 < 1) return fail(h, "hazard_maps: bad shape");
+  if (!curves || !imls || !poes || !out) return fail(h, "hazard_maps: missing array");
+  int64_t tot = K * M * P;
+  k_hazard_maps<<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(
+      curves, K, M, L1, imls, P, poes, out);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -1,0 +1,163 @@
+"""Post-processing of the rates map on the device (SURVEY.md section 8f row
+3): hazard curves per realization, statistics over the realizations and
+hazard maps.
+
+Mirrors `postclassical` (openquake/calculators/classical.py:258-325), which
+for every site calls MapGetter.get_hcurve (calculators/getters.py:351-364)
+and build_stat_curve (getters.py:47-76) with the statistics of
+hazardlib/stats.py:156-214, then calc.make_hmaps -> compute_hazard_maps
+(hazardlib/map_array.py:94-141).  Here all the sites go through one kernel
+(`oqg_postclassical`) and the maps through another (`oqg_hazard_maps`).
+"""
+import ctypes
+import numpy
+
+from .map_array import MapArray
+
+TWO24 = 2 ** 24
+KINDS = {'mean': 0, 'std': 1, 'quantile': 2}
+
+
+def _stat_spec(name):
+    """'mean' | 'std' | 'quantile-0.05' -> (kind, q); like the keys of
+    OqParam.hazard_stats()"""
+    if name in ('mean', 'std'):
+        return KINDS[name], 0.
+    if name.startswith('quantile-'):
+        q = float(name.split('-', 1)[1])
+        if not 0. <= q <= 1.:
+            raise ValueError('quantile %s out of range' % q)
+        return KINDS['quantile'], q
+    raise NotImplementedError('statistic %r has no device implementation'
+                              % name)
+
+
+def _handle(device):
+    from .contexts import get_handle, _device_index
+    return get_handle(_device_index(device))
+
+
+def compute_hazard_maps(curves, imls, poes, device=None):
+    """
+    hazardlib/map_array.py:94-141: curves (N, L1) PoEs -> (N, P) intensity
+    levels by log-log interpolation; 0 where the PoE is above the curve.
+    """
+    curves = numpy.asarray(curves, numpy.float32)
+    N, L1 = curves.shape
+    if L1 != len(imls):
+        raise ValueError('The curves have %d levels, %d were passed' %
+                         (L1, len(imls)))
+    return compute_hmaps(curves[:, None, :], {'_': imls}, poes,
+                         device)[:, 0]
+
+
+def compute_hmaps(curvesNML, imtls, poes, device=None):
+    """hazardlib/map_array.py:144-158: (N, M, L1) -> (N, M, P)"""
+    import torch
+    from .contexts import _dev, _ptr
+    h = _handle(device)
+    curves = numpy.ascontiguousarray(curvesNML, numpy.float32) \
+        if not isinstance(curvesNML, torch.Tensor) else curvesNML
+    N, M, L1 = curves.shape
+    assert M == len(imtls), (M, len(imtls))
+    imls = numpy.array([numpy.asarray(v, float) for v in imtls.values()])
+    assert imls.shape == (M, L1), imls.shape
+    P = len(poes)
+    t_c = _dev(curves, h.device, torch.float32)
+    t_i = _dev(imls, h.device)
+    t_p = _dev(numpy.asarray(poes, float), h.device)
+    t_o = torch.empty((N, M, P), dtype=torch.float32,
+                      device='cuda:%d' % h.device)
+    h.call('oqg_hazard_maps', _ptr(t_c), N, M, L1, _ptr(t_i), P, _ptr(t_p),
+           _ptr(t_o))
+    return t_o.cpu().numpy()
+
+
+def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
+                  individual_rlzs=False, poes=(), use_rates=False,
+                  device=None):
+    """
+    :param rmap: a rates MapArray (N, L, Gt) (or its array)
+    :param trt_rlzs: for each gsim column g the realizations it belongs to
+        (possibly with the TRT index in the high bits, as in the reference)
+    :param weights: (R,) realization weights, or (R, M + 1) IMT-dependent
+        weights (one column per IMT, the last one the default weight)
+    :param imtls: dict imt -> levels (M IMTs of L1 levels, L = M * L1)
+    :param hstats: names of the statistics: 'mean', 'std', 'quantile-X'
+    :returns: a dictionary kind -> list of MapArray (N, M, L1) [or (N, M, P)
+        for the hazard maps], kinds 'hcurves-rlzs', 'hcurves-stats',
+        'hmaps-rlzs', 'hmaps-stats' as in the reference
+    """
+    import torch
+    from .contexts import _dev, _ptr
+    h = _handle(device)
+    dev = h.device
+    cuda = 'cuda:%d' % dev
+    if isinstance(rmap, MapArray):
+        assert rmap.rates, 'postclassical needs a map of rates'
+        sids, arr = rmap.sids, rmap.array
+    else:
+        arr = rmap
+        sids = numpy.arange(len(arr), dtype=numpy.uint32)
+    N, L, Gt = arr.shape
+    M = len(imtls)
+    L1 = L // M
+    assert M * L1 == L, (M, L1, L)
+    rlzs = [numpy.asarray(t, numpy.int64) % TWO24 for t in trt_rlzs]
+    assert len(rlzs) == Gt, (len(rlzs), Gt)
+    weights = numpy.asarray(weights, float)
+    R = len(weights)
+    if max(int(r.max()) for r in rlzs if len(r)) >= R:
+        raise ValueError('realization index out of range')
+    if weights.ndim == 1 or weights.shape[1] == 1:
+        wdev = weights.reshape(R, -1)[:, -1][None]         # (1, R)
+    else:
+        if weights.shape[1] != M + 1:
+            raise ValueError('IMT-dependent weights must have M + 1 columns')
+        wdev = weights[:, :M].T                            # (M, R)
+    wdev = numpy.ascontiguousarray(wdev)
+    wsum = wdev.sum(axis=1)
+    specs = [_stat_spec(name) for name in hstats]
+    S = len(specs)
+    do_rlzs = R == 1 or individual_rlzs
+    t_rates = _dev(arr, dev, torch.float32)
+    g_off = numpy.concatenate([[0], numpy.cumsum([len(r) for r in rlzs])]
+                              ).astype(numpy.int32)
+    g_rlz = numpy.concatenate(rlzs).astype(numpy.int32)
+    t_off, t_rlz, t_w = _dev(g_off, dev), _dev(g_rlz, dev), _dev(wdev, dev)
+    t_r = torch.empty((R, N, L), dtype=torch.float32, device=cuda) \
+        if do_rlzs else None
+    t_s = torch.empty((S, N, L), dtype=torch.float32, device=cuda) \
+        if S else None
+    kinds = (ctypes.c_int32 * max(S, 1))(*[k for k, _ in specs])
+    qs = (ctypes.c_double * max(S, 1))(*[q for _, q in specs])
+    ws = (ctypes.c_double * len(wsum))(*wsum)
+    h.call('oqg_postclassical', _ptr(t_rates), N, L, Gt, M, _ptr(t_off),
+           _ptr(t_rlz), R, _ptr(t_w), len(wsum), ws, S, kinds, qs,
+           int(use_rates), _ptr(t_r), _ptr(t_s))
+    out = {}
+
+    def maps(t, P_or_L1):
+        res = []
+        for a in t.cpu().numpy():
+            m = MapArray(sids, M, P_or_L1)
+            m.array = a.reshape(N, M, P_or_L1)
+            res.append(m)
+        return res
+    P = len(poes)
+    if P:
+        t_i = _dev(numpy.array([numpy.asarray(v, float)
+                                for v in imtls.values()]), dev)
+        t_p = _dev(numpy.asarray(poes, float), dev)
+    for kind, t in (('rlzs', t_r), ('stats', t_s)):
+        if t is None:
+            continue
+        out['hcurves-' + kind] = maps(t, L1)
+        if P:
+            K = t.shape[0] * N
+            t_o = torch.empty((t.shape[0], N, M * P), dtype=torch.float32,
+                              device=cuda)
+            h.call('oqg_hazard_maps', _ptr(t), K, M, L1, _ptr(t_i), P,
+                   _ptr(t_p), _ptr(t_o))
+            out['hmaps-' + kind] = maps(t_o, P)
+    return out

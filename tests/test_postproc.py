@@ -1,0 +1,162 @@
+"""Post-processing of the rates map.
+
+CPU part: the oracle (oracle/post_np.py) against the fixture produced by the
+reference's own functions (oracle/make_golden_post.py).  GPU part (-m gpu):
+oqg_postclassical / oqg_hazard_maps through the Python mirror of
+`postclassical` against the same fixture.
+
+Tolerances: curves and statistics are float32 on output as in the reference
+(MapArray arrays): rtol 2e-6 (the device reads the rates as float32, as
+stored by MapArray), atol 1e-9 (float32 rounding of 1 - exp(-x) near 0 is
+exact to 1e-7 relative; std of nearly equal curves cancels).  Hazard maps:
+rtol 1e-5 -- the reference takes a float32 logarithm of the curve
+(see oracle/post_np.py), the device a float64 one.
+"""
+import os
+import numpy as np
+import pytest
+
+import post_np
+from helpers import GOLDEN
+
+D = np.load(os.path.join(GOLDEN, 'post.npz'))
+N, L, Gt = D['rates'].shape
+R, M = int(D['R']), int(D['M'])
+L1 = L // M
+OFF = D['trt_rlzs_off']
+TRT_RLZS = [D['trt_rlzs'][OFF[g]:OFF[g + 1]] for g in range(Gt)]
+QUANT = list(D['quantiles'])
+KINDS = [('mean', 0.), ('std', 0.)] + [('quantile', q) for q in QUANT]
+NAMES = ['mean', 'std'] + ['quantile-%s' % q for q in QUANT]
+IMTLS = {imt: D['imls'] for imt in ('PGA', 'SA(0.2)', 'SA(1.0)')}
+
+
+def weights_of(name):
+    return D['w1'][:, None] if name == 'w1' else D['wim']
+
+
+# ------------------------------------------------------------------ CPU
+def test_oracle_hcurves_golden():
+    np.testing.assert_allclose(
+        post_np.hcurves_from_rates(D['rates'], TRT_RLZS, R), D['hcurves'],
+        rtol=1e-15)
+
+
+@pytest.mark.parametrize('wname', ['w1', 'wim'])
+@pytest.mark.parametrize('use_rates', [0, 1])
+def test_oracle_stats_golden(wname, use_rates):
+    want = D['stats_%s_%d' % (wname, use_rates)]
+    w = weights_of(wname)
+    for k, (kind, q) in enumerate(KINDS):
+        for n in range(0, N, 3):
+            got = post_np.stat_curve(D['hcurves'][n], kind, q, w, M,
+                                     bool(use_rates))
+            np.testing.assert_allclose(got, want[k, n], rtol=1e-12,
+                                       atol=1e-300)
+
+
+def test_oracle_hazard_maps_golden():
+    mean = D['stats_w1_0'][0].reshape(N, M, L1).astype(np.float32)
+    for m in range(M):
+        np.testing.assert_allclose(
+            post_np.compute_hazard_maps(mean[:, m], D['imls'], D['poes']),
+            D['hmaps'][:, m], rtol=1e-13)
+
+
+def test_oracle_to_rates_edges():
+    np.testing.assert_array_equal(post_np.to_rates(D['to_rates_in']),
+                                  D['to_rates_out'])
+
+
+def test_quantile_tie_break_is_by_weight():
+    # numpy's sort(order='c') breaks ties in the value with the weight
+    c = np.array([[0.2], [0.1], [0.2], [0.3]])
+    w = np.array([0.4, 0.1, 0.2, 0.3])
+    got = post_np.quantile_curve(0.25, c, w)
+    # sorted (c, w): (.1,.1) (.2,.2) (.2,.4) (.3,.3); cum .1 .3 .7 1.
+    assert abs(got[0] - (0.1 + (0.25 - 0.1) * (0.2 - 0.1) / 0.2)) < 1e-15
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.fixture(scope='module')
+def oq():
+    import oq_engine_b200
+    oq_engine_b200._lib.lib()
+    return oq_engine_b200
+
+
+def rmap_of(oq):
+    rmap = oq.MapArray(np.arange(N, dtype=np.uint32) * 2 + 1, L, Gt,
+                       rates=True)
+    rmap.array = D['rates'].astype(np.float32)
+    return rmap
+
+
+def oracle32_hcurves():
+    r32 = D['rates'].astype(np.float32).astype(float)
+    return post_np.hcurves_from_rates(r32, TRT_RLZS, R)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('wname', ['w1', 'wim'])
+@pytest.mark.parametrize('use_rates', [0, 1])
+def test_postclassical_golden(oq, wname, use_rates):
+    w = weights_of(wname)
+    res = oq.postclassical(rmap_of(oq), TRT_RLZS, w if wname == 'wim'
+                           else w[:, 0], IMTLS, NAMES, individual_rlzs=True,
+                           poes=list(D['poes']), use_rates=bool(use_rates))
+    assert set(res) == {'hcurves-rlzs', 'hcurves-stats', 'hmaps-rlzs',
+                        'hmaps-stats'}
+    assert len(res['hcurves-rlzs']) == R and len(res['hcurves-stats']) == 5
+    assert res['hcurves-stats'][0].array.shape == (N, M, L1)
+    assert (res['hcurves-stats'][0].sids == np.arange(N) * 2 + 1).all()
+    # realizations: against the oracle on the float32 rates the device reads
+    hc = oracle32_hcurves()
+    got = np.stack([m.array.reshape(N, L) for m in res['hcurves-rlzs']], -1)
+    np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
+    # ... and against the reference (float64 rates): float32 input rounding
+    np.testing.assert_allclose(got, D['hcurves'], rtol=2e-6, atol=1e-30)
+    # statistics against the reference
+    want = D['stats_%s_%d' % (wname, use_rates)]
+    for k, name in enumerate(NAMES):
+        got = res['hcurves-stats'][k].array.reshape(N, L)
+        np.testing.assert_allclose(got, want[k], rtol=2e-6, atol=1e-9,
+                                   err_msg=name)
+        # and tightly against the oracle on the same float32 rates
+        for n in (0, 3, 7, 9, 21):
+            mine = post_np.stat_curve(hc[n], KINDS[k][0], KINDS[k][1], w, M,
+                                      bool(use_rates))
+            np.testing.assert_allclose(got[n], mine, rtol=3e-7, atol=1e-12,
+                                       err_msg=name)
+    if wname == 'wim':   # SA(0.2) has zero weights: no curve
+        assert (res['hcurves-stats'][0].array[:, 1] == 0).all()
+
+
+@pytest.mark.gpu
+def test_hazard_maps_golden(oq):
+    mean = D['stats_w1_0'][0].reshape(N, M, L1).astype(np.float32)
+    got = oq.compute_hmaps(mean, IMTLS, list(D['poes']))
+    assert got.shape == (N, M, len(D['poes']))
+    np.testing.assert_allclose(got, D['hmaps'], rtol=1e-5, atol=0)
+    assert ((got == 0) == (D['hmaps'] == 0)).all()   # PoE above the curve
+    one = oq.compute_hazard_maps(mean[:, 0], D['imls'], D['poes'])
+    np.testing.assert_array_equal(one, got[:, 0])
+    with pytest.raises(ValueError):
+        oq.compute_hazard_maps(mean[:, 0], D['imls'][:-1], D['poes'])
+
+
+@pytest.mark.gpu
+def test_postclassical_errors_and_single_rlz(oq):
+    rmap = rmap_of(oq)
+    with pytest.raises(NotImplementedError):
+        oq.postclassical(rmap, TRT_RLZS, D['w1'], IMTLS, ['max'])
+    with pytest.raises(ValueError):
+        oq.postclassical(rmap, TRT_RLZS, D['w1'][:3], IMTLS, ['mean'])
+    # R = 1: the realization curves are produced even without
+    # individual_rlzs (classical.py:288), the mean equals the realization
+    one = oq.postclassical(rmap, [[0]] * Gt, [1.], IMTLS, ['mean'])
+    np.testing.assert_allclose(one['hcurves-stats'][0].array,
+                               one['hcurves-rlzs'][0].array, rtol=1e-7)
+    tot = D['rates'].astype(np.float32).astype(float).sum(axis=2)
+    np.testing.assert_allclose(one['hcurves-rlzs'][0].array.reshape(N, L),
+                               1 - np.exp(-tot), rtol=2e-7, atol=1e-30)
