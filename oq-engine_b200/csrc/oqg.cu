@@ -1022,6 +1022,74 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     A.kind[s] = kinds[s];
     A.q[s] = qs[s];
   }
+  if (R <= 32) {
+    // register path: inverse map realization -> gsim columns, weight ranks
+    // (small host-side tables, copied through a staging buffer)
+    std::vector<int32_t> goff(Gt + 1), tab;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(goff.data(), g_off, (Gt + 1) * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> grlz(goff[Gt]);
+    if (goff[Gt])
+      CK(cudaMemcpy(grlz.data(), g_rlz, (size_t)goff[Gt] * 4, cudaMemcpyDeviceToHost));
+    std::vector<std::vector<int32_t>> inv(R);
+    for (int g = 0; g < Gt; g++)
+      for (int k = goff[g]; k < goff[g + 1]; k++) {
+        if (grlz[k] < 0 || grlz[k] >= R)
+          return fail(h, "postclassical: realization index out of range");
+        inv[grlz[k]].push_back(g);
+      }
+    std::vector<int32_t> roff(R + 1, 0), rgs;
+    for (int r = 0; r < R; r++) {
+      rgs.insert(rgs.end(), inv[r].begin(), inv[r].end());
+      roff[r + 1] = (int32_t)rgs.size();
+    }
+    std::vector<double> wh((size_t)std::max(W, 1) * R, 0.);
+    std::vector<int32_t> rank((size_t)std::max(W, 1) * R, 0);
+    if (S) {
+      CK(cudaMemcpy(wh.data(), weights, wh.size() * 8, cudaMemcpyDeviceToHost));
+      for (int c = 0; c < W; c++) {
+        std::vector<int> ord(R);
+        for (int r = 0; r < R; r++) ord[r] = r;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+          return wh[(size_t)c * R + a] < wh[(size_t)c * R + b]; });
+        // equal weights get equal ranks
+        int rk = 0;
+        for (int i = 0; i < R; i++) {
+          if (i && wh[(size_t)c * R + ord[i]] != wh[(size_t)c * R + ord[i - 1]]) rk = i;
+          rank[(size_t)c * R + ord[i]] = rk;
+        }
+      }
+    }
+    size_t nb = (roff.size() + rgs.size() + rank.size()) * 4;
+    if (reserve(h, h->stage[10], nb + 16)) return 1;
+    int32_t *d = (int32_t *)h->stage[10].p;
+    CK(cudaMemcpy(d, roff.data(), roff.size() * 4, cudaMemcpyHostToDevice));
+    if (!rgs.empty())
+      CK(cudaMemcpy(d + roff.size(), rgs.data(), rgs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d + roff.size() + rgs.size(), rank.data(), rank.size() * 4,
+                  cudaMemcpyHostToDevice));
+    PostRegArgs B;
+    memset(&B, 0, sizeof(B));
+    B.rates = rates; B.r_off = d; B.r_gs = d + roff.size();
+    B.wrank = d + roff.size() + rgs.size();
+    B.weights = weights; B.rlz_out = rlz_out; B.stat_out = stat_out;
+    B.n_elems = A.n_elems; B.L = L; B.L1 = L / M; B.Gt = Gt; B.R = R;
+    B.W = std::max(W, 1); B.S = S; B.use_rates = use_rates;
+    if (!S) { B.W = 1; B.weights = (const double *)d; }  // never read
+    memcpy(B.wsum, A.wsum, sizeof(B.wsum));
+    memcpy(B.kind, A.kind, sizeof(B.kind));
+    memcpy(B.q, A.q, sizeof(B.q));
+    size_t smem = (size_t)B.W * R * 12 + (R + 1 + rgs.size()) * 4 + 16 +
+                  (size_t)128 * (Gt | 1) * 4;
+    unsigned grid = (unsigned)((A.n_elems + 127) / 128);
+    if (R <= 4) k_postclassical_reg<4><<<grid, 128, smem, h->stream>>>(B);
+    else if (R <= 8) k_postclassical_reg<8><<<grid, 128, smem, h->stream>>>(B);
+    else if (R <= 16) k_postclassical_reg<16><<<grid, 128, smem, h->stream>>>(B);
+    else k_postclassical_reg<32><<<grid, 128, smem, h->stream>>>(B);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   k_postclassical<<<(unsigned)((A.n_elems + 127) / 128), 128, 0, h->stream>>>(A);
   h->launches++;
   CK(cudaGetLastError());

@@ -15,6 +15,7 @@
 #pragma once
 #include <math.h>
 #include "../../include/oqg.h"
+#include "oqg_math.cuh"
 
 namespace oqg {
 
@@ -118,6 +119,161 @@ k_postclassical(const PostArgs A) {
         }
         prev_cum = cum;
         prev_v = v[k];
+      }
+    }
+    if (A.use_rates) res = 1. - exp(-res);
+    A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
+  }
+}
+
+// ---- register path, R <= 32 ------------------------------------------------
+// The realization values of a thread never leave the registers: they are
+// accumulated through the inverse map realization -> gsim columns, written
+// out, folded into the mean / variance sums in float64, and packed into
+// 64-bit sort keys
+//     [ bits 63..10 of the (non negative) float64 value | weight rank (5) |
+//       realization (5) ]
+// which a bitonic network with compile-time indices sorts for the quantiles
+// (ties of the value are broken by the weight like numpy's sort(order='c');
+// values are compared, and used in the interpolation, to 2^-42 relative).  The variance uses sums shifted by the first value, exact for
+// equal curves.
+struct PostRegArgs {
+  const float *rates;      // [N][L][Gt]
+  const int32_t *r_off;    // [R + 1] gsim columns of each realization
+  const int32_t *r_gs;
+  const double *weights;   // [W][R]
+  const int32_t *wrank;    // [W][R] rank of the weight among the realizations
+  double wsum[64];
+  float *rlz_out, *stat_out;
+  int64_t n_elems;
+  int L, L1, Gt, R, W, S, use_rates;
+  int kind[OQG_SMAX];
+  double q[OQG_SMAX];
+};
+
+__device__ __forceinline__ unsigned long long post_key(double v, int wrank,
+                                                        int r) {
+  // v >= 0 (a probability or a rate): the bit pattern is order preserving
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u & ~0x3ffull) | ((unsigned)wrank << 5) | (unsigned)r;
+}
+
+__device__ __forceinline__ double post_key_value(unsigned long long k) {
+  return __longlong_as_double((long long)(k & ~0x3ffull));
+}
+
+template <int RP>
+__global__ void __launch_bounds__(128)
+k_postclassical_reg(const PostRegArgs A) {
+  extern __shared__ double sm_post[];
+  math_tables_init();   // fast_exp of oqg_math.cuh
+  // shared: weights [W][R] (double), wrank [W][R], r_off [R + 1], r_gs
+  const int R = A.R, WR = A.W * R;
+  double *s_w = sm_post;
+  int *s_rank = (int *)(s_w + WR);
+  int *s_off = s_rank + WR;
+  int *s_gs = s_off + R + 1;
+  const int64_t e0 = blockIdx.x * (int64_t)blockDim.x;
+  for (int i = threadIdx.x; i < WR; i += blockDim.x) {
+    s_w[i] = A.weights[i];
+    s_rank[i] = A.wrank[i];
+  }
+  for (int i = threadIdx.x; i <= R; i += blockDim.x) s_off[i] = A.r_off[i];
+  __syncthreads();
+  const int ngs = s_off[R];
+  for (int i = threadIdx.x; i < ngs; i += blockDim.x) s_gs[i] = A.r_gs[i];
+  // the rates of the CTA's elements: one coalesced read of 128 * Gt floats,
+  // rows padded to an odd stride (conflict-free row reads)
+  const int gstride = A.Gt | 1;
+  float *s_rates = (float *)(s_gs + ngs);
+  {
+    const int64_t base = e0 * A.Gt;
+    const int64_t lim = min((int64_t)blockDim.x, A.n_elems - e0) * A.Gt;
+    for (int64_t i = threadIdx.x; i < lim; i += blockDim.x) {
+      const int t = (int)(i / A.Gt), g = (int)(i - (int64_t)t * A.Gt);
+      s_rates[t * gstride + g] = A.rates[base + i];
+    }
+  }
+  __syncthreads();
+  const int64_t e = e0 + threadIdx.x;
+  if (e >= A.n_elems) return;
+  const int l = (int)(e % A.L);
+  const int wcol = A.W > 1 ? l / A.L1 : 0;
+  const double *w = s_w + wcol * R;
+  const int *rk = s_rank + wcol * R;
+  const double wsum = A.wsum[wcol];
+  const float *row = s_rates + threadIdx.x * gstride;
+  const bool stats = A.stat_out && A.S > 0 && wsum != 0.;
+  unsigned long long key[RP];
+  double sw1 = 0., sw2 = 0., v0 = 0.;
+#pragma unroll
+  for (int r = 0; r < RP; r++) {
+    key[r] = ~0ull;                      // padding sorts last
+    if (r < R) {
+      double x = 0.;
+      for (int k = s_off[r]; k < s_off[r + 1]; k++) x += (double)row[s_gs[k]];
+      double v = 1. - fast_exp(fmax(-x, -700.));   // to_probs
+      if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
+      if (A.use_rates) v = to_rate(v);
+      if (r == 0) v0 = v;
+      const double d = v - v0;
+      sw1 = fma(w[r], d, sw1);
+      sw2 = fma(w[r] * d, d, sw2);
+      key[r] = post_key(v, rk[r], r);
+    }
+  }
+  if (A.stat_out && A.S > 0 && wsum == 0.) {   // getters.py:61-63
+    for (int s = 0; s < A.S; s++) A.stat_out[(int64_t)s * A.n_elems + e] = 0.f;
+    return;
+  }
+  if (!stats) return;
+  const double dm = sw1 / wsum;               // mean - v0
+  bool sorted = false;
+  for (int s = 0; s < A.S; s++) {
+    double res;
+    if (A.kind[s] == OQG_STAT_MEAN) {
+      res = v0 + dm;
+    } else if (A.kind[s] == OQG_STAT_STD) {
+      // sum w (m - v)^2 = sum w d^2 - 2 dm sum w d + dm^2 sum w
+      res = sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
+    } else {
+      if (!sorted) {
+#pragma unroll
+        for (int k = 2; k <= RP; k <<= 1) {
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < RP; i++) {
+              const int p = i ^ j;
+              if (p > i) {
+                const bool up = (i & k) == 0;
+                const unsigned long long a = key[i], b = key[p];
+                const bool sw = up ? a > b : a < b;
+                key[i] = sw ? b : a;
+                key[p] = sw ? a : b;
+              }
+            }
+          }
+        }
+        sorted = true;
+      }
+      const double q = A.q[s];
+      double cum = 0., prev_cum = 0., prev_v = 0.;
+      bool done = false;
+      res = 0.;
+#pragma unroll
+      for (int j = 0; j < RP; j++) {
+        if (j < R && !done) {
+          const double vk = post_key_value(key[j]);
+          cum += w[(int)(key[j] & 31u)];
+          if (q < cum || j == R - 1) {
+            if (j == 0 || q >= cum) res = vk;
+            else res = prev_v + (q - prev_cum) * ((vk - prev_v) / (cum - prev_cum));
+            done = true;
+          }
+          prev_cum = cum;
+          prev_v = vk;
+        }
       }
     }
     if (A.use_rates) res = 1. - exp(-res);
