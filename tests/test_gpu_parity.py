@@ -552,3 +552,70 @@ def test_sharding_on_one_gpu(oq):
                                rtol=1e-5)
     pm = oq.sharding.hazard_group_sharded([cm] * 4, srcs, sc, 0, 1)
     np.testing.assert_allclose(pm.numpy(), full.array, rtol=1e-6)
+
+
+def test_full_size_properties(oq):
+    """Size-independent properties of the fused pass at a size the oracle
+    cannot reach (20 000 ruptures x 10 000 sites, cfg3 models: 5.6e10 PoE
+    evaluations): additivity over a split of the ruptures, linearity in the
+    occurrence rates, invariance under a permutation of the sites,
+    monotonicity of the curves, and a spot check of 24 sites against the
+    oracle."""
+    rng = np.random.default_rng(2024)
+    U, N = 20_000, 10_000
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    pairs = CFG['cfg3']
+    cm = oq.ContextMaker('*', make_gsims(oq, pairs), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+
+    def planar(sel, scale=1.):
+        pla = oq.build_planar(
+            r['mag'][sel], r['strike'][sel], r['dip'][sel], r['rake'][sel],
+            r['rate'][sel] * scale, r['area'][sel], r['hypo_lon'][sel],
+            r['hypo_lat'][sel], r['hypo_dep'][sel], 0., 25., 1.5)
+        return oq.PlanarRuptures(pla, r['mag'][sel])
+
+    def rates(src, sitecol):
+        m = oq.MapArray(sitecol.sids, cm.L, cm.G, rates=True).fill(0)
+        kept = cm.hazard_planar(m, src, sitecol, count=True)
+        return m.array, kept
+    everything = slice(None)
+    full, kept = rates(planar(everything), sc)
+    assert kept == U * N
+    assert np.isfinite(full).all() and (full >= 0).all()
+    # additivity: ruptures split in two uneven parts
+    a, _ = rates(planar(slice(0, 7_003)), sc)
+    b, _ = rates(planar(slice(7_003, U)), sc)
+    np.testing.assert_allclose(a + b, full, rtol=3e-6, atol=1e-12)
+    # linearity in the rates
+    twice, _ = rates(planar(everything, 2.), sc)
+    np.testing.assert_allclose(twice, 2 * full, rtol=1e-6, atol=1e-12)
+    # permutation of the sites
+    perm = rng.permutation(N)
+    psites = {k: v[perm] for k, v in sites.items() if k != 'sids'}
+    psc = oq.SiteCollection.from_points(psites['lon'], psites['lat'],
+                                        psites['depth'], psites)
+    permuted, _ = rates(planar(everything), psc)
+    np.testing.assert_allclose(permuted, full[perm], rtol=1e-6, atol=1e-12)
+    # rates of exceedance do not increase with the level
+    curves = full.reshape(N, len(IMTS), 20, cm.G)
+    assert (np.diff(curves, axis=2) <= 1e-7 * curves[:, :, :-1]).all()
+    # spot check against the oracle: 24 sites x the first 300 ruptures
+    sel = rng.choice(N, 24, replace=False)
+    sub = {k: v[sel] for k, v in sites.items()}
+    sub['sids'] = np.arange(24, dtype=np.uint32)
+    ssc = oq.SiteCollection.from_points(sub['lon'], sub['lat'], sub['depth'],
+                                        sub)
+    got, _ = rates(planar(slice(0, 300)), ssc)
+    opla = geo_np.build_planar(
+        r['mag'][:300], r['strike'][:300], r['dip'][:300], r['rake'][:300],
+        r['rate'][:300], r['area'][:300], r['hypo_lon'][:300],
+        r['hypo_lat'][:300], r['hypo_dep'][:300], 0., 25., 1.5)
+    octx = hazard_np.get_ctx(pairs, opla, r['mag'][:300], sub)
+    acc = hazard_np.exact_rate_sum(pairs, octx, sub['sids'], imtls, 3., 50.)
+    big = acc > 1e-10
+    np.testing.assert_allclose(got[big], acc[big], rtol=1e-5)
