@@ -46,7 +46,7 @@ using namespace oqg;
                        // reaches rarely, accumulate in shared memory
 #endif
 #ifndef LGRP
-#define LGRP 1         // levels evaluated per level-skipping test (NL % LGRP == 0)
+#define LGRP 2         // levels evaluated per level-skipping test (NL % LGRP == 0)
 #endif
 #define NWMAX 7        // warps (units) per CTA in the fused kernel
 #ifndef MINB
@@ -378,7 +378,7 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 #endif
 #define PT_MAXNODES 512
 #ifndef FLUSH_TILES
-#define FLUSH_TILES 4
+#define FLUSH_TILES 8
 #endif
 //    // float32 partial sums are flushed to FP64 every
                           // FLUSH_TILES * RT ruptures
