@@ -21,6 +21,7 @@ from .source import (  # noqa
     ArbitraryMFD, point_ruptures_device)
 from .postproc import (  # noqa
     postclassical, compute_hazard_maps, compute_hmaps)
+from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from . import sharding  # noqa
 
 __version__ = '0.1.0'

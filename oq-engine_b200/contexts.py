@@ -294,6 +294,7 @@ class ContextMaker(object):
         maximum_distance, minimum_distance (same keys as the reference)
     """
     tom = None
+    cluster = 0
 
     def __init__(self, trt, gsims, oq, device=None):
         param = dict(oq)
@@ -552,7 +553,12 @@ class ContextMaker(object):
         itime = self.tom.time_span if self.tom is not None else (
             self.investigation_time)
         poes, _ms = self._device_poes(h, ctx)
-        update_device(pmap, poes, ctx.occurrence_rate, ctx.probs_occur,
+        probs_occur = ctx.probs_occur
+        if self.cluster:   # contexts.py:1243-1246: arr[sidx] *= 1 - poe
+            if pmap.rates:
+                raise ValueError('a cluster needs a map of probabilities')
+            probs_occur, itime = numpy.ones((len(ctx), 1)), 0.
+        update_device(pmap, poes, ctx.occurrence_rate, probs_occur,
                       pmap.sidx[ctx.sids], itime, handle=h)
         self.cfactor += [len(ctx), len(numpy.unique(numpy.round(ctx.mag, 3)))]
 
@@ -588,7 +594,11 @@ class ContextMaker(object):
         if U == 0 or N == 0:
             return 0
         K, t_probs = 0, None
-        if hasattr(tom, 'get_pmf'):
+        if self.cluster:
+            if pmap.rates:
+                raise ValueError('a cluster needs a map of probabilities')
+            t_probs, K = self._fated(U, dev)
+        elif hasattr(tom, 'get_pmf'):
             probs = numpy.ascontiguousarray(tom.get_pmf(src.rate))
             K = probs.shape[1]
             t_probs = _dev(probs, dev)
@@ -597,6 +607,14 @@ class ContextMaker(object):
         t_md = _dev(self.magdist(src.mag), dev)
         return self._hazard_planar_dev(pmap, t_pla, t_mag, t_md, t_probs, K,
                                        U, sitecol, count)
+
+    def _fated(self, U, dev):
+        # cluster groups (contexts.py:1243-1246): every rupture happens once
+        # when the cluster does, pne = prod (1 - poe); the kernels take that
+        # as a one-element probs_occur with investigation time 0
+        import torch
+        return torch.ones((U, 1), dtype=torch.float64,
+                          device='cuda:%d' % dev), 1
 
     def _hazard_planar_dev(self, pmap, t_pla, t_mag, t_md, t_probs, K, U,
                            sitecol, count):
@@ -613,7 +631,8 @@ class ContextMaker(object):
             if count else None
         h.call('oqg_hazard_planar', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
                _ptr(t_probs), K, U, ctypes.byref(st), _ptr(t_sidx), N,
-               float(self.minimum_distance), float(self.tom.time_span),
+               float(self.minimum_distance),
+               0. if self.cluster else float(self.tom.time_span),
                int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
         if on_host:
             pmap.array[:] = t_map.cpu().numpy()
@@ -649,7 +668,11 @@ class ContextMaker(object):
         if batch.U == 0 or len(sitecol) == 0:
             return 0
         K, t_probs = 0, None
-        if hasattr(tom, 'get_pmf'):
+        if self.cluster:
+            if pmap.rates:
+                raise ValueError('a cluster needs a map of probabilities')
+            t_probs, K = self._fated(batch.U, h.device)
+        elif hasattr(tom, 'get_pmf'):
             _mag, rate = batch.expand()
             probs = numpy.ascontiguousarray(tom.get_pmf(rate))
             K = probs.shape[1]

@@ -67,9 +67,15 @@ class MapArray(object):
         if self.rates:
             return self
         pnes = self.array
-        xp = numpy if self.device is None else __import__('torch')
-        rates = - xp.log(pnes.clip(1E-16, 1.)) if xp is numpy else \
-            - xp.log(pnes.clamp(1E-16, 1.))
+        # map_array.py:386-394: a PoE of exactly 1 becomes 1 - 1.11E-16
+        if self.device is None:
+            pnes = numpy.where(pnes == 0., F32(1.11E-16), pnes)
+            rates = - numpy.log(pnes)
+        else:
+            import torch
+            pnes = torch.where(pnes == 0., torch.full_like(pnes, 1.11E-16),
+                               pnes)
+            rates = - torch.log(pnes)
         if itime != 1.:
             rates = rates / itime
         new = self.new(rates)

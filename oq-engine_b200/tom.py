@@ -14,6 +14,11 @@ class PoissonTOM(object):
     def get_probability_no_exceedance(self, occurrence_rate, poes):
         return numpy.exp(- occurrence_rate * self.time_span * poes)
 
+    def get_probability_n_occurrences(self, occurrence_rate, num):
+        # tom.py:123-140 (scipy.stats.poisson.pmf)
+        from scipy.stats import poisson
+        return poisson(occurrence_rate * self.time_span).pmf(num)
+
 
 class NegativeBinomialTOM(object):
     """

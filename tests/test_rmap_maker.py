@@ -1,0 +1,117 @@
+"""RmapMaker.make (openquake/hazardlib/contexts.py:1478-1662): independent
+sources, mutually exclusive sources and a cluster group against the rates
+maps produced by the reference's own RmapMaker (oracle/make_golden_rmap.py).
+
+Tolerance: the reference accumulates in float32 per context row (rate maps:
+`arr += rate * poe * itime`; mutex / cluster: pne maps), the device once per
+map element: rtol 2e-5 on rates >= 1e-7 (the float32 noise of ~30 updates),
+plus an absolute 2e-7 floor for the maps that pass through 1 - pne.
+"""
+import os
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+D = np.load(os.path.join(GOLDEN, 'rmap_maker.npz'))
+SRC = [  # as in oracle/make_golden_rmap.py
+    (0.10, 0.10, [0.02, 0.008, 0.003, 0.001], 30., 60., 90., 6.),
+    (0.45, -0.20, [0.05, 0.01, 0.002], 120., 90., 0., 8.),
+    (-0.30, 0.35, [0.01, 0.006, 0.004, 0.002, 0.001], 250., 45., -90., 10.),
+]
+
+
+@pytest.fixture(scope='module')
+def oq():
+    import oq_engine_b200
+    oq_engine_b200._lib.lib()
+    return oq_engine_b200
+
+
+def setup(oq):
+    srcs = []
+    for i, (lon, lat, rates, strike, dip, rake, dep) in enumerate(SRC):
+        src = oq.PointSource(
+            str(i), lon, lat, oq.EvenlyDiscretizedMFD(5.05, 0.3, rates),
+            'WC1994', 1.5, 0., 20., [(1., strike, dip, rake)], [(1., dep)])
+        src.mutex_weight = float(D['mutex_weights'][i])
+        srcs.append(src)
+    N = len(D['site_lon'])
+    sc = oq.SiteCollection.from_points(
+        D['site_lon'], D['site_lat'], np.zeros(N), dict(vs30=D['vs30']))
+    imtls = {str(imt): D['levels'] for imt in D['imts']}
+    cm = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim('BooreEtAl2014'), oq.get_gsim('BooreAtkinson2008')],
+        dict(imtls=imtls, truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('100')))
+    return cm, sc, srcs
+
+
+def close(got, want, atol):
+    assert got.shape == want.shape and got.dtype == np.float32
+    big = want >= 1e-7
+    np.testing.assert_allclose(got[big], want[big], rtol=2e-5, atol=atol)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=max(atol, 1e-9))
+
+
+def test_host_validation():
+    import oq_engine_b200 as oq
+    with pytest.raises(ValueError):
+        oq.SourceGroup('*', [], src_interdep='sometimes')
+    g = oq.SourceGroup('*', [1, 2], grp_probability=0.5)
+    assert list(g) == [1, 2] and g.grp_probability == 0.5
+
+
+@pytest.mark.gpu
+def test_independent_sources(oq):
+    cm, sc, srcs = setup(oq)
+    dic = oq.RmapMaker(cm, sc, srcs).make()
+    assert set(dic) >= {'rmap', 'cfactor', 'rup_data', 'source_data',
+                        'task_no'}
+    rmap = dic['rmap']
+    assert rmap.rates and (rmap.gid == np.arange(2)).all()
+    close(rmap.array, D['indep_rates'], 0.)
+    sd = dic['source_data']
+    assert sd['nrupts'] == [4, 3, 5] and len(sd['ctimes']) == 3
+    # the reference reports the context rows of each source
+    np.testing.assert_allclose(sum(sd['nctxs']), D['indep_nctxs'].sum(),
+                               rtol=0, atol=0.5)
+
+
+@pytest.mark.gpu
+def test_mutex_sources(oq):
+    cm, sc, srcs = setup(oq)
+    grp = oq.SourceGroup('Active Shallow Crust', srcs, 'mutex group',
+                         src_interdep='mutex', grp_probability=0.9)
+    dic = oq.RmapMaker(cm, sc, grp).make()
+    close(dic['rmap'].array, D['mutex_rates'], 2e-7)
+    with pytest.raises(NotImplementedError):
+        oq.RmapMaker(cm, sc, oq.SourceGroup('*', srcs, rup_interdep='mutex'))
+
+
+@pytest.mark.gpu
+def test_cluster_group(oq):
+    cm, sc, srcs = setup(oq)
+    tom = oq.PoissonTOM(50.)
+    tom.occurrence_rate = float(D['cluster_rate'])
+    grp = oq.SourceGroup('Active Shallow Crust', srcs, 'cluster group',
+                         cluster=True, temporal_occurrence_model=tom)
+    dic = oq.RmapMaker(cm, sc, grp).make()
+    close(dic['rmap'].array, D['cluster_rates'], 2e-7)
+    assert cm.cluster == 1
+    # the unfused update gives the same pne map as the fused pass
+    cm2, _, _ = setup(oq)
+    cm2.cluster, cm2.tom = 1, tom
+    pla = oq.build_planar([6.], [10.], [80.], [0.], [1e-3], [80.], [0.],
+                          [0.], [7.], 0., 20., 1.5)
+    src = oq.PlanarRuptures(pla, np.array([6.]))
+    a = oq.MapArray(sc.sids, cm2.L, cm2.G).fill(1)
+    cm2.hazard_planar(a, src, sc)
+    b = oq.MapArray(sc.sids, cm2.L, cm2.G).fill(1)
+    ctx = cm2.recarray(cm2.get_ctxs(src, sc))
+    cm2.update(b, ctx)
+    rows = np.unique(b.sidx[ctx.sids])
+    np.testing.assert_allclose(a.array[rows], b.array[rows], rtol=2e-6,
+                               atol=1e-7)   # float32 PoEs of the unfused path
+    assert (a.array[rows] < 1).any()
