@@ -601,9 +601,22 @@ k_fused(const FusedArgs A) {
       ri.ztor = s_rup[RF_ZTOR * RT + i];
       ri.width = s_rup[RF_WIDTH * RT + i];
       ri.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];
-      st_soa(s_q + (warp * RT + i) * QW, 1, FF::rup(gs, C, ri));
-      if (warp == nw - 1)
-        st_soa(s_q + (nw * RT + i) * QW, 1, FF::rup(gs, Cp, ri));
+      if (FF::ROLL_Q) {
+        // one inlined copy of FF::rup for both rows: the CY14 kernel was
+        // fetch bound (6592 SASS instructions, stall no_instruction 1.5 per
+        // issue); measured -6 % time for CY14, +9 % for ASK14
+        const int npass = warp == nw - 1 ? 2 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; pass++) {
+          const CT &cc = pass ? Cp : C;
+          st_soa(s_q + ((pass ? nw : warp) * RT + i) * QW, 1,
+                 FF::rup(gs, cc, ri));
+        }
+      } else {
+        st_soa(s_q + (warp * RT + i) * QW, 1, FF::rup(gs, C, ri));
+        if (warp == nw - 1)
+          st_soa(s_q + (nw * RT + i) * QW, 1, FF::rup(gs, Cp, ri));
+      }
     }
     __syncthreads();
     // ---- the IMT-independent part of the model, once per pair, shared by

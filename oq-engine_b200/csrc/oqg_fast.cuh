@@ -76,6 +76,7 @@ template <int F> struct Fast {
   typedef Empty Q;
   typedef typename Fam<F>::R P;
   static constexpr bool HAS_S = false, HAS_Q = false, EVAL_QP = false;
+  static constexpr bool ROLL_Q = false;
   static constexpr bool HAS_P = sizeof(P) >= 8;
   static __device__ __forceinline__ S site(const oqg_gsim &, const C &,
                                            const SiteIn &) { return S(); }
@@ -108,6 +109,7 @@ template <> struct Fast<OQG_BSSA14> {
   struct P { double lnp, lrjb; };
   static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
   static constexpr bool EVAL_QP = false;
+  static constexpr bool ROLL_Q = false;
 
   static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
                                            const SiteIn &s) {
@@ -193,6 +195,7 @@ template <> struct Fast<OQG_CY14> {
   struct P { double fr, hwd, pga_mean; };
   static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
   static constexpr bool EVAL_QP = false;
+  static constexpr bool ROLL_Q = true;
 
   static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
                                            const SiteIn &s) {
@@ -228,9 +231,9 @@ template <> struct Fast<OQG_CY14> {
     if (rev) mz = fmax(2.704 - 1.226 * fmax(mag - 5.849, 0.), 0.);
     else mz = fmax(2.673 - 1.136 * fmax(mag - 4.970, 0.), 0.);
     double dz = r.ztor - mz * mz;
-    double fm = log(1.0 + exp(c.cn * (c.cm + 0. - mag)));
+    double fm = fast_log(1.0 + fast_exp(c.cn * (c.cm + 0. - mag)));
     fm = (C2 * (mag - 6.0) + ((C2 - c.c3) / c.cn) * fm - (C2 - c.c3) * 0.);
-    double coshm = cosh(2.0 * fmax(mag - 4.5, 0.));
+    double coshm = fast_cosh(2.0 * fmax(mag - 4.5, 0.));
     double fsrc = 0.;
     if (rev) fsrc += c.c1a + (c.c1c / coshm);
     if (-120. <= r.rake && r.rake <= -60.)
@@ -239,8 +242,8 @@ template <> struct Fast<OQG_CY14> {
     double cd = cos(r.dip * OQG_D2R);
     fsrc += (0.0 + (c.c11b / coshm)) * (cd * cd);
     q.a = c.c1 + fm + fsrc;
-    q.b = c.c5 * cosh(c.c6 * fmax(mag - c.chm, 0.0));
-    double gamma = c.cg1 + c.cg2 / cosh(fmax(mag - c.cg3, 0.0));
+    q.b = c.c5 * fast_cosh(c.c6 * fmax(mag - c.chm, 0.0));
+    double gamma = c.cg1 + c.cg2 / fast_cosh(fmax(mag - c.cg3, 0.0));
     if (region == 1 || region == 2) {
       if (mag > 6.0 && mag < 6.9) gamma = gamma * c.gjpit;
     } else if (region == 3) {
@@ -323,6 +326,7 @@ template <> struct Fast<OQG_ASK14> {
   struct P { double hwp; };
   static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
   static constexpr bool EVAL_QP = false;
+  static constexpr bool ROLL_Q = false;
 
   static __device__ __forceinline__ S site(const oqg_gsim &g, const C &c,
                                            const SiteIn &s) {
@@ -468,6 +472,7 @@ template <> struct Fast<OQG_CB14> {
   struct P { double a1100, pga_mean, hx, hrr; };
   static constexpr bool HAS_S = true, HAS_Q = true, HAS_P = true;
   static constexpr bool EVAL_QP = true;
+  static constexpr bool ROLL_Q = true;
 
   static __device__ __forceinline__ double site_lin(const C &c, int SJ,
                                                     double vs30, bool rock,

@@ -22,6 +22,7 @@
 //   fast_rcp(x)   MUFU.RCP64H + two Newton steps; relative error <= 2e-16.
 //                 Domain: x finite, normal, non-zero.
 //   fast_tanh_pos(x)  1 - 2 / (e^{2x} + 1), x >= 0 (absolute error 2e-16).
+//   fast_cosh(x)      (e^x + 1 / e^x) / 2, relative error <= 5e-16.
 //
 // The unfused operators (k_mean_stds, oqg_gmpe.cuh) keep the CUDA library
 // functions; the GPU parity tests compare the two (oqg_mean_stds_staged
@@ -93,6 +94,12 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // tanh for x >= 0 (x < 350)
 __device__ __forceinline__ double fast_tanh_pos(double x) {
   return fma(-2.0, fast_rcp(fast_exp(x + x) + 1.0), 1.0);
+}
+
+// cosh (|x| < 350): (e^x + e^-x) / 2 with one exp and one reciprocal
+__device__ __forceinline__ double fast_cosh(double x) {
+  const double e = fast_exp(x);
+  return 0.5 * (e + fast_rcp(e));
 }
 
 }  // namespace oqg
