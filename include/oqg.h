@@ -159,6 +159,15 @@ int oqg_update(oqg_handle *h, float *map_dev, int N, const float *poes_dev,
                int64_t P, const int64_t *order_dev, const int64_t *seg_dev,
                const double *rate_dev, const double *probs_occur_dev, int K,
                double itime, int rates_mode);
+/* mutually exclusive ruptures: map += (1 - pne) * weight[row]
+ * (MapArray.update_mutex -> update_pmap_m, hazardlib/map_array.py:262-269,
+ * 455-466); same row grouping as oqg_update; weight_dev[P] */
+int oqg_update_mutex(oqg_handle *h, float *map_dev, int N,
+                     const float *poes_dev, int64_t P,
+                     const int64_t *order_dev, const int64_t *seg_dev,
+                     const double *rate_dev, const double *probs_occur_dev,
+                     int K, double itime, const double *weight_dev);
+
 
 /* the fused path.  planar dev [U][42] (wlr[2] is the occurrence rate),
  * mag[U], magdist[U] (rows with rrup >= magdist are dropped,

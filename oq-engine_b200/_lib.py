@@ -71,6 +71,9 @@ def lib():
         'oqg_update': (C.c_int, [H, c_void, C.c_int, c_void, C.c_int64,
                                  c_void, c_void, c_void, c_void, C.c_int,
                                  C.c_double, C.c_int]),
+        'oqg_update_mutex': (C.c_int, [H, c_void, C.c_int, c_void, C.c_int64,
+                                       c_void, c_void, c_void, c_void,
+                                       C.c_int, C.c_double, c_void]),
         'oqg_hazard_planar': (C.c_int, [
             H, c_void, c_void, c_void, c_void, C.c_int, C.c_int,
             C.POINTER(OqgSites), c_void, C.c_int, C.c_double, C.c_double,

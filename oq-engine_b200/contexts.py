@@ -244,8 +244,10 @@ def _group_by_site(sidxs, N):
     return order, seg
 
 
-def update_device(pmap, poes, rates, probs_occur, sidxs, itime, handle=None):
-    """MapArray.update_indep on the GPU: poes (n, L, G) host or device"""
+def update_device(pmap, poes, rates, probs_occur, sidxs, itime, handle=None,
+                  weights=None):
+    """MapArray.update_indep (or, with `weights`, update_mutex) on the GPU:
+    poes (n, L, G) host or device"""
     import torch
     h = handle or get_handle(_device_index(pmap.device))
     dev = h.device
@@ -265,9 +267,15 @@ def update_device(pmap, poes, rates, probs_occur, sidxs, itime, handle=None):
     t_probs = _dev(probs, dev) if K else None
     on_host = pmap.device is None
     t_map = _dev(pmap.array, dev) if on_host else pmap.array
-    h.call('oqg_update', _ptr(t_map), N, _ptr(tpoes), n, _ptr(t_order),
-           _ptr(t_seg), _ptr(t_rate), _ptr(t_probs), K, float(itime),
-           int(pmap.rates))
+    if weights is not None:
+        t_w = _dev(numpy.asarray(weights, float), dev)
+        h.call('oqg_update_mutex', _ptr(t_map), N, _ptr(tpoes), n,
+               _ptr(t_order), _ptr(t_seg), _ptr(t_rate), _ptr(t_probs), K,
+               float(itime), _ptr(t_w))
+    else:
+        h.call('oqg_update', _ptr(t_map), N, _ptr(tpoes), n, _ptr(t_order),
+               _ptr(t_seg), _ptr(t_rate), _ptr(t_probs), K, float(itime),
+               int(pmap.rates))
     if on_host:
         pmap.array[:] = t_map.cpu().numpy()
 
@@ -545,8 +553,6 @@ class ContextMaker(object):
         Update the map in place (contexts.py:1232-1247): mean/stds, PoEs and
         the fold into the map all stay on the device.
         """
-        if rup_mutex:
-            raise NotImplementedError('mutex ruptures have no device path')
         if len(ctx) == 0:
             return
         h = self.handle()
@@ -554,6 +560,16 @@ class ContextMaker(object):
             self.investigation_time)
         poes, _ms = self._device_poes(h, ctx)
         probs_occur = ctx.probs_occur
+        if rup_mutex:      # contexts.py:1241-1242 -> MapArray.update_mutex
+            weights = numpy.array([
+                rup_mutex[src_id, rup_id]
+                for src_id, rup_id in zip(ctx.src_id, ctx.rup_id)])
+            update_device(pmap, poes, ctx.occurrence_rate, probs_occur,
+                          pmap.sidx[ctx.sids], itime, handle=h,
+                          weights=weights)
+            self.cfactor += [len(ctx),
+                             len(numpy.unique(numpy.round(ctx.mag, 3)))]
+            return
         if self.cluster:   # contexts.py:1243-1246: arr[sidx] *= 1 - poe
             if pmap.rates:
                 raise ValueError('a cluster needs a map of probabilities')
@@ -563,14 +579,14 @@ class ContextMaker(object):
         self.cfactor += [len(ctx), len(numpy.unique(numpy.round(ctx.mag, 3)))]
 
     def get_pmap(self, ctx, tom=None, rup_mutex={}):
-        """PoE map (contexts.py:1206-1218)"""
-        if rup_mutex:
-            raise NotImplementedError('mutex ruptures have no device path')
+        """PoE map (contexts.py:1205-1218); with `rup_mutex` (a dictionary
+        (src_id, rup_id) -> weight) the ruptures are mutually exclusive"""
+        rup_indep = not rup_mutex
         self.tom = tom or self.tom or PoissonTOM(self.investigation_time)
         sids = numpy.unique(ctx.sids)
-        pmap = MapArray(sids, self.L, self.G).fill(1)
-        self.update(pmap, ctx)
-        return ~pmap
+        pmap = MapArray(sids, self.L, self.G).fill(rup_indep)
+        self.update(pmap, ctx, rup_mutex)
+        return ~pmap if rup_indep else pmap
 
     # -------------------------------------------------------------- fused
     def magdist(self, mags):

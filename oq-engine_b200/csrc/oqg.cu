@@ -330,7 +330,8 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
                          const int64_t *__restrict__ seg,
                          const double *__restrict__ rate,
                          const double *__restrict__ probs, int K, double itime,
-                         int rates_mode) {
+                         int rates_mode,
+                         const double *__restrict__ weights) {
   int s = blockIdx.y;
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= LG) return;
@@ -340,7 +341,14 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
   for (int64_t i = a; i < b; i++) {
     int64_t row = order[i];
     double poe = (double)poes[row * LG + e];
-    if (K == 0) {
+    if (weights) {
+      // mutually exclusive ruptures, update_pmap_m (map_array.py:262-269):
+      // arr += (1 - pne) * weight
+      double pne = itime == 0. ? 1. - poe
+                   : (K == 0 ? exp(-rate[row] * poe * itime)
+                             : pne_from_pmf(probs + row * K, K, poe));
+      sum += (1. - pne) * weights[row];
+    } else if (K == 0) {
       sum += rate[row] * poe * itime;
     } else {
       double pne = itime == 0. ? 1. - poe
@@ -349,7 +357,7 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
     }
   }
   int64_t at = (int64_t)s * LG + e;
-  if (rates_mode) map[at] = (float)((double)map[at] + sum);
+  if (weights || rates_mode) map[at] = (float)((double)map[at] + sum);
   else map[at] = (float)((double)map[at] * (exp(-sum) * prod));
 }
 
@@ -1312,7 +1320,26 @@ int oqg_update(oqg_handle *h, float *map, int N, const float *poes, int64_t P,
   dim3 grid((LG + 127) / 128, N);
   k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
                                         rate, K ? probs : nullptr, K, itime,
-                                        rates_mode);
+                                        rates_mode, nullptr);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_update_mutex(oqg_handle *h, float *map, int N, const float *poes,
+                     int64_t P, const int64_t *order, const int64_t *seg,
+                     const double *rate, const double *probs, int K,
+                     double itime, const double *weights) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
+  if (P <= 0 || N <= 0) return 0;
+  if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
+  if (!weights) return fail(h, "update_mutex: missing weights");
+  int LG = h->M * h->L1 * h->G;
+  dim3 grid((LG + 127) / 128, N);
+  k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
+                                        rate, K ? probs : nullptr, K, itime,
+                                        0, weights);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -115,3 +115,34 @@ def test_cluster_group(oq):
     np.testing.assert_allclose(a.array[rows], b.array[rows], rtol=2e-6,
                                atol=1e-7)   # float32 PoEs of the unfused path
     assert (a.array[rows] < 1).any()
+
+
+@pytest.mark.gpu
+def test_mutex_ruptures(oq):
+    """ContextMaker.get_pmap(ctx, tom, rup_mutex): update_pmap_m
+    (map_array.py:262-269) against the reference on the same ruptures"""
+    M = np.load(os.path.join(GOLDEN, 'rup_mutex.npz'))
+    cm, _, srcs = setup(oq)
+    N = len(M['site_lon'])
+    sc = oq.SiteCollection.from_points(
+        M['site_lon'], M['site_lat'], np.zeros(N), dict(vs30=np.full(N, 500.)))
+    h = cm.handle()
+    ctxs = []
+    for i, src in enumerate(srcs):
+        b = oq.PointSourceBatch([src])
+        t_pla, t_mag, _ = oq.point_ruptures_device(b, h)
+        pla = t_pla.cpu().numpy().reshape(-1, 3, 14).view(
+            oq.planar_array_dt).reshape(-1, 3)
+        ctxs.extend(cm.get_ctxs(oq.PlanarRuptures(pla, t_mag.cpu().numpy()),
+                                sc, src_id=i))
+    ctx = cm.recarray(ctxs)
+    assert len(ctx) == int(M['nrows'])
+    rup_mutex = {(int(s), int(r)): w
+                 for (s, r), w in zip(M['keys'], M['weights'])}
+    assert set(zip(ctx.src_id.tolist(), ctx.rup_id.tolist())) == set(rup_mutex)
+    pmap = cm.get_pmap(ctx, oq.PoissonTOM(50.), rup_mutex)
+    assert (pmap.sids == M['sids']).all()
+    np.testing.assert_allclose(pmap.array, M['poes'], rtol=2e-5, atol=1e-9)
+    # independent ruptures through the same call: the usual PoE map
+    indep = cm.get_pmap(ctx, oq.PoissonTOM(50.))
+    assert (indep.array <= 1).all() and (indep.array != pmap.array).any()
