@@ -125,6 +125,10 @@ int oqg_required_distances(const oqg_gsim *g);
  * An unknown family or flag is an error (there is no fallback). */
 int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
                   const double *coeffs);
+/* mask[G][M] (host, may be NULL = none): 1 where the PoEs of (gsim, IMT) are
+ * zeroed -- the ImtWeight == 0 branch of set_poes (contexts.py:1469-1475);
+ * reset by oqg_set_gsims */
+int oqg_set_imt_mask(oqg_handle *h, const unsigned char *mask);
 /* levels: loglevels[M][L1] (host), as ContextMaker.loglevels
  * (contexts.py:718-724); phi_b = ndtr(truncation_level) (contexts.py:628) */
 int oqg_set_levels(oqg_handle *h, int M, int L1, const double *loglevels,

@@ -60,6 +60,7 @@ def lib():
         'oqg_required_distances': (C.c_int, [C.POINTER(OqgGsim)]),
         'oqg_set_gsims': (C.c_int, [H, C.c_int, C.POINTER(OqgGsim), C.c_int,
                                     c_double_p]),
+        'oqg_set_imt_mask': (C.c_int, [H, C.POINTER(C.c_ubyte)]),
         'oqg_set_levels': (C.c_int, [H, C.c_int, C.c_int, c_double_p,
                                      C.c_double]),
         'oqg_distances': (C.c_int, [H, c_void, C.c_int, C.POINTER(OqgSites),

@@ -376,6 +376,20 @@ class ContextMaker(object):
             h.call('oqg_set_levels', self.M, self.L1,
                    lev.ctypes.data_as(_lib.c_double_p),
                    float(self.truncation_level))
+            # set_poes, contexts.py:1469-1475: an ImtWeight of 0 (set by the
+            # engine when parsing the gsim logic tree) zeroes the PoEs of
+            # that IMT for that gsim
+            mask = numpy.zeros((self.G, self.M), numpy.uint8)
+            for g, gsim in enumerate(self.gsims):
+                weight = getattr(gsim, 'weight', None)
+                dic = getattr(weight, 'dic', None)
+                if dic:
+                    for m, imt in enumerate(self.imtls):
+                        if dic.get(imt) == 0:
+                            mask[g, m] = 1
+            if mask.any():
+                h.call('oqg_set_imt_mask', mask.ctypes.data_as(
+                    ctypes.POINTER(ctypes.c_ubyte)))
             h.owner = self
             h.cfg = (self.L, self.G)
         return h

@@ -59,6 +59,9 @@ __constant__ double c_coef[OQG_MAX_SLOTS][OQG_KMAX];
 // fused-kernel unit, [unit][NL] padded with +inf
 __constant__ double c_loglev[2 * OQG_MAX_LEVELS];
 __constant__ oqg_gsim c_gsim[OQG_MAX_G];
+// 1 where the PoEs of (gsim, IMT) are zeroed: the ImtWeight == 0 branch of
+// set_poes (contexts.py:1469-1475); index g * M + m
+__constant__ unsigned char c_imtmask[OQG_MAX_SLOTS];
 
 // ------------------------------------------------------------------ handle
 struct Buf {
@@ -73,6 +76,7 @@ struct oqg_handle {
   int G = 0, M = 0, L1 = 0;
   std::vector<oqg_gsim> gsims;
   std::vector<double> coef, loglev, loglev_pad;
+  std::vector<unsigned char> imtmask;
   double truncation_level = 0, phi_b = 0;
   bool const_dirty = true;
   unsigned long long launches = 0;
@@ -119,6 +123,9 @@ static int upload_const(oqg_handle *h) {
                                cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyToSymbolAsync(c_gsim, h->gsims.data(),
                                h->gsims.size() * sizeof(oqg_gsim), 0,
+                               cudaMemcpyHostToDevice, h->stream));
+    h->imtmask.resize(OQG_MAX_SLOTS, 0);
+    CK(cudaMemcpyToSymbolAsync(c_imtmask, h->imtmask.data(), OQG_MAX_SLOTS, 0,
                                cudaMemcpyHostToDevice, h->stream));
   }
   if (!h->loglev.empty())
@@ -319,7 +326,7 @@ __global__ void k_poes(const double *__restrict__ ms, int64_t P, int G, int M,
   int64_t idx = ((int64_t)g * M + m) * P + p;
   double mean = ms[idx], sig = ms[(int64_t)G * M * P + idx];
   double z = (c_loglev[l] - mean) / sig;
-  out[e] = (float)truncnorm_sf(phi_b, inv_norm, z);
+  out[e] = c_imtmask[g * M + m] ? 0.f : (float)truncnorm_sf(phi_b, inv_norm, z);
 }
 
 // ----------------------------------------------------------------- update
@@ -513,6 +520,8 @@ k_fused(const FusedArgs A) {
   const CT &Cp = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + A.M]);
   // log levels of this unit, padded to NL with +inf (poe = 0)
   const double *ll = c_loglev + OQG_MAX_LEVELS + (unit_ok ? unit : 0) * NL;
+  // 0 if the PoEs of this (gsim, IMT) are zeroed (ImtWeight == 0)
+  const float keepf = c_imtmask[A.g * A.M + m] ? 0.f : 1.f;
   const ST ss = FF::site(gs, C, si);      // this IMT
   const ST sp = FF::site(gs, Cp, si);     // PGA, for the shared pair state
 
@@ -658,7 +667,7 @@ k_fused(const FusedArgs A) {
         // x = (tl - (l - mean) / sig) * xscale, xscale = 1 / (2 tl)
         const double xa = -inv * A.xscale;
         const double xb = (A.tl + mean * inv) * A.xscale;
-        const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
+        const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime) * keepf;
         // levels are sorted: from the first one at or above mean + tl * sig
         // for every lane of the warp on, all the PoEs are zero (the padding
         // levels are +inf).  The threshold is reduced over the warp in
@@ -694,11 +703,11 @@ k_fused(const FusedArgs A) {
         const double *pr = s_probs + i * A.K;
 #pragma unroll
         for (int l = 0; l < NL; l++) {
-          double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
+          double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv) * keepf;
           acc[l] *= A.itime == 0. ? 1. - poe : pne_from_pmf(pr, A.K, poe);
         }
       } else {
-        const double rt = s_rup[RF_RATE * RT + i] * A.itime;
+        const double rt = s_rup[RF_RATE * RT + i] * A.itime * keepf;
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
@@ -948,6 +957,7 @@ int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
   CK(cudaStreamSynchronize(h->stream));
   h->G = G; h->M = M;
   h->gsims.assign(gsims, gsims + G);
+  h->imtmask.assign(OQG_MAX_SLOTS, 0);
   h->coef.assign(coeffs, coeffs + (size_t)G * (M + 1) * OQG_KMAX);
   // derived per-IMT constants of the staged model code (oqg_fast.cuh)
   for (int g = 0; g < G; g++)
@@ -959,6 +969,17 @@ int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
         row[OQG_DER + CY_INV_C9B] = 1. / c->c9b;
       }
     }
+  h->const_dirty = true;
+  return 0;
+}
+
+int oqg_set_imt_mask(oqg_handle *h, const unsigned char *mask) {
+  if (!h->G || !h->M) return fail(h, "set_imt_mask: set_gsims not called");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->imtmask.assign(OQG_MAX_SLOTS, 0);
+  if (mask)
+    for (int i = 0; i < h->G * h->M; i++) h->imtmask[i] = mask[i] ? 1 : 0;
   h->const_dirty = true;
   return 0;
 }

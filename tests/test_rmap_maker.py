@@ -146,3 +146,41 @@ def test_mutex_ruptures(oq):
     # independent ruptures through the same call: the usual PoE map
     indep = cm.get_pmap(ctx, oq.PoissonTOM(50.))
     assert (indep.array <= 1).all() and (indep.array != pmap.array).any()
+
+
+@pytest.mark.gpu
+def test_imt_weight_zero(oq):
+    """set_poes, contexts.py:1469-1475: an ImtWeight of zero zeroes the PoEs
+    of that IMT for that gsim -- fused pass and unfused operators against
+    the reference's get_pmap"""
+    import types
+    W = np.load(os.path.join(GOLDEN, 'imt_weight.npz'))
+    cm, _, srcs = setup(oq)
+    cm.gsims[1].weight = types.SimpleNamespace(dic={'SA(0.2)': 0, 'PGA': 0.5})
+    N = len(W['site_lon'])
+    sc = oq.SiteCollection.from_points(
+        W['site_lon'], W['site_lat'], np.zeros(N), dict(vs30=np.full(N, 500.)))
+    L1 = len(D['levels'])
+    pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1)
+    kept = cm.hazard_point_sources(pmap, srcs, sc, count=True)
+    assert kept == int(W['nrows'])
+    poes = (~pmap).array
+    assert (poes[:, L1:2 * L1, 1] == 0).all()
+    np.testing.assert_allclose(poes, W['poes'], rtol=2e-5, atol=2e-7)
+    # unfused: get_ctxs -> get_pmap
+    h = cm.handle()
+    ctxs = []
+    for i, src in enumerate(srcs):
+        t_pla, t_mag, _ = oq.point_ruptures_device(oq.PointSourceBatch([src]), h)
+        pla = t_pla.cpu().numpy().reshape(-1, 3, 14).view(
+            oq.planar_array_dt).reshape(-1, 3)
+        ctxs.extend(cm.get_ctxs(oq.PlanarRuptures(pla, t_mag.cpu().numpy()),
+                                sc, src_id=i))
+    unf = cm.get_pmap(cm.recarray(ctxs), oq.PoissonTOM(50.))
+    assert (unf.array[:, L1:2 * L1, 1] == 0).all()
+    np.testing.assert_allclose(unf.array, W['poes'], rtol=2e-5, atol=2e-7)
+    # a new ContextMaker without weights on the same handle resets the mask
+    cm2, _, _ = setup(oq)
+    pm2 = oq.MapArray(sc.sids, cm2.L, cm2.G).fill(1)
+    cm2.hazard_point_sources(pm2, srcs, sc)
+    assert ((~pm2).array[:, L1:2 * L1, 1] > 0).any()
