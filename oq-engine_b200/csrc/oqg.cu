@@ -1133,12 +1133,13 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     memcpy(B.wsum, A.wsum, sizeof(B.wsum));
     memcpy(B.kind, A.kind, sizeof(B.kind));
     memcpy(B.q, A.q, sizeof(B.q));
-    size_t smem = (size_t)B.W * R * 12 + (R + 1 + rgs.size()) * 4 + 16 +
-                  (size_t)128 * (Gt | 1) * 4;
+    const int RP = R <= 4 ? 4 : (R <= 8 ? 8 : (R <= 16 ? 16 : 32));
+    size_t smem = (size_t)RP * 128 * 8 + (size_t)B.W * R * 12 +
+                  (R + 1 + rgs.size()) * 4 + 16 + (size_t)128 * (Gt | 1) * 4;
     unsigned grid = (unsigned)((A.n_elems + 127) / 128);
-    if (R <= 4) k_postclassical_reg<4><<<grid, 128, smem, h->stream>>>(B);
-    else if (R <= 8) k_postclassical_reg<8><<<grid, 128, smem, h->stream>>>(B);
-    else if (R <= 16) k_postclassical_reg<16><<<grid, 128, smem, h->stream>>>(B);
+    if (RP == 4) k_postclassical_reg<4><<<grid, 128, smem, h->stream>>>(B);
+    else if (RP == 8) k_postclassical_reg<8><<<grid, 128, smem, h->stream>>>(B);
+    else if (RP == 16) k_postclassical_reg<16><<<grid, 128, smem, h->stream>>>(B);
     else k_postclassical_reg<32><<<grid, 128, smem, h->stream>>>(B);
     h->launches++;
     CK(cudaGetLastError());

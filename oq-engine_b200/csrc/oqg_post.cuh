@@ -133,7 +133,8 @@ k_postclassical(const PostArgs A) {
 // 64-bit sort keys
 //     [ bits 63..10 of the (non negative) float64 value | weight rank (5) |
 //       realization (5) ]
-// which a bitonic network with compile-time indices sorts for the quantiles
+// (staged through shared memory so that the value loop stays rolled) which
+// a bitonic network with compile-time register indices sorts for the quantiles
 // (ties of the value are broken by the weight like numpy's sort(order='c');
 // values are compared, and used in the interpolation, to 2^-42 relative).  The variance uses sums shifted by the first value, exact for
 // equal curves.
@@ -162,14 +163,37 @@ __device__ __forceinline__ double post_key_value(unsigned long long k) {
   return __longlong_as_double((long long)(k & ~0x3ffull));
 }
 
+// one stage of the bitonic network: compare-exchange of key[i] and key[i ^ J]
+// for all i; the direction of element i in the merge of size k is
+// (i & k) == 0 -> ascending.  Five instantiations (J = 16 .. 1) executed by
+// a rolled (k, j) loop keep the code at ~1 100 SASS instructions: the fully
+// unrolled network (15 stages) made the kernel instruction-fetch bound.
+template <int RP, int J>
+__device__ __forceinline__ void bitonic_stage(unsigned long long (&key)[RP],
+                                              int k) {
+#pragma unroll
+  for (int i = 0; i < RP; i++) {
+    const int p = i ^ J;
+    if (p > i) {
+      const bool up = (i & k) == 0;
+      const unsigned long long a = key[i], b = key[p];
+      const bool sw = (a > b) == up;
+      key[i] = sw ? b : a;
+      key[p] = sw ? a : b;
+    }
+  }
+}
+
 template <int RP>
 __global__ void __launch_bounds__(128)
 k_postclassical_reg(const PostRegArgs A) {
   extern __shared__ double sm_post[];
   math_tables_init();   // fast_exp of oqg_math.cuh
-  // shared: weights [W][R] (double), wrank [W][R], r_off [R + 1], r_gs
+  // shared: keys [RP][128], weights [W][R] (double), wrank [W][R],
+  // r_off [R + 1], r_gs, rates [128][Gt | 1]
   const int R = A.R, WR = A.W * R;
-  double *s_w = sm_post;
+  unsigned long long *s_key = (unsigned long long *)sm_post + threadIdx.x;
+  double *s_w = sm_post + RP * 128;
   int *s_rank = (int *)(s_w + WR);
   int *s_off = s_rank + WR;
   int *s_gs = s_off + R + 1;
@@ -204,23 +228,19 @@ k_postclassical_reg(const PostRegArgs A) {
   const double wsum = A.wsum[wcol];
   const float *row = s_rates + threadIdx.x * gstride;
   const bool stats = A.stat_out && A.S > 0 && wsum != 0.;
-  unsigned long long key[RP];
   double sw1 = 0., sw2 = 0., v0 = 0.;
-#pragma unroll
-  for (int r = 0; r < RP; r++) {
-    key[r] = ~0ull;                      // padding sorts last
-    if (r < R) {
-      double x = 0.;
-      for (int k = s_off[r]; k < s_off[r + 1]; k++) x += (double)row[s_gs[k]];
-      double v = 1. - fast_exp(fmax(-x, -700.));   // to_probs
-      if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
-      if (A.use_rates) v = to_rate(v);
-      if (r == 0) v0 = v;
-      const double d = v - v0;
-      sw1 = fma(w[r], d, sw1);
-      sw2 = fma(w[r] * d, d, sw2);
-      key[r] = post_key(v, rk[r], r);
-    }
+#pragma unroll 1
+  for (int r = 0; r < R; r++) {
+    double x = 0.;
+    for (int k = s_off[r]; k < s_off[r + 1]; k++) x += (double)row[s_gs[k]];
+    double v = 1. - fast_exp(fmax(-x, -700.));   // to_probs
+    if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
+    if (A.use_rates) v = to_rate(v);
+    if (r == 0) v0 = v;
+    const double d = v - v0;
+    sw1 = fma(w[r], d, sw1);
+    sw2 = fma(w[r] * d, d, sw2);
+    s_key[r * 128] = post_key(v, rk[r], r);
   }
   if (A.stat_out && A.S > 0 && wsum == 0.) {   // getters.py:61-63
     for (int s = 0; s < A.S; s++) A.stat_out[(int64_t)s * A.n_elems + e] = 0.f;
@@ -238,42 +258,43 @@ k_postclassical_reg(const PostRegArgs A) {
       res = sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
     } else {
       if (!sorted) {
+        unsigned long long key[RP];
 #pragma unroll
+        for (int r = 0; r < RP; r++)
+          key[r] = r < R ? s_key[r * 128] : ~0ull;   // padding sorts last
+#pragma unroll 1
         for (int k = 2; k <= RP; k <<= 1) {
-#pragma unroll
+#pragma unroll 1
           for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < RP; i++) {
-              const int p = i ^ j;
-              if (p > i) {
-                const bool up = (i & k) == 0;
-                const unsigned long long a = key[i], b = key[p];
-                const bool sw = up ? a > b : a < b;
-                key[i] = sw ? b : a;
-                key[p] = sw ? a : b;
-              }
+            switch (j) {
+              case 16: if (RP > 16) bitonic_stage<RP, (RP > 16 ? 16 : 1)>(key, k); break;
+              case 8: if (RP > 8) bitonic_stage<RP, (RP > 8 ? 8 : 1)>(key, k); break;
+              case 4: if (RP > 4) bitonic_stage<RP, (RP > 4 ? 4 : 1)>(key, k); break;
+              case 2: bitonic_stage<RP, 2>(key, k); break;
+              default: bitonic_stage<RP, 1>(key, k); break;
             }
           }
         }
+#pragma unroll
+        for (int r = 0; r < RP; r++) s_key[r * 128] = key[r];
         sorted = true;
       }
+      // numpy.interp(q, cumsum(w sorted), v sorted)
       const double q = A.q[s];
       double cum = 0., prev_cum = 0., prev_v = 0.;
-      bool done = false;
       res = 0.;
-#pragma unroll
-      for (int j = 0; j < RP; j++) {
-        if (j < R && !done) {
-          const double vk = post_key_value(key[j]);
-          cum += w[(int)(key[j] & 31u)];
-          if (q < cum || j == R - 1) {
-            if (j == 0 || q >= cum) res = vk;
-            else res = prev_v + (q - prev_cum) * ((vk - prev_v) / (cum - prev_cum));
-            done = true;
-          }
-          prev_cum = cum;
-          prev_v = vk;
+#pragma unroll 1
+      for (int j = 0; j < R; j++) {
+        const unsigned long long kj = s_key[j * 128];
+        const double vk = post_key_value(kj);
+        cum += w[(int)(kj & 31u)];
+        if (q < cum || j == R - 1) {
+          if (j == 0 || q >= cum) res = vk;
+          else res = prev_v + (q - prev_cum) * ((vk - prev_v) / (cum - prev_cum));
+          break;
         }
+        prev_cum = cum;
+        prev_v = vk;
       }
     }
     if (A.use_rates) res = 1. - exp(-res);
