@@ -238,6 +238,22 @@ int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        int64_t U, double *planar_dev, double *mag_dev,
                        double *magdist_dev);
 
+/* ---- non-planar surfaces, first step: rupture distance of
+ * mesh surfaces.  oqg_mesh_min_distance is Mesh.get_min_distance
+ * (hazardlib/geo/mesh.py:365-383, cdist(...).min(0)) for S meshes at once:
+ * mesh points lon/lat/depth_dev[P] (depth may be NULL = 0), the points of
+ * mesh s are off_dev[s] .. off_dev[s + 1]; out_dev[S][N] km.
+ * oqg_section_min is the multi-fault composition of contexts.py:969-971:
+ * out_dev[U][N] = min over the sections rup_sec_dev[rup_off_dev[u] ..
+ * rup_off_dev[u + 1]) of sec_dev[section][N]. */
+int oqg_mesh_min_distance(oqg_handle *h, const double *lon_dev,
+                          const double *lat_dev, const double *depth_dev,
+                          int64_t P, const int64_t *off_dev, int S,
+                          const oqg_sites *sites_dev, int N, double *out_dev);
+int oqg_section_min(oqg_handle *h, const double *sec_dev, int S, int N,
+                    const int64_t *rup_off_dev, const int32_t *rup_sec_dev,
+                    int U, double *out_dev);
+
 /* ---- post-processing of the rates map -------------------
  * oqg_postclassical replaces, for all the sites at once, the loop of
  * postclassical (calculators/classical.py:258-325): MapGetter.get_hcurve

@@ -1048,6 +1048,42 @@ static int prep_ruptures(oqg_handle *h, const double *planar,
   return 0;
 }
 
+int oqg_mesh_min_distance(oqg_handle *h, const double *lon, const double *lat,
+                          const double *depth, int64_t P, const int64_t *off,
+                          int S, const oqg_sites *sites, int N, double *out) {
+  CK(cudaSetDevice(h->device));
+  if (S <= 0 || N <= 0) return 0;
+  if (P <= 0 || !lon || !lat || !off || !out)
+    return fail(h, "mesh_min_distance: missing array");
+  if (S > 65535) return fail(h, "mesh_min_distance: at most 65535 meshes per call");
+  if (prep_sites(h, sites, N)) return 1;
+  if (reserve(h, h->stage[9], (size_t)P * 3 * 8)) return 1;
+  double *pts = (double *)h->stage[9].p;
+  k_mesh_xyz<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(lon, lat, depth,
+                                                                P, pts);
+  dim3 grid((N + 128 * MESH_SPT - 1) / (128 * MESH_SPT), S);
+  k_mesh_min_distance<<<grid, 128, 0, h->stream>>>(
+      pts, P, off, S, (const double *)h->site.p, N, out);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_section_min(oqg_handle *h, const double *sec, int S, int N,
+                    const int64_t *rup_off, const int32_t *rup_sec, int U,
+                    double *out) {
+  CK(cudaSetDevice(h->device));
+  if (U <= 0 || N <= 0) return 0;
+  if (!sec || !rup_off || !rup_sec || !out || S <= 0)
+    return fail(h, "section_min: missing array");
+  if (U > 65535) return fail(h, "section_min: at most 65535 ruptures per call");
+  dim3 grid((N + 127) / 128, U);
+  k_section_min<<<grid, 128, 0, h->stream>>>(sec, N, rup_off, rup_sec, U, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
                       int M, const int32_t *g_off, const int32_t *g_rlz, int R,
                       const double *weights, int W, const double *weight_sums,

@@ -1,0 +1,112 @@
+"""Mesh surfaces, first step: the rupture
+distance.  `Mesh.get_min_distance` mirrors
+openquake/hazardlib/geo/mesh.py:365-383; `mesh_min_distance` evaluates it
+for many meshes (the sections of multi-fault sources, or the ruptures of
+fault sources) in one call and `section_min` composes the per-section
+distances of multi-fault ruptures (contexts.py:969-971)."""
+import ctypes
+import numpy
+
+
+class Mesh(object):
+    """Points on or below the Earth surface: lons, lats (degrees), depths
+    (km, optional)"""
+    def __init__(self, lons, lats, depths=None):
+        self.lons = numpy.asarray(lons, float).ravel()
+        self.lats = numpy.asarray(lats, float).ravel()
+        self.depths = None if depths is None else \
+            numpy.asarray(depths, float).ravel()
+        assert len(self.lons) == len(self.lats)
+        assert self.depths is None or len(self.depths) == len(self.lons)
+
+    def __len__(self):
+        return len(self.lons)
+
+    def get_min_distance(self, mesh, device=None):
+        """minimum distance from this mesh to each point of `mesh` (a Mesh
+        or a SiteCollection), km, shape (len(mesh),)"""
+        return mesh_min_distance([self], mesh, device)[0]
+
+
+def _sites_struct(points, dev):
+    from . import _lib
+    from .contexts import _dev
+    st = _lib.OqgSites()
+    keep = []
+    if hasattr(points, 'array'):        # SiteCollection
+        lon, lat, dep = (points.array[n] for n in ('lon', 'lat', 'depth'))
+    else:
+        lon, lat = points.lons, points.lats
+        dep = points.depths if points.depths is not None else \
+            numpy.zeros(len(lon))
+    for name, arr in (('lon', lon), ('lat', lat), ('depth', dep)):
+        t = _dev(numpy.asarray(arr, float), dev)
+        keep.append(t)
+        setattr(st, name, t.data_ptr())
+    return st, keep, len(lon)
+
+
+def mesh_min_distance(meshes, points, device=None, as_tensor=False):
+    """
+    :param meshes: a list of S Mesh objects
+    :param points: a Mesh or a SiteCollection of N points
+    :returns: (S, N) float64 minimum distances in km
+    """
+    import torch
+    from .contexts import get_handle, _device_index, _dev, _ptr
+    h = get_handle(_device_index(device))
+    dev = h.device
+    S = len(meshes)
+    off = numpy.concatenate([[0], numpy.cumsum([len(m) for m in meshes])]
+                            ).astype(numpy.int64)
+    if S == 0 or off[-1] == 0:
+        raise ValueError('empty mesh')
+    has_dep = any(m.depths is not None for m in meshes)
+    t_lon = _dev(numpy.concatenate([m.lons for m in meshes]), dev)
+    t_lat = _dev(numpy.concatenate([m.lats for m in meshes]), dev)
+    t_dep = _dev(numpy.concatenate([
+        m.depths if m.depths is not None else numpy.zeros(len(m))
+        for m in meshes]), dev) if has_dep else None
+    t_off = _dev(off, dev)
+    st, keep, N = _sites_struct(points, dev)
+    out = torch.empty((S, N), dtype=torch.float64, device='cuda:%d' % dev)
+    for s0 in range(0, S, 65535):       # grid.y limit
+        s1 = min(S, s0 + 65535)
+        h.call('oqg_mesh_min_distance', _ptr(t_lon), _ptr(t_lat), _ptr(t_dep),
+               int(off[-1]), ctypes.c_void_p(t_off.data_ptr() + 8 * s0),
+               s1 - s0, ctypes.byref(st), N,
+               ctypes.c_void_p(out.data_ptr() + 8 * N * s0))
+    torch.cuda.current_stream(dev).synchronize()
+    return out if as_tensor else out.cpu().numpy()
+
+
+def section_min(sec_dist, rup_sections, device=None):
+    """
+    :param sec_dist: (S, N) distances of the sections (numpy or CUDA tensor)
+    :param rup_sections: for each rupture the list of its section indices
+    :returns: (U, N) float64, the minimum over the sections of each rupture
+    """
+    import torch
+    from .contexts import get_handle, _device_index, _dev, _ptr
+    h = get_handle(_device_index(device))
+    dev = h.device
+    t_sec = _dev(sec_dist, dev, torch.float64)
+    S, N = t_sec.shape
+    U = len(rup_sections)
+    roff = numpy.concatenate([[0], numpy.cumsum([len(r) for r in rup_sections])
+                              ]).astype(numpy.int64)
+    rsec = numpy.concatenate([numpy.asarray(r, numpy.int32)
+                              for r in rup_sections]).astype(numpy.int32)
+    if len(rsec) and (rsec.min() < 0 or rsec.max() >= S):
+        raise ValueError('section index out of range')
+    if (numpy.diff(roff) == 0).any():
+        raise ValueError('a rupture without sections')
+    t_roff, t_rsec = _dev(roff, dev), _dev(rsec, dev)
+    out = torch.empty((U, N), dtype=torch.float64, device='cuda:%d' % dev)
+    for u0 in range(0, U, 65535):
+        u1 = min(U, u0 + 65535)
+        h.call('oqg_section_min', _ptr(t_sec), S, N,
+               ctypes.c_void_p(t_roff.data_ptr() + 8 * u0), _ptr(t_rsec),
+               u1 - u0, ctypes.c_void_p(out.data_ptr() + 8 * N * u0))
+    torch.cuda.current_stream(dev).synchronize()
+    return out.cpu().numpy()
