@@ -187,6 +187,18 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar_dev,
                       int rates_mode, float *map_dev,
                       unsigned long long *counters_dev);
 
+/* oqg_hazard_planar with the per-rupture visibility of the
+ * pointsource_distance approximation: aux_dev [U][OQG_AUX_LEN] from
+ * oqg_point_ruptures, or NULL (every site sees every rupture) */
+int oqg_hazard_planar_aux(oqg_handle *h, const double *planar_dev,
+                          const double *mag_dev, const double *magdist_dev,
+                          const double *aux_dev, const double *probs_occur_dev,
+                          int K, int U, const oqg_sites *sites_dev,
+                          const uint32_t *sidx_dev, int N,
+                          double minimum_distance, double itime,
+                          int rates_mode, float *map_dev,
+                          unsigned long long *counters_dev);
+
 /* same with HOST buffers: copies the ruptures and sites in, the map in and
  * out, and synchronises; map is host [N][L][G] float32 (sidx = identity) */
 int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
@@ -226,17 +238,36 @@ typedef struct {
   const double *hd_frac;              /* hypo_dip_fracs; NULL = 0.5 */
   int32_t msr;                        /* OQG_MSR_* */
   int32_t shift_hypo;                 /* ContextMaker.shift_hypo */
+  /* the pointsource_distance approximation of _quintets
+   * (hazardlib/contexts.py:321-370; engine default 100 km): 0 = off.  When
+   * positive, a source with np_cnt * hd_cnt > 1 has, per magnitude,
+   * np_cnt * hd_cnt + 1 ruptures: all the planes and depths for the sites
+   * within psdist(mag) = min(radius(mag), mag_dist / 2) +
+   * pointsource_distance of the source location (chord distance,
+   * SiteCollection.get_cdist), and the average rupture of
+   * PointSource.iruptures (source/point.py:311-318) for the other sites;
+   * rup_off must count them. */
+  double pointsource_distance;
+  /* optional [U]: overrides the visibility of each rupture (0 all sites,
+   * 1 near, 2 far, 3 none) -- the all-or-nothing rule of the reference for
+   * few sites (contexts.py:358-362) is decided by the caller */
+  const uint8_t *mode;
 } oqg_point_sources;
+
+#define OQG_AUX_LEN 5 /* per rupture: x, y, z of the source location (km),
+                         psdist (km), mode */
 
 /* planar_dev[U][42] in the planar_array_dt record layout, except that wlr[2]
  * holds the occurrence rate mag_rate * (np_prob * hd_prob) (the convention
  * of oqg_hazard_planar; the reference keeps the weight there and multiplies
  * by the magnitude rate in _get_ctx_planar, contexts.py:416);
- * mag_dev[U]; magdist_dev[U] (NULL if mag_dist is NULL).  An unknown msr is
- * an error. */
+ * mag_dev[U]; magdist_dev[U] (NULL if mag_dist is NULL); aux_dev
+ * [U][OQG_AUX_LEN] (may be NULL when pointsource_distance is 0 and mode is
+ * NULL), to be passed to oqg_hazard_planar_aux.  An unknown msr is an
+ * error. */
 int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        int64_t U, double *planar_dev, double *mag_dev,
-                       double *magdist_dev);
+                       double *magdist_dev, double *aux_dev);
 
 /* ---- non-planar surfaces, first step: rupture distance of
  * mesh surfaces.  oqg_mesh_min_distance is Mesh.get_min_distance

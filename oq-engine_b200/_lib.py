@@ -84,7 +84,11 @@ def lib():
             C.POINTER(OqgSites), C.c_int, C.c_double, C.c_double, C.c_int,
             c_void, C.POINTER(C.c_ulonglong)]),
         'oqg_point_ruptures': (C.c_int, [H, c_void, C.c_int, C.c_int64,
-                                         c_void, c_void, c_void]),
+                                         c_void, c_void, c_void, c_void]),
+        'oqg_hazard_planar_aux': (C.c_int, [
+            H, c_void, c_void, c_void, c_void, c_void, C.c_int, C.c_int,
+            C.POINTER(OqgSites), c_void, C.c_int, C.c_double, C.c_double,
+            C.c_int, c_void, c_void]),
         'oqg_postclassical': (C.c_int, [
             H, c_void, C.c_int, C.c_int, C.c_int, C.c_int, c_void, c_void,
             C.c_int, c_void, C.c_int, c_double_p, C.c_int,

@@ -324,8 +324,11 @@ class ContextMaker(object):
         self.minimum_distance = param.get('minimum_distance', 0)
         self.investigation_time = param.get('investigation_time')
         self.shift_hypo = param.get('shift_hypo', False)
-        self.pointsource_distance = float(
-            param.get('pointsource_distance') or 0)
+        self.max_sites_disagg = param.get('max_sites_disagg', 10)
+        psd = param.get('pointsource_distance') or 0
+        if isinstance(psd, dict):   # floatdict of the job.ini, by TRT
+            psd = psd.get(trt, psd.get('default', 0))
+        self.pointsource_distance = float(psd)
         self.truncation_level = param.get('truncation_level', 99.)
         self.phi_b = float(ndtr(self.truncation_level))
         self.device = device
@@ -647,8 +650,8 @@ class ContextMaker(object):
                           device='cuda:%d' % dev), 1
 
     def _hazard_planar_dev(self, pmap, t_pla, t_mag, t_md, t_probs, K, U,
-                           sitecol, count):
-        # ruptures already on the device -> oqg_hazard_planar
+                           sitecol, count, t_aux=None):
+        # ruptures already on the device -> oqg_hazard_planar_aux
         import torch
         h = self.handle()
         dev = h.device
@@ -659,9 +662,9 @@ class ContextMaker(object):
         t_map = _dev(pmap.array, dev) if on_host else pmap.array
         t_cnt = torch.zeros(2, dtype=torch.int64, device='cuda:%d' % dev) \
             if count else None
-        h.call('oqg_hazard_planar', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
-               _ptr(t_probs), K, U, ctypes.byref(st), _ptr(t_sidx), N,
-               float(self.minimum_distance),
+        h.call('oqg_hazard_planar_aux', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
+               _ptr(t_aux), _ptr(t_probs), K, U, ctypes.byref(st),
+               _ptr(t_sidx), N, float(self.minimum_distance),
                0. if self.cluster else float(self.tom.time_span),
                int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
         if on_host:
@@ -676,22 +679,19 @@ class ContextMaker(object):
         ``for src in sources: for ctx in get_ctxs(src, sitecol):
         update(pmap, ctx)`` (genctxs_Pp, contexts.py:443-474) with the
         ruptures built on the device (oqg_point_ruptures) and no context
-        rows materialised.  As in the reference with the default
-        pointsource_distance, every rupture of every (magnitude, nodal
-        plane, depth) combination is used; the pointsource_distance
-        approximation of _quintets (contexts.py:321-370) is not applied.
+        rows materialised.  With a `pointsource_distance` below 1000 km in
+        the parameters (the engine default is 100) the approximation of
+        _quintets (contexts.py:321-370) applies: sites farther than
+        psdist(mag) from a source with several nodal planes / depths see one
+        average rupture per magnitude; with at most `max_sites_disagg`
+        sites the choice is all-or-nothing per magnitude.
         """
         from .source import PointSourceBatch, point_ruptures_device
-        batch = sources if isinstance(sources, PointSourceBatch) \
-            else PointSourceBatch(sources)
         # the reference's default (1000 km) keeps every site "close", i.e.
         # no approximation; a smaller value replaces, for far sites, the
         # nodal planes / depths by one average rupture (_quintets)
-        if 0 < self.pointsource_distance < 1000 and (
-                batch.cnt['np'] * batch.cnt['hd'] > 1).any():
-            raise NotImplementedError(
-                'the pointsource_distance approximation has no device '
-                'implementation')
+        batch = sources if isinstance(sources, PointSourceBatch) \
+            else PointSourceBatch(sources, self.pointsource_distance)
         h = self.handle()
         tom = self.tom or PoissonTOM(self.investigation_time)
         self.tom = tom
@@ -707,10 +707,16 @@ class ContextMaker(object):
             probs = numpy.ascontiguousarray(tom.get_pmf(rate))
             K = probs.shape[1]
             t_probs = _dev(probs, h.device)
-        t_pla, t_mag, t_md = point_ruptures_device(
-            batch, h, self.magdist(batch.mag), self.shift_hypo)
+        mag_dist = self.magdist(batch.mag)
+        mode = None
+        if batch.pointsource_distance > 0 and \
+                len(sitecol) <= self.max_sites_disagg:
+            # few sites: all-or-nothing per magnitude, contexts.py:358-362
+            mode = batch.fewsites_mode(mag_dist, sitecol)
+        t_pla, t_mag, t_md, t_aux = point_ruptures_device(
+            batch, h, mag_dist, self.shift_hypo, mode, with_aux=True)
         return self._hazard_planar_dev(pmap, t_pla, t_mag, t_md, t_probs, K,
-                                       batch.U, sitecol, count)
+                                       batch.U, sitecol, count, t_aux)
 
     def get_pmap_planar(self, src, sitecol):
         """PoE map of planar ruptures on the sites through the fused path"""

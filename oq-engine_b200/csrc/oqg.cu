@@ -156,11 +156,18 @@ __global__ void k_prep_ruptures(const double *__restrict__ planar,
   prep_rupture(pl, mag[u], magdist ? magdist[u] : INFINITY, out + u, U);
 }
 
-// one thread per rupture of a batch of point sources (oqg_source.cuh)
+// one thread per rupture of a batch of point sources (oqg_source.cuh).
+// Without the pointsource_distance approximation a source has M * N * D
+// ruptures ordered (magnitude, nodal plane, depth).  With it, a source with
+// N * D > 1 has M blocks of N * D + 1 ruptures: the N * D ruptures of the
+// magnitude, seen by the sites within psdist of the source (mode 1), and
+// the average rupture of PointSource.iruptures (point.py:311-318,
+// calc_average :47-95), seen by the others (mode 2).
 __global__ void k_point_ruptures(const oqg_point_sources P, int S, int64_t U,
                                  double *__restrict__ planar,
                                  double *__restrict__ mag_out,
-                                 double *__restrict__ magdist_out) {
+                                 double *__restrict__ magdist_out,
+                                 double *__restrict__ aux_out) {
   int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
   int lo = 0, hi = S;   // last s with rup_off[s] <= u
@@ -171,20 +178,75 @@ __global__ void k_point_ruptures(const oqg_point_sources P, int S, int64_t U,
   const int s = lo;
   const int64_t r = u - P.rup_off[s];
   const int N = P.np_cnt[s], D = P.hd_cnt[s];
-  const int m = (int)(r / ((int64_t)N * D));
-  const int n = (int)((r / D) % N), d = (int)(r % D);
-  const int im = P.mag_beg[s] + m, in = P.np_beg[s] + n, id = P.hd_beg[s] + d;
-  const double mag = P.mag[im], rake = P.np_rake[in];
-  const double weight = P.np_prob[in] * P.hd_prob[id];
+  const bool psd_on = P.pointsource_distance > 0. && N * D > 1;
+  const int B = N * D + (psd_on ? 1 : 0);
+  const int m = (int)(r / B), j = (int)(r % B);
+  const int im = P.mag_beg[s] + m;
+  const double mag = P.mag[im];
+  double strike, dip, rake, dep, frac, weight;
+  if (j < N * D) {
+    const int in = P.np_beg[s] + j / D, id = P.hd_beg[s] + j % D;
+    strike = P.np_strike[in]; dip = P.np_dip[in]; rake = P.np_rake[in];
+    dep = P.hd_depth[id];
+    frac = P.hd_frac ? P.hd_frac[id] : 0.5;
+    weight = P.np_prob[in] * P.hd_prob[id];
+  } else {
+    // numpy.average over the nodal planes / the depths, weight 1
+    double ws = 0., a = 0., b = 0., c = 0.;
+    for (int k = 0; k < N; k++) {
+      const int in = P.np_beg[s] + k;
+      const double w = P.np_prob[in];
+      ws += w; a += w * P.np_strike[in]; b += w * P.np_dip[in];
+      c += w * P.np_rake[in];
+    }
+    strike = a / ws; dip = b / ws; rake = c / ws;
+    ws = 0.; a = 0.; b = 0.;
+    for (int k = 0; k < D; k++) {
+      const int id = P.hd_beg[s] + k;
+      const double w = P.hd_prob[id];
+      ws += w; a += w * P.hd_depth[id];
+      b += w * (P.hd_frac ? P.hd_frac[id] : 0.5);
+    }
+    dep = a / ws; frac = b / ws;
+    weight = 1.;
+  }
   double pl[OQG_PLANAR_LEN];
   build_planar_rupture(P.usd[s], P.lsd[s], P.rar[s],
-                       median_area(P.msr, mag, rake), P.np_strike[in],
-                       P.np_dip[in], rake, P.lon[s], P.lat[s], P.hd_depth[id],
-                       P.hd_frac ? P.hd_frac[id] : 0.5,
-                       P.mag_rate[im] * weight, P.shift_hypo, pl);
+                       median_area(P.msr, mag, rake), strike, dip, rake,
+                       P.lon[s], P.lat[s], dep, frac, P.mag_rate[im] * weight,
+                       P.shift_hypo, pl);
   for (int k = 0; k < OQG_PLANAR_LEN; k++) planar[u * OQG_PLANAR_LEN + k] = pl[k];
   mag_out[u] = mag;
   if (magdist_out) magdist_out[u] = P.mag_dist[im];
+  if (aux_out) {
+    double *ax = aux_out + u * OQG_AUX_LEN;
+    double sl, cl, sp, cp;
+    sincos(P.lon[s] * 0.017453292519943295, &sl, &cl);
+    sincos(P.lat[s] * 0.017453292519943295, &sp, &cp);
+    ax[0] = OQG_EARTH_RADIUS * cp * cl;
+    ax[1] = OQG_EARTH_RADIUS * cp * sl;
+    ax[2] = OQG_EARTH_RADIUS * sp;
+    double psdist = 0., mode = 0.;
+    if (psd_on) {
+      // PointSource.get_psdist / _get_max_rupture_projection_radius
+      // (point.py:215-256): half the diagonal of the surface projection of
+      // the rupture of the LAST nodal plane; 0 for PointMSR
+      double radius = 0.;
+      if (P.msr != OQG_MSR_POINT) {
+        const int il = P.np_beg[s] + N - 1;
+        double len, wproj;
+        rupture_dims(P.usd[s], P.lsd[s], P.rar[s],
+                     median_area(P.msr, mag, P.np_rake[il]), P.np_dip[il], len,
+                     wproj);
+        radius = sqrt(len * len + wproj * wproj) / 2.0;
+      }
+      psdist = fmin(radius, P.mag_dist[im] / 2.) + P.pointsource_distance;
+      mode = j < N * D ? 1. : 2.;
+    }
+    if (P.mode) mode = (double)P.mode[u];
+    ax[3] = psdist;
+    ax[4] = mode;
+  }
 }
 
 __global__ void k_prep_sites(const double *__restrict__ lon,
@@ -401,6 +463,7 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 struct FusedArgs {
   const double *rup;      // [NF_RUP][U]
   const double *probs;    // [U][K] or null
+  const double *aux;      // [U][OQG_AUX_LEN] or null (pointsource_distance)
   const double *site;     // [NF_SITE][N]
   const double *vs30, *z1pt0, *z2pt5;
   const uint8_t *vs30measured;
@@ -599,6 +662,20 @@ k_fused(const FusedArgs A) {
             if (vals[k] < A.mindist) vals[k] = A.mindist;
       }
       bool ok = site_ok && vals[0] < s_rup[RF_MAGDIST * RT + i];
+      if (A.aux) {
+        // pointsource_distance (contexts.py:347-370): [x, y, z of the source
+        // location, psdist, mode] per rupture, uniform over the warp; near
+        // sites (chord distance to the location <= psdist) see every nodal
+        // plane and depth (mode 1), far sites one average rupture (mode 2)
+        const double *ax = A.aux + (r0 + i) * OQG_AUX_LEN;
+        const double mode = ax[4];
+        if (mode != 0.) {
+          const double dx = sx[0] - ax[0], dy = sx[1] - ax[1],
+                       dz = sx[2] - ax[2];
+          const bool close = fma(dx, dx, fma(dy, dy, dz * dz)) <= ax[3] * ax[3];
+          ok = ok && (mode == 1. ? close : (mode == 2. ? !close : false));
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 6; k++)
         if ((A.dmask >> k) & 1)
@@ -1204,7 +1281,7 @@ int oqg_hazard_maps(oqg_handle *h, const float *curves, int64_t K, int M,
 
 int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        int64_t U, double *planar, double *mag,
-                       double *magdist) {
+                       double *magdist, double *aux) {
   CK(cudaSetDevice(h->device));
   if (S <= 0 || U <= 0) return 0;
   if (src->msr != OQG_MSR_WC1994 && src->msr != OQG_MSR_POINT)
@@ -1218,8 +1295,13 @@ int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
   if (!planar || !mag) return fail(h, "point sources: missing output");
   if (magdist && !src->mag_dist)
     return fail(h, "point sources: magdist output without mag_dist");
+  if (src->pointsource_distance > 0. && (!src->mag_dist || !aux))
+    return fail(h, "point sources: pointsource_distance needs mag_dist and "
+                   "the aux output");
+  if (src->mode && !aux)
+    return fail(h, "point sources: mode needs the aux output");
   k_point_ruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
-      *src, S, U, planar, mag, magdist);
+      *src, S, U, planar, mag, magdist, aux);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1441,6 +1523,17 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
                       int U, const oqg_sites *sites, const uint32_t *sidx,
                       int N, double mindist, double itime, int rates_mode,
                       float *map, unsigned long long *counters) {
+  return oqg_hazard_planar_aux(h, planar, mag, magdist, nullptr, probs, K, U,
+                               sites, sidx, N, mindist, itime, rates_mode, map,
+                               counters);
+}
+
+int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
+                          const double *mag, const double *magdist,
+                          const double *aux, const double *probs, int K, int U,
+                          const oqg_sites *sites, const uint32_t *sidx, int N,
+                          double mindist, double itime, int rates_mode,
+                          float *map, unsigned long long *counters) {
   CK(cudaSetDevice(h->device));
   if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
   if (U <= 0 || N <= 0) return 0;
@@ -1455,6 +1548,7 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
   memset(&A, 0, sizeof(A));
   A.rup = (const double *)h->rup.p;
   A.probs = K ? probs : nullptr;
+  A.aux = aux;
   A.site = (const double *)h->site.p;
   A.vs30 = sites->vs30; A.z1pt0 = sites->z1pt0; A.z2pt5 = sites->z2pt5;
   A.vs30measured = sites->vs30measured;

@@ -52,6 +52,23 @@ __device__ __forceinline__ double median_area(int msr, double mag,
   return pow(10.0, -2.87 + 0.82 * mag);
 }
 
+// get_rupdims planar.py:68-95: rupture length and horizontal projection of
+// the width, km
+__device__ __forceinline__ void rupture_dims(double usd, double lsd, double rar,
+                                             double area, double dip,
+                                             double &length, double &wproj) {
+  double sdip, cdip;
+  sincos(dip * 0.017453292519943295, &sdip, &cdip);
+  const double max_width = (lsd - usd) / sdip;
+  length = sqrt(area * rar);
+  double width = area / length;
+  if (width > max_width) {
+    width = max_width;
+    length = area / width;
+  }
+  wproj = width * cdip;
+}
+
 // one planar rupture from its parameters; pl = 42 doubles [k][14]
 __device__ inline void build_planar_rupture(
     double usd, double lsd, double rar, double area, double strike, double dip,

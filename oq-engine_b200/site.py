@@ -3,6 +3,8 @@
 parameters vs30, vs30measured, z1pt0, z2pt5."""
 import numpy
 
+EARTH_RADIUS = 6371.0
+
 site_dt = numpy.dtype([
     ('sids', numpy.uint32), ('lon', float), ('lat', float), ('depth', float),
     ('vs30', float), ('vs30measured', bool), ('z1pt0', float),
@@ -45,6 +47,17 @@ class SiteCollection(object):
     @property
     def sids(self):
         return self.array['sids']
+
+    @property
+    def xyz(self):
+        """(N, 3) cartesian coordinates in km (site.py:316-324,
+        geo/utils.py spherical_to_cartesian)"""
+        lon, lat = numpy.radians(self.array['lon']), numpy.radians(
+            self.array['lat'])
+        rr = EARTH_RADIUS - self.array['depth']
+        return numpy.stack([rr * numpy.cos(lat) * numpy.cos(lon),
+                            rr * numpy.cos(lat) * numpy.sin(lon),
+                            rr * numpy.sin(lat)], axis=1)
 
     def filter(self, mask):
         return SiteCollection(self.array[mask])

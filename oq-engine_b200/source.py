@@ -149,7 +149,9 @@ class OqgPointSources(ctypes.Structure):
         'np_cnt', 'hd_beg', 'hd_cnt', 'rup_off', 'mag', 'mag_rate',
         'mag_dist', 'np_strike', 'np_dip', 'np_rake', 'np_prob', 'hd_depth',
         'hd_prob', 'hd_frac')] + [('msr', ctypes.c_int32),
-                                  ('shift_hypo', ctypes.c_int32)]
+                                  ('shift_hypo', ctypes.c_int32),
+                                  ('pointsource_distance', ctypes.c_double),
+                                  ('mode', ctypes.c_void_p)]
 
 
 class PointSourceBatch(object):
@@ -158,9 +160,18 @@ class PointSourceBatch(object):
     (include/oqg.h).  Sources sharing the same MFD object or equal nodal-plane /
     depth distributions (the points of an area source) share one slice of
     the lists.
+
+    :param pointsource_distance: None / 0 / >= 1000 km: every site sees
+        every rupture.  Otherwise the approximation of _quintets
+        (contexts.py:321-370): the sources with more than one (nodal plane,
+        depth) combination get, per magnitude, one more rupture -- the
+        average one of PointSource.iruptures -- for the sites farther than
+        psdist(mag) from the source.
     """
-    def __init__(self, sources):
+    def __init__(self, sources, pointsource_distance=None):
         sources = list(sources)
+        psd = float(pointsource_distance or 0.)
+        self.pointsource_distance = psd if 0. < psd < 1000. else 0.
         if not sources:
             raise ValueError('no sources')
         msrs = {s.msr for s in sources}
@@ -211,7 +222,11 @@ class PointSourceBatch(object):
         self.hd_prob, self.hd_depth = (
             numpy.ascontiguousarray(hdd[:, k]) for k in range(2))
         self.hd_frac = numpy.array(lists['frac'], float) if any_frac else None
-        n = (cnt['mag'].astype(numpy.int64) * cnt['np'] * cnt['hd'])
+        nphc = cnt['np'].astype(numpy.int64) * cnt['hd']
+        # ruptures per magnitude: all the planes and depths, plus the
+        # average rupture where the approximation applies
+        self.block = nphc + ((nphc > 1) & (self.pointsource_distance > 0))
+        n = cnt['mag'].astype(numpy.int64) * self.block
         self.rup_off = numpy.concatenate([[0], numpy.cumsum(n)]).astype(
             numpy.int64)
         self.U = int(self.rup_off[-1])
@@ -229,11 +244,72 @@ class PointSourceBatch(object):
             hb, hc = self.beg['hd'][s], self.cnt['hd'][s]
             w = (self.np_prob[nb:nb + nc, None] *
                  self.hd_prob[None, hb:hb + hc]).ravel()
-            mags.append(numpy.repeat(self.mag[mb:mb + mc], nc * hc))
+            if self.block[s] > nc * hc:      # the average rupture
+                w = numpy.append(w, 1.)
+            mags.append(numpy.repeat(self.mag[mb:mb + mc], len(w)))
             rates.append((self.mag_rate[mb:mb + mc, None] * w[None]).ravel())
         return numpy.concatenate(mags), numpy.concatenate(rates)
 
-    def to_device(self, dev, mag_dist=None, shift_hypo=False):
+    def psdist(self, mag_dist):
+        """
+        (psdist, close-enough radius) per source and magnitude as a list of
+        arrays, PointSource.get_psdist (point.py:215-256): min(radius,
+        magdist / 2) + pointsource_distance with radius half the diagonal of
+        the surface projection of the rupture of the LAST nodal plane
+        """
+        from .planar import wc1994_median_area
+        out = []
+        for s in range(self.S):
+            mb, mc = self.beg['mag'][s], self.cnt['mag'][s]
+            last = self.beg['np'][s] + self.cnt['np'][s] - 1
+            mags = self.mag[mb:mb + mc]
+            if self.msr == MSR['PointMSR']:
+                radius = numpy.zeros(mc)
+            else:
+                area = wc1994_median_area(mags, numpy.full(mc, self.np_rake[last]))
+                rdip = numpy.radians(self.np_dip[last])
+                max_width = (self.lsd[s] - self.usd[s]) / numpy.sin(rdip)
+                length = numpy.sqrt(area * self.rar[s])
+                width = area / length
+                over = width > max_width
+                width = numpy.where(over, max_width, width)
+                length = numpy.where(over, area / width, length)
+                radius = numpy.sqrt(length ** 2 +
+                                    (width * numpy.cos(rdip)) ** 2) / 2.
+            out.append(numpy.minimum(radius, mag_dist[mb:mb + mc] / 2.) +
+                       self.pointsource_distance)
+        return out
+
+    def fewsites_mode(self, mag_dist, sitecol):
+        """
+        The rule of the reference for few sites (contexts.py:358-362): for
+        each source and magnitude, if some site is within psdist all the
+        sites see all the planes and depths, otherwise all the sites see the
+        average rupture.  Returns the (U,) uint8 visibility of each rupture
+        (0 all sites, 3 none).
+        """
+        from .site import EARTH_RADIUS
+        lon, lat = numpy.radians(self.lon), numpy.radians(self.lat)
+        loc = EARTH_RADIUS * numpy.stack([
+            numpy.cos(lat) * numpy.cos(lon), numpy.cos(lat) * numpy.sin(lon),
+            numpy.sin(lat)], axis=1)                      # (S, 3)
+        xyz = sitecol.xyz                                  # (N, 3)
+        mode = numpy.zeros(self.U, numpy.uint8)
+        psd = self.psdist(mag_dist)
+        for s in range(self.S):
+            B = int(self.block[s])
+            nphc = int(self.cnt['np'][s]) * int(self.cnt['hd'][s])
+            if B == nphc:
+                continue
+            cdist = numpy.sqrt(((xyz - loc[s]) ** 2).sum(axis=1))
+            close = (cdist[None, :] <= psd[s][:, None]).any(axis=1)   # (M,)
+            blk = numpy.zeros((len(close), B), numpy.uint8)
+            blk[close, nphc:] = 3        # something is close: no average
+            blk[~close, :nphc] = 3       # all far: only the average
+            mode[self.rup_off[s]:self.rup_off[s + 1]] = blk.ravel()
+        return mode
+
+    def to_device(self, dev, mag_dist=None, shift_hypo=False, mode=None):
         """:returns: (OqgPointSources struct, list of tensors kept alive)"""
         from .contexts import _dev
         keep = {}
@@ -254,29 +330,44 @@ class PointSourceBatch(object):
         st.mag_dist = up('mag_dist', mag_dist)
         st.msr = self.msr
         st.shift_hypo = int(bool(shift_hypo))
+        st.pointsource_distance = self.pointsource_distance
+        st.mode = up('mode', mode)
         return st, keep
 
 
-def point_ruptures_device(batch, handle, mag_dist=None, shift_hypo=False):
+def point_ruptures_device(batch, handle, mag_dist=None, shift_hypo=False,
+                          mode=None, with_aux=False):
     """
     Build the planar ruptures of a PointSourceBatch on the handle's device:
     returns torch CUDA tensors (planar (U, 42), mag (U,), magdist (U,) or
-    None).  The equivalent of PointSource.get_planar for every source.
+    None) and, if `with_aux` or the batch uses the pointsource_distance
+    approximation, the (U, 5) visibility array for oqg_hazard_planar_aux.
+    The equivalent of PointSource.get_planar (and iruptures) for every
+    source.
     """
     import torch
     dev = handle.device
-    st, keep = batch.to_device(dev, mag_dist, shift_hypo)
+    want_aux = with_aux or batch.pointsource_distance > 0 or mode is not None
+    if batch.pointsource_distance > 0 and mag_dist is None:
+        raise ValueError('pointsource_distance needs the integration '
+                         'distances (mag_dist)')
+    st, keep = batch.to_device(dev, mag_dist, shift_hypo, mode)
     U = batch.U
     cuda = 'cuda:%d' % dev
     t_pla = torch.empty((U, _lib.PLANAR_LEN), dtype=torch.float64, device=cuda)
     t_mag = torch.empty(U, dtype=torch.float64, device=cuda)
     t_md = torch.empty(U, dtype=torch.float64, device=cuda) \
         if mag_dist is not None else None
+    t_aux = torch.empty((U, 5), dtype=torch.float64, device=cuda) \
+        if want_aux else None
     handle.call('oqg_point_ruptures', ctypes.byref(st), batch.S, U,
                 ctypes.c_void_p(t_pla.data_ptr()),
                 ctypes.c_void_p(t_mag.data_ptr()),
-                ctypes.c_void_p(t_md.data_ptr() if t_md is not None else None))
+                ctypes.c_void_p(t_md.data_ptr() if t_md is not None else None),
+                ctypes.c_void_p(t_aux.data_ptr() if want_aux else None))
     # the source arrays must outlive the kernel: the launch is asynchronous
     torch.cuda.current_stream(dev).synchronize()
     del keep
+    if want_aux:
+        return t_pla, t_mag, t_md, t_aux
     return t_pla, t_mag, t_md

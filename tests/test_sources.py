@@ -142,7 +142,7 @@ def test_device_point_ruptures_golden(oq, name):
     h = oq.contexts.get_handle()
     b = oq.PointSourceBatch([as_source(oq, d)])
     md = np.linspace(100., 300., len(b.mag))
-    t_pla, t_mag, t_md = oq.point_ruptures_device(b, h, md, d['shift'])
+    t_pla, t_mag, t_md = oq.point_ruptures_device(b, h, md, d['shift'])[:3]
     pla = t_pla.cpu().numpy()
     want = d['planar'].copy()
     # wlr[2] of the device ruptures is the occurrence rate, of the
@@ -265,3 +265,108 @@ def test_cfg1_area_source_demo(oq):
     big = acc > 1e-10
     np.testing.assert_allclose(rmap.array[big], acc[big], rtol=1e-5)
     np.testing.assert_allclose(rmap.array, acc, rtol=1e-5, atol=1e-10)
+
+
+# ------------------------------------------- pointsource_distance (psdist)
+PSD = np.load(os.path.join(GOLDEN, 'psdist.npz'))
+
+
+def psd_sources(oq):
+    s0 = oq.PointSource(
+        '0', 12.5, 44.1, oq.EvenlyDiscretizedMFD(
+            5.05, 0.3, [0.02, 0.011, 0.006, 0.002, 0.0007, 0.0002, 0.00008,
+                        0.00003, 0.00001]),
+        'WC1994', 2., 0., 12., [(0.3, 30., 30., 90.), (0.5, 140., 60., -90.),
+                                (0.2, 270., 90., 180.)],
+        [(0.4, 2.), (0.6, 11.)])
+    s1 = oq.PointSource(
+        '1', 12.9, 43.8, oq.TruncatedGRMFD(5.0, 7.0, 0.5, 3.2, 0.9), 'WC1994',
+        1., 0., 20., [(0.5, 10., 45., 0.), (0.5, 100., 80., 45.)],
+        [(1., 10.)])
+    return [s0, s1]
+
+
+def test_psdist_host_matches_reference():
+    """PointSource.get_psdist / _get_max_rupture_projection_radius
+    (point.py:215-256) and the rupture counts of the approximation"""
+    import oq_engine_b200 as oq
+    b = oq.PointSourceBatch(psd_sources(oq), float(PSD['psdist']))
+    assert list(b.block) == [3 * 2 + 1, 2 * 1 + 1]
+    assert list(b.rup_off) == [0, 9 * 7, 9 * 7 + 4 * 3]
+    psd = b.psdist(np.full(len(b.mag), float(PSD['maxdist'])))
+    np.testing.assert_allclose(psd[0], PSD['src0_psdist'], rtol=1e-14)
+    np.testing.assert_allclose(psd[1], PSD['src1_psdist'], rtol=1e-14)
+    # rates in device order: the average rupture carries the whole rate
+    mag, rate = b.expand()
+    blk = rate[:63].reshape(9, 7)
+    np.testing.assert_allclose(blk[:, 6], PSD['src0_avg_rate'], rtol=1e-15)
+    np.testing.assert_allclose(blk[:, :6].sum(axis=1), PSD['src0_avg_rate'],
+                               rtol=1e-14)
+    # no approximation: 1000 km (the hazardlib default) or nothing
+    for off in (None, 0, 1000.):
+        assert oq.PointSourceBatch(psd_sources(oq), off).U == 9 * 6 + 4 * 2
+
+
+@pytest.mark.gpu
+def test_psdist_average_ruptures_golden(oq):
+    """the average rupture per magnitude against PointSource.iruptures"""
+    h = oq.contexts.get_handle()
+    for i, src in enumerate(psd_sources(oq)):
+        b = oq.PointSourceBatch([src], float(PSD['psdist']))
+        md = np.full(len(b.mag), float(PSD['maxdist']))
+        t_pla, t_mag, t_md, t_aux = oq.point_ruptures_device(b, h, md)
+        pla, aux = t_pla.cpu().numpy(), t_aux.cpu().numpy()
+        B = int(b.block[0])
+        avg = pla.reshape(-1, B, 42)[:, B - 1]
+        want = PSD['src%d_avg_planar' % i].copy()
+        got_rate, avg[:, 2 * 14 + 11] = avg[:, 2 * 14 + 11].copy(), 0.
+        want[:, 2 * 14 + 11] = 0.
+        np.testing.assert_allclose(avg, want, rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(got_rate, PSD['src%d_avg_rate' % i],
+                                   rtol=1e-15)
+        aux = aux.reshape(-1, B, 5)
+        np.testing.assert_allclose(aux[:, 0, 3], PSD['src%d_psdist' % i],
+                                   rtol=1e-13)
+        assert (aux[:, :B - 1, 4] == 1).all() and (aux[:, B - 1, 4] == 2).all()
+        loc = oq.SiteCollection.from_points([src.lon], [src.lat]).xyz[0]
+        np.testing.assert_allclose(aux[0, 0, :3], loc, rtol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['many', 'few'])
+def test_psdist_hazard_golden(oq, tag):
+    """hazard with pointsource_distance = 30 km against the reference's
+    get_ctxs -> update: many sites (near / far split per site) and few
+    sites (all-or-nothing per magnitude)"""
+    N = len(PSD[tag + '_lon'])
+    sc = oq.SiteCollection.from_points(
+        PSD[tag + '_lon'], PSD[tag + '_lat'], np.zeros(N),
+        dict(vs30=PSD[tag + '_vs30']))
+    imtls = {str(imt): PSD['levels'] for imt in PSD['imts']}
+    cm = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim('BooreEtAl2014'), oq.get_gsim('BooreAtkinson2008')],
+        dict(imtls=imtls, truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('200'),
+             pointsource_distance=dict(default=float(PSD['psdist']))))
+    pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1.)
+    kept = cm.hazard_point_sources(pmap, psd_sources(oq), sc, count=True)
+    assert kept == int(PSD[tag + '_nrows'])
+    poes = (~pmap).array
+    np.testing.assert_allclose(1. - poes, 1. - PSD[tag + '_poes'], rtol=2e-5,
+                               atol=1.5e-7)
+    np.testing.assert_allclose(poes, PSD[tag + '_poes'], atol=1.5e-6)
+    # without the approximation the map is different (and has more rows)
+    cm0 = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim('BooreEtAl2014'), oq.get_gsim('BooreAtkinson2008')],
+        dict(imtls=imtls, truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('200')))
+    pm0 = oq.MapArray(sc.sids, cm0.L, cm0.G).fill(1.)
+    kept0 = cm0.hazard_point_sources(pm0, psd_sources(oq), sc, count=True)
+    if tag == 'many':
+        assert kept0 > kept
+        assert np.abs((~pm0).array - poes).max() > 1e-5
+    else:   # sites on top of both sources: every magnitude keeps all planes
+        assert kept0 == kept
+        np.testing.assert_allclose((~pm0).array, poes, rtol=1e-6, atol=1e-7)
