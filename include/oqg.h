@@ -285,6 +285,24 @@ int oqg_section_min(oqg_handle *h, const double *sec_dev, int S, int N,
                     const int64_t *rup_off_dev, const int32_t *rup_sec_dev,
                     int U, double *out_dev);
 
+/* ---- disaggregation: _disaggregate
+ * (hazardlib/calc/disagg.py:188-243, Poissonian lane) with _disagg_eps
+ * (:246-256), get_eps4 (:176-186) and _build_disagg_matrix (:262-296) for the
+ * U context rows of one site and one magnitude bin and one gsim.
+ *   rrup/clon/clat/rate_dev [U]; mea_dev, std_dev [M][U]
+ *   iml2 [M][P] log intensities (host; -inf = zero hazard, skipped)
+ *   dist/lon/lat edges (host, D + 1, Lo + 1, La + 1 values), eps_edges (host,
+ *   E + 1 <= 33 values); epsstar as in the reference; gp = group probability
+ *   out_dev [D][Lo][La][E][M][P] float64 = 1 - prod pne */
+int oqg_disaggregate(oqg_handle *h, const double *rrup_dev,
+                     const double *clon_dev, const double *clat_dev,
+                     const double *rate_dev, int64_t U, const double *mea_dev,
+                     const double *std_dev, int M, int P, const double *iml2,
+                     const double *dist_edges, int D, const double *lon_edges,
+                     int Lo, const double *lat_edges, int La,
+                     const double *eps_edges, int E, double truncation_level,
+                     double itime, int epsstar, double gp, double *out_dev);
+
 /* ---- post-processing of the rates map -------------------
  * oqg_postclassical replaces, for all the sites at once, the loop of
  * postclassical (calculators/classical.py:258-325): MapGetter.get_hcurve

@@ -427,15 +427,23 @@ class ContextMaker(object):
 
     def get_ctxs(self, src, sitecol, src_id=0, step=1):
         """
-        Context rows of the ruptures of `src` (a PlanarRuptures) on the
-        sites, one recarray per unique magnitude like genctxs_Pp
-        (contexts.py:443-474): rows with rrup >= maximum_distance(mag) are
-        dropped, required distances are clamped by minimum_distance.
+        Context rows of the ruptures of `src` (a PlanarRuptures or a
+        source.PointSource) on the sites, one recarray per unique magnitude
+        like genctxs_Pp (contexts.py:443-474): rows with rrup >=
+        maximum_distance(mag) are dropped, required distances are clamped by
+        minimum_distance.  For a PointSource the ruptures are built on the
+        device and, with a pointsource_distance below 1000 km, the near / far
+        split of _quintets (contexts.py:321-370) selects the rows.
         """
         import torch
+        from .source import PointSource
+        vis = None
+        if isinstance(src, PointSource):
+            src, vis = self._planar_of_point_source(src, sitecol, src_id)
         if not isinstance(src, PlanarRuptures):
             raise NotImplementedError(
-                'only planar ruptures (PlanarRuptures) have a device path')
+                'only planar ruptures (PlanarRuptures, PointSource) have a '
+                'device path')
         h = self.handle()
         U, N = len(src), len(sitecol)
         if U == 0 or N == 0:
@@ -485,7 +493,19 @@ class ContextMaker(object):
             ctx['sids'] = sitecol.sids[None, :]
             if K:
                 ctx['probs_occur'] = probs[idx][:, None, :]
-            ctx = ctx.flatten()
+            if vis is not None and (vis[idx, 4] != 0).any():
+                # near sites see all the planes and depths (mode 1), far
+                # sites the average rupture (mode 2), contexts.py:347-370
+                aux = vis[idx]
+                d2 = ((sitecol.xyz[None, :, :] - aux[:, None, :3]) ** 2
+                      ).sum(axis=2)
+                close = d2 <= (aux[:, 3] ** 2)[:, None]
+                mode = aux[:, 4][:, None]
+                keep = numpy.where(mode == 1, close, numpy.where(
+                    mode == 2, ~close, mode == 0))
+                ctx = ctx[keep]
+            else:
+                ctx = ctx.flatten()
             ctx = ctx[ctx['rrup'] < self.maximum_distance(mag)]
             if len(ctx):
                 ctxs.append(ctx.view(numpy.recarray))
@@ -493,6 +513,25 @@ class ContextMaker(object):
 
     # the name BASELINE.json's north_star uses for the same operator
     get_ctx_iter = get_ctxs
+
+    def _planar_of_point_source(self, src, sitecol, src_id=0):
+        """PlanarRuptures of a PointSource built on the device and the
+        per-rupture visibility (U, 5) of the pointsource_distance
+        approximation (None when it does not apply)"""
+        from .source import PointSourceBatch, point_ruptures_device
+        batch = PointSourceBatch([src], self.pointsource_distance)
+        h = self.handle()
+        mag_dist = self.magdist(batch.mag)
+        mode = None
+        if batch.pointsource_distance > 0 and \
+                len(sitecol) <= self.max_sites_disagg:
+            mode = batch.fewsites_mode(mag_dist, sitecol)
+        t_pla, t_mag, _md, t_aux = point_ruptures_device(
+            batch, h, mag_dist, self.shift_hypo, mode, with_aux=True)
+        pla = t_pla.cpu().numpy().reshape(-1, 3, 14).view(
+            planar_array_dt).reshape(-1, 3)
+        vis = t_aux.cpu().numpy() if batch.pointsource_distance > 0 else None
+        return PlanarRuptures(pla, t_mag.cpu().numpy(), src_id), vis
 
     def _sites_struct(self, sitecol, dev):
         st, keep = _lib.OqgSites(), []

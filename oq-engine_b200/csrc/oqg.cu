@@ -30,6 +30,7 @@
 #include "oqg_fast.cuh"
 #include "oqg_source.cuh"
 #include "oqg_post.cuh"
+#include "oqg_disagg.cuh"
 
 using namespace oqg;
 
@@ -1156,6 +1157,79 @@ int oqg_section_min(oqg_handle *h, const double *sec, int S, int N,
   if (U > 65535) return fail(h, "section_min: at most 65535 ruptures per call");
   dim3 grid((N + 127) / 128, U);
   k_section_min<<<grid, 128, 0, h->stream>>>(sec, N, rup_off, rup_sec, U, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_disaggregate(oqg_handle *h, const double *rrup, const double *clon,
+                     const double *clat, const double *rate, int64_t U,
+                     const double *mea, const double *std, int M, int P,
+                     const double *iml2, const double *dist_edges, int D,
+                     const double *lon_edges, int Lo, const double *lat_edges,
+                     int La, const double *eps_edges, int E,
+                     double truncation_level, double itime, int epsstar,
+                     double gp, double *out) {
+  CK(cudaSetDevice(h->device));
+  if (M < 1 || P < 1 || D < 1 || Lo < 1 || La < 1 || E < 1)
+    return fail(h, "disaggregate: bad shape");
+  if (E > OQG_DISAGG_EMAX) return fail(h, "disaggregate: at most 32 epsilon bins");
+  if (M * P > 4096) return fail(h, "disaggregate: M * P too large");
+  if (!out || !iml2 || !dist_edges || !lon_edges || !lat_edges || !eps_edges)
+    return fail(h, "disaggregate: missing array");
+  const int64_t n = (int64_t)D * Lo * La * E * M * P;
+  CK(cudaMemsetAsync(out, 0, (size_t)n * 8, h->stream));
+  if (U > 0) {
+    if (!rrup || !clon || !clat || !rate || !mea || !std)
+      return fail(h, "disaggregate: missing column");
+    // small host tables -> one staging buffer
+    size_t nd = (size_t)M * P + D + 1 + Lo + 1 + La + 1;
+    if (reserve(h, h->stage[8], nd * 8)) return 1;
+    std::vector<double> tab;
+    tab.insert(tab.end(), iml2, iml2 + (size_t)M * P);
+    tab.insert(tab.end(), dist_edges, dist_edges + D + 1);
+    tab.insert(tab.end(), lon_edges, lon_edges + Lo + 1);
+    tab.insert(tab.end(), lat_edges, lat_edges + La + 1);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->stage[8].p, tab.data(), nd * 8, cudaMemcpyHostToDevice));
+    DisaggArgs A;
+    memset(&A, 0, sizeof(A));
+    A.rrup = rrup; A.clon = clon; A.clat = clat; A.rate = rate;
+    A.mea = mea; A.std = std;
+    A.iml2 = (const double *)h->stage[8].p;
+    A.dist_edges = A.iml2 + (size_t)M * P;
+    A.lon_edges = A.dist_edges + D + 1;
+    A.lat_edges = A.lon_edges + Lo + 1;
+    A.U = U; A.M = M; A.P = P; A.D = D; A.Lo = Lo; A.La = La; A.E = E;
+    // cross_idl, geo/utils.py:802-827
+    A.lon_idl = lon_edges[0] * lon_edges[Lo] < 0 &&
+                fabs(lon_edges[0] - lon_edges[Lo]) > 180;
+    A.epsstar = epsstar; A.gp = gp; A.itime = itime;
+    A.phi_b = 0.5 * (1.0 + erf(truncation_level * sqrt(0.5)));
+    A.inv_norm = 1. / (2. * A.phi_b - 1.);
+    // get_eps4, disagg.py:176-186: scipy.stats.truncnorm(-tl, tl).cdf
+    auto cdf = [&](double x) {
+      double c = (0.5 * (1.0 + erf(x * sqrt(0.5))) - (1. - A.phi_b)) * A.inv_norm;
+      return c < 0. ? 0. : (c > 1. ? 1. : c);
+    };
+    A.min_eps = eps_edges[0]; A.max_eps = eps_edges[0];
+    for (int e = 0; e <= E; e++) {
+      A.eps_edges[e] = eps_edges[e];
+      A.min_eps = std::min(A.min_eps, eps_edges[e]);
+      A.max_eps = std::max(A.max_eps, eps_edges[e]);
+    }
+    for (int e = 0; e < E; e++) A.bands[e] = cdf(eps_edges[e + 1]) - cdf(eps_edges[e]);
+    for (int e = 0; e <= E; e++) {
+      double c = 0.;
+      for (int k = e; k < E; k++) c += A.bands[k];
+      A.cum[e] = c;
+    }
+    A.acc = out;
+    int64_t nt = U * M * P;
+    k_disagg_accumulate<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(A);
+    h->launches++;
+  }
+  k_disagg_finalize<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(out, n);
   h->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -1,0 +1,90 @@
+"""
+Golden fixture for the disaggregation kernel:
+the reference's `_disaggregate` ("the crucial bit for performance",
+openquake/hazardlib/calc/disagg.py:188-243) with `_disagg_eps` (:246-256),
+`get_eps4` (:176-186) and `_build_disagg_matrix` (:262-296), run in this
+container on synthetic rows of one site and one magnitude bin; the numpy
+oracle (oracle/disagg_np.py) is pinned against it in the same run.
+
+    python oracle/make_golden_disagg.py   -> tests/golden/disagg.npz
+"""
+import os
+import sys
+import types
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'refshim'))
+sys.path.insert(0, HERE)
+import oq_bootstrap  # noqa
+oq_bootstrap.install()
+
+from openquake.baselib.performance import Monitor  # noqa
+from openquake.hazardlib.calc import disagg  # noqa
+from openquake.hazardlib.stats import ndtr  # noqa
+import disagg_np  # noqa
+
+GOLDEN = os.path.join(HERE, '..', 'tests', 'golden')
+
+
+def main():
+    rng = np.random.default_rng(21)
+    U, G, M, P = 500, 2, 3, 2
+    tl = 3.
+    dt = [('rrup', float), ('clon', float), ('clat', float),
+          ('occurrence_rate', float), ('probs_occur', float, (0,))]
+    ctx = np.zeros(U, dt).view(np.recarray)
+    ctx.rrup = rng.uniform(0, 210, U)       # some beyond the last edge
+    ctx.rrup[:3] = [0., 200., 40.]          # on the edges
+    ctx.clon = 179.6 + rng.uniform(-1.5, 1.5, U)   # across the date line
+    ctx.clon = np.where(ctx.clon > 180, ctx.clon - 360, ctx.clon)
+    ctx.clat = 10. + rng.uniform(-1.2, 1.2, U)
+    ctx.occurrence_rate = 10 ** rng.uniform(-5, -2, U)
+    mea = rng.uniform(-5, -1, (G, M, U))
+    std = rng.uniform(0.4, 0.9, (G, M, U))
+    iml2 = np.log(np.array([[0.05, 0.3], [0.1, 0.5], [0.02, 0.2]]))
+    iml2[2, 1] = -np.inf                     # zero hazard: skipped
+    dist_edges = np.arange(0, 201, 20.)
+    lon_edges = np.array([178.0, 178.8, 179.6, -179.6, -178.8, -178.0])
+    lat_edges = np.arange(8.5, 11.6, 0.5)
+    eps_edges = np.linspace(-tl, tl, 7)
+    bin_edges = [np.array([5., 6.]), dist_edges, lon_edges, lat_edges,
+                 eps_edges]
+    cm = types.SimpleNamespace(phi_b=ndtr(tl), investigation_time=50.)
+    eps4 = disagg.get_eps4(tuple(eps_edges), tl)
+    mon = Monitor('x')
+    out = dict(rrup=ctx.rrup, clon=ctx.clon, clat=ctx.clat,
+               rate=ctx.occurrence_rate, mea=mea, std=std, iml2=iml2,
+               dist_edges=dist_edges, lon_edges=lon_edges,
+               lat_edges=lat_edges, eps_edges=eps_edges, tl=tl, itime=50.,
+               eps_bands=eps4[2], eps_cum=eps4[3])
+    for epsstar in (False, True):
+        for g, gp in ((0, 1.), (1, 0.8)):
+            mat = disagg._disaggregate(ctx, mea, std, cm, g, iml2, bin_edges,
+                                       eps4, epsstar, gp, False, mon, mon, mon)
+            mine = disagg_np.disaggregate(
+                ctx.rrup, ctx.clon, ctx.clat, ctx.occurrence_rate, mea[g],
+                std[g], iml2, dist_edges, lon_edges, lat_edges, eps_edges, tl,
+                50., epsstar, gp)
+            np.testing.assert_allclose(mine, mat, rtol=1e-12, atol=1e-15)
+            out['mat_%d_%d' % (epsstar, g)] = mat
+            print('epsstar=%s g=%d' % (epsstar, g), mat.shape, mat.max(),
+                  (mat > 0).mean())
+    # a lon grid that does not cross the date line (numpy.digitize branch)
+    lon2 = np.arange(-181.2, -177.9, 0.8)
+    ctx2 = ctx.copy()
+    ctx2.clon = np.where(ctx.clon > 0, ctx.clon - 360, ctx.clon)
+    be2 = [bin_edges[0], dist_edges, lon2, lat_edges, eps_edges]
+    mat = disagg._disaggregate(ctx2, mea, std, cm, 0, iml2, be2, eps4, False,
+                               1., False, mon, mon, mon)
+    mine = disagg_np.disaggregate(
+        ctx2.rrup, ctx2.clon, ctx2.clat, ctx2.occurrence_rate, mea[0], std[0],
+        iml2, dist_edges, lon2, lat_edges, eps_edges, tl, 50., False, 1.)
+    np.testing.assert_allclose(mine, mat, rtol=1e-12, atol=1e-15)
+    out['lon_edges2'], out['clon2'], out['mat_nodl'] = lon2, ctx2.clon, mat
+    np.savez_compressed(os.path.join(GOLDEN, 'disagg.npz'), **out)
+    print('disagg.npz written; oracle == reference')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,106 @@
+"""Disaggregation hot function: the oracle
+(oracle/disagg_np.py) and, on the GPU, oqg_disaggregate against the
+reference's own _disaggregate (oracle/make_golden_disagg.py): both epsilon
+modes, a group probability, lon bins across the date line, rows on and
+beyond the bin edges, a zero-hazard level.  Tolerance rtol 1e-10, atol 1e-14
+(float64 throughout; the product of the reference is a sum of logarithms on
+the device, in a non-deterministic order)."""
+import os
+import types
+import numpy as np
+import pytest
+
+import disagg_np
+from helpers import GOLDEN
+
+D = np.load(os.path.join(GOLDEN, 'disagg.npz'))
+
+
+def edges(lon='lon_edges'):
+    return [np.array([5., 6.]), D['dist_edges'], D[lon], D['lat_edges'],
+            D['eps_edges']]
+
+
+@pytest.mark.parametrize('epsstar,g,gp', [(0, 0, 1.), (0, 1, .8), (1, 0, 1.),
+                                          (1, 1, .8)])
+def test_oracle_golden(epsstar, g, gp):
+    mine = disagg_np.disaggregate(
+        D['rrup'], D['clon'], D['clat'], D['rate'], D['mea'][g], D['std'][g],
+        D['iml2'], D['dist_edges'], D['lon_edges'], D['lat_edges'],
+        D['eps_edges'], float(D['tl']), float(D['itime']), bool(epsstar), gp)
+    np.testing.assert_allclose(mine, D['mat_%d_%d' % (epsstar, g)],
+                               rtol=1e-12, atol=1e-15)
+
+
+def test_oracle_eps4():
+    _, _, bands, cum = disagg_np.eps4(D['eps_edges'], float(D['tl']))
+    np.testing.assert_allclose(bands, D['eps_bands'], rtol=1e-13)
+    np.testing.assert_allclose(cum, D['eps_cum'], rtol=1e-13)
+    assert abs(bands.sum() - 1) < 1e-12
+
+
+@pytest.fixture(scope='module')
+def oq():
+    import oq_engine_b200
+    oq_engine_b200._lib.lib()
+    return oq_engine_b200
+
+
+def ctx_of(clon='clon'):
+    return types.SimpleNamespace(
+        rrup=D['rrup'], clon=D[clon], clat=D['clat'],
+        occurrence_rate=D['rate'], probs_occur=np.zeros((len(D['rrup']), 0)),
+        __len__=None)
+
+
+class Ctx(object):
+    def __init__(self, clon='clon', n=None):
+        sl = slice(0, n)
+        self.rrup, self.clon, self.clat = (D['rrup'][sl], D[clon][sl],
+                                           D['clat'][sl])
+        self.occurrence_rate = D['rate'][sl]
+        self.probs_occur = np.zeros((len(self.rrup), 0))
+
+    def __len__(self):
+        return len(self.rrup)
+
+
+CM = types.SimpleNamespace(truncation_level=3., investigation_time=50.,
+                           device=None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('epsstar,g,gp', [(0, 0, 1.), (0, 1, .8), (1, 0, 1.),
+                                          (1, 1, .8)])
+def test_disaggregate_golden(oq, epsstar, g, gp):
+    got = oq.disaggregate(Ctx(), D['mea'], D['std'], CM, g, D['iml2'],
+                          edges(), bool(epsstar), gp)
+    want = D['mat_%d_%d' % (epsstar, g)]
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-14)
+    assert (got[..., 2, 1] == 0).all()        # the zero-hazard level
+
+
+@pytest.mark.gpu
+def test_disaggregate_no_date_line_and_edge_cases(oq):
+    got = oq.disaggregate(Ctx('clon2'), D['mea'], D['std'], CM, 0, D['iml2'],
+                          edges('lon_edges2'))
+    np.testing.assert_allclose(got, D['mat_nodl'], rtol=1e-10, atol=1e-14)
+    # no rows: a matrix of zeros
+    empty = oq.disaggregate(Ctx(n=0), D['mea'][:, :, :0], D['std'][:, :, :0],
+                            CM, 0, D['iml2'], edges())
+    assert empty.shape == D['mat_0_0'].shape and (empty == 0).all()
+    # a subset of the rows against the oracle
+    n = 37
+    sub = oq.disaggregate(Ctx(n=n), D['mea'][:, :, :n], D['std'][:, :, :n],
+                          CM, 1, D['iml2'], edges(), False, 0.5)
+    mine = disagg_np.disaggregate(
+        D['rrup'][:n], D['clon'][:n], D['clat'][:n], D['rate'][:n],
+        D['mea'][1][:, :n], D['std'][1][:, :n], D['iml2'], D['dist_edges'],
+        D['lon_edges'], D['lat_edges'], D['eps_edges'], 3., 50., False, 0.5)
+    np.testing.assert_allclose(sub, mine, rtol=1e-10, atol=1e-14)
+    # non-Poissonian rows: no device path
+    bad = Ctx()
+    bad.probs_occur = np.ones((len(bad), 3))
+    with pytest.raises(NotImplementedError):
+        oq.disaggregate(bad, D['mea'], D['std'], CM, 0, D['iml2'], edges())

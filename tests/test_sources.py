@@ -370,3 +370,42 @@ def test_psdist_hazard_golden(oq, tag):
     else:   # sites on top of both sources: every magnitude keeps all planes
         assert kept0 == kept
         np.testing.assert_allclose((~pm0).array, poes, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['many', 'few'])
+def test_get_ctxs_of_point_sources(oq, tag):
+    """the unfused operator on PointSource objects: get_ctxs yields the same
+    rows as the reference (count) and get_pmap the same map as the fused
+    pass, with the pointsource_distance split"""
+    N = len(PSD[tag + '_lon'])
+    sc = oq.SiteCollection.from_points(
+        PSD[tag + '_lon'], PSD[tag + '_lat'], np.zeros(N),
+        dict(vs30=PSD[tag + '_vs30']))
+    imtls = {str(imt): PSD['levels'] for imt in PSD['imts']}
+    cm = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim('BooreEtAl2014'), oq.get_gsim('BooreAtkinson2008')],
+        dict(imtls=imtls, truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('200'),
+             pointsource_distance=float(PSD['psdist'])))
+    ctxs = []
+    for i, src in enumerate(psd_sources(oq)):
+        got = cm.get_ctx_iter(src, sc, src_id=i)
+        assert all(len(np.unique(c.mag)) == 1 for c in got)
+        ctxs.extend(got)
+    ctx = cm.recarray(ctxs)
+    assert len(ctx) == int(PSD[tag + '_nrows'])
+    pmap = cm.get_pmap(ctx, oq.PoissonTOM(50.))
+    np.testing.assert_allclose(1. - pmap.array, 1. - PSD[tag + '_poes'],
+                               rtol=2e-5, atol=1.5e-7)
+    # a rupture is seen either by the near or by the far sites, never both
+    if tag == 'many':
+        rates = {}
+        for c in ctxs:
+            for sid in np.unique(c.sids):
+                tot = c.occurrence_rate[c.sids == sid].sum()
+                rates.setdefault((int(c.src_id[0]), float(c.mag[0])), set()
+                                 ).add(round(float(tot), 14))
+        # every site sees the same total rate per (source, magnitude)
+        assert all(len(v) == 1 for v in rates.values()), rates
