@@ -444,6 +444,9 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 // different banks.
 #define PT_DEG 3
 #define PT_STRIDE 4       // floats per node: one LDS.128
+#ifndef PT_SOA
+#define PT_SOA 0
+#endif
 #ifndef PT_REP
 #define PT_REP 1          // copies of the table in shared memory (copy r of
                           // node k at float4 index k * PT_REP + r, lane i
@@ -498,10 +501,21 @@ __device__ __forceinline__ float poe_table(unsigned tab32, float nm1,
   float x = __saturatef((float)x64);    // NaN -> 0 -> poe 0
   float y = fmaf(x, nm1, 8388608.f);    // 2^23: round to nearest integer
   float u = fmaf(x, nm1, -(y - 8388608.f));
-  unsigned a = tab32 + __float_as_uint(y) * (PT_STRIDE * 4 * PT_REP);
   float c0, c1, c2, c3;
+#if PT_SOA
+  // experiment (default off): one array per coefficient, [4][PT_MAXNODES],
+  // four LDS.32 instead of one LDS.128.  Measured slower on B200 (cfg3, 30k
+  // ruptures: BSSA14 51.8 vs 48.9 ms, CY14 74.3 vs 71.5 ms)
+  unsigned a = tab32 + __float_as_uint(y) * 4;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(c0) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+2048];" : "=f"(c1) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+4096];" : "=f"(c2) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+6144];" : "=f"(c3) : "r"(a));
+#else
+  unsigned a = tab32 + __float_as_uint(y) * (PT_STRIDE * 4 * PT_REP);
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
       : "=f"(c0), "=f"(c1), "=f"(c2), "=f"(c3) : "r"(a));
+#endif
   float p = fmaf(c3, u, c2);
   p = fmaf(p, u, c1);
   return __saturatef(fmaf(p, u, c0));
@@ -536,7 +550,7 @@ k_fused(const FusedArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int nw = blockDim.x >> 5;
   float *s_tab = (float *)smem;           // [nodes][PT_REP][PT_STRIDE]
-  double *s_rup = smem + (FAST ? A.pt_nodes * PT_REP * PT_STRIDE / 2 : 0);  // [NF_RUP][RT]
+  double *s_rup = smem + (FAST ? (PT_SOA ? PT_MAXNODES : A.pt_nodes * PT_REP) * PT_STRIDE / 2 : 0);  // [NF_RUP][RT]
   double *s_dist = s_rup + NF_RUP * RT;            // [nplanes][RT][32]
   double *s_site = s_dist + A.nplanes * RT * 32;   // [NF_SITE][32]
   double *s_q = s_site + NF_SITE * 32;             // [nw + 1][RT][QW]
@@ -563,15 +577,20 @@ k_fused(const FusedArgs A) {
     s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
   }
   if (FAST)
+#if PT_SOA
+    for (int i = threadIdx.x; i < A.pt_nodes * PT_STRIDE; i += blockDim.x)
+      s_tab[(i & 3) * PT_MAXNODES + (i >> 2)] = A.ptab[i];
+#else
     for (int i = threadIdx.x; i < A.pt_nodes * PT_REP; i += blockDim.x)
       reinterpret_cast<float4 *>(s_tab)[i] =
           reinterpret_cast<const float4 *>(A.ptab)[i / PT_REP];
+#endif
   math_tables_init();   // log / exp tables of oqg_math.cuh
   // pt_bias = -(0x4b000000 * 16 * PT_REP) mod 2^32 comes in as a kernel argument: as
   // a literal the compiler splits it off again and adds it back before
   // every load
   const unsigned tab32 = (unsigned)__cvta_generic_to_shared(s_tab) + A.pt_bias +
-                         (threadIdx.x & (PT_REP - 1)) * (PT_STRIDE * 4);
+                         (PT_SOA ? 0 : (threadIdx.x & (PT_REP - 1)) * (PT_STRIDE * 4));
   const float nm1 = (float)(A.pt_nodes - 1);
   SiteIn si;
   si.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
@@ -1583,7 +1602,7 @@ static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
   size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
                  NF_SITE * 32 + (size_t)(nw + 1) * RT * QW +
                  (size_t)PW * RT * 32 + (A.K ? RT * A.K : 0)) * 8 +
-                (fast ? A.pt_nodes * PT_REP * PT_STRIDE * 4 : 0) + RT * 4 +
+                (fast ? (PT_SOA ? PT_MAXNODES : A.pt_nodes * PT_REP) * PT_STRIDE * 4 : 0) + RT * 4 +
                 (fast ? (size_t)(NL - NLR) * threads * 4 : 0);
   if (A.K) return launch_fused2<F, true, false>(A, grid, threads, smem, st);
   if (fast) return launch_fused2<F, false, true>(A, grid, threads, smem, st);
@@ -1635,7 +1654,7 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   A.tl = h->truncation_level; A.xscale = h->xscale;
   A.pt_nodes = h->pt_nodes;
   A.sorted = h->sorted;
-  A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_STRIDE * 4 * PT_REP);
+  A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_SOA ? 4 : PT_STRIDE * 4 * PT_REP);
   A.mindist = mindist; A.itime = itime; A.phi_b = h->phi_b;
   A.inv_norm = 1. / (h->phi_b * 2. - 1.);
 
