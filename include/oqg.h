@@ -56,7 +56,12 @@ enum {
 /* distance metrics: bit positions for masks and order of output planes */
 enum {
   OQG_RRUP = 0, OQG_RJB = 1, OQG_RX = 2, OQG_RY0 = 3, OQG_REPI = 4,
-  OQG_RHYPO = 5, OQG_AZIMUTH = 6, OQG_NDIST = 7
+  OQG_RHYPO = 5, OQG_AZIMUTH = 6, OQG_NDIST = 7,
+  /* outputs of oqg_distances only: longitude and latitude (degrees) of the
+   * point of the rupture closest to the site, project_back
+   * (geo/surface/planar.py:407-424), the clon / clat columns of the context
+   * rows when there are few sites (contexts.py:385-386, 425-427) */
+  OQG_CLON = 7, OQG_CLAT = 8, OQG_NOUT = 9
 };
 
 #define OQG_KMAX 56       /* doubles per coefficient row */

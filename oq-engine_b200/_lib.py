@@ -11,7 +11,8 @@ KMAX = 56
 PLANAR_LEN = 42
 FAMILIES = {'BSSA14': 0, 'CY14': 1, 'ASK14': 2, 'CB14': 3, 'BA08': 4,
             'AB06': 5, 'AKKAR14': 6}
-DIST = ['rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth']
+DIST = ['rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth', 'clon',
+        'clat']
 
 c_double_p = C.POINTER(C.c_double)
 c_void = C.c_void_p

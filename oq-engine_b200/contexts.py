@@ -408,9 +408,15 @@ class ContextMaker(object):
         self._structs = _gsim_structs(self.gsims, self.imts)
 
     # --------------------------------------------------------------- ctxs
+    fewsites = False
+
     def ctx_dtype(self, K=0):
-        """The dtype of the context rows (contexts.py:660-678)"""
+        """The dtype of the context rows (contexts.py:660-678); with few
+        sites the closest points clon, clat are added (contexts.py:385-386,
+        425-427)"""
         dists = self.REQUIRES_DISTANCES | {'rrup'}
+        if self.fewsites:
+            dists = dists | {'clon', 'clat'}
         fields = []
         for name in sorted(self.REQUIRES_RUPTURE_PARAMETERS):
             fields.append((name, float))
@@ -448,7 +454,10 @@ class ContextMaker(object):
         U, N = len(src), len(sitecol)
         if U == 0 or N == 0:
             return []
-        dists = sorted(self.REQUIRES_DISTANCES | {'rrup'})
+        # contexts.py:1064: few sites -> closest points in the rows
+        self.fewsites = N <= self.max_sites_disagg
+        dists = sorted(self.REQUIRES_DISTANCES | {'rrup'} |
+                       ({'clon', 'clat'} if self.fewsites else set()))
         mask = 0
         for d in dists:
             mask |= 1 << _lib.DIST.index(d)

@@ -275,11 +275,11 @@ __global__ void k_distances(const double *__restrict__ rup, int U,
   for (int u = blockIdx.y; u < U; u += gridDim.y) {
     Dist d;
     pair_distances(rup + u, U, sx, sq, sdep, mask, d);
-    const double vals[OQG_NDIST] = {d.rrup, d.rjb, d.rx, d.ry0, d.repi,
-                                    d.rhypo, d.azimuth};
+    const double vals[OQG_NOUT] = {d.rrup, d.rjb, d.rx, d.ry0, d.repi,
+                                   d.rhypo, d.azimuth, d.clon, d.clat};
     int plane = 0;
 #pragma unroll
-    for (int k = 0; k < OQG_NDIST; k++)
+    for (int k = 0; k < OQG_NOUT; k++)
       if (mask & (1 << k)) {
         out[((int64_t)plane * U + u) * N + n] = vals[k];
         plane++;
@@ -1404,7 +1404,7 @@ int oqg_distances(oqg_handle *h, const double *planar, int U,
                   const oqg_sites *sites, int N, int mask, double *out) {
   CK(cudaSetDevice(h->device));
   if (U <= 0 || N <= 0) return 0;
-  if (mask <= 0 || mask >= (1 << OQG_NDIST)) return fail(h, "bad distance mask");
+  if (mask <= 0 || mask >= (1 << OQG_NOUT)) return fail(h, "bad distance mask");
   // mag is not used by the distances: pass the planar pointer as a dummy
   if (reserve(h, h->stage[11], (size_t)U * 8)) return 1;
   CK(cudaMemsetAsync(h->stage[11].p, 0, (size_t)U * 8, h->stream));

@@ -58,7 +58,7 @@ enum {
 };
 
 struct Dist {
-  double rrup, rjb, rx, ry0, repi, rhypo, azimuth;
+  double rrup, rjb, rx, ry0, repi, rhypo, azimuth, clon, clat;
 };
 
 __device__ __forceinline__ void unit_from_lonlat(double lon_deg, double lat_deg,
@@ -185,6 +185,17 @@ __device__ __forceinline__ void pair_distances(RupPtr rup, int rs,
     double mxx = xx < 0. ? xx : (xx > len ? xx - len : 0.);
     double myy = yy < 0. ? yy : (yy > wid ? yy - wid : 0.);
     d.rrup = sqrt(dn * dn + mxx * mxx + myy * myy);
+    if (mask & ((1 << OQG_CLON) | (1 << OQG_CLAT))) {
+      // project_back planar.py:407-424: the closest point of the rupture
+      // plane, back to spherical coordinates (geo/utils.py:689-707)
+      const double cx = fmin(fmax(xx, 0.), len), cy = fmin(fmax(yy, 0.), wid);
+      const double p0 = RUP(RF_TL) + RUP(RF_UV1) * cx + RUP(RF_UV2) * cy,
+                   p1 = RUP(RF_TL + 1) + RUP(RF_UV1 + 1) * cx + RUP(RF_UV2 + 1) * cy,
+                   p2 = RUP(RF_TL + 2) + RUP(RF_UV1 + 2) * cx + RUP(RF_UV2 + 2) * cy;
+      const double rr = sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+      d.clon = atan2(p1, p0) * OQG_R2D;
+      d.clat = asin(fmin(fmax(p2 / rr, -1.), 1.)) * OQG_R2D;
+    }
   }
   if (mask & ((1 << OQG_RJB) | (1 << OQG_RX) | (1 << OQG_RY0))) {
     // signed sines of the four cross-track angles

@@ -277,6 +277,22 @@ def get_azimuth(planar, points):
     return (-np.degrees(tc) - planar['sdr'][:, 0, None]) % 360
 
 
+def project_back(planar, points):
+    """planar.py:407-424: the point of each rupture plane closest to each
+    site as (lon, lat, depth), each (U, N)"""
+    _, xx, yy = project(planar, points)
+    width, length = planar['wlr'][:, None, 0], planar['wlr'][:, None, 1]
+    mxx, myy = np.clip(xx, 0., length), np.clip(yy, 0., width)
+    xyz = (planar['xyz'][:, None, :, 0] + planar['uv1'][:, None, :] *
+           mxx[..., None] + planar['uv2'][:, None, :] * myy[..., None])
+    rr = np.sqrt((xyz * xyz).sum(axis=-1))
+    lon = np.degrees(np.arctan2(xyz[..., 1], xyz[..., 0]))
+    lat = np.degrees(np.arcsin(np.clip(xyz[..., 2] / rr, -1., 1.)))
+    return lon, lat, EARTH_RADIUS - rr
+
+
 DIST = {'rjb': get_rjb, 'rx': get_rx, 'ry0': get_ry0, 'repi': get_repi,
         'rhypo': get_rhypo, 'azimuth': get_azimuth,
-        'rrup': lambda p, x: project(p, x)[0]}
+        'rrup': lambda p, x: project(p, x)[0],
+        'clon': lambda p, x: project_back(p, x)[0],
+        'clat': lambda p, x: project_back(p, x)[1]}

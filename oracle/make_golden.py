@@ -244,6 +244,9 @@ def make_planar():
     dists['rrup'] = P.project(ref, sc.xyz)[0]
     for name in ('rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth'):
         dists[name] = P.get_distances_planar(ref, sc, name)
+    _rrup, xx, yy = P.project(ref, sc.xyz)
+    closest = P.project_back(ref, xx, yy)        # (3, U, N)
+    dists['clon'], dists['clat'] = closest[0], closest[1]
     for name, d in dists.items():
         m = geo_np.DIST[name](mine, sc.xyz)
         np.testing.assert_allclose(m, d, rtol=1e-11, atol=1e-9, err_msg=name)

@@ -131,18 +131,46 @@ def test_distances_c_abi_all_metrics(oq):
         t = torch.from_numpy(np.ascontiguousarray(s[name])).to(dev)
         keep.append(t)
         setattr(st, name, t.data_ptr())
-    out = torch.empty((7, U, N), dtype=torch.float64, device=dev)
+    out = torch.empty((9, U, N), dtype=torch.float64, device=dev)
     h.call('oqg_distances', ctypes.c_void_p(t_pla.data_ptr()), U,
-           ctypes.byref(st), N, 0x7f, ctypes.c_void_p(out.data_ptr()))
+           ctypes.byref(st), N, 0x1ff, ctypes.c_void_p(out.data_ptr()))
     out = out.cpu().numpy()
     for k, name in enumerate(oq._lib.DIST):
         exp = d['dist_' + name]
         if name == 'azimuth':   # circular quantity
             diff = np.abs((out[k] - exp + 180) % 360 - 180)
             assert diff.max() < 1e-6, diff.max()
+        elif name in ('clon', 'clat'):   # degrees: 1e-10 deg = 1e-8 km
+            np.testing.assert_allclose(out[k], exp, rtol=0, atol=1e-10,
+                                       err_msg=name)
         else:
             np.testing.assert_allclose(out[k], exp, rtol=1e-9, atol=1e-8,
                                        err_msg=name)
+
+
+def test_few_sites_rows_carry_the_closest_points(oq):
+    """contexts.py:385-386, 425-427: with at most max_sites_disagg sites
+    the context rows have the clon / clat columns (project_back)"""
+    d = load('planar')
+    r, pla = planar_of(oq, d)
+    s = sites_of(d)
+    few = {k: v[:6] for k, v in s.items()}
+    sc = oq.SiteCollection.from_points(few['lon'], few['lat'], few['depth'],
+                                       few)
+    cm = oq.ContextMaker('*', [oq.BooreEtAl2014()], dict(imtls={'PGA': [0.1]}))
+    ctx = cm.recarray(cm.get_ctxs(oq.contexts.PlanarRuptures(pla, r['mag']),
+                                  sc))
+    assert cm.fewsites and {'clon', 'clat'} <= set(ctx.dtype.names)
+    for name in ('clon', 'clat', 'rrup', 'rjb'):
+        got = np.zeros((len(r['mag']), 6))
+        got[ctx.rup_id, ctx.sids] = ctx[name]
+        np.testing.assert_allclose(got, d['dist_' + name][:, :6], rtol=1e-9,
+                                   atol=1e-8, err_msg=name)
+    # many sites: no such columns
+    many = sitecol_of(oq, d)
+    ctx = cm.recarray(cm.get_ctxs(oq.contexts.PlanarRuptures(pla, r['mag']),
+                                  many))
+    assert not cm.fewsites and 'clon' not in ctx.dtype.names
 
 
 def test_distances_random_vs_oracle(oq):

@@ -88,7 +88,8 @@ def test_planar_golden():
         np.testing.assert_allclose(pla[f], d['planar_' + f], rtol=0,
                                    atol=1e-10, err_msg=f)
     xyz = hazard_np.site_xyz(sites_of(d))
-    for name in ('rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth'):
+    for name in ('rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth',
+                 'clon', 'clat'):
         np.testing.assert_allclose(geo_np.DIST[name](pla, xyz),
                                    d['dist_' + name], rtol=1e-11, atol=1e-9,
                                    err_msg=name)
