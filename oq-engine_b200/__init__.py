@@ -23,7 +23,7 @@ from .postproc import (  # noqa
     postclassical, compute_hazard_maps, compute_hmaps)
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import Mesh, mesh_min_distance, section_min  # noqa
-from .disagg import disaggregate  # noqa
+from .disagg import disaggregate, Disaggregator, FarAwayRupture  # noqa
 from . import sharding  # noqa
 
 __version__ = '0.1.0'

@@ -55,3 +55,120 @@ def disaggregate(ctx, mea, std, cmaker, g, iml2, bin_edges, epsstar=False,
            float(cmaker.truncation_level), float(cmaker.investigation_time),
            int(bool(epsstar)), float(gp), _ptr(out))
     return out.cpu().numpy()
+
+
+# ------------------------------------------------------------ Disaggregator
+class FarAwayRupture(Exception):
+    """Raised if no rupture affects the site (contexts.py:277-278)"""
+
+
+def to_rates(probs, itime=1., minrate=0.):
+    # hazardlib/calc/mean_rates.py:28-41
+    pnes = 1. - numpy.asarray(probs, float)
+    pnes[pnes == 0] = 1E-45
+    rates = - numpy.log(pnes) / itime
+    rates[rates < 1E-12] = minrate
+    rates[rates > 100.] = 100.
+    return rates
+
+
+def split_by_magbin(ctxt, mag_edges):
+    """disagg.py:339-350: magnitude bin -> context rows"""
+    ctx = ctxt[numpy.argsort(ctxt.mag)]
+    fullmagi = numpy.searchsorted(mag_edges, ctx.mag) - 1
+    fullmagi[fullmagi == -1] = 0  # magnitude on the edge
+    return {magi: ctx[fullmagi == magi] for magi in numpy.unique(fullmagi)}
+
+
+class Disaggregator(object):
+    """
+    Single-site disaggregation, mirroring the reference's driver
+    (openquake/hazardlib/calc/disagg.py:353-538) for independent sources:
+    `.init(magi)` selects the rows of a magnitude bin and evaluates mean and
+    standard deviations with `cmaker.get_mean_stds`, `._disagg6D(imldic, g)`
+    returns the (D, Lo, La, E, M, P) matrix of rates of gsim `g` through
+    `disaggregate` (oqg_disaggregate), `.disagg_mag_dist_eps(imldic,
+    rlz_weights)` the (Ma, D, E, M) matrix of rates weighted over the
+    realizations.
+
+    :param ctxs: context rows (a recarray or a list of them) with the clon,
+        clat columns (few sites: ContextMaker.get_ctxs adds them)
+    :param sitecol: a site collection of length 1
+    :param bin_edges: [mag, dist, lon, lat, eps] edges; lon and lat may be
+        dictionaries by site ID as in the reference
+    :param rlzs_by_g: for each gsim of the cmaker the realizations using it
+        (the reference keeps them as the values of cmaker.gsims)
+    """
+    def __init__(self, ctxs, sitecol, cmaker, bin_edges, rlzs_by_g,
+                 epsstar=False):
+        assert len(sitecol) == 1, sitecol
+        self.sitecol = sitecol
+        self.sid = sid = int(sitecol.sids[0])
+        self.cmaker = cmaker
+        self.epsstar = epsstar
+
+        def of_site(e):
+            return e[sid] if isinstance(e, dict) else e
+        self.bin_edges = (bin_edges[0], bin_edges[1], of_site(bin_edges[2]),
+                          of_site(bin_edges[3]), bin_edges[4])
+        for i, name in enumerate(['Ma', 'D', 'Lo', 'La', 'E']):
+            setattr(self, name, len(self.bin_edges[i]) - 1)
+        self.mea, self.std = {}, {}   # magi -> array[G, M, U]
+        self.g_by_rlz = {}
+        for g, rlzs in enumerate(rlzs_by_g):
+            for rlz in rlzs:
+                self.g_by_rlz[int(rlz)] = g
+        ctxt = cmaker.recarray(ctxs) if isinstance(ctxs, (list, tuple)) \
+            else ctxs
+        ctx = ctxt[ctxt.sids == sid]
+        if len(ctx) == 0:
+            raise FarAwayRupture('No ruptures affecting site #%d' % sid)
+        if 'clon' not in ctx.dtype.names:
+            raise ValueError('the context rows need the clon, clat columns')
+        self.ctx_by_magi = split_by_magbin(ctx, self.bin_edges[0])
+
+    def init(self, magi, src_mutex=None):
+        if src_mutex:
+            raise NotImplementedError(
+                'disaggregation of mutually exclusive sources has no device '
+                'implementation')
+        try:
+            self.ctx = self.ctx_by_magi[magi]
+        except KeyError:
+            raise FarAwayRupture
+        self.magi = magi
+        if magi not in self.mea:
+            self.mea[magi], self.std[magi] = self.cmaker.get_mean_stds(
+                [self.ctx])[:2]
+        return 1.
+
+    def _disagg6D(self, imldic, g):
+        # imldic: imt -> list of P intensities; returns rates
+        iml2 = numpy.array([numpy.asarray(v, float) for v in imldic.values()])
+        imlog2 = numpy.zeros_like(iml2)
+        for m, imt in enumerate(imldic):
+            with numpy.errstate(divide='ignore'):
+                imlog2[m] = iml2[m] if str(imt) == 'MMI' else numpy.log(iml2[m])
+        poes = disaggregate(self.ctx, self.mea[self.magi], self.std[self.magi],
+                            self.cmaker, g, imlog2, self.bin_edges,
+                            self.epsstar, 1.)
+        return to_rates(poes)
+
+    def disagg_mag_dist_eps(self, imldic, rlz_weights, src_mutex=None):
+        """
+        :param imldic: a dictionary imt -> iml
+        :param rlz_weights: the weights of the realizations
+        :returns: a 4D matrix of rates of shape (Ma, D, E, M)
+        """
+        M = len(imldic)
+        imtls = {imt: [iml] for imt, iml in imldic.items()}
+        out = numpy.zeros((self.Ma, self.D, self.E, M))
+        for magi in range(self.Ma):
+            try:
+                mw = self.init(magi, src_mutex)
+            except FarAwayRupture:
+                continue
+            for rlz, g in self.g_by_rlz.items():
+                mat5 = self._disagg6D(imtls, g)[..., 0]  # p = 0
+                out[magi] += mat5.sum(axis=(1, 2)) * rlz_weights[rlz] * mw
+        return out

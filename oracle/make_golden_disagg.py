@@ -88,3 +88,95 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def make_disaggregator():
+    """
+    The Disaggregator driver (disagg.py:353-538) on the context rows of three
+    point sources at one site: disagg_mag_dist_eps -> (Ma, D, E, M) rates and
+    the 6D matrices per magnitude bin and gsim -> tests/golden/disaggregator.npz
+    """
+    from openquake.hazardlib.contexts import ContextMaker
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, NodalPlane
+    from openquake.hazardlib.pmf import PMF
+    from openquake.hazardlib.mfd import EvenlyDiscretizedMFD
+    from openquake.hazardlib.scalerel.wc1994 import WC1994
+    from openquake.hazardlib.source import PointSource
+    from openquake.hazardlib.tom import PoissonTOM
+    from openquake.hazardlib.site import SiteCollection
+    from openquake.hazardlib.calc.filters import IntegrationDistance
+    from openquake.baselib.general import DictArray
+    tom = PoissonTOM(50.)
+    SRC = [(0.10, 0.10, [0.02, 0.008, 0.003, 0.001], 30., 60., 90., 6.),
+           (0.45, -0.20, [0.05, 0.01, 0.002], 120., 90., 0., 8.),
+           (-0.30, 0.35, [0.01, 0.006, 0.004, 0.002, 0.001], 250., 45., -90.,
+            10.)]
+    srcs = []
+    for i, (lon, lat, rates, strike, dip, rake, dep) in enumerate(SRC):
+        src = PointSource(
+            str(i), 'src%d' % i, 'Active Shallow Crust',
+            EvenlyDiscretizedMFD(5.05, 0.3, rates), 2., WC1994(), 1.5, tom,
+            0., 20., Point(lon, lat),
+            PMF([(1., NodalPlane(strike, dip, rake))]), PMF([(1., dep)]))
+        src.id, src.grp_id, src.weight, src.offset = i, 0, 1., 0
+        srcs.append(src)
+    sitecol = SiteCollection.from_points(
+        [0.05], [0.0], sitemodel=types.SimpleNamespace(
+            reference_vs30_value=500., reference_vs30_type='measured',
+            reference_depth_to_1pt0km_per_sec=100.,
+            reference_depth_to_2pt5km_per_sec=5.))
+    imts = ['PGA', 'SA(0.2)']
+    imtls = DictArray({imt: [0.05, 0.2] for imt in imts})
+    gsims = {valid.gsim('[BooreEtAl2014]'): [0, 2],
+             valid.gsim('[BooreAtkinson2008]'): [1]}
+    oq = types.SimpleNamespace(
+        imtls=imtls, truncation_level=3., investigation_time=50.,
+        maximum_distance=IntegrationDistance.new('100'), epsilon_star=False,
+        infer_occur_rates=False, split_sources=True, min_iml=np.zeros(2),
+        af=None, calculation_mode='disaggregation', keep_rupdata=False,
+        disagg_by_src=False, mea_tau_phi=False, cross_correl=None,
+        max_sites_disagg=10, use_rates=False, with_betw_ratio=None,
+        disagg_bin_edges={}, mag_bin_width=0.5, collect_rlzs=False,
+        pointsource_distance={'default': 1000}, ps_grid_spacing=0,
+        maximum_distance_stations=None)
+    cm = ContextMaker('Active Shallow Crust', gsims, dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.,
+        maximum_distance=IntegrationDistance.new('100')))
+    cm.oq = oq
+    cm.tom = tom
+    ctxs = []
+    for src in srcs:
+        ctxs.extend(cm.get_ctxs(src, sitecol, src_id=src.id))
+    ctx = cm.recarray(ctxs)
+    mag_edges = np.array([5., 5.5, 6., 6.5])
+    dist_edges = np.arange(0, 101, 20.)
+    lon_edges = np.linspace(-0.6, 0.7, 5)
+    lat_edges = np.linspace(-0.5, 0.6, 4)
+    eps_edges = np.linspace(-3, 3, 5)
+    bin_edges = [mag_edges, dist_edges, {0: lon_edges}, {0: lat_edges},
+                 eps_edges]
+    dis = disagg.Disaggregator([ctx], sitecol, cm, bin_edges)
+    imldic = {'PGA': 0.1, 'SA(0.2)': 0.25}
+    rlz_weights = np.array([0.5, 0.3, 0.2])
+    mde = dis.disagg_mag_dist_eps(imldic, rlz_weights)
+    out = dict(mag_edges=mag_edges, dist_edges=dist_edges, lon_edges=lon_edges,
+               lat_edges=lat_edges, eps_edges=eps_edges, mde=mde,
+               rlz_weights=rlz_weights, iml=np.array([0.1, 0.25]),
+               nrows=len(ctx), ctx_mag=ctx.mag, ctx_rrup=ctx.rrup,
+               ctx_clon=ctx.clon, ctx_clat=ctx.clat)
+    imtls2 = {'PGA': [0.1, 0.3], 'SA(0.2)': [0.25, 0.6]}
+    for magi in range(dis.Ma):
+        try:
+            dis.init(magi, {})
+        except disagg.FarAwayRupture:
+            continue
+        for g in range(2):
+            out['mat6_%d_%d' % (magi, g)] = dis._disagg6D(imtls2, g)
+    np.savez_compressed(os.path.join(GOLDEN, 'disaggregator.npz'), **out)
+    print('disaggregator.npz', mde.shape, mde.sum(), len(ctx),
+          [k for k in out if k.startswith('mat6')])
+
+
+if __name__ == '__main__':
+    make_disaggregator()

@@ -104,3 +104,65 @@ def test_disaggregate_no_date_line_and_edge_cases(oq):
     bad.probs_occur = np.ones((len(bad), 3))
     with pytest.raises(NotImplementedError):
         oq.disaggregate(bad, D['mea'], D['std'], CM, 0, D['iml2'], edges())
+
+
+# ----------------------------------------------------------- Disaggregator
+DG = np.load(os.path.join(GOLDEN, 'disaggregator.npz'))
+SRC = [(0.10, 0.10, [0.02, 0.008, 0.003, 0.001], 30., 60., 90., 6.),
+       (0.45, -0.20, [0.05, 0.01, 0.002], 120., 90., 0., 8.),
+       (-0.30, 0.35, [0.01, 0.006, 0.004, 0.002, 0.001], 250., 45., -90., 10.)]
+
+
+def test_host_split_by_magbin_and_to_rates():
+    import oq_engine_b200.disagg as dg
+    ctx = np.zeros(5, [('mag', float)]).view(np.recarray)
+    ctx.mag = [5.0, 6.4, 5.5, 5.49, 6.0]
+    got = dg.split_by_magbin(ctx, np.array([5., 5.5, 6., 6.5]))
+    assert {k: list(v.mag) for k, v in got.items()} == {
+        0: [5.0, 5.49, 5.5], 1: [6.0], 2: [6.4]}
+    np.testing.assert_allclose(dg.to_rates(np.array([0., 0.5, 1.])),
+                               [0., np.log(2.), 100.])
+
+
+@pytest.mark.gpu
+def test_disaggregator_golden(oq):
+    """the driver on the rows of three point sources at one site against the
+    reference's Disaggregator (disagg_mag_dist_eps and the 6D matrices)"""
+    srcs = [oq.PointSource(
+        str(i), lon, lat, oq.EvenlyDiscretizedMFD(5.05, 0.3, rates), 'WC1994',
+        1.5, 0., 20., [(1., strike, dip, rake)], [(1., dep)])
+        for i, (lon, lat, rates, strike, dip, rake, dep) in enumerate(SRC)]
+    sc = oq.SiteCollection.from_points([0.05], [0.0], [0.],
+                                       dict(vs30=500.))
+    cm = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim('BooreEtAl2014'), oq.get_gsim('BooreAtkinson2008')],
+        dict(imtls={'PGA': [0.05, 0.2], 'SA(0.2)': [0.05, 0.2]},
+             truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('100')))
+    ctxs = []
+    for i, src in enumerate(srcs):
+        ctxs.extend(cm.get_ctxs(src, sc, src_id=i))
+    ctx = cm.recarray(ctxs)
+    assert len(ctx) == int(DG['nrows'])
+    np.testing.assert_allclose(np.sort(ctx.rrup), np.sort(DG['ctx_rrup']),
+                               rtol=1e-9)
+    np.testing.assert_allclose(np.sort(ctx.clon), np.sort(DG['ctx_clon']),
+                               atol=1e-9)
+    edges = [DG['mag_edges'], DG['dist_edges'], {0: DG['lon_edges']},
+             {0: DG['lat_edges']}, DG['eps_edges']]
+    dis = oq.Disaggregator(ctx, sc, cm, edges, rlzs_by_g=[[0, 2], [1]])
+    assert (dis.Ma, dis.D, dis.Lo, dis.La, dis.E) == (3, 5, 4, 3, 4)
+    mde = dis.disagg_mag_dist_eps({'PGA': 0.1, 'SA(0.2)': 0.25},
+                                  DG['rlz_weights'])
+    assert mde.shape == DG['mde'].shape
+    np.testing.assert_allclose(mde, DG['mde'], rtol=1e-8, atol=1e-13)
+    imtls2 = {'PGA': [0.1, 0.3], 'SA(0.2)': [0.25, 0.6]}
+    for magi in range(dis.Ma):
+        dis.init(magi)
+        for g in range(2):
+            np.testing.assert_allclose(
+                dis._disagg6D(imtls2, g), DG['mat6_%d_%d' % (magi, g)],
+                rtol=1e-8, atol=1e-13)
+    with pytest.raises(oq.FarAwayRupture):
+        oq.Disaggregator(ctx[:0], sc, cm, edges, rlzs_by_g=[[0], [1]])
