@@ -308,6 +308,20 @@ int oqg_disaggregate(oqg_handle *h, const double *rrup_dev,
                      const double *eps_edges, int E, double truncation_level,
                      double itime, int epsstar, double gp, double *out_dev);
 
+/* conditional spectrum: _cs_out (hazardlib/calc/cond_spectra.py:35-85) for the
+ * U context rows of one site and one gsim.  mu_dev, sig_dev [M][U] (mean and
+ * total standard deviation of log ground motion); probs_dev [U] probability
+ * of at least one occurrence; host arrays rho[M] (correlation with the
+ * conditioning IMT of index imti), imls[P], cs_poes[P], prev[M][P] (the
+ * previously computed c[m, 1, p], or NULL); out (HOST) [M][3][P] =
+ * sum of weights, weighted mean term, weighted variance term (0 without
+ * prev).  Synchronises. */
+int oqg_cs_out(oqg_handle *h, const double *mu_dev, const double *sig_dev,
+               const double *probs_dev, int64_t U, int M, const double *rho,
+               int imti, const double *imls, const double *cs_poes, int P,
+               double truncation_level, double invtime, const double *prev,
+               double *out);
+
 /* ---- post-processing of the rates map -------------------
  * oqg_postclassical replaces, for all the sites at once, the loop of
  * postclassical (calculators/classical.py:258-325): MapGetter.get_hcurve

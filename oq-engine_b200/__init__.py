@@ -24,6 +24,8 @@ from .postproc import (  # noqa
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import Mesh, mesh_min_distance, section_min  # noqa
 from .disagg import disaggregate, Disaggregator, FarAwayRupture  # noqa
+from .cond_spectra import (  # noqa
+    cond_spectra, get_cs_out, BakerJayaram2008)
 from . import sharding  # noqa
 
 __version__ = '0.1.0'

@@ -106,6 +106,10 @@ def lib():
             C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, c_double_p,
             C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, C.c_double,
             C.c_double, C.c_int, C.c_double, c_void]),
+        'oqg_cs_out': (C.c_int, [
+            H, c_void, c_void, c_void, C.c_int64, C.c_int, c_double_p, C.c_int,
+            c_double_p, c_double_p, C.c_int, C.c_double, C.c_double,
+            c_double_p, c_double_p]),
         'oqg_set_exact_poe': (C.c_int, [H, C.c_int]),
         'oqg_poe_table_info': (C.c_int, [H, C.POINTER(C.c_int), c_double_p]),
         'oqg_launch_count': (C.c_ulonglong, [H]),

@@ -565,12 +565,12 @@ class ContextMaker(object):
     def get_mean_stds(self, ctxs, split_by_mag=True):
         """
         :returns: (4, G, M, N) float64: mean, sig, tau, phi
-        (contexts.py:1250-1279); with split_by_mag the rows are reordered by
-        magnitude exactly as the reference does
+        (contexts.py:1250-1279), in the order of the rows.  `split_by_mag`
+        only makes the reference evaluate runs of equal magnitude one at a
+        time (split_array on ORDERED indices, baselib/performance.py:579-592):
+        it does not reorder anything, and has no effect here.
         """
         ctx = self.recarray(list(ctxs))
-        if split_by_mag:
-            ctx = ctx[numpy.argsort(numpy.round(ctx.mag, 3), kind='stable')]
         h = self.handle()
         return mean_stds_device(self.gsims, ctx, self.imts, handle=h,
                                 configure=False)

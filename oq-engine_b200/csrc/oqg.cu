@@ -1254,6 +1254,48 @@ int oqg_disaggregate(oqg_handle *h, const double *rrup, const double *clon,
   return 0;
 }
 
+int oqg_cs_out(oqg_handle *h, const double *mu, const double *sig,
+               const double *probs, int64_t U, int M, const double *rho,
+               int imti, const double *imls, const double *cs_poes, int P,
+               double truncation_level, double invtime, const double *prev,
+               double *out) {
+  CK(cudaSetDevice(h->device));
+  if (M < 1 || P < 1 || imti < 0 || imti >= M) return fail(h, "cs_out: bad shape");
+  if (!rho || !imls || !cs_poes || !out) return fail(h, "cs_out: missing array");
+  const size_t nout = (size_t)M * 3 * P;
+  if (U <= 0) {
+    for (size_t i = 0; i < nout; i++) out[i] = 0.;
+    return 0;
+  }
+  if (!mu || !sig || !probs) return fail(h, "cs_out: missing column");
+  size_t nd = (size_t)M + 2 * P + (prev ? (size_t)M * P : 0) + nout;
+  if (reserve(h, h->stage[8], nd * 8)) return 1;
+  std::vector<double> tab;
+  tab.insert(tab.end(), rho, rho + M);
+  tab.insert(tab.end(), imls, imls + P);
+  tab.insert(tab.end(), cs_poes, cs_poes + P);
+  if (prev) tab.insert(tab.end(), prev, prev + (size_t)M * P);
+  CK(cudaStreamSynchronize(h->stream));
+  double *d = (double *)h->stage[8].p;
+  CK(cudaMemcpy(d, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+  CsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.mu = mu; A.sig = sig; A.probs = probs;
+  A.rho = d; A.imls = d + M; A.cs_poes = A.imls + P;
+  A.prev = prev ? A.cs_poes + P : nullptr;
+  A.out = d + tab.size();
+  A.U = U; A.M = M; A.P = P; A.imti = imti;
+  A.phi_b = 0.5 * (1.0 + erf(truncation_level * sqrt(0.5)));
+  A.inv_norm = 1. / (2. * A.phi_b - 1.);
+  A.invtime = invtime;
+  k_cs_out<<<dim3(P, M + 1), 256, 0, h->stream>>>(A);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, A.out, nout * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
                       int M, const int32_t *g_off, const int32_t *g_rlz, int R,
                       const double *weights, int W, const double *weight_sums,

@@ -110,3 +110,73 @@ __global__ void k_disagg_finalize(double *acc, int64_t n) {
 }
 
 }  // namespace oqg
+
+// ---------------------------------------------------------------------------
+// Conditional spectrum: _cs_out (openquake/hazardlib/calc/cond_spectra.py:
+// 35-85, Lin et al. 2013 eq. 13-15) for one site and one gsim.  Block
+// (p, j): j < M -> the weighted sums of IMT j (mean term and, given the
+// previously computed mean spectrum, the variance term), j == M -> the sum
+// of the weights.  Deterministic tree reduction over the U ruptures.
+namespace oqg {
+
+struct CsArgs {
+  const double *mu, *sig;   // [M][U]
+  const double *probs;      // [U] probability of one or more occurrences
+  const double *rho;        // [M]
+  const double *imls;       // [P] levels of the conditioning IMT
+  const double *cs_poes;    // [P]
+  const double *prev;       // [M][P] previous c[m, 1, p] or null
+  double *out;              // [M][3][P]
+  int64_t U;
+  int M, P, imti;
+  double phi_b, inv_norm, invtime;
+};
+
+__global__ void __launch_bounds__(256) k_cs_out(const CsArgs A) {
+  __shared__ double r1[256], r2[256];
+  const int p = blockIdx.x, j = blockIdx.y;
+  const double liml = log(A.imls[p]);
+  const double norm = -log(1. - A.cs_poes[p]) / A.invtime;
+  const double rho = j < A.M ? A.rho[j] : 0.;
+  const double prev = (j < A.M && A.prev) ? A.prev[j * A.P + p] : 0.;
+  double s1 = 0., s2 = 0.;
+  for (int64_t u = threadIdx.x; u < A.U; u += blockDim.x) {
+    const double eps = (liml - A.mu[(int64_t)A.imti * A.U + u]) /
+                       A.sig[(int64_t)A.imti * A.U + u];
+    const double poe = truncnorm_sf(A.phi_b, A.inv_norm, eps);
+    double ws = -log(pow(1. - A.probs[u], poe)) / A.invtime;
+    ws /= norm;
+    if (j == A.M) {
+      s1 += ws;
+    } else {
+      const double sg = A.sig[(int64_t)j * A.U + u];
+      const double term1 = A.mu[(int64_t)j * A.U + u] + rho * eps * sg;
+      s1 += ws * term1;
+      if (A.prev) {
+        const double term2 = sg * sqrt(1. - rho * rho);
+        const double term3 = term1 - prev;
+        s2 += ws * (term2 * term2 + term3 * term3);
+      }
+    }
+  }
+  r1[threadIdx.x] = s1;
+  r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) {
+      r1[threadIdx.x] += r1[threadIdx.x + k];
+      r2[threadIdx.x] += r2[threadIdx.x + k];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (j == A.M) {
+      for (int m = 0; m < A.M; m++) A.out[(m * 3 + 0) * A.P + p] = r1[0];
+    } else {
+      A.out[(j * 3 + 1) * A.P + p] = r1[0];
+      A.out[(j * 3 + 2) * A.P + p] = A.prev ? r2[0] : 0.;
+    }
+  }
+}
+
+}  // namespace oqg

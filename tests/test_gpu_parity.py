@@ -647,3 +647,18 @@ def test_full_size_properties(oq):
     acc = hazard_np.exact_rate_sum(pairs, octx, sub['sids'], imtls, 3., 50.)
     big = acc > 1e-10
     np.testing.assert_allclose(got[big], acc[big], rtol=1e-5)
+
+
+def test_get_mean_stds_keeps_the_row_order(oq):
+    """split_by_mag evaluates runs of equal magnitude (split_array on ordered
+    indices): the columns stay in the order of the rows"""
+    d = load('gmpe_bssa14')
+    ctx = to_recarray(ctx_of(d))[:50]
+    assert len(np.unique(ctx.mag)) > 3 and (np.diff(ctx.mag) < 0).any()
+    cm = oq.ContextMaker('*', [oq.BooreEtAl2014()], dict(
+        imtls={'PGA': [0.1], 'SA(1.0)': [0.1]}))
+    a = cm.get_mean_stds([ctx], split_by_mag=True)
+    b = cm.get_mean_stds([ctx], split_by_mag=False)
+    np.testing.assert_array_equal(a, b)
+    rev = cm.get_mean_stds([ctx[::-1]])
+    np.testing.assert_array_equal(rev[..., ::-1], a)
