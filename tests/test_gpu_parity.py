@@ -662,3 +662,18 @@ def test_get_mean_stds_keeps_the_row_order(oq):
     np.testing.assert_array_equal(a, b)
     rev = cm.get_mean_stds([ctx[::-1]])
     np.testing.assert_array_equal(rev[..., ::-1], a)
+
+
+def test_reference_known_ask14_stddevs(oq):
+    """contexts_test.py:384-387 (test_from_planar): sig, tau, phi of
+    AbrahamsonEtAl2014 for PGA are .79162428, .47, .637"""
+    from test_oracle import ask14_from_planar_rows
+    ctx = to_recarray(ask14_from_planar_rows())
+    cm = oq.ContextMaker('*', [oq.AbrahamsonEtAl2014()],
+                         dict(imtls={'PGA': [0.1]}))
+    mea, sig, tau, phi = cm.get_mean_stds([ctx])
+    np.testing.assert_allclose(sig, .79162428, rtol=1e-8)
+    np.testing.assert_allclose(tau, .47, rtol=1e-12)
+    np.testing.assert_allclose(phi, .637, rtol=1e-12)
+    ms = oq.contexts.mean_stds_staged_device(cm.gsims, ctx, cm.imts)
+    np.testing.assert_allclose(ms[1], .79162428, rtol=1e-8)

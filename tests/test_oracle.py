@@ -183,3 +183,24 @@ def test_truncnorm_golden():
     np.testing.assert_allclose(
         poe_np.truncnorm_sf(phi_b, np.array([2.99, 2.9999999, 3., 3.5])),
         [4.51109943e-05, 4.44384681e-10, 0., 0.], rtol=1e-6, atol=1e-18)
+
+
+def ask14_from_planar_rows(n=6):
+    """the rows of contexts_test.py:370-387 (test_from_planar): M5, rake 45,
+    vertical strike-slip plane, vs30 760 not measured, z1pt0 20"""
+    from helpers import Bag
+    rrup = np.linspace(1., 100., n)
+    return Bag(mag=np.full(n, 5.), rake=np.full(n, 45.), dip=np.full(n, 90.),
+               ztor=np.full(n, 3.5), width=np.full(n, 3.), rrup=rrup,
+               rjb=rrup, rx=rrup, ry0=np.zeros(n), vs30=np.full(n, 760.),
+               vs30measured=np.zeros(n, bool), z1pt0=np.full(n, 20.))
+
+
+def test_reference_known_ask14_stddevs():
+    """contexts_test.py:384-387: sig, tau, phi of AbrahamsonEtAl2014 for PGA
+    are .79162428, .47, .637 on all the sites of that example"""
+    ms = gmpe_np.mean_stds([('AbrahamsonEtAl2014', {})],
+                           ask14_from_planar_rows(), ['PGA'])
+    np.testing.assert_allclose(ms[1], .79162428, rtol=1e-8)
+    np.testing.assert_allclose(ms[2], .47, rtol=1e-12)
+    np.testing.assert_allclose(ms[3], .637, rtol=1e-12)
