@@ -39,6 +39,12 @@ class SourceGroup(object):
     def __iter__(self):
         return iter(self.sources)
 
+    def __len__(self):
+        return len(self.sources)
+
+    def __getitem__(self, i):
+        return self.sources[i]
+
 
 class RmapMaker(object):
     def __init__(self, cmaker, sitecol, group, task_no=0):

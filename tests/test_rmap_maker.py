@@ -184,3 +184,32 @@ def test_imt_weight_zero(oq):
     pm2 = oq.MapArray(sc.sids, cm2.L, cm2.G).fill(1)
     cm2.hazard_point_sources(pm2, srcs, sc)
     assert ((~pm2).array[:, L1:2 * L1, 1] > 0).any()
+
+
+@pytest.mark.gpu
+def test_calc_hazard_curves(oq):
+    """hazardlib's calc_hazard_curves (calc/hazard_curve.py:76-164): two
+    tectonic region types with their own GSIM, composed as
+    1 - (1 - pmap) exp(-rmap), against the reference"""
+    H = np.load(os.path.join(GOLDEN, 'hazard_curves.npz'))
+    _, _, srcs = setup(oq)
+    for src in srcs[:2]:
+        src.tectonic_region_type = 'Active Shallow Crust'
+    srcs[2].tectonic_region_type = 'Stable Shallow Crust'
+    N = len(H['site_lon'])
+    sc = oq.SiteCollection.from_points(
+        H['site_lon'], H['site_lat'], np.zeros(N), dict(vs30=np.full(N, 600.)))
+    imtls = {str(imt): H['levels'] for imt in H['imts']}
+    gsim_by_trt = {'Active Shallow Crust': oq.get_gsim('BooreEtAl2014'),
+                   'Stable Shallow Crust': oq.get_gsim('AtkinsonBoore2006')}
+    curves = oq.calc_hazard_curves(srcs, sc, imtls, gsim_by_trt,
+                                   truncation_level=3.,
+                                   investigation_time=50.)
+    assert curves.dtype.names == tuple(imtls) and len(curves) == N
+    for imt in imtls:
+        np.testing.assert_allclose(curves[imt], H['curve_' + imt], rtol=2e-5,
+                                   atol=2e-7, err_msg=imt)
+    with pytest.raises(KeyError):
+        oq.calc_hazard_curves(srcs, sc, imtls, {'Active Shallow Crust':
+                                                gsim_by_trt['Active Shallow Crust']},
+                              truncation_level=3., investigation_time=50.)
