@@ -208,9 +208,13 @@ def test_cfg1_area_source_demo(oq):
     mfd = oq.ArbitraryMFD(d['mags'], d['mag_rates'])
     npd = [tuple(x) for x in d['npd']]
     hdd = [tuple(x) for x in d['hdd']]
-    srcs = [oq.PointSource(str(i), lon, lat, mfd, 'WC1994', float(d['rar']),
-                           float(d['usd']), float(d['lsd']), npd, hdd)
-            for i, (lon, lat) in enumerate(zip(d['src_lon'], d['src_lat']))]
+    # the point sources come from the area source itself (polygon
+    # discretisation on the host, area.py), as in the demo's job.ini
+    srcs = list(oq.AreaSource(
+        '1', [-0.5, -0.3, 0.1, 0.3], [-0.5, -0.1, 0.2, -0.8], 10., total,
+        'WC1994', float(d['rar']), float(d['usd']), float(d['lsd']), npd,
+        hdd))
+    assert len(srcs) == len(d['src_lon'])
     N = len(d['site_lon'])
     sites = dict(vs30=np.full(N, float(d['vs30'])))
     sc = oq.SiteCollection.from_points(d['site_lon'], d['site_lat'],
@@ -409,3 +413,44 @@ def test_get_ctxs_of_point_sources(oq, tag):
                                  ).add(round(float(tot), 14))
         # every site sees the same total rate per (source, magnitude)
         assert all(len(v) == 1 for v in rates.values()), rates
+
+
+# ------------------------------------------------------------ area sources
+AP = np.load(os.path.join(GOLDEN, 'area_polygons.npz'))
+
+
+@pytest.mark.parametrize('name', [str(n) for n in AP['names']])
+def test_area_discretization_matches_reference(name):
+    """Polygon.discretize (geo/polygon.py:232-264): the demo polygon, one
+    with edges longer than 100 km (resampled), one across the date line and
+    a concave one -- the same points, bit for bit"""
+    from oq_engine_b200.area import discretize
+    lons, lats = discretize(AP[name + '_poly'][0], AP[name + '_poly'][1],
+                            float(AP[name + '_spacing']))
+    np.testing.assert_array_equal(lons, AP[name + '_lons'])
+    np.testing.assert_array_equal(lats, AP[name + '_lats'])
+
+
+def test_area_source_yields_the_demo_point_sources():
+    """source/area.py:232-290: the 52 point sources of the
+    AreaSourceClassicalPSHA demo with the rescaled MFD (a - log10(52))"""
+    import oq_engine_b200 as oq
+    d = np.load(os.path.join(GOLDEN, 'cfg1_area_demo.npz'))
+    area = oq.AreaSource(
+        '1', [-0.5, -0.3, 0.1, 0.3], [-0.5, -0.1, 0.2, -0.8], 10.,
+        oq.TruncatedGRMFD(*d['gr']), 'WC1994', float(d['rar']),
+        float(d['usd']), float(d['lsd']), [tuple(x) for x in d['npd']],
+        [tuple(x) for x in d['hdd']])
+    pts = list(area)
+    np.testing.assert_array_equal([p.lon for p in pts], d['src_lon'])
+    np.testing.assert_array_equal([p.lat for p in pts], d['src_lat'])
+    mags, rates = zip(*pts[0].get_annual_occurrence_rates())
+    np.testing.assert_allclose(mags, d['mags'], rtol=1e-15)
+    np.testing.assert_allclose(rates, d['mag_rates'], rtol=1e-15)
+    assert all(p.mfd is pts[0].mfd for p in pts)   # one shared slice
+    b = oq.PointSourceBatch(pts)
+    assert b.U == 52 * 8 and len(b.mag) == 8
+    with pytest.raises(ValueError):
+        list(oq.AreaSource('2', [0., 0.01, 0.01], [0., 0., 0.01], 50.,
+                           oq.TruncatedGRMFD(*d['gr']), 'WC1994', 1., 0., 10.,
+                           [(1., 0., 90., 0.)], [(1., 5.)]))
