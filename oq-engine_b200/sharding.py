@@ -125,3 +125,41 @@ def hazard_group_sharded(cmakers, srcs, sitecol, rank, world, rates=False,
         cmakers[g].hazard_planar(pmap, srcs[g], sitecol)
     combine_maps(pmap.array, rates, group)
     return pmap
+
+
+def gid_offsets(cmakers):
+    """Column offsets of groups with their own gsims in the global map:
+    group g owns the columns off[g] .. off[g + 1] (the `gid` of the
+    reference's cmakers, contexts.py:1988-1991)"""
+    return numpy.concatenate([[0], numpy.cumsum([cm.G for cm in cmakers])])
+
+
+def hazard_group_sharded_gid(cmakers, srcs, sitecol, rank, world, rates=True,
+                             group=None):
+    """
+    Source-group sharding when the groups have DIFFERENT gsim sets: group g
+    owns its own columns of the (N, L, Gt) map (Gt = sum of the G of the
+    groups), so combining the ranks is a concatenation on the G axis.  Every
+    rank fills the columns of its groups in a map initialised with the
+    identity of the reduction (0 rates / 1 pne) and the same all-reduce as in
+    `hazard_group_sharded` assembles the whole map on every rank: a column is
+    written by exactly one rank, so SUM / PRODUCT with identities IS the
+    concatenation.  All the groups must share the levels (L).
+    """
+    import torch
+    from .map_array import MapArray
+    off = gid_offsets(cmakers)
+    L = cmakers[0].L
+    assert all(cm.L == L for cm in cmakers), 'the groups must share L'
+    dev = 'cuda:%d' % cmakers[0].handle().device
+    big = MapArray(sitecol.sids, L, int(off[-1]), rates=rates, device=dev)
+    big.fill(0 if rates else 1)
+    for g in groups_of(rank, world, len(srcs)):
+        cm = cmakers[g]
+        pm = MapArray(sitecol.sids, L, cm.G, rates=rates, device=dev)
+        pm.fill(0 if rates else 1)
+        cm.hazard_planar(pm, srcs[g], sitecol)
+        big.array[:, :, off[g]:off[g + 1]] = pm.array
+    combine_maps(big.array, rates, group)
+    big.gid = numpy.arange(off[-1], dtype=numpy.uint16)
+    return big

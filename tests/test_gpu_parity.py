@@ -677,3 +677,50 @@ def test_reference_known_ask14_stddevs(oq):
     np.testing.assert_allclose(phi, .637, rtol=1e-12)
     ms = oq.contexts.mean_stds_staged_device(cm.gsims, ctx, cm.imts)
     np.testing.assert_allclose(ms[1], .79162428, rtol=1e-8)
+
+
+def test_sharding_groups_with_their_own_gsims(oq):
+    """groups with different gsim sets occupy different columns
+    of the map (gid): combining the ranks is a concatenation on the G axis,
+    done by the same all-reduce with identities elsewhere"""
+    import torch
+    rng = np.random.default_rng(31)
+    N = 70
+    sites = synth_sites(N, rng)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    par = dict(imtls=imtls, truncation_level=3., investigation_time=50.)
+    sets = [CFG['cfg3'], [('BooreAtkinson2008', {})],
+            [('CampbellBozorgnia2014', {}), ('AbrahamsonEtAl2014', {})]]
+    cms = [oq.ContextMaker('*', make_gsims(oq, s), par) for s in sets]
+    srcs = []
+    for g in range(3):
+        r = synth_ruptures(30, np.random.default_rng(70 + g))
+        pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                              r['rate'], r['area'], r['hypo_lon'],
+                              r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+        srcs.append(oq.PlanarRuptures(pla, r['mag']))
+    off = oq.sharding.gid_offsets(cms)
+    assert list(off) == [0, 2, 3, 5]
+    # reference: every group on its own
+    want = np.zeros((N, cms[0].L, 5), np.float32)
+    for g in range(3):
+        pm = oq.MapArray(sc.sids, cms[g].L, cms[g].G, rates=True).fill(0)
+        cms[g].hazard_planar(pm, srcs[g], sc)
+        want[:, :, off[g]:off[g + 1]] = pm.array
+    # two "ranks" executed one after the other: their maps add up to it
+    tot = torch.zeros((N, cms[0].L, 5), device='cuda:0')
+    for rank in range(2):
+        big = oq.sharding.hazard_group_sharded_gid(cms, srcs, sc, rank, 2)
+        assert big.array.shape == (N, cms[0].L, 5) and big.rates
+        mine = oq.sharding.groups_of(rank, 2, 3)
+        for g in range(3):
+            cols = big.array[:, :, off[g]:off[g + 1]]
+            assert bool((cols != 0).any()) == (g in mine)
+        tot += big.array
+    np.testing.assert_array_equal(tot.cpu().numpy(), want)
+    one = oq.sharding.hazard_group_sharded_gid(cms, srcs, sc, 0, 1,
+                                               rates=False)
+    np.testing.assert_allclose(one.numpy(), np.exp(-want.astype(float)),
+                               rtol=1e-6)
