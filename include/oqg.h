@@ -192,6 +192,14 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar_dev,
                       int rates_mode, float *map_dev,
                       unsigned long long *counters_dev);
 
+/* the name SURVEY.md section 8b gives to the fused entry point: the same
+ * call for Poissonian ruptures (no probs_occur, identity site index) */
+int oqg_fused_planar(oqg_handle *h, const double *planar_dev,
+                     const double *mag_dev, int R, const oqg_sites *sites_dev,
+                     int N, const double *magdist_dev, double minimum_distance,
+                     double itime, int rates_mode, float *map_dev,
+                     unsigned long long *counters_dev);
+
 /* oqg_hazard_planar with the per-rupture visibility of the
  * pointsource_distance approximation: aux_dev [U][OQG_AUX_LEN] from
  * oqg_point_ruptures, or NULL (every site sees every rupture) */
@@ -321,6 +329,17 @@ int oqg_cs_out(oqg_handle *h, const double *mu_dev, const double *sig_dev,
                int imti, const double *imls, const double *cs_poes, int P,
                double truncation_level, double invtime, const double *prev,
                double *out);
+
+/* ground motion fields: GmfComputer._compute (hazardlib/calc/gmf.py:476-525)
+ * given the epsilons, float32 as in the reference.  mean_stds_dev [4][M][N]
+ * (mean, sig, tau, phi), within_eps_dev [M][N][E], between_eps_dev [E][M]
+ * (may be NULL for modes 0 and 1), not_mmi (host) [M] (0 for MMI: not
+ * exponentiated); mode 0: exp(mean); 1: exp(mean + sig * within);
+ * 2: exp(mean + phi * within + tau * between); out_dev [M][N][E] */
+int oqg_gmf(oqg_handle *h, const float *mean_stds_dev,
+            const float *within_eps_dev, const float *between_eps_dev,
+            const unsigned char *not_mmi, int M, int N, int E, int mode,
+            float *out_dev);
 
 /* ---- post-processing of the rates map -------------------
  * oqg_postclassical replaces, for all the sites at once, the loop of

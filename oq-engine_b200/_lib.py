@@ -86,6 +86,9 @@ def lib():
             c_void, C.POINTER(C.c_ulonglong)]),
         'oqg_point_ruptures': (C.c_int, [H, c_void, C.c_int, C.c_int64,
                                          c_void, c_void, c_void, c_void]),
+        'oqg_fused_planar': (C.c_int, [
+            H, c_void, c_void, C.c_int, C.POINTER(OqgSites), C.c_int, c_void,
+            C.c_double, C.c_double, C.c_int, c_void, c_void]),
         'oqg_hazard_planar_aux': (C.c_int, [
             H, c_void, c_void, c_void, c_void, c_void, C.c_int, C.c_int,
             C.POINTER(OqgSites), c_void, C.c_int, C.c_double, C.c_double,
@@ -110,6 +113,9 @@ def lib():
             H, c_void, c_void, c_void, C.c_int64, C.c_int, c_double_p, C.c_int,
             c_double_p, c_double_p, C.c_int, C.c_double, C.c_double,
             c_double_p, c_double_p]),
+        'oqg_gmf': (C.c_int, [H, c_void, c_void, c_void,
+                              C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int,
+                              C.c_int, c_void]),
         'oqg_set_exact_poe': (C.c_int, [H, C.c_int]),
         'oqg_poe_table_info': (C.c_int, [H, C.POINTER(C.c_int), c_double_p]),
         'oqg_launch_count': (C.c_ulonglong, [H]),

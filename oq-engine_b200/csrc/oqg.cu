@@ -1296,6 +1296,29 @@ int oqg_cs_out(oqg_handle *h, const double *mu, const double *sig,
   return 0;
 }
 
+int oqg_gmf(oqg_handle *h, const float *ms, const float *within,
+            const float *between, const unsigned char *not_mmi, int M, int N,
+            int E, int mode, float *out) {
+  CK(cudaSetDevice(h->device));
+  if (M < 1 || N < 0 || E < 0 || mode < 0 || mode > 2)
+    return fail(h, "gmf: bad shape or mode");
+  if (N == 0 || E == 0) return 0;
+  if (!ms || !out || !not_mmi) return fail(h, "gmf: missing array");
+  if (mode >= 1 && !within) return fail(h, "gmf: missing within epsilons");
+  if (mode == 2 && !between) return fail(h, "gmf: missing between epsilons");
+  if (M > 256) return fail(h, "gmf: at most 256 IMTs");
+  if (reserve(h, h->stage[8], 256)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(h->stage[8].p, not_mmi, M, cudaMemcpyHostToDevice));
+  int64_t n = (int64_t)M * N * E;
+  k_gmf<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+      ms, within, between, (const unsigned char *)h->stage[8].p, M, N, E, mode,
+      out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
                       int M, const int32_t *g_off, const int32_t *g_rlz, int R,
                       const double *weights, int W, const double *weight_sums,
@@ -1661,6 +1684,16 @@ int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
   return oqg_hazard_planar_aux(h, planar, mag, magdist, nullptr, probs, K, U,
                                sites, sidx, N, mindist, itime, rates_mode, map,
                                counters);
+}
+
+int oqg_fused_planar(oqg_handle *h, const double *planar, const double *mag,
+                     int R, const oqg_sites *sites, int N,
+                     const double *magdist, double mindist, double itime,
+                     int rates_mode, float *map,
+                     unsigned long long *counters) {
+  return oqg_hazard_planar_aux(h, planar, mag, magdist, nullptr, nullptr, 0, R,
+                               sites, nullptr, N, mindist, itime, rates_mode,
+                               map, counters);
 }
 
 int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,

@@ -180,3 +180,37 @@ __global__ void __launch_bounds__(256) k_cs_out(const CsArgs A) {
 }
 
 }  // namespace oqg
+
+// ---------------------------------------------------------------------------
+// Ground motion fields: GmfComputer._compute
+// (openquake/hazardlib/calc/gmf.py:476-525), float32 like the reference
+// (mean_stds.astype(F32), float32 epsilons).  One thread per (IMT, site,
+// event); HBM bound: reads the epsilon and writes the value.
+//   mode 0  both truncation levels zero: exp(mean)
+//   mode 1  gsim with total standard deviation only: exp(mean + sig * eps)
+//   mode 2  exp(mean + phi * within_eps + tau * between_eps)
+namespace oqg {
+
+__global__ void k_gmf(const float *__restrict__ ms,      // [4][M][N]
+                      const float *__restrict__ within,  // [M][N][E]
+                      const float *__restrict__ between, // [E][M]
+                      const unsigned char *__restrict__ not_mmi,  // [M]
+                      int M, int N, int E, int mode,
+                      float *__restrict__ out) {         // [M][N][E]
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)M * N * E) return;
+  const int e = (int)(t % E);
+  const int64_t mn = t / E;
+  const int m = (int)(mn / N);
+  const int64_t MN = (int64_t)M * N;
+  float v = ms[mn];
+  if (mode == 1) {
+    v = v + ms[MN + mn] * within[t];
+  } else if (mode == 2) {
+    // (mean + within_res) + between_res, each product rounded to float32
+    v = (v + ms[3 * MN + mn] * within[t]) + ms[2 * MN + mn] * between[e * M + m];
+  }
+  out[t] = not_mmi[m] ? expf(v) : v;
+}
+
+}  // namespace oqg

@@ -724,3 +724,33 @@ def test_sharding_groups_with_their_own_gsims(oq):
                                                rates=False)
     np.testing.assert_allclose(one.numpy(), np.exp(-want.astype(float)),
                                rtol=1e-6)
+
+
+def test_fused_planar_alias(oq):
+    """oqg_fused_planar (the name of SURVEY 8b) == oqg_hazard_planar"""
+    import torch
+    rng = np.random.default_rng(77)
+    U, N = 40, 50
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+        imtls={imt: np.logspace(-2, 0.3, 20) for imt in IMTS},
+        truncation_level=3., investigation_time=50.))
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    want = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+    cm.hazard_planar(want, oq.PlanarRuptures(pla, r['mag']), sc)
+    h = cm.handle()
+    from oq_engine_b200.contexts import _dev, _ptr
+    t_pla = _dev(oq.planar.as_flat(pla), h.device)
+    t_mag = _dev(r['mag'], h.device)
+    t_md = _dev(cm.magdist(r['mag']), h.device)
+    st, keep = cm._sites_struct(sc, h.device)
+    t_map = torch.zeros((N, cm.L, cm.G), dtype=torch.float32,
+                        device='cuda:%d' % h.device)
+    h.call('oqg_fused_planar', _ptr(t_pla), _ptr(t_mag), U, ctypes.byref(st),
+           N, _ptr(t_md), 0., 50., 1, _ptr(t_map), None)
+    np.testing.assert_array_equal(t_map.cpu().numpy(), want.array)
