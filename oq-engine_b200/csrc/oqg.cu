@@ -46,6 +46,9 @@ using namespace oqg;
                        // upper NL - NLR levels, which the level skipping
                        // reaches rarely, accumulate in shared memory
 #endif
+#ifndef OQG_ROLL_ALL
+#define OQG_ROLL_ALL 0   // experiment: roll the rupture stage of every family
+#endif
 #ifndef LGRP
 #define LGRP 2         // levels evaluated per level-skipping test (NL % LGRP == 0)
 #endif
@@ -603,8 +606,6 @@ k_fused(const FusedArgs A) {
   const CT &Cp = *reinterpret_cast<const CT *>(c_coef[A.g * (A.M + 1) + A.M]);
   // log levels of this unit, padded to NL with +inf (poe = 0)
   const double *ll = c_loglev + OQG_MAX_LEVELS + (unit_ok ? unit : 0) * NL;
-  // 0 if the PoEs of this (gsim, IMT) are zeroed (ImtWeight == 0)
-  const float keepf = c_imtmask[A.g * A.M + m] ? 0.f : 1.f;
   const ST ss = FF::site(gs, C, si);      // this IMT
   const ST sp = FF::site(gs, Cp, si);     // PGA, for the shared pair state
 
@@ -715,14 +716,17 @@ k_fused(const FusedArgs A) {
       ri.ztor = s_rup[RF_ZTOR * RT + i];
       ri.width = s_rup[RF_WIDTH * RT + i];
       ri.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];
-      if (FF::ROLL_Q) {
+      if (FF::ROLL_Q || OQG_ROLL_ALL) {
         // one inlined copy of FF::rup for both rows: the CY14 kernel was
         // fetch bound (6592 SASS instructions, stall no_instruction 1.5 per
         // issue); measured -6 % time for CY14, +9 % for ASK14
         const int npass = warp == nw - 1 ? 2 : 1;
 #pragma unroll 1
         for (int pass = 0; pass < npass; pass++) {
-          const CT &cc = pass ? Cp : C;
+          // indexed constant load (LDC), not a select of two references
+          // (which turns the coefficient reads into generic loads)
+          const CT &cc = *reinterpret_cast<const CT *>(
+              c_coef[A.g * (A.M + 1) + (pass ? A.M : m)]);
           st_soa(s_q + ((pass ? nw : warp) * RT + i) * QW, 1,
                  FF::rup(gs, cc, ri));
         }
@@ -764,7 +768,7 @@ k_fused(const FusedArgs A) {
         // x = (tl - (l - mean) / sig) * xscale, xscale = 1 / (2 tl)
         const double xa = -inv * A.xscale;
         const double xb = (A.tl + mean * inv) * A.xscale;
-        const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime) * keepf;
+        const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
         // levels are sorted: from the first one at or above mean + tl * sig
         // for every lane of the warp on, all the PoEs are zero (the padding
         // levels are +inf).  The threshold is reduced over the warp in
@@ -800,11 +804,11 @@ k_fused(const FusedArgs A) {
         const double *pr = s_probs + i * A.K;
 #pragma unroll
         for (int l = 0; l < NL; l++) {
-          double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv) * keepf;
+          double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
           acc[l] *= A.itime == 0. ? 1. - poe : pne_from_pmf(pr, A.K, poe);
         }
       } else {
-        const double rt = s_rup[RF_RATE * RT + i] * A.itime * keepf;
+        const double rt = s_rup[RF_RATE * RT + i] * A.itime;
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
@@ -840,8 +844,9 @@ k_fused(const FusedArgs A) {
 
 // partial sums -> map[sidx[n]][l][g]
 __global__ void k_finalize(const double *__restrict__ part, int RC, int G,
-                           int N, int L, const uint32_t *__restrict__ sidx,
-                           int rates_mode, float *__restrict__ map) {
+                           int N, int L, int L1,
+                           const uint32_t *__restrict__ sidx, int rates_mode,
+                           float *__restrict__ map) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t tot = (int64_t)N * L * G;
   if (e >= tot) return;
@@ -851,6 +856,10 @@ __global__ void k_finalize(const double *__restrict__ part, int RC, int G,
   double s = 0.;
   for (int rc = 0; rc < RC; rc++)
     s += part[(((int64_t)rc * G + g) * N + n) * L + l];
+  // ImtWeight == 0 (set_poes, contexts.py:1469-1475): the PoEs of this
+  // (gsim, IMT) count as zero.  Applied here, once per map element, and not
+  // in the fused kernel, where one more live value cost ASK14 15 %
+  if (c_imtmask[g * (L / L1) + l / L1]) s = 0.;
   int64_t at = ((int64_t)(sidx ? sidx[n] : n) * L + l) * G + g;
   if (rates_mode) map[at] = (float)((double)map[at] + s);
   else map[at] = (float)((double)map[at] * exp(-s));
@@ -1787,7 +1796,7 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   h->n_fused_ev = G;
   int64_t tot = (int64_t)N * L * G;
   k_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
-      A.part, (int)rc, G, N, L, sidx, rates_mode, map);
+      A.part, (int)rc, G, N, L, L1, sidx, rates_mode, map);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
