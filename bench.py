@@ -358,17 +358,17 @@ def run_ours(args):
     except Exception:
         hbm_peak, hbm_src = 6650., 'fallback'
     # DRAM traffic and pipe utilisation of the same kernel from the committed
-    # ncu capture (profiles/r1_v11_traffic.json; cfg3 full size), if the
+    # ncu capture (profiles/r1_v12_traffic.json; cfg3 full size), if the
     # workload is the one that was profiled
     traffic, pipes = None, None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_v11_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r1_v12_traffic.json')) as f:
             prof = json.load(f)
         k = prof['kernels'].get('k_fused<%s>' % names[gdom])
         if k and args.workload == 'cfg3' and not args.ruptures and \
                 not args.sites:
             traffic = k['dram_bytes_read'] + k['dram_bytes_write']
-            pipes = {'source': 'ncu, profiles/r1_v11_traffic.json',
+            pipes = {'source': 'ncu, profiles/r1_v12_traffic.json',
                      'l1tex_lsu_data_pipe_pct': k['lsu_data_pipe_pct'],
                      'issue_slots_pct': k['issue_active_pct'],
                      'fp64_pipe_pct': k['fp64_pipe_pct']}
