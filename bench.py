@@ -404,7 +404,7 @@ def run_ours(args):
     }
     # ---- CPU baseline on a bounded sample, rank 0 only
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # rank 0 at N = 1 only
         v, cores, dt, ev = cpu_baseline(args.workload, args.cpu_ruptures, N,
                                         1, 1)
         cpu = {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
