@@ -160,3 +160,36 @@ def test_postclassical_errors_and_single_rlz(oq):
     tot = D['rates'].astype(np.float32).astype(float).sum(axis=2)
     np.testing.assert_allclose(one['hcurves-rlzs'][0].array.reshape(N, L),
                                1 - np.exp(-tot), rtol=2e-7, atol=1e-30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('R', [1, 4, 9, 33, 40, 130])
+def test_postclassical_other_sizes_vs_oracle(oq, R):
+    """every kernel variant (register path RP = 4 .. 32, generic path for
+    R > 32) against the oracle on random rates, with ties between
+    realizations sharing all their gsim columns"""
+    rng = np.random.default_rng(R)
+    n, m, l1, gt = 23, 2, 5, 6
+    L = m * l1
+    rates = (10 ** rng.uniform(-4, 0.3, (n, L, gt))).astype(np.float32)
+    rates[2] = 0
+    pick = rng.integers(0, gt, (R, 2))          # two columns per realization
+    trt_rlzs = [np.where((pick == g).any(axis=1))[0] for g in range(gt)]
+    w = rng.uniform(0.2, 1., R)
+    w /= w.sum()
+    names = ['mean', 'std', 'quantile-0.16', 'quantile-0.5', 'quantile-0.84']
+    imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
+    res = oq.postclassical(rates, trt_rlzs, w, imtls, names,
+                           individual_rlzs=True)
+    hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
+    got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
+    np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
+    kinds = [('mean', 0.), ('std', 0.), ('quantile', .16), ('quantile', .5),
+             ('quantile', .84)]
+    for k, (kind, q) in enumerate(kinds):
+        got = res['hcurves-stats'][k].array.reshape(n, L)
+        for i in range(0, n, 4):
+            mine = post_np.stat_curve(hc[i], kind, q, w[:, None], m)
+            np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
+                                       err_msg='%s R=%d site %d' % (
+                                           names[k], R, i))
