@@ -1356,8 +1356,16 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     A.kind[s] = kinds[s];
     A.q[s] = qs[s];
   }
-  if (R <= 32) {
-    // register path: inverse map realization -> gsim columns, weight ranks
+  // shared-memory need of the register / shared-memory sort path; the
+  // generic kernel (local arrays, insertion sort) remains for the rare case
+  // that does not fit (many IMT-dependent weight columns x many realizations)
+  int rp_ = 4;
+  while (rp_ < R) rp_ <<= 1;
+  const size_t smem_est = (size_t)rp_ * (rp_ <= 32 ? 128 : 64) * 8 +
+                          (size_t)std::max(W, 1) * R * 12 + (size_t)R * 64 +
+                          (size_t)128 * (Gt | 1) * 4 + 4096;
+  if (R <= 256 && smem_est <= 200 * 1024) {
+    // register / shared-memory sort path: inverse map realization -> gsim columns, weight ranks
     // (small host-side tables, copied through a staging buffer)
     std::vector<int32_t> goff(Gt + 1), tab;
     CK(cudaStreamSynchronize(h->stream));
@@ -1413,14 +1421,27 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     memcpy(B.wsum, A.wsum, sizeof(B.wsum));
     memcpy(B.kind, A.kind, sizeof(B.kind));
     memcpy(B.q, A.q, sizeof(B.q));
-    const int RP = R <= 4 ? 4 : (R <= 8 ? 8 : (R <= 16 ? 16 : 32));
-    size_t smem = (size_t)RP * 128 * 8 + (size_t)B.W * R * 12 +
-                  (R + 1 + rgs.size()) * 4 + 16 + (size_t)128 * (Gt | 1) * 4;
-    unsigned grid = (unsigned)((A.n_elems + 127) / 128);
-    if (RP == 4) k_postclassical_reg<4><<<grid, 128, smem, h->stream>>>(B);
-    else if (RP == 8) k_postclassical_reg<8><<<grid, 128, smem, h->stream>>>(B);
-    else if (RP == 16) k_postclassical_reg<16><<<grid, 128, smem, h->stream>>>(B);
-    else k_postclassical_reg<32><<<grid, 128, smem, h->stream>>>(B);
+    int RP = 4;
+    while (RP < R) RP <<= 1;
+    const int TPB = RP <= 32 ? 128 : 64;
+    size_t smem = (size_t)RP * TPB * 8 + (size_t)B.W * R * 12 +
+                  (R + 1 + rgs.size()) * 4 + 16 + (size_t)TPB * (Gt | 1) * 4;
+    unsigned grid = (unsigned)((A.n_elems + TPB - 1) / TPB);
+#define POST_LAUNCH(rp, tpb)                                                  \
+  {                                                                           \
+    CK(cudaFuncSetAttribute(k_postclassical_reg<rp, tpb>,                     \
+                            cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                            (int)smem));                                      \
+    k_postclassical_reg<rp, tpb><<<grid, tpb, smem, h->stream>>>(B);          \
+  }
+    if (RP == 4) POST_LAUNCH(4, 128)
+    else if (RP == 8) POST_LAUNCH(8, 128)
+    else if (RP == 16) POST_LAUNCH(16, 128)
+    else if (RP == 32) POST_LAUNCH(32, 128)
+    else if (RP == 64) POST_LAUNCH(64, 64)
+    else if (RP == 128) POST_LAUNCH(128, 64)
+    else POST_LAUNCH(256, 64)
+#undef POST_LAUNCH
     h->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -152,15 +152,19 @@ struct PostRegArgs {
   double q[OQG_SMAX];
 };
 
+// IB = bits of the realization index (5 for R <= 32, 8 for R <= 256); the
+// key keeps bits 63 .. 2 IB of the value
+template <int IB>
 __device__ __forceinline__ unsigned long long post_key(double v, int wrank,
                                                         int r) {
   // v >= 0 (a probability or a rate): the bit pattern is order preserving
   unsigned long long u = (unsigned long long)__double_as_longlong(v);
-  return (u & ~0x3ffull) | ((unsigned)wrank << 5) | (unsigned)r;
+  return (u & ~((1ull << (2 * IB)) - 1)) | ((unsigned)wrank << IB) | (unsigned)r;
 }
 
+template <int IB>
 __device__ __forceinline__ double post_key_value(unsigned long long k) {
-  return __longlong_as_double((long long)(k & ~0x3ffull));
+  return __longlong_as_double((long long)(k & ~((1ull << (2 * IB)) - 1)));
 }
 
 // one stage of the bitonic network: compare-exchange of key[i] and key[i ^ J]
@@ -184,16 +188,20 @@ __device__ __forceinline__ void bitonic_stage(unsigned long long (&key)[RP],
   }
 }
 
-template <int RP>
-__global__ void __launch_bounds__(128)
+// RP <= 32: TPB = 128 threads, keys sorted in registers; RP = 64 .. 256: TPB =
+// 64 threads, the same network on the keys in shared memory ([RP][TPB],
+// conflict free: consecutive threads, consecutive 8-byte words)
+template <int RP, int TPB>
+__global__ void __launch_bounds__(TPB)
 k_postclassical_reg(const PostRegArgs A) {
+  constexpr int IB = RP <= 32 ? 5 : 8;
   extern __shared__ double sm_post[];
   math_tables_init();   // fast_exp of oqg_math.cuh
   // shared: keys [RP][128], weights [W][R] (double), wrank [W][R],
   // r_off [R + 1], r_gs, rates [128][Gt | 1]
   const int R = A.R, WR = A.W * R;
   unsigned long long *s_key = (unsigned long long *)sm_post + threadIdx.x;
-  double *s_w = sm_post + RP * 128;
+  double *s_w = sm_post + RP * TPB;
   int *s_rank = (int *)(s_w + WR);
   int *s_off = s_rank + WR;
   int *s_gs = s_off + R + 1;
@@ -206,7 +214,7 @@ k_postclassical_reg(const PostRegArgs A) {
   __syncthreads();
   const int ngs = s_off[R];
   for (int i = threadIdx.x; i < ngs; i += blockDim.x) s_gs[i] = A.r_gs[i];
-  // the rates of the CTA's elements: one coalesced read of 128 * Gt floats,
+  // the rates of the CTA's elements: one coalesced read of TPB * Gt floats,
   // rows padded to an odd stride (conflict-free row reads)
   const int gstride = A.Gt | 1;
   float *s_rates = (float *)(s_gs + ngs);
@@ -240,7 +248,7 @@ k_postclassical_reg(const PostRegArgs A) {
     const double d = v - v0;
     sw1 = fma(w[r], d, sw1);
     sw2 = fma(w[r] * d, d, sw2);
-    s_key[r * 128] = post_key(v, rk[r], r);
+    s_key[r * TPB] = post_key<IB>(v, rk[r], r);
   }
   if (A.stat_out && A.S > 0 && wsum == 0.) {   // getters.py:61-63
     for (int s = 0; s < A.S; s++) A.stat_out[(int64_t)s * A.n_elems + e] = 0.f;
@@ -257,26 +265,43 @@ k_postclassical_reg(const PostRegArgs A) {
       // sum w (m - v)^2 = sum w d^2 - 2 dm sum w d + dm^2 sum w
       res = sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
     } else {
+      if (!sorted && RP > 32) {
+        for (int r = R; r < RP; r++) s_key[r * TPB] = ~0ull;   // padding
+        for (int k = 2; k <= RP; k <<= 1)
+          for (int j = k >> 1; j > 0; j >>= 1)
+            for (int i = 0; i < RP; i++) {
+              const int p = i ^ j;
+              if (p > i) {
+                const unsigned long long a = s_key[i * TPB], b = s_key[p * TPB];
+                if ((a > b) == ((i & k) == 0)) {
+                  s_key[i * TPB] = b;
+                  s_key[p * TPB] = a;
+                }
+              }
+            }
+        sorted = true;
+      }
       if (!sorted) {
-        unsigned long long key[RP];
+        constexpr int RR = RP <= 32 ? RP : 4;   // register network: RP <= 32
+        unsigned long long key[RR];
 #pragma unroll
-        for (int r = 0; r < RP; r++)
-          key[r] = r < R ? s_key[r * 128] : ~0ull;   // padding sorts last
+        for (int r = 0; r < RR; r++)
+          key[r] = r < R ? s_key[r * TPB] : ~0ull;   // padding sorts last
 #pragma unroll 1
-        for (int k = 2; k <= RP; k <<= 1) {
+        for (int k = 2; k <= RR; k <<= 1) {
 #pragma unroll 1
           for (int j = k >> 1; j > 0; j >>= 1) {
             switch (j) {
-              case 16: if (RP > 16) bitonic_stage<RP, (RP > 16 ? 16 : 1)>(key, k); break;
-              case 8: if (RP > 8) bitonic_stage<RP, (RP > 8 ? 8 : 1)>(key, k); break;
-              case 4: if (RP > 4) bitonic_stage<RP, (RP > 4 ? 4 : 1)>(key, k); break;
-              case 2: bitonic_stage<RP, 2>(key, k); break;
-              default: bitonic_stage<RP, 1>(key, k); break;
+              case 16: if (RR > 16) bitonic_stage<RR, (RR > 16 ? 16 : 1)>(key, k); break;
+              case 8: if (RR > 8) bitonic_stage<RR, (RR > 8 ? 8 : 1)>(key, k); break;
+              case 4: if (RR > 4) bitonic_stage<RR, (RR > 4 ? 4 : 1)>(key, k); break;
+              case 2: bitonic_stage<RR, 2>(key, k); break;
+              default: bitonic_stage<RR, 1>(key, k); break;
             }
           }
         }
 #pragma unroll
-        for (int r = 0; r < RP; r++) s_key[r * 128] = key[r];
+        for (int r = 0; r < RR; r++) s_key[r * TPB] = key[r];
         sorted = true;
       }
       // numpy.interp(q, cumsum(w sorted), v sorted)
@@ -285,9 +310,9 @@ k_postclassical_reg(const PostRegArgs A) {
       res = 0.;
 #pragma unroll 1
       for (int j = 0; j < R; j++) {
-        const unsigned long long kj = s_key[j * 128];
-        const double vk = post_key_value(kj);
-        cum += w[(int)(kj & 31u)];
+        const unsigned long long kj = s_key[j * TPB];
+        const double vk = post_key_value<IB>(kj);
+        cum += w[(int)(kj & ((1u << IB) - 1))];
         if (q < cum || j == R - 1) {
           if (j == 0 || q >= cum) res = vk;
           else res = prev_v + (q - prev_cum) * ((vk - prev_v) / (cum - prev_cum));
