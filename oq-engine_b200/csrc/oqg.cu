@@ -1335,7 +1335,7 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
                       int use_rates, float *rlz_out, float *stat_out) {
   CK(cudaSetDevice(h->device));
   if (N <= 0 || L <= 0) return 0;
-  if (R < 1 || R > OQG_RMAX) return fail(h, "postclassical: R must be in 1..256");
+  if (R < 1) return fail(h, "postclassical: R must be positive");
   if (S < 0 || S > OQG_SMAX) return fail(h, "postclassical: at most 16 statistics");
   if (M < 1 || L % M) return fail(h, "postclassical: L must be a multiple of M");
   if (W != 1 && W != M) return fail(h, "postclassical: W must be 1 or M");
@@ -1364,7 +1364,13 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
   const size_t smem_est = (size_t)rp_ * (rp_ <= 32 ? 128 : 64) * 8 +
                           (size_t)std::max(W, 1) * R * 12 + (size_t)R * 64 +
                           (size_t)128 * (Gt | 1) * 4 + 4096;
-  if (R <= 256 && smem_est <= 200 * 1024) {
+  bool any_quantile = false;
+  for (int s = 0; s < S; s++) any_quantile |= kinds[s] == OQG_STAT_QUANTILE;
+  if (any_quantile && R > OQG_RMAX)
+    return fail(h, "postclassical: quantiles need R <= 256 (mean and std "
+                   "have no limit)");
+  const bool stream = !any_quantile && (R > 256 || smem_est > 200 * 1024);
+  if (stream || (R <= 256 && smem_est <= 200 * 1024)) {
     // register / shared-memory sort path: inverse map realization -> gsim columns, weight ranks
     // (small host-side tables, copied through a staging buffer)
     std::vector<int32_t> goff(Gt + 1), tab;
@@ -1387,7 +1393,7 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     }
     std::vector<double> wh((size_t)std::max(W, 1) * R, 0.);
     std::vector<int32_t> rank((size_t)std::max(W, 1) * R, 0);
-    if (S) {
+    if (S && !stream) {
       CK(cudaMemcpy(wh.data(), weights, wh.size() * 8, cudaMemcpyDeviceToHost));
       for (int c = 0; c < W; c++) {
         std::vector<int> ord(R);
@@ -1421,6 +1427,13 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     memcpy(B.wsum, A.wsum, sizeof(B.wsum));
     memcpy(B.kind, A.kind, sizeof(B.kind));
     memcpy(B.q, A.q, sizeof(B.q));
+    if (stream) {
+      k_postclassical_stream<<<(unsigned)((A.n_elems + 127) / 128), 128, 0,
+                               h->stream>>>(B);
+      h->launches++;
+      CK(cudaGetLastError());
+      return 0;
+    }
     int RP = 4;
     while (RP < R) RP <<= 1;
     const int TPB = RP <= 32 ? 128 : 64;

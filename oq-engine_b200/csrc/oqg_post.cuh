@@ -327,6 +327,44 @@ k_postclassical_reg(const PostRegArgs A) {
   }
 }
 
+// ---- streaming path: no quantile asked, any number of realizations ---------
+// mean and standard deviation need no sort: one pass over the realizations
+// with the sums shifted by the first value; nothing is kept per realization,
+// so R is unlimited (sampled logic trees with thousands of realizations).
+__global__ void __launch_bounds__(128)
+k_postclassical_stream(const PostRegArgs A) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= A.n_elems) return;
+  const int l = (int)(e % A.L);
+  const int wcol = A.W > 1 ? l / A.L1 : 0;
+  const double *w = A.weights + (int64_t)wcol * A.R;
+  const double wsum = A.wsum[wcol];
+  const float *row = A.rates + e * A.Gt;
+  double sw1 = 0., sw2 = 0., v0 = 0.;
+  for (int r = 0; r < A.R; r++) {
+    double x = 0.;
+    for (int k = A.r_off[r]; k < A.r_off[r + 1]; k++) x += (double)row[A.r_gs[k]];
+    double v = 1. - exp(-x);
+    if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
+    if (!A.stat_out) continue;
+    if (A.use_rates) v = to_rate(v);
+    if (r == 0) v0 = v;
+    const double d = v - v0, wr = w[r];
+    sw1 = fma(wr, d, sw1);
+    sw2 = fma(wr * d, d, sw2);
+  }
+  if (!A.stat_out) return;
+  const double dm = wsum != 0. ? sw1 / wsum : 0.;
+  for (int s = 0; s < A.S; s++) {
+    double res = A.kind[s] == OQG_STAT_MEAN
+                     ? v0 + dm
+                     : sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
+    if (wsum == 0.) res = 0.;             // getters.py:61-63
+    else if (A.use_rates) res = 1. - exp(-res);
+    A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
+  }
+}
+
 // compute_hazard_maps, map_array.py:94-141: one thread per (curve, imt, poe)
 // curves [K][M][L1] float32, imls [M][L1], out [K][M][P]
 __global__ void k_hazard_maps(const float *__restrict__ curves, int64_t K,

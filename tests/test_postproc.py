@@ -193,3 +193,34 @@ def test_postclassical_other_sizes_vs_oracle(oq, R):
             np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
                                        err_msg='%s R=%d site %d' % (
                                            names[k], R, i))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('use_rates', [False, True])
+def test_postclassical_many_rlzs_stream(oq, use_rates):
+    """mean and std need no sort: the streaming kernel takes any number of
+    realizations (sampled logic trees); quantiles beyond 256 are refused"""
+    R = 600
+    rng = np.random.default_rng(7)
+    n, m, l1, gt = 17, 2, 5, 9
+    L = m * l1
+    rates = (10 ** rng.uniform(-4, 0.3, (n, L, gt))).astype(np.float32)
+    rates[3] = 0
+    pick = rng.integers(0, gt, (R, 2))
+    trt_rlzs = [np.where((pick == g).any(axis=1))[0] for g in range(gt)]
+    w = np.full(R, 1. / R)                       # sampling: equal weights
+    imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
+    res = oq.postclassical(rates, trt_rlzs, w, imtls, ['mean', 'std'],
+                           individual_rlzs=True, use_rates=use_rates)
+    hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
+    got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
+    np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
+    for k, kind in enumerate(['mean', 'std']):
+        got = res['hcurves-stats'][k].array.reshape(n, L)
+        for i in range(n):
+            mine = post_np.stat_curve(hc[i], kind, 0., w[:, None], m,
+                                      use_rates=use_rates)
+            np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
+                                       err_msg='%s site %d' % (kind, i))
+    with pytest.raises(ValueError):
+        oq.postclassical(rates, trt_rlzs, w, imtls, ['quantile-0.5'])
