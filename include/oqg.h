@@ -294,6 +294,18 @@ int oqg_mesh_min_distance(oqg_handle *h, const double *lon_dev,
                           const double *lat_dev, const double *depth_dev,
                           int64_t P, const int64_t *off_dev, int S,
                           const oqg_sites *sites_dev, int N, double *out_dev);
+/* Rx and Ry0 of S mesh surfaces at once: BaseSurface.get_rx_distance
+ * (hazardlib/geo/surface/base.py:319-384) and get_ry0_distance
+ * (base.py:193-239).  top_lon/top_lat_dev: the top edges (first mesh row) in
+ * degrees, the vertices of surface s are off_dev[s] .. off_dev[s + 1] (at
+ * least two; a shorter edge gives NaN); strike_dev[S]: the mean strike of
+ * each surface in degrees (surface.get_strike(); only read for ry0).
+ * rx_dev[S][N], ry0_dev[S][N] km; either may be NULL. */
+int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon_dev,
+                    const double *top_lat_dev, const int64_t *off_dev,
+                    const double *strike_dev, int S,
+                    const oqg_sites *sites_dev, int N, double *rx_dev,
+                    double *ry0_dev);
 int oqg_section_min(oqg_handle *h, const double *sec_dev, int S, int N,
                     const int64_t *rup_off_dev, const int32_t *rup_sec_dev,
                     int U, double *out_dev);

@@ -22,7 +22,8 @@ from .source import (  # noqa
 from .postproc import (  # noqa
     postclassical, compute_hazard_maps, compute_hmaps)
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
-from .mesh import Mesh, mesh_min_distance, section_min  # noqa
+from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
+                   mesh_rx_ry0)
 from .disagg import disaggregate, Disaggregator, FarAwayRupture  # noqa
 from .cond_spectra import (  # noqa
     cond_spectra, get_cs_out, BakerJayaram2008)

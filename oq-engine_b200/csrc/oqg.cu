@@ -1175,6 +1175,26 @@ int oqg_mesh_min_distance(oqg_handle *h, const double *lon, const double *lat,
   return 0;
 }
 
+int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon,
+                    const double *top_lat, const int64_t *off,
+                    const double *strike, int S, const oqg_sites *sites, int N,
+                    double *rx, double *ry0) {
+  CK(cudaSetDevice(h->device));
+  if (S <= 0 || N <= 0) return 0;
+  if (!top_lon || !top_lat || !off || (!rx && !ry0))
+    return fail(h, "mesh_rx_ry0: missing array");
+  if (ry0 && !strike) return fail(h, "mesh_rx_ry0: ry0 needs the mean strike");
+  if (S > 65535) return fail(h, "mesh_rx_ry0: at most 65535 surfaces per call");
+  if (prep_sites(h, sites, N)) return 1;
+  dim3 grid((N + 127) / 128, S);
+  k_mesh_rx_ry0<<<grid, 128, 0, h->stream>>>(top_lon, top_lat, off, strike,
+                                            (const double *)h->site.p, N, rx,
+                                            ry0);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int oqg_section_min(oqg_handle *h, const double *sec, int S, int N,
                     const int64_t *rup_off, const int32_t *rup_sec, int U,
                     double *out) {

@@ -355,4 +355,144 @@ __global__ void k_section_min(const double *__restrict__ sec, int N,
   out[(int64_t)u * N + n] = best;
 }
 
+// ---- Rx and Ry0 of mesh surfaces ------------------------------------------
+// BaseSurface.get_rx_distance (geo/surface/base.py:319-384) and
+// get_ry0_distance (base.py:193-239) for S top edges at once.  The reference
+// solves spherical triangles with azimuths and arc lengths (geodetic.py
+// distance_to_arc :612-647, distance_to_semi_arc :556-609,
+// min_distance_to_segment :182-257); here the same quantities are dot
+// products with unit vectors: at a vertex p with east / north vectors e, n, a
+// direction of azimuth a is t = sin a e + cos a n and the direction to its
+// right is r = t x p, and for a site q at arc length d and azimuth z from p
+//     sin(d) cos(z - a) = (q - p) . t      (in front of / behind p)
+//     sin(d) sin(z - a) = (q - p) . r      (distance_to_arc = R asin of it)
+//     geodetic distance = 2 R asin(|q - p| / 2), chord = R |q - p|
+// so the branches of the reference are sign tests on two dot products and
+// each distance is one asin or one sqrt.  One thread per site, one CTA row
+// per surface; the per-segment vectors are built by the CTA in shared memory.
+struct EdgeSeg {
+  double pa[3], ta[3], ra[3], pb[3], tb[3];
+};
+#define RX_CHUNK 32
+
+__device__ __forceinline__ double dot3(const double *a, const double *b) {
+  return fma(a[0], b[0], fma(a[1], b[1], a[2] * b[2]));
+}
+
+// segment from vertex a to vertex b: tangent ta at a towards b, its right
+// hand side ra, and the direction tb at b with the same azimuth as ta (the
+// reference compares the azimuth of the segment, measured at its first
+// point, with azimuths measured at its second point, geodetic.py:224-226)
+__device__ inline void edge_seg_setup(double lon_a, double lat_a, double lon_b,
+                                      double lat_b, EdgeSeg &g) {
+  double ea[3], na[3], eb[3], nb[3], d[3];
+  unit_from_lonlat(lon_a, lat_a, g.pa, ea, na);
+  unit_from_lonlat(lon_b, lat_b, g.pb, eb, nb);
+  for (int k = 0; k < 3; k++) d[k] = g.pb[k] - g.pa[k];
+  const double along = dot3(d, g.pa);
+  for (int k = 0; k < 3; k++) g.ta[k] = fma(-along, g.pa[k], d[k]);
+  const double nrm = sqrt(dot3(g.ta, g.ta));
+  // coincident vertices: azimuth(p, p) = 0 in the reference (atan2(0, 0))
+  for (int k = 0; k < 3; k++) g.ta[k] = nrm > 0. ? g.ta[k] / nrm : na[k];
+  const double sa = dot3(g.ta, ea), ca = dot3(g.ta, na);
+  for (int k = 0; k < 3; k++) g.tb[k] = fma(sa, eb[k], ca * nb[k]);
+  g.ra[0] = g.ta[1] * g.pa[2] - g.ta[2] * g.pa[1];
+  g.ra[1] = g.ta[2] * g.pa[0] - g.ta[0] * g.pa[2];
+  g.ra[2] = g.ta[0] * g.pa[1] - g.ta[1] * g.pa[0];
+}
+
+__device__ __forceinline__ double arc_of(double x) {
+  return OQG_EARTH_RADIUS * asin(fmin(fmax(x, -1.), 1.));
+}
+
+__global__ void __launch_bounds__(128)
+k_mesh_rx_ry0(const double *__restrict__ tlon, const double *__restrict__ tlat,
+              const int64_t *__restrict__ off, const double *__restrict__ strike,
+              const double *__restrict__ site, int N, double *__restrict__ rx,
+              double *__restrict__ ry0) {
+  __shared__ EdgeSeg s_seg[RX_CHUNK];
+  __shared__ double s_end[2][6];   // first / last vertex: p, r of strike + 90
+  const int s = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pa = off[s];
+  const int K = (int)(off[s + 1] - pa);
+  const bool ok = n < N;
+  double q[3] = {0., 0., 1.};
+  if (ok)
+    for (int k = 0; k < 3; k++) q[k] = site[(int64_t)(SF_Q + k) * N + n];
+  if (K < 2) {          // no segment: not a surface
+    if (ok && rx) rx[(int64_t)s * N + n] = NAN;
+    if (ok && ry0) ry0[(int64_t)s * N + n] = NAN;
+    return;
+  }
+  if (ry0) {
+    if (threadIdx.x < 2) {
+      const int64_t v = threadIdx.x == 0 ? pa : pa + K - 1;
+      double p[3], e[3], nn[3], sa, ca;
+      unit_from_lonlat(tlon[v], tlat[v], p, e, nn);
+      sincos((strike[s] + 90.) * 0.017453292519943295, &sa, &ca);
+      for (int k = 0; k < 3; k++) {
+        s_end[threadIdx.x][k] = p[k];
+        s_end[threadIdx.x][3 + k] = fma(ca, e[k], -sa * nn[k]);
+      }
+    }
+    __syncthreads();
+    if (ok) {
+      double d[2];
+      for (int v = 0; v < 2; v++) {
+        const double dx[3] = {q[0] - s_end[v][0], q[1] - s_end[v][1],
+                              q[2] - s_end[v][2]};
+        d[v] = arc_of(dot3(dx, &s_end[v][3]));
+      }
+      const int s0 = (d[0] > 0.) - (d[0] < 0.), s1 = (d[1] > 0.) - (d[1] < 0.);
+      ry0[(int64_t)s * N + n] = s0 == s1 ? fmin(fabs(d[0]), fabs(d[1])) : 0.;
+    }
+  }
+  if (!rx) return;
+  double best = 0., babs = INFINITY;
+  for (int i0 = 0; i0 < K - 1; i0 += RX_CHUNK) {
+    const int ns = min(RX_CHUNK, K - 1 - i0);
+    __syncthreads();
+    if (threadIdx.x < ns) {
+      const int i = i0 + threadIdx.x;
+      // the first segment of a polyline runs backwards (base.py:360-361)
+      const int64_t a = (K > 2 && i == 0) ? pa + 1 : pa + i;
+      const int64_t b = (K > 2 && i == 0) ? pa : pa + i + 1;
+      edge_seg_setup(tlon[a], tlat[a], tlon[b], tlat[b], s_seg[threadIdx.x]);
+    }
+    __syncthreads();
+    if (!ok) continue;
+    for (int j = 0; j < ns; j++) {
+      const EdgeSeg &g = s_seg[j];
+      const int i = i0 + j;
+      const double dx[3] = {q[0] - g.pa[0], q[1] - g.pa[1], q[2] - g.pa[2]};
+      const double c = dot3(dx, g.ta), x = dot3(dx, g.ra);
+      double d;
+      if (K == 2) {
+        d = arc_of(x);                              // distance_to_arc
+      } else if (i == 0 || i == K - 2) {            // distance_to_semi_arc
+        if (c > 0.) {
+          d = arc_of(x);
+        } else {
+          d = 2. * arc_of(0.5 * sqrt(dot3(dx, dx)));
+          if (x < 0.) d = -d;
+        }
+        if (i == 0) d = -d;
+      } else {                                      // min_distance_to_segment
+        const double ex[3] = {q[0] - g.pb[0], q[1] - g.pb[1], q[2] - g.pb[2]};
+        if (c >= 0. && dot3(ex, g.tb) <= 0.)
+          d = fabs(arc_of(x));
+        else
+          d = OQG_EARTH_RADIUS * sqrt(fmin(dot3(dx, dx), dot3(ex, ex)));
+        if (x < 0.) d = -d;
+      }
+      if (fabs(d) < babs) {     // numpy argmin: the first of equal minima
+        babs = fabs(d);
+        best = d;
+      }
+    }
+  }
+  if (ok) rx[(int64_t)s * N + n] = best;
+}
+
 }  // namespace oqg

@@ -3,7 +3,9 @@ distance.  `Mesh.get_min_distance` mirrors
 openquake/hazardlib/geo/mesh.py:365-383; `mesh_min_distance` evaluates it
 for many meshes (the sections of multi-fault sources, or the ruptures of
 fault sources) in one call and `section_min` composes the per-section
-distances of multi-fault ruptures (contexts.py:969-971)."""
+distances of multi-fault ruptures (contexts.py:969-971).  `mesh_rx_ry0` is
+BaseSurface.get_rx_distance / get_ry0_distance
+(geo/surface/base.py:319-384, :193-239) for many top edges in one call."""
 import ctypes
 import numpy
 
@@ -110,3 +112,58 @@ def section_min(sec_dist, rup_sections, device=None):
                u1 - u0, ctypes.c_void_p(out.data_ptr() + 8 * N * u0))
     torch.cuda.current_stream(dev).synchronize()
     return out.cpu().numpy()
+
+
+def mesh_rx_ry0(top_edges, strikes, points, device=None, rx=True, ry0=True):
+    """
+    :param top_edges: a list of S top edges (the first row of the surface
+        meshes): Mesh objects or (lons, lats) pairs of at least two vertices
+    :param strikes: the S mean strikes (surface.get_strike()), degrees; may
+        be None when ry0 is False
+    :param points: a Mesh or a SiteCollection of N points
+    :returns: (rx, ry0), each (S, N) float64 km or None if not asked
+    """
+    import torch
+    from .contexts import get_handle, _device_index, _dev, _ptr
+    h = get_handle(_device_index(device))
+    dev = h.device
+    edges = [e if isinstance(e, Mesh) else Mesh(*e) for e in top_edges]
+    S = len(edges)
+    if S == 0:
+        raise ValueError('no surface')
+    if any(len(e) < 2 for e in edges):
+        # the reference fails in _get_p1_p2 (base.py:126-138)
+        raise ValueError('a top edge needs at least two points')
+    if ry0:
+        if strikes is None or len(strikes) != S:
+            raise ValueError('ry0 needs one mean strike per surface')
+        t_strike = _dev(numpy.asarray(strikes, float), dev)
+    else:
+        t_strike = None
+    off = numpy.concatenate([[0], numpy.cumsum([len(e) for e in edges])]
+                            ).astype(numpy.int64)
+    t_lon = _dev(numpy.concatenate([e.lons for e in edges]), dev)
+    t_lat = _dev(numpy.concatenate([e.lats for e in edges]), dev)
+    t_off = _dev(off, dev)
+    st, keep, N = _sites_struct(points, dev)
+    cuda = 'cuda:%d' % dev
+    t_rx = torch.empty((S, N), dtype=torch.float64, device=cuda) if rx \
+        else None
+    t_ry0 = torch.empty((S, N), dtype=torch.float64, device=cuda) if ry0 \
+        else None
+    for s0 in range(0, S, 65535):       # grid.y limit
+        s1 = min(S, s0 + 65535)
+        h.call('oqg_mesh_rx_ry0', _ptr(t_lon), _ptr(t_lat),
+               ctypes.c_void_p(t_off.data_ptr() + 8 * s0),
+               ctypes.c_void_p(t_strike.data_ptr() + 8 * s0) if ry0 else None,
+               s1 - s0, ctypes.byref(st), N,
+               ctypes.c_void_p(t_rx.data_ptr() + 8 * N * s0) if rx else None,
+               ctypes.c_void_p(t_ry0.data_ptr() + 8 * N * s0) if ry0 else None)
+    torch.cuda.current_stream(dev).synchronize()
+    out = []
+    for t, name in ((t_rx, 'Rx'), (t_ry0, 'Ry0')):
+        a = None if t is None else t.cpu().numpy()
+        if a is not None and numpy.isnan(a).any():
+            raise ValueError('NaN in %s' % name)      # base.py:236, :382
+        out.append(a)
+    return tuple(out)

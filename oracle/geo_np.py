@@ -296,3 +296,99 @@ DIST = {'rjb': get_rjb, 'rx': get_rx, 'ry0': get_ry0, 'repi': get_repi,
         'rrup': lambda p, x: project(p, x)[0],
         'clon': lambda p, x: project_back(p, x)[0],
         'clat': lambda p, x: project_back(p, x)[1]}
+
+
+# ---- Rx / Ry0 of mesh surfaces ---------------
+# restatement of BaseSurface.get_rx_distance (geo/surface/base.py:319-384)
+# and get_ry0_distance (base.py:193-239) with their geodetic helpers
+# (geo/geodetic.py: azimuth :124-152, fast_distance :93-103, distance_to_arc
+# :612-647, distance_to_semi_arc :556-609, min_distance_to_segment :182-257,
+# min_geodetic_distance :330-343).  Scalar reference point, arrays of sites;
+# everything in float64 (the reference takes the float64 fast_distance branch
+# because the reference point is a Python float).
+
+def _azimuth(lon1, lat1, lon2, lat2):
+    lon1, lat1, lon2, lat2 = (np.radians(x) for x in (lon1, lat1, lon2, lat2))
+    c2 = np.cos(lat2)
+    tc = np.degrees(np.arctan2(
+        np.sin(lon1 - lon2) * c2,
+        np.cos(lat1) * np.sin(lat2) - np.sin(lat1) * c2 * np.cos(lon1 - lon2)))
+    return (360 - tc) % 360
+
+
+def _arc_length(lon1, lat1, lon2, lat2):
+    lon1, lat1, lon2, lat2 = (np.radians(x) for x in (lon1, lat1, lon2, lat2))
+    a = np.sin((lat1 - lat2) / 2.0) ** 2.0 + np.cos(lat1) * np.cos(lat2) * \
+        np.sin((lon1 - lon2) / 2.0) ** 2.0
+    return 2 * EARTH_RADIUS * np.arcsin(np.sqrt(a))
+
+
+def distance_to_arc(alon, alat, aazimuth, plons, plats):
+    az = _azimuth(alon, alat, plons, plats)
+    dist = _arc_length(alon, alat, plons, plats)
+    t_angle = (az - aazimuth + 360) % 360
+    angle = np.arccos(np.sin(np.radians(t_angle)) *
+                      np.sin(dist / EARTH_RADIUS))
+    return (np.pi / 2 - angle) * EARTH_RADIUS
+
+
+def distance_to_semi_arc(alon, alat, aazimuth, plons, plats):
+    az = _azimuth(alon, alat, plons, plats)
+    c = np.cos(np.radians(aazimuth - az))
+    s = np.sin(np.radians(aazimuth - az))
+    dist = _arc_length(alon, alat, plons, plats)
+    t_angle = (az - aazimuth + 360) % 360
+    angle = np.arccos(np.sin(np.radians(t_angle)) *
+                      np.sin(dist / EARTH_RADIUS))
+    front = (np.pi / 2 - angle) * EARTH_RADIUS
+    back = np.where(s > 0., -dist, dist)
+    return np.where(c > 0., front, back)
+
+
+def min_distance_to_segment(seglons, seglats, lons, lats):
+    seg_az = _azimuth(seglons[0], seglats[0], seglons[1], seglats[1])
+    az1 = _azimuth(seglons[0], seglats[0], lons, lats)
+    az2 = _azimuth(seglons[1], seglats[1], lons, lats)
+    inside = (np.cos(np.radians(seg_az - az1)) >= 0.0) & \
+        (np.cos(np.radians(seg_az - az2)) <= 0.0)
+    arc = distance_to_arc(seglons[0], seglats[0], seg_az, lons, lats)
+    ends = spherical_to_cartesian(np.asarray(seglons, float),
+                                  np.asarray(seglats, float), np.zeros(2))
+    pts = spherical_to_cartesian(lons, lats, np.zeros(len(lons)))
+    chord = np.sqrt(((ends[:, None, :] - pts[None]) ** 2).sum(-1)).min(axis=0)
+    d = np.abs(np.where(inside, arc, chord))
+    return np.where(np.sin(np.radians(az1 - seg_az)) < 0.0, -d, d)
+
+
+def rx_distance(top_lons, top_lats, lons, lats):
+    """get_rx_distance for a top edge of K >= 2 points"""
+    K = len(top_lons)
+    dists = []
+    if K < 3:
+        az = _azimuth(top_lons[0], top_lats[0], top_lons[1], top_lats[1])
+        dists.append(distance_to_arc(top_lons[0], top_lats[0], az, lons, lats))
+    else:
+        for i in range(K - 1):
+            a, b = (i + 1, i) if i == 0 else (i, i + 1)
+            if i == 0 or i == K - 2:
+                az = _azimuth(top_lons[a], top_lats[a], top_lons[b],
+                              top_lats[b])
+                dst = distance_to_semi_arc(top_lons[a], top_lats[a], az, lons,
+                                           lats)
+            else:
+                dst = min_distance_to_segment(
+                    [top_lons[a], top_lons[b]], [top_lats[a], top_lats[b]],
+                    lons, lats)
+            dists.append(-dst if i == 0 else dst)
+    dists = np.array(dists)
+    iii = np.abs(dists).argmin(axis=0)
+    return dists[iii, np.arange(dists.shape[1])]
+
+
+def ry0_distance(top_lons, top_lats, mean_strike, lons, lats):
+    """get_ry0_distance given the mean strike of the surface"""
+    az = (mean_strike + 90.) % 360
+    d1 = distance_to_arc(top_lons[0], top_lats[0], az, lons, lats)
+    d2 = distance_to_arc(top_lons[-1], top_lats[-1], az, lons, lats)
+    same = np.sign(d1) == np.sign(d2)
+    return np.where(same, np.fmin(np.abs(d1), np.abs(d2)), 0.)

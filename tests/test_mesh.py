@@ -60,3 +60,77 @@ def test_section_min_golden(oq):
     np.testing.assert_array_equal(got, D['rup_rrup'])
     with pytest.raises(ValueError):
         oq.section_min(D['rrup'], [[99]])
+
+
+# ---- Rx / Ry0 (oracle/make_golden_mesh_rx.py) ------------------------------
+X = np.load(os.path.join(GOLDEN, 'mesh_rx.npz'))
+XOFF = X['off']
+
+
+def test_oracle_rx_ry0_matches_reference():
+    for s in range(len(XOFF) - 1):
+        sl = slice(XOFF[s], XOFF[s + 1])
+        rx = geo_np.rx_distance(X['top_lon'][sl], X['top_lat'][sl],
+                                X['site_lon'][s], X['site_lat'][s])
+        np.testing.assert_allclose(rx, X['rx'][s], rtol=1e-12, atol=1e-9)
+        ry0 = geo_np.ry0_distance(X['top_lon'][sl], X['top_lat'][sl],
+                                  X['strike'][s], X['site_lon'][s],
+                                  X['site_lat'][s])
+        np.testing.assert_allclose(ry0, X['ry0'][s], rtol=1e-12, atol=1e-9)
+    # the fixture exercises both signs, the zero band of ry0 and all the
+    # branches (arc, semi-arc, segment)
+    assert (X['rx'] > 0).any() and (X['rx'] < 0).any()
+    assert (X['ry0'] == 0).any() and (X['ry0'] > 0).any()
+
+
+@pytest.mark.gpu
+def test_mesh_rx_ry0_golden(oq):
+    """atol 1e-8 km: the device evaluates the reference's spherical
+    triangles with unit vectors (k_mesh_rx_ry0), the same quantities up to
+    rounding"""
+    S = len(XOFF) - 1
+    edges = [(X['top_lon'][XOFF[s]:XOFF[s + 1]],
+              X['top_lat'][XOFF[s]:XOFF[s + 1]]) for s in range(S)]
+    # each surface has its own sites in the fixture
+    for s in range(S):
+        sites = oq.Mesh(X['site_lon'][s], X['site_lat'][s])
+        rx, ry0 = oq.mesh_rx_ry0(edges, X['strike'], sites)
+        np.testing.assert_allclose(rx[s], X['rx'][s], rtol=1e-10, atol=1e-8)
+        np.testing.assert_allclose(ry0[s], X['ry0'][s], rtol=1e-10, atol=1e-8)
+        # the other surfaces against the oracle on these sites
+        for t in range(S):
+            if t != s:
+                np.testing.assert_allclose(
+                    rx[t], geo_np.rx_distance(*edges[t], X['site_lon'][s],
+                                              X['site_lat'][s]),
+                    rtol=1e-10, atol=1e-8)
+                np.testing.assert_allclose(
+                    ry0[t], geo_np.ry0_distance(
+                        *edges[t], X['strike'][t], X['site_lon'][s],
+                        X['site_lat'][s]), rtol=1e-10, atol=1e-8)
+    sites = oq.Mesh(X['site_lon'][0], X['site_lat'][0])
+    only_rx, none = oq.mesh_rx_ry0(edges[:3], None, sites, ry0=False)
+    assert none is None
+    np.testing.assert_allclose(only_rx[0], X['rx'][0], rtol=1e-10, atol=1e-8)
+    with pytest.raises(ValueError):
+        oq.mesh_rx_ry0([([1.], [2.])], [0.], sites)
+    with pytest.raises(ValueError):
+        oq.mesh_rx_ry0(edges, None, sites)
+
+
+@pytest.mark.gpu
+def test_mesh_rx_long_edge_vs_oracle(oq):
+    """a top edge longer than one shared-memory chunk of segments"""
+    rng = np.random.default_rng(3)
+    K = 150
+    lons = 20. + np.cumsum(rng.uniform(0.005, 0.02, K))
+    lats = 40. + np.cumsum(rng.uniform(-0.01, 0.012, K))
+    slon = rng.uniform(19.5, 23., 700)
+    slat = rng.uniform(39., 41.5, 700)
+    rx, ry0 = oq.mesh_rx_ry0([(lons, lats)], [75.], oq.Mesh(slon, slat))
+    np.testing.assert_allclose(rx[0], geo_np.rx_distance(lons, lats, slon,
+                                                         slat),
+                               rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(
+        ry0[0], geo_np.ry0_distance(lons, lats, 75., slon, slat),
+        rtol=1e-10, atol=1e-8)
