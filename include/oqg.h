@@ -306,6 +306,18 @@ int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon_dev,
                     const double *strike_dev, int S,
                     const oqg_sites *sites_dev, int N, double *rx_dev,
                     double *ry0_dev);
+/* Mean dip, strike and width of S rectangular meshes:
+ * RectangularMesh.get_mean_inclination_and_azimuth (hazardlib/geo/mesh.py:
+ * 728-783) and get_mean_width (mesh.py:861-885), the surface.get_dip() /
+ * get_strike() / get_width() of fault surfaces.  Mesh s has shape_dev[2 s]
+ * rows x shape_dev[2 s + 1] columns (row-major from off_dev[s]) in
+ * lon/lat/depth_dev (depth may be NULL = 0, which makes the dip 0 as in the
+ * reference); out_dev[S][3] = inclination, azimuth (degrees), width (km);
+ * NaN for a mesh with less than two rows or columns. */
+int oqg_mesh_dip_strike_width(oqg_handle *h, const double *lon_dev,
+                              const double *lat_dev, const double *depth_dev,
+                              const int64_t *off_dev, const int32_t *shape_dev,
+                              int S, double *out_dev);
 int oqg_section_min(oqg_handle *h, const double *sec_dev, int S, int N,
                     const int64_t *rup_off_dev, const int32_t *rup_sec_dev,
                     int U, double *out_dev);

@@ -23,7 +23,7 @@ from .postproc import (  # noqa
     postclassical, compute_hazard_maps, compute_hmaps)
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
-                   mesh_rx_ry0)
+                   mesh_rx_ry0, mesh_dip_strike_width)
 from .disagg import disaggregate, Disaggregator, FarAwayRupture  # noqa
 from .cond_spectra import (  # noqa
     cond_spectra, get_cs_out, BakerJayaram2008)

@@ -105,6 +105,8 @@ def lib():
         'oqg_mesh_rx_ry0': (C.c_int, [
             H, c_void, c_void, c_void, c_void, C.c_int, C.POINTER(OqgSites),
             C.c_int, c_void, c_void]),
+        'oqg_mesh_dip_strike_width': (C.c_int, [
+            H, c_void, c_void, c_void, c_void, c_void, C.c_int, c_void]),
         'oqg_section_min': (C.c_int, [H, c_void, C.c_int, C.c_int, c_void,
                                       c_void, C.c_int, c_void]),
         'oqg_disaggregate': (C.c_int, [

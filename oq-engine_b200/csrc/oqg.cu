@@ -1195,6 +1195,21 @@ int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon,
   return 0;
 }
 
+int oqg_mesh_dip_strike_width(oqg_handle *h, const double *lon,
+                              const double *lat, const double *depth,
+                              const int64_t *off, const int32_t *shape, int S,
+                              double *out) {
+  CK(cudaSetDevice(h->device));
+  if (S <= 0) return 0;
+  if (!lon || !lat || !off || !shape || !out)
+    return fail(h, "mesh_dip_strike_width: missing array");
+  k_mesh_dip_strike_width<<<S, MESH_DIP_TPB, 0, h->stream>>>(lon, lat, depth,
+                                                            off, shape, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int oqg_section_min(oqg_handle *h, const double *sec, int S, int N,
                     const int64_t *rup_off, const int32_t *rup_sec, int U,
                     double *out) {

@@ -495,4 +495,135 @@ k_mesh_rx_ry0(const double *__restrict__ tlon, const double *__restrict__ tlat,
   if (ok) rx[(int64_t)s * N + n] = best;
 }
 
+// ---- mean dip, strike and width of rectangular meshes ---------------------
+// RectangularMesh.get_mean_inclination_and_azimuth (geo/mesh.py:728-783 with
+// calc_inclination :101-133, calc_azimuth :136-196) and get_mean_width
+// (:861-885, get_cell_dimensions :785-827): the rupture parameters dip,
+// strike (needed by Ry0) and width of a non-planar surface.  Every mesh cell
+// is split in a top-left and a bottom-right triangle; inclination and
+// azimuth are area-weighted circular means over the triangles, the width is
+// the mean over the columns weighted by the mean cell length of the column.
+// One CTA per mesh, one thread per column of cells walking down the rows.
+__device__ __forceinline__ void mesh_point(const double *lon, const double *lat,
+                                           const double *dep, int64_t i,
+                                           double *p) {
+  double sl, cl, sp, cp;
+  sincos(lon[i] * 0.017453292519943295, &sl, &cl);
+  sincos(lat[i] * 0.017453292519943295, &sp, &cp);
+  const double rr = OQG_EARTH_RADIUS - (dep ? dep[i] : 0.);
+  p[0] = rr * cp * cl; p[1] = rr * cp * sl; p[2] = rr * sp;
+}
+
+__device__ __forceinline__ void cross3(const double *a, const double *b,
+                                       double *c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ __forceinline__ double heron(double a, double b, double c) {
+  const double s = (a + b + c) / 2.0;
+  return sqrt(s * (s - a) * (s - b) * (s - c));
+}
+
+// one triangle with azimuthal edge e1 and up-dip edge e2 at the corner p:
+// adds its share to the inclination sums (ix, iy) and azimuth sums (ax, ay)
+__device__ inline void mesh_triangle(const double *p, const double *e1,
+                                     const double *e2, double area, double *acc) {
+  double nrm[3], west[3], north[3], pz[3] = {p[0], p[1], p[2] + 1.0};
+  cross3(e1, e2, nrm);
+  const double ic = fmin(fmax(dot3(p, nrm) * rsqrt(dot3(p, p)) /
+                                  sqrt(dot3(nrm, nrm)), -1.), 1.);
+  acc[0] += area * ic;
+  acc[1] += area * sqrt(fmax(1. - ic * ic, 0.));
+  cross3(pz, p, west);
+  cross3(p, west, north);
+  const double l1 = sqrt(dot3(e1, e1));
+  const double aw = dot3(e1, west) / (l1 * sqrt(dot3(west, west)));
+  const double ac = dot3(e1, north) / (l1 * sqrt(dot3(north, north)));
+  acc[2] += area * ac;
+  const double y = area * sqrt(fmax(1. - ac * ac, 0.));
+  acc[3] += aw < 0. ? -y : y;    // sign(sign(.) + 0.1): zero counts as +1
+}
+
+#define MESH_DIP_TPB 64
+__global__ void __launch_bounds__(MESH_DIP_TPB)
+k_mesh_dip_strike_width(const double *__restrict__ lon,
+                        const double *__restrict__ lat,
+                        const double *__restrict__ dep,
+                        const int64_t *__restrict__ off,
+                        const int32_t *__restrict__ shape,
+                        double *__restrict__ out) {
+  __shared__ double s_red[MESH_DIP_TPB / 32][8];
+  const int s = blockIdx.x;
+  const int R = shape[2 * s], C = shape[2 * s + 1];
+  const int64_t base = off[s];
+  // acc: ix iy ax ay, sum widths * mcl, sum mcl, any depth != 0
+  double acc[7] = {0., 0., 0., 0., 0., 0., 0.};
+  for (int c = threadIdx.x; c < C - 1; c += blockDim.x) {
+    double width = 0., col_area = 0., len_area = 0.;
+    double p00[3], p01[3], p10[3], p11[3];
+    mesh_point(lon, lat, dep, base + c, p00);
+    mesh_point(lon, lat, dep, base + c + 1, p01);
+    if (dep && (dep[base + c] != 0. || dep[base + c + 1] != 0.)) acc[6] = 1.;
+    for (int r = 0; r < R - 1; r++) {
+      const int64_t i10 = base + (int64_t)(r + 1) * C + c;
+      mesh_point(lon, lat, dep, i10, p10);
+      mesh_point(lon, lat, dep, i10 + 1, p11);
+      if (dep && (dep[i10] != 0. || dep[i10 + 1] != 0.)) acc[6] = 1.;
+      double top[3], left[3], bottom[3], right[3], diag[3];
+      for (int k = 0; k < 3; k++) {
+        top[k] = p01[k] - p00[k];        // along_azimuth[r][c]
+        left[k] = p00[k] - p10[k];       // updip[r][c]
+        bottom[k] = p11[k] - p10[k];     // along_azimuth[r + 1][c]
+        right[k] = p01[k] - p11[k];      // updip[r][c + 1]
+        diag[k] = p01[k] - p10[k];
+      }
+      const double lt = sqrt(dot3(top, top)), ll = sqrt(dot3(left, left)),
+                   lb = sqrt(dot3(bottom, bottom)),
+                   lr = sqrt(dot3(right, right)), ld = sqrt(dot3(diag, diag));
+      const double tl_area = heron(lt, ll, ld), br_area = heron(lb, lr, ld);
+      mesh_triangle(p00, top, left, tl_area, acc);
+      mesh_triangle(p11, bottom, right, br_area, acc);
+      const double area = tl_area + br_area;
+      width += (ll * tl_area + lr * br_area) / area;
+      len_area += lt * tl_area + lb * br_area;   // cell_length * cell_area
+      col_area += area;
+      for (int k = 0; k < 3; k++) {
+        p00[k] = p10[k];
+        p01[k] = p11[k];
+      }
+    }
+    const double mcl = len_area / col_area;
+    acc[4] += width * mcl;
+    acc[5] += mcl;
+  }
+  for (int k = 0; k < 7; k++) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 7; k++) {
+      acc[k] = 0.;
+      for (int w = 0; w < MESH_DIP_TPB / 32; w++) acc[k] += s_red[w][k];
+    }
+    if (R < 2 || C < 2) {     // an assertion in the reference
+      out[3 * s] = out[3 * s + 1] = out[3 * s + 2] = NAN;
+      return;
+    }
+    double incl = acc[6] != 0. ? atan2(acc[1], acc[0]) * OQG_R2D : 0.;
+    double azim = atan2(acc[3], acc[2]) * OQG_R2D;
+    if (azim < 0.) azim += 360.;
+    if (incl > 90.) {
+      incl = 180. - incl;
+      azim = fmod(azim + 180., 360.);
+    }
+    out[3 * s] = incl;
+    out[3 * s + 1] = azim;
+    out[3 * s + 2] = acc[4] / acc[5];
+  }
+}
+
 }  // namespace oqg

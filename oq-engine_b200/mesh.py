@@ -167,3 +167,49 @@ def mesh_rx_ry0(top_edges, strikes, points, device=None, rx=True, ry0=True):
             raise ValueError('NaN in %s' % name)      # base.py:236, :382
         out.append(a)
     return tuple(out)
+
+
+def mesh_dip_strike_width(meshes, device=None):
+    """
+    Mean inclination, azimuth and width of rectangular meshes
+    (RectangularMesh.get_mean_inclination_and_azimuth, geo/mesh.py:728-783,
+    and get_mean_width, :861-885).
+
+    :param meshes: a list of S (lons, lats, depths) triples of 2D arrays
+        (rows, cols), rows and cols >= 2, rows not shallower than the
+        previous one
+    :returns: (S, 3) float64: dip and strike in degrees, width in km
+    """
+    import torch
+    from .contexts import get_handle, _device_index, _dev, _ptr
+    h = get_handle(_device_index(device))
+    dev = h.device
+    S = len(meshes)
+    if S == 0:
+        raise ValueError('no mesh')
+    lon, lat, dep, shape = [], [], [], []
+    for lons, lats, deps in meshes:
+        lons = numpy.asarray(lons, float)
+        deps = numpy.zeros_like(lons) if deps is None else \
+            numpy.asarray(deps, float)
+        if lons.ndim != 2 or 1 in lons.shape:
+            raise ValueError(
+                'inclination and azimuth are only defined for mesh of more '
+                'than one row and more than one column of points')
+        if not ((deps[1:] - deps[:-1]) >= 0).all():
+            raise ValueError('a mesh row is shallower than the previous one')
+        lon.append(lons.ravel())
+        lat.append(numpy.asarray(lats, float).ravel())
+        dep.append(deps.ravel())
+        shape.append(lons.shape)
+    off = numpy.concatenate([[0], numpy.cumsum([len(x) for x in lon])]
+                            ).astype(numpy.int64)
+    t_lon, t_lat, t_dep = (_dev(numpy.concatenate(x), dev)
+                           for x in (lon, lat, dep))
+    t_off = _dev(off, dev)
+    t_shape = _dev(numpy.array(shape, numpy.int32), dev)
+    out = torch.empty((S, 3), dtype=torch.float64, device='cuda:%d' % dev)
+    h.call('oqg_mesh_dip_strike_width', _ptr(t_lon), _ptr(t_lat), _ptr(t_dep),
+           _ptr(t_off), _ptr(t_shape), S, _ptr(out))
+    torch.cuda.current_stream(dev).synchronize()
+    return out.cpu().numpy()

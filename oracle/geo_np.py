@@ -392,3 +392,81 @@ def ry0_distance(top_lons, top_lats, mean_strike, lons, lats):
     d2 = distance_to_arc(top_lons[-1], top_lats[-1], az, lons, lats)
     same = np.sign(d1) == np.sign(d2)
     return np.where(same, np.fmin(np.abs(d1), np.abs(d2)), 0.)
+
+
+# ---- mean dip / strike / width of a rectangular mesh ----------------------
+# restatement of RectangularMesh.get_mean_inclination_and_azimuth
+# (geo/mesh.py:728-783, calc_inclination :101-133, calc_azimuth :136-196,
+# triangulate :829-859), get_cell_dimensions (:785-827) and get_mean_width
+# (:861-885); geo/utils.py triangle_area :722-743, normalized :746-759.
+
+def _normalized(v):
+    return v / np.sqrt((v * v).sum(axis=-1))[..., None]
+
+
+def _triangle_area(e1, e2, e3):
+    a, b, c = (np.sqrt((e * e).sum(axis=-1)) for e in (e1, e2, e3))
+    s = (a + b + c) / 2.0
+    return np.sqrt(s * (s - a) * (s - b) * (s - c))
+
+
+def _sqrt0(x):
+    return np.sqrt(np.where(x < 0, 0., x))
+
+
+def _triangulate(lons, lats, deps):
+    pts = spherical_to_cartesian(np.ravel(lons), np.ravel(lats),
+                                 np.ravel(deps)).reshape(np.shape(lons) + (3,))
+    return pts, pts[:, 1:] - pts[:, :-1], pts[:-1] - pts[1:], \
+        pts[:-1, 1:] - pts[1:, :-1]
+
+
+def mean_inclination_and_azimuth(lons, lats, deps):
+    """lons, lats, deps: (rows, cols) arrays, rows and cols >= 2"""
+    pts, along, updip, diag = _triangulate(lons, lats, deps)
+    en = _normalized(pts)
+    tl_area = _triangle_area(along[:-1], updip[:, :-1], diag)
+    tl_normal = _normalized(np.cross(along[:-1], updip[:, :-1]))
+    br_area = _triangle_area(along[1:], updip[:, 1:], diag)
+    br_normal = _normalized(np.cross(along[1:], updip[:, 1:]))
+    if (np.asarray(deps) == 0).all():
+        incl = 0
+    else:
+        c1 = (en[:-1, :-1] * tl_normal).sum(-1).clip(-1., 1.)
+        c2 = (en[1:, 1:] * br_normal).sum(-1).clip(-1., 1.)
+        xx = (tl_area * c1).sum() + (br_area * c2).sum()
+        yy = (tl_area * _sqrt0(1 - c1 * c1)).sum() + \
+            (br_area * _sqrt0(1 - c2 * c2)).sum()
+        incl = np.degrees(np.arctan2(yy, xx))
+    west = _normalized(np.cross(pts + np.array([0., 0., 1.]), pts))
+    north = _normalized(np.cross(pts, west))
+    al = _normalized(along)
+    xx = yy = 0.
+    for a, w, n, area in ((al[:-1], west[:-1, :-1], north[:-1, :-1], tl_area),
+                          (al[1:], west[1:, 1:], north[1:, 1:], br_area)):
+        sign = np.sign(np.sign((a * w).sum(-1)) + 0.1)
+        ac = (a * n).sum(-1)
+        xx += (area * ac).sum()
+        yy += (area * _sqrt0(1 - ac * ac) * sign).sum()
+    azim = np.degrees(np.arctan2(yy, xx))
+    if azim < 0:
+        azim += 360
+    if incl > 90:
+        incl = 180 - incl
+        azim = (azim + 180) % 360
+    return incl, azim
+
+
+def mean_width(lons, lats, deps):
+    pts, along, updip, diag = _triangulate(lons, lats, deps)
+    top, left = along[:-1], updip[:, :-1]
+    bottom, right = along[1:], updip[:, 1:]
+    tl_area = _triangle_area(top, left, diag)
+    br_area = _triangle_area(bottom, right, diag)
+    ln = lambda v: np.sqrt((v * v).sum(-1))  # noqa
+    area = tl_area + br_area
+    cell_length = (ln(top) * tl_area + ln(bottom) * br_area) / area
+    cell_width = (ln(left) * tl_area + ln(right) * br_area) / area
+    widths = cell_width.sum(axis=0)
+    mcl = (cell_length * area).sum(axis=0) / area.sum(axis=0)
+    return (widths * mcl).sum() / mcl.sum()

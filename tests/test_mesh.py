@@ -134,3 +134,58 @@ def test_mesh_rx_long_edge_vs_oracle(oq):
     np.testing.assert_allclose(
         ry0[0], geo_np.ry0_distance(lons, lats, 75., slon, slat),
         rtol=1e-10, atol=1e-8)
+
+
+# ---- mean dip / strike / width (oracle/make_golden_mesh_dip.py) ------------
+G = np.load(os.path.join(GOLDEN, 'mesh_dip.npz'))
+
+
+def _dip_meshes():
+    out = []
+    for s, (r, c) in enumerate(G['shape']):
+        sl = slice(G['off'][s], G['off'][s + 1])
+        out.append(tuple(G[k][sl].reshape(r, c) for k in ('lon', 'lat', 'dep')))
+    return out
+
+
+def test_oracle_dip_strike_width_matches_reference():
+    for s, m in enumerate(_dip_meshes()):
+        incl, azim = geo_np.mean_inclination_and_azimuth(*m)
+        np.testing.assert_allclose([incl, azim, geo_np.mean_width(*m)],
+                                   G['res'][s], rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_mesh_dip_strike_width_golden(oq):
+    """degrees and km; atol 1e-6 degrees: a vertical surface sits on the
+    square-root singularity of sqrt(1 - cos^2) (the reference itself returns
+    89.9999999999997 there)"""
+    meshes = _dip_meshes()
+    got = oq.mesh_dip_strike_width(meshes)
+    np.testing.assert_allclose(np.delete(got, 2, axis=0),
+                               np.delete(G['res'], 2, axis=0), rtol=1e-10,
+                               atol=1e-9)
+    # mesh 2 is exactly vertical: the sum of area * cos(inclination) is pure
+    # rounding noise and its sign decides between (90 - 0, strike) and
+    # (90 + 0 -> flipped to 90 - 0, strike + 180), two names of the same
+    # plane; the reference's own answer depends on its summation order
+    np.testing.assert_allclose(got[2, [0, 2]], G['res'][2, [0, 2]],
+                               rtol=1e-10, atol=1e-6)
+    assert min(abs(got[2, 1] - G['res'][2, 1]),
+               abs(abs(got[2, 1] - G['res'][2, 1]) - 180.)) < 1e-6
+    assert got[6, 0] == 0.       # flat on the Earth surface
+    # SimpleFaultSurface.get_dip / get_strike: the top row of cells only
+    top = [tuple(a[:2] for a in m) for m in meshes]
+    got_top = oq.mesh_dip_strike_width(top)
+    for s, m in enumerate(top):
+        if s == 2:
+            continue
+        incl, azim = geo_np.mean_inclination_and_azimuth(*m)
+        np.testing.assert_allclose(got_top[s, :2], [incl, azim], rtol=1e-10,
+                                   atol=1e-6)
+    # the strike feeds Ry0
+    with pytest.raises(ValueError):
+        oq.mesh_dip_strike_width([(m[0][:1], m[1][:1], m[2][:1])
+                                  for m in meshes])
+    with pytest.raises(ValueError):
+        oq.mesh_dip_strike_width([tuple(a[::-1] for a in meshes[1])])
