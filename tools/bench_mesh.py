@@ -73,6 +73,38 @@ def main():
                      'peak_source': 'DFMA microbenchmark in this process',
                      'flop_per_pair': 8}}))
 
+    # ---- k_mesh_rx_ry0: S top edges of V vertices x N sites -----------------
+    V = 20
+    S2 = min(a.sections, 1000)
+    elon = rng.uniform(0, 3, (S2, 1)) + np.cumsum(
+        rng.uniform(0.01, 0.03, (S2, V)), axis=1)
+    elat = rng.uniform(0, 3, (S2, 1)) + np.cumsum(
+        rng.uniform(-0.01, 0.02, (S2, V)), axis=1)
+    t_elon, t_elat = _dev(elon.ravel(), 0), _dev(elat.ravel(), 0)
+    t_eoff = _dev(np.arange(S2 + 1, dtype=np.int64) * V, 0)
+    t_strike = _dev(rng.uniform(0, 360, S2), 0)
+    rx = torch.empty((S2, N), dtype=torch.float64, device='cuda')
+    ry0 = torch.empty((S2, N), dtype=torch.float64, device='cuda')
+
+    def run2():
+        h.call('oqg_mesh_rx_ry0', _ptr(t_elon), _ptr(t_elat), _ptr(t_eoff),
+               _ptr(t_strike), S2, ctypes.byref(st), N, _ptr(rx), _ptr(ry0))
+    run2()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.steps):
+        run2()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / a.steps
+    segs = float(S2) * (V - 1) * N
+    out_bytes = 2. * S2 * N * 8
+    print(json.dumps({
+        'kernel': 'k_mesh_rx_ry0', 'ms': ms2, 'surfaces': S2,
+        'vertices_per_edge': V, 'sites': a.sites,
+        'segment_site_pairs_per_s': segs / (ms2 * 1e-3),
+        'output_GBps': out_bytes / (ms2 * 1e-3) / 1e9}))
+
 
 if __name__ == '__main__':
     main()
