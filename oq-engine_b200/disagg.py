@@ -83,7 +83,8 @@ def split_by_magbin(ctxt, mag_edges):
 class Disaggregator(object):
     """
     Single-site disaggregation, mirroring the reference's driver
-    (openquake/hazardlib/calc/disagg.py:353-538) for independent sources:
+    (openquake/hazardlib/calc/disagg.py:353-538) for independent sources and
+    for a group of mutually exclusive sources (`src_mutex`):
     `.init(magi)` selects the rows of a magnitude bin and evaluates mean and
     standard deviations with `cmaker.get_mean_stds`, `._disagg6D(imldic, g)`
     returns the (D, Lo, La, E, M, P) matrix of rates of gsim `g` through
@@ -114,6 +115,7 @@ class Disaggregator(object):
         for i, name in enumerate(['Ma', 'D', 'Lo', 'La', 'E']):
             setattr(self, name, len(self.bin_edges[i]) - 1)
         self.mea, self.std = {}, {}   # magi -> array[G, M, U]
+        self._key = {}                # magi -> (magi, mutex) of mea / std
         self.g_by_rlz = {}
         for g, rlzs in enumerate(rlzs_by_g):
             for rlz in rlzs:
@@ -128,19 +130,43 @@ class Disaggregator(object):
         self.ctx_by_magi = split_by_magbin(ctx, self.bin_edges[0])
 
     def init(self, magi, src_mutex=None):
-        if src_mutex:
-            raise NotImplementedError(
-                'disaggregation of mutually exclusive sources has no device '
-                'implementation')
+        """
+        :param src_mutex: empty, or a dictionary with keys src_id, weight and
+            grp_probability for a group of mutually exclusive sources
+            (disagg.py:736-742)
+        :returns: the sum of the weights of the mutually exclusive sources
+            reaching the magnitude bin, or 1
+        """
         try:
-            self.ctx = self.ctx_by_magi[magi]
+            ctx = self.ctx_by_magi[magi]
         except KeyError:
             raise FarAwayRupture
         self.magi = magi
-        if magi not in self.mea:
+        self.src_mutex = dict(src_mutex) if src_mutex else {}
+        key = (magi, bool(self.src_mutex))
+        if self.src_mutex:
+            # rows ordered by source, one slice per source (disagg.py:421-441)
+            ctx = ctx[numpy.argsort(ctx.src_id, kind='stable')]
+        self.ctx = ctx
+        if self._key.get(magi) != key:
             self.mea[magi], self.std[magi] = self.cmaker.get_mean_stds(
-                [self.ctx])[:2]
-        return 1.
+                [ctx])[:2]
+            self._key[magi] = key
+        if not self.src_mutex:
+            return 1.
+        src_ids, start = numpy.unique(ctx.src_id, return_index=True)
+        self.src_mutex['start'] = start
+        self.src_mutex['stop'] = numpy.append(start[1:], len(ctx))
+        present = set(int(s) for s in src_ids)
+        pairs = [(int(s), w) for s, w in zip(self.src_mutex['src_id'],
+                                             self.src_mutex['weight'])
+                 if int(s) in present]
+        if sorted(s for s, _ in pairs) != sorted(present):
+            raise ValueError('a source of the context has no mutex weight')
+        # the slices are in increasing src_id order; the weights follow the
+        # order of src_mutex['src_id'] like in the reference (disagg.py:438)
+        self.weights = [w for _, w in pairs]
+        return sum(self.weights)
 
     def _disagg6D(self, imldic, g):
         # imldic: imt -> list of P intensities; returns rates
@@ -149,10 +175,48 @@ class Disaggregator(object):
         for m, imt in enumerate(imldic):
             with numpy.errstate(divide='ignore'):
                 imlog2[m] = iml2[m] if str(imt) == 'MMI' else numpy.log(iml2[m])
-        poes = disaggregate(self.ctx, self.mea[self.magi], self.std[self.magi],
-                            self.cmaker, g, imlog2, self.bin_edges,
-                            self.epsstar, 1.)
-        return to_rates(poes)
+        mea, std = self.mea[self.magi], self.std[self.magi]
+        if not self.src_mutex:
+            poes = disaggregate(self.ctx, mea, std, self.cmaker, g, imlog2,
+                                self.bin_edges, self.epsstar, 1.)
+            return to_rates(poes)
+        # mutually exclusive sources: the weighted sum of the matrices of
+        # probabilities of the sources (disagg.py:463-475); poes, not rates
+        gp = self.src_mutex.get('grp_probability', 1.)
+        poes = 0.
+        for w, s1, s2 in zip(self.weights, self.src_mutex['start'],
+                             self.src_mutex['stop']):
+            poes = poes + w * disaggregate(
+                self.ctx[s1:s2], mea[:, :, s1:s2], std[:, :, s1:s2],
+                self.cmaker, g, imlog2, self.bin_edges, self.epsstar, gp)
+        return poes
+
+    def disagg_by_magi(self, imtls, rlzs, rwdic=None, src_mutex=None):
+        """
+        disagg.py:477-513: for each magnitude bin with ruptures a dictionary
+        with keys trti, magi, sid, one 6D matrix of rates per realization and
+        'mean' (the mean over the realizations weighted by `rwdic`, rlz ->
+        weight) if `rwdic` is given
+        """
+        for magi in range(self.Ma):
+            try:
+                mw = self.init(magi, src_mutex)
+            except FarAwayRupture:
+                continue
+            res = {'trti': getattr(self.cmaker, 'trti', 0), 'magi': magi,
+                   'sid': self.sid}
+            for rlz in rlzs:
+                try:
+                    g = self.g_by_rlz[int(rlz)]
+                except KeyError:   # non-contributing realization
+                    continue
+                arr6D = self._disagg6D(imtls, g)
+                res[rlz] = to_rates(arr6D) if src_mutex else arr6D
+                if rwdic:
+                    res['mean'] = res.get('mean', 0.) + arr6D * rwdic[rlz] * mw
+            if rwdic and src_mutex:
+                res['mean'] = to_rates(res['mean'])
+            yield res
 
     def disagg_mag_dist_eps(self, imldic, rlz_weights, src_mutex=None):
         """
@@ -171,4 +235,4 @@ class Disaggregator(object):
             for rlz, g in self.g_by_rlz.items():
                 mat5 = self._disagg6D(imtls, g)[..., 0]  # p = 0
                 out[magi] += mat5.sum(axis=(1, 2)) * rlz_weights[rlz] * mw
-        return out
+        return to_rates(out) if src_mutex else out

@@ -173,6 +173,23 @@ def make_disaggregator():
             continue
         for g in range(2):
             out['mat6_%d_%d' % (magi, g)] = dis._disagg6D(imtls2, g)
+    # mutually exclusive sources (disagg.py:421-441, :463-475, :534): a
+    # magnitude bin reached by a subset of the sources uses the sum of the
+    # weights of that subset (the last bin here: the third source only)
+    src_mutex = {'grp_probability': 0.8, 'src_id': np.array([0, 1, 2]),
+                 'weight': [0.5, 0.3, 0.2]}
+    dis2 = disagg.Disaggregator([ctx], sitecol, cm, bin_edges)
+    out['mde_mutex'] = dis2.disagg_mag_dist_eps(imldic, rlz_weights,
+                                                dict(src_mutex))
+    out['mutex_weight'] = np.array(src_mutex['weight'])
+    out['mutex_gp'] = 0.8
+    for magi in range(dis2.Ma):
+        try:
+            out['mutex_mw_%d' % magi] = dis2.init(magi, dict(src_mutex))
+        except disagg.FarAwayRupture:
+            continue
+        for g in range(2):
+            out['mat6m_%d_%d' % (magi, g)] = dis2._disagg6D(imtls2, g)
     np.savez_compressed(os.path.join(GOLDEN, 'disaggregator.npz'), **out)
     print('disaggregator.npz', mde.shape, mde.sum(), len(ctx),
           [k for k in out if k.startswith('mat6')])

@@ -164,5 +164,34 @@ def test_disaggregator_golden(oq):
             np.testing.assert_allclose(
                 dis._disagg6D(imtls2, g), DG['mat6_%d_%d' % (magi, g)],
                 rtol=1e-8, atol=1e-13)
+    # disagg_by_magi: the same matrices per realization and their mean
+    rw = {0: .5, 1: .3, 2: .2}
+    for res in dis.disagg_by_magi(imtls2, [0, 1, 2], rw):
+        magi = res['magi']
+        m0, m1 = (DG['mat6_%d_%d' % (magi, g)] for g in range(2))
+        np.testing.assert_allclose(res[1], m1, rtol=1e-8, atol=1e-13)
+        np.testing.assert_allclose(res['mean'], .7 * m0 + .3 * m1, rtol=1e-8,
+                                   atol=1e-13)
+    # a group of mutually exclusive sources (disagg.py:421-441, 463-475)
+    src_mutex = {'grp_probability': float(DG['mutex_gp']),
+                 'src_id': np.array([0, 1, 2]), 'weight': DG['mutex_weight']}
+    dis2 = oq.Disaggregator(ctx, sc, cm, edges, rlzs_by_g=[[0, 2], [1]])
+    mde = dis2.disagg_mag_dist_eps({'PGA': 0.1, 'SA(0.2)': 0.25},
+                                   DG['rlz_weights'], src_mutex)
+    np.testing.assert_allclose(mde, DG['mde_mutex'], rtol=1e-8, atol=1e-13)
+    for magi in range(dis2.Ma):
+        mw = dis2.init(magi, src_mutex)
+        np.testing.assert_allclose(mw, DG['mutex_mw_%d' % magi], rtol=1e-15)
+        for g in range(2):
+            np.testing.assert_allclose(
+                dis2._disagg6D(imtls2, g), DG['mat6m_%d_%d' % (magi, g)],
+                rtol=1e-8, atol=1e-13)
+    # back to independent sources on the same object: mea / std follow the
+    # row order
+    dis2.init(0)
+    np.testing.assert_allclose(dis2._disagg6D(imtls2, 0), DG['mat6_0_0'],
+                               rtol=1e-8, atol=1e-13)
+    with pytest.raises(ValueError):
+        dis2.init(0, {'grp_probability': 1., 'src_id': [0], 'weight': [1.]})
     with pytest.raises(oq.FarAwayRupture):
         oq.Disaggregator(ctx[:0], sc, cm, edges, rlzs_by_g=[[0], [1]])
