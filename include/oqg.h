@@ -378,12 +378,14 @@ int oqg_gmf(oqg_handle *h, const float *mean_stds_dev,
  *               (IMT-dependent weights, one row per IMT); an IMT whose
  *               weights sum to zero gives zero curves (getters.py:61-63)
  *   kinds, qs   S statistics (host arrays): OQG_STAT_MEAN, OQG_STAT_STD,
+ *               OQG_STAT_MAX (stats.max_curve, the weights are ignored),
  *               OQG_STAT_QUANTILE with its quantile in qs[s]
  *   rlz_out_dev [R][N][L] float32 or NULL ('hcurves-rlzs')
  *   stat_out_dev[S][N][L] float32 or NULL ('hcurves-stats')
  * S <= 16, W <= 64; quantiles need R <= 256, mean and std have no limit on
  * R (an error otherwise). */
-enum { OQG_STAT_MEAN = 0, OQG_STAT_STD = 1, OQG_STAT_QUANTILE = 2 };
+enum { OQG_STAT_MEAN = 0, OQG_STAT_STD = 1, OQG_STAT_QUANTILE = 2,
+       OQG_STAT_MAX = 3 };
 int oqg_postclassical(oqg_handle *h, const float *rates_dev, int N, int L,
                       int Gt, int M, const int32_t *g_off_dev,
                       const int32_t *g_rlz_dev, int R,

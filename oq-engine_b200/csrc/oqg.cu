@@ -1386,7 +1386,7 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
   A.S = S; A.use_rates = use_rates;
   for (int w = 0; w < W && S; w++) A.wsum[w] = weight_sums[w];
   for (int s = 0; s < S; s++) {
-    if (kinds[s] < OQG_STAT_MEAN || kinds[s] > OQG_STAT_QUANTILE)
+    if (kinds[s] < OQG_STAT_MEAN || kinds[s] > OQG_STAT_MAX)
       return fail(h, "postclassical: unknown statistic");
     A.kind[s] = kinds[s];
     A.q[s] = qs[s];

@@ -88,6 +88,9 @@ k_postclassical(const PostArgs A) {
       double acc = 0.;
       for (int r = 0; r < R; r++) acc += w[r] * ((mean - v[r]) * (mean - v[r]));
       res = sqrt(acc);
+    } else if (A.kind[s] == OQG_STAT_MAX) {   // stats.max_curve: no weights
+      res = v[0];
+      for (int r = 1; r < R; r++) res = fmax(res, v[r]);
     } else {
       if (!sorted) {
         // insertion sort of the realizations by (value, weight): numpy's
@@ -236,7 +239,7 @@ k_postclassical_reg(const PostRegArgs A) {
   const double wsum = A.wsum[wcol];
   const float *row = s_rates + threadIdx.x * gstride;
   const bool stats = A.stat_out && A.S > 0 && wsum != 0.;
-  double sw1 = 0., sw2 = 0., v0 = 0.;
+  double sw1 = 0., sw2 = 0., v0 = 0., vmax = 0.;
 #pragma unroll 1
   for (int r = 0; r < R; r++) {
     double x = 0.;
@@ -245,6 +248,7 @@ k_postclassical_reg(const PostRegArgs A) {
     if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
     if (A.use_rates) v = to_rate(v);
     if (r == 0) v0 = v;
+    vmax = fmax(vmax, v);                       // probabilities, rates: >= 0
     const double d = v - v0;
     sw1 = fma(w[r], d, sw1);
     sw2 = fma(w[r] * d, d, sw2);
@@ -264,6 +268,8 @@ k_postclassical_reg(const PostRegArgs A) {
     } else if (A.kind[s] == OQG_STAT_STD) {
       // sum w (m - v)^2 = sum w d^2 - 2 dm sum w d + dm^2 sum w
       res = sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
+    } else if (A.kind[s] == OQG_STAT_MAX) {
+      res = vmax;
     } else {
       if (!sorted && RP > 32) {
         for (int r = R; r < RP; r++) s_key[r * TPB] = ~0ull;   // padding
@@ -340,7 +346,7 @@ k_postclassical_stream(const PostRegArgs A) {
   const double *w = A.weights + (int64_t)wcol * A.R;
   const double wsum = A.wsum[wcol];
   const float *row = A.rates + e * A.Gt;
-  double sw1 = 0., sw2 = 0., v0 = 0.;
+  double sw1 = 0., sw2 = 0., v0 = 0., vmax = 0.;
   for (int r = 0; r < A.R; r++) {
     double x = 0.;
     for (int k = A.r_off[r]; k < A.r_off[r + 1]; k++) x += (double)row[A.r_gs[k]];
@@ -349,6 +355,7 @@ k_postclassical_stream(const PostRegArgs A) {
     if (!A.stat_out) continue;
     if (A.use_rates) v = to_rate(v);
     if (r == 0) v0 = v;
+    vmax = fmax(vmax, v);
     const double d = v - v0, wr = w[r];
     sw1 = fma(wr, d, sw1);
     sw2 = fma(wr * d, d, sw2);
@@ -356,8 +363,9 @@ k_postclassical_stream(const PostRegArgs A) {
   if (!A.stat_out) return;
   const double dm = wsum != 0. ? sw1 / wsum : 0.;
   for (int s = 0; s < A.S; s++) {
-    double res = A.kind[s] == OQG_STAT_MEAN
-                     ? v0 + dm
+    double res = A.kind[s] == OQG_STAT_MEAN ? v0 + dm
+                 : A.kind[s] == OQG_STAT_MAX
+                     ? vmax
                      : sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
     if (wsum == 0.) res = 0.;             // getters.py:61-63
     else if (A.use_rates) res = 1. - exp(-res);

@@ -15,13 +15,13 @@ import numpy
 from .map_array import MapArray
 
 TWO24 = 2 ** 24
-KINDS = {'mean': 0, 'std': 1, 'quantile': 2}
+KINDS = {'mean': 0, 'std': 1, 'quantile': 2, 'max': 3}
 
 
 def _stat_spec(name):
-    """'mean' | 'std' | 'quantile-0.05' -> (kind, q); like the keys of
+    """'mean' | 'std' | 'max' | 'quantile-0.05' -> (kind, q); like the keys of
     OqParam.hazard_stats()"""
-    if name in ('mean', 'std'):
+    if name in ('mean', 'std', 'max'):
         return KINDS[name], 0.
     if name.startswith('quantile-'):
         q = float(name.split('-', 1)[1])

@@ -75,6 +75,7 @@ def stat_curve(hcurve, kind, q, weights, M, use_rates=False):
     poes = hcurve.T
     fn = {'mean': lambda v, w: mean_curve(v, w),
           'std': lambda v, w: std_curve(v, w),
+          'max': lambda v, w: np.max(v, axis=0),   # stats.py:228-237
           'quantile': lambda v, w: quantile_curve(q, v, w)}[kind]
     out = np.zeros(L)
     for m in range(M):

@@ -26,8 +26,9 @@ L1 = L // M
 OFF = D['trt_rlzs_off']
 TRT_RLZS = [D['trt_rlzs'][OFF[g]:OFF[g + 1]] for g in range(Gt)]
 QUANT = list(D['quantiles'])
-KINDS = [('mean', 0.), ('std', 0.)] + [('quantile', q) for q in QUANT]
-NAMES = ['mean', 'std'] + ['quantile-%s' % q for q in QUANT]
+KINDS = [('mean', 0.), ('std', 0.)] + [('quantile', q) for q in QUANT] + [
+    ('max', 0.)]
+NAMES = ['mean', 'std'] + ['quantile-%s' % q for q in QUANT] + ['max']
 IMTLS = {imt: D['imls'] for imt in ('PGA', 'SA(0.2)', 'SA(1.0)')}
 
 
@@ -107,7 +108,7 @@ def test_postclassical_golden(oq, wname, use_rates):
                            poes=list(D['poes']), use_rates=bool(use_rates))
     assert set(res) == {'hcurves-rlzs', 'hcurves-stats', 'hmaps-rlzs',
                         'hmaps-stats'}
-    assert len(res['hcurves-rlzs']) == R and len(res['hcurves-stats']) == 5
+    assert len(res['hcurves-rlzs']) == R and len(res['hcurves-stats']) == 6
     assert res['hcurves-stats'][0].array.shape == (N, M, L1)
     assert (res['hcurves-stats'][0].sids == np.arange(N) * 2 + 1).all()
     # realizations: against the oracle on the float32 rates the device reads
@@ -149,7 +150,7 @@ def test_hazard_maps_golden(oq):
 def test_postclassical_errors_and_single_rlz(oq):
     rmap = rmap_of(oq)
     with pytest.raises(NotImplementedError):
-        oq.postclassical(rmap, TRT_RLZS, D['w1'], IMTLS, ['max'])
+        oq.postclassical(rmap, TRT_RLZS, D['w1'], IMTLS, ['median'])
     with pytest.raises(ValueError):
         oq.postclassical(rmap, TRT_RLZS, D['w1'][:3], IMTLS, ['mean'])
     # R = 1: the realization curves are produced even without
@@ -177,7 +178,8 @@ def test_postclassical_other_sizes_vs_oracle(oq, R):
     trt_rlzs = [np.where((pick == g).any(axis=1))[0] for g in range(gt)]
     w = rng.uniform(0.2, 1., R)
     w /= w.sum()
-    names = ['mean', 'std', 'quantile-0.16', 'quantile-0.5', 'quantile-0.84']
+    names = ['mean', 'std', 'quantile-0.16', 'quantile-0.5', 'quantile-0.84',
+             'max']
     imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
     res = oq.postclassical(rates, trt_rlzs, w, imtls, names,
                            individual_rlzs=True)
@@ -185,7 +187,7 @@ def test_postclassical_other_sizes_vs_oracle(oq, R):
     got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
     np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
     kinds = [('mean', 0.), ('std', 0.), ('quantile', .16), ('quantile', .5),
-             ('quantile', .84)]
+             ('quantile', .84), ('max', 0.)]
     for k, (kind, q) in enumerate(kinds):
         got = res['hcurves-stats'][k].array.reshape(n, L)
         for i in range(0, n, 4):
@@ -210,12 +212,12 @@ def test_postclassical_many_rlzs_stream(oq, use_rates):
     trt_rlzs = [np.where((pick == g).any(axis=1))[0] for g in range(gt)]
     w = np.full(R, 1. / R)                       # sampling: equal weights
     imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
-    res = oq.postclassical(rates, trt_rlzs, w, imtls, ['mean', 'std'],
+    res = oq.postclassical(rates, trt_rlzs, w, imtls, ['mean', 'std', 'max'],
                            individual_rlzs=True, use_rates=use_rates)
     hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
     got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
     np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
-    for k, kind in enumerate(['mean', 'std']):
+    for k, kind in enumerate(['mean', 'std', 'max']):
         got = res['hcurves-stats'][k].array.reshape(n, L)
         for i in range(n):
             mine = post_np.stat_curve(hc[i], kind, 0., w[:, None], m,
