@@ -382,8 +382,8 @@ int oqg_gmf(oqg_handle *h, const float *mean_stds_dev,
  *               OQG_STAT_QUANTILE with its quantile in qs[s]
  *   rlz_out_dev [R][N][L] float32 or NULL ('hcurves-rlzs')
  *   stat_out_dev[S][N][L] float32 or NULL ('hcurves-stats')
- * S <= 16, W <= 64; quantiles need R <= 256, mean and std have no limit on
- * R (an error otherwise). */
+ * S <= 16, W <= 64; quantiles need R <= 4096, mean, std and max have no
+ * limit on R (an error otherwise). */
 enum { OQG_STAT_MEAN = 0, OQG_STAT_STD = 1, OQG_STAT_QUANTILE = 2,
        OQG_STAT_MAX = 3 };
 int oqg_postclassical(oqg_handle *h, const float *rates_dev, int N, int L,

@@ -1401,11 +1401,12 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
                           (size_t)128 * (Gt | 1) * 4 + 4096;
   bool any_quantile = false;
   for (int s = 0; s < S; s++) any_quantile |= kinds[s] == OQG_STAT_QUANTILE;
-  if (any_quantile && R > OQG_RMAX)
-    return fail(h, "postclassical: quantiles need R <= 256 (mean and std "
-                   "have no limit)");
+  if (any_quantile && R > OQG_RMAX_CTA)
+    return fail(h, "postclassical: quantiles need R <= 4096 (mean, std and "
+                   "max have no limit)");
   const bool stream = !any_quantile && (R > 256 || smem_est > 200 * 1024);
-  if (stream || (R <= 256 && smem_est <= 200 * 1024)) {
+  const bool cta = any_quantile && R > 256;
+  if (stream || cta || (R <= 256 && smem_est <= 200 * 1024)) {
     // register / shared-memory sort path: inverse map realization -> gsim columns, weight ranks
     // (small host-side tables, copied through a staging buffer)
     std::vector<int32_t> goff(Gt + 1), tab;
@@ -1462,6 +1463,25 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     memcpy(B.wsum, A.wsum, sizeof(B.wsum));
     memcpy(B.kind, A.kind, sizeof(B.kind));
     memcpy(B.q, A.q, sizeof(B.q));
+    if (cta) {
+      // one CTA per (site, level): keys and scanned weights in shared memory
+      int RPc = 512;
+      while (RPc < R) RPc <<= 1;
+      const size_t smem_c = (size_t)RPc * 16;
+      CK(cudaFuncSetAttribute(k_postclassical_cta,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem_c));
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(
+          8, (200 * 1024) / (smem_c + 4096)));
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+      const unsigned grid_c = (unsigned)std::min<int64_t>(
+          A.n_elems, (int64_t)sms * per_sm);
+      k_postclassical_cta<<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B, RPc);
+      h->launches++;
+      CK(cudaGetLastError());
+      return 0;
+    }
     if (stream) {
       k_postclassical_stream<<<(unsigned)((A.n_elems + 127) / 128), 128, 0,
                                h->stream>>>(B);

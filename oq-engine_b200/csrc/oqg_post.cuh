@@ -373,6 +373,169 @@ k_postclassical_stream(const PostRegArgs A) {
   }
 }
 
+// ---- CTA-cooperative path: quantiles of 256 < R <= 4096 realizations -------
+// (sampled logic trees).  One CTA of 256 threads per (site, level), looping
+// over the elements: the realization values are packed into sort keys
+//     [ bits 63..24 of the float64 value | weight rank (12) | realization (12) ]
+// in shared memory, sorted by a cooperative bitonic network (one barrier per
+// stage), the weights in sorted order are scanned by the CTA and every
+// quantile is found by the thread whose slot brackets it.  Values are
+// compared, and used in the interpolation, to 2^-28 relative (the output is
+// float32); ties are broken by the weight as in the other paths.
+#define OQG_RMAX_CTA 4096
+#define POST_CTA_TPB 256
+#define POST_CTA_IB 12
+
+__device__ __forceinline__ double post_block_sum(double v, double *s_red,
+                                                 bool is_max) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, t) : v + t;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = s_red[0];
+  for (int w = 1; w < POST_CTA_TPB / 32; w++)
+    r = is_max ? fmax(r, s_red[w]) : r + s_red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(POST_CTA_TPB)
+k_postclassical_cta(const PostRegArgs A, int RP) {
+  extern __shared__ double sm_post[];
+  __shared__ double s_red[POST_CTA_TPB / 32];
+  __shared__ double s_part[POST_CTA_TPB];
+  __shared__ int s_found;
+  unsigned long long *s_key = (unsigned long long *)sm_post;   // [RP]
+  double *s_cum = sm_post + RP;                                // [RP]
+  const int R = A.R, tid = threadIdx.x;
+  const int per = RP / POST_CTA_TPB;      // RP >= 512: a multiple of 256
+  for (int64_t e = blockIdx.x; e < A.n_elems; e += gridDim.x) {
+    const int l = (int)(e % A.L);
+    const int wcol = A.W > 1 ? l / A.L1 : 0;
+    const double *w = A.weights + (int64_t)wcol * R;
+    const int *rk = A.wrank + (int64_t)wcol * R;
+    const double wsum = A.wsum[wcol];
+    const float *row = A.rates + e * A.Gt;
+    // the value of realization 0 shifts the sums (exact for equal curves)
+    double v0 = 0.;
+    for (int k = A.r_off[0]; k < A.r_off[1]; k++) v0 += (double)row[A.r_gs[k]];
+    v0 = 1. - exp(-v0);
+    if (A.use_rates) v0 = to_rate(v0);
+    double sw1 = 0., sw2 = 0., vmax = 0.;
+    __syncthreads();                       // the previous element is done
+    for (int r = tid; r < RP; r += POST_CTA_TPB) {
+      if (r >= R) {
+        s_key[r] = ~0ull;                  // padding sorts last
+        continue;
+      }
+      double x = 0.;
+      for (int k = A.r_off[r]; k < A.r_off[r + 1]; k++)
+        x += (double)row[A.r_gs[k]];
+      double v = 1. - exp(-x);
+      if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
+      if (A.use_rates) v = to_rate(v);
+      vmax = fmax(vmax, v);
+      const double d = v - v0, wr = w[r];
+      sw1 = fma(wr, d, sw1);
+      sw2 = fma(wr * d, d, sw2);
+      s_key[r] = post_key<POST_CTA_IB>(v, rk[r], r);
+    }
+    if (!A.stat_out || A.S == 0) continue;
+    sw1 = post_block_sum(sw1, s_red, false);
+    sw2 = post_block_sum(sw2, s_red, false);
+    vmax = post_block_sum(vmax, s_red, true);
+    if (wsum == 0.) {                      // getters.py:61-63
+      if (tid < A.S) A.stat_out[(int64_t)tid * A.n_elems + e] = 0.f;
+      continue;
+    }
+    const double dm = sw1 / wsum;
+    bool sorted = false;
+    for (int s = 0; s < A.S; s++) {
+      if (A.kind[s] != OQG_STAT_QUANTILE) {
+        if (tid == 0) {
+          double res = A.kind[s] == OQG_STAT_MEAN ? v0 + dm
+                       : A.kind[s] == OQG_STAT_MAX
+                           ? vmax
+                           : sqrt(fmax(sw2 - 2. * dm * sw1 + dm * dm * wsum, 0.));
+          if (A.use_rates) res = 1. - exp(-res);
+          A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
+        }
+        continue;
+      }
+      if (!sorted) {
+        __syncthreads();
+        for (int k = 2; k <= RP; k <<= 1)
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < RP / 2; t += POST_CTA_TPB) {
+              const int i = 2 * t - (t & (j - 1)), p = i + j;
+              const unsigned long long a = s_key[i], b = s_key[p];
+              if ((a > b) == ((i & k) == 0)) {
+                s_key[i] = b;
+                s_key[p] = a;
+              }
+            }
+            __syncthreads();
+          }
+        // inclusive scan of the weights in sorted order: `per` consecutive
+        // slots per thread, then the partial sums of the threads
+        double acc = 0.;
+        for (int j = tid * per; j < (tid + 1) * per; j++) {
+          if (j < R) acc += w[(int)(s_key[j] & ((1u << POST_CTA_IB) - 1))];
+          s_cum[j] = acc;
+        }
+        s_part[tid] = acc;
+        __syncthreads();
+        if (tid < 32) {          // exclusive scan of 256 partials by one warp
+          double run = 0.;
+          for (int c = 0; c < POST_CTA_TPB / 32; c++) {
+            const int i = c * 32 + tid;
+            double v = s_part[i];
+            for (int o = 1; o < 32; o <<= 1) {
+              const double t = __shfl_up_sync(0xffffffffu, v, o);
+              if (tid >= o) v += t;
+            }
+            s_part[i] = run + v - s_part[i];
+            run += __shfl_sync(0xffffffffu, v, 31);
+          }
+        }
+        __syncthreads();
+        const double base = s_part[tid];
+        for (int j = tid * per; j < (tid + 1) * per; j++) s_cum[j] += base;
+        sorted = true;
+      }
+      // numpy.interp(q, cumsum(w sorted), v sorted): the first slot j with
+      // q < cum[j], or the last one
+      const double q = A.q[s];
+      if (tid == 0) s_found = 0;
+      __syncthreads();
+      for (int j = tid; j < R; j += POST_CTA_TPB) {
+        const double cum = s_cum[j];
+        const bool here = q < cum && (j == 0 || !(q < s_cum[j - 1]));
+        if (here) {
+          const double vk = post_key_value<POST_CTA_IB>(s_key[j]);
+          double res = vk;
+          if (j > 0) {
+            const double pc = s_cum[j - 1],
+                         pv = post_key_value<POST_CTA_IB>(s_key[j - 1]);
+            res = pv + (q - pc) * ((vk - pv) / (cum - pc));
+          }
+          if (A.use_rates) res = 1. - exp(-res);
+          A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
+          s_found = 1;
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && !s_found) {          // q >= the total weight
+        double res = post_key_value<POST_CTA_IB>(s_key[R - 1]);
+        if (A.use_rates) res = 1. - exp(-res);
+        A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
+      }
+    }
+  }
+}
+
 // compute_hazard_maps, map_array.py:94-141: one thread per (curve, imt, poe)
 // curves [K][M][L1] float32, imls [M][L1], out [K][M][P]
 __global__ void k_hazard_maps(const float *__restrict__ curves, int64_t K,

@@ -119,9 +119,9 @@ def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
     wsum = wdev.sum(axis=1)
     specs = [_stat_spec(name) for name in hstats]
     S = len(specs)
-    if R > 256 and any(k == KINDS['quantile'] for k, _ in specs):
-        raise ValueError('quantiles need at most 256 realizations, got %d '
-                         '(mean and std have no limit)' % R)
+    if R > 4096 and any(k == KINDS['quantile'] for k, _ in specs):
+        raise ValueError('quantiles need at most 4096 realizations, got %d '
+                         '(mean, std and max have no limit)' % R)
     do_rlzs = R == 1 or individual_rlzs
     t_rates = _dev(arr, dev, torch.float32)
     g_off = numpy.concatenate([[0], numpy.cumsum([len(r) for r in rlzs])]

@@ -224,5 +224,44 @@ def test_postclassical_many_rlzs_stream(oq, use_rates):
                                       use_rates=use_rates)
             np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
                                        err_msg='%s site %d' % (kind, i))
-    with pytest.raises(ValueError):
-        oq.postclassical(rates, trt_rlzs, w, imtls, ['quantile-0.5'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('R, use_rates', [(257, False), (600, True),
+                                          (1500, False), (4096, False)])
+def test_postclassical_many_rlzs_quantiles(oq, R, use_rates):
+    """quantiles of 256 < R <= 4096 realizations: the CTA-cooperative sort
+    (k_postclassical_cta) against the oracle, with ties (realizations sharing
+    their gsim columns) and unequal weights"""
+    rng = np.random.default_rng(R)
+    n, m, l1, gt = 5, 2, 4, 12
+    L = m * l1
+    rates = (10 ** rng.uniform(-4, 0.3, (n, L, gt))).astype(np.float32)
+    rates[1] = 0
+    pick = rng.integers(0, gt, (R, 2))
+    trt_rlzs = [np.where((pick == g).any(axis=1))[0] for g in range(gt)]
+    w = rng.uniform(0.2, 1., R) if R != 600 else np.ones(R)
+    w /= w.sum()
+    names = ['mean', 'quantile-0.05', 'std', 'quantile-0.5', 'max',
+             'quantile-0.95', 'quantile-1.0', 'quantile-0.0']
+    kinds = [('mean', 0.), ('quantile', .05), ('std', 0.), ('quantile', .5),
+             ('max', 0.), ('quantile', .95), ('quantile', 1.), ('quantile', 0.)]
+    imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
+    res = oq.postclassical(rates, trt_rlzs, w, imtls, names,
+                           individual_rlzs=True, use_rates=use_rates)
+    hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
+    got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
+    np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
+    for k, (kind, q) in enumerate(kinds):
+        got = res['hcurves-stats'][k].array.reshape(n, L)
+        for i in range(n):
+            mine = post_np.stat_curve(hc[i], kind, q, w[:, None], m,
+                                      use_rates=use_rates)
+            np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
+                                       err_msg='%s R=%d site %d' % (
+                                           names[k], R, i))
+    if R == 4096:
+        with pytest.raises(ValueError):
+            oq.postclassical(np.zeros((1, L, 1), np.float32),
+                             [np.arange(4097)], np.full(4097, 1 / 4097.),
+                             imtls, ['quantile-0.5'])
