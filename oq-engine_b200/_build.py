@@ -4,9 +4,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'oqg.cu')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in
-        ('oqg.cu', 'oqg_gmpe.cuh', 'oqg_geo.cuh', 'oqg_poe.cuh',
-         'oqg_fast.cuh')] + [
+CSRC = os.path.join(HERE, 'csrc')
+DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
+              if f.endswith(('.cu', '.cuh', '.h'))) + [
     os.path.join(HERE, '..', 'include', 'oqg.h')]
 LIB = os.path.join(HERE, 'liboqg.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

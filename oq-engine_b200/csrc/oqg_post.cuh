@@ -406,7 +406,6 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
   extern __shared__ double sm_post[];
   __shared__ double s_red[POST_CTA_TPB / 32];
   __shared__ double s_part[POST_CTA_TPB];
-  __shared__ int s_found;
   unsigned long long *s_key = (unsigned long long *)sm_post;   // [RP]
   double *s_cum = sm_post + RP;                                // [RP]
   const int R = A.R, tid = threadIdx.x;
@@ -503,34 +502,27 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
         __syncthreads();
         const double base = s_part[tid];
         for (int j = tid * per; j < (tid + 1) * per; j++) s_cum[j] += base;
+        __syncthreads();
         sorted = true;
       }
       // numpy.interp(q, cumsum(w sorted), v sorted): the first slot j with
-      // q < cum[j], or the last one
+      // q < cum[j], or the last one when q >= the total weight
       const double q = A.q[s];
-      if (tid == 0) s_found = 0;
-      __syncthreads();
       for (int j = tid; j < R; j += POST_CTA_TPB) {
         const double cum = s_cum[j];
-        const bool here = q < cum && (j == 0 || !(q < s_cum[j - 1]));
+        const bool lt = q < cum;
+        const bool here = lt ? (j == 0 || !(q < s_cum[j - 1])) : j == R - 1;
         if (here) {
           const double vk = post_key_value<POST_CTA_IB>(s_key[j]);
           double res = vk;
-          if (j > 0) {
+          if (lt && j > 0) {
             const double pc = s_cum[j - 1],
                          pv = post_key_value<POST_CTA_IB>(s_key[j - 1]);
             res = pv + (q - pc) * ((vk - pv) / (cum - pc));
           }
           if (A.use_rates) res = 1. - exp(-res);
           A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
-          s_found = 1;
         }
-      }
-      __syncthreads();
-      if (tid == 0 && !s_found) {          // q >= the total weight
-        double res = post_key_value<POST_CTA_IB>(s_key[R - 1]);
-        if (A.use_rates) res = 1. - exp(-res);
-        A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
       }
     }
   }
