@@ -653,6 +653,66 @@ class ContextMaker(object):
         self.update(pmap, ctx, rup_mutex)
         return ~pmap if rup_indep else pmap
 
+    # ------------------------------------------- notebook-level operators
+    def from_srcs(self, srcs, sitecol):
+        """
+        contexts.py:866-881: the context rows of a list of sources on the
+        sites within the integration distance, one array; a source without
+        an `id` gets its position in the list as src_id
+        """
+        ctxs = []
+        for i, src in enumerate(srcs):
+            sid = getattr(src, 'id', -1)
+            if sid == -1:
+                sid = getattr(src, 'src_id', i) \
+                    if isinstance(src, PlanarRuptures) else i
+            ctxs.extend(self.get_ctxs(src, sitecol, src_id=sid))
+        return self.recarray(ctxs)
+
+    def get_poes(self, srcs, sitecol, tom=None, rup_mutex={}):
+        """
+        contexts.py:1145-1153
+        :returns: an array of PoEs of shape (N, L, G), N the sites reached
+        """
+        ctx = self.from_srcs(srcs, sitecol)
+        return self.get_pmap(ctx, tom, rup_mutex).array
+
+    def get_rmap(self, ctx):
+        """
+        contexts.py:1220-1230
+        :returns: a MapArray of rates of shape (N, L, G)
+        """
+        rmap = (~self.get_pmap(ctx)).to_rates()
+        rmap.gid = self.gid
+        rmap.wei = getattr(self, 'wei', None)
+        return rmap
+
+    def get_occ_rates(self, ctxt):
+        """
+        contexts.py:1132-1142: the occurrence rates, from probs_occur[0] for
+        non-parametric ruptures
+        """
+        if numpy.isfinite(ctxt[0].occurrence_rate):
+            return ctxt.occurrence_rate
+        probs = numpy.array([rec.probs_occur[0] for rec in ctxt])
+        return -numpy.log(probs) / self.investigation_time
+
+    def get_4MN(self, ctxs, gsim):
+        """
+        contexts.py:1281-1303 (called by the GmfComputer): mean, sig, tau, phi
+        of one model of this ContextMaker, shape (4, M, N)
+        """
+        for g, gs in enumerate(self.gsims):
+            if gs is gsim or gs == gsim:
+                break
+        else:
+            raise ValueError('%s is not a model of this ContextMaker' % gsim)
+        out = self.get_mean_stds(ctxs, split_by_mag=False)[:, g]
+        if self.truncation_level not in (0, 1E-9, 99.) and \
+                (out[1] == 0.).any():
+            raise ValueError('Total StdDev is zero for %s' % gsim)
+        return out
+
     # -------------------------------------------------------------- fused
     def magdist(self, mags):
         """maximum distance for each magnitude"""

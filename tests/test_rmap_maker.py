@@ -213,3 +213,39 @@ def test_calc_hazard_curves(oq):
         oq.calc_hazard_curves(srcs, sc, imtls, {'Active Shallow Crust':
                                                 gsim_by_trt['Active Shallow Crust']},
                               truncation_level=3., investigation_time=50.)
+
+
+@pytest.mark.gpu
+def test_notebook_operators(oq):
+    """from_srcs / get_poes / get_rmap / get_occ_rates / get_4MN
+    (contexts.py:866-881, 1132-1153, 1220-1230, 1281-1303) against the
+    reference on the three point sources (oracle/make_golden_rmap.py)"""
+    A = np.load(os.path.join(GOLDEN, 'cm_api.npz'))
+    cm, _, srcs = setup(oq)
+    N = len(A['site_lon'])
+    sc = oq.SiteCollection.from_points(
+        A['site_lon'], A['site_lat'], np.zeros(N), dict(vs30=np.full(N, 500.)))
+    ctx = cm.from_srcs(srcs, sc)
+    assert len(ctx) == int(A['nrows'])
+
+    def order(src_id, sids, mag, rrup):
+        return np.lexsort((rrup, np.round(mag, 3), sids, src_id))
+    mine = order(ctx.src_id, ctx.sids, ctx.mag, ctx.rrup)
+    ref = order(A['ctx_src_id'], A['ctx_sids'], A['ctx_mag'], A['ctx_rrup'])
+    assert (ctx.sids[mine] == A['ctx_sids'][ref]).all()
+    assert (ctx.src_id[mine] == A['ctx_src_id'][ref]).all()
+    np.testing.assert_allclose(ctx.rrup[mine], A['ctx_rrup'][ref], rtol=1e-9)
+    np.testing.assert_allclose(cm.get_occ_rates(ctx)[mine],
+                               A['occ_rates'][ref], rtol=1e-12)
+    poes = cm.get_poes(srcs, sc)
+    # the reference folds pne in float32, chunk after chunk: one ulp of 1
+    close(poes, A['poes'], 3e-7)
+    rmap = cm.get_rmap(ctx)
+    assert (rmap.sids == A['rmap_sids']).all() and (rmap.gid == [0, 1]).all()
+    np.testing.assert_allclose(rmap.array, A['rates'], rtol=3e-5, atol=3e-7)
+    out4 = cm.get_4MN([ctx], cm.gsims[1])
+    assert out4.shape == A['out4'].shape
+    np.testing.assert_allclose(out4[:, :, mine], A['out4'][:, :, ref],
+                               rtol=1e-9, atol=1e-12)
+    with pytest.raises(ValueError):
+        cm.get_4MN([ctx], oq.get_gsim('ChiouYoungs2014'))
