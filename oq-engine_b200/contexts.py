@@ -687,6 +687,30 @@ class ContextMaker(object):
         rmap.wei = getattr(self, 'wei', None)
         return rmap
 
+    def max_intensity(self, sitecol1, mags, dists):
+        """
+        contexts.py:1101-1130: the largest median intensity over the models
+        and IMTs for every (magnitude, distance), all the required distances
+        set to the distance, the other rupture parameters to zero and a
+        width of 10 m; one batched evaluation instead of a loop of contexts
+
+        :param sitecol1: a SiteCollection with a single site
+        :returns: an array of GMVs of shape (#mags, #dists)
+        """
+        assert len(sitecol1) == 1, sitecol1
+        nmags, ndists = len(mags), len(dists)
+        ctx = self.new_ctx(nmags * ndists)
+        for dst in self.REQUIRES_DISTANCES | {'rrup'}:
+            ctx[dst] = numpy.tile(numpy.asarray(dists, float), nmags)
+        for par in self.REQUIRES_SITES_PARAMETERS:
+            ctx[par] = sitecol1.array[par][0]
+        ctx['sids'] = sitecol1.sids[0]
+        ctx['mag'] = numpy.repeat(numpy.asarray(mags, float), ndists)
+        if 'width' in ctx.dtype.names:
+            ctx['width'] = .01
+        mean = self.get_mean_stds([ctx])[0]          # (G, M, n)
+        return numpy.exp(mean.max(axis=(0, 1))).reshape(nmags, ndists)
+
     def get_occ_rates(self, ctxt):
         """
         contexts.py:1132-1142: the occurrence rates, from probs_occur[0] for

@@ -249,3 +249,16 @@ def test_notebook_operators(oq):
                                rtol=1e-9, atol=1e-12)
     with pytest.raises(ValueError):
         cm.get_4MN([ctx], oq.get_gsim('ChiouYoungs2014'))
+    # max_intensity with the four NGA-West2 models
+    cm4 = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim(n) for n in ('AbrahamsonEtAl2014', 'ChiouYoungs2014',
+                                  'CampbellBozorgnia2014', 'BooreEtAl2014')],
+        dict(imtls=cm.imtls, truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('100')))
+    sc1 = oq.SiteCollection.from_points(
+        A['site_lon'][:1], A['site_lat'][:1], np.zeros(1), dict(
+            vs30=np.full(1, 500.), vs30measured=np.ones(1, bool),
+            z1pt0=np.full(1, 100.), z2pt5=np.full(1, 5.)))
+    got = cm4.max_intensity(sc1, A['mi_mags'], A['mi_dists'])
+    np.testing.assert_allclose(got, A['maxint'], rtol=1e-9)
