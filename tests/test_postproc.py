@@ -265,3 +265,37 @@ def test_postclassical_many_rlzs_quantiles(oq, R, use_rates):
             oq.postclassical(np.zeros((1, L, 1), np.float32),
                              [np.arange(4097)], np.full(4097, 1 / 4097.),
                              imtls, ['quantile-0.5'])
+
+
+@pytest.mark.gpu
+def test_postclassical_many_rlzs_imt_weights(oq):
+    """IMT-dependent weights with more than 256 realizations (the weight
+    column, its ranks and its sum change with the IMT; one IMT has no weight
+    at all): CTA path with quantiles, streaming path without"""
+    R = 300
+    rng = np.random.default_rng(12)
+    n, m, l1, gt = 6, 3, 4, 10
+    L = m * l1
+    rates = (10 ** rng.uniform(-4, 0.3, (n, L, gt))).astype(np.float32)
+    pick = rng.integers(0, gt, (R, 2))
+    trt_rlzs = [np.where((pick == g).any(axis=1))[0] for g in range(gt)]
+    w = rng.uniform(0.2, 1., (R, m + 1))
+    w[:, 1] = 0.
+    w[:, [0, 2, 3]] /= w[:, [0, 2, 3]].sum(axis=0)
+    imtls = {imt: np.logspace(-2, 0, l1) for imt in ('PGA', 'SA(0.3)',
+                                                     'SA(1.0)')}
+    hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
+    for names, kinds in (
+            (['mean', 'quantile-0.1', 'quantile-0.9', 'std'],
+             [('mean', 0.), ('quantile', .1), ('quantile', .9), ('std', 0.)]),
+            (['std', 'max', 'mean'],
+             [('std', 0.), ('max', 0.), ('mean', 0.)])):
+        res = oq.postclassical(rates, trt_rlzs, w, imtls, names)
+        assert 'hcurves-rlzs' not in res
+        for k, (kind, q) in enumerate(kinds):
+            got = res['hcurves-stats'][k].array.reshape(n, L)
+            assert (got[:, l1:2 * l1] == 0).all()     # no weight: no curve
+            for i in range(n):
+                mine = post_np.stat_curve(hc[i], kind, q, w, m)
+                np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
+                                           err_msg='%s site %d' % (names[k], i))
