@@ -24,7 +24,8 @@ from .postproc import (  # noqa
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
                    mesh_rx_ry0, mesh_dip_strike_width)
-from .disagg import disaggregate, Disaggregator, FarAwayRupture  # noqa
+from .disagg import (disaggregate, Disaggregator, FarAwayRupture,  # noqa
+                     disaggregation, build_bin_edges, lon_lat_bins)
 from .cond_spectra import (  # noqa
     cond_spectra, get_cs_out, BakerJayaram2008)
 from .hazard_curve import calc_hazard_curves, classical  # noqa

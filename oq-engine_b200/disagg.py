@@ -236,3 +236,147 @@ class Disaggregator(object):
                 mat5 = self._disagg6D(imtls, g)[..., 0]  # p = 0
                 out[magi] += mat5.sum(axis=(1, 2)) * rlz_weights[rlz] * mw
         return to_rates(out) if src_mutex else out
+
+
+# ------------------------------------------------------------ bin edges
+KM_TO_DEGREES = 0.0089932          # geo/utils.py:47
+DEGREES_TO_RAD = 0.01745329252     # geo/utils.py:48
+
+
+def uniform_bins(min_value, max_value, bin_width):
+    """disagg.py:299-310: bins of the given width including all values"""
+    return bin_width * numpy.arange(
+        int(numpy.floor(min_value / bin_width)),
+        int(numpy.ceil(max_value / bin_width) + 1))
+
+
+def lon_lat_bins(lon, lat, size_km, coord_bin_width):
+    """disagg.py:63-83: lon, lat bin edges around a site"""
+    import math
+    nbins = numpy.ceil(size_km * KM_TO_DEGREES / coord_bin_width)
+    delta_lon = min(size_km * KM_TO_DEGREES / math.cos(lat * DEGREES_TO_RAD),
+                    180)
+    delta_lat = min(size_km * KM_TO_DEGREES, 90)
+    EPS = .001  # avoid discarding the last edge
+    lon_bins = lon + numpy.arange(-delta_lon, delta_lon + EPS,
+                                  2 * delta_lon / nbins)
+    lat_bins = lat + numpy.arange(-delta_lat, delta_lat + EPS,
+                                  2 * delta_lat / nbins)
+    l1, l2 = lon_bins.min(), lon_bins.max()
+    if l1 * l2 < 0 and abs(l1 - l2) > 180:    # geo/utils.py cross_idl
+        lon_bins %= 360
+    return lon_bins, lat_bins
+
+
+def build_bin_edges(mags, maxdist, site_lon, site_lat, truncation_level,
+                    n_epsilons, mag_bin_width, dist_bin_width,
+                    coord_bin_width, bin_edges={}):
+    """
+    _build_bin_edges, disagg.py:86-142, for one site
+    :returns: [mag, dist, lon, lat, eps] edges
+    """
+    if 'mag' in bin_edges:
+        mag_edges = bin_edges['mag']
+    else:
+        mags = sorted(set(float(m) for m in mags))
+        n1 = int(numpy.floor(mags[0] / mag_bin_width))
+        n2 = int(numpy.ceil(mags[-1] / mag_bin_width))
+        if n2 == n1 or mags[-1] >= round((mag_bin_width * n2), 3):
+            n2 += 1
+        mag_edges = mag_bin_width * numpy.arange(n1, n2 + 1)
+    if 'dist' in bin_edges:
+        dist_edges = bin_edges['dist']
+    elif dist_bin_width:
+        dist_edges = uniform_bins(0, maxdist, dist_bin_width)
+    else:
+        dist_edges = [0, maxdist]
+    if 'lon' in bin_edges or 'lat' in bin_edges:
+        lon_edges, lat_edges = bin_edges['lon'], bin_edges['lat']
+    else:
+        lon_edges, lat_edges = lon_lat_bins(site_lon, site_lat, maxdist,
+                                            coord_bin_width)
+    if 'eps' in bin_edges:
+        eps_edges = bin_edges['eps']
+    else:
+        eps_edges = numpy.linspace(-truncation_level, truncation_level,
+                                   n_epsilons + 1)
+    return [numpy.asarray(e, float) for e in (
+        mag_edges, dist_edges, lon_edges, lat_edges, eps_edges)]
+
+
+def disaggregation(sources, site, imt, iml, gsim_by_trt, truncation_level,
+                   n_epsilons=None, mag_bin_width=None, dist_bin_width=None,
+                   coord_bin_width=None, maximum_distance=None, epsstar=False,
+                   bin_edges={}, investigation_time=None):
+    """
+    The hazardlib function calc.disagg.disaggregation (disagg.py:544-669):
+    the disaggregation matrix of `imt` exceeding `iml` at one site by
+    magnitude, distance, longitude and latitude of the closest point,
+    epsilon and tectonic region type.
+
+    :param sources: point-like sources with a `tectonic_region_type`
+    :param site: a SiteCollection with one site
+    :param gsim_by_trt: tectonic region type -> gsim
+    :param maximum_distance: an IntegrationDistance (the reference's
+        `source_filter.integration_distance`); None = no filter: 1000 km for
+        the contexts, the largest rupture distance for the bins
+    :param investigation_time: the time span of the temporal occurrence
+        model (the reference reads it from the first source)
+    :returns: (mag, dist, lon, lat, eps edges, trts), 6D matrix of
+        probabilities
+    """
+    from .contexts import ContextMaker, IntegrationDistance
+    from .tom import PoissonTOM
+    sources = list(sources)
+    assert len(site) == 1, site
+    trts = sorted(set(src.tectonic_region_type for src in sources))
+    tom = getattr(sources[0], 'temporal_occurrence_model', None)
+    if tom is None:
+        if investigation_time is None:
+            raise ValueError('the sources have no temporal occurrence model: '
+                             'pass the investigation_time')
+        tom = PoissonTOM(investigation_time)
+    param = dict(imtls={str(imt): [iml]}, truncation_level=truncation_level,
+                 investigation_time=tom.time_span)
+    if maximum_distance is not None:
+        param['maximum_distance'] = maximum_distance
+    ctxs, cmaker, mags, dists = {}, {}, set(), []
+    for trt in trts:
+        # NB: like the reference (disagg.py:621, 645, 667) every ContextMaker
+        # gets the models of ALL the tectonic region types and the matrix is
+        # computed with g = 0, i.e. with the model of the first tectonic
+        # region type in sorted order
+        cmaker[trt] = cm = ContextMaker(
+            trt, [gsim_by_trt[t] for t in trts], param)
+        cm.tom = tom
+        ctxs[trt] = cm.from_srcs(
+            [s for s in sources if s.tectonic_region_type == trt], site)
+        mags |= set(ctxs[trt].mag)
+        dists.extend(ctxs[trt].rrup)
+    if not dists:
+        raise FarAwayRupture('No ruptures affecting the site')
+    if maximum_distance is None:
+        maxdist = max(dists)
+    else:   # filters.upper_maxdist
+        maxdist = max(maximum_distance[t][-1][1] for t in maximum_distance)
+    edges = build_bin_edges(
+        mags, maxdist, float(site.array['lon'][0]),
+        float(site.array['lat'][0]), truncation_level, n_epsilons,
+        mag_bin_width, dist_bin_width, coord_bin_width, bin_edges)
+    shape = [len(e) - 1 for e in edges] + [len(trts)]
+    matrix = numpy.zeros(shape)
+    sid = int(site.sids[0])
+    for t, trt in enumerate(trts):
+        if len(ctxs[trt]) == 0:
+            continue
+        dis = Disaggregator(
+            ctxs[trt], site, cmaker[trt],
+            [edges[0], edges[1], {sid: edges[2]}, {sid: edges[3]}, edges[4]],
+            rlzs_by_g=[[0]] * len(trts), epsstar=epsstar)
+        for magi in range(dis.Ma):
+            try:
+                dis.init(magi)
+            except FarAwayRupture:
+                continue
+            matrix[magi, ..., t] = dis._disagg6D({imt: [iml]}, 0)[..., 0, 0]
+    return edges + [trts], 1. - numpy.exp(-matrix)     # to_probs

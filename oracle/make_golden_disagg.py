@@ -197,3 +197,58 @@ def make_disaggregator():
 
 if __name__ == '__main__':
     make_disaggregator()
+
+
+def make_disaggregation():
+    """
+    The top-level hazardlib function calc.disagg.disaggregation
+    (disagg.py:544-669) on three point sources of two tectonic region types
+    at one site, bin edges built from the bin widths
+    -> tests/golden/disaggregation.npz
+    """
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, NodalPlane
+    from openquake.hazardlib.pmf import PMF
+    from openquake.hazardlib.mfd import EvenlyDiscretizedMFD
+    from openquake.hazardlib.scalerel.wc1994 import WC1994
+    from openquake.hazardlib.source import PointSource
+    from openquake.hazardlib.tom import PoissonTOM
+    from openquake.hazardlib.site import Site
+    from openquake.hazardlib.imt import from_string
+    tom = PoissonTOM(50.)
+    SRC = [(0.10, 0.10, [0.02, 0.008, 0.003, 0.001], 30., 60., 90., 6.),
+           (0.45, -0.20, [0.05, 0.01, 0.002], 120., 90., 0., 8.),
+           (-0.30, 0.35, [0.01, 0.006, 0.004, 0.002, 0.001], 250., 45., -90.,
+            10.)]
+    TRT = ['Active Shallow Crust', 'Stable Shallow Crust',
+           'Active Shallow Crust']
+    srcs = []
+    for i, (lon, lat, rates, strike, dip, rake, dep) in enumerate(SRC):
+        src = PointSource(
+            str(i), 'src%d' % i, TRT[i],
+            EvenlyDiscretizedMFD(5.05, 0.3, rates), 2., WC1994(), 1.5, tom,
+            0., 20., Point(lon, lat),
+            PMF([(1., NodalPlane(strike, dip, rake))]), PMF([(1., dep)]))
+        src.id, src.grp_id, src.weight, src.offset = -1, 0, 1., 0
+        srcs.append(src)
+    site = Site(Point(0.05, 0.0), vs30=500., vs30measured=True, z1pt0=100.,
+                z2pt5=5.)
+    gsim_by_trt = {'Active Shallow Crust': valid.gsim('[BooreEtAl2014]'),
+                   'Stable Shallow Crust': valid.gsim('[BooreAtkinson2008]')}
+    out = {}
+    for tag, epsstar in (('', False), ('_star', True)):
+        edges, matrix = disagg.disaggregation(
+            srcs, site, from_string('SA(0.2)'), 0.15, gsim_by_trt, 3.,
+            n_epsilons=6, mag_bin_width=0.5, dist_bin_width=15.,
+            coord_bin_width=0.2, epsstar=epsstar)
+        mag, dist, lon, lat, eps, trts = edges
+        out.update({'mag' + tag: mag, 'dist' + tag: dist, 'lon' + tag: lon[0],
+                    'lat' + tag: lat[0], 'eps' + tag: eps,
+                    'matrix' + tag: matrix})
+        print('disaggregation%s' % tag, matrix.shape, matrix.max(), trts,
+              len(mag), len(dist), len(lon[0]), len(lat[0]))
+    np.savez_compressed(os.path.join(GOLDEN, 'disaggregation.npz'), **out)
+
+
+if __name__ == '__main__':
+    make_disaggregation()

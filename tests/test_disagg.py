@@ -195,3 +195,56 @@ def test_disaggregator_golden(oq):
         dis2.init(0, {'grp_probability': 1., 'src_id': [0], 'weight': [1.]})
     with pytest.raises(oq.FarAwayRupture):
         oq.Disaggregator(ctx[:0], sc, cm, edges, rlzs_by_g=[[0], [1]])
+
+
+# ------------------------------------------------- disaggregation (top level)
+def test_host_bin_edges():
+    """uniform_bins / lon_lat_bins / the magnitude edges of _build_bin_edges
+    (disagg.py:63-142) against the reference's edges of the fixture"""
+    from oq_engine_b200 import disagg as dg
+    T = np.load(os.path.join(GOLDEN, 'disaggregation.npz'))
+    np.testing.assert_allclose(dg.uniform_bins(1, 10, 1.1),
+                               [0., 1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8,
+                                9.9, 11.])
+    maxdist = T['dist'][-1] - 1e-3      # any value in the last 15 km bin
+    edges = dg.build_bin_edges([5.05, 5.35, 6.25], maxdist, 0.05, 0.0, 3., 6,
+                               0.5, 15., 0.2)
+    np.testing.assert_allclose(edges[0], T['mag'], rtol=1e-15)
+    np.testing.assert_allclose(edges[1], T['dist'], rtol=1e-15)
+    np.testing.assert_allclose(edges[4], T['eps'], rtol=1e-15)
+    lon, lat = dg.lon_lat_bins(179.9, 10., 100., 0.4)
+    assert (lon >= 0).all() and lon.max() > 180      # across the date line
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('epsstar', [False, True])
+def test_disaggregation_function_golden(oq, epsstar):
+    """calc.disagg.disaggregation (disagg.py:544-669) on three point sources
+    of two tectonic region types against the reference's edges and matrix"""
+    T = np.load(os.path.join(GOLDEN, 'disaggregation.npz'))
+    tag = '_star' if epsstar else ''
+    TRT = ['Active Shallow Crust', 'Stable Shallow Crust',
+           'Active Shallow Crust']
+    srcs = [oq.PointSource(
+        str(i), lon, lat, oq.EvenlyDiscretizedMFD(5.05, 0.3, rates), 'WC1994',
+        1.5, 0., 20., [(1., strike, dip, rake)], [(1., dep)],
+        tectonic_region_type=TRT[i])
+        for i, (lon, lat, rates, strike, dip, rake, dep) in enumerate(SRC)]
+    sc = oq.SiteCollection.from_points([0.05], [0.0], [0.], dict(vs30=500.))
+    gsim_by_trt = {'Active Shallow Crust': oq.get_gsim('BooreEtAl2014'),
+                   'Stable Shallow Crust': oq.get_gsim('BooreAtkinson2008')}
+    edges, matrix = oq.disaggregation(
+        srcs, sc, 'SA(0.2)', 0.15, gsim_by_trt, 3., n_epsilons=6,
+        mag_bin_width=0.5, dist_bin_width=15., coord_bin_width=0.2,
+        epsstar=epsstar, investigation_time=50.)
+    for got, name in zip(edges, ['mag', 'dist', 'lon', 'lat', 'eps']):
+        np.testing.assert_allclose(got, T[name + tag], rtol=1e-9, atol=1e-12,
+                                   err_msg=name)
+    assert edges[5] == ['Active Shallow Crust', 'Stable Shallow Crust']
+    assert matrix.shape == T['matrix' + tag].shape
+    np.testing.assert_allclose(matrix, T['matrix' + tag], rtol=1e-8,
+                               atol=1e-13)
+    assert (matrix[..., 1] > 0).any()
+    with pytest.raises(ValueError):
+        oq.disaggregation(srcs, sc, 'SA(0.2)', 0.15, gsim_by_trt, 3., 6, 0.5,
+                          15., 0.2)
