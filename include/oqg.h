@@ -393,6 +393,14 @@ int oqg_postclassical(oqg_handle *h, const float *rates_dev, int N, int L,
                       const double *weight_sums, int S, const int32_t *kinds,
                       const double *qs, int use_rates, float *rlz_out_dev,
                       float *stat_out_dev);
+/* calc_mean_rates (hazardlib/calc/mean_rates.py:62-74): the mean rates
+ * out_dev[N][L] (float64) = rates_dev[N][L][Gt] (float32) times the weights
+ * of the gsim columns weights_dev[W][Gt], W = 1 (one weight per column, the
+ * "fast mean") or W = M (IMT-dependent weights, one row per IMT). */
+int oqg_mean_rates(oqg_handle *h, const float *rates_dev, int64_t N, int L,
+                   int Gt, int M, const double *weights_dev, int W,
+                   double *out_dev);
+
 /* compute_hazard_maps (hazardlib/map_array.py:94-141) for K curves:
  * curves_dev [K][M][L1] float32 PoEs, imls_dev [M][L1], poes_dev [P]
  * -> out_dev [K][M][P] float32 intensity levels (0 where the PoE is above

@@ -20,7 +20,7 @@ from .source import (  # noqa
     PointSource, PointSourceBatch, TruncatedGRMFD, EvenlyDiscretizedMFD,
     ArbitraryMFD, point_ruptures_device)
 from .postproc import (  # noqa
-    postclassical, compute_hazard_maps, compute_hmaps)
+    postclassical, compute_hazard_maps, compute_hmaps, calc_mean_rates)
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
                    mesh_rx_ry0, mesh_dip_strike_width)

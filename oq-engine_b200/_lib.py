@@ -97,6 +97,8 @@ def lib():
             H, c_void, C.c_int, C.c_int, C.c_int, C.c_int, c_void, c_void,
             C.c_int, c_void, C.c_int, c_double_p, C.c_int,
             C.POINTER(C.c_int32), c_double_p, C.c_int, c_void, c_void]),
+        'oqg_mean_rates': (C.c_int, [H, c_void, C.c_int64, C.c_int, C.c_int,
+                                     C.c_int, c_void, C.c_int, c_void]),
         'oqg_hazard_maps': (C.c_int, [H, c_void, C.c_int64, C.c_int, C.c_int,
                                       c_void, C.c_int, c_void, c_void]),
         'oqg_mesh_min_distance': (C.c_int, [

@@ -528,6 +528,54 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
   }
 }
 
+// calc_mean_rates, calc/mean_rates.py:62-74: rates[N][L][Gt] (float32) times
+// the weights of the gsim columns, one weight vector or one per IMT;
+// float64 out [N][L]: a pure HBM stream.  A CTA copies the rows of its
+// elements to shared memory as one contiguous, coalesced range, then one
+// thread per element sums its row; the column loop of thread r starts at
+// column r % Gt and wraps, which spreads the rows (stride Gt words) over the
+// banks.  (One thread reading its own row straight from global memory runs
+// at 17 % of the HBM peak for Gt = 32: 32 different lines per request.)
+#define MR_TPB 256
+#define MR_FLOATS 12288           // 48 KB of rows per CTA
+__global__ void __launch_bounds__(MR_TPB)
+k_mean_rates(const float *__restrict__ rates, int64_t n_elems, int L, int L1,
+             int Gt, int rows, const double *__restrict__ weights, int W,
+             double *__restrict__ out) {
+  __shared__ float s_row[MR_FLOATS];
+  const int64_t e0 = blockIdx.x * (int64_t)rows;
+  const int nr = (int)min((int64_t)rows, n_elems - e0);
+  const float *src = rates + e0 * Gt;
+  for (int i = threadIdx.x; i < nr * Gt; i += MR_TPB) s_row[i] = src[i];
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r >= nr) return;
+  const int64_t e = e0 + r;
+  const double *w = weights + (int64_t)(W > 1 ? (int)(e % L) / L1 : 0) * Gt;
+  const float *row = s_row + r * Gt;
+  double acc = 0.;
+  int g = r % Gt;
+  for (int k = 0; k < Gt; k++) {
+    acc = fma((double)row[g], w[g], acc);
+    if (++g == Gt) g = 0;
+  }
+  out[e] = acc;
+}
+
+// more gsim columns than a CTA can stage: one thread per element
+__global__ void __launch_bounds__(256)
+k_mean_rates_direct(const float *__restrict__ rates, int64_t n_elems, int L,
+                    int L1, int Gt, const double *__restrict__ weights, int W,
+                    double *__restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  const double *w = weights + (int64_t)(W > 1 ? (int)(e % L) / L1 : 0) * Gt;
+  const float *row = rates + e * Gt;
+  double acc = 0.;
+  for (int g = 0; g < Gt; g++) acc = fma((double)row[g], w[g], acc);
+  out[e] = acc;
+}
+
 // compute_hazard_maps, map_array.py:94-141: one thread per (curve, imt, poe)
 // curves [K][M][L1] float32, imls [M][L1], out [K][M][P]
 __global__ void k_hazard_maps(const float *__restrict__ curves, int64_t K,

@@ -73,6 +73,44 @@ def compute_hmaps(curvesNML, imtls, poes, device=None):
     return t_o.cpu().numpy()
 
 
+def calc_mean_rates(rmap, gweights, wget, imtls, device=None,
+                    as_tensor=False):
+    """
+    hazardlib/calc/mean_rates.py:62-74: the mean hazard rates, shape
+    (N, M, L1) float64.
+
+    :param rmap: a rates MapArray (N, L, Gt) (or its array, or a CUDA tensor)
+    :param gweights: (Gt,) weights of the gsim columns, or a 2D array of
+        IMT-dependent weights from which `wget(gweights, imt)` selects the
+        (Gt,) weights of each IMT
+    :param wget: None for 1D weights
+    """
+    import torch
+    from .contexts import _dev, _ptr
+    h = _handle(device)
+    arr = rmap if isinstance(rmap, (numpy.ndarray, torch.Tensor)) \
+        else rmap.array
+    N, L, Gt = arr.shape
+    M = len(imtls)
+    if L % M:
+        raise ValueError('%d levels for %d IMTs' % (L, M))
+    gweights = numpy.asarray(gweights, float)
+    if gweights.ndim == 1:
+        w = gweights[None]
+    else:
+        w = numpy.array([numpy.asarray(wget(gweights, imt), float)
+                         for imt in imtls])
+    if w.shape[1] != Gt:
+        raise ValueError('%d weights for %d gsim columns' % (w.shape[1], Gt))
+    t_r = _dev(arr, h.device, torch.float32)
+    t_w = _dev(numpy.ascontiguousarray(w), h.device)
+    out = torch.empty((N, M, L // M), dtype=torch.float64,
+                      device='cuda:%d' % h.device)
+    h.call('oqg_mean_rates', _ptr(t_r), N, L, Gt, M, _ptr(t_w), len(w),
+           _ptr(out))
+    return out if as_tensor else out.cpu().numpy()
+
+
 def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
                   individual_rlzs=False, poes=(), use_rates=False,
                   device=None):

@@ -299,3 +299,28 @@ def test_postclassical_many_rlzs_imt_weights(oq):
                 mine = post_np.stat_curve(hc[i], kind, q, w, m)
                 np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
                                            err_msg='%s site %d' % (names[k], i))
+
+
+@pytest.mark.gpu
+def test_calc_mean_rates_golden(oq):
+    """calc_mean_rates (calc/mean_rates.py:62-74) against the reference: one
+    weight per gsim column and IMT-dependent weights"""
+    imts = list(IMTLS)
+    got = oq.calc_mean_rates(rmap_of(oq), D['gw1'], None, IMTLS)
+    assert got.shape == (N, M, L1) and got.dtype == np.float64
+    np.testing.assert_allclose(got, D['mean_rates_w1'], rtol=1e-13)
+    got = oq.calc_mean_rates(D['rates'].astype(np.float32), D['gwim'],
+                             lambda w, imt: w[:, imts.index(imt)], IMTLS)
+    np.testing.assert_allclose(got, D['mean_rates_wim'], rtol=1e-13)
+    assert (got[:, 1] == 0).all()
+    with pytest.raises(ValueError):
+        oq.calc_mean_rates(D['rates'], D['gw1'][:-1], None, IMTLS)
+    # other numbers of gsim columns (rows per CTA, the direct kernel)
+    rng = np.random.default_rng(5)
+    for gt in (1, 7, 32, 100, 500):
+        r = rng.uniform(0, 1e-2, (301, 6, gt)).astype(np.float32)
+        w = rng.uniform(0.1, 1., gt)
+        got = oq.calc_mean_rates(r, w, None, {'PGA': [1, 2, 3],
+                                              'SA(1.0)': [1, 2, 3]})
+        np.testing.assert_allclose(got.reshape(301, 6), r.astype(float) @ w,
+                                   rtol=1e-13)

@@ -63,6 +63,12 @@ def main():
     def hmaps():
         h.call('oqg_hazard_maps', _ptr(curves), K, M, L1, _ptr(t_i), P,
                _ptr(t_p), _ptr(t_o))
+    t_gw = _dev(rng.uniform(0.1, 1., (1, Gt)), 0)
+    t_mr = torch.empty((N, L), dtype=torch.float64, device='cuda')
+
+    def mean_rates():
+        h.call('oqg_mean_rates', _ptr(rates), N, L, Gt, M, _ptr(t_gw), 1,
+               _ptr(t_mr))
     try:
         peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
         src = 'MEASURED_PEAKS.json'
@@ -70,7 +76,8 @@ def main():
         peak, src = 6650., 'fallback'
     for name, fn, nbytes in (
             ('k_postclassical', post, 4. * N * L * (Gt + R + S)),
-            ('k_hazard_maps', hmaps, 4. * K * M * (L1 + P))):
+            ('k_hazard_maps', hmaps, 4. * K * M * (L1 + P)),
+            ('k_mean_rates', mean_rates, 4. * N * L * Gt + 8. * N * L)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
