@@ -9,9 +9,19 @@
 // (hazardlib/map_array.py:94-141), driven by postclassical
 // (calculators/classical.py:258-325).
 //
-// HBM-bound: one thread per (site, level) reads Gt rates and writes R + S
-// float32 values; the realization values of the thread live in local memory
-// (R <= OQG_RMAX doubles), sorted once for all the quantiles.
+// Kernels (oqg_postclassical picks one):
+//   k_postclassical_reg     R <= 32: keys sorted in registers; 32 < R <= 256:
+//                           the same network on keys in shared memory
+//   k_postclassical_cta     quantiles of 256 < R <= 4096 realizations: one CTA
+//                           per (site, level), cooperative sort and scan
+//   k_postclassical_stream  no quantile and R > 256 (or tables that do not
+//                           fit): one pass, nothing kept per realization
+//   k_postclassical         generic fallback for R <= 256 when the tables of
+//                           the register path do not fit in shared memory:
+//                           one thread per (site, level), values in local
+//                           memory, insertion sort
+//   k_mean_rates            calc_mean_rates (calc/mean_rates.py:62-74)
+//   k_hazard_maps           compute_hazard_maps
 #pragma once
 #include <math.h>
 #include "../../include/oqg.h"
