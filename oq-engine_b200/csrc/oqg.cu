@@ -1477,8 +1477,22 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
       const unsigned grid_c = (unsigned)std::min<int64_t>(
           A.n_elems, (int64_t)sms * per_sm);
-      k_postclassical_cta<<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B, RPc);
-      h->launches++;
+      if (B.rlz_out) {
+        // the realization curves are written by the streaming kernel, whose
+        // consecutive threads write consecutive (site, level) elements: a
+        // CTA per element would scatter 4-byte writes n_elems apart
+        PostRegArgs C = B;
+        C.stat_out = nullptr;
+        C.S = 0;
+        k_postclassical_stream<<<(unsigned)((A.n_elems + 127) / 128), 128, 0,
+                                 h->stream>>>(C);
+        h->launches++;
+        B.rlz_out = nullptr;
+      }
+      if (B.stat_out && B.S) {
+        k_postclassical_cta<<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B, RPc);
+        h->launches++;
+      }
       CK(cudaGetLastError());
       return 0;
     }
