@@ -1468,9 +1468,15 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
       int RPc = 512;
       while (RPc < R) RPc <<= 1;
       const size_t smem_c = (size_t)RPc * 16;
-      CK(cudaFuncSetAttribute(k_postclassical_cta,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)smem_c));
+#define CTA_ATTR(per)                                                         \
+  CK(cudaFuncSetAttribute(k_postclassical_cta<per>,                           \
+                          cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                          (int)smem_c))
+      if (RPc == 512) CTA_ATTR(2);
+      else if (RPc == 1024) CTA_ATTR(4);
+      else if (RPc == 2048) CTA_ATTR(8);
+      else CTA_ATTR(16);
+#undef CTA_ATTR
       const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(
           8, (200 * 1024) / (smem_c + 4096)));
       int sms = 148;
@@ -1490,7 +1496,14 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
         B.rlz_out = nullptr;
       }
       if (B.stat_out && B.S) {
-        k_postclassical_cta<<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B, RPc);
+        if (RPc == 512)
+          k_postclassical_cta<2><<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B);
+        else if (RPc == 1024)
+          k_postclassical_cta<4><<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B);
+        else if (RPc == 2048)
+          k_postclassical_cta<8><<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B);
+        else
+          k_postclassical_cta<16><<<grid_c, POST_CTA_TPB, smem_c, h->stream>>>(B);
         h->launches++;
       }
       CK(cudaGetLastError());

@@ -411,15 +411,47 @@ __device__ __forceinline__ double post_block_sum(double v, double *s_red,
   return r;
 }
 
+// One compare-exchange stage of the bitonic network on the keys of a thread
+// (sort position i = base + q): the element keeps the minimum when it is
+// the lower one of its pair in an ascending run (or the upper one in a
+// descending run)
+__device__ __forceinline__ unsigned long long cta_pick(
+    unsigned long long mine, unsigned long long other, int i, int j, int k) {
+  const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+  return keep_min ? (mine < other ? mine : other)
+                  : (mine > other ? mine : other);
+}
+
+template <int PER, int J>
+__device__ __forceinline__ void cta_reg_stage(unsigned long long (&key)[PER],
+                                              int base, int k) {
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int p = q ^ J;
+    if (p > q) {
+      const unsigned long long a = key[q], b = key[p];
+      const bool sw = (a > b) == (((base + q) & k) == 0);
+      key[q] = sw ? b : a;
+      key[p] = sw ? a : b;
+    }
+  }
+}
+
+// PER = RP / 256 keys per thread, thread t owning the sort positions
+// t PER .. t PER + PER - 1: the stages with j < PER exchange registers, those
+// with j < 32 PER exchange between the lanes of a warp (shuffles), only the
+// six stages with j >= 32 PER per sort go through shared memory.
+template <int PER>
 __global__ void __launch_bounds__(POST_CTA_TPB)
-k_postclassical_cta(const PostRegArgs A, int RP) {
+k_postclassical_cta(const PostRegArgs A) {
+  constexpr int RP = PER * POST_CTA_TPB;
   extern __shared__ double sm_post[];
   __shared__ double s_red[POST_CTA_TPB / 32];
   __shared__ double s_part[POST_CTA_TPB];
   unsigned long long *s_key = (unsigned long long *)sm_post;   // [RP]
   double *s_cum = sm_post + RP;                                // [RP]
   const int R = A.R, tid = threadIdx.x;
-  const int per = RP / POST_CTA_TPB;      // RP >= 512: a multiple of 256
+  constexpr int per = PER;
   for (int64_t e = blockIdx.x; e < A.n_elems; e += gridDim.x) {
     const int l = (int)(e % A.L);
     const int wcol = A.W > 1 ? l / A.L1 : 0;
@@ -433,12 +465,13 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
     v0 = 1. - exp(-v0);
     if (A.use_rates) v0 = to_rate(v0);
     double sw1 = 0., sw2 = 0., vmax = 0.;
+    unsigned long long key[PER];
     __syncthreads();                       // the previous element is done
-    for (int r = tid; r < RP; r += POST_CTA_TPB) {
-      if (r >= R) {
-        s_key[r] = ~0ull;                  // padding sorts last
-        continue;
-      }
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int r = tid + q * POST_CTA_TPB;
+      key[q] = ~0ull;                      // padding sorts last
+      if (r >= R) continue;
       double x = 0.;
       for (int k = A.r_off[r]; k < A.r_off[r + 1]; k++)
         x += (double)row[A.r_gs[k]];
@@ -449,7 +482,7 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
       const double d = v - v0, wr = w[r];
       sw1 = fma(wr, d, sw1);
       sw2 = fma(wr * d, d, sw2);
-      s_key[r] = post_key<POST_CTA_IB>(v, rk[r], r);
+      key[q] = post_key<POST_CTA_IB>(v, rk[r], r);
     }
     if (!A.stat_out || A.S == 0) continue;
     sw1 = post_block_sum(sw1, s_red, false);
@@ -474,19 +507,44 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
         continue;
       }
       if (!sorted) {
-        __syncthreads();
-        for (int k = 2; k <= RP; k <<= 1)
+        const int base = tid * PER;
+#pragma unroll 1
+        for (int k = 2; k <= RP; k <<= 1) {
+#pragma unroll 1
           for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < RP / 2; t += POST_CTA_TPB) {
-              const int i = 2 * t - (t & (j - 1)), p = i + j;
-              const unsigned long long a = s_key[i], b = s_key[p];
-              if ((a > b) == ((i & k) == 0)) {
-                s_key[i] = b;
-                s_key[p] = a;
+            if (j >= 32 * PER) {
+              // partner in another warp: through shared memory, [q][thread]
+              __syncthreads();
+#pragma unroll
+              for (int q = 0; q < PER; q++) s_key[q * POST_CTA_TPB + tid] = key[q];
+              __syncthreads();
+              const int pt = tid ^ (j / PER);
+#pragma unroll
+              for (int q = 0; q < PER; q++)
+                key[q] = cta_pick(key[q], s_key[q * POST_CTA_TPB + pt],
+                                  base + q, j, k);
+            } else if (j >= PER) {
+              const int lm = j / PER;      // partner lane
+#pragma unroll
+              for (int q = 0; q < PER; q++) {
+                const unsigned long long other =
+                    __shfl_xor_sync(0xffffffffu, key[q], lm);
+                key[q] = cta_pick(key[q], other, base + q, j, k);
+              }
+            } else {
+              switch (j) {
+                case 8: if (PER > 8) cta_reg_stage<PER, (PER > 8 ? 8 : 1)>(key, base, k); break;
+                case 4: if (PER > 4) cta_reg_stage<PER, (PER > 4 ? 4 : 1)>(key, base, k); break;
+                case 2: if (PER > 2) cta_reg_stage<PER, (PER > 2 ? 2 : 1)>(key, base, k); break;
+                default: cta_reg_stage<PER, 1>(key, base, k); break;
               }
             }
-            __syncthreads();
           }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; q++) s_key[base + q] = key[q];
+        __syncthreads();
         // inclusive scan of the weights in sorted order: `per` consecutive
         // slots per thread, then the partial sums of the threads
         double acc = 0.;
@@ -510,8 +568,8 @@ k_postclassical_cta(const PostRegArgs A, int RP) {
           }
         }
         __syncthreads();
-        const double base = s_part[tid];
-        for (int j = tid * per; j < (tid + 1) * per; j++) s_cum[j] += base;
+        const double before = s_part[tid];
+        for (int j = tid * per; j < (tid + 1) * per; j++) s_cum[j] += before;
         __syncthreads();
         sorted = true;
       }
