@@ -387,9 +387,9 @@ k_postclassical_stream(const PostRegArgs A) {
 // (sampled logic trees).  One CTA of 256 threads per (site, level), looping
 // over the elements: the realization values are packed into sort keys
 //     [ bits 63..24 of the float64 value | weight rank (12) | realization (12) ]
-// in shared memory, sorted by a cooperative bitonic network (one barrier per
-// stage), the weights in sorted order are scanned by the CTA and every
-// quantile is found by the thread whose slot brackets it.  Values are
+// sorted by a cooperative bitonic network (keys in registers, see
+// k_postclassical_cta), the weights in sorted order are scanned by the CTA
+// and every quantile is found by the thread whose slot brackets it.  Values are
 // compared, and used in the interpolation, to 2^-28 relative (the output is
 // float32); ties are broken by the weight as in the other paths.
 #define OQG_RMAX_CTA 4096
