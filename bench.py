@@ -232,6 +232,8 @@ def run_ours(args):
     sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
                                        sites['depth'], sites)
     h = cm.handle()
+    if args.fused_subs or args.plain_table:
+        h.call('oqg_set_fused_config', args.fused_subs, int(args.plain_table))
     dev = 'cuda:%d' % local
     L_ = oq._lib.lib()
     # ---- device resident inputs
@@ -452,6 +454,10 @@ def main():
     ap.add_argument('--cpu-ruptures', type=int, default=768,
                     help='ruptures of the bounded CPU sample (x all sites)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--fused-subs', type=int, default=0,
+                    help='A/B: cap of the sub-CTAs per CTA (0 = automatic)')
+    ap.add_argument('--plain-table', action='store_true',
+                    help='A/B: one work item per CTA, unreplicated PoE table')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -418,6 +418,15 @@ int oqg_hazard_maps(oqg_handle *h, const float *curves_dev, int64_t K, int M,
 int oqg_set_exact_poe(oqg_handle *h, int on);
 int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err);
 
+/* Shape of the fused kernel's CTAs (tuning / A-B measurements; the default
+ * 0, 0 is automatic).  subs = 1..4 caps the number of (site tile x rupture
+ * chunk) work items that share one CTA and its 8-fold replicated,
+ * bank-conflict-free PoE table; plain_table != 0 forces the one-work-item
+ * CTAs with the unreplicated table.  oqg_last_fused_subs returns what the
+ * last launch used. */
+int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table);
+int oqg_last_fused_subs(oqg_handle *h);
+
 /* number of kernels launched by this handle so far (for bench accounting) */
 unsigned long long oqg_launch_count(oqg_handle *h);
 /* average device milliseconds of the last fused kernel launches measured

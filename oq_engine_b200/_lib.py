@@ -125,6 +125,8 @@ def lib():
                               C.c_int, c_void]),
         'oqg_set_exact_poe': (C.c_int, [H, C.c_int]),
         'oqg_poe_table_info': (C.c_int, [H, C.POINTER(C.c_int), c_double_p]),
+        'oqg_set_fused_config': (C.c_int, [H, C.c_int, C.c_int]),
+        'oqg_last_fused_subs': (C.c_int, [H]),
         'oqg_launch_count': (C.c_ulonglong, [H]),
         'oqg_last_fused_ms': (C.c_int, [H, C.POINTER(C.c_float), C.c_int]),
         'oqg_measure_fp64_peak': (C.c_int, [H, c_double_p]),

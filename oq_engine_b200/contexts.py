@@ -14,6 +14,7 @@ device buffers.  There is no CPU fallback: an unsupported GMPE, a missing
 library or a missing CUDA device raises.
 """
 import os
+import ast
 import ctypes
 import numpy
 from scipy.special import ndtr
@@ -93,14 +94,24 @@ class IntegrationDistance(dict):
             self['default'] = [(3, 0), (6, 150), (10, 600)]
             return self
         if isinstance(value, str):
-            value = eval(value, {}, {})   # '300' or '[(4., 50), (8., 200.)]'
+            # '300' or '[(4., 50), (8., 200.)]' or a dict literal, parsed
+            # like the reference's floatdict (literal_eval, never eval)
+            value = ast.literal_eval(value)
         if isinstance(value, dict):
             items = value
         else:
             items = {'default': value}
         for trt, val in items.items():
             if isinstance(val, (list, tuple)):
-                self[trt] = sorted(set(tuple(it) for it in val))
+                pairs = [tuple(it) for it in val]
+                if len(set(pairs)) < len(pairs):
+                    raise ValueError('Found duplicates in %s' % pairs)
+                if pairs != sorted(pairs):
+                    raise ValueError('%s is not ordered' % pairs)
+                for mag, dist in pairs:
+                    if mag < MINMAG or mag > MAXMAG:
+                        raise ValueError('Invalid magnitude %s' % mag)
+                self[trt] = pairs
             else:
                 assert val >= 0, val
                 self[trt] = [(MINMAG, val), (MAXMAG, val)]
@@ -112,13 +123,16 @@ class IntegrationDistance(dict):
 
 
 class magdepdist(object):
-    """Linear interpolation mag -> distance (calc/filters.py magdepdist)"""
+    """Linear interpolation mag -> distance (calc/filters.py:183-190:
+    interp1d(bounds_error=False, fill_value=0.)): the distance is ZERO for a
+    magnitude outside the pairs, so such ruptures are dropped by the
+    `rrup < magdist` filter, as in the reference"""
     def __init__(self, pairs):
         self.mags = numpy.array([m for m, d in pairs], float)
         self.dists = numpy.array([d for m, d in pairs], float)
 
     def __call__(self, mag):
-        return numpy.interp(mag, self.mags, self.dists)
+        return numpy.interp(mag, self.mags, self.dists, left=0., right=0.)
 
 
 def _interp(param, name, trt):
@@ -369,7 +383,12 @@ class ContextMaker(object):
     def handle(self):
         """The configured device handle (created lazily in the worker
         process, like init_monitoring in the reference)"""
-        h = get_handle(_device_index(self.device))
+        return self.configure(get_handle(_device_index(self.device)))
+
+    def configure(self, h):
+        """Load the models, levels and IMT mask of this ContextMaker into the
+        oqg handle `h` (a _lib.Handle; any number of handles may exist on a
+        device, each with its own stream)"""
         if getattr(h, 'owner', None) is not self:
             arr, coeffs = self._structs
             h.call('oqg_set_gsims', self.G, arr, self.M,

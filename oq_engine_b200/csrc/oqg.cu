@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 #include "../../include/oqg.h"
 #include "oqg_gmpe.cuh"
@@ -57,6 +58,7 @@ using namespace oqg;
 #define MINB 4         // CTAs per SM the fused kernel is compiled for
 #endif
 #define MAXPLANES 6
+#define OQG_GRID_Y 65535   // CUDA limit of gridDim.y: larger extents are launched in chunks
 
 __constant__ double c_coef[OQG_MAX_SLOTS][OQG_KMAX];
 // [0, MAX_LEVELS): loglevels[M][L1]; [MAX_LEVELS, 2 MAX_LEVELS): the same by
@@ -90,12 +92,14 @@ struct oqg_handle {
   double ptab_err = 0., xscale = 0.;
   int *flag_dev = nullptr;
   cudaEvent_t ev[2 * OQG_MAX_G + 2];
+  cudaEvent_t const_ev = nullptr;   // after the last launch reading the __constant__ tables
   int n_fused_ev = 0;
   int sm_count = 148;
+  int fused_cfg[2] = {0, 0};   // oqg_set_fused_config
+  int last_subs = 1;
 };
 
 static std::string g_create_err;
-static oqg_handle *g_const_owner = nullptr;
 
 static int fail(oqg_handle *h, const std::string &msg) {
   if (h) h->err = msg; else g_create_err = msg;
@@ -119,8 +123,29 @@ static int reserve(oqg_handle *h, Buf &b, size_t bytes) {
   return 0;
 }
 
+// ---- ownership of the __constant__ tables -------------------------------
+// The coefficient rows, levels, model descriptors and the IMT mask live in
+// __constant__ memory (the fused kernel reads them as instruction operands),
+// of which a device has ONE copy shared by all the handles of the process.
+// A handle therefore OWNS the tables of its device while its kernels use
+// them: ConstGuard, held by every entry point that launches such kernels,
+//   * serialises the host threads that enqueue work using the tables,
+//   * when the owner changes, makes the new owner's stream wait for the
+//     event recorded after the previous owner's last such launch before it
+//     overwrites the tables (stream-ordered: no host synchronisation), and
+//   * records that event for this handle when the entry point returns.
+// Two handles on one device with different models on different streams thus
+// interleave correctly (tests/test_gpu_parity.py::test_two_handles_two_streams);
+// they do not run concurrently.
+#define OQG_MAX_DEVICES 64
+static std::mutex g_const_mu;
+static oqg_handle *g_const_owner[OQG_MAX_DEVICES];
+
 static int upload_const(oqg_handle *h) {
-  if (!h->const_dirty && g_const_owner == h) return 0;
+  oqg_handle *&owner = g_const_owner[h->device];
+  if (!h->const_dirty && owner == h) return 0;
+  if (owner && owner != h)
+    CK(cudaStreamWaitEvent(h->stream, owner->const_ev, 0));
   if (h->G && !h->coef.empty()) {
     CK(cudaMemcpyToSymbolAsync(c_coef, h->coef.data(),
                                h->coef.size() * sizeof(double), 0,
@@ -144,9 +169,21 @@ static int upload_const(oqg_handle *h) {
   // the host vectors must stay alive until the copies ran: they are members
   // and only replaced by set_* calls, which synchronise first
   h->const_dirty = false;
-  g_const_owner = h;
+  owner = h;
   return 0;
 }
+
+struct ConstGuard {
+  oqg_handle *h;
+  std::unique_lock<std::mutex> lock;
+  explicit ConstGuard(oqg_handle *h_) : h(h_), lock(g_const_mu) {}
+  // uploads the tables of h if it does not own them (or they changed)
+  int acquire() { return upload_const(h); }
+  ~ConstGuard() {
+    // everything enqueued so far on the handle's stream may read the tables
+    cudaEventRecord(h->const_ev, h->stream);
+  }
+};
 
 // ----------------------------------------------------------- prep kernels
 __global__ void k_prep_ruptures(const double *__restrict__ planar,
@@ -404,8 +441,8 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
                          const double *__restrict__ rate,
                          const double *__restrict__ probs, int K, double itime,
                          int rates_mode,
-                         const double *__restrict__ weights) {
-  int s = blockIdx.y;
+                         const double *__restrict__ weights, int y0) {
+  int s = blockIdx.y + y0;   // y0: the host launches grid.y in chunks
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= LG) return;
   int64_t a = seg[s], b = seg[s + 1];
@@ -445,21 +482,20 @@ __global__ void k_update(float *__restrict__ map, int N, int LG, int G,
 // 16-byte load per evaluation: lanes with the same node broadcast, the lanes
 // of a quarter warp (neighbouring sites) hit nodes less than 8 apart, i.e.
 // different banks.
+//
+// Shared-memory bandwidth is what bounds the evaluation: an LDS.128 whose 32
+// lanes read 32 different nodes is served quarter warp by quarter warp, and
+// the 8 lanes of a quarter conflict when their nodes fall into the same
+// 16-byte bank group (k mod 8): 8.3 wavefronts per load were measured instead
+// of the 4 that deliver 512 bytes.  With REP = 8 copies of the table (copy r
+// of node k at float4 index 8 k + r, lane i reads copy i mod 8) every lane of
+// a quarter warp has its own bank group and the load is conflict free.  A
+// 32 KB table per CTA only pays when one CTA fills the SM, hence the
+// "sub-CTAs" of k_fused: SUBS independent (site tile x rupture chunk) work
+// items of 32 * nw threads each share one CTA, one table and nothing else,
+// and synchronise among themselves with named barriers.
 #define PT_DEG 3
 #define PT_STRIDE 4       // floats per node: one LDS.128
-#ifndef PT_SOA
-#define PT_SOA 0
-#endif
-#ifndef PT_REP
-#define PT_REP 1          // copies of the table in shared memory (copy r of
-                          // node k at float4 index k * PT_REP + r, lane i
-                          // reads copy i % PT_REP).  Measured on B200: 2, 4
-                          // and 8 copies are all SLOWER than 1 (cfg3, 30k
-                          // ruptures: 51.7 / 54.3 / 55.9 / 65.8 ms for the
-                          // BSSA14 launch) although ncu attributes 4 excess
-                          // wavefronts per LDS.128 to bank conflicts: the
-                          // larger table costs residency (2-3 CTAs per SM)
-#endif
 #define PT_MAXNODES 512
 #ifndef FLUSH_TILES
 #define FLUSH_TILES 8
@@ -485,11 +521,12 @@ struct FusedArgs {
   int nlc;                // level chunks per IMT
   int lpc;                // levels per chunk (<= NL)
   int nunits;             // M * nlc
+  int nw;                 // warps (units) per sub-CTA
+  int subs;               // sub-CTAs per CTA
   int rup_per_chunk;
+  int ntiles;             // site tiles of 32 sites
   int dmask;              // distances to compute
   int clampmask;          // distances clamped by minimum_distance
-  int nplanes;
-  int plane_of[OQG_NDIST];
   int count_pairs;
   int sorted;             // the levels of every IMT are increasing
   double mindist, itime, phi_b, inv_norm, tl, xscale;
@@ -499,26 +536,16 @@ struct FusedArgs {
 // that tab32 + bits(k + 2^23) * 16 is the address of node k.  12 instructions
 // per evaluation with the DFMA of x and the FFMA into the accumulator: F2F,
 // FADD.SAT, FFMA (round), FADD, FFMA (u), IMAD (address), LDS.128, 3 FFMA.
+template <int REP>
 __device__ __forceinline__ float poe_table(unsigned tab32, float nm1,
                                            double x64) {
   float x = __saturatef((float)x64);    // NaN -> 0 -> poe 0
   float y = fmaf(x, nm1, 8388608.f);    // 2^23: round to nearest integer
   float u = fmaf(x, nm1, -(y - 8388608.f));
   float c0, c1, c2, c3;
-#if PT_SOA
-  // experiment (default off): one array per coefficient, [4][PT_MAXNODES],
-  // four LDS.32 instead of one LDS.128.  Measured slower on B200 (cfg3, 30k
-  // ruptures: BSSA14 51.8 vs 48.9 ms, CY14 74.3 vs 71.5 ms)
-  unsigned a = tab32 + __float_as_uint(y) * 4;
-  asm("ld.shared.f32 %0, [%1];" : "=f"(c0) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+2048];" : "=f"(c1) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+4096];" : "=f"(c2) : "r"(a));
-  asm("ld.shared.f32 %0, [%1+6144];" : "=f"(c3) : "r"(a));
-#else
-  unsigned a = tab32 + __float_as_uint(y) * (PT_STRIDE * 4 * PT_REP);
+  unsigned a = tab32 + __float_as_uint(y) * (PT_STRIDE * 4 * REP);
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
       : "=f"(c0), "=f"(c1), "=f"(c2), "=f"(c3) : "r"(a));
-#endif
   float p = fmaf(c3, u, c2);
   p = fmaf(p, u, c1);
   return __saturatef(fmaf(p, u, c0));
@@ -540,8 +567,48 @@ __device__ __forceinline__ T ld_soa(const double *base, int stride) {
   return v;
 }
 
-template <int F, bool NEGBIN, bool FAST>
-__global__ void __launch_bounds__(32 * NWMAX, MINB)
+// Distances a family may read, as a compile-time superset of
+// required_distances() (+ rrup for the filter, repi under rhypo): the planes
+// of s_dist and every shared-memory offset of the fused kernel are then
+// compile-time constants (immediates in the LDS / STS instead of address
+// registers and IMADs)
+template <int F> struct DistMask {
+  static constexpr int value =
+      F == OQG_BSSA14 || F == OQG_BA08 ? (1 << OQG_RRUP) | (1 << OQG_RJB)
+      : F == OQG_CY14 || F == OQG_CB14
+          ? (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_RX)
+      : F == OQG_ASK14
+          ? (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_RX) | (1 << OQG_RY0)
+      : F == OQG_AB06 ? (1 << OQG_RRUP)
+      : (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_REPI) | (1 << OQG_RHYPO);
+};
+__host__ __device__ constexpr int popc_below(int mask, int k) {   // planes before distance k
+  int n = 0;
+  for (int j = 0; j < k; j++) n += (mask >> j) & 1;
+  return n;
+}
+
+// shared memory of one sub-CTA, in doubles (the layout of k_fused)
+template <int F, bool NEGBIN, bool FAST> struct FusedLayout {
+  typedef Fast<F> FF;
+  static constexpr int QW = FF::HAS_Q ? sizeof(typename FF::Q) / 8 : 0;
+  static constexpr int PW = FF::HAS_P ? sizeof(typename FF::P) / 8 : 0;
+  static constexpr int DM = DistMask<F>::value;
+  static constexpr int NPL = popc_below(DM, OQG_NDIST);
+  static constexpr int RUP = 0;                          // [NF_RUP][RT]
+  static constexpr int DIST = RUP + NF_RUP * RT;         // [NPL][RT][32]
+  static constexpr int SITE = DIST + NPL * RT * 32;      // [NF_SITE][32]
+  static constexpr int SQ = SITE + NF_SITE * 32;         // [NWMAX + 1][RT][QW]
+  static constexpr int SP = SQ + (NWMAX + 1) * RT * QW;  // [PW][RT][32]
+  static constexpr int PROBS = SP + PW * RT * 32;        // [RT][OQG_MAX_OCC]
+  static constexpr int VALID = PROBS + (NEGBIN ? RT * OQG_MAX_OCC : 0);  // u32 [RT]
+  static constexpr int HI = VALID + RT / 2;              // f32 [NL - NLR][32 NWMAX]
+  static constexpr int SIZE =
+      (HI + (FAST ? (NL - NLR) * 32 * NWMAX / 2 : 0) + 1) / 2 * 2;
+};
+
+template <int F, bool NEGBIN, bool FAST, int SUBS, int REP>
+__global__ void __launch_bounds__(32 * NWMAX * SUBS, SUBS == 1 ? MINB : 1)
 k_fused(const FusedArgs A) {
   typedef Fast<F> FF;
   typedef typename FF::C CT;
@@ -550,21 +617,40 @@ k_fused(const FusedArgs A) {
   typedef typename FF::P PT;
   constexpr int QW = FF::HAS_Q ? sizeof(QT) / 8 : 0;   // doubles
   constexpr int PW = FF::HAS_P ? sizeof(PT) / 8 : 0;
+  typedef FusedLayout<F, NEGBIN, FAST> LY;
+  constexpr int DM = LY::DM;
   extern __shared__ __align__(16) double smem[];
-  const int nw = blockDim.x >> 5;
-  float *s_tab = (float *)smem;           // [nodes][PT_REP][PT_STRIDE]
-  double *s_rup = smem + (FAST ? (PT_SOA ? PT_MAXNODES : A.pt_nodes * PT_REP) * PT_STRIDE / 2 : 0);  // [NF_RUP][RT]
-  double *s_dist = s_rup + NF_RUP * RT;            // [nplanes][RT][32]
-  double *s_site = s_dist + A.nplanes * RT * 32;   // [NF_SITE][32]
-  double *s_q = s_site + NF_SITE * 32;             // [nw + 1][RT][QW]
-  double *s_p = s_q + (nw + 1) * RT * QW;          // [PW][RT][32]
-  double *s_probs = s_p + PW * RT * 32;            // [RT][K]
-  unsigned *s_valid = (unsigned *)(s_probs + (NEGBIN ? RT * A.K : 0));
-  float *s_hi = (float *)(s_valid + RT) + threadIdx.x;  // [NL - NLR][threads]
-  const int hs = blockDim.x;
+  // a CTA holds `subs` sub-CTAs of nw warps each (subs = 1 when SUBS == 1):
+  // sub-CTA `sub` works on site tile blockIdx.x * subs + sub and shares only
+  // the read-only tables with the others.  Layout: the sub-CTA regions
+  // (compile-time offsets, FusedLayout), then the PoE table.
+  const int nw = A.nw;
+  const int tb = nw << 5;                          // threads of a sub-CTA
+  const int wall = threadIdx.x >> 5;
+  const int sub = SUBS == 1 ? 0 : wall / nw;
+  const int warp = wall - sub * nw;
+  const int lane = threadIdx.x & 31;
+  const int tid = (warp << 5) | lane;
+  const int tile = SUBS == 1 ? blockIdx.x : blockIdx.x * A.subs + sub;
+  double *const s_base = SUBS == 1 ? smem : smem + sub * LY::SIZE;
+  float *s_tab = (float *)(smem + (SUBS == 1 ? 1 : A.subs) * LY::SIZE);  // [nodes][REP][4]
+  double *const s_rup = s_base + LY::RUP;
+  double *const s_dist = s_base + LY::DIST;
+  double *const s_site = s_base + LY::SITE;
+  double *const s_q = s_base + LY::SQ;
+  double *const s_p = s_base + LY::SP;
+  double *const s_probs = s_base + LY::PROBS;
+  unsigned *const s_valid = (unsigned *)(s_base + LY::VALID);
+  float *const s_hi = (float *)(s_base + LY::HI) + tid;   // [NL - NLR][32 NWMAX]
+  constexpr int hs = 32 * NWMAX;
+  // barrier among the threads of this sub-CTA
+#define SUB_SYNC()                                                         \
+  do {                                                                     \
+    if (SUBS == 1) __syncthreads();                                        \
+    else asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(tb) : "memory"); \
+  } while (0)
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int site0 = blockIdx.x * 32;
+  const int site0 = tile * 32;
   const int n = site0 + lane;
   const bool site_ok = n < A.N;
   const int unit = blockIdx.z * nw + warp;     // (m, level chunk)
@@ -574,26 +660,26 @@ k_fused(const FusedArgs A) {
   const int l0 = lc * A.lpc;
   const int nl = min(A.lpc, A.L1 - l0);
 
+  // the PoE table and the log / exp tables of oqg_math.cuh: whole CTA
+  if (FAST)
+    for (int i = threadIdx.x; i < A.pt_nodes * REP; i += blockDim.x)
+      reinterpret_cast<float4 *>(s_tab)[i] =
+          reinterpret_cast<const float4 *>(A.ptab)[i / REP];
+  math_tables_init();
+  if (SUBS > 1) {
+    __syncthreads();
+    if (tile >= A.ntiles) return;     // named barriers only from here on
+  }
   // site tile to shared memory (geometry) and registers (site parameters)
-  for (int i = threadIdx.x; i < NF_SITE * 32; i += blockDim.x) {
+  for (int i = tid; i < NF_SITE * 32; i += tb) {
     int f = i >> 5, j = i & 31;
     s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
   }
-  if (FAST)
-#if PT_SOA
-    for (int i = threadIdx.x; i < A.pt_nodes * PT_STRIDE; i += blockDim.x)
-      s_tab[(i & 3) * PT_MAXNODES + (i >> 2)] = A.ptab[i];
-#else
-    for (int i = threadIdx.x; i < A.pt_nodes * PT_REP; i += blockDim.x)
-      reinterpret_cast<float4 *>(s_tab)[i] =
-          reinterpret_cast<const float4 *>(A.ptab)[i / PT_REP];
-#endif
-  math_tables_init();   // log / exp tables of oqg_math.cuh
-  // pt_bias = -(0x4b000000 * 16 * PT_REP) mod 2^32 comes in as a kernel argument: as
-  // a literal the compiler splits it off again and adds it back before
-  // every load
+  // pt_bias = -(0x4b000000 * 16 * REP) mod 2^32 comes in as a kernel
+  // argument: as a literal the compiler splits it off again and adds it back
+  // before every load
   const unsigned tab32 = (unsigned)__cvta_generic_to_shared(s_tab) + A.pt_bias +
-                         (PT_SOA ? 0 : (threadIdx.x & (PT_REP - 1)) * (PT_STRIDE * 4));
+                         (lane & (REP - 1)) * (PT_STRIDE * 4);
   const float nm1 = (float)(A.pt_nodes - 1);
   SiteIn si;
   si.vs30 = site_ok && A.vs30 ? A.vs30[n] : 760.;
@@ -637,7 +723,7 @@ k_fused(const FusedArgs A) {
   const int64_t r_begin = (int64_t)blockIdx.y * A.rup_per_chunk;
   const int64_t r_end = min(A.U, r_begin + A.rup_per_chunk);
 
-#define DGET(k) (((A.dmask >> (k)) & 1) ? s_dist[(A.plane_of[k] * RT + i) * 32 + lane] : 0.)
+#define DGET(k) (((DM >> (k)) & 1) ? s_dist[(popc_below(DM, k) * RT + i) * 32 + lane] : 0.)
 #define LOAD_PAIR(i)                                                       \
   RupIn ri;                                                                \
   ri.mag = s_rup[RF_MAG * RT + i];                                         \
@@ -653,15 +739,15 @@ k_fused(const FusedArgs A) {
 
   for (int64_t r0 = r_begin; r0 < r_end; r0 += RT) {
     const int nr = (int)min((int64_t)RT, r_end - r0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < NF_RUP * RT; i += blockDim.x) {
+    SUB_SYNC();
+    for (int i = tid; i < NF_RUP * RT; i += tb) {
       int f = i / RT, j = i - f * RT;
       s_rup[i] = j < nr ? A.rup[(int64_t)f * A.U + r0 + j] : 0.;
     }
     if (NEGBIN)
-      for (int i = threadIdx.x; i < nr * A.K; i += blockDim.x)
-        s_probs[i] = A.probs[r0 * A.K + i];
-    __syncthreads();
+      for (int i = tid; i < nr * A.K; i += tb)
+        s_probs[(i / A.K) * OQG_MAX_OCC + i % A.K] = A.probs[r0 * A.K + i];
+    SUB_SYNC();
     // ---- distances: rupture i of the tile by warp i % nw, lane = site
     for (int i = warp; i < nr; i += nw) {
       double sx[3], sq[3];
@@ -699,8 +785,8 @@ k_fused(const FusedArgs A) {
       }
 #pragma unroll
       for (int k = 0; k < 6; k++)
-        if ((A.dmask >> k) & 1)
-          s_dist[(A.plane_of[k] * RT + i) * 32 + lane] = vals[k];
+        if ((DM >> k) & 1)
+          s_dist[(popc_below(DM, k) * RT + i) * 32 + lane] = vals[k];
       unsigned b = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) s_valid[i] = b;
       if (A.count_pairs && lane == 0 && blockIdx.z == 0) kept += __popc(b);
@@ -736,7 +822,7 @@ k_fused(const FusedArgs A) {
           st_soa(s_q + (nw * RT + i) * QW, 1, FF::rup(gs, Cp, ri));
       }
     }
-    __syncthreads();
+    SUB_SYNC();
     // ---- the IMT-independent part of the model, once per pair, shared by
     // the IMT warps through shared memory
     if (FF::HAS_P) {
@@ -748,7 +834,7 @@ k_fused(const FusedArgs A) {
         st_soa(s_p + i * 32 + lane, RT * 32,
                FF::pair(gs, Cp, sp, qp, ri, si, dd));
       }
-      __syncthreads();
+      SUB_SYNC();
     }
     // ---- GMPE + PoEs + accumulation: this warp's (IMT, level chunk)
     if (!unit_ok) continue;
@@ -788,7 +874,7 @@ k_fused(const FusedArgs A) {
           if (ll[l] >= thr_w) break;
 #pragma unroll
           for (int j = 0; j < LGRP; j++)
-            facc[l + j] = fmaf(rt, poe_table(tab32, nm1, fma(ll[l + j], xa, xb)),
+            facc[l + j] = fmaf(rt, poe_table<REP>(tab32, nm1, fma(ll[l + j], xa, xb)),
                                facc[l + j]);
         }
         // the levels are sorted: if the loop above stopped early, this one
@@ -797,11 +883,11 @@ k_fused(const FusedArgs A) {
         for (int l = NLR; l < NL; l++) {
           const double lv = ll[l];
           if (lv >= thr_w) break;
-          s_hi[(l - NLR) * hs] = fmaf(rt, poe_table(tab32, nm1, fma(lv, xa, xb)),
+          s_hi[(l - NLR) * hs] = fmaf(rt, poe_table<REP>(tab32, nm1, fma(lv, xa, xb)),
                                       s_hi[(l - NLR) * hs]);
         }
       } else if (NEGBIN) {
-        const double *pr = s_probs + i * A.K;
+        const double *pr = s_probs + i * OQG_MAX_OCC;
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
@@ -834,6 +920,7 @@ k_fused(const FusedArgs A) {
   }
 #undef DGET
 #undef LOAD_PAIR
+#undef SUB_SYNC
   if (A.count_pairs && lane == 0 && kept)
     atomicAdd(A.counters, kept);  // statistics only, not the map
   if (FAST || !writer) return;
@@ -975,7 +1062,8 @@ int oqg_create(oqg_handle **out, int device) {
     return fail(nullptr, std::string("no CUDA device: ") +
                              cudaGetErrorString(e) +
                              " (liboqg has no CPU fallback)");
-  if (device < 0 || device >= n) return fail(nullptr, "bad device index");
+  if (device < 0 || device >= n || device >= OQG_MAX_DEVICES)
+    return fail(nullptr, "bad device index");
   h = new oqg_handle();
   h->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
@@ -987,6 +1075,7 @@ int oqg_create(oqg_handle **out, int device) {
   h->stream = h->own_stream;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   for (auto &ev : h->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&h->const_ev, cudaEventDisableTiming);
   cudaMalloc((void **)&h->flag_dev, sizeof(int));
   cudaMemset(h->flag_dev, 0, sizeof(int));
   *out = h;
@@ -1001,8 +1090,13 @@ void oqg_destroy(oqg_handle *h) {
   for (auto &b : h->stage) if (b.p) cudaFree(b.p);
   if (h->flag_dev) cudaFree(h->flag_dev);
   for (auto &ev : h->ev) cudaEventDestroy(ev);
+  {
+    // the stream is idle: nothing of this handle reads the tables any more
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
+  }
+  cudaEventDestroy(h->const_ev);
   cudaStreamDestroy(h->own_stream);
-  if (g_const_owner == h) g_const_owner = nullptr;
   delete h;
 }
 
@@ -1161,16 +1255,19 @@ int oqg_mesh_min_distance(oqg_handle *h, const double *lon, const double *lat,
   if (S <= 0 || N <= 0) return 0;
   if (P <= 0 || !lon || !lat || !off || !out)
     return fail(h, "mesh_min_distance: missing array");
-  if (S > 65535) return fail(h, "mesh_min_distance: at most 65535 meshes per call");
   if (prep_sites(h, sites, N)) return 1;
   if (reserve(h, h->stage[9], (size_t)P * 3 * 8)) return 1;
   double *pts = (double *)h->stage[9].p;
   k_mesh_xyz<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(lon, lat, depth,
                                                                 P, pts);
-  dim3 grid((N + 128 * MESH_SPT - 1) / (128 * MESH_SPT), S);
-  k_mesh_min_distance<<<grid, 128, 0, h->stream>>>(
-      pts, P, off, S, (const double *)h->site.p, N, out);
-  h->launches += 2;
+  h->launches++;
+  for (int y0 = 0; y0 < S; y0 += OQG_GRID_Y) {   // gridDim.y <= 65535
+    dim3 grid((N + 128 * MESH_SPT - 1) / (128 * MESH_SPT),
+              std::min(S - y0, OQG_GRID_Y));
+    k_mesh_min_distance<<<grid, 128, 0, h->stream>>>(
+        pts, P, off, S, (const double *)h->site.p, N, out, y0);
+    h->launches++;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1184,13 +1281,14 @@ int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon,
   if (!top_lon || !top_lat || !off || (!rx && !ry0))
     return fail(h, "mesh_rx_ry0: missing array");
   if (ry0 && !strike) return fail(h, "mesh_rx_ry0: ry0 needs the mean strike");
-  if (S > 65535) return fail(h, "mesh_rx_ry0: at most 65535 surfaces per call");
   if (prep_sites(h, sites, N)) return 1;
-  dim3 grid((N + 127) / 128, S);
-  k_mesh_rx_ry0<<<grid, 128, 0, h->stream>>>(top_lon, top_lat, off, strike,
-                                            (const double *)h->site.p, N, rx,
-                                            ry0);
-  h->launches++;
+  for (int y0 = 0; y0 < S; y0 += OQG_GRID_Y) {
+    dim3 grid((N + 127) / 128, std::min(S - y0, OQG_GRID_Y));
+    k_mesh_rx_ry0<<<grid, 128, 0, h->stream>>>(top_lon, top_lat, off, strike,
+                                              (const double *)h->site.p, N,
+                                              rx, ry0, y0);
+    h->launches++;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1217,10 +1315,12 @@ int oqg_section_min(oqg_handle *h, const double *sec, int S, int N,
   if (U <= 0 || N <= 0) return 0;
   if (!sec || !rup_off || !rup_sec || !out || S <= 0)
     return fail(h, "section_min: missing array");
-  if (U > 65535) return fail(h, "section_min: at most 65535 ruptures per call");
-  dim3 grid((N + 127) / 128, U);
-  k_section_min<<<grid, 128, 0, h->stream>>>(sec, N, rup_off, rup_sec, U, out);
-  h->launches++;
+  for (int y0 = 0; y0 < U; y0 += OQG_GRID_Y) {
+    dim3 grid((N + 127) / 128, std::min(U - y0, OQG_GRID_Y));
+    k_section_min<<<grid, 128, 0, h->stream>>>(sec, N, rup_off, rup_sec, U,
+                                              out, y0);
+    h->launches++;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1688,7 +1788,8 @@ int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx, int64_t P, double *out) {
   for (int g = 0; g < h->G; g++)
     if (const char *m = missing_column(h->gsims[g], ctx))
       return fail(h, std::string("context column missing: ") + m);
-  if (upload_const(h)) return 1;
+  ConstGuard guard(h);
+  if (guard.acquire()) return 1;
   CK(cudaMemsetAsync(h->flag_dev, 0, sizeof(int), h->stream));
   for (int g = 0; g < h->G; g++) {
     switch (h->gsims[g].family) {
@@ -1724,7 +1825,8 @@ int oqg_mean_stds_staged(oqg_handle *h, const oqg_ctx *ctx, int64_t P,
   for (int g = 0; g < h->G; g++)
     if (const char *m = missing_column(h->gsims[g], ctx))
       return fail(h, std::string("context column missing: ") + m);
-  if (upload_const(h)) return 1;
+  ConstGuard guard(h);
+  if (guard.acquire()) return 1;
   for (int g = 0; g < h->G; g++) {
     switch (h->gsims[g].family) {
       case OQG_BSSA14: launch_mean_stds_staged<OQG_BSSA14>(h, g, ctx, P, out); break;
@@ -1745,7 +1847,8 @@ int oqg_poes(oqg_handle *h, const double *ms, int64_t P, float *poes) {
   CK(cudaSetDevice(h->device));
   if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
   if (P <= 0) return 0;
-  if (upload_const(h)) return 1;
+  ConstGuard guard(h);
+  if (guard.acquire()) return 1;
   int64_t tot = P * h->M * h->L1 * h->G;
   double inv_norm = 1. / (h->phi_b * 2. - 1.);
   k_poes<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
@@ -1763,11 +1866,13 @@ int oqg_update(oqg_handle *h, float *map, int N, const float *poes, int64_t P,
   if (P <= 0 || N <= 0) return 0;
   if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
   int LG = h->M * h->L1 * h->G;
-  dim3 grid((LG + 127) / 128, N);
-  k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
-                                        rate, K ? probs : nullptr, K, itime,
-                                        rates_mode, nullptr);
-  h->launches++;
+  for (int y0 = 0; y0 < N; y0 += OQG_GRID_Y) {   // gridDim.y <= 65535
+    dim3 grid((LG + 127) / 128, std::min(N - y0, OQG_GRID_Y));
+    k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
+                                          rate, K ? probs : nullptr, K, itime,
+                                          rates_mode, nullptr, y0);
+    h->launches++;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1782,44 +1887,71 @@ int oqg_update_mutex(oqg_handle *h, float *map, int N, const float *poes,
   if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
   if (!weights) return fail(h, "update_mutex: missing weights");
   int LG = h->M * h->L1 * h->G;
-  dim3 grid((LG + 127) / 128, N);
-  k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
-                                        rate, K ? probs : nullptr, K, itime,
-                                        0, weights);
-  h->launches++;
+  for (int y0 = 0; y0 < N; y0 += OQG_GRID_Y) {
+    dim3 grid((LG + 127) / 128, std::min(N - y0, OQG_GRID_Y));
+    k_update<<<grid, 128, 0, h->stream>>>(map, N, LG, h->G, poes, order, seg,
+                                          rate, K ? probs : nullptr, K, itime,
+                                          0, weights, y0);
+    h->launches++;
+  }
   CK(cudaGetLastError());
   return 0;
 }
 
 }  // extern "C"
 
-template <int F, bool NB, bool FAST>
+template <int F, bool NB, bool FAST, int SUBS, int REP>
 static cudaError_t launch_fused2(const FusedArgs &A, dim3 grid, int threads,
                                  size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(
-      k_fused<F, NB, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-      (int)smem);
+      k_fused<F, NB, FAST, SUBS, REP>,
+      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_fused<F, NB, FAST><<<grid, threads, smem, st>>>(A);
+  k_fused<F, NB, FAST, SUBS, REP><<<grid, threads, smem, st>>>(A);
   return cudaGetLastError();
 }
 
+#define OQG_SUBS_MAX 4
+#define OQG_SMEM_SM (227 * 1024 - 4096)   // per SM, minus the static tables
+
+// Launch of one model.  Fast path with a 256-node table: `subs` sub-CTAs per
+// CTA around one 8-fold replicated PoE table (conflict-free LDS.128), as
+// many as fit into the shared memory of an SM; otherwise the one-work-item
+// CTAs with the plain table (4 per SM).  cfg[0] forces subs (0 = automatic),
+// cfg[1] != 0 forces the plain table.
 template <int F>
-static cudaError_t launch_fused(const FusedArgs &A, dim3 grid, int threads,
-                                cudaStream_t st) {
-  typedef Fast<F> FF;
+static cudaError_t launch_fused(FusedArgs &A, int tiles, int rc, int ugroups,
+                                const int *cfg, cudaStream_t st) {
   const bool fast = A.ptab != nullptr && A.K == 0;
-  const int nw = threads / 32;
-  const int QW = FF::HAS_Q ? sizeof(typename FF::Q) / 8 : 0;
-  const int PW = FF::HAS_P ? sizeof(typename FF::P) / 8 : 0;
-  size_t smem = ((size_t)NF_RUP * RT + (size_t)A.nplanes * RT * 32 +
-                 NF_SITE * 32 + (size_t)(nw + 1) * RT * QW +
-                 (size_t)PW * RT * 32 + (A.K ? RT * A.K : 0)) * 8 +
-                (fast ? (PT_SOA ? PT_MAXNODES : A.pt_nodes * PT_REP) * PT_STRIDE * 4 : 0) + RT * 4 +
-                (fast ? (size_t)(NL - NLR) * threads * 4 : 0);
-  if (A.K) return launch_fused2<F, true, false>(A, grid, threads, smem, st);
-  if (fast) return launch_fused2<F, false, true>(A, grid, threads, smem, st);
-  return launch_fused2<F, false, false>(A, grid, threads, smem, st);
+  A.ntiles = tiles;
+  const size_t tab1 = fast ? (size_t)A.pt_nodes * PT_STRIDE * 4 : 0;
+  int subs = 1;
+  if (fast && !cfg[1] && A.pt_nodes == 256) {
+    const size_t sub = FusedLayout<F, false, true>::SIZE * 8;
+    subs = (int)((OQG_SMEM_SM - 8 * tab1) / sub);
+    subs = std::min(subs, OQG_SUBS_MAX);
+    if (cfg[0]) subs = std::min(subs, cfg[0]);
+    if (subs * A.nw > 32) subs = 32 / A.nw;
+    if (subs > 1) {
+      A.subs = subs;
+      A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_STRIDE * 4 * 8);
+      dim3 grid((tiles + subs - 1) / subs, rc, ugroups);
+      return launch_fused2<F, false, true, OQG_SUBS_MAX, 8>(
+          A, grid, 32 * A.nw * subs, 8 * tab1 + subs * sub, st);
+    }
+  }
+  A.subs = 1;
+  A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_STRIDE * 4);
+  dim3 grid(tiles, rc, ugroups);
+  const int threads = 32 * A.nw;
+  if (A.K)
+    return launch_fused2<F, true, false, 1, 1>(
+        A, grid, threads, FusedLayout<F, true, false>::SIZE * 8, st);
+  if (fast)
+    return launch_fused2<F, false, true, 1, 1>(
+        A, grid, threads, FusedLayout<F, false, true>::SIZE * 8 + tab1, st);
+  return launch_fused2<F, false, false, 1, 1>(
+      A, grid, threads, FusedLayout<F, false, false>::SIZE * 8, st);
 }
 
 extern "C" {
@@ -1856,7 +1988,8 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
   if (K && !probs) return fail(h, "probs_occur missing");
   const int G = h->G, M = h->M, L1 = h->L1, L = M * L1;
-  if (upload_const(h)) return 1;
+  ConstGuard guard(h);
+  if (guard.acquire()) return 1;
   if (prep_ruptures(h, planar, mag, magdist, U)) return 1;
   if (prep_sites(h, sites, N)) return 1;
 
@@ -1877,7 +2010,6 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   A.tl = h->truncation_level; A.xscale = h->xscale;
   A.pt_nodes = h->pt_nodes;
   A.sorted = h->sorted;
-  A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_SOA ? 4 : PT_STRIDE * 4 * PT_REP);
   A.mindist = mindist; A.itime = itime; A.phi_b = h->phi_b;
   A.inv_norm = 1. / (h->phi_b * 2. - 1.);
 
@@ -1910,23 +2042,23 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
     A.clampmask = required_distances(gs);
     A.dmask = A.clampmask | (1 << OQG_RRUP);
     if (A.dmask & (1 << OQG_RHYPO)) A.dmask |= 1 << OQG_REPI;
-    A.nplanes = 0;
-    for (int k = 0; k < 6; k++)
-      if ((A.dmask >> k) & 1) A.plane_of[k] = A.nplanes++;
     A.count_pairs = counters && g == 0;  // blockIdx.z == 0 only
-    dim3 grid(tiles, (unsigned)rc, ugroups);
     // only blockIdx.z == 0 counts pairs
     cudaError_t e = cudaSuccess;
+    A.nw = nw;
     CK(cudaEventRecord(h->ev[2 * g], h->stream));
+#define LF(FAM) e = launch_fused<FAM>(A, tiles, (int)rc, ugroups, h->fused_cfg, h->stream)
     switch (gs.family) {
-      case OQG_BSSA14: e = launch_fused<OQG_BSSA14>(A, grid, 32 * nw, h->stream); break;
-      case OQG_CY14: e = launch_fused<OQG_CY14>(A, grid, 32 * nw, h->stream); break;
-      case OQG_ASK14: e = launch_fused<OQG_ASK14>(A, grid, 32 * nw, h->stream); break;
-      case OQG_CB14: e = launch_fused<OQG_CB14>(A, grid, 32 * nw, h->stream); break;
-      case OQG_BA08: e = launch_fused<OQG_BA08>(A, grid, 32 * nw, h->stream); break;
-      case OQG_AB06: e = launch_fused<OQG_AB06>(A, grid, 32 * nw, h->stream); break;
-      case OQG_AKKAR14: e = launch_fused<OQG_AKKAR14>(A, grid, 32 * nw, h->stream); break;
+      case OQG_BSSA14: LF(OQG_BSSA14); break;
+      case OQG_CY14: LF(OQG_CY14); break;
+      case OQG_ASK14: LF(OQG_ASK14); break;
+      case OQG_CB14: LF(OQG_CB14); break;
+      case OQG_BA08: LF(OQG_BA08); break;
+      case OQG_AB06: LF(OQG_AB06); break;
+      case OQG_AKKAR14: LF(OQG_AKKAR14); break;
     }
+#undef LF
+    h->last_subs = A.subs;
     CK(cudaEventRecord(h->ev[2 * g + 1], h->stream));
     h->launches++;
     if (e != cudaSuccess)
@@ -2001,6 +2133,15 @@ int oqg_set_exact_poe(oqg_handle *h, int on) {
   h->exact_poe = on != 0;
   return 0;
 }
+
+int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table) {
+  if (subs < 0 || subs > OQG_SUBS_MAX) return fail(h, "subs must be in 0..4");
+  h->fused_cfg[0] = subs;
+  h->fused_cfg[1] = plain_table != 0;
+  return 0;
+}
+
+int oqg_last_fused_subs(oqg_handle *h) { return h->last_subs; }
 
 int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err) {
   *in_use = h->fast_ok && !h->exact_poe;

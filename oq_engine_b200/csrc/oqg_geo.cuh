@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(128)
 k_mesh_min_distance(const double *__restrict__ pts, int64_t P,
                     const int64_t *__restrict__ off, int S,
                     const double *__restrict__ site, int N,
-                    double *__restrict__ out) {
+                    double *__restrict__ out, int y0) {
   __shared__ double sx[256], sy[256], sz[256], sp[256];
-  const int s = blockIdx.y;
+  const int s = blockIdx.y + y0;   // y0: the host launches grid.y in chunks
   const int n0 = blockIdx.x * (blockDim.x * MESH_SPT) + threadIdx.x;
   const int64_t pa = off[s], pb = off[s + 1];
   const double cx = pts[pa], cy = pts[P + pa], cz = pts[2 * P + pa];
@@ -345,8 +345,8 @@ __global__ void k_mesh_xyz(const double *__restrict__ lon,
 __global__ void k_section_min(const double *__restrict__ sec, int N,
                               const int64_t *__restrict__ roff,
                               const int32_t *__restrict__ rsec, int U,
-                              double *__restrict__ out) {
-  const int u = blockIdx.y;
+                              double *__restrict__ out, int y0) {
+  const int u = blockIdx.y + y0;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double best = INFINITY;
@@ -409,10 +409,10 @@ __global__ void __launch_bounds__(128)
 k_mesh_rx_ry0(const double *__restrict__ tlon, const double *__restrict__ tlat,
               const int64_t *__restrict__ off, const double *__restrict__ strike,
               const double *__restrict__ site, int N, double *__restrict__ rx,
-              double *__restrict__ ry0) {
+              double *__restrict__ ry0, int y0) {
   __shared__ EdgeSeg s_seg[RX_CHUNK];
   __shared__ double s_end[2][6];   // first / last vertex: p, r of strike + 90
-  const int s = blockIdx.y;
+  const int s = blockIdx.y + y0;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t pa = off[s];
   const int K = (int)(off[s + 1] - pa);

@@ -13,7 +13,7 @@ tests/golden/gmpe_*.npz (produced by oracle/make_golden.py running the
 reference itself) plus the reference's own CSV verification tables
 (tests/golden/kat_*.csv).
 
-Coefficients come from oq-engine_b200/data/coeffs.json (published tables,
+Coefficients come from oq_engine_b200/data/coeffs.json (published tables,
 extracted by tools/extract_coeffs.py); interpolation between tabulated
 periods is linear in log-period as in
 openquake/hazardlib/gsim/coeffs_table.py:231-286.
@@ -25,7 +25,7 @@ import math
 import numpy as np
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..',
-                     'oq-engine_b200', 'data', 'coeffs.json')
+                     'oq_engine_b200', 'data', 'coeffs.json')
 _TABLES = None
 
 

@@ -754,3 +754,253 @@ def test_fused_planar_alias(oq):
     h.call('oqg_fused_planar', _ptr(t_pla), _ptr(t_mag), U, ctypes.byref(st),
            N, _ptr(t_md), 0., 50., 1, _ptr(t_map), None)
     np.testing.assert_array_equal(t_map.cpu().numpy(), want.array)
+
+
+# ------------------------------------------- per-PoE parity of the fused path
+def _one_rupture(oq, rng, N):
+    """One M6.5 rupture with rate * T = 1 exactly and N sites around it: the
+    rates map of the fused kernel then holds the PoEs themselves"""
+    r = synth_ruptures(1, rng)
+    r['mag'][:] = 6.5
+    r['rate'][:] = 2. ** -5
+    r['area'] = np.array([400.])
+    sites = synth_sites(N, rng, sentinels=True)
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    return oq.contexts.PlanarRuptures(pla, r['mag']), sc
+
+
+def _check_poes(got, exp, tag):
+    """north_star tolerance: rtol 1e-5 where the PoE is >= 1e-8, 1e-7
+    absolute below"""
+    big = exp >= 1e-8
+    rel = np.abs(got[big] / exp[big] - 1.)
+    assert rel.max() < 1e-5, (tag, rel.max(), exp[big][rel.argmax()])
+    assert np.abs(got[~big] - exp[~big]).max(initial=0.) < 1e-7, tag
+    return int(big.sum())
+
+
+@pytest.mark.parametrize('tl', [2., 2.5, 3., 5., 6.])
+@pytest.mark.parametrize('shape', ['auto', 'plain'])
+def test_fused_fast_path_per_poe(oq, tl, shape):
+    """Every PoE of the table-driven fused path against truncnorm_sf
+    (hazardlib/stats.py:38-73) in float64, not a sum over ruptures: one
+    rupture with rate * T = 1 and 3000 sites give 3000 x 140 x 2 PoEs per
+    truncation level with z spread over [-13, 13]; both CTA shapes of the
+    fused kernel (sub-CTAs around the replicated table / plain table)"""
+    rng = np.random.default_rng(int(tl * 10))
+    N, L1 = 3000, 20
+    src, sc = _one_rupture(oq, rng, N)
+    imls = np.logspace(-4, 1.5, L1)
+    imtls = {imt: imls for imt in IMTS}
+    cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+        imtls=imtls, truncation_level=tl, investigation_time=32.))
+    h = cm.handle()
+    L_ = oq._lib.lib()
+    in_use, err = ctypes.c_int(0), ctypes.c_double(0)
+    L_.oqg_poe_table_info(h._h, ctypes.byref(in_use), ctypes.byref(err))
+    assert in_use.value, 'the table path must be the one under test'
+    h.call('oqg_set_fused_config', 0, int(shape == 'plain'))
+    try:
+        rmap = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+        kept = cm.hazard_planar(rmap, src, sc, count=True)
+        subs = L_.oqg_last_fused_subs(h._h)
+    finally:
+        h.call('oqg_set_fused_config', 0, 0)
+    assert kept == N
+    assert (subs == 1) == (shape == 'plain' or tl > 4.), (subs, tl)
+    ctx = cm.recarray(cm.get_ctxs(src, sc))
+    np.testing.assert_array_equal(ctx.sids, sc.sids)
+    ms = cm.get_mean_stds([ctx])        # (4, G, M, N) float64, device
+    phi_b = float(poe_np.ndtr(tl))
+    ll = np.log(imls)
+    n = 0
+    for g in range(cm.G):
+        for m in range(cm.M):
+            z = (ll[None, :] - ms[0, g, m][:, None]) / ms[1, g, m][:, None]
+            exp = poe_np.truncnorm_sf(phi_b, z)
+            got = rmap.array[:, m * L1:(m + 1) * L1, g].astype(float)
+            n += _check_poes(got, exp, (tl, shape, g, m))
+    assert n > 50_000, n     # PoEs checked at rtol 1e-5
+
+
+@pytest.mark.parametrize('tl', [2., 3., 5.])
+def test_fused_fast_path_edge_z(oq, tl):
+    """The reference's edge cases through the fused table path, one site and
+    levels placed at chosen z: z = +-tl, tl - 1e-7 ... tl - 1e-2 (relative
+    accuracy next to the truncation point, where the textbook formula
+    cancels), 2.99, 2.9999999, and just above tl (exactly 0)"""
+    rng = np.random.default_rng(7)
+    src, sc = _one_rupture(oq, rng, 1)
+    zs = [-tl - 1e-7, -tl, -tl + 1e-7, -1., 0., 1., tl - 1e-2, tl - 1e-3,
+          tl - 1e-4, tl - 1e-5, tl - 3e-6, tl - 1e-7, tl, tl + 1e-7]
+    if tl == 3.:
+        zs += [2.99, 2.9999999]
+    zs = np.array(sorted(zs))
+    for name in ('BooreEtAl2014', 'ChiouYoungs2014', 'AbrahamsonEtAl2014',
+                 'CampbellBozorgnia2014'):
+        prm = dict(imtls={imt: [1.] * len(zs) for imt in IMTS},
+                   truncation_level=tl, investigation_time=32.)
+        cm0 = oq.ContextMaker('*', [oq.get_gsim(name)], prm)
+        ctx = cm0.recarray(cm0.get_ctxs(src, sc))
+        ms = cm0.get_mean_stds([ctx])
+        imtls = {imt: np.exp(ms[0, 0, m, 0] + zs * ms[1, 0, m, 0])
+                 for m, imt in enumerate(IMTS)}
+        prm['imtls'] = imtls
+        cm = oq.ContextMaker('*', [oq.get_gsim(name)], prm)
+        rmap = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+        cm.hazard_planar(rmap, src, sc)
+        phi_b = float(poe_np.ndtr(tl))
+        for m, imt in enumerate(IMTS):
+            z = (np.log(imtls[imt]) - ms[0, 0, m, 0]) / ms[1, 0, m, 0]
+            exp = poe_np.truncnorm_sf(phi_b, z)
+            got = rmap.array[0, m * len(zs):(m + 1) * len(zs), 0].astype(float)
+            _check_poes(got, exp, (tl, name, imt))
+            # at and beyond the truncation level the PoE is exactly 0 / 1
+            assert (got[z >= tl + 5e-8] == 0.).all()
+            assert (got[z <= -tl - 5e-8] == 1.).all()
+
+
+def test_fused_unsorted_levels(oq):
+    """A level grid that is not increasing (the level skipping of the fused
+    kernel assumes sorted levels and must switch itself off)"""
+    rng = np.random.default_rng(11)
+    N, L1 = 500, 20
+    src, sc = _one_rupture(oq, rng, N)
+    imls = np.logspace(-3, 1., L1)
+    imtls = {imt: rng.permutation(imls) for imt in IMTS}
+    cm = oq.ContextMaker('*', make_gsims(oq, CFG['cfg3']), dict(
+        imtls=imtls, truncation_level=3., investigation_time=32.))
+    rmap = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+    cm.hazard_planar(rmap, src, sc)
+    ctx = cm.recarray(cm.get_ctxs(src, sc))
+    ms = cm.get_mean_stds([ctx])
+    phi_b = float(poe_np.ndtr(3.))
+    for g in range(cm.G):
+        for m, imt in enumerate(IMTS):
+            ll = np.log(imtls[imt])
+            z = (ll[None, :] - ms[0, g, m][:, None]) / ms[1, g, m][:, None]
+            _check_poes(rmap.array[:, m * L1:(m + 1) * L1, g].astype(float),
+                        poe_np.truncnorm_sf(phi_b, z), (g, imt))
+
+
+def test_two_handles_two_streams(oq):
+    """Two oqg handles on one device, each with its own stream, models and
+    levels, used alternately without host synchronisation: the __constant__
+    tables have one owner at a time (ConstGuard in csrc/oqg.cu), so every
+    call must see its own handle's tables"""
+    import torch
+    from oq_engine_b200.contexts import _dev, _ptr
+    rng = np.random.default_rng(3)
+    U, N = 600, 400
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    src = oq.contexts.PlanarRuptures(pla, r['mag'])
+    cms = [oq.ContextMaker('*', [oq.get_gsim('BooreEtAl2014')], dict(
+               imtls={imt: np.logspace(-2, 0.3, 20) for imt in IMTS},
+               truncation_level=3., investigation_time=50.)),
+           oq.ContextMaker('*', [oq.get_gsim('ChiouYoungs2014'),
+                                 oq.get_gsim('CampbellBozorgnia2014')], dict(
+               imtls={imt: np.logspace(-3, 0., 15) for imt in IMTS[:4]},
+               truncation_level=2.5, investigation_time=1.))]
+    # solo results through the usual one-handle-per-device path
+    solo = []
+    for cm in cms:
+        m = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+        cm.hazard_planar(m, src, sc)
+        solo.append(m.array.copy())
+    dev = 0
+    hs = [oq._lib.Handle(dev) for _ in cms]      # own streams
+    for cm, h in zip(cms, hs):
+        cm.configure(h)
+    flat = oq.planar.as_flat(pla)
+    t_pla, t_mag = _dev(flat, dev), _dev(r['mag'], dev)
+    st, keep = cms[0]._sites_struct(sc, dev)
+    maps, mds = [], []
+    for cm in cms:
+        maps.append(torch.zeros((N, cm.L, cm.G), dtype=torch.float32,
+                                device='cuda:%d' % dev))
+        mds.append(_dev(cm.magdist(r['mag']), dev))
+    torch.cuda.synchronize()
+    reps = 6
+    for _ in range(reps):
+        for cm, h, t_map, t_md in zip(cms, hs, maps, mds):
+            h.call('oqg_hazard_planar', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
+                   None, 0, U, ctypes.byref(st), None, N, 0.,
+                   float(cm.investigation_time), 1, _ptr(t_map), None)
+    for h in hs:
+        h.call('oqg_synchronize')
+    for t_map, exp in zip(maps, solo):
+        np.testing.assert_allclose(t_map.cpu().numpy(), reps * exp,
+                                   rtol=2e-6, atol=1e-30)
+    for h in hs:
+        h.close()
+
+
+def test_magnitude_outside_the_integration_distance_pairs(oq):
+    """maximum_distance = [(5.5, 100), (7, 300)]: the reference's magdepdist
+    (calc/filters.py:183-190) gives distance 0 outside [5.5, 7], so those
+    ruptures contribute nothing"""
+    rng = np.random.default_rng(21)
+    U, N = 200, 64
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    pairs = CFG['cfg3']
+    md = oq.IntegrationDistance.new('[(5.5, 100), (7, 300)]')
+    cm = oq.ContextMaker('*', make_gsims(oq, pairs), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.,
+        maximum_distance=md))
+    mags = r['mag']
+    inside = (mags >= 5.5) & (mags <= 7)
+    assert inside.any() and (~inside).any()
+    magdist = cm.magdist(mags)
+    assert (magdist[~inside] == 0).all()
+    np.testing.assert_allclose(magdist[inside],
+                               np.interp(mags[inside], [5.5, 7], [100, 300]))
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    rmap = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+    kept = cm.hazard_planar(rmap, oq.contexts.PlanarRuptures(pla, mags), sc,
+                            count=True)
+    opla = geo_np.build_planar(
+        r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+        r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+    octx = hazard_np.get_ctx(pairs, opla, mags, sites, magdist, 0.)
+    assert kept == len(octx) and set(np.unique(octx.mag)) <= set(
+        mags[inside])
+    acc = hazard_np.exact_rate_sum(pairs, octx, sites['sids'], imtls, 3., 50.)
+    big = acc > 1e-10
+    np.testing.assert_allclose(rmap.array[big], acc[big], rtol=1e-5)
+    # the unfused operator drops the same rows
+    ctx = cm.recarray(cm.get_ctxs(oq.contexts.PlanarRuptures(pla, mags), sc))
+    assert len(ctx) == kept
+
+
+def test_update_more_than_65535_sites(oq):
+    """ContextMaker.update on a map with more rows than gridDim.y allows in
+    one launch (the site dimension is launched in chunks)"""
+    rng = np.random.default_rng(5)
+    N = 70_000
+    src, sc = _one_rupture(oq, rng, N)
+    cm = oq.ContextMaker('*', [oq.get_gsim('BooreEtAl2014')], dict(
+        imtls={'PGA': np.logspace(-2, 0, 4)}, truncation_level=3.,
+        investigation_time=32.))
+    ctx = cm.recarray(cm.get_ctxs(src, sc))
+    a = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+    cm.update(a, ctx)
+    b = oq.MapArray(sc.sids, cm.L, cm.G, rates=True).fill(0)
+    cm.hazard_planar(b, src, sc)
+    np.testing.assert_allclose(a.array, b.array, rtol=2e-6, atol=1e-30)
+    assert (a.array[-1] > 0).any()

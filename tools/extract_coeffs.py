@@ -1,5 +1,5 @@
 """Dump the published GMPE coefficient tables used by the hot path into
-oq-engine_b200/data/coeffs.json.
+oq_engine_b200/data/coeffs.json.
 
 The numbers are the published regression coefficients of the ground-motion
 models (NGA-West2 etc.); they are read here from the reference's CoeffsTable
@@ -64,7 +64,7 @@ def dump(table):
 
 if __name__ == '__main__':
     out = {name: dump(tab) for name, tab in TABLES.items()}
-    dest = os.path.join(HERE, '..', 'oq-engine_b200', 'data', 'coeffs.json')
+    dest = os.path.join(HERE, '..', 'oq_engine_b200', 'data', 'coeffs.json')
     with open(dest, 'w') as f:
         json.dump(out, f, separators=(',', ':'))
     for name, dic in out.items():

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def line_table(func_substr):
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all',
-                    os.path.join(ROOT, 'oq-engine_b200', 'liboqg.so')],
+                    os.path.join(ROOT, 'oq_engine_b200', 'liboqg.so')],
                    cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
     out = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)],
@@ -75,7 +75,7 @@ def main(rep, func, top=40, stall=None, kernel=None):
                                           )[:int(top)]:
         if f not in src:
             try:
-                src[f] = open(os.path.join(ROOT, 'oq-engine_b200', 'csrc', f)
+                src[f] = open(os.path.join(ROOT, 'oq_engine_b200', 'csrc', f)
                               ).read().splitlines()
             except OSError:
                 src[f] = []
