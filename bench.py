@@ -196,6 +196,192 @@ def workload_name(args):
         len(IMTS))
 
 
+
+# ------------------------------------------------- strong-scaling legs
+# Fixed total workloads split over the ranks, run inside the same bench
+# process after the headline measurement, so that the driver's per-N lines
+# carry both shardings of SURVEY 8e with their collectives timed:
+#   strong_sites   cfg4 models, STRONG_SITES ruptures x sites in total, the
+#                  sites split by `sids % world` (the reference's tiling rule);
+#                  the tiles are gathered into the whole map on every rank
+#                  (all_gather, timed separately)
+#   strong_groups  cfg5 shape: 8 source groups of STRONG_GROUPS ruptures over
+#                  the same sites, rank k folds groups k, k + world, ...; the
+#                  pne maps are multiplied with one NCCL all-reduce (PRODUCT)
+#                  inside the timed region (timed separately as well)
+STRONG_SITES = (100_000, 80_000)       # ruptures, sites in total
+STRONG_GROUPS = (50_000, 50_000, 8)    # ruptures per group, sites, groups
+
+
+def _planar_inputs(oq, cm, U, seed, local):
+    from oq_engine_b200.contexts import _dev
+    r, _ = synth(U, 4, seed)
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    return (_dev(oq.planar.as_flat(pla), local),
+            _dev(np.ascontiguousarray(r['mag']), local),
+            _dev(cm.magdist(r['mag']), local))
+
+
+def _events_ms(pairs):
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
+def strong_legs(args, oq, rank, world, local, timed_max):
+    """The two strong-scaling legs; returns {'strong_sites': {...},
+    'strong_groups': {...}} on every rank (values are whole-job)"""
+    import torch
+    import torch.distributed as dist
+    from oq_engine_b200.contexts import _ptr
+    dev = 'cuda:%d' % local
+    M, L1 = len(IMTS), 20
+    L = M * L1
+    imtls = {imt: np.logspace(-2, 0.3, L1) for imt in IMTS}
+    out = {}
+    steps, warm = args.strong_steps, 1
+
+    def cmaker(names):
+        return oq.ContextMaker('*', [oq.get_gsim(n) for n in names], dict(
+            imtls=imtls, truncation_level=3., investigation_time=50.),
+            device=local)
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- sites: cfg4 models, fixed grid split by sids % world ------------
+    U, N = STRONG_SITES
+    U, N = int(U * args.strong_scale), N
+    names = WORKLOADS['cfg4'][2]
+    G = len(names)
+    cm = cmaker(names)
+    h = cm.handle()
+    inp = _planar_inputs(oq, cm, U, 20240, local)
+    _, sites = synth(4, N, 21240)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    tile = oq.sharding.site_tile(sc, rank, world)
+    n_k = len(tile)
+    st, keep = cm._sites_struct(tile, local)
+    t_map = torch.ones((n_k, L, G), dtype=torch.float32, device=dev)
+    t_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    ev = []
+    whole = [None]
+
+    def step_sites():
+        t_map.fill_(1.)
+        h.call('oqg_hazard_planar', _ptr(inp[0]), _ptr(inp[1]), _ptr(inp[2]),
+               None, 0, U, ctypes.byref(st), None, n_k, 0., 50., 0,
+               _ptr(t_map), _ptr(t_cnt))
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        whole[0] = oq.sharding.gather_tiles(t_map, tile.sids, N)
+        b.record()
+        ev.append((a, b))
+
+    for _ in range(warm):
+        step_sites()
+    ev.clear()
+    t_cnt.zero_()
+    ms = timed_max(step_sites, steps)
+    pairs = torch.tensor([float(t_cnt[0].item()) / steps],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pairs)
+    evals = float(pairs.item()) * L * G
+    gather_ms = allmax(sum(_events_ms(ev)) / steps)
+    # parity spot check: the first sites of the gathered map against a
+    # single-rank pass over exactly those sites
+    nchk = min(256, N)
+    sub = sc.filter(np.arange(N) < nchk)
+    st2, keep2 = cm._sites_struct(sub, local)
+    chk = torch.ones((nchk, L, G), dtype=torch.float32, device=dev)
+    h.call('oqg_hazard_planar', _ptr(inp[0]), _ptr(inp[1]), _ptr(inp[2]),
+           None, 0, U, ctypes.byref(st2), None, nchk, 0., 50., 0, _ptr(chk),
+           None)
+    diff = float((whole[0][:nchk] - chk).abs().max().item())
+    out['strong_sites'] = {
+        'value': evals / (ms / steps * 1e-3), 'unit': 'evals/s',
+        'ms_per_step': ms / steps, 'gather_ms': gather_ms,
+        'gather_bytes': N * L * G * 4, 'steps': steps,
+        'workload': 'cfg4 models, %d ruptures x %d sites in total, sites '
+                    'split by sids %% %d, tiles all-gathered into the whole '
+                    'map on every rank' % (U, N, world),
+        'check_max_abs_diff_vs_single_rank': diff}
+    del t_map, whole, chk, inp
+    torch.cuda.empty_cache()
+
+    # ---- source groups: cfg5 shape, NCCL PRODUCT all-reduce ---------------
+    U, N, NG = STRONG_GROUPS
+    U = int(U * args.strong_scale)
+    names = WORKLOADS['cfg5'][2]
+    G = len(names)
+    cm = cmaker(names)
+    h = cm.handle()
+    mine = oq.sharding.groups_of(rank, world, NG)
+    inps = [_planar_inputs(oq, cm, U, 20240 + g, local) for g in mine]
+    _, sites = synth(4, N, 21240)
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    st, keep = cm._sites_struct(sc, local)
+    t_map = torch.ones((N, L, G), dtype=torch.float32, device=dev)
+    t_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    ev = []
+
+    def step_groups():
+        t_map.fill_(1.)
+        for a, b, c in inps:
+            h.call('oqg_hazard_planar', _ptr(a), _ptr(b), _ptr(c), None, 0, U,
+                   ctypes.byref(st), None, N, 0., 50., 0, _ptr(t_map),
+                   _ptr(t_cnt))
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        oq.sharding.combine_maps(t_map, rates=False)
+        e1.record()
+        ev.append((e0, e1))
+
+    for _ in range(warm):
+        step_groups()
+    ev.clear()
+    t_cnt.zero_()
+    ms = timed_max(step_groups, steps)
+    pairs = torch.tensor([float(t_cnt[0].item()) / steps],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pairs)
+    evals = float(pairs.item()) * L * G
+    ar_ms = allmax(sum(_events_ms(ev)) / steps)
+    nbytes = N * L * G * 4
+    bus = (2. * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9
+           if world > 1 and ar_ms > 0 else None)
+    # parity spot check: all the groups folded by THIS rank alone over the
+    # first sites, against the all-reduced map
+    nchk = min(128, N)
+    sub = sc.filter(np.arange(N) < nchk)
+    st2, keep2 = cm._sites_struct(sub, local)
+    chk = torch.ones((nchk, L, G), dtype=torch.float32, device=dev)
+    for g in range(NG):
+        a, b, c = (inps[mine.index(g)] if g in mine
+                   else _planar_inputs(oq, cm, U, 20240 + g, local))
+        h.call('oqg_hazard_planar', _ptr(a), _ptr(b), _ptr(c), None, 0, U,
+               ctypes.byref(st2), None, nchk, 0., 50., 0, _ptr(chk), None)
+    rel = float(((t_map[:nchk] - chk).abs() / chk.clamp_min(1e-30)).max())
+    out['strong_groups'] = {
+        'value': evals / (ms / steps * 1e-3), 'unit': 'evals/s',
+        'ms_per_step': ms / steps, 'allreduce_ms': ar_ms,
+        'allreduce_bytes': nbytes, 'allreduce_bus_gbs': bus,
+        'allreduce_bus_reference_gbs': 725.0, 'steps': steps,
+        'workload': 'cfg5 shape: %d source groups x %d ruptures x %d sites, '
+                    'groups round-robin over %d ranks, NCCL all-reduce '
+                    '(PRODUCT) of the %d-byte pne maps inside the timed '
+                    'region' % (NG, U, N, world, nbytes),
+        'check_max_rel_diff_vs_single_rank': rel}
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -348,6 +534,13 @@ def run_ours(args):
     else:
         value = evals_step * world / (ms / args.steps * 1e-3)
         e2e = evals_step * world / (ms_e2e / args.steps * 1e-3)
+    # ---- strong-scaling legs (every rank takes part in their collectives)
+    strong = {}
+    if not args.no_strong and args.workload == 'cfg3' and not args.ruptures \
+            and not args.sites:
+        del t_pla, t_mag, t_md, t_map, group_inputs
+        torch.cuda.empty_cache()
+        strong = strong_legs(args, oq, rank, world, local, timed)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,8 +548,23 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (the slowest fused launch)
     peak = ctypes.c_double(0)
     h.call('oqg_measure_fp64_peak', ctypes.byref(peak))
+    # second, independent FP64 probe: cuBLAS DGEMM through torch
+    a64 = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+    b64 = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+    torch.matmul(a64, b64)
+    dg = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        torch.matmul(a64, b64)
+        e1.record()
+        torch.cuda.synchronize()
+        dg.append(e0.elapsed_time(e1))
+    dgemm_tflops = 2 * 4096 ** 3 / (min(dg) * 1e-3) / 1e12
+    del a64, b64
     gdom = int(np.argmax(kernel_ms)) if kernel_ms else 0
-    fl = flops_per_row(names[gdom], M, L1) * pairs_kept / len(group_inputs)
+    ngrp = len(my_groups)
+    fl = flops_per_row(names[gdom], M, L1) * pairs_kept / ngrp
     ach = fl / (kernel_ms[gdom] * 1e-3) / 1e12 if kernel_ms else None
     alg_bytes = U * 65 * 8 + N * (7 * 8 + 33) + N * L * 8 * 2
     try:
@@ -365,43 +573,90 @@ def run_ours(args):
         hbm_src = 'MEASURED_PEAKS.json'
     except Exception:
         hbm_peak, hbm_src = 6650., 'fallback'
-    # DRAM traffic and pipe utilisation of the same kernel from the committed
-    # ncu capture (profiles/r1_v12_traffic.json; cfg3 full size), if the
-    # workload is the one that was profiled
-    traffic, pipes = None, None
+    # Per-launch figures that only a profiler can give (DRAM traffic, warp
+    # instructions, pipe utilisation) come from the ncu capture of THIS
+    # kernel version committed under profiles/ (tools/ncu_metrics.py writes
+    # the JSON from the .ncu-rep); they are null when the capture is absent
+    # or was taken with another build of the kernels.
+    prof, prof_src = None, None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_v12_traffic.json')) as f:
-            prof = json.load(f)
-        k = prof['kernels'].get('k_fused<%s>' % names[gdom])
-        if k and args.workload == 'cfg3' and not args.ruptures and \
-                not args.sites:
-            traffic = k['dram_bytes_read'] + k['dram_bytes_write']
-            pipes = {'source': 'ncu, profiles/r1_v12_traffic.json',
-                     'l1tex_lsu_data_pipe_pct': k['lsu_data_pipe_pct'],
-                     'issue_slots_pct': k['issue_active_pct'],
-                     'fp64_pipe_pct': k['fp64_pipe_pct']}
+        from oq_engine_b200 import _build
+        with open(os.path.join(ROOT, 'profiles', 'r2_fused_metrics.json')) as f:
+            allprof = json.load(f)
+        if allprof.get('kernel_fingerprint') == _build.kernel_fingerprint():
+            prof = allprof['kernels'].get(names[gdom])
+            prof_src = 'profiles/r2_fused_metrics.json (%s)' % allprof['report']
     except Exception:
         pass
+    sm_hz = (clocks or {}).get('sm_mhz') or 1965.
+    sm_hz *= 1e6
+    issue = None
+    if prof and kernel_ms:
+        # warp instructions scale with the rupture-site pairs of a launch
+        inst = prof['warp_inst_per_pair'] * pairs_kept / ngrp
+        slots = kernel_ms[gdom] * 1e-3 * sm_hz * 148 * 4
+        issue = {'warp_inst_per_pair': prof['warp_inst_per_pair'],
+                 'warp_inst_per_launch': inst,
+                 'issue_slots_per_launch': slots, 'frac': inst / slots,
+                 'definition': 'warp instructions of the launch (ncu '
+                               'smsp__inst_executed.sum per pair x pairs) / '
+                               '(launch time x 148 SMs x 4 schedulers x SM '
+                               'clock sampled in this run)',
+                 'ncu_issue_active_pct': prof.get('issue_active_pct'),
+                 'ncu_lsu_data_pipe_pct': prof.get('lsu_data_pipe_pct'),
+                 'ncu_fp64_pipe_pct': prof.get('fp64_pipe_pct'),
+                 'source': prof_src}
+    # executed evaluations: one extra, untimed statistics pass
+    executed = None
+    if not by_groups:
+        h = cm.handle()     # the strong legs configured other models
+        L_.oqg_set_count_evals(h._h, 1)
+        t_cnt.zero_()
+        t_map2 = torch.ones((N, L, G), dtype=torch.float32, device=dev)
+        a, b, c = _planar_inputs(oq, cm, U, 20240, local)
+        h.call('oqg_hazard_planar', _ptr(a), _ptr(b), _ptr(c), None, 0, U,
+               ctypes.byref(st), None, N, 0., 50., 0, _ptr(t_map2),
+               _ptr(t_cnt))
+        L_.oqg_set_count_evals(h._h, 0)
+        ex = int(t_cnt[1].item())
+        nominal = pairs_kept * L * G
+        executed = {
+            'evals_per_step': ex, 'nominal_evals_per_step': nominal,
+            'level_skip_fraction': 1. - ex / nominal,
+            'executed_evals_per_s': ex / (ms / args.steps * 1e-3),
+            'note': '`value` counts every (pair, gsim, IMT, level) as the '
+                    'metric defines it; the kernel skips the levels above '
+                    'mean + truncation_level * sigma of a whole warp, whose '
+                    'PoEs are exactly 0, and executes this many'}
+        del t_map2
     roofline = {
         'bound': 'fp64', 'kernel': 'k_fused<%s>' % names[gdom],
         'achieved': ach, 'peak': peak.value, 'unit': 'TFLOP/s',
-        'frac': ach / peak.value if ach else None, 'traffic': traffic,
-        'pipes': pipes,
-        'convention': 'achieved = SURVEY 8d algorithmic FP64 flop of the '
+        'frac': ach / peak.value if ach else None,
+        'traffic': prof['dram_bytes'] if prof else None,
+        'traffic_source': prof_src,
+        'convention': 'achieved = SURVEY 8d ALGORITHMIC FP64 flop of the '
                       'reference operation mix (erf = 50 flop, GMPE 220-560, '
-                      'distances 40-1300 per row) / launch time; the kernel '
-                      'executes fewer operations than that (table-driven PoE '
-                      'and log/exp), so frac > 1 is possible: it measures '
-                      'speed against "the reference arithmetic at the FP64 '
-                      'peak"; the hardware limit of the kernel is the '
-                      'L1/shared-memory data pipe (pipes)',
-        'peak_source': 'DFMA microbenchmark (oqg_measure_fp64_peak) run in '
-                       'this process; nominal %.0f' % FP64_NOMINAL_TFLOPS,
+                      'distances 40-1300 per row) / launch time.  The kernel '
+                      'does that work with far fewer operations (float32 '
+                      'cubic table for the PoE, table-driven log / exp, level '
+                      'skipping), so frac > 1: it is speed relative to "the '
+                      'reference arithmetic at the FP64 peak", NOT a hardware '
+                      'utilisation.  The hardware fractions are `issue` '
+                      '(instruction-issue roofline) and the ncu pipe '
+                      'percentages inside it; `executed` gives the '
+                      'evaluations really performed.',
+        'peak_source': 'DFMA microbenchmark (oqg_measure_fp64_peak) in this '
+                       'process; cross-checked by `peak_probes`',
+        'peak_probes': {'dfma_tflops': peak.value,
+                        'cublas_dgemm_4096_tflops': dgemm_tflops,
+                        'nominal_tflops': FP64_NOMINAL_TFLOPS},
         'flop_per_row': flops_per_row(names[gdom], M, L1),
         'kernel_ms': kernel_ms,
+        'issue': issue, 'executed': executed,
         'hbm': {'achieved': alg_bytes / (kernel_ms[gdom] * 1e-3) / 1e9
                 if kernel_ms else None, 'peak': hbm_peak, 'unit': 'GB/s',
-                'peak_source': hbm_src,
+                'peak_source': hbm_src, 'algorithmic_bytes': alg_bytes,
                 'note': 'algorithmic bytes per launch; not the bound'},
     }
     # ---- CPU baseline on a bounded sample, rank 0 only
@@ -437,6 +692,7 @@ def run_ours(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+        **strong,
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -454,6 +710,11 @@ def main():
     ap.add_argument('--cpu-ruptures', type=int, default=768,
                     help='ruptures of the bounded CPU sample (x all sites)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-strong', action='store_true',
+                    help='skip the strong-scaling legs')
+    ap.add_argument('--strong-steps', type=int, default=2)
+    ap.add_argument('--strong-scale', type=float, default=1.0,
+                    help='scales the ruptures of the strong-scaling legs')
     ap.add_argument('--fused-subs', type=int, default=0,
                     help='A/B: cap of the sub-CTAs per CTA (0 = automatic)')
     ap.add_argument('--plain-table', action='store_true',

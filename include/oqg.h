@@ -130,6 +130,15 @@ int oqg_required_distances(const oqg_gsim *g);
  * An unknown family or flag is an error (there is no fallback). */
 int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
                   const double *coeffs);
+/* ContextMaker.horiz_comp_to_geom_mean (hazardlib/contexts.py:761-776, the
+ * conversion tables of set_imts_conv :726-746): conv [G][M][3] = conv_median,
+ * conv_sigma, rstd per (gsim, IMT), all zero where there is no conversion;
+ * oqg_mean_stds then returns mean - log(conv_median) and
+ * sqrt((sig^2 - conv_sigma^2) / rstd^2) (tau and phi unchanged, the zero
+ * sigma check comes first, as in get_4MN :1297-1302).  NULL switches it off;
+ * oqg_set_gsims resets it.  The fused pass refuses to run while it is set. */
+int oqg_set_conversion(oqg_handle *h, const double *conv);
+
 /* mask[G][M] (host, may be NULL = none): 1 where the PoEs of (gsim, IMT) are
  * zeroed -- the ImtWeight == 0 branch of set_poes (contexts.py:1469-1475);
  * reset by oqg_set_gsims */
@@ -426,6 +435,13 @@ int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err);
  * last launch used. */
 int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table);
 int oqg_last_fused_subs(oqg_handle *h);
+
+/* Statistics pass of the fused kernel: while on, a call with `counters`
+ * also adds to counters[1] the PoE evaluations the kernel EXECUTES (the
+ * levels its level skipping does not cut off: skipped levels have a PoE of
+ * exactly 0), so that a benchmark can state executed next to nominal
+ * evaluations.  It costs time; leave it off in timed runs. */
+int oqg_set_count_evals(oqg_handle *h, int on);
 
 /* number of kernels launched by this handle so far (for bench accounting) */
 unsigned long long oqg_launch_count(oqg_handle *h);

@@ -32,6 +32,9 @@ def fingerprint():
     return h.hexdigest()
 
 
+kernel_fingerprint = fingerprint   # identifies the build a profile belongs to
+
+
 def stale():
     if not os.path.exists(LIB):
         return True

@@ -62,6 +62,7 @@ def lib():
         'oqg_set_gsims': (C.c_int, [H, C.c_int, C.POINTER(OqgGsim), C.c_int,
                                     c_double_p]),
         'oqg_set_imt_mask': (C.c_int, [H, C.POINTER(C.c_ubyte)]),
+        'oqg_set_conversion': (C.c_int, [H, c_double_p]),
         'oqg_set_levels': (C.c_int, [H, C.c_int, C.c_int, c_double_p,
                                      C.c_double]),
         'oqg_distances': (C.c_int, [H, c_void, C.c_int, C.POINTER(OqgSites),
@@ -127,6 +128,7 @@ def lib():
         'oqg_poe_table_info': (C.c_int, [H, C.POINTER(C.c_int), c_double_p]),
         'oqg_set_fused_config': (C.c_int, [H, C.c_int, C.c_int]),
         'oqg_last_fused_subs': (C.c_int, [H]),
+        'oqg_set_count_evals': (C.c_int, [H, C.c_int]),
         'oqg_launch_count': (C.c_ulonglong, [H]),
         'oqg_last_fused_ms': (C.c_int, [H, C.POINTER(C.c_float), C.c_int]),
         'oqg_measure_fp64_peak': (C.c_int, [H, c_double_p]),

@@ -761,13 +761,17 @@ class ContextMaker(object):
         """maximum distance for each magnitude"""
         return numpy.array([float(self.maximum_distance(m)) for m in mags])
 
-    def hazard_planar(self, pmap, src, sitecol, count=False):
+    def hazard_planar(self, pmap, src, sitecol, count=False, aux=None):
         """
         Fold all the ruptures of `src` (PlanarRuptures) on the sites into
         `pmap` in one fused pass: the equivalent of
         ``for ctx in get_ctxs(src, sitecol): update(pmap, ctx)`` without
         materialising the context rows.  Returns the number of rupture-site
-        pairs kept by the distance filter if `count`.
+        pairs kept by the distance filter if `count`.  `aux` (U, 5) float64,
+        optional: the per-rupture records [x, y, z of the source location in
+        km, psdist, mode] of the pointsource_distance approximation
+        (oqg_hazard_planar_aux; mode 0 all sites, 1 the sites within psdist
+        of the location, 2 the others).
         """
         import torch
         h = self.handle()
@@ -789,8 +793,10 @@ class ContextMaker(object):
         t_pla = _dev(as_flat(src.planar), dev)
         t_mag = _dev(src.mag, dev)
         t_md = _dev(self.magdist(src.mag), dev)
+        t_aux = None if aux is None else _dev(
+            numpy.ascontiguousarray(aux, float), dev)
         return self._hazard_planar_dev(pmap, t_pla, t_mag, t_md, t_probs, K,
-                                       U, sitecol, count)
+                                       U, sitecol, count, t_aux)
 
     def _fated(self, U, dev):
         # cluster groups (contexts.py:1243-1246): every rupture happens once

@@ -86,7 +86,8 @@ struct oqg_handle {
   double truncation_level = 0, phi_b = 0;
   bool const_dirty = true;
   unsigned long long launches = 0;
-  Buf rup, site, part, ptab, stage[12];
+  Buf rup, site, part, ptab, conv, stage[12];
+  bool has_conv = false;       // oqg_set_conversion
   bool fast_ok = false, exact_poe = false, sorted = false;
   int pt_nodes = 0;
   double ptab_err = 0., xscale = 0.;
@@ -96,6 +97,7 @@ struct oqg_handle {
   int n_fused_ev = 0;
   int sm_count = 148;
   int fused_cfg[2] = {0, 0};   // oqg_set_fused_config
+  bool count_evals = false;    // oqg_set_count_evals
   int last_subs = 1;
 };
 
@@ -186,15 +188,20 @@ struct ConstGuard {
 };
 
 // ----------------------------------------------------------- prep kernels
+// the prepared ruptures are stored [NF_RUP][Us] with the stride Us = U rounded
+// up to even, so that pairs of ruptures are 16-byte aligned in every field
+// (the fused kernel fetches its rupture tiles with 16-byte cp.async)
+static inline int64_t rup_stride(int64_t U) { return (U + 1) & ~(int64_t)1; }
+
 __global__ void k_prep_ruptures(const double *__restrict__ planar,
                                 const double *__restrict__ mag,
                                 const double *__restrict__ magdist, int64_t U,
-                                double *__restrict__ out) {
+                                int64_t Us, double *__restrict__ out) {
   int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
   double pl[OQG_PLANAR_LEN];
   for (int k = 0; k < OQG_PLANAR_LEN; k++) pl[k] = planar[u * OQG_PLANAR_LEN + k];
-  prep_rupture(pl, mag[u], magdist ? magdist[u] : INFINITY, out + u, U);
+  prep_rupture(pl, mag[u], magdist ? magdist[u] : INFINITY, out + u, Us);
 }
 
 // one thread per rupture of a batch of point sources (oqg_source.cuh).
@@ -302,8 +309,8 @@ __global__ void k_prep_sites(const double *__restrict__ lon,
 // -------------------------------------------------------------- distances
 // out[k][U][N]; one thread per site, blockIdx.y strides over the ruptures
 __global__ void k_distances(const double *__restrict__ rup, int U,
-                            const double *__restrict__ site, int N, int mask,
-                            double *__restrict__ out) {
+                            int64_t Us, const double *__restrict__ site,
+                            int N, int mask, double *__restrict__ out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double sx[3], sq[3], sdep;
@@ -314,7 +321,7 @@ __global__ void k_distances(const double *__restrict__ rup, int U,
   sdep = site[(int64_t)SF_DEPTH * N + n];
   for (int u = blockIdx.y; u < U; u += gridDim.y) {
     Dist d;
-    pair_distances(rup + u, U, sx, sq, sdep, mask, d);
+    pair_distances(rup + u, Us, sx, sq, sdep, mask, d);
     const double vals[OQG_NOUT] = {d.rrup, d.rjb, d.rx, d.ry0, d.repi,
                                    d.rhypo, d.azimuth, d.clon, d.clat};
     int plane = 0;
@@ -339,7 +346,8 @@ __device__ __forceinline__ double ld(const double *p, int64_t i) {
 template <int F>
 __global__ void __launch_bounds__(128)
 k_mean_stds(int g, int G, int M, CtxDev cd, int64_t P,
-            double *__restrict__ out, int *__restrict__ flag) {
+            double *__restrict__ out, int *__restrict__ flag,
+            const double *__restrict__ conv) {
   typedef typename Fam<F>::C CT;
   int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -360,11 +368,22 @@ k_mean_stds(int g, int G, int M, CtxDev cd, int64_t P,
     const CT &C = *reinterpret_cast<const CT *>(c_coef[g * (M + 1) + m]);
     Out o = Fam<F>::imt(gs, C, Cp, r, st);
     int64_t idx = ((int64_t)g * M + m) * P + p;
+    // the zero-sigma check of get_4MN comes BEFORE the conversion
+    // (contexts.py:1297-1302)
+    if (o.sig == 0.) *flag = 1;  // benign race: every writer stores 1
+    if (conv) {
+      // horiz_comp_to_geom_mean (contexts.py:761-776): [log conv_median,
+      // conv_sigma^2, 1 / rstd^2] per (gsim, IMT); tau and phi stay
+      const double *cv = conv + (g * M + m) * 3;
+      if (cv[2] != 0.) {
+        o.mean -= cv[0];
+        o.sig = sqrt((o.sig * o.sig - cv[1]) * cv[2]);
+      }
+    }
     out[idx] = o.mean;
     out[plane + idx] = o.sig;
     out[2 * plane + idx] = o.tau;
     out[3 * plane + idx] = o.phi;
-    if (o.sig == 0.) *flag = 1;  // benign race: every writer stores 1
   }
 }
 
@@ -515,7 +534,7 @@ struct FusedArgs {
   unsigned pt_bias;
   double *part;           // [RC][G][N][L]
   unsigned long long *counters;
-  int64_t U;
+  int64_t U, Us;          // ruptures, stride of the fields of `rup`
   int N, K;
   int g, G, M, L1;
   int nlc;                // level chunks per IMT
@@ -572,6 +591,12 @@ __device__ __forceinline__ T ld_soa(const double *base, int stride) {
 // of s_dist and every shared-memory offset of the fused kernel are then
 // compile-time constants (immediates in the LDS / STS instead of address
 // registers and IMADs)
+// rupture parameters the stages after the distances read (a copy of those
+// fields of the rupture tile: s_rup itself is refilled with the next tile
+// while the tile is evaluated)
+enum { PF_MAG, PF_RAKE, PF_DIP, PF_ZTOR, PF_WIDTH, PF_HYPO_DEPTH, PF_RATE,
+       NPAR = 8 };
+
 template <int F> struct DistMask {
   static constexpr int value =
       F == OQG_BSSA14 || F == OQG_BA08 ? (1 << OQG_RRUP) | (1 << OQG_RJB)
@@ -600,9 +625,11 @@ template <int F, bool NEGBIN, bool FAST> struct FusedLayout {
   static constexpr int SITE = DIST + NPL * RT * 32;      // [NF_SITE][32]
   static constexpr int SQ = SITE + NF_SITE * 32;         // [NWMAX + 1][RT][QW]
   static constexpr int SP = SQ + (NWMAX + 1) * RT * QW;  // [PW][RT][32]
-  static constexpr int PROBS = SP + PW * RT * 32;        // [RT][OQG_MAX_OCC]
+  static constexpr int PAR = SP + PW * RT * 32;          // [NPAR][RT]
+  static constexpr int PROBS = PAR + NPAR * RT;          // [RT][OQG_MAX_OCC]
   static constexpr int VALID = PROBS + (NEGBIN ? RT * OQG_MAX_OCC : 0);  // u32 [RT]
-  static constexpr int HI = VALID + RT / 2;              // f32 [NL - NLR][32 NWMAX]
+  static constexpr int CNT = VALID + RT / 2;             // u64 evaluation counter (+ pad)
+  static constexpr int HI = CNT + 2;                     // f32 [NL - NLR][32 NWMAX]
   static constexpr int SIZE =
       (HI + (FAST ? (NL - NLR) * 32 * NWMAX / 2 : 0) + 1) / 2 * 2;
 };
@@ -626,7 +653,12 @@ k_fused(const FusedArgs A) {
   // (compile-time offsets, FusedLayout), then the PoE table.
   const int nw = A.nw;
   const int tb = nw << 5;                          // threads of a sub-CTA
-  const int wall = threadIdx.x >> 5;
+  // REDUX leaves the warp index in a UNIFORM register: the compiler then
+  // knows that everything derived from it (the IMT of this warp, its
+  // coefficient row, its levels) is warp-uniform and reads the __constant__
+  // tables through the uniform datapath (LDCU / UR operands) instead of
+  // per-thread indexed LDC into vector registers
+  const int wall = __reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
   const int sub = SUBS == 1 ? 0 : wall / nw;
   const int warp = wall - sub * nw;
   const int lane = threadIdx.x & 31;
@@ -639,8 +671,10 @@ k_fused(const FusedArgs A) {
   double *const s_site = s_base + LY::SITE;
   double *const s_q = s_base + LY::SQ;
   double *const s_p = s_base + LY::SP;
+  double *const s_par = s_base + LY::PAR;
   double *const s_probs = s_base + LY::PROBS;
   unsigned *const s_valid = (unsigned *)(s_base + LY::VALID);
+  unsigned long long *const s_cnt = (unsigned long long *)(s_base + LY::CNT);
   float *const s_hi = (float *)(s_base + LY::HI) + tid;   // [NL - NLR][32 NWMAX]
   constexpr int hs = 32 * NWMAX;
   // barrier among the threads of this sub-CTA
@@ -675,6 +709,7 @@ k_fused(const FusedArgs A) {
     int f = i >> 5, j = i & 31;
     s_site[i] = site0 + j < A.N ? A.site[(int64_t)f * A.N + site0 + j] : 0.;
   }
+  if (tid == 0) *s_cnt = 0ull;
   // pt_bias = -(0x4b000000 * 16 * REP) mod 2^32 comes in as a kernel
   // argument: as a literal the compiler splits it off again and adds it back
   // before every load
@@ -726,28 +761,54 @@ k_fused(const FusedArgs A) {
 #define DGET(k) (((DM >> (k)) & 1) ? s_dist[(popc_below(DM, k) * RT + i) * 32 + lane] : 0.)
 #define LOAD_PAIR(i)                                                       \
   RupIn ri;                                                                \
-  ri.mag = s_rup[RF_MAG * RT + i];                                         \
-  ri.rake = s_rup[RF_RAKE * RT + i];                                       \
-  ri.dip = s_rup[RF_DIP * RT + i];                                         \
-  ri.ztor = s_rup[RF_ZTOR * RT + i];                                       \
-  ri.width = s_rup[RF_WIDTH * RT + i];                                     \
-  ri.hypo_depth = s_rup[RF_HYPO_DEPTH * RT + i];                           \
+  ri.mag = s_par[PF_MAG * RT + i];                                         \
+  ri.rake = s_par[PF_RAKE * RT + i];                                       \
+  ri.dip = s_par[PF_DIP * RT + i];                                         \
+  ri.ztor = s_par[PF_ZTOR * RT + i];                                       \
+  ri.width = s_par[PF_WIDTH * RT + i];                                     \
+  ri.hypo_depth = s_par[PF_HYPO_DEPTH * RT + i];                           \
   Dist dd;                                                                 \
   dd.rrup = DGET(OQG_RRUP); dd.rjb = DGET(OQG_RJB);                        \
   dd.rx = DGET(OQG_RX); dd.ry0 = DGET(OQG_RY0);                            \
   dd.repi = DGET(OQG_REPI); dd.rhypo = DGET(OQG_RHYPO);
 
+  // The rupture tile [NF_RUP][RT] is fetched with 16-byte cp.async (two
+  // ruptures of one field), zero-filled past the end of the chunk.  The
+  // stages after the distances only read the copy s_par of the rupture
+  // parameters, so the fetch of the NEXT tile is issued as soon as the pair
+  // stage is done and flies during the evaluation of this one (78 % of the
+  // loop): its latency was 10-12 % of the kernel when it was a plain load
+  // between two barriers.
+  auto fetch_tile = [&](int64_t r0) {
+    const int nr = (int)min((int64_t)RT, r_end - r0);
+    for (int i = tid; i < NF_RUP * (RT / 2); i += tb) {
+      const int f = i / (RT / 2), j = (i - f * (RT / 2)) * 2;
+      const int nb = min(max(nr - j, 0), 2) * 8;          // bytes to read
+      const double *src = A.rup + (int64_t)f * A.Us + r0 + (nb ? j : 0);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rup + f * RT + j);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                   "l"(src), "r"(nb) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (r_begin < r_end) fetch_tile(r_begin);
   for (int64_t r0 = r_begin; r0 < r_end; r0 += RT) {
     const int nr = (int)min((int64_t)RT, r_end - r0);
-    SUB_SYNC();
-    for (int i = tid; i < NF_RUP * RT; i += tb) {
-      int f = i / RT, j = i - f * RT;
-      s_rup[i] = j < nr ? A.rup[(int64_t)f * A.U + r0 + j] : 0.;
-    }
-    if (NEGBIN)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    SUB_SYNC();   // tile r0 is in s_rup; everybody is done with the last one
+    if (NEGBIN) {
       for (int i = tid; i < nr * A.K; i += tb)
         s_probs[(i / A.K) * OQG_MAX_OCC + i % A.K] = A.probs[r0 * A.K + i];
-    SUB_SYNC();
+    }
+    if (warp == 0 && lane < RT) {
+      s_par[PF_MAG * RT + lane] = s_rup[RF_MAG * RT + lane];
+      s_par[PF_RAKE * RT + lane] = s_rup[RF_RAKE * RT + lane];
+      s_par[PF_DIP * RT + lane] = s_rup[RF_DIP * RT + lane];
+      s_par[PF_ZTOR * RT + lane] = s_rup[RF_ZTOR * RT + lane];
+      s_par[PF_WIDTH * RT + lane] = s_rup[RF_WIDTH * RT + lane];
+      s_par[PF_HYPO_DEPTH * RT + lane] = s_rup[RF_HYPO_DEPTH * RT + lane];
+      s_par[PF_RATE * RT + lane] = s_rup[RF_RATE * RT + lane];
+    }
     // ---- distances: rupture i of the tile by warp i % nw, lane = site
     for (int i = warp; i < nr; i += nw) {
       double sx[3], sq[3];
@@ -823,6 +884,8 @@ k_fused(const FusedArgs A) {
       }
     }
     SUB_SYNC();
+    // s_rup is dead from here on: fetch the next tile into it
+    if (r0 + RT < r_end) fetch_tile(r0 + RT);
     // ---- the IMT-independent part of the model, once per pair, shared by
     // the IMT warps through shared memory
     if (FF::HAS_P) {
@@ -854,7 +917,7 @@ k_fused(const FusedArgs A) {
         // x = (tl - (l - mean) / sig) * xscale, xscale = 1 / (2 tl)
         const double xa = -inv * A.xscale;
         const double xb = (A.tl + mean * inv) * A.xscale;
-        const float rt = (float)(s_rup[RF_RATE * RT + i] * A.itime);
+        const float rt = (float)(s_par[PF_RATE * RT + i] * A.itime);
         // levels are sorted: from the first one at or above mean + tl * sig
         // for every lane of the warp on, all the PoEs are zero (the padding
         // levels are +inf).  The threshold is reduced over the warp in
@@ -866,6 +929,17 @@ k_fused(const FusedArgs A) {
         key = __reduce_max_sync(vm, key);
         key ^= (key >> 31) & 0x7fffffff;
         const double thr_w = A.sorted ? (double)__int_as_float(key) : INFINITY;
+        if (A.count_pairs > 1 && lane == __ffs(vm) - 1) {
+          // statistics pass only (oqg_set_count_evals): the evaluations this
+          // warp executes for this rupture, i.e. the levels the skipping
+          // below does not cut off, times the active lanes
+          int nlev = 0;
+#pragma unroll
+          for (int l = 0; l < NLR; l += LGRP) nlev += ll[l] < thr_w ? LGRP : 0;
+#pragma unroll
+          for (int l = NLR; l < NL; l++) nlev += ll[l] < thr_w ? 1 : 0;
+          atomicAdd(s_cnt, (unsigned long long)(nlev * __popc(vm)));
+        }
         // The test is made once per LGRP levels: the evaluations of a group
         // are independent instruction chains in one basic block (a level
         // past the threshold evaluates to exactly 0: x saturates to node 0)
@@ -894,7 +968,7 @@ k_fused(const FusedArgs A) {
           acc[l] *= A.itime == 0. ? 1. - poe : pne_from_pmf(pr, A.K, poe);
         }
       } else {
-        const double rt = s_rup[RF_RATE * RT + i] * A.itime;
+        const double rt = s_par[PF_RATE * RT + i] * A.itime;
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           double poe = truncnorm_sf(A.phi_b, A.inv_norm, (ll[l] - mean) * inv);
@@ -920,9 +994,13 @@ k_fused(const FusedArgs A) {
   }
 #undef DGET
 #undef LOAD_PAIR
-#undef SUB_SYNC
   if (A.count_pairs && lane == 0 && kept)
     atomicAdd(A.counters, kept);  // statistics only, not the map
+  if (FAST && A.count_pairs > 1) {
+    SUB_SYNC();
+    if (tid == 0 && *s_cnt) atomicAdd(A.counters + 1, *s_cnt);
+  }
+#undef SUB_SYNC
   if (FAST || !writer) return;
 #pragma unroll
   for (int l = 0; l < NL; l++)
@@ -1086,7 +1164,7 @@ void oqg_destroy(oqg_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (Buf *b : {&h->rup, &h->site, &h->part, &h->ptab}) if (b->p) cudaFree(b->p);
+  for (Buf *b : {&h->rup, &h->site, &h->part, &h->ptab, &h->conv}) if (b->p) cudaFree(b->p);
   for (auto &b : h->stage) if (b.p) cudaFree(b.p);
   if (h->flag_dev) cudaFree(h->flag_dev);
   for (auto &ev : h->ev) cudaEventDestroy(ev);
@@ -1156,6 +1234,7 @@ int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   h->G = G; h->M = M;
+  h->has_conv = false;
   h->gsims.assign(gsims, gsims + G);
   h->imtmask.assign(OQG_MAX_SLOTS, 0);
   h->coef.assign(coeffs, coeffs + (size_t)G * (M + 1) * OQG_KMAX);
@@ -1170,6 +1249,29 @@ int oqg_set_gsims(oqg_handle *h, int G, const oqg_gsim *gsims, int M,
       }
     }
   h->const_dirty = true;
+  return 0;
+}
+
+int oqg_set_conversion(oqg_handle *h, const double *conv) {
+  if (!h->G || !h->M) return fail(h, "set_conversion: set_gsims not called");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->has_conv = false;
+  if (!conv) return 0;
+  std::vector<double> t((size_t)h->G * h->M * 3, 0.);
+  bool any = false;
+  for (int i = 0; i < h->G * h->M; i++) {
+    const double cm = conv[3 * i], cs = conv[3 * i + 1], rs = conv[3 * i + 2];
+    if (cm == 0. && cs == 0. && rs == 0.) continue;   // no conversion
+    if (!(cm > 0.) || !(rs > 0.))
+      return fail(h, "set_conversion: conv_median and rstd must be positive");
+    t[3 * i] = log(cm); t[3 * i + 1] = cs * cs; t[3 * i + 2] = 1. / (rs * rs);
+    any = true;
+  }
+  if (!any) return 0;
+  if (reserve(h, h->conv, t.size() * 8)) return 1;
+  CK(cudaMemcpy(h->conv.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+  h->has_conv = true;
   return 0;
 }
 
@@ -1240,9 +1342,9 @@ static int prep_sites(oqg_handle *h, const oqg_sites *s, int N) {
 
 static int prep_ruptures(oqg_handle *h, const double *planar,
                          const double *mag, const double *magdist, int64_t U) {
-  if (reserve(h, h->rup, (size_t)NF_RUP * U * 8)) return 1;
+  if (reserve(h, h->rup, (size_t)NF_RUP * rup_stride(U) * 8)) return 1;
   k_prep_ruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
-      planar, mag, magdist, U, (double *)h->rup.p);
+      planar, mag, magdist, U, rup_stride(U), (double *)h->rup.p);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1726,6 +1828,7 @@ int oqg_distances(oqg_handle *h, const double *planar, int U,
   if (prep_sites(h, sites, N)) return 1;
   dim3 grid((N + 127) / 128, std::min(U, 4096));
   k_distances<<<grid, 128, 0, h->stream>>>((const double *)h->rup.p, U,
+                                           rup_stride(U),
                                            (const double *)h->site.p, N, mask,
                                            out);
   h->launches++;
@@ -1741,7 +1844,8 @@ static void launch_mean_stds(oqg_handle *h, int g, const oqg_ctx *ctx,
   CtxDev cd;
   cd.c = *ctx;
   k_mean_stds<F><<<(unsigned)((P + 127) / 128), 128, 0, h->stream>>>(
-      g, h->G, h->M, cd, P, out, h->flag_dev);
+      g, h->G, h->M, cd, P, out, h->flag_dev,
+      h->has_conv ? (const double *)h->conv.p : nullptr);
 }
 
 template <int F>
@@ -1911,7 +2015,9 @@ static cudaError_t launch_fused2(const FusedArgs &A, dim3 grid, int threads,
   return cudaGetLastError();
 }
 
+#ifndef OQG_SUBS_MAX
 #define OQG_SUBS_MAX 4
+#endif
 #define OQG_SMEM_SM (227 * 1024 - 4096)   // per SM, minus the static tables
 
 // Launch of one model.  Fast path with a 256-node table: `subs` sub-CTAs per
@@ -1987,6 +2093,10 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   if (U <= 0 || N <= 0) return 0;
   if (K < 0 || K > OQG_MAX_OCC) return fail(h, "bad probs_occur length");
   if (K && !probs) return fail(h, "probs_occur missing");
+  if (h->has_conv)
+    return fail(h, "the fused pass has no horizontal-component conversion: "
+                   "use the context operators (oqg_mean_stds, oqg_poes, "
+                   "oqg_update)");
   const int G = h->G, M = h->M, L1 = h->L1, L = M * L1;
   ConstGuard guard(h);
   if (guard.acquire()) return 1;
@@ -2002,7 +2112,7 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   A.vs30 = sites->vs30; A.z1pt0 = sites->z1pt0; A.z2pt5 = sites->z2pt5;
   A.vs30measured = sites->vs30measured;
   A.counters = counters;
-  A.U = U; A.N = N; A.K = K; A.G = G; A.M = M; A.L1 = L1;
+  A.U = U; A.Us = rup_stride(U); A.N = N; A.K = K; A.G = G; A.M = M; A.L1 = L1;
   A.nlc = (L1 + NL - 1) / NL;
   A.lpc = (L1 + A.nlc - 1) / A.nlc;
   A.nunits = M * A.nlc;
@@ -2042,7 +2152,9 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
     A.clampmask = required_distances(gs);
     A.dmask = A.clampmask | (1 << OQG_RRUP);
     if (A.dmask & (1 << OQG_RHYPO)) A.dmask |= 1 << OQG_REPI;
-    A.count_pairs = counters && g == 0;  // blockIdx.z == 0 only
+    // pairs: model 0, blockIdx.z == 0 only; executed evaluations (statistics
+    // pass, oqg_set_count_evals): every model and unit group
+    A.count_pairs = !counters ? 0 : (h->count_evals ? 2 : (g == 0 ? 1 : 0));
     // only blockIdx.z == 0 counts pairs
     cudaError_t e = cudaSuccess;
     A.nw = nw;
@@ -2142,6 +2254,11 @@ int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table) {
 }
 
 int oqg_last_fused_subs(oqg_handle *h) { return h->last_subs; }
+
+int oqg_set_count_evals(oqg_handle *h, int on) {
+  h->count_evals = on != 0;
+  return 0;
+}
 
 int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err) {
   *in_use = h->fast_ok && !h->exact_poe;

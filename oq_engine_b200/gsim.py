@@ -28,9 +28,10 @@ class GMPE(object):
     family = None
     tables = {}   # prefix -> table name; '' is the main table
 
-    def __init_subclass__(cls, **kw):
+    def __init_subclass__(cls, register=True, **kw):
         super().__init_subclass__(**kw)
-        registry[cls.__name__] = cls
+        if register:     # by class name, for get_gsim
+            registry[cls.__name__] = cls
 
     def __init__(self, **kwargs):
         self.kwargs = kwargs

@@ -58,38 +58,68 @@ def combine_maps(array, rates, group=None):
     return array
 
 
-def gather_tiles(tile_array, tile_sids, n_sites, group=None):
+def gather_tiles(tile_array, tile_sids, sids, group=None, partial=False):
     """
-    Assemble the whole (n_sites, L, G) map from the site tiles of the ranks
-    (all_gather of equally padded tiles); returns a tensor on every rank
+    Assemble the whole (N, L, G) map from the site tiles of the ranks;
+    returns a tensor on every rank, rows in the order of `sids`.
+
+    :param tile_array: (n_k, L, G) tensor of this rank
+    :param tile_sids: the site IDs of its rows
+    :param sids: the site IDs of the complete site collection (any unique
+        integers: a filtered collection has gaps), or their number N when
+        they are 0 .. N-1
+
+    The tiles may have any sizes: their lengths are all-gathered first and
+    the tiles padded to the longest.  Every site must be owned by exactly one
+    rank; a site nobody owns is an error, not an uninitialised row (unless
+    `partial`: then such rows are zero, for callers that assemble the tiles
+    of several ranks themselves).
     """
     import torch
     import torch.distributed as dist
+    dev = tile_array.device
+    if numpy.isscalar(sids):
+        sids = numpy.arange(int(sids), dtype=numpy.int64)
+    sids = numpy.asarray(sids, numpy.int64)
+    N = len(sids)
+    tile_sids = numpy.asarray(tile_sids, numpy.int64)
+    assert len(tile_sids) == len(tile_array), (len(tile_sids), len(tile_array))
+    # site ID -> row of the assembled map
+    order = numpy.argsort(sids, kind='stable')
+    pos = numpy.searchsorted(sids[order], tile_sids)
+    if len(tile_sids) and (pos.max(initial=0) >= N or
+                           (sids[order][pos] != tile_sids).any()):
+        raise ValueError('gather_tiles: a tile holds site IDs that are not '
+                         'in the site collection')
+    rows = torch.as_tensor(order[pos], dtype=torch.int64, device=dev)
+    shape = tuple(tile_array.shape[1:])
+    out = torch.zeros((N,) + shape, dtype=tile_array.dtype, device=dev)
+    seen = torch.zeros(N, dtype=torch.int32, device=dev)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        out = torch.empty((n_sites,) + tuple(tile_array.shape[1:]),
-                          dtype=tile_array.dtype, device=tile_array.device)
-        out[torch.as_tensor(numpy.asarray(tile_sids, numpy.int64),
-                            device=tile_array.device)] = tile_array
-        return out
-    world = dist.get_world_size(group)
-    nmax = (n_sites + world - 1) // world
-    L, G = tile_array.shape[1:]
-    pad = torch.zeros((nmax, L, G), dtype=tile_array.dtype,
-                      device=tile_array.device)
-    pad[:len(tile_array)] = tile_array
-    sids = torch.full((nmax,), -1, dtype=torch.int64,
-                      device=tile_array.device)
-    sids[:len(tile_sids)] = torch.as_tensor(
-        numpy.asarray(tile_sids, numpy.int64), device=tile_array.device)
-    tiles = [torch.empty_like(pad) for _ in range(world)]
-    allsids = [torch.empty_like(sids) for _ in range(world)]
-    dist.all_gather(tiles, pad, group=group)
-    dist.all_gather(allsids, sids, group=group)
-    out = torch.empty((n_sites, L, G), dtype=tile_array.dtype,
-                      device=tile_array.device)
-    for t, s in zip(tiles, allsids):
-        ok = s >= 0
-        out[s[ok]] = t[ok]
+        out[rows] = tile_array
+        seen[rows] += 1
+    else:
+        world = dist.get_world_size(group)
+        n = torch.tensor([len(tile_array)], dtype=torch.int64, device=dev)
+        lens = [torch.empty_like(n) for _ in range(world)]
+        dist.all_gather(lens, n, group=group)
+        nmax = max(int(x.item()) for x in lens)
+        pad = torch.zeros((nmax,) + shape, dtype=tile_array.dtype, device=dev)
+        pad[:len(tile_array)] = tile_array
+        prow = torch.full((nmax,), -1, dtype=torch.int64, device=dev)
+        prow[:len(rows)] = rows
+        tiles = [torch.empty_like(pad) for _ in range(world)]
+        allrows = [torch.empty_like(prow) for _ in range(world)]
+        dist.all_gather(tiles, pad, group=group)
+        dist.all_gather(allrows, prow, group=group)
+        for t, r in zip(tiles, allrows):
+            ok = r >= 0
+            out[r[ok]] = t[ok]
+            seen[r[ok]] += 1
+    if not partial and not bool((seen == 1).all()):
+        raise ValueError('gather_tiles: %d sites have no owner and %d have '
+                         'several' % (int((seen == 0).sum()),
+                                      int((seen > 1).sum())))
     return out
 
 

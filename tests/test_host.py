@@ -149,8 +149,23 @@ def test_negbin_tom_matches_reference_fixture():
 def test_integration_distance():
     md = oq.IntegrationDistance.new('[(4., 50), (8., 200.)]')
     f = md('Active Shallow Crust')
-    assert f(6.0) == 125. and f(3.0) == 50. and f(9.0) == 200.
-    assert oq.IntegrationDistance.new('300')('x')(7.3) == 300.
+    assert f(6.0) == 125. and f(4.0) == 50. and f(8.0) == 200.
+    # outside the pairs the distance is ZERO like the reference's
+    # interp1d(bounds_error=False, fill_value=0.) (calc/filters.py:183-190):
+    # such ruptures are dropped by the rrup < magdist filter
+    assert f(3.0) == 0. and f(9.0) == 0.
+    g = oq.IntegrationDistance.new('300')('x')
+    assert g(7.3) == 300. and g(2.4) == 0. and g(10.3) == 0.
+    # parsed like the reference's floatdict (ast.literal_eval, never eval)
+    with pytest.raises(ValueError):
+        oq.IntegrationDistance.new('__import__("os").getcwd()')
+    with pytest.raises(ValueError, match='Invalid magnitude'):
+        oq.IntegrationDistance.new('[(1., 50), (8., 200.)]')
+    with pytest.raises(ValueError, match='not ordered'):
+        oq.IntegrationDistance.new('[(8., 200.), (4., 50)]')
+    md2 = oq.IntegrationDistance.new(
+        "{'default': 200, 'Stable Shallow Crust': [(5, 100), (7, 300)]}")
+    assert md2('Stable Shallow Crust')(6.) == 200. and md2('x')(6.) == 200.
     cm = oq.ContextMaker('*', [oq.BooreEtAl2014()],
                          dict(imtls={'PGA': [0.1]}, maximum_distance=md))
     np.testing.assert_allclose(cm.magdist([4., 6., 8.]), [50., 125., 200.])
