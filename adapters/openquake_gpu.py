@@ -380,10 +380,6 @@ class GpuContextMaker(ContextMaker):
     """
     def __init__(self, trt, gsims, oq, monitor=Monitor(), extraparams=()):
         super().__init__(trt, gsims, oq, monitor, extraparams)
-        if getattr(self, 'conv', None) and any(self.conv.values()):
-            raise NotImplementedError(
-                'horizontal component conversion has no device '
-                'implementation')
         pack_gsims(list(self.gsims), [i.string for i in self.imts])  # validate
         self._engine = None
 
@@ -412,7 +408,12 @@ class GpuContextMaker(ContextMaker):
                 minimum_distance=self.minimum_distance,
                 pointsource_distance=getattr(self, 'pointsource_distance', 0),
                 max_sites_disagg=self.max_sites_disagg,
-                shift_hypo=self.shift_hypo)
+                shift_hypo=self.shift_hypo,
+                # horiz_comp_to_geom_mean: the reference's own coefficients
+                conv={g: {imt.string: tuple(map(float, cv))
+                          for imt, cv in self.conv[gsim].items()}
+                      for g, gsim in enumerate(self.gsims)
+                      if self.conv.get(gsim)})
             self._engine = _gpu.ContextMaker(
                 self.trt, [PackedGsim(g) for g in self.gsims], param)
         eng = self._engine
@@ -456,6 +457,10 @@ class GpuContextMaker(ContextMaker):
         update(pmap, ctx)``.  Returns the number of rupture-site pairs kept.
         """
         eng = self.engine
+        if eng.conv:
+            raise NotImplementedError(
+                'the fused pass has no horizontal component conversion: use '
+                'update()')
         dsites = _device_sitecol(sitecol)
         dmap = _device_map(pmap)
         kept = 0

@@ -315,6 +315,22 @@ int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon_dev,
                     const double *strike_dev, int S,
                     const oqg_sites *sites_dev, int N, double *rx_dev,
                     double *ry0_dev);
+/* RectangularMesh.get_joyner_boore_distance (hazardlib/geo/mesh.py:453-540,
+ * _get_proj_enclosing_polygon :541-597) for S rectangular meshes at once:
+ * lon_dev / lat_dev [P] the points of all the meshes (row-major), off_dev
+ * [S + 1] their offsets, shape_dev [S][2] rows and columns, owner_dev [P] the
+ * mesh of every point, frame_dev [S][9] the east, north and radial unit
+ * vectors at the centre of the orthographic projection of each mesh (the
+ * middle point of its spherical bounding box, geo/utils.py:652-658) ->
+ * out_dev [S][N] km: the minimum chord distance of the surface projections
+ * beyond 40 km, the distance to the union of the mesh cells (zero inside)
+ * below.  Agrees with the reference to the 0.02 km of the reference's own
+ * tests (shapely grows, simplifies and rounds the polygon by up to 10 m). */
+int oqg_mesh_rjb(oqg_handle *h, const double *lon_dev, const double *lat_dev,
+                 int64_t P, const int64_t *off_dev, const int32_t *shape_dev,
+                 const int32_t *owner_dev, const double *frame_dev, int S,
+                 const oqg_sites *sites, int N, double *out_dev);
+
 /* Mean dip, strike and width of S rectangular meshes:
  * RectangularMesh.get_mean_inclination_and_azimuth (hazardlib/geo/mesh.py:
  * 728-783) and get_mean_width (mesh.py:861-885), the surface.get_dip() /

@@ -108,6 +108,9 @@ def lib():
         'oqg_mesh_rx_ry0': (C.c_int, [
             H, c_void, c_void, c_void, c_void, C.c_int, C.POINTER(OqgSites),
             C.c_int, c_void, c_void]),
+        'oqg_mesh_rjb': (C.c_int, [
+            H, c_void, c_void, C.c_int64, c_void, c_void, c_void, c_void,
+            C.c_int, C.POINTER(OqgSites), C.c_int, c_void]),
         'oqg_mesh_dip_strike_width': (C.c_int, [
             H, c_void, c_void, c_void, c_void, c_void, C.c_int, c_void]),
         'oqg_section_min': (C.c_int, [H, c_void, C.c_int, C.c_int, c_void,

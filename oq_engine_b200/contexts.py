@@ -345,6 +345,16 @@ class ContextMaker(object):
         self.pointsource_distance = float(psd)
         self.truncation_level = param.get('truncation_level', 99.)
         self.phi_b = float(ndtr(self.truncation_level))
+        # horizontal component conversion (set_imts_conv, contexts.py:726-746):
+        # `conv` = {gsim index: {imt string: (conv_median, conv_sigma, rstd)}}
+        # as the reference builds it from IMC.apply_conversion; the name of a
+        # component (`horiz_comp`) alone is an error here: the conversion
+        # tables are not part of this package
+        self.conv = param.get('conv') or {}
+        if param.get('horiz_comp') and not self.conv:
+            raise NotImplementedError(
+                'horiz_comp needs the conversion coefficients: pass '
+                'conv={g: {imt: (conv_median, conv_sigma, rstd)}}')
         self.device = device
         self.cfactor = numpy.zeros(2)
         self.set_imts_conv()
@@ -412,6 +422,14 @@ class ContextMaker(object):
             if mask.any():
                 h.call('oqg_set_imt_mask', mask.ctypes.data_as(
                     ctypes.POINTER(ctypes.c_ubyte)))
+            if self.conv:
+                cv = numpy.zeros((self.G, self.M, 3))
+                for g, dic in self.conv.items():
+                    for m, imt in enumerate(self.imtls):
+                        if imt in dic:
+                            cv[g, m] = dic[imt]
+                h.call('oqg_set_conversion',
+                       cv.ctypes.data_as(_lib.c_double_p))
             h.owner = self
             h.cfg = (self.L, self.G)
         return h
@@ -575,7 +593,13 @@ class ContextMaker(object):
         return st, keep
 
     def recarray(self, ctxs):
-        """Concatenate context arrays"""
+        """Concatenate context arrays.  An empty list (no rupture within
+        the integration distance) gives an EMPTY context array with the
+        fields of this ContextMaker, not numpy's bare ValueError: callers
+        test ``len(ctx)`` (the reference asserts a non-empty list,
+        contexts.py:798-803, and its callers filter the sources first)"""
+        if len(ctxs) == 0:
+            return self.new_ctx(0)
         if len(ctxs) == 1:
             return ctxs[0]
         return numpy.concatenate(ctxs).view(numpy.recarray)

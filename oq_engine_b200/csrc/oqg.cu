@@ -1395,6 +1395,31 @@ int oqg_mesh_rx_ry0(oqg_handle *h, const double *top_lon,
   return 0;
 }
 
+int oqg_mesh_rjb(oqg_handle *h, const double *lon, const double *lat,
+                 int64_t P, const int64_t *off, const int32_t *shape,
+                 const int32_t *owner, const double *frame, int S,
+                 const oqg_sites *sites, int N, double *out) {
+  CK(cudaSetDevice(h->device));
+  if (S <= 0 || N <= 0) return 0;
+  if (P <= 0 || !lon || !lat || !off || !shape || !owner || !frame || !out)
+    return fail(h, "mesh_rjb: missing array");
+  if (prep_sites(h, sites, N)) return 1;
+  if (reserve(h, h->stage[9], (size_t)P * 3 * 8)) return 1;
+  double *pts = (double *)h->stage[9].p;
+  k_mesh_frame<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(
+      lon, lat, P, owner, frame, pts);
+  h->launches++;
+  for (int y0 = 0; y0 < S; y0 += OQG_GRID_Y) {   // gridDim.y <= 65535
+    dim3 grid((N + 127) / 128, std::min(S - y0, OQG_GRID_Y));
+    k_mesh_rjb<<<grid, 128, 0, h->stream>>>(pts, P, off, shape, frame,
+                                           (const double *)h->site.p, N, out,
+                                           y0);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int oqg_mesh_dip_strike_width(oqg_handle *h, const double *lon,
                               const double *lat, const double *depth,
                               const int64_t *off, const int32_t *shape, int S,

@@ -213,3 +213,68 @@ def mesh_dip_strike_width(meshes, device=None):
            _ptr(t_off), _ptr(t_shape), S, _ptr(out))
     torch.cuda.current_stream(dev).synchronize()
     return out.cpu().numpy()
+
+
+def projection_frames(meshes):
+    """
+    The frames of the orthographic projections of S meshes
+    (geo/utils.py:610-668: centred on the middle point of the spherical
+    bounding box of each mesh): (S, 9) float64 = the east, north and radial
+    unit vectors at the centre.  With them the projection of a point p (unit
+    vector) is (R p.e, R p.n).
+    """
+    from .area import OrthographicProjection, get_spherical_bounding_box
+    out = numpy.zeros((len(meshes), 9))
+    for s, (lons, lats) in enumerate(meshes):
+        proj = OrthographicProjection(*get_spherical_bounding_box(
+            numpy.asarray(lons, float).ravel(),
+            numpy.asarray(lats, float).ravel()))
+        sl, cl = numpy.sin(proj.lam0), numpy.cos(proj.lam0)
+        sp, cp = numpy.sin(proj.phi0), numpy.cos(proj.phi0)
+        out[s, 0:3] = -sl, cl, 0.
+        out[s, 3:6] = -sp * cl, -sp * sl, cp
+        out[s, 6:9] = cp * cl, cp * sl, sp
+    return out
+
+
+def mesh_rjb(meshes, points, device=None, as_tensor=False):
+    """
+    RectangularMesh.get_joyner_boore_distance (geo/mesh.py:453-540) for S
+    rectangular meshes at once.
+
+    :param meshes: a list of S (lons, lats) pairs of 2D arrays (rows, cols);
+        a 1D array is a mesh of one row
+    :param points: a Mesh or a SiteCollection of N points
+    :returns: (S, N) float64 Joyner-Boore distances in km (zero inside the
+        surface projection of a mesh)
+    """
+    import torch
+    from .contexts import get_handle, _device_index, _dev, _ptr
+    h = get_handle(_device_index(device))
+    dev = h.device
+    S = len(meshes)
+    if S == 0:
+        raise ValueError('no mesh')
+    lon, lat, shape, owner = [], [], [], []
+    for s, (lons, lats) in enumerate(meshes):
+        lons = numpy.atleast_2d(numpy.asarray(lons, float))
+        lats = numpy.atleast_2d(numpy.asarray(lats, float))
+        assert lons.shape == lats.shape and lons.ndim == 2, lons.shape
+        lon.append(lons.ravel())
+        lat.append(lats.ravel())
+        shape.append(lons.shape)
+        owner.append(numpy.full(lons.size, s, numpy.int32))
+    off = numpy.concatenate([[0], numpy.cumsum([len(x) for x in lon])]
+                            ).astype(numpy.int64)
+    frames = projection_frames(list(zip(lon, lat)))
+    t_lon, t_lat = _dev(numpy.concatenate(lon), dev), _dev(
+        numpy.concatenate(lat), dev)
+    t_off, t_shape = _dev(off, dev), _dev(numpy.array(shape, numpy.int32), dev)
+    t_owner, t_frame = _dev(numpy.concatenate(owner), dev), _dev(frames, dev)
+    st, keep, N = _sites_struct(points, dev)
+    out = torch.empty((S, N), dtype=torch.float64, device='cuda:%d' % dev)
+    h.call('oqg_mesh_rjb', _ptr(t_lon), _ptr(t_lat), int(off[-1]), _ptr(t_off),
+           _ptr(t_shape), _ptr(t_owner), _ptr(t_frame), S, ctypes.byref(st),
+           N, _ptr(out))
+    torch.cuda.current_stream(dev).synchronize()
+    return out if as_tensor else out.cpu().numpy()

@@ -79,7 +79,10 @@ class RmapMaker(object):
         points = [s for s in srcs if isinstance(s, PointSource)]
         if points:
             for msr in sorted({s.msr for s in points}):
-                batch = PointSourceBatch([s for s in points if s.msr == msr])
+                # the pointsource_distance of the ContextMaker applies here
+                # as in get_ctxs (_quintets, contexts.py:321-370)
+                batch = PointSourceBatch([s for s in points if s.msr == msr],
+                                         cm.pointsource_distance)
                 kept += cm.hazard_point_sources(pmap, batch, self.sitecol,
                                                 count=True)
         for s in srcs:

@@ -93,34 +93,36 @@ def gather_tiles(tile_array, tile_sids, sids, group=None, partial=False):
                          'in the site collection')
     rows = torch.as_tensor(order[pos], dtype=torch.int64, device=dev)
     shape = tuple(tile_array.shape[1:])
-    out = torch.zeros((N,) + shape, dtype=tile_array.dtype, device=dev)
-    seen = torch.zeros(N, dtype=torch.int32, device=dev)
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        out[rows] = tile_array
-        seen[rows] += 1
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi:
+        allrows, tiles = rows, tile_array
     else:
+        # one all_gather of the tile lengths, then one of the padded rows and
+        # one of the padded tiles into contiguous buffers; a padding row
+        # points at the extra row N, dropped at the end
         world = dist.get_world_size(group)
         n = torch.tensor([len(tile_array)], dtype=torch.int64, device=dev)
-        lens = [torch.empty_like(n) for _ in range(world)]
-        dist.all_gather(lens, n, group=group)
-        nmax = max(int(x.item()) for x in lens)
+        lens = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(lens, n, group=group)
+        nmax = int(lens.max().item())
         pad = torch.zeros((nmax,) + shape, dtype=tile_array.dtype, device=dev)
         pad[:len(tile_array)] = tile_array
-        prow = torch.full((nmax,), -1, dtype=torch.int64, device=dev)
+        prow = torch.full((nmax,), N, dtype=torch.int64, device=dev)
         prow[:len(rows)] = rows
-        tiles = [torch.empty_like(pad) for _ in range(world)]
-        allrows = [torch.empty_like(prow) for _ in range(world)]
-        dist.all_gather(tiles, pad, group=group)
-        dist.all_gather(allrows, prow, group=group)
-        for t, r in zip(tiles, allrows):
-            ok = r >= 0
-            out[r[ok]] = t[ok]
-            seen[r[ok]] += 1
-    if not partial and not bool((seen == 1).all()):
-        raise ValueError('gather_tiles: %d sites have no owner and %d have '
-                         'several' % (int((seen == 0).sum()),
-                                      int((seen > 1).sum())))
-    return out
+        tiles = torch.empty((world * nmax,) + shape, dtype=tile_array.dtype,
+                            device=dev)
+        allrows = torch.empty(world * nmax, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(tiles, pad, group=group)
+        dist.all_gather_into_tensor(allrows, prow, group=group)
+    out = torch.zeros((N + 1,) + shape, dtype=tile_array.dtype, device=dev)
+    out.index_copy_(0, allrows, tiles)
+    if not partial:
+        seen = torch.bincount(allrows, minlength=N + 1)[:N]
+        if not bool((seen == 1).all()):
+            raise ValueError('gather_tiles: %d sites have no owner and %d '
+                             'have several' % (int((seen == 0).sum()),
+                                               int((seen > 1).sum())))
+    return out[:N]
 
 
 def hazard_site_sharded(cmaker, src, sitecol, rank, world, rates=False,

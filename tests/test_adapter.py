@@ -238,3 +238,48 @@ def test_replay_packed_fixture():
     np.testing.assert_allclose(out.cpu().numpy(), d['mean_stds'], rtol=1e-10,
                                atol=1e-12)
     h.close()
+
+
+@pytest.mark.gpu
+def test_horizontal_component_conversion_replay():
+    """ContextMaker.horiz_comp_to_geom_mean (contexts.py:726-776): the
+    reference's conversion coefficients for RotD50 (BSSA14) and GMRotI50
+    (BA08) fed to oqg_set_conversion; oqg_mean_stds then reproduces the
+    reference's converted mean and sigma"""
+    import torch
+    from oq_engine_b200 import _lib
+    from oq_engine_b200.contexts import _dev, _ptr
+    d = load('adapter_packed')
+    G, M = len(d['conv_names']), len(d['imts'])
+    h = _lib.Handle(0)
+    arr = (_lib.OqgGsim * G).from_buffer_copy(d['conv_gsim_bytes'].tobytes())
+    rows = np.ascontiguousarray(d['conv_rows'])
+    h.call('oqg_set_gsims', G, arr, M, rows.ctypes.data_as(_lib.c_double_p))
+    conv = np.ascontiguousarray(d['conv'])
+    h.call('oqg_set_conversion', conv.ctypes.data_as(_lib.c_double_p))
+    keep, ctx = [], _lib.OqgCtx()
+    for name in ('mag', 'rake', 'rjb', 'vs30'):
+        t = _dev(d['conv_' + name], 0)
+        keep.append(t)
+        setattr(ctx, name, t.data_ptr())
+    P = len(d['conv_mag'])
+    out = torch.empty((4, G, M, P), dtype=torch.float64, device='cuda:0')
+    h.call('oqg_mean_stds', ctypes.byref(ctx), P, _ptr(out))
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got, d['conv_mean_stds'], rtol=1e-10,
+                               atol=1e-12)
+    # and it is a real change for the converted models only
+    h.call('oqg_set_conversion', None)
+    h.call('oqg_mean_stds', ctypes.byref(ctx), P, _ptr(out))
+    raw = out.cpu().numpy()
+    assert np.abs(raw[0, 0] - got[0, 0]).max() > 1e-3      # RotD50
+    assert np.abs(raw[1, 1] - got[1, 1]).max() > 1e-3      # GMRotI50 sigma
+    np.testing.assert_array_equal(raw[:, 2], got[:, 2])    # geometric mean
+    # the fused pass refuses to run with a conversion set
+    h.call('oqg_set_conversion', conv.ctypes.data_as(_lib.c_double_p))
+    lev = np.zeros((M, 2))
+    h.call('oqg_set_levels', M, 2, lev.ctypes.data_as(_lib.c_double_p), 3.)
+    with pytest.raises(RuntimeError, match='horizontal-component'):
+        h.call('oqg_hazard_planar', None, None, None, None, 0, 1,
+               ctypes.byref(_lib.OqgSites()), None, 1, 0., 1., 0, None, None)
+    h.close()

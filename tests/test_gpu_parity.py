@@ -1006,3 +1006,99 @@ def test_update_more_than_65535_sites(oq):
     cm.hazard_planar(b, src, sc)
     np.testing.assert_allclose(a.array, b.array, rtol=2e-6, atol=1e-30)
     assert (a.array[-1] > 0).any()
+
+
+# ------------------------------------------- full-size spot rows (BASELINE 3)
+def _oracle_rows(pairs, r, sites, sel, imtls):
+    """float64 rate sums of the oracle for the sites `sel` and ALL the
+    ruptures of r: len(sel) x U context rows"""
+    sub = {k: v[sel] for k, v in sites.items()}
+    sub['sids'] = np.arange(len(sel), dtype=np.uint32)
+    opla = geo_np.build_planar(
+        r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+        r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+    octx = hazard_np.get_ctx(pairs, opla, r['mag'], sub)
+    return hazard_np.exact_rate_sum(pairs, octx, sub['sids'], imtls, 3., 50.)
+
+
+def test_cfg4_full_site_grid_spot_rows(oq):
+    """cfg4: the four NGA-West2 models on the FULL 100 000-site grid (1000
+    ruptures: 1e8 pairs, 5.6e10 evaluations), the map rows of 100 random
+    sites against the oracle: 1e5 (rupture, site) rows x 4 models; then the
+    same through the site sharding of SURVEY 8e (tiles by sids % 4, gathered)"""
+    import torch
+    rng = np.random.default_rng(44)
+    U, N = 1000, 100_000
+    r = synth_ruptures(U, rng)
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    pairs = CFG['cfg4']
+    cm = oq.ContextMaker('*', make_gsims(oq, pairs), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                          r['rate'], r['area'], r['hypo_lon'], r['hypo_lat'],
+                          r['hypo_dep'], 0., 25., 1.5)
+    src = oq.PlanarRuptures(pla, r['mag'])
+    rmap = oq.MapArray(sc.sids, cm.L, cm.G, rates=True,
+                       device='cuda:0').fill(0)
+    kept = cm.hazard_planar(rmap, src, sc, count=True)
+    assert kept == U * N
+    sel = np.sort(rng.choice(N, 100, replace=False))
+    acc = _oracle_rows(pairs, r, sites, sel, imtls)       # 1e5 rows
+    got = rmap.array[sel].cpu().numpy()
+    big = acc > 1e-10
+    assert big.sum() > 30_000
+    np.testing.assert_allclose(got[big], acc[big], rtol=1e-5)
+    # site sharding: 4 tiles by sids % 4, assembled by gather_tiles
+    world = 4
+    whole = None
+    for rank in range(world):
+        tmap, tile = oq.sharding.hazard_site_sharded(cm, src, sc, rank, world,
+                                                     rates=True)
+        part = oq.sharding.gather_tiles(tmap.array, tile.sids, N,
+                                        partial=True)
+        whole = part if whole is None else whole + part
+    # same kernel, same sites; another split of the ruptures into chunks
+    # (float32 partial sums are flushed at other points)
+    torch.testing.assert_close(whole, rmap.array, rtol=2e-6, atol=1e-30)
+
+
+def test_cfg5_groups_product_spot_rows(oq):
+    """cfg5: 8 source groups over the full 50 000-site grid, the pne maps of
+    the ranks multiplied as the NCCL PRODUCT all-reduce does (2 emulated
+    ranks of 4 groups), 50 random sites against the oracle: 8 x 250 x 50 =
+    1e5 (rupture, site) rows"""
+    import torch
+    rng = np.random.default_rng(55)
+    NG, U, N = 8, 250, 50_000
+    sites = synth_sites(N, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    pairs = CFG['cfg3']
+    cm = oq.ContextMaker('*', make_gsims(oq, pairs), dict(
+        imtls=imtls, truncation_level=3., investigation_time=50.))
+    sc = oq.SiteCollection.from_points(sites['lon'], sites['lat'],
+                                       sites['depth'], sites)
+    groups, srcs = [], []
+    for g in range(NG):
+        r = synth_ruptures(U, np.random.default_rng(20240 + g))
+        groups.append(r)
+        pla = oq.build_planar(r['mag'], r['strike'], r['dip'], r['rake'],
+                              r['rate'], r['area'], r['hypo_lon'],
+                              r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+        srcs.append(oq.PlanarRuptures(pla, r['mag']))
+    world = 2
+    prod = None
+    for rank in range(world):
+        pm = oq.MapArray(sc.sids, cm.L, cm.G, device='cuda:0').fill(1)
+        for g in oq.sharding.groups_of(rank, world, NG):
+            cm.hazard_planar(pm, srcs[g], sc)
+        prod = pm.array if prod is None else prod * pm.array   # PRODUCT
+    sel = np.sort(rng.choice(N, 50, replace=False))
+    acc = sum(_oracle_rows(pairs, r, sites, sel, imtls) for r in groups)
+    got = prod[torch.as_tensor(sel, device='cuda:0')].cpu().numpy()
+    np.testing.assert_allclose(got, np.exp(-acc), rtol=1e-5)
+    big = acc > 1e-3          # ... and where the hazard is: on the rates
+    np.testing.assert_allclose(-np.log(got[big].astype(np.float64)),
+                               acc[big], rtol=2e-4)

@@ -77,6 +77,19 @@ def worker(rank, world, port, q):
     m = oracle_map(grps[0], sub, False)
     full = oq.sharding.gather_tiles(torch.from_numpy(m), tile.sids, N)
     res['sites'] = full.numpy()
+    # ---- a filtered site collection: site IDs with gaps, ragged tiles (rank
+    # 0 owns 3 sites, rank 1 owns 8) -> rows in the order of the given sids
+    fsids = np.array([3, 40, 7, 9, 22, 5, 11, 13, 17, 19, 2], np.int64)
+    mine = fsids[:3] if rank == 0 else fsids[3:]
+    tile_arr = torch.from_numpy(
+        (mine[:, None, None] * np.ones((1, 2, 2))).astype(np.float32))
+    res['ragged'] = oq.sharding.gather_tiles(tile_arr, mine, fsids).numpy()
+    # a site nobody owns is an error on every rank, not an empty row
+    try:
+        oq.sharding.gather_tiles(tile_arr[:2], mine[:2], fsids)
+        res['unowned'] = 'no error'
+    except ValueError as exc:
+        res['unowned'] = str(exc)
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
@@ -109,5 +122,9 @@ def test_world_size_2():
         np.testing.assert_allclose(res['groups_rates'], exp_rat, rtol=1e-6,
                                    atol=1e-12)
         np.testing.assert_array_equal(res['sites'], single)
+        fsids = np.array([3, 40, 7, 9, 22, 5, 11, 13, 17, 19, 2])
+        np.testing.assert_array_equal(
+            res['ragged'], fsids[:, None, None] * np.ones((1, 2, 2)))
+        assert 'no owner' in res['unowned'], res['unowned']
     # pne product and rate sum describe the same hazard
     np.testing.assert_allclose(np.exp(-exp_rat), exp_pne, rtol=2e-5)

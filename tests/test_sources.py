@@ -454,3 +454,35 @@ def test_area_source_yields_the_demo_point_sources():
         list(oq.AreaSource('2', [0., 0.01, 0.01], [0., 0., 0.01], 50.,
                            oq.TruncatedGRMFD(*d['gr']), 'WC1994', 1., 0., 10.,
                            [(1., 0., 90., 0.)], [(1., 5.)]))
+
+
+@pytest.mark.gpu
+def test_psdist_through_rmap_maker(oq):
+    """pointsource_distance reaches the fused pass through RmapMaker (and so
+    through classical / calc_hazard_curves) too: same rows and map as
+    get_ctxs -> update of the reference with pointsource_distance = 30 km"""
+    tag = 'many'
+    N = len(PSD[tag + '_lon'])
+    sc = oq.SiteCollection.from_points(
+        PSD[tag + '_lon'], PSD[tag + '_lat'], np.zeros(N),
+        dict(vs30=PSD[tag + '_vs30']))
+    imtls = {str(imt): PSD['levels'] for imt in PSD['imts']}
+    cm = oq.ContextMaker(
+        'Active Shallow Crust',
+        [oq.get_gsim('BooreEtAl2014'), oq.get_gsim('BooreAtkinson2008')],
+        dict(imtls=imtls, truncation_level=3., investigation_time=50.,
+             maximum_distance=oq.IntegrationDistance.new('200'),
+             pointsource_distance=float(PSD['psdist'])))
+    res = oq.RmapMaker(cm, sc, psd_sources(oq)).make()
+    rates = res['rmap'].array
+    exp = -np.log(1. - PSD[tag + '_poes'].astype(np.float64))
+    big = exp > 1e-7
+    np.testing.assert_allclose(rates[big], exp[big], rtol=3e-5)
+
+
+def test_recarray_of_no_contexts_is_empty():
+    import oq_engine_b200 as oq
+    cm = oq.ContextMaker('*', [oq.get_gsim('BooreEtAl2014')],
+                         dict(imtls={'PGA': [0.1]}))
+    ctx = cm.recarray([])
+    assert len(ctx) == 0 and 'rjb' in ctx.dtype.names
