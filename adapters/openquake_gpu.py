@@ -129,6 +129,12 @@ def _spec_akkar(kind):
     return spec
 
 
+def _spec_plain(family):
+    def spec(g):
+        return family, 0, [0., 0., 0., 0.]
+    return spec
+
+
 # class name of the reference -> (spec function, {prefix: table attribute})
 SUPPORTED = {
     'BooreEtAl2014': (_spec_bssa14, {'': 'COEFFS'}),
@@ -144,6 +150,9 @@ SUPPORTED = {
     'AkkarEtAlRjb2014': (_spec_akkar(0), {'': 'COEFFS'}),
     'AkkarEtAlRepi2014': (_spec_akkar(1), {'': 'COEFFS'}),
     'AkkarEtAlRhyp2014': (_spec_akkar(2), {'': 'COEFFS'}),
+    'ChiouYoungs2008': (_spec_plain('CY08'), {'': 'COEFFS'}),
+    'ToroEtAl2002': (_spec_plain('TORO02'), {'': 'COEFFS'}),
+    'Campbell2003': (_spec_plain('C03'), {'': 'COEFFS'}),
 }
 
 

@@ -50,7 +50,10 @@ enum {
   OQG_BA08 = 4,    /* gsim/boore_atkinson_2008.py BooreAtkinson2008 */
   OQG_AB06 = 5,    /* gsim/atkinson_boore_2006.py AtkinsonBoore2006 */
   OQG_AKKAR14 = 6, /* gsim/akkar_2014.py AkkarEtAl{Rjb,Repi,Rhyp}2014 */
-  OQG_NFAMILIES = 7
+  OQG_CY08 = 7,    /* gsim/chiou_youngs_2008.py ChiouYoungs2008 */
+  OQG_TORO02 = 8,  /* gsim/toro_2002.py ToroEtAl2002 */
+  OQG_C03 = 9,     /* gsim/campbell_2003.py Campbell2003 */
+  OQG_NFAMILIES = 10
 };
 
 /* distance metrics: bit positions for masks and order of output planes */
@@ -85,6 +88,7 @@ enum {
  *  AB06   : flags bit0-1 mag_eq (0 NA, 1 Mblg87, 2 Mblg96); par[0] scale_fac
  *  AKKAR14: flags bit0-1 distance (0 rjb, 1 repi, 2 rhypo);
  *           par[0] log(adjustment_factor)
+ *  CY08, TORO02, C03: - (the models of the LogicTreeCase2ClassicalPSHA demo)
  */
 typedef struct {
   int32_t family;
@@ -220,6 +224,24 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar_dev,
                           double minimum_distance, double itime,
                           int rates_mode, float *map_dev,
                           unsigned long long *counters_dev);
+
+/* The same fused pass (GMPE -> PoEs -> map) for ruptures that are NOT planar
+ * (the ruptures of fault sources: ContextMaker.genctxs, contexts.py:959-1029,
+ * get_distances, calc/filters.py:75-116): their distances come from the mesh
+ * kernels (oqg_mesh_min_distance, oqg_mesh_rjb, oqg_mesh_rx_ry0) as planes
+ * [U][N] float64 in HBM.  rup_params_dev [U][8] = mag, rake, dip, ztor,
+ * width, hypo_depth, occurrence rate, integration distance of each rupture
+ * (get_rparams, contexts.py:905-957); planes (HOST array of 6 device
+ * pointers, order OQG_RRUP .. OQG_RHYPO; rrup is required, the others may be
+ * NULL when no configured model reads them).  A pair is kept when rrup <=
+ * the integration distance (contexts.py:974; planar ruptures: <).  The other
+ * arguments are those of oqg_hazard_planar. */
+int oqg_hazard_dist(oqg_handle *h, const double *rup_params_dev,
+                    const double *const *planes, const double *probs_occur_dev,
+                    int K, int U, const oqg_sites *sites_dev,
+                    const uint32_t *sidx_dev, int N, double minimum_distance,
+                    double itime, int rates_mode, float *map_dev,
+                    unsigned long long *counters_dev);
 
 /* same with HOST buffers: copies the ruptures and sites in, the map in and
  * out, and synchronises; map is host [N][L][G] float32 (sidx = identity) */

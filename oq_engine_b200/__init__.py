@@ -9,7 +9,8 @@ from .coeffs import CoeffsTable  # noqa
 from .gsim import (  # noqa
     GMPE, BooreEtAl2014, ChiouYoungs2014, AbrahamsonEtAl2014,
     CampbellBozorgnia2014, BooreAtkinson2008, AtkinsonBoore2006,
-    AkkarEtAlRjb2014, AkkarEtAlRepi2014, AkkarEtAlRhyp2014, get_gsim,
+    AkkarEtAlRjb2014, AkkarEtAlRepi2014, AkkarEtAlRhyp2014, ChiouYoungs2008,
+    ToroEtAl2002, Campbell2003, get_gsim,
     registry)
 from .tom import PoissonTOM, NegativeBinomialTOM  # noqa
 from .map_array import MapArray  # noqa
@@ -23,7 +24,8 @@ from .postproc import (  # noqa
     postclassical, compute_hazard_maps, compute_hmaps, calc_mean_rates)
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
-                   mesh_rx_ry0, mesh_dip_strike_width)
+                   mesh_rx_ry0, mesh_dip_strike_width, mesh_rjb)
+from .fault import MeshRuptures, SimpleFaultSource  # noqa
 from .disagg import (disaggregate, Disaggregator, FarAwayRupture,  # noqa
                      disaggregation, build_bin_edges, lon_lat_bins)
 from .cond_spectra import (  # noqa

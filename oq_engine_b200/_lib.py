@@ -10,7 +10,7 @@ LIBPATH = os.environ.get('OQG_LIB') or os.path.join(HERE, 'liboqg.so')
 KMAX = 56
 PLANAR_LEN = 42
 FAMILIES = {'BSSA14': 0, 'CY14': 1, 'ASK14': 2, 'CB14': 3, 'BA08': 4,
-            'AB06': 5, 'AKKAR14': 6}
+            'AB06': 5, 'AKKAR14': 6, 'CY08': 7, 'TORO02': 8, 'C03': 9}
 DIST = ['rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth', 'clon',
         'clat']
 
@@ -92,6 +92,10 @@ def lib():
             C.c_double, C.c_double, C.c_int, c_void, c_void]),
         'oqg_hazard_planar_aux': (C.c_int, [
             H, c_void, c_void, c_void, c_void, c_void, C.c_int, C.c_int,
+            C.POINTER(OqgSites), c_void, C.c_int, C.c_double, C.c_double,
+            C.c_int, c_void, c_void]),
+        'oqg_hazard_dist': (C.c_int, [
+            H, c_void, C.POINTER(c_void), c_void, C.c_int, C.c_int,
             C.POINTER(OqgSites), c_void, C.c_int, C.c_double, C.c_double,
             C.c_int, c_void, c_void]),
         'oqg_postclassical': (C.c_int, [

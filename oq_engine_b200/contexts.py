@@ -480,13 +480,22 @@ class ContextMaker(object):
         """
         import torch
         from .source import PointSource
+        from . import fault
+        if isinstance(src, fault.SimpleFaultSource):
+            src_id = src.id if src_id == 0 else src_id
+            src = src.ruptures()
+        if isinstance(src, fault.MeshRuptures):
+            # non-planar ruptures: genctxs (contexts.py:959-1029), one
+            # context per rupture
+            return fault.get_ctxs_mesh(self, src, sitecol, src_id, step)
         vis = None
         if isinstance(src, PointSource):
             src, vis = self._planar_of_point_source(src, sitecol, src_id)
         if not isinstance(src, PlanarRuptures):
             raise NotImplementedError(
-                'only planar ruptures (PlanarRuptures, PointSource) have a '
-                'device path')
+                'only planar ruptures (PlanarRuptures, PointSource) and mesh '
+                'ruptures (fault.MeshRuptures, fault.SimpleFaultSource) have '
+                'a device path')
         h = self.handle()
         U, N = len(src), len(sitecol)
         if U == 0 or N == 0:
@@ -821,6 +830,19 @@ class ContextMaker(object):
             numpy.ascontiguousarray(aux, float), dev)
         return self._hazard_planar_dev(pmap, t_pla, t_mag, t_md, t_probs, K,
                                        U, sitecol, count, t_aux)
+
+    def hazard_mesh(self, pmap, src, sitecol, count=False):
+        """
+        Fold the ruptures of a fault source (fault.MeshRuptures or
+        fault.SimpleFaultSource) into `pmap`: distances of the rupture meshes
+        on the device, then the fused GMPE -> PoE -> map pass
+        (oqg_hazard_dist); the equivalent of genctxs + update of the
+        reference (contexts.py:959-1029, 1232-1247)
+        """
+        from . import fault
+        if isinstance(src, fault.SimpleFaultSource):
+            src = src.ruptures()
+        return fault.hazard_mesh(self, pmap, src, sitecol, count)
 
     def _fated(self, U, dev):
         # cluster groups (contexts.py:1243-1246): every rupture happens once

@@ -204,6 +204,24 @@ __global__ void k_prep_ruptures(const double *__restrict__ planar,
   prep_rupture(pl, mag[u], magdist ? magdist[u] : INFINITY, out + u, Us);
 }
 
+// ruptures with external distances (oqg_hazard_dist): par [U][8] = mag, rake,
+// dip, ztor, width, hypo_depth, occurrence rate, integration distance ->
+// the fields of the rupture SoA the stages after the distances read
+__global__ void k_prep_xruptures(const double *__restrict__ par, int64_t U,
+                                 int64_t Us, double *__restrict__ out) {
+  int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const double *p = par + u * 8;
+  out[RF_MAG * Us + u] = p[0];
+  out[RF_RAKE * Us + u] = p[1];
+  out[RF_DIP * Us + u] = p[2];
+  out[RF_ZTOR * Us + u] = p[3];
+  out[RF_WIDTH * Us + u] = p[4];
+  out[RF_HYPO_DEPTH * Us + u] = p[5];
+  out[RF_RATE * Us + u] = p[6];
+  out[RF_MAGDIST * Us + u] = p[7];
+}
+
 // one thread per rupture of a batch of point sources (oqg_source.cuh).
 // Without the pointsource_distance approximation a source has M * N * D
 // ruptures ordered (magnitude, nodal plane, depth).  With it, a source with
@@ -526,6 +544,8 @@ struct FusedArgs {
   const double *rup;      // [NF_RUP][U]
   const double *probs;    // [U][K] or null
   const double *aux;      // [U][OQG_AUX_LEN] or null (pointsource_distance)
+  const double *xd[6];    // external distance planes [U][N] (rrup, rjb, rx,
+                          // ry0, repi, rhypo) of non-planar ruptures, or null
   const double *site;     // [NF_SITE][N]
   const double *vs30, *z1pt0, *z2pt5;
   const uint8_t *vs30measured;
@@ -599,12 +619,13 @@ enum { PF_MAG, PF_RAKE, PF_DIP, PF_ZTOR, PF_WIDTH, PF_HYPO_DEPTH, PF_RATE,
 
 template <int F> struct DistMask {
   static constexpr int value =
-      F == OQG_BSSA14 || F == OQG_BA08 ? (1 << OQG_RRUP) | (1 << OQG_RJB)
-      : F == OQG_CY14 || F == OQG_CB14
+      F == OQG_BSSA14 || F == OQG_BA08 || F == OQG_TORO02
+          ? (1 << OQG_RRUP) | (1 << OQG_RJB)
+      : F == OQG_CY14 || F == OQG_CB14 || F == OQG_CY08
           ? (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_RX)
       : F == OQG_ASK14
           ? (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_RX) | (1 << OQG_RY0)
-      : F == OQG_AB06 ? (1 << OQG_RRUP)
+      : F == OQG_AB06 || F == OQG_C03 ? (1 << OQG_RRUP)
       : (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_REPI) | (1 << OQG_RHYPO);
 };
 __host__ __device__ constexpr int popc_below(int mask, int k) {   // planes before distance k
@@ -817,11 +838,22 @@ k_fused(const FusedArgs A) {
         sx[k] = s_site[(SF_XYZ + k) * 32 + lane];
         sq[k] = s_site[(SF_Q + k) * 32 + lane];
       }
-      Dist d;
-      pair_distances(s_rup + i, RT, sx, sq, s_site[SF_DEPTH * 32 + lane],
-                     A.dmask, d);
-      double vals[OQG_NDIST] = {d.rrup, d.rjb, d.rx, d.ry0, d.repi, d.rhypo,
-                                0.};
+      double vals[OQG_NDIST];
+      if (A.xd[0]) {
+        // non-planar ruptures (oqg_hazard_dist): the distances were computed
+        // by the mesh kernels into [U][N] planes; lane = site, coalesced
+        const int64_t at = (r0 + i) * (int64_t)A.N + (site_ok ? n : 0);
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          vals[k] = ((DM >> k) & 1) && A.xd[k] ? A.xd[k][at] : 0.;
+        vals[6] = 0.;
+      } else {
+        Dist d;
+        pair_distances(s_rup + i, RT, sx, sq, s_site[SF_DEPTH * 32 + lane],
+                       A.dmask, d);
+        vals[0] = d.rrup; vals[1] = d.rjb; vals[2] = d.rx; vals[3] = d.ry0;
+        vals[4] = d.repi; vals[5] = d.rhypo; vals[6] = 0.;
+      }
       // minimum_distance clamp of the required distances, contexts.py:391
       if (A.mindist != 0.) {
 #pragma unroll
@@ -829,7 +861,10 @@ k_fused(const FusedArgs A) {
           if ((A.clampmask >> k) & 1)
             if (vals[k] < A.mindist) vals[k] = A.mindist;
       }
-      bool ok = site_ok && vals[0] < s_rup[RF_MAGDIST * RT + i];
+      // planar ruptures: rrup < magdist (contexts.py:472); the others:
+      // rrup <= magdist (genctxs, contexts.py:974)
+      bool ok = site_ok && (A.xd[0] ? vals[0] <= s_rup[RF_MAGDIST * RT + i]
+                                    : vals[0] < s_rup[RF_MAGDIST * RT + i]);
       if (A.aux) {
         // pointsource_distance (contexts.py:347-370): [x, y, z of the source
         // location, psdist, mode] per rupture, uniform over the warp; near
@@ -1207,6 +1242,9 @@ const char *oqg_family_fields(int family) {
     case OQG_BA08: return Fam<OQG_BA08>::fields();
     case OQG_AB06: return Fam<OQG_AB06>::fields();
     case OQG_AKKAR14: return Fam<OQG_AKKAR14>::fields();
+    case OQG_CY08: return Fam<OQG_CY08>::fields();
+    case OQG_TORO02: return Fam<OQG_TORO02>::fields();
+    case OQG_C03: return Fam<OQG_C03>::fields();
   }
   return nullptr;
 }
@@ -1929,6 +1967,9 @@ int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx, int64_t P, double *out) {
       case OQG_BA08: launch_mean_stds<OQG_BA08>(h, g, ctx, P, out); break;
       case OQG_AB06: launch_mean_stds<OQG_AB06>(h, g, ctx, P, out); break;
       case OQG_AKKAR14: launch_mean_stds<OQG_AKKAR14>(h, g, ctx, P, out); break;
+      case OQG_CY08: launch_mean_stds<OQG_CY08>(h, g, ctx, P, out); break;
+      case OQG_TORO02: launch_mean_stds<OQG_TORO02>(h, g, ctx, P, out); break;
+      case OQG_C03: launch_mean_stds<OQG_C03>(h, g, ctx, P, out); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -1965,6 +2006,9 @@ int oqg_mean_stds_staged(oqg_handle *h, const oqg_ctx *ctx, int64_t P,
       case OQG_BA08: launch_mean_stds_staged<OQG_BA08>(h, g, ctx, P, out); break;
       case OQG_AB06: launch_mean_stds_staged<OQG_AB06>(h, g, ctx, P, out); break;
       case OQG_AKKAR14: launch_mean_stds_staged<OQG_AKKAR14>(h, g, ctx, P, out); break;
+      case OQG_CY08: launch_mean_stds_staged<OQG_CY08>(h, g, ctx, P, out); break;
+      case OQG_TORO02: launch_mean_stds_staged<OQG_TORO02>(h, g, ctx, P, out); break;
+      case OQG_C03: launch_mean_stds_staged<OQG_C03>(h, g, ctx, P, out); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -2085,6 +2129,14 @@ static cudaError_t launch_fused(FusedArgs &A, int tiles, int rc, int ugroups,
       A, grid, threads, FusedLayout<F, false, false>::SIZE * 8, st);
 }
 
+static int hazard_fused(oqg_handle *h, const double *planar,
+                        const double *mag, const double *magdist,
+                        const double *xpar, const double *const *xplanes,
+                        const double *aux, const double *probs, int K, int U,
+                        const oqg_sites *sites, const uint32_t *sidx, int N,
+                        double mindist, double itime, int rates_mode,
+                        float *map, unsigned long long *counters);
+
 extern "C" {
 
 int oqg_hazard_planar(oqg_handle *h, const double *planar, const double *mag,
@@ -2113,6 +2165,35 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
                           const oqg_sites *sites, const uint32_t *sidx, int N,
                           double mindist, double itime, int rates_mode,
                           float *map, unsigned long long *counters) {
+  return hazard_fused(h, planar, mag, magdist, nullptr, nullptr, aux, probs, K,
+                      U, sites, sidx, N, mindist, itime, rates_mode, map,
+                      counters);
+}
+
+int oqg_hazard_dist(oqg_handle *h, const double *rup_params,
+                    const double *const *planes, const double *probs, int K,
+                    int U, const oqg_sites *sites, const uint32_t *sidx, int N,
+                    double mindist, double itime, int rates_mode, float *map,
+                    unsigned long long *counters) {
+  if (!rup_params || !planes || !planes[OQG_RRUP])
+    return fail(h, "hazard_dist: rupture parameters and the rrup plane are "
+                   "required");
+  return hazard_fused(h, nullptr, nullptr, nullptr, rup_params, planes,
+                      nullptr, probs, K, U, sites, sidx, N, mindist, itime,
+                      rates_mode, map, counters);
+}
+
+}  // extern "C"
+
+// The fused pass over planar ruptures (planar, mag, magdist) or over ruptures
+// with external distance planes (xpar, xplanes)
+static int hazard_fused(oqg_handle *h, const double *planar,
+                        const double *mag, const double *magdist,
+                        const double *xpar, const double *const *xplanes,
+                        const double *aux, const double *probs, int K, int U,
+                        const oqg_sites *sites, const uint32_t *sidx, int N,
+                        double mindist, double itime, int rates_mode,
+                        float *map, unsigned long long *counters) {
   CK(cudaSetDevice(h->device));
   if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
   if (U <= 0 || N <= 0) return 0;
@@ -2125,11 +2206,23 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   const int G = h->G, M = h->M, L1 = h->L1, L = M * L1;
   ConstGuard guard(h);
   if (guard.acquire()) return 1;
-  if (prep_ruptures(h, planar, mag, magdist, U)) return 1;
+  if (xpar) {
+    const int64_t Us = rup_stride(U);
+    if (reserve(h, h->rup, (size_t)NF_RUP * Us * 8)) return 1;
+    CK(cudaMemsetAsync(h->rup.p, 0, (size_t)NF_RUP * Us * 8, h->stream));
+    k_prep_xruptures<<<(unsigned)((U + 127) / 128), 128, 0, h->stream>>>(
+        xpar, U, Us, (double *)h->rup.p);
+    h->launches++;
+    CK(cudaGetLastError());
+  } else if (prep_ruptures(h, planar, mag, magdist, U)) {
+    return 1;
+  }
   if (prep_sites(h, sites, N)) return 1;
 
   FusedArgs A;
   memset(&A, 0, sizeof(A));
+  if (xpar)
+    for (int k = 0; k < 6; k++) A.xd[k] = xplanes[k];
   A.rup = (const double *)h->rup.p;
   A.probs = K ? probs : nullptr;
   A.aux = aux;
@@ -2169,12 +2262,19 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   for (int g = 0; g < G; g++) {
     const oqg_gsim &gs = h->gsims[g];
     if (gs.family == OQG_CB14 && !sites->z2pt5) return fail(h, "sites need z2pt5");
-    if (!sites->vs30) return fail(h, "sites need vs30");
-    if ((gs.family == OQG_CY14 || gs.family == OQG_ASK14) &&
+    if (!sites->vs30 && gs.family != OQG_TORO02 && gs.family != OQG_C03)
+      return fail(h, "sites need vs30");
+    if ((gs.family == OQG_CY14 || gs.family == OQG_ASK14 ||
+         gs.family == OQG_CY08) &&
         (!sites->z1pt0 || !sites->vs30measured))
       return fail(h, "sites need z1pt0 and vs30measured");
     A.g = g;
     A.clampmask = required_distances(gs);
+    if (xpar)
+      for (int k = 0; k < 6; k++)
+        if (((A.clampmask >> k) & 1) && !xplanes[k])
+          return fail(h, std::string("hazard_dist: the model needs the "
+                                     "distance plane ") + std::to_string(k));
     A.dmask = A.clampmask | (1 << OQG_RRUP);
     if (A.dmask & (1 << OQG_RHYPO)) A.dmask |= 1 << OQG_REPI;
     // pairs: model 0, blockIdx.z == 0 only; executed evaluations (statistics
@@ -2193,6 +2293,9 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
       case OQG_BA08: LF(OQG_BA08); break;
       case OQG_AB06: LF(OQG_AB06); break;
       case OQG_AKKAR14: LF(OQG_AKKAR14); break;
+      case OQG_CY08: LF(OQG_CY08); break;
+      case OQG_TORO02: LF(OQG_TORO02); break;
+      case OQG_C03: LF(OQG_C03); break;
     }
 #undef LF
     h->last_subs = A.subs;
@@ -2209,6 +2312,8 @@ int oqg_hazard_planar_aux(oqg_handle *h, const double *planar,
   CK(cudaGetLastError());
   return 0;
 }
+
+extern "C" {
 
 static int h2d(oqg_handle *h, Buf &b, const void *src, size_t bytes,
                const void **dev) {

@@ -14,6 +14,9 @@
 //   BA08     gsim/boore_atkinson_2008.py:100-151 + atkinson_boore_2006.py:63-195
 //   AB06     gsim/atkinson_boore_2006.py:109-124, 213-221, 421-448
 //   AKKAR14  gsim/akkar_2014.py:33-126, 177-198
+//   CY08     gsim/chiou_youngs_2008.py:29-167, 204-228
+//   TORO02   gsim/toro_2002.py:31-57, 103-128
+//   C03      gsim/campbell_2003.py:39-47, 71-106, 178-189
 //   epistemic sigma: gsim/abrahamson_2014.py:440-464
 //
 // Coefficient rows are arrays of OQG_KMAX doubles laid out by the *_FIELDS
@@ -72,6 +75,18 @@ struct Out {
   X(a1) X(a2) X(a3) X(a4) X(a5) X(a6) X(a7) X(a8) X(a9) X(c) X(n) X(b1)      \
   X(b2) X(sigma) X(tau) X(period)
 
+#define CY08_FIELDS(X)                                                       \
+  X(c2) X(c3) X(c4) X(c4a) X(crb) X(chm) X(cg3) X(c1) X(c1a) X(c1b) X(cn)    \
+  X(cm) X(c5) X(c6) X(c7) X(c7a) X(c9) X(c9a) X(c10) X(cg1) X(cg2) X(phi1)   \
+  X(phi2) X(phi3) X(phi4) X(phi5) X(phi6) X(phi7) X(phi8) X(tau1) X(tau2)    \
+  X(sig1) X(sig2) X(sig3) X(sig4) X(period)
+#define TORO02_FIELDS(X)                                                     \
+  X(c1) X(c2) X(c3) X(c4) X(c5) X(c6) X(c7) X(m50) X(m55) X(m80) X(r5)       \
+  X(r20) X(period)
+#define C03_FIELDS(X)                                                        \
+  X(c1) X(c2) X(c3) X(c4) X(c5) X(c6) X(c7) X(c8) X(c9) X(c10) X(c11)        \
+  X(c12) X(c13) X(period)
+
 struct Bssa14C { BSSA14_FIELDS(OQG_DECL) };
 struct Cy14C { CY14_FIELDS(OQG_DECL) };
 struct Ask14C { ASK14_FIELDS(OQG_DECL) };
@@ -79,6 +94,9 @@ struct Cb14C { CB14_FIELDS(OQG_DECL) };
 struct Ba08C { BA08_FIELDS(OQG_DECL) };
 struct Ab06C { AB06_FIELDS(OQG_DECL) };
 struct Akkar14C { AKKAR14_FIELDS(OQG_DECL) };
+struct Cy08C { CY08_FIELDS(OQG_DECL) };
+struct Toro02C { TORO02_FIELDS(OQG_DECL) };
+struct C03C { C03_FIELDS(OQG_DECL) };
 
 // the last OQG_KMAX - OQG_DER doubles of a row hold constants derived on the
 // host from the packed coefficients (oqg_set_gsims; read by oqg_fast.cuh)
@@ -92,6 +110,7 @@ static_assert(sizeof(Cb14C) <= OQG_KMAX * 8, "row too long");
 static_assert(sizeof(Ba08C) <= OQG_KMAX * 8, "row too long");
 static_assert(sizeof(Ab06C) <= OQG_KMAX * 8, "row too long");
 static_assert(sizeof(Akkar14C) <= OQG_KMAX * 8, "row too long");
+static_assert(sizeof(Cy08C) <= OQG_KMAX * 8, "row too long");
 
 #define OQG_D2R 0.017453292519943295  // pi / 180, numpy.radians
 
@@ -776,6 +795,118 @@ __device__ __forceinline__ Out akkar14_imt(const oqg_gsim &g,
   return o;
 }
 
+// ===================================================================== CY08
+// chiou_youngs_2008.py: no rock-PGA pass, every IMT has its own reference
+// motion ln_y_ref (eq. 13a), site response (eq. 13b) and sigma (eq. 19-21)
+struct NoRow {};
+
+__device__ __forceinline__ Out cy08_imt(const oqg_gsim &, const Cy08C &C,
+                                        const Row &r) {
+  // :56-99
+  const double frv = (30. <= r.rake && r.rake <= 150.) ? 1. : 0.;
+  const double fnm = (-120. <= r.rake && r.rake <= -60.) ? 1. : 0.;
+  const double fhw = r.rx >= 0. ? 1. : 0.;
+  const double cd = cos(r.dip * OQG_D2R);
+  double ln_y_ref =
+      C.c1 + (C.c1a * frv + C.c1b * fnm + C.c7 * (r.ztor - 4.)) +
+      C.c2 * (r.mag - 6.) +
+      ((C.c2 - C.c3) / C.cn) * log(1. + exp(C.cn * (C.cm - r.mag))) +
+      C.c4 * log(r.rrup + C.c5 * cosh(C.c6 * fmax(r.mag - C.chm, 0.))) +
+      (C.c4a - C.c4) * log(sqrt(r.rrup * r.rrup + C.crb * C.crb)) +
+      (C.cg1 + C.cg2 / cosh(fmax(r.mag - C.cg3, 0.))) * r.rrup +
+      C.c9 * fhw * tanh(r.rx * (cd * cd) / C.c9a) *
+          (1. - sqrt(r.rjb * r.rjb + r.ztor * r.ztor) / (r.rrup + 0.001));
+  // :218-219
+  const double exp1 = exp(C.phi3 * (fmin(r.vs30, 1130.) - 360.));
+  const double exp2 = exp(C.phi3 * (1130. - 360.));
+  // basin term :37-53 (z1pt0 = -999: the model's own vs30 -> z1pt0, :29-34)
+  double z1 = r.z1pt0;
+  if (z1 == -999.)
+    z1 = exp(28.5 - (3.82 / 8.) * log(pow(r.vs30, 8.) + pow(378.7, 8.)));
+  const double deep =
+      C.phi5 * (1.0 - 1.0 / cosh(C.phi6 * fmax(z1 - C.phi7, 0.)));
+  const double shallow = C.phi8 / cosh(0.15 * fmax(z1 - 15., 0.));
+  const double y_ref = exp(ln_y_ref);
+  Out o;
+  // :102-124
+  o.mean = ln_y_ref + C.phi1 * fmin(log(r.vs30 / 1130.), 0.) +
+           C.phi2 * (exp1 - exp2) * log((y_ref + C.phi4) / C.phi4) +
+           (deep + shallow);
+  // :127-164
+  const double mag_test = fmin(fmax(r.mag, 5.0), 7.0) - 5.0;
+  const double t = C.tau1 + (C.tau2 - C.tau1) / 2. * mag_test;
+  const double b = C.phi2 * (exp1 - exp2);
+  const double nl = b * y_ref / (y_ref + C.phi4);
+  const double fmeas = r.vs30measured ? 1. : 0.;
+  const double sigma = (C.sig1 + 0.5 * (C.sig2 - C.sig1) * mag_test) *
+                       sqrt((C.sig3 * (1. - fmeas) + 0.7 * fmeas) +
+                            (1. + nl) * (1. + nl));
+  o.sig = sqrt(((1. + nl) * (1. + nl)) * (t * t) + sigma * sigma);
+  o.tau = fabs((1. + nl) * t);
+  o.phi = sigma;
+  return o;
+}
+
+// =================================================================== TORO02
+// numpy.interp on increasing nodes: constant outside, slope * (x - x0) + y0
+// inside (numpy/_core/src/multiarray/compiled_base.c arr_interp)
+__device__ __forceinline__ double np_interp3(double x, double x0, double x1,
+                                             double x2, double y0, double y1,
+                                             double y2) {
+  if (x <= x0) return y0;
+  if (x >= x2) return y2;
+  if (x < x1) return (y1 - y0) / (x1 - x0) * (x - x0) + y0;
+  return (y2 - y1) / (x2 - x1) * (x - x1) + y1;
+}
+
+__device__ __forceinline__ Out toro02_imt(const oqg_gsim &, const Toro02C &C,
+                                          const Row &r) {
+  // toro_2002.py:31-57
+  const double md = r.mag - 6.;
+  const double e = exp(-1.25 + 0.227 * r.mag);
+  const double RM = sqrt(r.rjb * r.rjb + (C.c7 * C.c7) * (e * e));
+  const double term1 = C.c2 * md + C.c3 * (md * md);
+  const double term2 = -C.c4 * log(RM) -
+                       (C.c5 - C.c4) * fmax(log(RM / 100.), 0.) - C.c6 * RM;
+  Out o;
+  o.mean = C.c1 + term1 + term2;
+  // :110-128
+  const double am = np_interp3(r.mag, 5.0, 5.5, 8.0, C.m50, C.m55, C.m80);
+  double ar;
+  if (r.rjb <= 5.0) ar = C.r5;
+  else if (r.rjb >= 20.0) ar = C.r20;
+  else ar = (C.r20 - C.r5) / (20.0 - 5.0) * (r.rjb - 5.0) + C.r5;
+  const double ale = sqrt(am * am + ar * ar);
+  const double epi = C.period < 1. ? 0.36 + 0.07 * md : 0.34 + 0.06 * md;
+  o.sig = sqrt(ale * ale + epi * epi);
+  if (C.period == 3.0) o.mean /= 0.612;
+  if (C.period == 4.0) o.mean /= 0.559;
+  o.tau = 0.;
+  o.phi = 0.;
+  return o;
+}
+
+// ====================================================================== C03
+__device__ __forceinline__ Out c03_imt(const oqg_gsim &, const C03C &C,
+                                       const Row &r) {
+  // campbell_2003.py:39-47, 71-106 (kind "base")
+  const double term1 = (C.c2 * r.mag) + C.c3 * ((8.5 - r.mag) * (8.5 - r.mag));
+  const double c78 = C.c7 * exp(C.c8 * r.mag);
+  const double R = sqrt(r.rrup * r.rrup + c78 * c78);
+  const double term2 = C.c4 * log(R) + (C.c5 + C.c6 * r.mag) * r.rrup;
+  double f3 = 0.;
+  if (r.rrup > 70. && r.rrup <= 130.)
+    f3 = C.c9 * (log(r.rrup) - log(70.));
+  else if (r.rrup > 130.)
+    f3 = C.c9 * (log(r.rrup) - log(70.)) + C.c10 * (log(r.rrup) - log(130.));
+  Out o;
+  o.mean = C.c1 + term1 + term2 + f3;
+  o.sig = r.mag < 7.16 ? C.c11 + C.c12 * r.mag : C.c13;
+  o.tau = 0.;
+  o.phi = 0.;
+  return o;
+}
+
 // ================================================================ dispatch
 // Fam<F>: the coefficient row type, the per-row state and the two stages
 template <int F> struct Fam;
@@ -808,6 +939,15 @@ OQG_FAM(OQG_AB06, Ab06C, Ab06Row, ab06_row, ab06_imt(g, c, Cp, r, s),
         AB06_FIELDS)
 OQG_FAM(OQG_AKKAR14, Akkar14C, Akkar14Row, akkar14_row,
         akkar14_imt(g, c, r, s), AKKAR14_FIELDS)
+template <typename CT>
+__device__ __forceinline__ NoRow no_row_t(const oqg_gsim &, const CT &,
+                                          const Row &) { return NoRow(); }
+OQG_FAM(OQG_CY08, Cy08C, NoRow, no_row_t<Cy08C>, ((void)s, cy08_imt(g, c, r)),
+        CY08_FIELDS)
+OQG_FAM(OQG_TORO02, Toro02C, NoRow, no_row_t<Toro02C>,
+        ((void)s, toro02_imt(g, c, r)), TORO02_FIELDS)
+OQG_FAM(OQG_C03, C03C, NoRow, no_row_t<C03C>, ((void)s, c03_imt(g, c, r)),
+        C03_FIELDS)
 
 // distances a model reads (REQUIRES_DISTANCES of the reference classes,
 // SURVEY.md appendix B) as a mask of 1 << OQG_R*
@@ -825,6 +965,9 @@ __host__ __device__ inline int required_distances(const oqg_gsim &g) {
       int k = g.flags & 3;
       return k == 0 ? RJB : (k == 1 ? (1 << OQG_REPI) : (1 << OQG_RHYPO));
     }
+    case OQG_CY08: return RRUP | RJB | RX;
+    case OQG_TORO02: return RJB;
+    case OQG_C03: return RRUP;
   }
   return 0;
 }

@@ -298,6 +298,47 @@ class AkkarEtAlRhyp2014(AkkarEtAlRjb2014):
     _kind = 2
 
 
+class _PlainGMPE(GMPE, register=False):
+    """A model without options and without a rock-PGA pass"""
+    def __init__(self, **kwargs):
+        if kwargs:
+            raise NotImplementedError(
+                '%s options %s have no device implementation'
+                % (self.__class__.__name__, sorted(kwargs)))
+        super().__init__()
+
+    def device_spec(self):
+        return (_lib.FAMILIES[self.family], 0, [0., 0., 0., 0.])
+
+
+class ChiouYoungs2008(_PlainGMPE):
+    """chiou_youngs_2008.py:168-228"""
+    REQUIRES_DISTANCES = frozenset({'rrup', 'rjb', 'rx'})
+    REQUIRES_RUPTURE_PARAMETERS = frozenset({'dip', 'rake', 'mag', 'ztor'})
+    REQUIRES_SITES_PARAMETERS = frozenset({'vs30', 'vs30measured', 'z1pt0'})
+    family = 'CY08'
+    tables = {'': 'CY08'}
+
+
+class ToroEtAl2002(_PlainGMPE):
+    """toro_2002.py:59-146 (total standard deviation only)"""
+    REQUIRES_DISTANCES = frozenset({'rjb'})
+    REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag'})
+    REQUIRES_SITES_PARAMETERS = frozenset()
+    family = 'TORO02'
+    tables = {'': 'TORO02'}
+
+
+class Campbell2003(_PlainGMPE):
+    """campbell_2003.py:138-212 (kind "base"; total standard deviation
+    only)"""
+    REQUIRES_DISTANCES = frozenset({'rrup'})
+    REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag'})
+    REQUIRES_SITES_PARAMETERS = frozenset()
+    family = 'C03'
+    tables = {'': 'C03'}
+
+
 def get_gsim(name, **kwargs):
     """Instantiate a supported model by class name (like valid.gsim); an
     unsupported model is a hard error: there is no CPU fallback"""

@@ -19,6 +19,7 @@ import numpy
 from .map_array import MapArray, F32
 from .tom import PoissonTOM
 from .contexts import PlanarRuptures
+from .fault import MeshRuptures, SimpleFaultSource
 from .source import PointSource, PointSourceBatch
 
 
@@ -88,6 +89,8 @@ class RmapMaker(object):
         for s in srcs:
             if isinstance(s, PlanarRuptures):
                 kept += cm.hazard_planar(pmap, s, self.sitecol, count=True)
+            elif isinstance(s, (MeshRuptures, SimpleFaultSource)):
+                kept += cm.hazard_mesh(pmap, s, self.sitecol, count=True)
             elif not isinstance(s, PointSource):
                 raise NotImplementedError(
                     '%s sources have no device implementation'
@@ -96,7 +99,7 @@ class RmapMaker(object):
 
     @staticmethod
     def _nrupts(src):
-        return src.count_ruptures() if isinstance(src, PointSource) \
+        return src.count_ruptures() if hasattr(src, 'count_ruptures') \
             else len(src)
 
     def _make_src_indep(self):

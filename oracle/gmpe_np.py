@@ -853,6 +853,114 @@ def akkar14(ctx, imts, kind='rjb', adjustment_factor=1.0):
 
 
 # --------------------------------------------------------------------- #
+#        the models of the LogicTreeCase2ClassicalPSHA demo (cfg2)       #
+# --------------------------------------------------------------------- #
+
+def cy08(ctx, imts):
+    """ChiouYoungs2008.compute, chiou_youngs_2008.py:204-228 with
+    _get_ln_y_ref :56-99, _get_mean :102-124, _get_basin_term :37-53,
+    _set_stddevs :127-164"""
+    out = _out(len(imts), len(ctx.mag))
+    mag, rake, rrup = ctx.mag, ctx.rake, ctx.rrup
+    frv = ((30 <= rake) & (rake <= 150)).astype(float)
+    fnm = ((-120 <= rake) & (rake <= -60)).astype(float)
+    fhw = np.where(ctx.rx >= 0, 1, 0)
+    for m, imt in enumerate(imts):
+        C = coeffs('CY08', imt)
+        ln_y_ref = (
+            C['c1'] + (C['c1a'] * frv + C['c1b'] * fnm
+                       + C['c7'] * (ctx.ztor - 4))
+            + C['c2'] * (mag - 6)
+            + ((C['c2'] - C['c3']) / C['cn'])
+            * np.log(1 + np.exp(C['cn'] * (C['cm'] - mag)))
+            + C['c4'] * np.log(rrup + C['c5'] * np.cosh(
+                C['c6'] * np.fmax(mag - C['chm'], 0)))
+            + (C['c4a'] - C['c4']) * np.log(np.sqrt(rrup ** 2 + C['crb'] ** 2))
+            + (C['cg1'] + C['cg2'] / (np.cosh(np.fmax(mag - C['cg3'], 0))))
+            * rrup
+            + C['c9'] * fhw * np.tanh(
+                ctx.rx * (np.cos(np.radians(ctx.dip)) ** 2) / C['c9a'])
+            * (1 - np.sqrt(ctx.rjb ** 2 + ctx.ztor ** 2) / (rrup + 0.001)))
+        exp1 = np.exp(C['phi3'] * (ctx.vs30.clip(-np.inf, 1130) - 360))
+        exp2 = np.exp(C['phi3'] * (1130 - 360))
+        z1pt0 = np.array(ctx.z1pt0, float)
+        mask = z1pt0 == -999
+        z1pt0[mask] = np.exp(28.5 - (3.82 / 8) * np.log(
+            ctx.vs30[mask] ** 8 + 378.7 ** 8))
+        deep = C['phi5'] * (1.0 - 1.0 / np.cosh(
+            C['phi6'] * (z1pt0 - C['phi7']).clip(0, np.inf)))
+        shallow = C['phi8'] / np.cosh(0.15 * (z1pt0 - 15).clip(0, np.inf))
+        out[0, m] = (
+            ln_y_ref + C['phi1'] * np.log(ctx.vs30 / 1130).clip(-np.inf, 0)
+            + C['phi2'] * (exp1 - exp2)
+            * np.log((np.exp(ln_y_ref) + C['phi4']) / C['phi4'])
+            + (deep + shallow))
+        fmeas = np.where(ctx.vs30measured, True, False)
+        mag_test = np.clip(mag, 5.0, 7.0) - 5.0
+        t = C['tau1'] + (C['tau2'] - C['tau1']) / 2 * mag_test
+        b = C['phi2'] * (exp1 - exp2)
+        y_ref = np.exp(ln_y_ref)
+        NL = b * y_ref / (y_ref + C['phi4'])
+        sigma = ((C['sig1'] + 0.5 * (C['sig2'] - C['sig1']) * mag_test)
+                 * np.sqrt((C['sig3'] * ~fmeas + 0.7 * fmeas) + (1 + NL) ** 2))
+        out[1, m] = np.sqrt(((1 + NL) ** 2) * (t ** 2) + sigma ** 2)
+        out[2, m] = np.abs((1 + NL) * t)
+        out[3, m] = sigma
+    return out
+
+
+def toro02(ctx, imts):
+    """ToroEtAl2002.compute, toro_2002.py:103-128 with _compute_mean :31-57
+    (total standard deviation only: tau and phi stay zero)"""
+    out = _out(len(imts), len(ctx.mag))
+    mag, rjb = ctx.mag, ctx.rjb
+    for m, imt in enumerate(imts):
+        C = coeffs('TORO02', imt)
+        period = parse_imt(imt)[1]
+        md = mag - 6
+        RM = np.sqrt(rjb ** 2 + (C['c7'] ** 2) *
+                     np.exp(-1.25 + 0.227 * mag) ** 2)
+        term2 = (-C['c4'] * np.log(RM) - (C['c5'] - C['c4']) *
+                 np.maximum(np.log(RM / 100), 0) - C['c6'] * RM)
+        out[0, m] = C['c1'] + (C['c2'] * md + C['c3'] * md ** 2) + term2
+        ale_m = np.interp(mag, [5.0, 5.5, 8.0],
+                          [C['m50'], C['m55'], C['m80']])
+        ale_r = np.interp(rjb, [5.0, 20.0], [C['r5'], C['r20']])
+        ale = np.sqrt(ale_m ** 2 + ale_r ** 2)
+        if period < 1:
+            epi = 0.36 + 0.07 * (mag - 6)
+        else:
+            epi = 0.34 + 0.06 * (mag - 6)
+        out[1, m] = np.sqrt(ale ** 2 + epi ** 2)
+        if period == 3.0:
+            out[0, m] /= 0.612
+        if period == 4.0:
+            out[0, m] /= 0.559
+    return out
+
+
+def campbell03(ctx, imts):
+    """Campbell2003.compute (kind "base"), campbell_2003.py:178-189 with
+    _compute_mean_1 :39-47 and the terms :71-106"""
+    out = _out(len(imts), len(ctx.mag))
+    mag, rrup = ctx.mag, ctx.rrup
+    for m, imt in enumerate(imts):
+        C = coeffs('C03', imt)
+        term1 = (C['c2'] * mag) + C['c3'] * (8.5 - mag) ** 2
+        R = np.sqrt(rrup ** 2 + (C['c7'] * np.exp(C['c8'] * mag)) ** 2)
+        term2 = C['c4'] * np.log(R) + (C['c5'] + C['c6'] * mag) * rrup
+        f3 = np.zeros_like(rrup)
+        mid = (rrup > 70) & (rrup <= 130)
+        far = rrup > 130
+        f3[mid] = C['c9'] * (np.log(rrup[mid]) - np.log(70))
+        f3[far] = (C['c9'] * (np.log(rrup[far]) - np.log(70)) +
+                   C['c10'] * (np.log(rrup[far]) - np.log(130)))
+        out[0, m] = C['c1'] + term1 + term2 + f3
+        out[1, m] = np.where(mag < 7.16, C['c11'] + C['c12'] * mag, C['c13'])
+    return out
+
+
+# --------------------------------------------------------------------- #
 #                              registry                                  #
 # --------------------------------------------------------------------- #
 
@@ -868,6 +976,9 @@ MODELS = {
         lambda ctx, imts, **kw: akkar14(ctx, imts, 'repi', **kw),
     'AkkarEtAlRhyp2014':
         lambda ctx, imts, **kw: akkar14(ctx, imts, 'rhypo', **kw),
+    'ChiouYoungs2008': cy08,
+    'ToroEtAl2002': toro02,
+    'Campbell2003': campbell03,
 }
 
 

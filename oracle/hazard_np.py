@@ -36,6 +36,10 @@ REQUIRES = {
     'AkkarEtAlRjb2014': (('rjb',), ('mag', 'rake'), ('vs30',)),
     'AkkarEtAlRepi2014': (('repi',), ('mag', 'rake'), ('vs30',)),
     'AkkarEtAlRhyp2014': (('rhypo',), ('mag', 'rake'), ('vs30',)),
+    'ChiouYoungs2008': (('rrup', 'rjb', 'rx'), ('mag', 'rake', 'dip', 'ztor'),
+                        ('vs30', 'vs30measured', 'z1pt0')),
+    'ToroEtAl2002': (('rjb',), ('mag',), ()),
+    'Campbell2003': (('rrup',), ('mag',), ()),
 }
 
 

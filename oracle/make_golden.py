@@ -89,6 +89,15 @@ GMPE_CASES = {
     'akkar14_rhyp': ('AkkarEtAlRhyp2014',
                      '[AkkarEtAlRhyp2014]\nadjustment_factor=1.2',
                      dict(adjustment_factor=1.2)),
+    # the models of the LogicTreeCase2ClassicalPSHA demo; a 4th element is
+    # the IMT list when the model does not cover IMTS_X
+    'cy08': ('ChiouYoungs2008', '[ChiouYoungs2008]', {}),
+    'toro02': ('ToroEtAl2002', '[ToroEtAl2002]', {},
+               ['PGA', 'SA(0.04)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)', 'SA(1.0)',
+                'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
+    'c03': ('Campbell2003', '[Campbell2003]', {},
+            ['PGA', 'SA(0.02)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)', 'SA(1.0)',
+             'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
 }
 
 
@@ -108,9 +117,10 @@ def random_ctx(cm, n, rng):
         ctx['width'] = rng.uniform(1, 25, n)
     if 'hypo_depth' in names:
         ctx['hypo_depth'] = rng.uniform(2, 25, n)
-    ctx['vs30'] = rng.choice([150, 180, 200, 225, 260, 300, 400, 560, 760,
-                              800, 1000, 1130, 1500, 2200], n
-                             ) * rng.uniform(0.95, 1.05, n)
+    if 'vs30' in names:
+        ctx['vs30'] = rng.choice([150, 180, 200, 225, 260, 300, 400, 560, 760,
+                                  800, 1000, 1130, 1500, 2200], n
+                                 ) * rng.uniform(0.95, 1.05, n)
     if 'vs30measured' in names:
         ctx['vs30measured'] = rng.random(n) < .5
     if 'z1pt0' in names:
@@ -148,18 +158,26 @@ def ctx_columns(ctx):
 
 def make_gmpe():
     rng = np.random.default_rng(7)
-    for tag, (name, toml, kw) in GMPE_CASES.items():
+    # OQ_GOLDEN_ONLY=tag1,tag2 writes only those fixtures (the random
+    # stream still runs through every case, so the others do not change)
+    only = os.environ.get('OQ_GOLDEN_ONLY')
+    only = only.split(',') if only else None
+    for tag, case in GMPE_CASES.items():
+        name, toml, kw = case[:3]
+        imts = case[3] if len(case) > 3 else IMTS_X
         gs = valid.gsim(toml)
         cm = ContextMaker('*', [gs], dict(
-            imtls={i: [0.1] for i in IMTS_X}, truncation_level=3.))
+            imtls={i: [0.1] for i in imts}, truncation_level=3.))
         ctx = random_ctx(cm, 384, rng)
+        if only and tag not in only:
+            continue
         ref = cm.get_mean_stds([ctx], split_by_mag=False)[:, 0]
-        mine = gmpe_np.MODELS[name](ctx, IMTS_X, **kw)
+        mine = gmpe_np.MODELS[name](ctx, imts, **kw)
         np.testing.assert_allclose(mine, ref, rtol=1e-13, atol=1e-14,
                                    err_msg=tag)
         np.savez_compressed(
             os.path.join(GOLDEN, 'gmpe_%s.npz' % tag), name=name,
-            kwargs=json.dumps(kw), imts=np.array(IMTS_X), mean_stds=ref,
+            kwargs=json.dumps(kw), imts=np.array(imts), mean_stds=ref,
             **ctx_columns(ctx))
         print('gmpe', tag, 'oracle == reference to',
               np.abs(mine - ref).max())
@@ -404,6 +422,14 @@ KAT = {  # reference verification tables (hazardlib/tests/gsim/data) ->
                           'BA08_STD_INTER.csv', 'BA08_SIGTM_SS.csv']),
     'akkar14_rjb': ('AKKAR14', ['AKKAR_2014_RJB_MEAN.csv',
                                 'AKKAR_2014_RJB_STD_TOTAL.csv']),
+    'cy08': ('NGA/CY08', ['CY08_MEDIAN_MS_HW_NM.csv', 'CY08_MEDIAN_MS_HW_RV.csv',
+                          'CY08_MEDIAN_MS_HW_SS.csv',
+                          'CY08_SIGMEAS_MS_HW_SS.csv',
+                          'CY08_SIGINFER_MS_HW_SS.csv',
+                          'CY08_INTER_EVENT_SIGMA.csv',
+                          'CY08_INTRA_EVENT_SIGMA.csv']),
+    'toro02': ('TORO02', ['T02_MEAN.csv', 'T02_STD_TOTAL.csv']),
+    'c03': ('C03', ['C03_MEAN.csv', 'C03_STD_TOTAL.csv']),
 }
 
 
@@ -411,6 +437,8 @@ def make_kat(keep=60):
     base = os.path.join(oq_bootstrap.REFERENCE, 'openquake', 'hazardlib',
                         'tests', 'gsim', 'data')
     rng = np.random.default_rng(3)
+    only = os.environ.get('OQ_GOLDEN_ONLY')
+    only = only.split(',') if only else None
     for tag, (sub, files) in KAT.items():
         for fname in files:
             src = os.path.join(base, sub, fname)
@@ -422,6 +450,8 @@ def make_kat(keep=60):
             header, body = rows[0], rows[1:]
             idx = sorted(rng.choice(len(body), min(keep, len(body)),
                                     replace=False))
+            if only and tag not in only:
+                continue
             dest = os.path.join(GOLDEN, 'kat_%s__%s' % (tag, fname))
             with open(dest, 'w', newline='') as f:
                 w = csv.writer(f)

@@ -44,6 +44,7 @@ CASES = [
     ('AtkinsonBoore2006', dict(mag_eq='Mblg96', scale_fac=0.5)),
     ('AkkarEtAlRjb2014', {}), ('AkkarEtAlRepi2014', {}),
     ('AkkarEtAlRhyp2014', dict(adjustment_factor=1.2)),
+    ('ChiouYoungs2008', {}), ('ToroEtAl2002', {}), ('Campbell2003', {}),
 ]
 IMTS = ['PGA', 'SA(0.1)', 'SA(0.27)', 'SA(1.0)', 'SA(3.0)']
 

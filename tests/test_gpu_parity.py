@@ -86,7 +86,7 @@ def test_gmpe_staged_golden(oq, tag):
 
 def test_gmpe_unsupported_is_an_error(oq):
     with pytest.raises(NotImplementedError):
-        oq.get_gsim('ToroEtAl2002')
+        oq.get_gsim('ZhaoEtAl2006Asc')
     with pytest.raises(NotImplementedError):
         oq.BooreEtAl2014(usgs_basin_scaling=True)
     with pytest.raises(KeyError):   # IMT outside the table

@@ -31,6 +31,9 @@ from openquake.hazardlib.gsim.atkinson_boore_2006 import (  # noqa
     AtkinsonBoore2006)
 from openquake.hazardlib.gsim.akkar_2014 import (  # noqa
     AkkarEtAlRjb2014, AkkarEtAlRepi2014, AkkarEtAlRhyp2014)
+from openquake.hazardlib.gsim.chiou_youngs_2008 import ChiouYoungs2008  # noqa
+from openquake.hazardlib.gsim.toro_2002 import ToroEtAl2002  # noqa
+from openquake.hazardlib.gsim.campbell_2003 import Campbell2003  # noqa
 
 TABLES = {
     'BSSA14': BooreEtAl2014.COEFFS,
@@ -45,6 +48,9 @@ TABLES = {
     'AKKAR14_RJB': AkkarEtAlRjb2014.COEFFS,
     'AKKAR14_REPI': AkkarEtAlRepi2014.COEFFS,
     'AKKAR14_RHYP': AkkarEtAlRhyp2014.COEFFS,
+    'CY08': ChiouYoungs2008.COEFFS,
+    'TORO02': ToroEtAl2002.COEFFS,
+    'C03': Campbell2003.COEFFS,
 }
 
 
