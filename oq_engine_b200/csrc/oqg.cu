@@ -1931,17 +1931,19 @@ static const char *missing_column(const oqg_gsim &g, const oqg_ctx *c) {
   if ((d >> OQG_REPI & 1) && !c->repi) return "repi";
   if ((d >> OQG_RHYPO & 1) && !c->rhypo) return "rhypo";
   if (!c->mag) return "mag";
-  if (!c->vs30) return "vs30";
   int f = g.family;
-  if (f != OQG_AB06 && !c->rake) return "rake";
-  if (f == OQG_CY14 || f == OQG_ASK14 || f == OQG_CB14) {
+  const bool plain = f == OQG_TORO02 || f == OQG_C03;   // mag + one distance
+  if (!plain && !c->vs30) return "vs30";
+  if (f != OQG_AB06 && !plain && !c->rake) return "rake";
+  if (f == OQG_CY14 || f == OQG_ASK14 || f == OQG_CB14 || f == OQG_CY08) {
     if (!c->dip) return "dip";
     if (!c->ztor) return "ztor";
   }
   if ((f == OQG_ASK14 || f == OQG_CB14) && !c->width) return "width";
   if (f == OQG_CB14 && !c->hypo_depth) return "hypo_depth";
   if (f == OQG_CB14 && !c->z2pt5) return "z2pt5";
-  if ((f == OQG_CY14 || f == OQG_ASK14) && (!c->z1pt0 || !c->vs30measured))
+  if ((f == OQG_CY14 || f == OQG_ASK14 || f == OQG_CY08) &&
+      (!c->z1pt0 || !c->vs30measured))
     return "z1pt0/vs30measured";
   if (f == OQG_BSSA14 && (g.flags & 3) && !c->z1pt0) return "z1pt0";
   if (g.par[0] != 0. && f <= OQG_CB14 && !c->rrup) return "rrup";
