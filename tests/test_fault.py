@@ -148,9 +148,9 @@ def test_hazard_of_a_fault_source_fused(oq, tag):
     np.testing.assert_allclose(pmap.array[sids], 1. - D[tag + '_poes'],
                                rtol=2e-5, atol=1.5e-7)
     poes = D[tag + '_poes'].astype(np.float64)
-    big = poes > 1e-4
+    big = poes > 1e-2       # float32 pnes: 6e-8 absolute each
     np.testing.assert_allclose(
-        1. - pmap.array[sids][big].astype(np.float64), poes[big], rtol=2e-3)
+        1. - pmap.array[sids][big].astype(np.float64), poes[big], rtol=5e-4)
     # rates map, device resident, through RmapMaker
     res = oq.RmapMaker(cm, sc, [src]).make()
     rates = res['rmap'].array
