@@ -57,7 +57,14 @@ def synth(U, N, seed):
     """SURVEY.md section 8d synthetic ruptures and sites"""
     from helpers import synth_ruptures, synth_sites
     rng = np.random.default_rng(seed)
-    return synth_ruptures(U, rng), synth_sites(N, rng)
+    r, sites = synth_ruptures(U, rng), synth_sites(N, rng)
+    if os.environ.get('OQG_BENCH_SITE_PATCH'):
+        # experiment: the caller hands the grid in 8 x 4 patches, not rows
+        n_side = int(np.ceil(np.sqrt(N)))
+        iy, ix = np.divmod(np.arange(N), n_side)
+        order = np.lexsort((ix % 8, iy % 4, ix // 8, iy // 4))
+        sites = {k: (v if k == 'sids' else v[order]) for k, v in sites.items()}
+    return r, sites
 
 
 def flops_per_row(gsim, M, L1):

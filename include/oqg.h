@@ -474,6 +474,13 @@ int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err);
 int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table);
 int oqg_last_fused_subs(oqg_handle *h);
 
+/* Site grouping of the fused pass (default on, cells of 0.16 degrees): the
+ * sites are sorted by (cell, vs30) on the device before the pass so that the
+ * 32 sites of a warp are alike and the exact-zero level skipping fires more
+ * often; the map rows follow through the permuted site index, the results
+ * are bit-identical.  on = 0 keeps the caller's site order. */
+int oqg_set_site_grouping(oqg_handle *h, int on, double cell_deg);
+
 /* Statistics pass of the fused kernel: while on, a call with `counters`
  * also adds to counters[1] the PoE evaluations the kernel EXECUTES (the
  * levels its level skipping does not cut off: skipped levels have a PoE of

@@ -14,6 +14,7 @@
 //                    (site, level) with distances, GMPE and PoEs in
 //                    registers / shared memory, nothing materialised
 //   k_finalize       partial sums -> float32 pne / rate map
+#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -99,6 +100,11 @@ struct oqg_handle {
   int fused_cfg[2] = {0, 0};   // oqg_set_fused_config
   bool count_evals = false;    // oqg_set_count_evals
   int last_subs = 1;
+  // site grouping of the fused pass (oqg_set_site_grouping): scratch of the
+  // sort and the permuted site parameters
+  bool site_grouping = true;
+  double site_cell_deg = 0.16;
+  Buf sg_keys[2], sg_idx[2], sg_tmp, sg_par[4], sg_sidx;
 };
 
 static std::string g_create_err;
@@ -575,10 +581,77 @@ struct FusedArgs {
 // that tab32 + bits(k + 2^23) * 16 is the address of node k.  12 instructions
 // per evaluation with the DFMA of x and the FFMA into the accumulator: F2F,
 // FADD.SAT, FFMA (round), FADD, FFMA (u), IMAD (address), LDS.128, 3 FFMA.
+#ifndef OQG_F2F_SAT
+#define OQG_F2F_SAT 1     // one F2F.SAT instead of F2F + FADD.SAT
+#endif
+#ifndef OQG_POE_PAIR
+#define OQG_POE_PAIR 0    // two levels per evaluation with packed f32x2 ops
+#endif
+
+// float64 -> float32 clamped to [0, 1], NaN -> 0 (poe 0)
+__device__ __forceinline__ float sat_f32(double x64) {
+#if OQG_F2F_SAT
+  float x;
+  asm("cvt.rn.sat.f32.f64 %0, %1;" : "=f"(x) : "d"(x64));
+  return x;
+#else
+  return __saturatef((float)x64);
+#endif
+}
+
+// Blackwell packed float32 pairs (FFMA2 / FADD2): one issue slot for two
+// independent operations
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// two evaluations of the table at once: the rounding to the node and the
+// offset inside it in packed arithmetic, the two cubics interleaved
+template <int REP>
+__device__ __forceinline__ f32x2 poe_table2(unsigned tab32, f32x2 nm1,
+                                            double x64a, double x64b) {
+  const f32x2 big = pack2(8388608.f, 8388608.f);
+  const f32x2 mone = pack2(-1.f, -1.f);
+  const f32x2 x = pack2(sat_f32(x64a), sat_f32(x64b));
+  const f32x2 y = fma2(x, nm1, big);        // round to the nearest integer
+  const f32x2 negk = fma2(y, mone, big);    // 2^23 - y = -k, exact
+  const f32x2 u = fma2(x, nm1, negk);
+  float ya, yb, ua, ub;
+  unpack2(y, ya, yb);
+  unpack2(u, ua, ub);
+  float a0, a1, a2, a3, b0, b1, b2, b3;
+  unsigned aa = tab32 + __float_as_uint(ya) * (PT_STRIDE * 4 * REP);
+  unsigned ab = tab32 + __float_as_uint(yb) * (PT_STRIDE * 4 * REP);
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3) : "r"(aa));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(ab));
+  float pa = fmaf(a3, ua, a2), pb = fmaf(b3, ub, b2);
+  pa = fmaf(pa, ua, a1); pb = fmaf(pb, ub, b1);
+  pa = __saturatef(fmaf(pa, ua, a0)); pb = __saturatef(fmaf(pb, ub, b0));
+  return pack2(pa, pb);
+}
+
 template <int REP>
 __device__ __forceinline__ float poe_table(unsigned tab32, float nm1,
                                            double x64) {
-  float x = __saturatef((float)x64);    // NaN -> 0 -> poe 0
+  float x = sat_f32(x64);    // NaN -> 0 -> poe 0
   float y = fmaf(x, nm1, 8388608.f);    // 2^23: round to nearest integer
   float u = fmaf(x, nm1, -(y - 8388608.f));
   float c0, c1, c2, c3;
@@ -755,7 +828,13 @@ k_fused(const FusedArgs A) {
   // fast path: float32 accumulators per tile, flushed to the FP64 partial
   // sums of this thread in global memory (L2 resident)
   double acc[FAST ? 1 : NL];
+#if OQG_POE_PAIR
+  f32x2 facc2[FAST ? NLR / 2 : 1];
+#define FACC_GET(l) __uint_as_float((unsigned)(facc2[(l) >> 1] >> (((l) & 1) * 32)))
+#else
   float facc[FAST ? NLR : 1];
+#define FACC_GET(l) facc[l]
+#endif
   const int L = A.M * A.L1;
   double *dst = A.part + (((int64_t)blockIdx.y * A.G + A.g) * A.N +
                           (site_ok ? n : 0)) * L + m * A.L1 + l0;
@@ -769,8 +848,13 @@ k_fused(const FusedArgs A) {
   }
   unsigned long long kept = 0;
   if (FAST) {
+#if OQG_POE_PAIR
+#pragma unroll
+    for (int l = 0; l < NLR / 2; l++) facc2[l] = 0ull;
+#else
 #pragma unroll
     for (int l = 0; l < NLR; l++) facc[l] = 0.f;
+#endif
 #pragma unroll
     for (int l = NLR; l < NL; l++) s_hi[(l - NLR) * hs] = 0.f;
   }
@@ -978,6 +1062,16 @@ k_fused(const FusedArgs A) {
         // The test is made once per LGRP levels: the evaluations of a group
         // are independent instruction chains in one basic block (a level
         // past the threshold evaluates to exactly 0: x saturates to node 0)
+#if OQG_POE_PAIR
+        const f32x2 rt2 = pack2(rt, rt), nm2 = pack2(nm1, nm1);
+#pragma unroll
+        for (int l = 0; l < NLR; l += 2) {
+          if (ll[l] >= thr_w) break;
+          facc2[l >> 1] = fma2(rt2, poe_table2<REP>(tab32, nm2, fma(ll[l], xa, xb),
+                                                    fma(ll[l + 1], xa, xb)),
+                               facc2[l >> 1]);
+        }
+#else
 #pragma unroll
         for (int l = 0; l < NLR; l += LGRP) {
           if (ll[l] >= thr_w) break;
@@ -986,6 +1080,7 @@ k_fused(const FusedArgs A) {
             facc[l + j] = fmaf(rt, poe_table<REP>(tab32, nm1, fma(ll[l + j], xa, xb)),
                                facc[l + j]);
         }
+#endif
         // the levels are sorted: if the loop above stopped early, this one
         // stops at once
 #pragma unroll
@@ -1016,13 +1111,18 @@ k_fused(const FusedArgs A) {
       if (site_ok) {
 #pragma unroll
         for (int l = 0; l < NLR; l++)
-          if (l < nl) dst[l] += (double)facc[l];
+          if (l < nl) dst[l] += (double)FACC_GET(l);
 #pragma unroll
         for (int l = NLR; l < NL; l++)
           if (l < nl) dst[l] += (double)s_hi[(l - NLR) * hs];
       }
+#if OQG_POE_PAIR
+#pragma unroll
+      for (int l = 0; l < NLR / 2; l++) facc2[l] = 0ull;
+#else
 #pragma unroll
       for (int l = 0; l < NLR; l++) facc[l] = 0.f;
+#endif
 #pragma unroll
       for (int l = NLR; l < NL; l++) s_hi[(l - NLR) * hs] = 0.f;
     }
@@ -1191,6 +1291,10 @@ int oqg_create(oqg_handle **out, int device) {
   cudaEventCreateWithFlags(&h->const_ev, cudaEventDisableTiming);
   cudaMalloc((void **)&h->flag_dev, sizeof(int));
   cudaMemset(h->flag_dev, 0, sizeof(int));
+  // tuning knobs for A/B measurements (oqg_set_site_grouping)
+  if (const char *e = getenv("OQG_SITE_GROUPING")) h->site_grouping = atoi(e) != 0;
+  if (const char *e = getenv("OQG_SITE_CELL"))
+    if (atof(e) > 0.) h->site_cell_deg = atof(e);
   *out = h;
   return 0;
 }
@@ -1199,7 +1303,11 @@ void oqg_destroy(oqg_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (Buf *b : {&h->rup, &h->site, &h->part, &h->ptab, &h->conv}) if (b->p) cudaFree(b->p);
+  for (Buf *b : {&h->rup, &h->site, &h->part, &h->ptab, &h->conv,
+                 &h->sg_keys[0], &h->sg_keys[1], &h->sg_idx[0], &h->sg_idx[1],
+                 &h->sg_tmp, &h->sg_par[0], &h->sg_par[1], &h->sg_par[2],
+                 &h->sg_par[3], &h->sg_sidx})
+    if (b->p) cudaFree(b->p);
   for (auto &b : h->stage) if (b.p) cudaFree(b.p);
   if (h->flag_dev) cudaFree(h->flag_dev);
   for (auto &ev : h->ev) cudaEventDestroy(ev);
@@ -1375,6 +1483,101 @@ static int prep_sites(oqg_handle *h, const oqg_sites *s, int N) {
       s->lon, s->lat, s->depth, N, (double *)h->site.p);
   h->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- site grouping ----------------------------------------------------------
+// The fused kernel skips, for a whole warp of 32 sites, the levels above the
+// largest mean + truncation_level * sigma of the warp (their PoEs are exactly
+// 0).  How often that fires depends on how alike the 32 sites are: on a grid
+// handed over row by row, with unrelated vs30 values, 32 % of the levels are
+// skipped on the cfg3 workload; with the sites of a warp taken from one
+// ~18 km cell and neighbouring in vs30 it is 43 % (a thread alone would skip
+// 50 %).  The sites are therefore sorted by (cell row, cell column, vs30)
+// before the pass -- a radix sort of N 64-bit keys on the device -- and the
+// map rows go through the permuted site index.  Per site nothing changes:
+// the same ruptures in the same order, so the map is bit-identical.
+__global__ void k_site_keys(const double *__restrict__ lon,
+                            const double *__restrict__ lat,
+                            const double *__restrict__ vs30, int N,
+                            double inv_cell, unsigned long long *keys,
+                            int *idx) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const double x = (lon[n] + 180.) * inv_cell, y = (lat[n] + 90.) * inv_cell;
+  const unsigned long long cx = (unsigned long long)fmin(fmax(x, 0.), 65535.);
+  const unsigned long long cy = (unsigned long long)fmin(fmax(y, 0.), 65535.);
+  const float v = vs30 ? (float)vs30[n] : 0.f;
+  const unsigned vb = v > 0.f ? __float_as_uint(v) : 0u;   // NaN, <= 0 -> 0
+  keys[n] = (cy << 48) | (cx << 32) | vb;
+  idx[n] = n;
+}
+
+__global__ void k_prep_sites_perm(const double *__restrict__ lon,
+                                  const double *__restrict__ lat,
+                                  const double *__restrict__ dep,
+                                  const double *__restrict__ vs30,
+                                  const double *__restrict__ z1pt0,
+                                  const double *__restrict__ z2pt5,
+                                  const uint8_t *__restrict__ measured,
+                                  const uint32_t *__restrict__ sidx,
+                                  const int *__restrict__ perm, int N,
+                                  double *__restrict__ out,
+                                  double *__restrict__ o_vs30,
+                                  double *__restrict__ o_z1pt0,
+                                  double *__restrict__ o_z2pt5,
+                                  uint8_t *__restrict__ o_measured,
+                                  uint32_t *__restrict__ o_sidx) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int j = perm[n];
+  prep_site(lon[j], lat[j], dep ? dep[j] : 0., out + n, N);
+  if (vs30) o_vs30[n] = vs30[j];
+  if (z1pt0) o_z1pt0[n] = z1pt0[j];
+  if (z2pt5) o_z2pt5[n] = z2pt5[j];
+  if (measured) o_measured[n] = measured[j];
+  o_sidx[n] = sidx ? sidx[j] : (uint32_t)j;
+}
+
+// prepared sites in grouped order: `view` gets the permuted parameter arrays
+// and *sidx_out the permuted map rows
+static int prep_sites_grouped(oqg_handle *h, const oqg_sites *s,
+                              const uint32_t *sidx, int N, oqg_sites *view,
+                              const uint32_t **sidx_out) {
+  if (!s->lon || !s->lat) return fail(h, "sites need lon and lat");
+  if (reserve(h, h->site, (size_t)NF_SITE * N * 8)) return 1;
+  for (int k = 0; k < 2; k++) {
+    if (reserve(h, h->sg_keys[k], (size_t)N * 8)) return 1;
+    if (reserve(h, h->sg_idx[k], (size_t)N * 4)) return 1;
+  }
+  for (int k = 0; k < 3; k++)
+    if (reserve(h, h->sg_par[k], (size_t)N * 8)) return 1;
+  if (reserve(h, h->sg_par[3], (size_t)N)) return 1;
+  if (reserve(h, h->sg_sidx, (size_t)N * 4)) return 1;
+  auto *k0 = (unsigned long long *)h->sg_keys[0].p;
+  auto *k1 = (unsigned long long *)h->sg_keys[1].p;
+  int *i0 = (int *)h->sg_idx[0].p, *i1 = (int *)h->sg_idx[1].p;
+  k_site_keys<<<(N + 255) / 256, 256, 0, h->stream>>>(
+      s->lon, s->lat, s->vs30, N, 1. / h->site_cell_deg, k0, i0);
+  size_t tmp = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, i0, i1, N, 0, 64,
+                                     h->stream));
+  if (reserve(h, h->sg_tmp, tmp)) return 1;
+  CK(cub::DeviceRadixSort::SortPairs(h->sg_tmp.p, tmp, k0, k1, i0, i1, N, 0,
+                                     64, h->stream));
+  k_prep_sites_perm<<<(N + 127) / 128, 128, 0, h->stream>>>(
+      s->lon, s->lat, s->depth, s->vs30, s->z1pt0, s->z2pt5, s->vs30measured,
+      sidx, i1, N, (double *)h->site.p, (double *)h->sg_par[0].p,
+      (double *)h->sg_par[1].p, (double *)h->sg_par[2].p,
+      (uint8_t *)h->sg_par[3].p, (uint32_t *)h->sg_sidx.p);
+  h->launches += 3;
+  CK(cudaGetLastError());
+  *view = *s;
+  if (s->vs30) view->vs30 = (const double *)h->sg_par[0].p;
+  if (s->z1pt0) view->z1pt0 = (const double *)h->sg_par[1].p;
+  if (s->z2pt5) view->z2pt5 = (const double *)h->sg_par[2].p;
+  if (s->vs30measured) view->vs30measured = (const uint8_t *)h->sg_par[3].p;
+  *sidx_out = (const uint32_t *)h->sg_sidx.p;
   return 0;
 }
 
@@ -2219,7 +2422,15 @@ static int hazard_fused(oqg_handle *h, const double *planar,
   } else if (prep_ruptures(h, planar, mag, magdist, U)) {
     return 1;
   }
-  if (prep_sites(h, sites, N)) return 1;
+  // planar ruptures: sites grouped by cell and vs30 (the external distance
+  // planes of the other ruptures are in the caller's site order)
+  oqg_sites grouped;
+  if (!xpar && h->site_grouping && N >= 256) {
+    if (prep_sites_grouped(h, sites, sidx, N, &grouped, &sidx)) return 1;
+    sites = &grouped;
+  } else if (prep_sites(h, sites, N)) {
+    return 1;
+  }
 
   FusedArgs A;
   memset(&A, 0, sizeof(A));
@@ -2386,6 +2597,13 @@ int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table) {
 }
 
 int oqg_last_fused_subs(oqg_handle *h) { return h->last_subs; }
+
+int oqg_set_site_grouping(oqg_handle *h, int on, double cell_deg) {
+  if (on && !(cell_deg > 0.)) cell_deg = 0.16;
+  h->site_grouping = on != 0;
+  if (on) h->site_cell_deg = cell_deg;
+  return 0;
+}
 
 int oqg_set_count_evals(oqg_handle *h, int on) {
   h->count_evals = on != 0;
