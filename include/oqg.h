@@ -474,6 +474,22 @@ int oqg_poe_table_info(oqg_handle *h, int *in_use, double *max_rel_err);
 int oqg_set_fused_config(oqg_handle *h, int subs, int plain_table);
 int oqg_last_fused_subs(oqg_handle *h);
 
+/* MapArray.to_array + the chunk grouping of _store (hazardlib/map_array.py:
+ * 396-405, 520-540, 49-64; calculators/classical.py:58-101): the rates
+ * map_dev [N][L][G] float32 as records of rates_dt -- {uint32 sid, uint16 lid,
+ * uint16 gid, float32 rate}, 12 bytes -- for the elements with rate > 0.
+ * rows_dev [R] (may be NULL = all the N * G rows in natural order) lists the
+ * curves g * N + s in output order (the reference: by chunk = sid %
+ * num_chunks, then gsim column, then site); inside a curve the levels are in
+ * order.  sids_dev [N] (NULL = 0..N-1), gid_dev [G] the gsim IDs, level0 the
+ * offset of the level index.  out_dev has room for `capacity` records (NULL:
+ * count only); *total gets the number of records.  Synchronises. */
+int oqg_rates_to_records(oqg_handle *h, const float *rates_dev, int N, int L,
+                         int G, const uint32_t *sids_dev,
+                         const int32_t *gid_dev, int level0,
+                         const int64_t *rows_dev, int64_t R, void *out_dev,
+                         int64_t capacity, int64_t *total);
+
 /* Site grouping of the fused pass (default on, cells of 0.16 degrees): the
  * sites are sorted by (cell, vs30) on the device before the pass so that the
  * 32 sites of a warp are alike and the exact-zero level skipping fires more

@@ -21,7 +21,8 @@ from .source import (  # noqa
     PointSource, PointSourceBatch, TruncatedGRMFD, EvenlyDiscretizedMFD,
     ArbitraryMFD, point_ruptures_device)
 from .postproc import (  # noqa
-    postclassical, compute_hazard_maps, compute_hmaps, calc_mean_rates)
+    postclassical, compute_hazard_maps, compute_hmaps, calc_mean_rates,
+    rates_to_records, rates_dt)
 from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
                    mesh_rx_ry0, mesh_dip_strike_width, mesh_rjb)

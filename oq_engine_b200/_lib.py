@@ -106,6 +106,9 @@ def lib():
                                      C.c_int, c_void, C.c_int, c_void]),
         'oqg_hazard_maps': (C.c_int, [H, c_void, C.c_int64, C.c_int, C.c_int,
                                       c_void, C.c_int, c_void, c_void]),
+        'oqg_rates_to_records': (C.c_int, [
+            H, c_void, C.c_int, C.c_int, C.c_int, c_void, c_void, C.c_int,
+            c_void, C.c_int64, c_void, C.c_int64, C.POINTER(C.c_int64)]),
         'oqg_mesh_min_distance': (C.c_int, [
             H, c_void, c_void, c_void, C.c_int64, c_void, C.c_int,
             C.POINTER(OqgSites), C.c_int, c_void]),

@@ -15,6 +15,7 @@
 //                    registers / shared memory, nothing materialised
 //   k_finalize       partial sums -> float32 pne / rate map
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -44,7 +45,7 @@ using namespace oqg;
 #define RT 16          // ruptures per shared-memory tile
 #endif
 #ifndef NLR
-#define NLR 10         // level accumulators kept in registers (fast path); the
+#define NLR 12         // level accumulators kept in registers (fast path); the
                        // upper NL - NLR levels, which the level skipping
                        // reaches rarely, accumulate in shared memory
 #endif
@@ -52,8 +53,9 @@ using namespace oqg;
 #define OQG_ROLL_ALL 0   // experiment: roll the rupture stage of every family
 #endif
 #ifndef LGRP
-#define LGRP 2         // levels evaluated per level-skipping test (NL % LGRP == 0)
+#define LGRP 4         // levels evaluated per level-skipping test (NLR % LGRP == 0)
 #endif
+static_assert(NLR % LGRP == 0 && NLR % 2 == 0 && NLR <= NL, "NLR, LGRP");
 #define NWMAX 7        // warps (units) per CTA in the fused kernel
 #ifndef MINB
 #define MINB 4         // CTAs per SM the fused kernel is compiled for
@@ -558,7 +560,7 @@ struct FusedArgs {
   const float *ptab;      // [nodes][PT_STRIDE] or null (exact FP64 PoEs)
   int pt_nodes;
   unsigned pt_bias;
-  double *part;           // [RC][G][N][L]
+  double *part;           // [RC][G][L][N] (site fastest)
   unsigned long long *counters;
   int64_t U, Us;          // ruptures, stride of the fields of `rup`
   int N, K;
@@ -714,8 +716,12 @@ template <int F, bool NEGBIN, bool FAST> struct FusedLayout {
   static constexpr int PW = FF::HAS_P ? sizeof(typename FF::P) / 8 : 0;
   static constexpr int DM = DistMask<F>::value;
   static constexpr int NPL = popc_below(DM, OQG_NDIST);
-  static constexpr int RUP = 0;                          // [NF_RUP][RT]
-  static constexpr int DIST = RUP + NF_RUP * RT;         // [NPL][RT][32]
+  // rupture fields staged per tile: without repi / rhypo the hypocentre
+  // fields stay in HBM
+  static constexpr int NFR =
+      (DM & ((1 << OQG_REPI) | (1 << OQG_RHYPO))) ? NF_RUP : NF_RUP_NOHYPO;
+  static constexpr int RUP = 0;                          // [NFR][RT]
+  static constexpr int DIST = RUP + NFR * RT;            // [NPL][RT][32]
   static constexpr int SITE = DIST + NPL * RT * 32;      // [NF_SITE][32]
   static constexpr int SQ = SITE + NF_SITE * 32;         // [NWMAX + 1][RT][QW]
   static constexpr int SP = SQ + (NWMAX + 1) * RT * QW;  // [PW][RT][32]
@@ -836,12 +842,20 @@ k_fused(const FusedArgs A) {
 #define FACC_GET(l) facc[l]
 #endif
   const int L = A.M * A.L1;
-  double *dst = A.part + (((int64_t)blockIdx.y * A.G + A.g) * A.N +
-                          (site_ok ? n : 0)) * L + m * A.L1 + l0;
+  // partial sums [chunk][gsim][level][site]: site fastest, so that the warp's
+  // read-modify-write of one level is one contiguous 256-byte request
+  const int64_t ds = A.N;
+  const int64_t dat = (((int64_t)blockIdx.y * A.G + A.g) * L + m * A.L1 + l0) *
+                          ds + (site_ok ? n : 0);
+  // exact path: float64 results; fast path: float32 partial sums (the
+  // float32 register accumulators of <= 128 ruptures are added to them: one
+  // more rounding of 6e-8 per flush, against 128 in the registers)
+  double *dst = A.part + dat;
+  float *dstf = reinterpret_cast<float *>(A.part) + dat;
   const bool writer = unit_ok && site_ok;
   if (FAST) {
     if (writer)
-      for (int l = 0; l < nl; l++) dst[l] = 0.;
+      for (int l = 0; l < nl; l++) dstf[l * ds] = 0.f;
   } else {
 #pragma unroll
     for (int l = 0; l < NL; l++) acc[l] = NEGBIN ? 1. : 0.;
@@ -886,7 +900,7 @@ k_fused(const FusedArgs A) {
   // between two barriers.
   auto fetch_tile = [&](int64_t r0) {
     const int nr = (int)min((int64_t)RT, r_end - r0);
-    for (int i = tid; i < NF_RUP * (RT / 2); i += tb) {
+    for (int i = tid; i < LY::NFR * (RT / 2); i += tb) {
       const int f = i / (RT / 2), j = (i - f * (RT / 2)) * 2;
       const int nb = min(max(nr - j, 0), 2) * 8;          // bytes to read
       const double *src = A.rup + (int64_t)f * A.Us + r0 + (nb ? j : 0);
@@ -1109,12 +1123,25 @@ k_fused(const FusedArgs A) {
     if (FAST && (--tiles_left == 0 || r0 + RT >= r_end)) {
       tiles_left = FLUSH_TILES;
       if (site_ok) {
+        // all the loads first: as `dst[l] += x` the twenty read-modify-write
+        // round trips to L2 were serialised (47 % of the long-scoreboard
+        // stalls of the kernel)
+        float t[NL];
+        // the stride goes through an opaque asm so that the twenty level
+        // addresses are formed here and not hoisted out of the rupture
+        // loop (as loop invariants they were spilled: 392 bytes of stack)
+        int64_t dsv = ds;
+        asm volatile("" : "+l"(dsv));
+        float *pl = dstf;
 #pragma unroll
-        for (int l = 0; l < NLR; l++)
-          if (l < nl) dst[l] += (double)FACC_GET(l);
+        for (int l = 0; l < NL; l++, pl += dsv) t[l] = l < nl ? __ldcg(pl) : 0.f;
+        pl = dstf;
 #pragma unroll
-        for (int l = NLR; l < NL; l++)
-          if (l < nl) dst[l] += (double)s_hi[(l - NLR) * hs];
+        for (int l = 0; l < NLR; l++, pl += dsv)
+          if (l < nl) __stcg(pl, t[l] + FACC_GET(l));
+#pragma unroll
+        for (int l = NLR; l < NL; l++, pl += dsv)
+          if (l < nl) __stcg(pl, t[l] + s_hi[(l - NLR) * hs]);
       }
 #if OQG_POE_PAIR
 #pragma unroll
@@ -1139,30 +1166,47 @@ k_fused(const FusedArgs A) {
   if (FAST || !writer) return;
 #pragma unroll
   for (int l = 0; l < NL; l++)
-    if (l < nl) dst[l] = NEGBIN ? -log(acc[l]) : acc[l];
+    if (l < nl) dst[l * ds] = NEGBIN ? -log(acc[l]) : acc[l];
 }
 
 // partial sums -> map[sidx[n]][l][g]
-__global__ void k_finalize(const double *__restrict__ part, int RC, int G,
-                           int N, int L, int L1,
-                           const uint32_t *__restrict__ sidx, int rates_mode,
-                           float *__restrict__ map) {
-  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t tot = (int64_t)N * L * G;
-  if (e >= tot) return;
-  int n = (int)(e / ((int64_t)L * G));
-  int rem = (int)(e - (int64_t)n * L * G);
-  int l = rem / G, g = rem - l * G;
-  double s = 0.;
-  for (int rc = 0; rc < RC; rc++)
-    s += part[(((int64_t)rc * G + g) * N + n) * L + l];
-  // ImtWeight == 0 (set_poes, contexts.py:1469-1475): the PoEs of this
-  // (gsim, IMT) count as zero.  Applied here, once per map element, and not
-  // in the fused kernel, where one more live value cost ASK14 15 %
-  if (c_imtmask[g * (L / L1) + l / L1]) s = 0.;
-  int64_t at = ((int64_t)(sidx ? sidx[n] : n) * L + l) * G + g;
-  if (rates_mode) map[at] = (float)((double)map[at] + s);
-  else map[at] = (float)((double)map[at] * exp(-s));
+// part [RC][G][L][N] (site fastest) -> map[sidx[n]][l][g]: a 32 x 32 tile of
+// (site, level-gsim) elements goes through shared memory so that both the
+// reads (along the sites) and the writes (along l, g) are coalesced
+__global__ void __launch_bounds__(256)
+k_finalize(const double *__restrict__ part, int part_f32, int RC, int G,
+           int N, int L, int L1, const uint32_t *__restrict__ sidx,
+           int rates_mode, float *__restrict__ map) {
+  __shared__ double tile[32][33];
+  const int LG = L * G;
+  const int n0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;     // (32, 8)
+  for (int j = ty; j < 32; j += 8) {
+    const int e = e0 + j, n = n0 + tx;              // e = l * G + g
+    double s = 0.;
+    if (e < LG && n < N) {
+      const int l = e / G, g = e - l * G;
+      const float *partf = reinterpret_cast<const float *>(part);
+      for (int rc = 0; rc < RC; rc++) {
+        const int64_t at = (((int64_t)rc * G + g) * L + l) * N + n;
+        s += part_f32 ? (double)partf[at] : part[at];
+      }
+      // ImtWeight == 0 (set_poes, contexts.py:1469-1475): the PoEs of this
+      // (gsim, IMT) count as zero.  Applied here, once per map element, and
+      // not in the fused kernel, where one more live value cost ASK14 15 %
+      if (c_imtmask[g * (L / L1) + l / L1]) s = 0.;
+    }
+    tile[j][tx] = s;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int n = n0 + j, e = e0 + tx;
+    if (n >= N || e >= LG) continue;
+    const double s = tile[tx][j];
+    const int64_t at = (int64_t)(sidx ? sidx[n] : n) * LG + e;
+    if (rates_mode) map[at] = (float)((double)map[at] + s);
+    else map[at] = (float)((double)map[at] * exp(-s));
+  }
 }
 
 // FP64 FMA microbenchmark (8 independent chains per thread)
@@ -2053,6 +2097,46 @@ int oqg_hazard_maps(oqg_handle *h, const float *curves, int64_t K, int M,
   return 0;
 }
 
+int oqg_rates_to_records(oqg_handle *h, const float *rates, int N, int L,
+                         int G, const uint32_t *sids, const int32_t *gid,
+                         int level0, const int64_t *rows, int64_t R,
+                         void *out, int64_t capacity, int64_t *total) {
+  CK(cudaSetDevice(h->device));
+  if (total) *total = 0;
+  if (N <= 0 || L <= 0 || G <= 0 || R <= 0) return 0;
+  if (!rates || !gid || !total) return fail(h, "rates_to_records: missing array");
+  if (R > (int64_t)N * G) return fail(h, "rates_to_records: too many rows");
+  if (level0 < 0 || level0 + L > 65536)
+    return fail(h, "rates_to_records: the level index does not fit in 16 bits");
+  // counts [R], offsets [R + 1] (the last one is the total)
+  if (reserve(h, h->stage[8], (size_t)(2 * R + 2) * 8)) return 1;
+  int64_t *counts = (int64_t *)h->stage[8].p, *offs = counts + R + 1;
+  CK(cudaMemsetAsync(counts + R, 0, 8, h->stream));
+  const unsigned blocks = (unsigned)((R * 32 + 127) / 128);
+  k_rate_rows_count<<<blocks, 128, 0, h->stream>>>(rates, N, L, G, rows, R,
+                                                   counts);
+  size_t tmp = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, counts, offs, R + 1,
+                                   h->stream));
+  if (reserve(h, h->sg_tmp, tmp)) return 1;
+  CK(cub::DeviceScan::ExclusiveSum(h->sg_tmp.p, tmp, counts, offs, R + 1,
+                                   h->stream));
+  h->launches += 2;
+  int64_t tot = 0;
+  CK(cudaMemcpyAsync(&tot, offs + R, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *total = tot;
+  if (!out) return 0;                  // counting pass only
+  if (tot > capacity)
+    return fail(h, "rates_to_records: " + std::to_string(tot) +
+                       " records, room for " + std::to_string(capacity));
+  k_rate_rows_write<<<blocks, 128, 0, h->stream>>>(
+      rates, N, L, G, sids, gid, level0, rows, R, offs, (RateRecord *)out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        int64_t U, double *planar, double *mag,
                        double *magdist, double *aux) {
@@ -2518,9 +2602,13 @@ static int hazard_fused(oqg_handle *h, const double *planar,
       return fail(h, std::string("fused launch: ") + cudaGetErrorString(e));
   }
   h->n_fused_ev = G;
-  int64_t tot = (int64_t)N * L * G;
-  k_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
-      A.part, (int)rc, G, N, L, L1, sidx, rates_mode, map);
+  {
+    dim3 fgrid((N + 31) / 32, (L * G + 31) / 32), fblock(32, 8);
+    const int part_f32 = A.ptab != nullptr && A.K == 0;   // the fast path
+    k_finalize<<<fgrid, fblock, 0, h->stream>>>(A.part, part_f32, (int)rc, G,
+                                                N, L, L1, sidx, rates_mode,
+                                                map);
+  }
   h->launches++;
   CK(cudaGetLastError());
   return 0;

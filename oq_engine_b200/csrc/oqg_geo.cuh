@@ -39,13 +39,16 @@ enum {
   RF_P0 = 26,      // arc origins as unit vectors BL, TL, TL, TR -> only 3
                    // distinct: BL (26), TL (29), TR (32)
   RF_CS = 35,      // surface projections of the corners TL TR BL BR, km (12)
-  RF_HYP = 47,     // hypocentre unit vector (3)
-  RF_HDEP = 50,    // hypocentre depth
-  RF_HE = 51,      // east unit vector at the hypocentre (3)
-  RF_HN = 54,      // north unit vector at the hypocentre (3)
-  RF_STRIKE = 57,
-  RF_MAG = 58, RF_RAKE = 59, RF_DIP = 60, RF_ZTOR = 61, RF_HYPO_DEPTH = 62,
-  RF_RATE = 63, RF_MAGDIST = 64,
+  RF_MAG = 47, RF_RAKE = 48, RF_DIP = 49, RF_ZTOR = 50, RF_HYPO_DEPTH = 51,
+  RF_RATE = 52, RF_MAGDIST = 53,
+  // the fields only repi, rhypo and the azimuth read come last: the fused
+  // kernel stages the first NF_RUP_NOHYPO fields for the other models
+  NF_RUP_NOHYPO = 54,
+  RF_HYP = 54,     // hypocentre unit vector (3)
+  RF_HDEP = 57,    // hypocentre depth
+  RF_HE = 58,      // east unit vector at the hypocentre (3)
+  RF_HN = 61,      // north unit vector at the hypocentre (3)
+  RF_STRIKE = 64,
   NF_RUP = 65
 };
 

@@ -22,6 +22,10 @@
 //                           memory, insertion sort
 //   k_mean_rates            calc_mean_rates (calc/mean_rates.py:62-74)
 //   k_hazard_maps           compute_hazard_maps
+//   k_rate_rows_count /     MapArray.to_array + the chunk grouping of _store
+//   k_rate_rows_write       (map_array.py:396-405, 520-540; calculators/
+//                           classical.py:58-101): stream compaction of the
+//                           rates into (sid, lid, gid, rate) records
 #pragma once
 #include <math.h>
 #include "../../include/oqg.h"
@@ -683,6 +687,76 @@ __global__ void k_hazard_maps(const float *__restrict__ curves, int64_t K,
 #undef LC
 #undef LI
   out[e] = (float)res;
+}
+
+
+// ---- rates map -> records (sid, lid, gid, rate) ------------------------------
+// MapArray.to_array (map_array.py:396-405 with to_rates :520-540): for every
+// gsim column g, site s and level l with rate > 0 one record of rates_dt
+// (u4 sid, u2 lid, u2 gid, f4 rate: 12 bytes), ordered by (g, s, l); _store
+// (calculators/classical.py:58-101) then regroups them by chunk = sid %
+// num_chunks (gen_chunks, map_array.py:49-64) keeping that order inside a
+// chunk.  Here a "row" is one (g, s) curve of L levels; the host passes the
+// rows in output order (by chunk, then g, then s), one warp counts / writes
+// one row with ballots, and an exclusive scan of the counts (CUB) gives the
+// offsets: the records come out in the reference's order.
+struct RateRecord {
+  uint32_t sid;
+  uint16_t lid, gid;
+  float rate;
+};
+static_assert(sizeof(RateRecord) == 12, "rates_dt is 12 bytes");
+
+__global__ void __launch_bounds__(128)
+k_rate_rows_count(const float *__restrict__ rates, int N, int L, int G,
+                  const int64_t *__restrict__ rows, int64_t R,
+                  int64_t *__restrict__ counts) {
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int64_t row = rows ? rows[r] : r;       // g * N + s
+  const int g = (int)(row / N);
+  const int64_t sx = row - (int64_t)g * N;
+  const float *c = rates + (sx * L) * G + g;
+  int n = 0;
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const bool ok = l < L && c[(int64_t)l * G] > 0.f;
+    n += __popc(__ballot_sync(0xffffffffu, ok));
+  }
+  if (lane == 0) counts[r] = n;
+}
+
+__global__ void __launch_bounds__(128)
+k_rate_rows_write(const float *__restrict__ rates, int N, int L, int G,
+                  const uint32_t *__restrict__ sids,
+                  const int32_t *__restrict__ gid, int level0,
+                  const int64_t *__restrict__ rows, int64_t R,
+                  const int64_t *__restrict__ offsets,
+                  RateRecord *__restrict__ out) {
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int64_t row = rows ? rows[r] : r;
+  const int g = (int)(row / N);
+  const int64_t sx = row - (int64_t)g * N;
+  const float *c = rates + (sx * L) * G + g;
+  int64_t at = offsets[r];
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const float v = l < L ? c[(int64_t)l * G] : 0.f;
+    const bool ok = v > 0.f;
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      RateRecord rec;
+      rec.sid = sids ? sids[sx] : (uint32_t)sx;
+      rec.lid = (uint16_t)(level0 + l);
+      rec.gid = (uint16_t)gid[g];
+      rec.rate = v;
+      out[at + __popc(b & ((1u << lane) - 1u))] = rec;
+    }
+    at += __popc(b);
+  }
 }
 
 }  // namespace oqg

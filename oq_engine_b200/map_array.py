@@ -82,6 +82,12 @@ class MapArray(object):
         new.rates = True
         return new
 
+    def to_array(self, gid):
+        """map_array.py:396-405: the rates > 0 as records (sid, lid, gid,
+        rate), ordered by gsim column, site and level (device compaction)"""
+        from .postproc import rates_to_records
+        return rates_to_records(self, gid)[0]
+
     def __invert__(self):
         return self.new(1. - self.array)
 

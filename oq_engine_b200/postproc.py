@@ -202,3 +202,69 @@ def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
                    _ptr(t_p), _ptr(t_o))
             out['hmaps-' + kind] = maps(t_o, P)
     return out
+
+
+rates_dt = numpy.dtype([('sid', numpy.uint32), ('lid', numpy.uint16),
+                        ('gid', numpy.uint16), ('rate', numpy.float32)])
+slice_dt = numpy.dtype([('idx', numpy.uint32), ('start', int), ('stop', int)])
+
+
+def rates_to_records(rmap, gid=None, num_chunks=1, level0=0, device=None):
+    """
+    The compaction of a rates map into the `_rates` records the reference
+    stores: MapArray.to_array (hazardlib/map_array.py:396-405, to_rates
+    :520-540) followed by the chunk grouping of `_store`
+    (calculators/classical.py:58-101, gen_chunks map_array.py:49-64), as one
+    device stream compaction (oqg_rates_to_records).
+
+    :param rmap: a rates MapArray (N, L, G) (host or device resident)
+    :param gid: the G gsim IDs of the columns (default: rmap.gid or 0..G-1)
+    :param num_chunks: the records are grouped by chunk = sid % num_chunks
+    :returns: (records, slice_by_idx): a structured array of rates_dt with
+        the elements of rate > 0 ordered by (chunk, gsim column, site,
+        level), and an array of (idx, start, stop) with the slice of every
+        chunk that has records of sites in it
+    """
+    import torch
+    from .contexts import _dev, _ptr
+    assert rmap.rates, 'a map of rates is needed'
+    h = _handle(device if device is not None else rmap.device)
+    dev = h.device
+    N, L, G = rmap.shape
+    if gid is None:
+        gid = getattr(rmap, 'gid', None)
+    gid = numpy.arange(G) if gid is None else numpy.asarray(gid)
+    assert len(gid) == G, (len(gid), G)
+    sids = numpy.asarray(rmap.sids, numpy.uint32)
+    chunk = sids % num_chunks if num_chunks > 1 else numpy.zeros(N, int)
+    # rows g * N + s in output order: by chunk, then column, then site
+    ch = numpy.repeat(chunk[None, :], G, axis=0).ravel()      # (G * N,)
+    rows = numpy.argsort(ch, kind='stable').astype(numpy.int64)
+    t_rates = _dev(rmap.array, dev, torch.float32)
+    t_sids, t_gid = _dev(sids, dev), _dev(gid.astype(numpy.int32), dev)
+    t_rows = _dev(rows, dev)
+    total = ctypes.c_int64(0)
+    R = len(rows)
+    if R == 0:
+        return numpy.zeros(0, rates_dt), numpy.zeros(0, slice_dt)
+    # counting pass, then the records in a buffer of the exact size
+    h.call('oqg_rates_to_records', _ptr(t_rates), N, L, G, _ptr(t_sids),
+           _ptr(t_gid), int(level0), _ptr(t_rows), R, None, 0,
+           ctypes.byref(total))
+    n = total.value
+    out = torch.empty((max(n, 1), 12), dtype=torch.uint8,
+                      device='cuda:%d' % dev)
+    h.call('oqg_rates_to_records', _ptr(t_rates), N, L, G, _ptr(t_sids),
+           _ptr(t_gid), int(level0), _ptr(t_rows), R, _ptr(out), n,
+           ctypes.byref(total))
+    torch.cuda.current_stream(dev).synchronize()
+    recs = out[:n].cpu().numpy().reshape(-1).view(rates_dt)
+    # slices of the chunks: the records are sorted by chunk
+    rch = recs['sid'] % num_chunks if num_chunks > 1 else numpy.zeros(
+        n, numpy.uint32)
+    idx = numpy.unique(chunk)
+    start = numpy.searchsorted(rch, idx, 'left')
+    stop = numpy.searchsorted(rch, idx, 'right')
+    slices = numpy.zeros(len(idx), slice_dt)
+    slices['idx'], slices['start'], slices['stop'] = idx, start, stop
+    return recs, slices

@@ -20,8 +20,8 @@ def line_table(func_substr):
     tmp = tempfile.mkdtemp()
     # the library the report was taken with: OQG_LIB or the in-tree build
     subprocess.run(['cuobjdump', '-xelf', 'all',
-                    os.environ.get('OQG_LIB') or
-                    os.path.join(ROOT, 'oq_engine_b200', 'liboqg.so')],
+                    os.path.abspath(os.environ.get('OQG_LIB') or os.path.join(
+                        ROOT, 'oq_engine_b200', 'liboqg.so'))],
                    cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
     out = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)],
