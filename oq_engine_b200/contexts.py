@@ -496,10 +496,23 @@ class ContextMaker(object):
                 'only planar ruptures (PlanarRuptures, PointSource) and mesh '
                 'ruptures (fault.MeshRuptures, fault.SimpleFaultSource) have '
                 'a device path')
+        return list(self._gen_ctxs_planar(src, sitecol, src_id, step, vis))
+
+    # distance planes pulled to the host per block of ruptures of get_ctxs
+    GET_CTXS_BYTES = 256 << 20
+
+    def _gen_ctxs_planar(self, src, sitecol, src_id, step, vis):
+        """Generator behind get_ctxs / get_ctx_iter for planar ruptures: one
+        magnitude at a time -- the distances of the ruptures of that
+        magnitude only are computed on the device and copied to the host,
+        in blocks of at most GET_CTXS_BYTES -- so that the memory does not
+        grow with the size of the source (the reference generates per
+        magnitude too, genctxs_Pp contexts.py:443-474)"""
+        import torch
         h = self.handle()
         U, N = len(src), len(sitecol)
         if U == 0 or N == 0:
-            return []
+            return
         # contexts.py:1064: few sites -> closest points in the rows
         self.fewsites = N <= self.max_sites_disagg
         dists = sorted(self.REQUIRES_DISTANCES | {'rrup'} |
@@ -509,65 +522,86 @@ class ContextMaker(object):
             mask |= 1 << _lib.DIST.index(d)
         order = [d for d in _lib.DIST if d in dists]
         dev = h.device
-        t_pla = _dev(as_flat(src.planar), dev)
         st, keep = self._sites_struct(sitecol, dev)
-        out = torch.empty((len(order), U, N), dtype=torch.float64,
-                          device='cuda:%d' % dev)
-        h.call('oqg_distances', _ptr(t_pla), U, ctypes.byref(st), N, mask,
-               _ptr(out))
-        dd = dict(zip(order, out.cpu().numpy()))
         tom = self.tom
         K = 0
         probs = None
         if tom is not None and hasattr(tom, 'get_pmf'):
             probs = tom.get_pmf(src.rate)
             K = probs.shape[1]
-        ctxs = []
         mags = src.mag
+        flat = as_flat(src.planar)
+        per = max(1, self.GET_CTXS_BYTES // (len(order) * N * 8))
         for mag in numpy.unique(mags)[::step]:
-            idx = numpy.flatnonzero(mags == mag)
-            ctx = self.new_ctx(len(idx) * N, K).reshape(len(idx), N)
-            for name in dists:
-                arr = dd[name][idx]
-                if self.minimum_distance and name in self.REQUIRES_DISTANCES:
-                    arr = numpy.where(arr < self.minimum_distance,
-                                      self.minimum_distance, arr)
-                ctx[name] = arr
-            pla = src.planar[idx]
-            par = dict(mag=mags[idx], width=pla['wlr'][:, 0],
-                       dip=pla['sdr'][:, 1], rake=pla['sdr'][:, 2],
-                       strike=pla['sdr'][:, 0], ztor=pla['corners'][:, 2, 0],
-                       hypo_depth=pla['hypo'][:, 2])
-            for name in self.REQUIRES_RUPTURE_PARAMETERS:
-                ctx[name] = par[name][:, None]
-            for name in self.REQUIRES_SITES_PARAMETERS:
-                ctx[name] = sitecol.array[name][None, :]
-            ctx['occurrence_rate'] = pla['wlr'][:, 2][:, None]
-            ctx['rup_id'] = idx[:, None]
-            ctx['src_id'] = src_id
-            ctx['sids'] = sitecol.sids[None, :]
-            if K:
-                ctx['probs_occur'] = probs[idx][:, None, :]
-            if vis is not None and (vis[idx, 4] != 0).any():
-                # near sites see all the planes and depths (mode 1), far
-                # sites the average rupture (mode 2), contexts.py:347-370
-                aux = vis[idx]
-                d2 = ((sitecol.xyz[None, :, :] - aux[:, None, :3]) ** 2
-                      ).sum(axis=2)
-                close = d2 <= (aux[:, 3] ** 2)[:, None]
-                mode = aux[:, 4][:, None]
-                keep = numpy.where(mode == 1, close, numpy.where(
-                    mode == 2, ~close, mode == 0))
-                ctx = ctx[keep]
-            else:
-                ctx = ctx.flatten()
-            ctx = ctx[ctx['rrup'] < self.maximum_distance(mag)]
-            if len(ctx):
-                ctxs.append(ctx.view(numpy.recarray))
-        return ctxs
+            allidx = numpy.flatnonzero(mags == mag)
+            parts = []
+            for b0 in range(0, len(allidx), per):
+                idx = allidx[b0:b0 + per]
+                t_pla = _dev(flat[idx], dev)
+                out = torch.empty((len(order), len(idx), N),
+                                  dtype=torch.float64, device='cuda:%d' % dev)
+                h.call('oqg_distances', _ptr(t_pla), len(idx),
+                       ctypes.byref(st), N, mask, _ptr(out))
+                dd = dict(zip(order, out.cpu().numpy()))
+                ctx = self.new_ctx(len(idx) * N, K).reshape(len(idx), N)
+                for name in dists:
+                    arr = dd[name]
+                    if self.minimum_distance and \
+                            name in self.REQUIRES_DISTANCES:
+                        arr = numpy.where(arr < self.minimum_distance,
+                                          self.minimum_distance, arr)
+                    ctx[name] = arr
+                pla = src.planar[idx]
+                par = dict(mag=mags[idx], width=pla['wlr'][:, 0],
+                           dip=pla['sdr'][:, 1], rake=pla['sdr'][:, 2],
+                           strike=pla['sdr'][:, 0],
+                           ztor=pla['corners'][:, 2, 0],
+                           hypo_depth=pla['hypo'][:, 2])
+                for name in self.REQUIRES_RUPTURE_PARAMETERS:
+                    ctx[name] = par[name][:, None]
+                for name in self.REQUIRES_SITES_PARAMETERS:
+                    ctx[name] = sitecol.array[name][None, :]
+                ctx['occurrence_rate'] = pla['wlr'][:, 2][:, None]
+                ctx['rup_id'] = idx[:, None]
+                ctx['src_id'] = src_id
+                ctx['sids'] = sitecol.sids[None, :]
+                if K:
+                    ctx['probs_occur'] = probs[idx][:, None, :]
+                if vis is not None and (vis[idx, 4] != 0).any():
+                    # near sites see all the planes and depths (mode 1), far
+                    # sites the average rupture (mode 2), contexts.py:347-370
+                    aux = vis[idx]
+                    d2 = ((sitecol.xyz[None, :, :] - aux[:, None, :3]) ** 2
+                          ).sum(axis=2)
+                    close = d2 <= (aux[:, 3] ** 2)[:, None]
+                    mode = aux[:, 4][:, None]
+                    keepm = numpy.where(mode == 1, close, numpy.where(
+                        mode == 2, ~close, mode == 0))
+                    ctx = ctx[keepm]
+                else:
+                    ctx = ctx.flatten()
+                ctx = ctx[ctx['rrup'] < self.maximum_distance(mag)]
+                if len(ctx):
+                    parts.append(ctx)
+            if parts:
+                yield (parts[0] if len(parts) == 1 else
+                       numpy.concatenate(parts)).view(numpy.recarray)
+        del keep
 
-    # the name BASELINE.json's north_star uses for the same operator
-    get_ctx_iter = get_ctxs
+    def get_ctx_iter(self, src, sitecol, src_id=0, step=1):
+        """The name BASELINE.json's north_star uses for get_ctxs: the same
+        contexts, generated lazily (one magnitude of a planar source in
+        memory at a time)"""
+        from .source import PointSource
+        from . import fault
+        if isinstance(src, (fault.SimpleFaultSource, fault.MeshRuptures)):
+            return iter(self.get_ctxs(src, sitecol, src_id, step))
+        vis = None
+        if isinstance(src, PointSource):
+            src, vis = self._planar_of_point_source(src, sitecol, src_id)
+        if not isinstance(src, PlanarRuptures):
+            raise NotImplementedError(type(src).__name__)
+        return self._gen_ctxs_planar(src, sitecol, src_id, step, vis)
 
     def _planar_of_point_source(self, src, sitecol, src_id=0):
         """PlanarRuptures of a PointSource built on the device and the
@@ -642,11 +676,20 @@ class ContextMaker(object):
         h.call('oqg_poes', _ptr(ms), n, _ptr(poes))
         return poes, ms
 
+    # rows per block of gen_poes: the (n, L, G) PoEs of a block are at most
+    # this many bytes as float32 on the device (and twice that as the float64
+    # array the caller gets)
+    GEN_POES_BYTES = 32 << 20
+
     def gen_poes(self, ctx):
         """
         :yields: poes (n, L, G) float64, mea, sig, tau (G, M, n) and the
-            context rows, one block per unique magnitude rounded to 3 digits
-            in increasing order (contexts.py:1190-1203)
+            context rows: one or more blocks per unique magnitude (rounded to
+            3 digits, in increasing order).  Like the reference, which cuts
+            every magnitude into slabs so that `poes` stays small
+            (contexts.py:1155-1203, split_in_slices), a block never holds
+            more than GEN_POES_BYTES of PoEs, whatever the size of `ctx`:
+            mean / stds and PoEs are computed block by block on the device.
         """
         h = self.handle()
         ctx.mag = numpy.round(ctx.mag, 3)
@@ -654,15 +697,18 @@ class ContextMaker(object):
         sctx = ctx[order]
         if len(sctx) == 0:
             return
-        poes, ms = self._device_poes(h, sctx)
-        poes = poes.cpu().numpy().astype(numpy.float64)
-        ms = ms.cpu().numpy()
         mags, starts = numpy.unique(sctx.mag, return_index=True)
         stops = list(starts[1:]) + [len(sctx)]
         self.cfactor += [len(sctx), len(mags)]
+        rows = max(1, self.GEN_POES_BYTES // (self.L * self.G * 4))
         for a, b in zip(starts, stops):
-            yield (poes[a:b], ms[0, :, :, a:b], ms[1, :, :, a:b],
-                   ms[2, :, :, a:b], sctx[a:b])
+            for c in range(a, b, rows):
+                d = min(b, c + rows)
+                blk = sctx[c:d]
+                poes, ms = self._device_poes(h, blk)
+                ms = ms.cpu().numpy()
+                yield (poes.cpu().numpy().astype(numpy.float64), ms[0], ms[1],
+                       ms[2], blk)
 
     # ---------------------------------------------------------------- map
     def update(self, pmap, ctx, rup_mutex=None):

@@ -229,6 +229,11 @@ def test_pipeline_unfused_golden(oq, tag):
     ctx = cm.recarray(cm.get_ctxs(src, sc))
     ref = to_recarray(ctx_of(d))
     assert len(ctx) == len(ref)
+    # the lazy form with a small host budget: the same rows, block by block
+    cm.GET_CTXS_BYTES = 4 * len(sc) * 8 * 5
+    lazy = cm.recarray(list(cm.get_ctx_iter(src, sc)))
+    del cm.GET_CTXS_BYTES
+    assert lazy.tobytes() == ctx.tobytes()
     # same order: by magnitude, then rupture, then site
     np.testing.assert_array_equal(ctx.sids, ref.sids)
     for name in ctx.dtype.names:
@@ -246,6 +251,16 @@ def test_pipeline_unfused_golden(oq, tag):
     big = exp > 1e-8
     np.testing.assert_allclose(poes[big], exp[big], rtol=1e-5)
     assert np.abs(poes - exp).max() < 1e-7
+    # gen_poes never holds more than GEN_POES_BYTES of PoEs: with a small
+    # budget the same rows come in more, smaller blocks of one magnitude
+    cm.GEN_POES_BYTES = 40 * cm.L * cm.G * 4
+    blocks = list(cm.gen_poes(ref.copy().view(np.recarray)))
+    assert max(len(b[0]) for b in blocks) <= 40
+    assert all(len(np.unique(b[4].mag)) == 1 for b in blocks)
+    assert all(b[1].shape == (cm.G, cm.M, len(b[0])) for b in blocks)
+    np.testing.assert_array_equal(np.concatenate([b[0] for b in blocks]),
+                                  poes)
+    del cm.GEN_POES_BYTES
     # maps
     N, L, G = d['pmap'].shape
     pmap = oq.MapArray(sc.sids, L, G).fill(1)

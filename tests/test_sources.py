@@ -395,7 +395,7 @@ def test_get_ctxs_of_point_sources(oq, tag):
              pointsource_distance=float(PSD['psdist'])))
     ctxs = []
     for i, src in enumerate(psd_sources(oq)):
-        got = cm.get_ctx_iter(src, sc, src_id=i)
+        got = list(cm.get_ctx_iter(src, sc, src_id=i))   # a generator
         assert all(len(np.unique(c.mag)) == 1 for c in got)
         ctxs.extend(got)
     ctx = cm.recarray(ctxs)
