@@ -146,6 +146,58 @@ def cpu_pass(pairs, r, sites, imtls, cores, pool):
     return sum(x[0] for x in res), dt
 
 
+def _ref_worker(args):
+    # the REAL reference (baseline/_ref), loaded and JIT-compiled in the
+    # parent before the fork
+    (names, imtls, planar, mags, sites, idx) = args
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_runner
+    sub = {k: v[idx] for k, v in sites.items()}
+    rows, dt, arr = ref_runner.hazard_pass(names, imtls, planar, mags, sub)
+    return rows, dt, float(arr.sum())
+
+
+def reference_baseline(workload, U_sample, N, steps, warmup, seed=20240):
+    """The unmodified reference (openquake.hazardlib from baseline/_ref) on
+    the first U_sample ruptures of the workload x all the sites: its own
+    get_ctx + ContextMaker.update, site tiles (sids % cores, the reference's
+    tiling rule) over one process per host core.  Returns evals/s, cores,
+    seconds per step, evaluations per step."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_runner
+    _, _, names = WORKLOADS[workload]
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    r, sites = synth(U_sample, N, seed)
+    planar = ref_runner.build_planar(r)          # untimed, as on the GPU arm
+    cores = os.cpu_count() or 1
+    tiles = [np.flatnonzero(sites['sids'] % cores == k) for k in range(cores)]
+    tiles = [t for t in tiles if len(t)]
+    # JIT-compile everything in this process; the workers are forked from it
+    ref_runner.hazard_pass(names, imtls, planar[:2], r['mag'][:2],
+                           {k: v[tiles[0][:8]] for k, v in sites.items()})
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        jobs = [(names, imtls, planar, r['mag'], sites, t) for t in tiles]
+        for _ in range(warmup):
+            pool.map(_ref_worker, [(names, imtls, planar[:2], r['mag'][:2],
+                                    sites, t[:8]) for t in tiles])
+        times, rows = [], 0
+        for _ in range(steps):
+            t0 = time.time()
+            res = pool.map(_ref_worker, jobs)
+            times.append(time.time() - t0)
+            rows = sum(x[0] for x in res)
+    evals = rows * len(IMTS) * 20 * len(names)
+    dt = sum(times) / len(times)
+    return evals / dt, cores, dt, evals
+
+
+def have_reference():
+    return os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'openquake',
+                                      'hazardlib'))
+
+
 def cpu_baseline(workload, U_sample, N, steps, warmup, seed=20240):
     import multiprocessing as mp
     _, _, names = WORKLOADS[workload]
@@ -174,12 +226,20 @@ def run_reference(args):
     U, N, names = WORKLOADS[args.workload]
     N = args.sites or N
     U_sample = args.cpu_ruptures
-    value, cores, dt, evals = cpu_baseline(args.workload, U_sample, N,
-                                           args.steps, min(args.warmup, 1))
+    if have_reference() and not args.port:
+        kind = 'reference'
+        value, cores, dt, evals = reference_baseline(
+            args.workload, U_sample, N, args.steps, min(args.warmup, 1))
+        what = ('the unmodified reference (openquake.hazardlib 3.27 from '
+                'baseline/_ref): _get_ctx_planar + ContextMaker.update')
+    else:
+        kind = 'port'
+        value, cores, dt, evals = cpu_baseline(
+            args.workload, U_sample, N, args.steps, min(args.warmup, 1))
+        what = 'numpy restatement of get_ctxs + update (oracle/)'
     sample = ('first %d of %d ruptures x %d sites (%.3g evals per step), '
-              'numpy restatement of get_ctxs + update, site tiles '
-              '(sids %% %d) over %d processes'
-              % (U_sample, args.ruptures or U, N, evals, cores, cores))
+              '%s, site tiles (sids %% %d) over %d processes'
+              % (U_sample, args.ruptures or U, N, evals, what, cores, cores))
     print(json.dumps({
         'impl': 'reference', 'metric': 'PoE evaluations per second',
         'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus,
@@ -190,7 +250,7 @@ def run_reference(args):
         'config': {'workload': workload_name(args), 'gsims': names,
                    'imts': len(IMTS), 'levels': 20},
         'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores,
-                         'kind': 'port', 'sample': sample},
+                         'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }))
@@ -669,9 +729,15 @@ def run_ours(args):
     # ---- CPU baseline on a bounded sample, rank 0 only
     cpu = None
     if not args.no_cpu and world == 1:      # rank 0 at N = 1 only
-        v, cores, dt, ev = cpu_baseline(args.workload, args.cpu_ruptures, N,
-                                        1, 1)
-        cpu = {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
+        if have_reference() and not args.port:
+            v, cores, dt, ev = reference_baseline(
+                args.workload, args.cpu_ruptures, N, 1, 1)
+            kind = 'reference'
+        else:
+            v, cores, dt, ev = cpu_baseline(args.workload, args.cpu_ruptures,
+                                            N, 1, 1)
+            kind = 'port'
+        cpu = {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': kind,
                'sample': 'first %d ruptures x %d sites (%.3g evals, %.1f s)'
                % (args.cpu_ruptures, N, ev, dt)}
     print(json.dumps({
@@ -717,6 +783,9 @@ def main():
     ap.add_argument('--cpu-ruptures', type=int, default=768,
                     help='ruptures of the bounded CPU sample (x all sites)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--port', action='store_true',
+                    help='CPU arm: the numpy port of oracle/ even when the '
+                         'reference is installed under baseline/_ref')
     ap.add_argument('--no-strong', action='store_true',
                     help='skip the strong-scaling legs')
     ap.add_argument('--strong-steps', type=int, default=2)

@@ -115,9 +115,12 @@ def gather_tiles(tile_array, tile_sids, sids, group=None, partial=False):
         dist.all_gather_into_tensor(tiles, pad, group=group)
         dist.all_gather_into_tensor(allrows, prow, group=group)
     out = torch.zeros((N + 1,) + shape, dtype=tile_array.dtype, device=dev)
-    out.index_copy_(0, allrows, tiles)
+    out[allrows] = tiles    # (index_copy_ took 60 ms for 179 MB on B200)
     if not partial:
-        seen = torch.bincount(allrows, minlength=N + 1)[:N]
+        seen = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+        seen.index_add_(0, allrows, torch.ones_like(allrows,
+                                                   dtype=torch.int32))
+        seen = seen[:N]
         if not bool((seen == 1).all()):
             raise ValueError('gather_tiles: %d sites have no owner and %d '
                              'have several' % (int((seen == 0).sum()),

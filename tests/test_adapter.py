@@ -284,3 +284,29 @@ def test_horizontal_component_conversion_replay():
         h.call('oqg_hazard_planar', None, None, None, None, 0, 1,
                ctypes.byref(_lib.OqgSites()), None, 1, 0., 1., 0, None, None)
     h.close()
+
+
+def test_reference_arm_runs_the_installed_reference():
+    """bench.py --impl reference: the unmodified reference from baseline/_ref
+    (oracle/ref_runner.py) gives the map of the oracle on the same inputs"""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_runner
+    if not ref_runner.available():
+        pytest.skip('the reference is not installed under baseline/_ref')
+    import hazard_np
+    import geo_np
+    from helpers import synth_ruptures, synth_sites, IMTS
+    rng = np.random.default_rng(3)
+    r, sites = synth_ruptures(24, rng), synth_sites(40, rng)
+    imtls = {imt: np.logspace(-2, 0.3, 20) for imt in IMTS}
+    names = ['BooreEtAl2014', 'ChiouYoungs2014']
+    pla = ref_runner.build_planar(r)
+    rows, dt, arr = ref_runner.hazard_pass(names, imtls, pla, r['mag'], sites)
+    assert rows == 24 * 40 and arr.shape == (40, 140, 2)
+    pairs = [(n, {}) for n in names]
+    args = (r['mag'], r['strike'], r['dip'], r['rake'], r['rate'], r['area'],
+            r['hypo_lon'], r['hypo_lat'], r['hypo_dep'], 0., 25., 1.5)
+    octx = hazard_np.get_ctx(pairs, geo_np.build_planar(*args), r['mag'],
+                             sites, None, 0)
+    acc = hazard_np.exact_rate_sum(pairs, octx, sites['sids'], imtls, 3., 50.)
+    np.testing.assert_allclose(arr, np.exp(-acc), rtol=2e-5, atol=1e-7)
