@@ -335,23 +335,32 @@ def strong_legs(args, oq, rank, world, local, timed_max):
     st, keep = cm._sites_struct(tile, local)
     t_map = torch.ones((n_k, L, G), dtype=torch.float32, device=dev)
     t_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
-    ev = []
+    ev, ev_wait = [], []
     whole = [None]
+    sync_token = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def step_sites():
         t_map.fill_(1.)
         h.call('oqg_hazard_planar', _ptr(inp[0]), _ptr(inp[1]), _ptr(inp[2]),
                None, 0, U, ctypes.byref(st), None, n_k, 0., 50., 0,
                _ptr(t_map), _ptr(t_cnt))
+        # the ranks meet first (a 4-byte all-reduce on the stream), so that
+        # the events time the exchange and not the wait for the slowest rank
+        w0 = torch.cuda.Event(True)
+        w0.record()
+        if world > 1:
+            dist.all_reduce(sync_token)
         a, b = torch.cuda.Event(True), torch.cuda.Event(True)
         a.record()
         whole[0] = oq.sharding.gather_tiles(t_map, tile.sids, N)
         b.record()
         ev.append((a, b))
+        ev_wait.append((w0, a))
 
     for _ in range(warm):
         step_sites()
     ev.clear()
+    ev_wait.clear()
     t_cnt.zero_()
     ms = timed_max(step_sites, steps)
     pairs = torch.tensor([float(t_cnt[0].item()) / steps],
@@ -360,6 +369,7 @@ def strong_legs(args, oq, rank, world, local, timed_max):
         dist.all_reduce(pairs)
     evals = float(pairs.item()) * L * G
     gather_ms = allmax(sum(_events_ms(ev)) / steps)
+    wait_sites_ms = allmax(sum(_events_ms(ev_wait)) / steps)
     # parity spot check: the first sites of the gathered map against a
     # single-rank pass over exactly those sites
     nchk = min(256, N)
@@ -373,6 +383,7 @@ def strong_legs(args, oq, rank, world, local, timed_max):
     out['strong_sites'] = {
         'value': evals / (ms / steps * 1e-3), 'unit': 'evals/s',
         'ms_per_step': ms / steps, 'gather_ms': gather_ms,
+        'wait_for_slowest_rank_ms': wait_sites_ms,
         'gather_bytes': N * L * G * 4, 'steps': steps,
         'workload': 'cfg4 models, %d ruptures x %d sites in total, sites '
                     'split by sids %% %d, tiles all-gathered into the whole '
@@ -396,7 +407,7 @@ def strong_legs(args, oq, rank, world, local, timed_max):
     st, keep = cm._sites_struct(sc, local)
     t_map = torch.ones((N, L, G), dtype=torch.float32, device=dev)
     t_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
-    ev = []
+    ev, ev_wait = [], []
 
     def step_groups():
         t_map.fill_(1.)
@@ -404,15 +415,21 @@ def strong_legs(args, oq, rank, world, local, timed_max):
             h.call('oqg_hazard_planar', _ptr(a), _ptr(b), _ptr(c), None, 0, U,
                    ctypes.byref(st), None, N, 0., 50., 0, _ptr(t_map),
                    _ptr(t_cnt))
+        w0 = torch.cuda.Event(True)
+        w0.record()
+        if world > 1:
+            dist.all_reduce(sync_token)     # meet first, see step_sites
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
         oq.sharding.combine_maps(t_map, rates=False)
         e1.record()
         ev.append((e0, e1))
+        ev_wait.append((w0, e0))
 
     for _ in range(warm):
         step_groups()
     ev.clear()
+    ev_wait.clear()
     t_cnt.zero_()
     ms = timed_max(step_groups, steps)
     pairs = torch.tensor([float(t_cnt[0].item()) / steps],
@@ -421,6 +438,7 @@ def strong_legs(args, oq, rank, world, local, timed_max):
         dist.all_reduce(pairs)
     evals = float(pairs.item()) * L * G
     ar_ms = allmax(sum(_events_ms(ev)) / steps)
+    wait_groups_ms = allmax(sum(_events_ms(ev_wait)) / steps)
     nbytes = N * L * G * 4
     bus = (2. * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9
            if world > 1 and ar_ms > 0 else None)
@@ -439,6 +457,7 @@ def strong_legs(args, oq, rank, world, local, timed_max):
     out['strong_groups'] = {
         'value': evals / (ms / steps * 1e-3), 'unit': 'evals/s',
         'ms_per_step': ms / steps, 'allreduce_ms': ar_ms,
+        'wait_for_slowest_rank_ms': wait_groups_ms,
         'allreduce_bytes': nbytes, 'allreduce_bus_gbs': bus,
         'allreduce_bus_reference_gbs': 725.0, 'steps': steps,
         'workload': 'cfg5 shape: %d source groups x %d ruptures x %d sites, '
