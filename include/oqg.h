@@ -353,6 +353,34 @@ int oqg_mesh_rjb(oqg_handle *h, const double *lon_dev, const double *lat_dev,
                  const int32_t *owner_dev, const double *frame_dev, int S,
                  const oqg_sites *sites, int N, double *out_dev);
 
+/* Multi-fault ruptures: the `dparam` cache of ContextMaker
+ * (hazardlib/contexts.py:1039-1049, calc/filters.py:51-71).
+ *
+ * oqg_line_tuw: Line.get_tuw (hazardlib/geo/line.py:178-266), the GC2
+ * coordinates of N sites for S2 oriented top-of-rupture lines: seg_dev
+ * [T][7] = projected start (x, y), length, uhat (2), that (2) of every
+ * segment (Line.sut_hat :543-565), loff_dev [S2 + 1] the segments of each
+ * line, proj_dev [S2][2] = lam0, phi0 of its orthographic projection ->
+ * out_dev [S2][N][3] float32 = t, u, sum of the weights.
+ *
+ * oqg_multi_compose: genctxs with the cache (contexts.py:959-1029, _get_tu
+ * :85-98, set_distances :113-135, multiline.get_tu geo/multiline.py:246-261):
+ * from the section planes sec_rrup_dev / sec_rjb_dev [S][N] and tuw_dev
+ * [S][2][N][3] (orientation 0 as given, 1 flipped) the planes [U][N] of U
+ * ruptures: rrup / rjb = minimum over the sections, rx = T, ry0 = |U| below
+ * 0, U - u_max above u_max, else 0.  roff_dev [U + 1]; rsec_dev, rflip_dev,
+ * rshift_dev per (rupture, section) in the order of the rupture's MultiLine;
+ * umax_dev [U].  Output pointers may be NULL. */
+int oqg_line_tuw(oqg_handle *h, const double *seg_dev, const int64_t *loff_dev,
+                 const double *proj_dev, int S2, const oqg_sites *sites_dev,
+                 int N, float *out_dev);
+int oqg_multi_compose(oqg_handle *h, const double *sec_rrup_dev,
+                      const double *sec_rjb_dev, const float *tuw_dev, int S,
+                      int N, const int64_t *roff_dev, const int32_t *rsec_dev,
+                      const uint8_t *rflip_dev, const float *rshift_dev,
+                      const float *umax_dev, int U, double *rrup_dev,
+                      double *rjb_dev, double *rx_dev, double *ry0_dev);
+
 /* Mean dip, strike and width of S rectangular meshes:
  * RectangularMesh.get_mean_inclination_and_azimuth (hazardlib/geo/mesh.py:
  * 728-783) and get_mean_width (mesh.py:861-885), the surface.get_dip() /

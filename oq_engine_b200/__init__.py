@@ -27,6 +27,7 @@ from .rmap_maker import RmapMaker, SourceGroup  # noqa
 from .mesh import (Mesh, mesh_min_distance, section_min,  # noqa
                    mesh_rx_ry0, mesh_dip_strike_width, mesh_rjb)
 from .fault import MeshRuptures, SimpleFaultSource  # noqa
+from .multifault import MultiFaultRuptures  # noqa
 from .disagg import (disaggregate, Disaggregator, FarAwayRupture,  # noqa
                      disaggregation, build_bin_edges, lon_lat_bins)
 from .cond_spectra import (  # noqa

@@ -118,6 +118,11 @@ def lib():
         'oqg_mesh_rjb': (C.c_int, [
             H, c_void, c_void, C.c_int64, c_void, c_void, c_void, c_void,
             C.c_int, C.POINTER(OqgSites), C.c_int, c_void]),
+        'oqg_line_tuw': (C.c_int, [H, c_void, c_void, c_void, C.c_int,
+                                   C.POINTER(OqgSites), C.c_int, c_void]),
+        'oqg_multi_compose': (C.c_int, [
+            H, c_void, c_void, c_void, C.c_int, C.c_int, c_void, c_void,
+            c_void, c_void, c_void, C.c_int, c_void, c_void, c_void, c_void]),
         'oqg_mesh_dip_strike_width': (C.c_int, [
             H, c_void, c_void, c_void, c_void, c_void, C.c_int, c_void]),
         'oqg_section_min': (C.c_int, [H, c_void, C.c_int, C.c_int, c_void,

@@ -484,7 +484,8 @@ class ContextMaker(object):
         if isinstance(src, fault.SimpleFaultSource):
             src_id = src.id if src_id == 0 else src_id
             src = src.ruptures()
-        if isinstance(src, fault.MeshRuptures):
+        from .multifault import MultiFaultRuptures
+        if isinstance(src, (fault.MeshRuptures, MultiFaultRuptures)):
             # non-planar ruptures: genctxs (contexts.py:959-1029), one
             # context per rupture
             return fault.get_ctxs_mesh(self, src, sitecol, src_id, step)

@@ -732,4 +732,118 @@ k_mesh_dip_strike_width(const double *__restrict__ lon,
   }
 }
 
+
+// ---- GC2 coordinates of multi-fault ruptures --------------------------------
+// Line.get_tuw (geo/line.py:178-266: get_ui_ti, get_ti_weights, line_get_tu)
+// for S2 oriented lines (every section's top-of-rupture line and its flip)
+// and N sites: out [S2][N][3] float32 = t, u and the sum of the segment
+// weights, as get_dparam(sec, sites, 'tuw') stores them (calc/filters.py:
+// 54-59).  seg [T][7] = projected start (x, y) of each segment, its length,
+// uhat (2), that (2); loff [S2 + 1] the segments of each line; proj [S2][2] =
+// lam0, phi0 of the line's orthographic projection.  One thread per (line,
+// site); the arithmetic is float64 like the reference's, the result float32.
+#define GC2_TOL 0.1    // geo/line.py:26
+__global__ void __launch_bounds__(128)
+k_line_tuw(const double *__restrict__ seg, const int64_t *__restrict__ loff,
+           const double *__restrict__ proj, int S2,
+           const double *__restrict__ slon, const double *__restrict__ slat,
+           int N, float *__restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (n >= N || s >= S2) return;
+  const double lam0 = proj[2 * s], phi0 = proj[2 * s + 1];
+  // project_direct (geo/utils.py:599-607)
+  const double lam = slon[n] * 0.017453292519943295 - lam0;
+  const double phi = slat[n] * 0.017453292519943295;
+  double sl, cl, sp, cp, sp0, cp0;
+  sincos(lam, &sl, &cl);
+  sincos(phi, &sp, &cp);
+  sincos(phi0, &sp0, &cp0);
+  const double sx = cp * sl * OQG_EARTH_RADIUS;
+  const double sy = (cp0 * sp - sp0 * cp * cl) * OQG_EARTH_RADIUS;
+  double wsum = 0., tacc = 0., uacc = 0., delta = 0.;
+  bool on_trace = false;
+  // two passes as the reference: the weights first (t = sum(ti w / wsum))
+  for (int pass = 0; pass < 2; pass++) {
+    delta = 0.;
+    for (int64_t k = loff[s]; k < loff[s + 1]; k++) {
+      const double *g = seg + k * 7;
+      const double dx = sx - g[0], dy = sy - g[1], len = g[2];
+      const double ui = dx * g[3] + dy * g[4];
+      const double ti = dx * g[5] + dy * g[6];
+      double w;
+      if (fabs(ti) >= GC2_TOL) {
+        w = (atan((len - ui) / ti) - atan(-ui / ti)) / ti;
+      } else if (ui < 0. - GC2_TOL || ui > len + GC2_TOL) {
+        w = 1. / (ui - len) - 1. / ui;       // on the extension of the segment
+      } else {
+        w = 1 / (-0.01 - len) + 1 / 0.01;    // on the segment
+        on_trace = true;
+      }
+      if (pass == 0) {
+        wsum += w;
+      } else {
+        tacc += ti * w / wsum;
+        uacc += (ui + delta) * w;
+      }
+      delta += len;
+    }
+  }
+  float *o = out + ((int64_t)s * N + n) * 3;
+  o[0] = on_trace ? 0.f : (float)tacc;
+  o[1] = (float)(uacc / wsum);
+  o[2] = (float)wsum;
+}
+
+// genctxs with the dparam cache (contexts.py:959-1029, _get_tu :85-98,
+// set_distances :113-135, multiline.get_tu geo/multiline.py:246-261): the
+// distances of U ruptures made of sections from the section planes.
+//   rrup, rjb [U][N] = minimum over the sections of the rupture
+//   rx = T, ry0 from U and u_max, T and U the weighted means of the
+//   sections' (t, u + shift) in the order of the rupture's MultiLine, taken
+//   from the orientation (flip) the MultiLine gives each section; the
+//   accumulation is float32 like the reference's
+// roff [U + 1], rsec / rflip / rshift per (rupture, section) in MultiLine
+// order; tuw [S][2][N][3] (orientation 0 = as given, 1 = flipped).
+__global__ void __launch_bounds__(128)
+k_multi_compose(const double *__restrict__ sec_rrup,
+                const double *__restrict__ sec_rjb,
+                const float *__restrict__ tuw, int N,
+                const int64_t *__restrict__ roff,
+                const int32_t *__restrict__ rsec,
+                const uint8_t *__restrict__ rflip,
+                const float *__restrict__ rshift,
+                const float *__restrict__ umax, int U,
+                double *__restrict__ rrup, double *__restrict__ rjb,
+                double *__restrict__ rx, double *__restrict__ ry0, int y0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int u = blockIdx.y + y0;
+  if (n >= N || u >= U) return;
+  double best = INFINITY, bestj = INFINITY;
+  float ts = 0.f, us = 0.f, ws = 0.f;
+  for (int64_t k = roff[u]; k < roff[u + 1]; k++) {
+    const int64_t s = rsec[k];
+    if (sec_rrup) best = fmin(best, sec_rrup[s * N + n]);
+    if (sec_rjb) bestj = fmin(bestj, sec_rjb[s * N + n]);
+    if (tuw) {
+      const float *t = tuw + ((s * 2 + (rflip[k] ? 1 : 0)) * N + n) * 3;
+      const float w = t[2];
+      ts += t[0] * w;
+      us += (t[1] + rshift[k]) * w;
+      ws += w;
+    }
+  }
+  const int64_t at = (int64_t)u * N + n;
+  if (rrup) rrup[at] = best;
+  if (rjb) rjb[at] = bestj;
+  if (tuw) {
+    const float tt = ts / ws, uu = us / ws;
+    if (rx) rx[at] = (double)tt;
+    if (ry0) {
+      const float um = umax[u];
+      ry0[at] = uu < 0.f ? (double)fabsf(uu) : (uu > um ? (double)(uu - um) : 0.);
+    }
+  }
+}
+
 }  // namespace oqg

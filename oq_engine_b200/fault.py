@@ -457,6 +457,13 @@ def rupture_planes(cmaker, rups, sitecol, names):
     return planes, par
 
 
+def _planes_of(cmaker, rups, sitecol, names):
+    if isinstance(rups, MeshRuptures):
+        return rupture_planes(cmaker, rups, sitecol, names)
+    from . import multifault          # ruptures made of sections
+    return multifault.rupture_planes(cmaker, rups, sitecol, names)
+
+
 # bytes of distance planes per chunk of ruptures (HBM is 180 GB; the planes
 # are scratch)
 PLANE_BYTES = 2 << 30
@@ -497,9 +504,10 @@ def hazard_mesh(cmaker, pmap, rups, sitecol, count=False):
     t_map = _dev(pmap.array, dev) if on_host else pmap.array
     t_cnt = torch.zeros(2, dtype=torch.int64, device='cuda:%d' % dev) \
         if count else None
-    for u0, u1 in _chunks(cmaker, U, N, len(names)):
+    multi = not isinstance(rups, MeshRuptures)     # MultiFaultRuptures
+    for u0, u1 in ([(0, U)] if multi else _chunks(cmaker, U, N, len(names))):
         r = _slice(rups, u0, u1) if (u0, u1) != (0, U) else rups
-        planes, par = rupture_planes(cmaker, r, sitecol, names)
+        planes, par = _planes_of(cmaker, r, sitecol, names)
         K, t_probs = 0, None
         if cmaker.cluster:
             if pmap.rates:
@@ -550,9 +558,10 @@ def get_ctxs_mesh(cmaker, rups, sitecol, src_id=0, step=1):
     order = ok[numpy.argsort(rups.mag[ok], kind='stable')][::step]
     ctxs = []
     tom = cmaker.tom
-    for u0, u1 in _chunks(cmaker, U, N, len(names)):
+    multi = not isinstance(rups, MeshRuptures)     # MultiFaultRuptures
+    for u0, u1 in ([(0, U)] if multi else _chunks(cmaker, U, N, len(names))):
         r = _slice(rups, u0, u1) if (u0, u1) != (0, U) else rups
-        planes, par = rupture_planes(cmaker, r, sitecol, names)
+        planes, par = _planes_of(cmaker, r, sitecol, names)
         host = {n: t.cpu().numpy() for n, t in planes.items()}
         probs = r.probs_occur
         if probs is None and tom is not None and hasattr(tom, 'get_pmf'):

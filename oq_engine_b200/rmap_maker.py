@@ -20,6 +20,7 @@ from .map_array import MapArray, F32
 from .tom import PoissonTOM
 from .contexts import PlanarRuptures
 from .fault import MeshRuptures, SimpleFaultSource
+from .multifault import MultiFaultRuptures
 from .source import PointSource, PointSourceBatch
 
 
@@ -89,7 +90,8 @@ class RmapMaker(object):
         for s in srcs:
             if isinstance(s, PlanarRuptures):
                 kept += cm.hazard_planar(pmap, s, self.sitecol, count=True)
-            elif isinstance(s, (MeshRuptures, SimpleFaultSource)):
+            elif isinstance(s, (MeshRuptures, SimpleFaultSource,
+                                MultiFaultRuptures)):
                 kept += cm.hazard_mesh(pmap, s, self.sitecol, count=True)
             elif not isinstance(s, PointSource):
                 raise NotImplementedError(
