@@ -381,6 +381,36 @@ def planar_of_source(src, shift_hypo=False, cmaker=None, sitecol=None):
 
 
 # ------------------------------------------------------------ ContextMaker
+def fault_of_source(src):
+    """
+    The device-side description of a reference SimpleFaultSource
+    (source/simple_fault.py): its fault mesh from the reference's own
+    SimpleFaultSurface.from_fault_data, its magnitudes and rates from
+    get_annual_occurrence_rates; the floating ruptures are then windows of
+    that mesh (oq_engine_b200.fault.SimpleFaultSource).
+    """
+    from openquake.hazardlib.geo.surface.simple_fault import (
+        SimpleFaultSurface)
+    msr = src.magnitude_scaling_relationship.__class__.__name__
+    _no(src, hypo_list=len(src.hypo_list), slip_list=len(src.slip_list),
+        hypo_depth_list=len(src.hypo_depth_list),
+        msr=msr not in ('WC1994', 'PointMSR'),
+        magnitude_dependent_aspect_ratio=not isinstance(
+            src.rupture_aspect_ratio, (int, float)))
+    mesh = SimpleFaultSurface.from_fault_data(
+        src.fault_trace, src.upper_seismogenic_depth,
+        src.lower_seismogenic_depth, src.dip, src.rupture_mesh_spacing).mesh
+    mags, rates = zip(*src.get_annual_occurrence_rates())
+    out = _gpu.SimpleFaultSource(
+        src.source_id, (mesh.lons, mesh.lats, mesh.depths),
+        _gpu.ArbitraryMFD(mags, rates), src.rupture_mesh_spacing, msr,
+        float(src.rupture_aspect_ratio), float(src.rake),
+        src.tectonic_region_type)
+    out.id = getattr(src, 'id', 0)
+    out.offset = getattr(src, 'offset', 0)
+    return out
+
+
 class GpuContextMaker(ContextMaker):
     """
     The reference's ContextMaker with the hot operators on the device.
@@ -475,10 +505,17 @@ class GpuContextMaker(ContextMaker):
         kept = 0
         with self.poe_mon:
             for src in sources:
+                if src.__class__.__name__ == 'SimpleFaultSource':
+                    # genctxs of a fault source: distance planes of the
+                    # rupture meshes + the fused pass (oqg_hazard_dist)
+                    kept += eng.hazard_mesh(dmap, fault_of_source(src),
+                                            dsites, count=True)
+                    continue
                 if not hasattr(src, 'get_planar'):
                     raise NotImplementedError(
                         '%s has no device implementation of its ruptures '
-                        '(point-like sources only)' % src.__class__.__name__)
+                        '(point-like and simple fault sources only)'
+                        % src.__class__.__name__)
                 planar, mags, aux = planar_of_source(
                     src, self.shift_hypo, self, sitecol)
                 kept += eng.hazard_planar(

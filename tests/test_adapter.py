@@ -310,3 +310,35 @@ def test_reference_arm_runs_the_installed_reference():
                              sites, None, 0)
     acc = hazard_np.exact_rate_sum(pairs, octx, sites['sids'], imtls, 3., 50.)
     np.testing.assert_allclose(arr, np.exp(-acc), rtol=2e-5, atol=1e-7)
+
+
+@needs_ref
+def test_fault_source_of_the_reference(ref):
+    """a reference SimpleFaultSource becomes the device-side description
+    whose floating ruptures are the reference's own (the fault of the
+    LogicTreeCase2ClassicalPSHA demo, fixture of oracle/make_golden_fault.py)"""
+    og, _avail = ref
+    from openquake.hazardlib.geo import Point, Line
+    from openquake.hazardlib.mfd import TruncatedGRMFD
+    from openquake.hazardlib.scalerel.wc1994 import WC1994
+    from openquake.hazardlib.source import SimpleFaultSource
+    from openquake.hazardlib.tom import PoissonTOM
+    d = load('fault_ctxs')
+    src = SimpleFaultSource(
+        'second', 'Simple Fault Source', 'Active Shallow Crust',
+        TruncatedGRMFD(*d['mfd']), float(d['spacing']), WC1994(), 2.0,
+        PoissonTOM(50.), 8., 20., Line([Point(1.0, -0.5), Point(1.4, 0.0),
+                                        Point(1.4, 0.3)]), 30., 90.)
+    dev = og.fault_of_source(src)
+    np.testing.assert_array_equal(dev.mesh[0], d['mesh_lons'])
+    np.testing.assert_array_equal(dev.mesh[2], d['mesh_deps'])
+    mag, rate, win = dev.windows()
+    np.testing.assert_array_equal(win, d['windows'])
+    np.testing.assert_allclose(mag, d['mag'], rtol=1e-15)
+    np.testing.assert_allclose(rate, d['rate'], rtol=1e-14)
+    assert dev.count_ruptures() == src.count_ruptures() == 400
+    import copy
+    bad = copy.copy(src)
+    bad.hypo_list = ((0.5, 0.5, 1.),)
+    with pytest.raises(NotImplementedError, match='hypo_list'):
+        og.fault_of_source(bad)
