@@ -457,8 +457,10 @@ int oqg_gmf(oqg_handle *h, const float *mean_stds_dev,
  *               OQG_STAT_QUANTILE with its quantile in qs[s]
  *   rlz_out_dev [R][N][L] float32 or NULL ('hcurves-rlzs')
  *   stat_out_dev[S][N][L] float32 or NULL ('hcurves-stats')
- * S <= 16, W <= 64; quantiles need R <= 4096, mean, std and max have no
- * limit on R (an error otherwise). */
+ * S <= 16, W <= 64.  Realizations using the same set of gsim columns have
+ * the same curve and are handled as one group (exactly: see oqg_post.cuh);
+ * quantiles need at most 256 distinct groups or R <= 4096; mean, std and max
+ * have no limit on R (an error otherwise). */
 enum { OQG_STAT_MEAN = 0, OQG_STAT_STD = 1, OQG_STAT_QUANTILE = 2,
        OQG_STAT_MAX = 3 };
 int oqg_postclassical(oqg_handle *h, const float *rates_dev, int N, int L,
@@ -468,6 +470,14 @@ int oqg_postclassical(oqg_handle *h, const float *rates_dev, int N, int L,
                       const double *weight_sums, int S, const int32_t *kinds,
                       const double *qs, int use_rates, float *rlz_out_dev,
                       float *stat_out_dev);
+/* grouping of the realizations with equal gsim columns in oqg_postclassical
+ * (default on; off = one group per realization, for tests and measurements) */
+int oqg_set_post_grouping(oqg_handle *h, int on);
+/* the kernel path of the last oqg_postclassical call: 0 groups in registers /
+ * shared memory, 1 streaming (no quantile), 2 one CTA per element, 3 generic;
+ * *groups (may be NULL) = the number of groups it worked on */
+int oqg_last_post_path(oqg_handle *h, int *groups);
+
 /* calc_mean_rates (hazardlib/calc/mean_rates.py:62-74): the mean rates
  * out_dev[N][L] (float64) = rates_dev[N][L][Gt] (float32) times the weights
  * of the gsim columns weights_dev[W][Gt], W = 1 (one weight per column, the

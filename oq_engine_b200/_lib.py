@@ -144,6 +144,8 @@ def lib():
         'oqg_set_fused_config': (C.c_int, [H, C.c_int, C.c_int]),
         'oqg_last_fused_subs': (C.c_int, [H]),
         'oqg_set_site_grouping': (C.c_int, [H, C.c_int, C.c_double]),
+        'oqg_set_post_grouping': (C.c_int, [H, C.c_int]),
+        'oqg_last_post_path': (C.c_int, [H, C.POINTER(C.c_int)]),
         'oqg_set_count_evals': (C.c_int, [H, C.c_int]),
         'oqg_launch_count': (C.c_ulonglong, [H]),
         'oqg_last_fused_ms': (C.c_int, [H, C.POINTER(C.c_float), C.c_int]),

@@ -23,6 +23,7 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <map>
 #include <algorithm>
 #include <mutex>
 
@@ -107,6 +108,10 @@ struct oqg_handle {
   bool site_grouping = true;
   double site_cell_deg = 0.16;
   Buf sg_keys[2], sg_idx[2], sg_tmp, sg_par[4], sg_sidx;
+  // oqg_postclassical: grouping of the realizations with the same gsim
+  // columns (oqg_set_post_grouping), the kernel path of the last call
+  bool post_grouping = true;
+  int last_post_path = -1, last_post_groups = 0;
 };
 
 static std::string g_create_err;
@@ -1959,59 +1964,170 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
     A.kind[s] = kinds[s];
     A.q[s] = qs[s];
   }
-  // shared-memory need of the register / shared-memory sort path; the
-  // generic kernel (local arrays, insertion sort) remains for the rare case
-  // that does not fit (many IMT-dependent weight columns x many realizations)
-  int rp_ = 4;
-  while (rp_ < R) rp_ <<= 1;
-  const size_t smem_est = (size_t)rp_ * (rp_ <= 32 ? 128 : 64) * 8 +
-                          (size_t)std::max(W, 1) * R * 12 + (size_t)R * 64 +
-                          (size_t)128 * (Gt | 1) * 4 + 4096;
   bool any_quantile = false;
   for (int s = 0; s < S; s++) any_quantile |= kinds[s] == OQG_STAT_QUANTILE;
-  if (any_quantile && R > OQG_RMAX_CTA)
-    return fail(h, "postclassical: quantiles need R <= 4096 (mean, std and "
-                   "max have no limit)");
-  const bool stream = !any_quantile && (R > 256 || smem_est > 200 * 1024);
-  const bool cta = any_quantile && R > 256;
-  if (stream || cta || (R <= 256 && smem_est <= 200 * 1024)) {
-    // register / shared-memory sort path: inverse map realization -> gsim columns, weight ranks
-    // (small host-side tables, copied through a staging buffer)
-    std::vector<int32_t> goff(Gt + 1), tab;
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(goff.data(), g_off, (Gt + 1) * 4, cudaMemcpyDeviceToHost));
-    std::vector<int32_t> grlz(goff[Gt]);
-    if (goff[Gt])
-      CK(cudaMemcpy(grlz.data(), g_rlz, (size_t)goff[Gt] * 4, cudaMemcpyDeviceToHost));
-    std::vector<std::vector<int32_t>> inv(R);
-    for (int g = 0; g < Gt; g++)
-      for (int k = goff[g]; k < goff[g + 1]; k++) {
-        if (grlz[k] < 0 || grlz[k] >= R)
-          return fail(h, "postclassical: realization index out of range");
-        inv[grlz[k]].push_back(g);
+  // the gsim columns of every realization (inverse of g_off / g_rlz), and the
+  // GROUPS of realizations with the same columns, hence the same curve
+  std::vector<int32_t> goff(Gt + 1);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(goff.data(), g_off, (Gt + 1) * 4, cudaMemcpyDeviceToHost));
+  if (goff[0] != 0 || goff[Gt] < 0)
+    return fail(h, "postclassical: bad g_off");
+  std::vector<int32_t> grlz(goff[Gt]);
+  if (goff[Gt])
+    CK(cudaMemcpy(grlz.data(), g_rlz, (size_t)goff[Gt] * 4, cudaMemcpyDeviceToHost));
+  std::vector<std::vector<int32_t>> inv(R);
+  for (int g = 0; g < Gt; g++)
+    for (int k = goff[g]; k < goff[g + 1]; k++) {
+      if (grlz[k] < 0 || grlz[k] >= R)
+        return fail(h, "postclassical: realization index out of range");
+      inv[grlz[k]].push_back(g);
+    }
+  std::vector<int32_t> grp(R);
+  std::vector<std::vector<int32_t>> members;
+  if (h->post_grouping) {
+    std::map<std::vector<int32_t>, int32_t> seen;
+    for (int r = 0; r < R; r++) {
+      auto it = seen.find(inv[r]);
+      if (it == seen.end()) {
+        it = seen.emplace(inv[r], (int32_t)members.size()).first;
+        members.emplace_back();
       }
+      grp[r] = it->second;
+      members[it->second].push_back(r);
+    }
+  } else {
+    for (int r = 0; r < R; r++) { grp[r] = r; members.push_back({r}); }
+  }
+  const int D = (int)members.size();
+  int rp_ = 4;
+  while (rp_ < D) rp_ <<= 1;
+  const int Wn = std::max(W, 1);
+  const size_t smem_reg = (size_t)rp_ * (rp_ <= 32 ? 128 : 64) * 8 +
+                          (size_t)Wn * D * 20 + (size_t)(D + 1) * 8 +
+                          (size_t)goff[Gt] * 4 + 16 +
+                          (size_t)(rp_ <= 32 ? 128 : 64) * (Gt | 1) * 4;
+  const bool reg = D <= 256 && smem_reg <= 200 * 1024;
+  if (any_quantile && !reg && R > OQG_RMAX_CTA)
+    return fail(h, "postclassical: quantiles need at most 256 distinct sets of "
+                   "gsim columns or R <= 4096 (mean, std and max have no limit)");
+  const bool stream = !reg && !any_quantile;
+  const bool cta = !reg && any_quantile && R > 256;
+  h->last_post_path = reg ? 0 : stream ? 1 : cta ? 2 : 3;
+  h->last_post_groups = reg ? D : R;
+  std::vector<double> wh((size_t)Wn * R, 0.);
+  if (S && (reg || cta))
+    CK(cudaMemcpy(wh.data(), weights, wh.size() * 8, cudaMemcpyDeviceToHost));
+  // ranks of n weights per weight column, equal weights get equal ranks
+  auto ranks_of = [&](const std::vector<double> &x, int n) {
+    std::vector<int32_t> rank((size_t)Wn * n, 0);
+    for (int c = 0; c < Wn; c++) {
+      std::vector<int> ord(n);
+      for (int r = 0; r < n; r++) ord[r] = r;
+      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+        return x[(size_t)c * n + a] < x[(size_t)c * n + b]; });
+      int rk = 0;
+      for (int i = 0; i < n; i++) {
+        if (i && x[(size_t)c * n + ord[i]] != x[(size_t)c * n + ord[i - 1]]) rk = i;
+        rank[(size_t)c * n + ord[i]] = rk;
+      }
+    }
+    return rank;
+  };
+  PostRegArgs B;
+  memset(&B, 0, sizeof(B));
+  B.rates = rates; B.rlz_out = rlz_out; B.stat_out = stat_out;
+  B.n_elems = A.n_elems; B.L = L; B.L1 = L / M; B.Gt = Gt;
+  B.W = Wn; B.S = S; B.use_rates = use_rates;
+  memcpy(B.wsum, A.wsum, sizeof(B.wsum));
+  memcpy(B.kind, A.kind, sizeof(B.kind));
+  memcpy(B.q, A.q, sizeof(B.q));
+  if (reg) {
+    // tables of the groups: columns, member realizations, W_d, w_d, rank of w_d
+    std::vector<int32_t> roff(D + 1, 0), rgs, moff(D + 1, 0), mrlz;
+    std::vector<double> gw((size_t)Wn * D, 0.), gmin((size_t)Wn * D, 0.);
+    for (int d = 0; d < D; d++) {
+      const auto &cols = inv[members[d][0]];
+      rgs.insert(rgs.end(), cols.begin(), cols.end());
+      roff[d + 1] = (int32_t)rgs.size();
+      mrlz.insert(mrlz.end(), members[d].begin(), members[d].end());
+      moff[d + 1] = (int32_t)mrlz.size();
+      for (int c = 0; c < Wn && S; c++) {
+        // summed in increasing order, like the cumsum over the sorted weights
+        std::vector<double> ws;
+        for (int r : members[d]) ws.push_back(wh[(size_t)c * R + r]);
+        std::sort(ws.begin(), ws.end());
+        double tot = 0.;
+        for (double x : ws) tot += x;
+        gw[(size_t)c * D + d] = tot;
+        gmin[(size_t)c * D + d] = ws[0];
+      }
+    }
+    std::vector<int32_t> rank = ranks_of(gmin, D);
+    const size_t nd = gw.size() + gmin.size();
+    const size_t ni = rank.size() + roff.size() + moff.size() + rgs.size() + mrlz.size();
+    if (reserve(h, h->stage[10], nd * 8 + ni * 4 + 16)) return 1;
+    double *dd = (double *)h->stage[10].p;
+    int32_t *di = (int32_t *)(dd + nd);
+    std::vector<int32_t> ints;
+    ints.insert(ints.end(), rank.begin(), rank.end());
+    ints.insert(ints.end(), roff.begin(), roff.end());
+    ints.insert(ints.end(), moff.begin(), moff.end());
+    ints.insert(ints.end(), rgs.begin(), rgs.end());
+    ints.insert(ints.end(), mrlz.begin(), mrlz.end());
+    std::vector<double> dbl(gw);
+    dbl.insert(dbl.end(), gmin.begin(), gmin.end());
+    CK(cudaMemcpy(dd, dbl.data(), nd * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(di, ints.data(), ni * 4, cudaMemcpyHostToDevice));
+    B.weights = dd; B.wmin = dd + gw.size();
+    B.wrank = di; B.r_off = di + rank.size(); B.m_off = B.r_off + roff.size();
+    B.r_gs = B.m_off + moff.size(); B.m_rlz = B.r_gs + rgs.size();
+    B.R = D;
+    // the quantiles in increasing order: one scan of the sorted groups
+    std::vector<int> qord;
+    for (int s = 0; s < S; s++)
+      if (kinds[s] == OQG_STAT_QUANTILE) qord.push_back(s);
+    std::stable_sort(qord.begin(), qord.end(),
+                     [&](int a, int b) { return qs[a] < qs[b]; });
+    B.nq = (int)qord.size();
+    for (int i = 0; i < B.nq; i++) {
+      B.qstat[i] = qord[i];
+      B.qsorted[i] = qs[qord[i]];
+    }
+    const int RP = rp_;
+    const int TPB = RP <= 32 ? 128 : 64;
+    const size_t smem = (size_t)RP * TPB * 8 + (size_t)Wn * D * 20 +
+                        (size_t)(D + 1) * 8 + rgs.size() * 4 + 16 +
+                        (size_t)TPB * (Gt | 1) * 4;
+    unsigned grid = (unsigned)((A.n_elems + TPB - 1) / TPB);
+#define POST_LAUNCH(rp, tpb)                                                  \
+  {                                                                           \
+    CK(cudaFuncSetAttribute(k_postclassical_reg<rp, tpb>,                     \
+                            cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                            (int)smem));                                      \
+    k_postclassical_reg<rp, tpb><<<grid, tpb, smem, h->stream>>>(B);          \
+  }
+    if (RP == 4) POST_LAUNCH(4, 128)
+    else if (RP == 8) POST_LAUNCH(8, 128)
+    else if (RP == 16) POST_LAUNCH(16, 128)
+    else if (RP == 32) POST_LAUNCH(32, 128)
+    else if (RP == 64) POST_LAUNCH(64, 64)
+    else if (RP == 128) POST_LAUNCH(128, 64)
+    else POST_LAUNCH(256, 64)
+#undef POST_LAUNCH
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  if (stream || cta) {
+    // one table entry per realization
     std::vector<int32_t> roff(R + 1, 0), rgs;
     for (int r = 0; r < R; r++) {
       rgs.insert(rgs.end(), inv[r].begin(), inv[r].end());
       roff[r + 1] = (int32_t)rgs.size();
     }
-    std::vector<double> wh((size_t)std::max(W, 1) * R, 0.);
-    std::vector<int32_t> rank((size_t)std::max(W, 1) * R, 0);
-    if (S && !stream) {
-      CK(cudaMemcpy(wh.data(), weights, wh.size() * 8, cudaMemcpyDeviceToHost));
-      for (int c = 0; c < W; c++) {
-        std::vector<int> ord(R);
-        for (int r = 0; r < R; r++) ord[r] = r;
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-          return wh[(size_t)c * R + a] < wh[(size_t)c * R + b]; });
-        // equal weights get equal ranks
-        int rk = 0;
-        for (int i = 0; i < R; i++) {
-          if (i && wh[(size_t)c * R + ord[i]] != wh[(size_t)c * R + ord[i - 1]]) rk = i;
-          rank[(size_t)c * R + ord[i]] = rk;
-        }
-      }
-    }
+    std::vector<int32_t> rank((size_t)Wn * R, 0);
+    if (S && cta) rank = ranks_of(wh, R);
     size_t nb = (roff.size() + rgs.size() + rank.size()) * 4;
     if (reserve(h, h->stage[10], nb + 16)) return 1;
     int32_t *d = (int32_t *)h->stage[10].p;
@@ -2020,17 +2136,10 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
       CK(cudaMemcpy(d + roff.size(), rgs.data(), rgs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d + roff.size() + rgs.size(), rank.data(), rank.size() * 4,
                   cudaMemcpyHostToDevice));
-    PostRegArgs B;
-    memset(&B, 0, sizeof(B));
-    B.rates = rates; B.r_off = d; B.r_gs = d + roff.size();
+    B.r_off = d; B.r_gs = d + roff.size();
     B.wrank = d + roff.size() + rgs.size();
-    B.weights = weights; B.rlz_out = rlz_out; B.stat_out = stat_out;
-    B.n_elems = A.n_elems; B.L = L; B.L1 = L / M; B.Gt = Gt; B.R = R;
-    B.W = std::max(W, 1); B.S = S; B.use_rates = use_rates;
+    B.weights = weights; B.R = R;
     if (!S) { B.W = 1; B.weights = (const double *)d; }  // never read
-    memcpy(B.wsum, A.wsum, sizeof(B.wsum));
-    memcpy(B.kind, A.kind, sizeof(B.kind));
-    memcpy(B.q, A.q, sizeof(B.q));
     if (cta) {
       // one CTA per (site, level): keys and scanned weights in shared memory
       int RPc = 512;
@@ -2077,42 +2186,29 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
       CK(cudaGetLastError());
       return 0;
     }
-    if (stream) {
-      k_postclassical_stream<<<(unsigned)((A.n_elems + 127) / 128), 128, 0,
-                               h->stream>>>(B);
-      h->launches++;
-      CK(cudaGetLastError());
-      return 0;
-    }
-    int RP = 4;
-    while (RP < R) RP <<= 1;
-    const int TPB = RP <= 32 ? 128 : 64;
-    size_t smem = (size_t)RP * TPB * 8 + (size_t)B.W * R * 12 +
-                  (R + 1 + rgs.size()) * 4 + 16 + (size_t)TPB * (Gt | 1) * 4;
-    unsigned grid = (unsigned)((A.n_elems + TPB - 1) / TPB);
-#define POST_LAUNCH(rp, tpb)                                                  \
-  {                                                                           \
-    CK(cudaFuncSetAttribute(k_postclassical_reg<rp, tpb>,                     \
-                            cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                            (int)smem));                                      \
-    k_postclassical_reg<rp, tpb><<<grid, tpb, smem, h->stream>>>(B);          \
-  }
-    if (RP == 4) POST_LAUNCH(4, 128)
-    else if (RP == 8) POST_LAUNCH(8, 128)
-    else if (RP == 16) POST_LAUNCH(16, 128)
-    else if (RP == 32) POST_LAUNCH(32, 128)
-    else if (RP == 64) POST_LAUNCH(64, 64)
-    else if (RP == 128) POST_LAUNCH(128, 64)
-    else POST_LAUNCH(256, 64)
-#undef POST_LAUNCH
+    k_postclassical_stream<<<(unsigned)((A.n_elems + 127) / 128), 128, 0,
+                             h->stream>>>(B);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
+  // generic kernel (local arrays, insertion sort): quantiles of R <= 256
+  // realizations whose tables do not fit in shared memory (many
+  // IMT-dependent weight columns x many groups)
   k_postclassical<<<(unsigned)((A.n_elems + 127) / 128), 128, 0, h->stream>>>(A);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+int oqg_set_post_grouping(oqg_handle *h, int on) {
+  h->post_grouping = on != 0;
+  return 0;
+}
+
+int oqg_last_post_path(oqg_handle *h, int *groups) {
+  if (groups) *groups = h->last_post_groups;
+  return h->last_post_path;
 }
 
 int oqg_mean_rates(oqg_handle *h, const float *rates, int64_t N, int L, int Gt,
@@ -2145,9 +2241,24 @@ int oqg_hazard_maps(oqg_handle *h, const float *curves, int64_t K, int M,
   if (K <= 0 || P <= 0) return 0;
   if (M < 1 || L1 < 1) return fail(h, "hazard_maps: bad shape");
   if (!curves || !imls || !poes || !out) return fail(h, "hazard_maps: missing array");
-  int64_t tot = K * M * P;
-  k_hazard_maps<<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(
-      curves, K, M, L1, imls, P, poes, out);
+  // rows of (curve, imt) per CTA: what 64 KB of shared memory hold
+  const size_t fixed = ((size_t)M * L1 + 2 * (size_t)P) * 8;
+  int rows = fixed < 32 * 1024
+                 ? (int)std::min<size_t>(HM_TPB, (64 * 1024 - fixed) / (4 * (size_t)(L1 | 1)))
+                 : 0;
+  rows -= rows % 32;
+  if (rows >= 64) {
+    const size_t smem = fixed + (size_t)rows * (L1 | 1) * 4;
+    CK(cudaFuncSetAttribute(k_hazard_maps,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t total_rows = K * M;
+    k_hazard_maps<<<(unsigned)((total_rows + rows - 1) / rows), HM_TPB, smem,
+                    h->stream>>>(curves, total_rows, M, L1, rows, imls, P, poes, out);
+  } else {
+    int64_t tot = K * M * P;
+    k_hazard_maps_direct<<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(
+        curves, K, M, L1, imls, P, poes, out);
+  }
   h->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -143,24 +143,43 @@ k_postclassical(const PostArgs A) {
   }
 }
 
-// ---- register path, R <= 32 ------------------------------------------------
-// The realization values of a thread never leave the registers: they are
-// accumulated through the inverse map realization -> gsim columns, written
-// out, folded into the mean / variance sums in float64, and packed into
-// 64-bit sort keys
-//     [ bits 63..10 of the (non negative) float64 value | weight rank (5) |
-//       realization (5) ]
+// ---- register path: up to 256 GROUPS of realizations ----------------------
+// Realizations that use the same set of gsim columns have the same curve
+// (full enumeration with one tectonic region type, sampled logic trees: a few
+// distinct sets, many realizations).  The host groups them (oqg_postclassical)
+// and the kernel works on the D distinct groups: one exp per group, the
+// realization curves are copies of the group values, and for the statistics
+// a group d is an element of weight W_d = the sum of its weights whose first
+// w_d = min weight matters for the quantiles: numpy sorts equal values by
+// weight, so of the interpolation points (cum, value) of a group only the
+// first one, at cum + w_d, is reached on a ramp from the previous value; the
+// others repeat the value.  With one realization per group (w_d = W_d) this
+// is the plain algorithm.
+// The values of a thread never leave the SM: accumulated through the map
+// group -> gsim columns, written out, folded into the mean / variance sums
+// in float64, and packed into 64-bit sort keys
+//     [ bits 63..10 of the (non negative) float64 value | rank of w_d (5) |
+//       group (5) ]
 // (staged through shared memory so that the value loop stays rolled) which
 // a bitonic network with compile-time register indices sorts for the quantiles
 // (ties of the value are broken by the weight like numpy's sort(order='c');
-// values are compared, and used in the interpolation, to 2^-42 relative).  The variance uses sums shifted by the first value, exact for
-// equal curves.
+// values are compared, and used in the interpolation, to 2^-42 relative).
+// All the quantiles are read off ONE scan of the sorted groups (the host
+// passes them in increasing order).  The variance uses sums shifted by the
+// first value, exact for equal curves.
 struct PostRegArgs {
   const float *rates;      // [N][L][Gt]
-  const int32_t *r_off;    // [R + 1] gsim columns of each realization
+  const int32_t *r_off;    // [R + 1] gsim columns of each realization (group)
   const int32_t *r_gs;
-  const double *weights;   // [W][R]
-  const int32_t *wrank;    // [W][R] rank of the weight among the realizations
+  const double *weights;   // [W][R] (register path: [W][D] group sums W_d)
+  const int32_t *wrank;    // [W][R] rank of the weight (of w_d) among them
+  // register path only (R = the number of groups D there)
+  const double *wmin;      // [W][D] smallest weight of the group
+  const int32_t *m_off;    // [D + 1] realizations of each group
+  const int32_t *m_rlz;
+  int nq;                  // quantiles in increasing order and their statistic
+  int qstat[OQG_SMAX];
+  double qsorted[OQG_SMAX];
   double wsum[64];
   float *rlz_out, *stat_out;
   int64_t n_elems;
@@ -207,27 +226,34 @@ __device__ __forceinline__ void bitonic_stage(unsigned long long (&key)[RP],
 
 // RP <= 32: TPB = 128 threads, keys sorted in registers; RP = 64 .. 256: TPB =
 // 64 threads, the same network on the keys in shared memory ([RP][TPB],
-// conflict free: consecutive threads, consecutive 8-byte words)
+// conflict free: consecutive threads, consecutive 8-byte words).  A.R is the
+// number of groups here.
 template <int RP, int TPB>
 __global__ void __launch_bounds__(TPB)
 k_postclassical_reg(const PostRegArgs A) {
   constexpr int IB = RP <= 32 ? 5 : 8;
   extern __shared__ double sm_post[];
   math_tables_init();   // fast_exp of oqg_math.cuh
-  // shared: keys [RP][128], weights [W][R] (double), wrank [W][R],
-  // r_off [R + 1], r_gs, rates [128][Gt | 1]
+  // shared: keys [RP][TPB], group weights and first weights [W][D] (double),
+  // wrank [W][D], r_off [D + 1], m_off [D + 1], r_gs, rates [TPB][Gt | 1]
   const int R = A.R, WR = A.W * R;
   unsigned long long *s_key = (unsigned long long *)sm_post + threadIdx.x;
   double *s_w = sm_post + RP * TPB;
-  int *s_rank = (int *)(s_w + WR);
+  double *s_wmin = s_w + WR;
+  int *s_rank = (int *)(s_wmin + WR);
   int *s_off = s_rank + WR;
-  int *s_gs = s_off + R + 1;
+  int *s_moff = s_off + R + 1;
+  int *s_gs = s_moff + R + 1;
   const int64_t e0 = blockIdx.x * (int64_t)blockDim.x;
   for (int i = threadIdx.x; i < WR; i += blockDim.x) {
     s_w[i] = A.weights[i];
+    s_wmin[i] = A.wmin[i];
     s_rank[i] = A.wrank[i];
   }
-  for (int i = threadIdx.x; i <= R; i += blockDim.x) s_off[i] = A.r_off[i];
+  for (int i = threadIdx.x; i <= R; i += blockDim.x) {
+    s_off[i] = A.r_off[i];
+    s_moff[i] = A.m_off[i];
+  }
   __syncthreads();
   const int ngs = s_off[R];
   for (int i = threadIdx.x; i < ngs; i += blockDim.x) s_gs[i] = A.r_gs[i];
@@ -249,6 +275,7 @@ k_postclassical_reg(const PostRegArgs A) {
   const int l = (int)(e % A.L);
   const int wcol = A.W > 1 ? l / A.L1 : 0;
   const double *w = s_w + wcol * R;
+  const double *wm = s_wmin + wcol * R;
   const int *rk = s_rank + wcol * R;
   const double wsum = A.wsum[wcol];
   const float *row = s_rates + threadIdx.x * gstride;
@@ -259,7 +286,12 @@ k_postclassical_reg(const PostRegArgs A) {
     double x = 0.;
     for (int k = s_off[r]; k < s_off[r + 1]; k++) x += (double)row[s_gs[k]];
     double v = 1. - fast_exp(fmax(-x, -700.));   // to_probs
-    if (A.rlz_out) A.rlz_out[(int64_t)r * A.n_elems + e] = (float)v;
+    if (A.rlz_out) {
+      // the curve of every realization of the group (uniform addresses)
+      const float vf = (float)v;
+      for (int k = s_moff[r]; k < s_moff[r + 1]; k++)
+        A.rlz_out[(int64_t)__ldg(A.m_rlz + k) * A.n_elems + e] = vf;
+    }
     if (A.use_rates) v = to_rate(v);
     if (r == 0) v0 = v;
     vmax = fmax(vmax, v);                       // probabilities, rates: >= 0
@@ -274,7 +306,6 @@ k_postclassical_reg(const PostRegArgs A) {
   }
   if (!stats) return;
   const double dm = sw1 / wsum;               // mean - v0
-  bool sorted = false;
   for (int s = 0; s < A.S; s++) {
     double res;
     if (A.kind[s] == OQG_STAT_MEAN) {
@@ -285,65 +316,74 @@ k_postclassical_reg(const PostRegArgs A) {
     } else if (A.kind[s] == OQG_STAT_MAX) {
       res = vmax;
     } else {
-      if (!sorted && RP > 32) {
-        for (int r = R; r < RP; r++) s_key[r * TPB] = ~0ull;   // padding
-        for (int k = 2; k <= RP; k <<= 1)
-          for (int j = k >> 1; j > 0; j >>= 1)
-            for (int i = 0; i < RP; i++) {
-              const int p = i ^ j;
-              if (p > i) {
-                const unsigned long long a = s_key[i * TPB], b = s_key[p * TPB];
-                if ((a > b) == ((i & k) == 0)) {
-                  s_key[i * TPB] = b;
-                  s_key[p * TPB] = a;
-                }
-              }
-            }
-        sorted = true;
-      }
-      if (!sorted) {
-        constexpr int RR = RP <= 32 ? RP : 4;   // register network: RP <= 32
-        unsigned long long key[RR];
-#pragma unroll
-        for (int r = 0; r < RR; r++)
-          key[r] = r < R ? s_key[r * TPB] : ~0ull;   // padding sorts last
-#pragma unroll 1
-        for (int k = 2; k <= RR; k <<= 1) {
-#pragma unroll 1
-          for (int j = k >> 1; j > 0; j >>= 1) {
-            switch (j) {
-              case 16: if (RR > 16) bitonic_stage<RR, (RR > 16 ? 16 : 1)>(key, k); break;
-              case 8: if (RR > 8) bitonic_stage<RR, (RR > 8 ? 8 : 1)>(key, k); break;
-              case 4: if (RR > 4) bitonic_stage<RR, (RR > 4 ? 4 : 1)>(key, k); break;
-              case 2: bitonic_stage<RR, 2>(key, k); break;
-              default: bitonic_stage<RR, 1>(key, k); break;
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < RR; r++) s_key[r * TPB] = key[r];
-        sorted = true;
-      }
-      // numpy.interp(q, cumsum(w sorted), v sorted)
-      const double q = A.q[s];
-      double cum = 0., prev_cum = 0., prev_v = 0.;
-      res = 0.;
-#pragma unroll 1
-      for (int j = 0; j < R; j++) {
-        const unsigned long long kj = s_key[j * TPB];
-        const double vk = post_key_value<IB>(kj);
-        cum += w[(int)(kj & ((1u << IB) - 1))];
-        if (q < cum || j == R - 1) {
-          if (j == 0 || q >= cum) res = vk;
-          else res = prev_v + (q - prev_cum) * ((vk - prev_v) / (cum - prev_cum));
-          break;
-        }
-        prev_cum = cum;
-        prev_v = vk;
-      }
+      continue;
     }
     if (A.use_rates) res = 1. - exp(-res);
     A.stat_out[(int64_t)s * A.n_elems + e] = (float)res;
+  }
+  if (A.nq == 0) return;
+  if (RP > 32) {
+    for (int r = R; r < RP; r++) s_key[r * TPB] = ~0ull;   // padding
+    for (int k = 2; k <= RP; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1)
+        for (int i = 0; i < RP; i++) {
+          const int p = i ^ j;
+          if (p > i) {
+            const unsigned long long a = s_key[i * TPB], b = s_key[p * TPB];
+            if ((a > b) == ((i & k) == 0)) {
+              s_key[i * TPB] = b;
+              s_key[p * TPB] = a;
+            }
+          }
+        }
+  } else {
+    constexpr int RR = RP <= 32 ? RP : 4;   // register network: RP <= 32
+    unsigned long long key[RR];
+#pragma unroll
+    for (int r = 0; r < RR; r++)
+      key[r] = r < R ? s_key[r * TPB] : ~0ull;   // padding sorts last
+#pragma unroll 1
+    for (int k = 2; k <= RR; k <<= 1) {
+#pragma unroll 1
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        switch (j) {
+          case 16: if (RR > 16) bitonic_stage<RR, (RR > 16 ? 16 : 1)>(key, k); break;
+          case 8: if (RR > 8) bitonic_stage<RR, (RR > 8 ? 8 : 1)>(key, k); break;
+          case 4: if (RR > 4) bitonic_stage<RR, (RR > 4 ? 4 : 1)>(key, k); break;
+          case 2: if (RR > 2) bitonic_stage<RR, (RR > 2 ? 2 : 1)>(key, k); break;
+          default: bitonic_stage<RR, 1>(key, k); break;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RR; r++) s_key[r * TPB] = key[r];
+  }
+  // numpy.interp(q, cumsum(w sorted), v sorted) for all the quantiles in one
+  // scan of the sorted groups: group j covers (cum, cum + W_j]; up to
+  // cum + w_j the curve ramps from the previous value, then it is flat
+  int qi = 0;
+  double cum = 0., prev_v = 0.;
+#pragma unroll 1
+  for (int j = 0; j < R && qi < A.nq; j++) {
+    const unsigned long long kj = s_key[j * TPB];
+    const double vk = post_key_value<IB>(kj);
+    const int g = (int)(kj & ((1u << IB) - 1));
+    const double c1 = cum + wm[g], c2 = cum + w[g];
+    while (qi < A.nq) {
+      const double q = A.qsorted[qi];
+      double res;
+      if (q < c1)
+        res = j == 0 ? vk : prev_v + (q - cum) * ((vk - prev_v) / (c1 - cum));
+      else if (q < c2 || j == R - 1)
+        res = vk;
+      else
+        break;
+      if (A.use_rates) res = 1. - exp(-res);
+      A.stat_out[(int64_t)A.qstat[qi] * A.n_elems + e] = (float)res;
+      qi++;
+    }
+    cum = c2;
+    prev_v = vk;
   }
 }
 
@@ -648,9 +688,76 @@ k_mean_rates_direct(const float *__restrict__ rates, int64_t n_elems, int L,
   out[e] = acc;
 }
 
-// compute_hazard_maps, map_array.py:94-141: one thread per (curve, imt, poe)
-// curves [K][M][L1] float32, imls [M][L1], out [K][M][P]
-__global__ void k_hazard_maps(const float *__restrict__ curves, int64_t K,
+// compute_hazard_maps, map_array.py:94-141.  curves [K][M][L1] float32, imls
+// [M][L1], out [K][M][P].  One thread per (curve, imt) row and all its P
+// poes; a CTA copies its rows to shared memory as one contiguous, coalesced
+// range (odd row stride: conflict free) and the logs of the levels once.
+// The bracketing levels are found by comparing the values themselves
+// (log is increasing and the curve values are float32: log(max(c, EPSILON))
+// <= log(poe) exactly when max(c, EPSILON) <= poe), so only the two
+// bracketing values go through log: 2 log + 1 exp per (row, poe) instead of
+// 2 L1 logs, and the kernel is an HBM stream.
+#define HM_TPB 256
+__global__ void __launch_bounds__(HM_TPB)
+k_hazard_maps(const float *__restrict__ curves, int64_t rows_total, int M,
+              int L1, int rows, const double *__restrict__ imls, int P,
+              const double *__restrict__ poes, float *__restrict__ out) {
+  extern __shared__ double sm_hm[];
+  double *s_li = sm_hm;                       // [M][L1] log of the levels
+  double *s_p = s_li + M * L1;                // [P] poes, [P] log poes
+  float *s_c = (float *)(s_p + 2 * P);        // [rows][L1 | 1]
+  const int stride = L1 | 1;
+  const int64_t r0 = blockIdx.x * (int64_t)rows;
+  const int nr = (int)min((int64_t)rows, rows_total - r0);
+  for (int i = threadIdx.x; i < M * L1; i += HM_TPB) s_li[i] = log(imls[i]);
+  for (int i = threadIdx.x; i < P; i += HM_TPB) {
+    s_p[i] = poes[i];
+    s_p[P + i] = log(poes[i]);
+  }
+  const float *src = curves + r0 * L1;
+  for (int i = threadIdx.x; i < nr * L1; i += HM_TPB) {
+    const int r = i / L1;
+    s_c[r * stride + (i - r * L1)] = src[i];
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r >= nr) return;
+  const int64_t km = r0 + r;
+  const int m = (int)(km % M);
+  const float *c = s_c + r * stride;
+  const double *li = s_li + m * L1;
+  const double EPS = 1E-30;
+  // reversed curve: x[j] = log(max(c[L1 - 1 - j], EPSILON)), increasing in j
+#define CV(j) fmax((double)c[L1 - 1 - (j)], EPS)
+  for (int p = 0; p < P; p++) {
+    const double poe = s_p[p], lp = s_p[P + p];
+    double res = 0.;
+    if (!(poe > CV(L1 - 1))) {
+      if (poe < CV(0)) {
+        res = exp(li[L1 - 1]);
+      } else {
+        // numpy.interp: the last j with x[j] <= lp
+        int j = 0;
+        for (int t = 1; t < L1; t++)
+          if (CV(t) <= poe) j = t;
+        const double y0 = li[L1 - 1 - j];
+        if (j == L1 - 1) {
+          res = exp(y0);
+        } else {
+          const double x0 = log(CV(j)), x1 = log(CV(j + 1));
+          const double y1 = li[L1 - 2 - j];
+          res = x0 == lp ? exp(y0) : exp(y0 + (lp - x0) * ((y1 - y0) / (x1 - x0)));
+        }
+      }
+    }
+    out[km * P + p] = (float)res;
+  }
+#undef CV
+}
+
+// curves too long for the shared memory of a CTA: one thread per
+// (curve, imt, poe) reading global memory
+__global__ void k_hazard_maps_direct(const float *__restrict__ curves, int64_t K,
                               int M, int L1, const double *__restrict__ imls,
                               int P, const double *__restrict__ poes,
                               float *__restrict__ out) {

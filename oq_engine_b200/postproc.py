@@ -113,7 +113,7 @@ def calc_mean_rates(rmap, gweights, wget, imtls, device=None,
 
 def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
                   individual_rlzs=False, poes=(), use_rates=False,
-                  device=None):
+                  device=None, grouping=True):
     """
     :param rmap: a rates MapArray (N, L, Gt) (or its array)
     :param trt_rlzs: for each gsim column g the realizations it belongs to
@@ -122,6 +122,8 @@ def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
         weights (one column per IMT, the last one the default weight)
     :param imtls: dict imt -> levels (M IMTs of L1 levels, L = M * L1)
     :param hstats: names of the statistics: 'mean', 'std', 'quantile-X'
+    :param grouping: False = do not group the realizations with the same
+        gsim columns (tests and measurements; the results are the same)
     :returns: a dictionary kind -> list of MapArray (N, M, L1) [or (N, M, P)
         for the hazard maps], kinds 'hcurves-rlzs', 'hcurves-stats',
         'hmaps-rlzs', 'hmaps-stats' as in the reference
@@ -158,8 +160,17 @@ def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
     specs = [_stat_spec(name) for name in hstats]
     S = len(specs)
     if R > 4096 and any(k == KINDS['quantile'] for k, _ in specs):
-        raise ValueError('quantiles need at most 4096 realizations, got %d '
-                         '(mean, std and max have no limit)' % R)
+        # realizations with the same gsim columns share their curve: the
+        # library works on the distinct groups
+        member = numpy.zeros((R, Gt), bool)
+        for g, r in enumerate(rlzs):
+            member[r, g] = True
+        ngroups = len(numpy.unique(member, axis=0)) if grouping else R
+        if ngroups > 256:
+            raise ValueError(
+                'quantiles need at most 4096 realizations or 256 distinct '
+                'sets of gsim columns, got %d / %d (mean, std and max have '
+                'no limit)' % (R, ngroups))
     do_rlzs = R == 1 or individual_rlzs
     t_rates = _dev(arr, dev, torch.float32)
     g_off = numpy.concatenate([[0], numpy.cumsum([len(r) for r in rlzs])]
@@ -173,6 +184,7 @@ def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
     kinds = (ctypes.c_int32 * max(S, 1))(*[k for k, _ in specs])
     qs = (ctypes.c_double * max(S, 1))(*[q for _, q in specs])
     ws = (ctypes.c_double * len(wsum))(*wsum)
+    h.call('oqg_set_post_grouping', int(bool(grouping)))
     h.call('oqg_postclassical', _ptr(t_rates), N, L, Gt, M, _ptr(t_off),
            _ptr(t_rlz), R, _ptr(t_w), len(wsum), ws, S, kinds, qs,
            int(use_rates), _ptr(t_r), _ptr(t_s))
@@ -202,6 +214,17 @@ def postclassical(rmap, trt_rlzs, weights, imtls, hstats=('mean',),
                    _ptr(t_p), _ptr(t_o))
             out['hmaps-' + kind] = maps(t_o, P)
     return out
+
+
+def last_post_path(device=None):
+    """(path, groups) of the last postclassical call on the device: path 0 =
+    groups in registers / shared memory, 1 = streaming, 2 = one CTA per
+    element, 3 = generic kernel"""
+    h = _handle(device)
+    n = ctypes.c_int(0)
+    from ._lib import lib
+    path = lib().oqg_last_post_path(h._h, ctypes.byref(n))
+    return path, n.value
 
 
 rates_dt = numpy.dtype([('sid', numpy.uint32), ('lid', numpy.uint16),

@@ -13,6 +13,7 @@ rtol 1e-5 -- the reference takes a float32 logarithm of the curve
 (see oracle/post_np.py), the device a float64 one.
 """
 import os
+import itertools
 import numpy as np
 import pytest
 
@@ -164,11 +165,13 @@ def test_postclassical_errors_and_single_rlz(oq):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('grouping', [True, False])
 @pytest.mark.parametrize('R', [1, 4, 9, 33, 40, 130])
-def test_postclassical_other_sizes_vs_oracle(oq, R):
-    """every kernel variant (register path RP = 4 .. 32, generic path for
-    R > 32) against the oracle on random rates, with ties between
-    realizations sharing all their gsim columns"""
+def test_postclassical_other_sizes_vs_oracle(oq, R, grouping):
+    """every kernel variant (register path RP = 4 .. 32, shared-memory path
+    for more groups) against the oracle on random rates, with ties between
+    realizations sharing all their gsim columns: grouped (at most 21 distinct
+    sets of 2 of 6 columns) and one group per realization"""
     rng = np.random.default_rng(R)
     n, m, l1, gt = 23, 2, 5, 6
     L = m * l1
@@ -182,7 +185,11 @@ def test_postclassical_other_sizes_vs_oracle(oq, R):
              'max']
     imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
     res = oq.postclassical(rates, trt_rlzs, w, imtls, names,
-                           individual_rlzs=True)
+                           individual_rlzs=True, grouping=grouping)
+    path, groups = oq.postproc.last_post_path()
+    assert path == 0, path
+    assert groups == (min(R, len(set(map(tuple, np.sort(pick, axis=1)))))
+                      if grouping else R), groups
     hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
     got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
     np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
@@ -198,10 +205,12 @@ def test_postclassical_other_sizes_vs_oracle(oq, R):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('grouping', [False, True])
 @pytest.mark.parametrize('use_rates', [False, True])
-def test_postclassical_many_rlzs_stream(oq, use_rates):
+def test_postclassical_many_rlzs_stream(oq, use_rates, grouping):
     """mean and std need no sort: the streaming kernel takes any number of
-    realizations (sampled logic trees); quantiles beyond 256 are refused"""
+    realizations (one group per realization); grouped, the 600 realizations
+    are at most 45 distinct sets of columns"""
     R = 600
     rng = np.random.default_rng(7)
     n, m, l1, gt = 17, 2, 5, 9
@@ -213,7 +222,9 @@ def test_postclassical_many_rlzs_stream(oq, use_rates):
     w = np.full(R, 1. / R)                       # sampling: equal weights
     imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
     res = oq.postclassical(rates, trt_rlzs, w, imtls, ['mean', 'std', 'max'],
-                           individual_rlzs=True, use_rates=use_rates)
+                           individual_rlzs=True, use_rates=use_rates,
+                           grouping=grouping)
+    assert oq.postproc.last_post_path()[0] == (0 if grouping else 1)
     hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
     got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
     np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
@@ -227,12 +238,14 @@ def test_postclassical_many_rlzs_stream(oq, use_rates):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('grouping', [False, True])
 @pytest.mark.parametrize('R, use_rates', [(257, False), (600, True),
                                           (1500, False), (4096, False)])
-def test_postclassical_many_rlzs_quantiles(oq, R, use_rates):
-    """quantiles of 256 < R <= 4096 realizations: the CTA-cooperative sort
-    (k_postclassical_cta) against the oracle, with ties (realizations sharing
-    their gsim columns) and unequal weights"""
+def test_postclassical_many_rlzs_quantiles(oq, R, use_rates, grouping):
+    """quantiles of 256 < R <= 4096 realizations against the oracle, with
+    ties (realizations sharing their gsim columns) and unequal weights: one
+    group per realization (the CTA-cooperative sort, k_postclassical_cta) and
+    grouped (78 distinct sets of columns: the shared-memory sort path)"""
     rng = np.random.default_rng(R)
     n, m, l1, gt = 5, 2, 4, 12
     L = m * l1
@@ -248,7 +261,10 @@ def test_postclassical_many_rlzs_quantiles(oq, R, use_rates):
              ('max', 0.), ('quantile', .95), ('quantile', 1.), ('quantile', 0.)]
     imtls = {'PGA': np.logspace(-2, 0, l1), 'SA(1.0)': np.logspace(-2, 0, l1)}
     res = oq.postclassical(rates, trt_rlzs, w, imtls, names,
-                           individual_rlzs=True, use_rates=use_rates)
+                           individual_rlzs=True, use_rates=use_rates,
+                           grouping=grouping)
+    path, groups = oq.postproc.last_post_path()
+    assert (path, groups <= 78) == ((0, True) if grouping else (2, False))
     hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
     got = np.stack([x.array.reshape(n, L) for x in res['hcurves-rlzs']], -1)
     np.testing.assert_allclose(got, hc, rtol=2e-7, atol=1e-30)
@@ -260,11 +276,24 @@ def test_postclassical_many_rlzs_quantiles(oq, R, use_rates):
             np.testing.assert_allclose(got[i], mine, rtol=5e-7, atol=1e-9,
                                        err_msg='%s R=%d site %d' % (
                                            names[k], R, i))
-    if R == 4096:
+    if R == 4096 and not grouping:
         with pytest.raises(ValueError):
             oq.postclassical(np.zeros((1, L, 1), np.float32),
                              [np.arange(4097)], np.full(4097, 1 / 4097.),
-                             imtls, ['quantile-0.5'])
+                             imtls, ['quantile-0.5'], grouping=False)
+    elif R == 4096:
+        # one gsim column, any number of realizations: one group
+        R2 = 5000
+        w2 = rng.uniform(0.2, 1., R2)
+        w2 /= w2.sum()
+        r1 = (10 ** rng.uniform(-3, 0, (3, L, 1))).astype(np.float32)
+        res = oq.postclassical(r1, [np.arange(R2)], w2, imtls,
+                               ['quantile-0.5', 'mean'])
+        assert oq.postproc.last_post_path() == (0, 1)
+        exp = 1 - np.exp(-r1[:, :, 0].astype(float))
+        for k in range(2):
+            np.testing.assert_allclose(
+                res['hcurves-stats'][k].array.reshape(3, L), exp, rtol=5e-7)
 
 
 @pytest.mark.gpu
@@ -285,12 +314,16 @@ def test_postclassical_many_rlzs_imt_weights(oq):
     imtls = {imt: np.logspace(-2, 0, l1) for imt in ('PGA', 'SA(0.3)',
                                                      'SA(1.0)')}
     hc = post_np.hcurves_from_rates(rates.astype(float), trt_rlzs, R)
-    for names, kinds in (
-            (['mean', 'quantile-0.1', 'quantile-0.9', 'std'],
-             [('mean', 0.), ('quantile', .1), ('quantile', .9), ('std', 0.)]),
-            (['std', 'max', 'mean'],
-             [('std', 0.), ('max', 0.), ('mean', 0.)])):
-        res = oq.postclassical(rates, trt_rlzs, w, imtls, names)
+    cases = ((['mean', 'quantile-0.1', 'quantile-0.9', 'std'],
+              [('mean', 0.), ('quantile', .1), ('quantile', .9), ('std', 0.)]),
+             (['std', 'max', 'mean'],
+              [('std', 0.), ('max', 0.), ('mean', 0.)]))
+    for (names, kinds), grouping in itertools.product(cases, (False, True)):
+        res = oq.postclassical(rates, trt_rlzs, w, imtls, names,
+                               grouping=grouping)
+        path = oq.postproc.last_post_path()[0]
+        assert path == (0 if grouping else 2 if 'quantile-0.1' in names
+                        else 1), path
         assert 'hcurves-rlzs' not in res
         for k, (kind, q) in enumerate(kinds):
             got = res['hcurves-stats'][k].array.reshape(n, L)

@@ -53,6 +53,12 @@ def main():
         h.call('oqg_postclassical', _ptr(rates), N, L, Gt, M, _ptr(t_off),
                _ptr(t_rlz), R, _ptr(t_w), 1, ws, S, kinds, qs, 0, _ptr(t_r),
                _ptr(t_s))
+
+    def post_ungrouped():
+        # one group per realization: what R distinct sets of columns cost
+        h.call('oqg_set_post_grouping', 0)
+        post()
+        h.call('oqg_set_post_grouping', 1)
     P = 2
     t_i = _dev(np.tile(np.logspace(-2, 0.3, L1), (M, 1)), 0)
     t_p = _dev(np.array([0.1, 0.02]), 0)
@@ -76,6 +82,8 @@ def main():
         peak, src = 6650., 'fallback'
     for name, fn, nbytes in (
             ('k_postclassical', post, 4. * N * L * (Gt + R + S)),
+            ('k_postclassical_ungrouped', post_ungrouped,
+             4. * N * L * (Gt + R + S)),
             ('k_hazard_maps', hmaps, 4. * K * M * (L1 + P)),
             ('k_mean_rates', mean_rates, 4. * N * L * Gt + 8. * N * L)):
         for _ in range(3):
