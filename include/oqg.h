@@ -434,11 +434,42 @@ int oqg_cs_out(oqg_handle *h, const double *mu_dev, const double *sig_dev,
  * (mean, sig, tau, phi), within_eps_dev [M][N][E], between_eps_dev [E][M]
  * (may be NULL for modes 0 and 1), not_mmi (host) [M] (0 for MMI: not
  * exponentiated); mode 0: exp(mean); 1: exp(mean + sig * within);
- * 2: exp(mean + phi * within + tau * between); out_dev [M][N][E] */
+ * 2: exp(mean + phi * within + tau * between); 3: exp(mean + within + tau *
+ * between) with `within` the spatially correlated residuals; out_dev
+ * [M][N][E] */
 int oqg_gmf(oqg_handle *h, const float *mean_stds_dev,
             const float *within_eps_dev, const float *between_eps_dev,
             const unsigned char *not_mmi, int M, int N, int E, int mode,
             float *out_dev);
+
+/* ---- sampling side of the ground motion fields: what
+ * GmfComputer.compute_all (hazardlib/calc/gmf.py:394-474) does around
+ * _compute ----------------------------------------------------------------
+ * oqg_truncnorm_rvs: n samples of scipy.stats.truncnorm(-tl, tl).rvs(size,
+ * rng) for rng = numpy.random.default_rng(seed) (PCG64), float32 as the
+ * reference stores its epsilons (gmf.py:443-446; NoCrossCorrelation.
+ * get_inter_eps, correlation_models/cross_imt/no_cross_correlation.py:33-36).
+ * state / inc (host, [hi, lo] 64-bit words) = numpy.random.PCG64(seed)
+ * .state['state']; `offset` = how many uniforms of the stream were consumed
+ * before (the draws of one rng follow each other).  The uniforms are numpy's
+ * bit for bit; the inverse CDF is evaluated in float64 by another routine
+ * than scipy's, so a sample may differ by one float32 rounding. */
+int oqg_truncnorm_rvs(oqg_handle *h, const uint64_t *state, const uint64_t *inc,
+                      uint64_t offset, int64_t n, double truncation_level,
+                      float *out_dev);
+/* correlation matrix exp(coeff * d_ij) over the geodetic distance matrix
+ * (Mesh.get_distance_matrix, geo/mesh.py:401-429) of N sites: JB2009 with
+ * coeff = -3 / decay_range (correlation_models/spatial/jayaram_baker_2009.py
+ * :33-44).  lon / lat in degrees, out_dev [N][N] float64. */
+int oqg_corr_matrix(oqg_handle *h, const double *lon_dev, const double *lat_dev,
+                    int N, double coeff, double *out_dev);
+/* set_max_min (gmf.py:71-91) in place on gmf_dev [M][N][E] float32: values
+ * above max_iml[m] become the median exp(mean) (mean_dev [M][N] float32, MMI
+ * not exponentiated), then the (site, event) columns whose values are below
+ * min_iml[m] for every IMT are zeroed.  max_iml, min_iml, not_mmi: host. */
+int oqg_gmf_max_min(oqg_handle *h, float *gmf_dev, const float *mean_dev,
+                    const double *max_iml, const double *min_iml,
+                    const unsigned char *not_mmi, int M, int N, int E);
 
 /* ---- post-processing of the rates map -------------------
  * oqg_postclassical replaces, for all the sites at once, the loop of

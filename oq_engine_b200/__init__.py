@@ -34,7 +34,10 @@ from .cond_spectra import (  # noqa
     cond_spectra, get_cs_out, BakerJayaram2008)
 from .hazard_curve import calc_hazard_curves, classical  # noqa
 from .area import AreaSource  # noqa
-from .gmf import compute_gmf  # noqa
+from .gmf import (compute_gmf, GmfComputer,  # noqa
+                  JB2009CorrelationModel)
+from .performance import Monitor  # noqa
+from . import postproc  # noqa
 from . import sharding  # noqa
 
 __version__ = '0.1.0'

@@ -145,6 +145,14 @@ def lib():
         'oqg_last_fused_subs': (C.c_int, [H]),
         'oqg_set_site_grouping': (C.c_int, [H, C.c_int, C.c_double]),
         'oqg_set_post_grouping': (C.c_int, [H, C.c_int]),
+        'oqg_truncnorm_rvs': (C.c_int, [
+            H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64,
+            C.c_int64, C.c_double, c_void]),
+        'oqg_corr_matrix': (C.c_int, [H, c_void, c_void, C.c_int, C.c_double,
+                                      c_void]),
+        'oqg_gmf_max_min': (C.c_int, [
+            H, c_void, c_void, c_double_p, c_double_p,
+            C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int]),
         'oqg_last_post_path': (C.c_int, [H, C.POINTER(C.c_int)]),
         'oqg_set_count_evals': (C.c_int, [H, C.c_int]),
         'oqg_launch_count': (C.c_ulonglong, [H]),

@@ -24,6 +24,7 @@ from .imt import from_string
 from .gsim import GMPE, get_gsim
 from .map_array import MapArray
 from .tom import PoissonTOM
+from .performance import Monitor
 from .planar import planar_array_dt, as_flat
 
 U32 = numpy.uint32
@@ -318,9 +319,10 @@ class ContextMaker(object):
     tom = None
     cluster = 0
 
-    def __init__(self, trt, gsims, oq, device=None):
+    def __init__(self, trt, gsims, oq, device=None, monitor=None):
         param = dict(oq)
         self.trt = trt
+        self.init_monitoring(monitor or Monitor())
         self.gsims = [get_gsim(g) for g in gsims]
         for g in self.gsims:
             if not isinstance(g, GMPE):
@@ -365,6 +367,22 @@ class ContextMaker(object):
             setattr(self, 'REQUIRES_' + req, reqset)
         # validate models and IMTs now: unsupported -> error at construction
         self._structs = _gsim_structs(self.gsims, self.imts)
+
+    def init_monitoring(self, monitor):
+        """Child monitors with the reference's names (contexts.py:681-690);
+        `fused_mon` is the one-kernel path (distances + mean_std + poes +
+        map), which the reference has no name for.  With a monitor made with
+        device_sync=True the durations are device times."""
+        self.gmf_mon = monitor('computing mean_std', measuremem=False)
+        self.poe_mon = monitor('get_poes', measuremem=False)
+        self.ir_mon = monitor('iter_ruptures', measuremem=False)
+        self.sec_mon = monitor('building dparam', measuremem=False)
+        self.delta_mon = monitor('getting delta_rates', measuremem=False)
+        self.fused_mon = monitor('fused distances+mean_std+poes+map',
+                                 measuremem=False)
+        self.task_no = getattr(monitor, 'task_no', 0)
+        self.out_no = getattr(monitor, 'out_no', self.task_no)
+        self.cfactor = numpy.zeros(2)
 
     def set_imts_conv(self):
         self.imts = tuple(from_string(im) for im in self.imtls)
@@ -488,7 +506,8 @@ class ContextMaker(object):
         if isinstance(src, (fault.MeshRuptures, MultiFaultRuptures)):
             # non-planar ruptures: genctxs (contexts.py:959-1029), one
             # context per rupture
-            return fault.get_ctxs_mesh(self, src, sitecol, src_id, step)
+            with self.ir_mon:
+                return fault.get_ctxs_mesh(self, src, sitecol, src_id, step)
         vis = None
         if isinstance(src, PointSource):
             src, vis = self._planar_of_point_source(src, sitecol, src_id)
@@ -497,7 +516,8 @@ class ContextMaker(object):
                 'only planar ruptures (PlanarRuptures, PointSource) and mesh '
                 'ruptures (fault.MeshRuptures, fault.SimpleFaultSource) have '
                 'a device path')
-        return list(self._gen_ctxs_planar(src, sitecol, src_id, step, vis))
+        with self.ir_mon:
+            return list(self._gen_ctxs_planar(src, sitecol, src_id, step, vis))
 
     # distance planes pulled to the host per block of ruptures of get_ctxs
     GET_CTXS_BYTES = 256 << 20
@@ -659,8 +679,9 @@ class ContextMaker(object):
         """
         ctx = self.recarray(list(ctxs))
         h = self.handle()
-        return mean_stds_device(self.gsims, ctx, self.imts, handle=h,
-                                configure=False)
+        with self.gmf_mon:
+            return mean_stds_device(self.gsims, ctx, self.imts, handle=h,
+                                    configure=False)
 
     # --------------------------------------------------------------- poes
     def _device_poes(self, h, ctx):
@@ -670,11 +691,13 @@ class ContextMaker(object):
         dev = 'cuda:%d' % h.device
         ms = torch.empty((4, self.G, self.M, n), dtype=torch.float64,
                          device=dev)
-        st, keep = _ctx_struct(ctx, h.device)
-        h.call('oqg_mean_stds', ctypes.byref(st), n, _ptr(ms))
-        poes = torch.empty((n, self.L, self.G), dtype=torch.float32,
-                           device=dev)
-        h.call('oqg_poes', _ptr(ms), n, _ptr(poes))
+        with self.gmf_mon:     # contexts.py:1161
+            st, keep = _ctx_struct(ctx, h.device)
+            h.call('oqg_mean_stds', ctypes.byref(st), n, _ptr(ms))
+        with self.poe_mon:     # contexts.py:1171
+            poes = torch.empty((n, self.L, self.G), dtype=torch.float32,
+                               device=dev)
+            h.call('oqg_poes', _ptr(ms), n, _ptr(poes))
         return poes, ms
 
     # rows per block of gen_poes: the (n, L, G) PoEs of a block are at most
@@ -912,11 +935,13 @@ class ContextMaker(object):
         t_map = _dev(pmap.array, dev) if on_host else pmap.array
         t_cnt = torch.zeros(2, dtype=torch.int64, device='cuda:%d' % dev) \
             if count else None
-        h.call('oqg_hazard_planar_aux', _ptr(t_pla), _ptr(t_mag), _ptr(t_md),
-               _ptr(t_aux), _ptr(t_probs), K, U, ctypes.byref(st),
-               _ptr(t_sidx), N, float(self.minimum_distance),
-               0. if self.cluster else float(self.tom.time_span),
-               int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
+        with self.fused_mon:
+            h.call('oqg_hazard_planar_aux', _ptr(t_pla), _ptr(t_mag),
+                   _ptr(t_md), _ptr(t_aux), _ptr(t_probs), K, U,
+                   ctypes.byref(st), _ptr(t_sidx), N,
+                   float(self.minimum_distance),
+                   0. if self.cluster else float(self.tom.time_span),
+                   int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
         if on_host:
             pmap.array[:] = t_map.cpu().numpy()
         if count:

@@ -35,6 +35,7 @@
 #include "oqg_source.cuh"
 #include "oqg_post.cuh"
 #include "oqg_disagg.cuh"
+#include "oqg_gmf.cuh"
 
 using namespace oqg;
 
@@ -112,6 +113,9 @@ struct oqg_handle {
   // columns (oqg_set_post_grouping), the kernel path of the last call
   bool post_grouping = true;
   int last_post_path = -1, last_post_groups = 0;
+  // oqg_truncnorm_rvs: the jump table in stage[11] belongs to this increment
+  bool pcg_tab_ok = false;
+  uint64_t pcg_inc[2] = {0, 0};
 };
 
 static std::string g_create_err;
@@ -1917,12 +1921,12 @@ int oqg_gmf(oqg_handle *h, const float *ms, const float *within,
             const float *between, const unsigned char *not_mmi, int M, int N,
             int E, int mode, float *out) {
   CK(cudaSetDevice(h->device));
-  if (M < 1 || N < 0 || E < 0 || mode < 0 || mode > 2)
+  if (M < 1 || N < 0 || E < 0 || mode < 0 || mode > 3)
     return fail(h, "gmf: bad shape or mode");
   if (N == 0 || E == 0) return 0;
   if (!ms || !out || !not_mmi) return fail(h, "gmf: missing array");
   if (mode >= 1 && !within) return fail(h, "gmf: missing within epsilons");
-  if (mode == 2 && !between) return fail(h, "gmf: missing between epsilons");
+  if (mode >= 2 && !between) return fail(h, "gmf: missing between epsilons");
   if (M > 256) return fail(h, "gmf: at most 256 IMTs");
   if (reserve(h, h->stage[8], 256)) return 1;
   CK(cudaStreamSynchronize(h->stream));
@@ -1931,6 +1935,97 @@ int oqg_gmf(oqg_handle *h, const float *ms, const float *within,
   k_gmf<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
       ms, within, between, (const unsigned char *)h->stage[8].p, M, N, E, mode,
       out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- sampling side of the ground motion fields (oqg_gmf.cuh) ---------------
+typedef unsigned __int128 h128;
+static const h128 PCG_MULT =
+    ((h128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+
+// coefficients of `delta` steps of state -> mult * state + inc
+static void pcg_advance_coeffs(h128 inc, uint64_t delta, h128 &am, h128 &ap) {
+  h128 cm = PCG_MULT, cp = inc;
+  am = 1; ap = 0;
+  while (delta) {
+    if (delta & 1) { am *= cm; ap = ap * cm + cp; }
+    cp = (cm + 1) * cp;
+    cm *= cm;
+    delta >>= 1;
+  }
+}
+
+int oqg_truncnorm_rvs(oqg_handle *h, const uint64_t *state, const uint64_t *inc,
+                      uint64_t offset, int64_t n, double truncation_level,
+                      float *out) {
+  CK(cudaSetDevice(h->device));
+  if (n <= 0) return 0;
+  if (!state || !inc || !out) return fail(h, "truncnorm_rvs: missing array");
+  if (!(truncation_level > 0.)) return fail(h, "truncnorm_rvs: truncation_level must be positive");
+  const h128 vinc = ((h128)inc[0] << 64) | inc[1];
+  h128 s0 = ((h128)state[0] << 64) | state[1], am, ap;
+  pcg_advance_coeffs(vinc, offset, am, ap);
+  s0 = am * s0 + ap;
+  if (reserve(h, h->stage[11], sizeof(Pcg64Jump))) return 1;
+  if (!h->pcg_tab_ok || h->pcg_inc[0] != inc[0] || h->pcg_inc[1] != inc[1]) {
+    Pcg64Jump J;
+    h128 cm = PCG_MULT, cp = vinc;
+    for (int i = 0; i < 64; i++) {
+      J.mult_hi[i] = (uint64_t)(cm >> 64); J.mult_lo[i] = (uint64_t)cm;
+      J.plus_hi[i] = (uint64_t)(cp >> 64); J.plus_lo[i] = (uint64_t)cp;
+      cp = (cm + 1) * cp;
+      cm *= cm;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->stage[11].p, &J, sizeof(J), cudaMemcpyHostToDevice));
+    h->pcg_inc[0] = inc[0]; h->pcg_inc[1] = inc[1];
+    h->pcg_tab_ok = true;
+  }
+  const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+  pcg_advance_coeffs(vinc, (uint64_t)(blocks * 256), am, ap);
+  const double pa = 0.5 * erfc(truncation_level * M_SQRT1_2);
+  const double pb = 0.5 * erfc(-truncation_level * M_SQRT1_2);
+  k_truncnorm_rvs<<<(unsigned)blocks, 256, 0, h->stream>>>(
+      (const Pcg64Jump *)h->stage[11].p, (uint64_t)(s0 >> 64), (uint64_t)s0,
+      inc[0], inc[1], (uint64_t)(am >> 64), (uint64_t)am, (uint64_t)(ap >> 64),
+      (uint64_t)ap, n, pa, pb - pa, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_corr_matrix(oqg_handle *h, const double *lon, const double *lat, int N,
+                    double coeff, double *out) {
+  CK(cudaSetDevice(h->device));
+  if (N <= 0) return 0;
+  if (!lon || !lat || !out) return fail(h, "corr_matrix: missing array");
+  const int64_t n = (int64_t)N * N;
+  k_corr_matrix<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(lon, lat, N,
+                                                                  coeff, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oqg_gmf_max_min(oqg_handle *h, float *gmf, const float *mean,
+                    const double *max_iml, const double *min_iml,
+                    const unsigned char *not_mmi, int M, int N, int E) {
+  CK(cudaSetDevice(h->device));
+  if (M < 1 || M > 256) return fail(h, "gmf_max_min: 1 .. 256 IMTs");
+  if (N <= 0 || E <= 0) return 0;
+  if (!gmf || !mean || !max_iml || !min_iml || !not_mmi)
+    return fail(h, "gmf_max_min: missing array");
+  if (reserve(h, h->stage[8], 16 * 256 + 256)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  double *d = (double *)h->stage[8].p;
+  CK(cudaMemcpy(d, max_iml, M * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d + 256, min_iml, M * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d + 512, not_mmi, M, cudaMemcpyHostToDevice));
+  const int64_t n = (int64_t)N * E;
+  k_gmf_max_min<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+      gmf, mean, d, d + 256, (const unsigned char *)(d + 512), M, N, E);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -2064,24 +2159,27 @@ int oqg_postclassical(oqg_handle *h, const float *rates, int N, int L, int Gt,
       }
     }
     std::vector<int32_t> rank = ranks_of(gmin, D);
+    std::vector<int64_t> mpos(mrlz.size());
+    for (size_t i = 0; i < mrlz.size(); i++) mpos[i] = (int64_t)mrlz[i] * A.n_elems;
     const size_t nd = gw.size() + gmin.size();
-    const size_t ni = rank.size() + roff.size() + moff.size() + rgs.size() + mrlz.size();
-    if (reserve(h, h->stage[10], nd * 8 + ni * 4 + 16)) return 1;
+    const size_t ni = rank.size() + roff.size() + moff.size() + rgs.size();
+    if (reserve(h, h->stage[10], (nd + mpos.size()) * 8 + ni * 4 + 16)) return 1;
     double *dd = (double *)h->stage[10].p;
-    int32_t *di = (int32_t *)(dd + nd);
+    int64_t *dl = (int64_t *)(dd + nd);
+    int32_t *di = (int32_t *)(dl + mpos.size());
     std::vector<int32_t> ints;
     ints.insert(ints.end(), rank.begin(), rank.end());
     ints.insert(ints.end(), roff.begin(), roff.end());
     ints.insert(ints.end(), moff.begin(), moff.end());
     ints.insert(ints.end(), rgs.begin(), rgs.end());
-    ints.insert(ints.end(), mrlz.begin(), mrlz.end());
     std::vector<double> dbl(gw);
     dbl.insert(dbl.end(), gmin.begin(), gmin.end());
     CK(cudaMemcpy(dd, dbl.data(), nd * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dl, mpos.data(), mpos.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(di, ints.data(), ni * 4, cudaMemcpyHostToDevice));
-    B.weights = dd; B.wmin = dd + gw.size();
+    B.weights = dd; B.wmin = dd + gw.size(); B.m_pos = dl;
     B.wrank = di; B.r_off = di + rank.size(); B.m_off = B.r_off + roff.size();
-    B.r_gs = B.m_off + moff.size(); B.m_rlz = B.r_gs + rgs.size();
+    B.r_gs = B.m_off + moff.size();
     B.R = D;
     // the quantiles in increasing order: one scan of the sorted groups
     std::vector<int> qord;

@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(256) k_cs_out(const CsArgs A) {
 //   mode 0  both truncation levels zero: exp(mean)
 //   mode 1  gsim with total standard deviation only: exp(mean + sig * eps)
 //   mode 2  exp(mean + phi * within_eps + tau * between_eps)
+//   mode 3  exp(mean + within_res + tau * between_eps), within_res the
+//           residuals after SpatialCorrelationModel.apply_correlation
 namespace oqg {
 
 __global__ void k_gmf(const float *__restrict__ ms,      // [4][M][N]
@@ -209,6 +211,9 @@ __global__ void k_gmf(const float *__restrict__ ms,      // [4][M][N]
   } else if (mode == 2) {
     // (mean + within_res) + between_res, each product rounded to float32
     v = (v + ms[3 * MN + mn] * within[t]) + ms[2 * MN + mn] * between[e * M + m];
+  } else if (mode == 3) {
+    // `within` holds the spatially correlated within-event residuals
+    v = (v + within[t]) + ms[2 * MN + mn] * between[e * M + m];
   }
   out[t] = not_mmi[m] ? expf(v) : v;
 }

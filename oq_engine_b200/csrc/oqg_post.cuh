@@ -175,8 +175,8 @@ struct PostRegArgs {
   const int32_t *wrank;    // [W][R] rank of the weight (of w_d) among them
   // register path only (R = the number of groups D there)
   const double *wmin;      // [W][D] smallest weight of the group
-  const int32_t *m_off;    // [D + 1] realizations of each group
-  const int32_t *m_rlz;
+  const int32_t *m_off;    // [D + 1] realizations of each group, as the
+  const int64_t *m_pos;    // element offsets r * n_elems of their curves
   int nq;                  // quantiles in increasing order and their statistic
   int qstat[OQG_SMAX];
   double qsorted[OQG_SMAX];
@@ -238,16 +238,14 @@ k_postclassical_reg(const PostRegArgs A) {
   // wrank [W][D], r_off [D + 1], m_off [D + 1], r_gs, rates [TPB][Gt | 1]
   const int R = A.R, WR = A.W * R;
   unsigned long long *s_key = (unsigned long long *)sm_post + threadIdx.x;
-  double *s_w = sm_post + RP * TPB;
-  double *s_wmin = s_w + WR;
-  int *s_rank = (int *)(s_wmin + WR);
+  double2 *s_ww = (double2 *)(sm_post + RP * TPB);   // (W_d, w_d)
+  int *s_rank = (int *)(s_ww + WR);
   int *s_off = s_rank + WR;
   int *s_moff = s_off + R + 1;
   int *s_gs = s_moff + R + 1;
   const int64_t e0 = blockIdx.x * (int64_t)blockDim.x;
   for (int i = threadIdx.x; i < WR; i += blockDim.x) {
-    s_w[i] = A.weights[i];
-    s_wmin[i] = A.wmin[i];
+    s_ww[i] = make_double2(A.weights[i], A.wmin[i]);
     s_rank[i] = A.wrank[i];
   }
   for (int i = threadIdx.x; i <= R; i += blockDim.x) {
@@ -264,9 +262,14 @@ k_postclassical_reg(const PostRegArgs A) {
   {
     const int64_t base = e0 * A.Gt;
     const int64_t lim = min((int64_t)blockDim.x, A.n_elems - e0) * A.Gt;
-    for (int64_t i = threadIdx.x; i < lim; i += blockDim.x) {
-      const int t = (int)(i / A.Gt), g = (int)(i - (int64_t)t * A.Gt);
+    // (row, column) of element i advanced without a division
+    const int dt = TPB / A.Gt, dg = TPB - dt * A.Gt;
+    int t = threadIdx.x / A.Gt, g = threadIdx.x - t * A.Gt;
+    for (int i = threadIdx.x; i < (int)lim; i += TPB) {
       s_rates[t * gstride + g] = A.rates[base + i];
+      t += dt;
+      g += dg;
+      if (g >= A.Gt) { g -= A.Gt; t++; }
     }
   }
   __syncthreads();
@@ -274,30 +277,33 @@ k_postclassical_reg(const PostRegArgs A) {
   if (e >= A.n_elems) return;
   const int l = (int)(e % A.L);
   const int wcol = A.W > 1 ? l / A.L1 : 0;
-  const double *w = s_w + wcol * R;
-  const double *wm = s_wmin + wcol * R;
+  const double2 *ww = s_ww + wcol * R;
   const int *rk = s_rank + wcol * R;
   const double wsum = A.wsum[wcol];
   const float *row = s_rates + threadIdx.x * gstride;
   const bool stats = A.stat_out && A.S > 0 && wsum != 0.;
   double sw1 = 0., sw2 = 0., v0 = 0., vmax = 0.;
+  float *const out_e = A.rlz_out ? A.rlz_out + e : nullptr;
+  int kc = 0, km = 0;      // running positions in the column / member lists
 #pragma unroll 1
   for (int r = 0; r < R; r++) {
     double x = 0.;
-    for (int k = s_off[r]; k < s_off[r + 1]; k++) x += (double)row[s_gs[k]];
+    for (const int kend = s_off[r + 1]; kc < kend; kc++)
+      x += (double)row[s_gs[kc]];
     double v = 1. - fast_exp(fmax(-x, -700.));   // to_probs
-    if (A.rlz_out) {
-      // the curve of every realization of the group (uniform addresses)
+    if (out_e) {
+      // the curve of every realization of the group (uniform offsets)
       const float vf = (float)v;
-      for (int k = s_moff[r]; k < s_moff[r + 1]; k++)
-        A.rlz_out[(int64_t)__ldg(A.m_rlz + k) * A.n_elems + e] = vf;
+      for (const int mend = s_moff[r + 1]; km < mend; km++)
+        out_e[__ldg(A.m_pos + km)] = vf;
     }
     if (A.use_rates) v = to_rate(v);
     if (r == 0) v0 = v;
     vmax = fmax(vmax, v);                       // probabilities, rates: >= 0
     const double d = v - v0;
-    sw1 = fma(w[r], d, sw1);
-    sw2 = fma(w[r] * d, d, sw2);
+    const double wr = ww[r].x;
+    sw1 = fma(wr, d, sw1);
+    sw2 = fma(wr * d, d, sw2);
     s_key[r * TPB] = post_key<IB>(v, rk[r], r);
   }
   if (A.stat_out && A.S > 0 && wsum == 0.) {   // getters.py:61-63
@@ -368,7 +374,8 @@ k_postclassical_reg(const PostRegArgs A) {
     const unsigned long long kj = s_key[j * TPB];
     const double vk = post_key_value<IB>(kj);
     const int g = (int)(kj & ((1u << IB) - 1));
-    const double c1 = cum + wm[g], c2 = cum + w[g];
+    const double2 wg = ww[g];
+    const double c1 = cum + wg.y, c2 = cum + wg.x;
     while (qi < A.nq) {
       const double q = A.qsorted[qi];
       double res;
@@ -715,9 +722,16 @@ k_hazard_maps(const float *__restrict__ curves, int64_t rows_total, int M,
     s_p[P + i] = log(poes[i]);
   }
   const float *src = curves + r0 * L1;
-  for (int i = threadIdx.x; i < nr * L1; i += HM_TPB) {
-    const int r = i / L1;
-    s_c[r * stride + (i - r * L1)] = src[i];
+  {
+    // (row, level) of element i advanced without a division
+    const int dr = HM_TPB / L1, dl = HM_TPB - dr * L1;
+    int r = threadIdx.x / L1, l = threadIdx.x - r * L1;
+    for (int i = threadIdx.x; i < nr * L1; i += HM_TPB) {
+      s_c[r * stride + l] = src[i];
+      r += dr;
+      l += dl;
+      if (l >= L1) { l -= L1; r++; }
+    }
   }
   __syncthreads();
   const int r = threadIdx.x;
@@ -736,10 +750,15 @@ k_hazard_maps(const float *__restrict__ curves, int64_t rows_total, int M,
       if (poe < CV(0)) {
         res = exp(li[L1 - 1]);
       } else {
-        // numpy.interp: the last j with x[j] <= lp
+        // numpy.interp: the last j with x[j] <= lp.  For a float32 value c,
+        // max(c, EPSILON) <= poe is c <= pf with pf the largest float32 not
+        // above poe (and EPSILON <= poe): a float32 comparison per level
         int j = 0;
-        for (int t = 1; t < L1; t++)
-          if (CV(t) <= poe) j = t;
+        if (EPS <= poe) {
+          const float pf = __double2float_rd(poe);
+          for (int t = 1; t < L1; t++)
+            if (c[L1 - 1 - t] <= pf) j = t;
+        }
         const double y0 = li[L1 - 1 - j];
         if (j == L1 - 1) {
           res = exp(y0);

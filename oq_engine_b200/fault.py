@@ -526,11 +526,12 @@ def hazard_mesh(cmaker, pmap, rups, sitecol, count=False):
         t_rp = _dev(rp, dev)
         ptrs = (ctypes.c_void_p * 6)(*[
             planes[n].data_ptr() if n in planes else None for n in order])
-        h.call('oqg_hazard_dist', _ptr(t_rp), ptrs, _ptr(t_probs), K, len(r),
-               ctypes.byref(st), _ptr(t_sidx), N,
-               float(cmaker.minimum_distance),
-               0. if cmaker.cluster else float(tom.time_span),
-               int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
+        with cmaker.fused_mon:
+            h.call('oqg_hazard_dist', _ptr(t_rp), ptrs, _ptr(t_probs), K,
+                   len(r), ctypes.byref(st), _ptr(t_sidx), N,
+                   float(cmaker.minimum_distance),
+                   0. if cmaker.cluster else float(tom.time_span),
+                   int(pmap.rates), _ptr(t_map), _ptr(t_cnt))
         torch.cuda.current_stream(dev).synchronize()
     if on_host:
         pmap.array[:] = t_map.cpu().numpy()

@@ -25,6 +25,9 @@ class GMPE(object):
     REQUIRES_DISTANCES = frozenset()
     REQUIRES_RUPTURE_PARAMETERS = frozenset()
     REQUIRES_SITES_PARAMETERS = frozenset()
+    # the reference's StdDev constants (const.py) as strings
+    DEFINED_FOR_STANDARD_DEVIATION_TYPES = frozenset(
+        {'Total', 'Inter event', 'Intra event'})
     family = None
     tables = {}   # prefix -> table name; '' is the main table
 
@@ -238,6 +241,7 @@ class AtkinsonBoore2006(GMPE):
     REQUIRES_DISTANCES = frozenset({'rrup'})
     REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag'})
     REQUIRES_SITES_PARAMETERS = frozenset({'vs30'})
+    DEFINED_FOR_STANDARD_DEVIATION_TYPES = frozenset({'Total'})
     family = 'AB06'
     tables = {'bc_': 'AB06_BC', 'hr_': 'AB06_HARD_ROCK',
               'st_': 'AB06_STRESS', 'so_': 'AB06_SOIL_RESPONSE'}
@@ -325,6 +329,7 @@ class ToroEtAl2002(_PlainGMPE):
     REQUIRES_DISTANCES = frozenset({'rjb'})
     REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag'})
     REQUIRES_SITES_PARAMETERS = frozenset()
+    DEFINED_FOR_STANDARD_DEVIATION_TYPES = frozenset({'Total'})
     family = 'TORO02'
     tables = {'': 'TORO02'}
 
@@ -335,6 +340,7 @@ class Campbell2003(_PlainGMPE):
     REQUIRES_DISTANCES = frozenset({'rrup'})
     REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag'})
     REQUIRES_SITES_PARAMETERS = frozenset()
+    DEFINED_FOR_STANDARD_DEVIATION_TYPES = frozenset({'Total'})
     family = 'C03'
     tables = {'': 'C03'}
 

@@ -393,7 +393,9 @@ def rupture_planes(cmaker, rups, sitecol, names, cache=None):
     if bad:
         raise NotImplementedError('distances %s of multi-fault ruptures'
                                   % sorted(bad))
-    cache = cache or section_planes(cmaker, rups, sitecol, names)
+    if not cache:
+        with cmaker.sec_mon:      # 'building dparam', contexts.py:1073
+            cache = section_planes(cmaker, rups, sitecol, names)
     U, N, S = len(rups), len(sitecol), len(rups.sections)
     roff = numpy.concatenate([[0], numpy.cumsum(
         [len(o) for o in rups.order])]).astype(numpy.int64)

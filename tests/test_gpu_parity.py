@@ -497,6 +497,13 @@ def test_map_on_device_and_sidx(oq):
         cm.hazard_planar(half, oq.contexts.PlanarRuptures(
             pla[sl], r['mag'][sl]), sc)
     np.testing.assert_allclose(half.array, full.array, rtol=1e-6)
+    # the monitors: one fused pass per hazard_planar call so far; the unfused
+    # operators count under the reference's names (contexts.py:1161, 1171)
+    assert cm.fused_mon.counts == 5 and cm.fused_mon.duration > 0
+    ctxs = cm.get_ctxs(src, sc)
+    cm.get_pmap(cm.recarray(ctxs))
+    assert cm.ir_mon.counts == 1
+    assert cm.gmf_mon.counts == 1 and cm.poe_mon.counts == 1
 
 
 def test_fast_poe_table_vs_exact(oq):

@@ -224,3 +224,27 @@ def test_site_tiles():
     blocks = [oq.sharding.site_tile(sc, k, 3, 'block') for k in range(3)]
     np.testing.assert_array_equal(blocks[0].sids, [0, 1, 2])
     assert oq.sharding.groups_of(1, 4, 8) == [1, 5]
+
+
+def test_monitors_have_the_reference_names():
+    """init_monitoring (contexts.py:681-690): the child monitors the
+    reference's calculators read, created under the monitor passed in"""
+    mon = oq.Monitor('classical')
+    mon.task_no = 7
+    cm = oq.ContextMaker('*', [oq.BooreEtAl2014()], dict(
+        imtls={'PGA': [.1, .2]}, truncation_level=3.), monitor=mon)
+    ops = [c.operation for c in mon.children]
+    assert ops[:5] == ['computing mean_std', 'get_poes', 'iter_ruptures',
+                       'building dparam', 'getting delta_rates']
+    assert cm.gmf_mon is mon.children[0] and cm.poe_mon is mon.children[1]
+    assert cm.task_no == 7 and cm.out_no == 7
+    with cm.poe_mon:
+        pass
+    with cm.poe_mon:
+        pass
+    assert cm.poe_mon.counts == 2 and cm.poe_mon.duration >= 0
+    assert mon.get_data() == [('get_poes', cm.poe_mon.duration, 2)]
+    # a ContextMaker made without a monitor has its own
+    cm2 = oq.ContextMaker('*', [oq.BooreEtAl2014()], dict(
+        imtls={'PGA': [.1, .2]}, truncation_level=3.))
+    assert cm2.gmf_mon.operation == 'computing mean_std'
