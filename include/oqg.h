@@ -253,6 +253,23 @@ int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
                            int rates_mode, float *map,
                            unsigned long long *pairs_kept);
 
+/* A stream of sources from host memory into one map (the reference's loop
+ * `for src in sources: cmaker.update(pmap, ctxs)`, hazardlib/contexts.py
+ * :1548-1579): oqg_host_begin uploads the sites and the map once (map NULL:
+ * the identity, 1 for a map of probabilities of no exceedance, 0 for rates),
+ * oqg_host_add folds the ruptures of one source -- the arguments of
+ * oqg_hazard_planar_host -- with its upload overlapping the kernels of the
+ * previous source (two device slots, a copy stream); it returns when the
+ * caller's buffers can be reused, not when the kernels are done.
+ * oqg_host_end downloads the map (and the number of pairs kept, may be NULL)
+ * and synchronises.  One session per handle at a time. */
+int oqg_host_begin(oqg_handle *h, const oqg_sites *sites, int N, int rates_mode,
+                   const float *map);
+int oqg_host_add(oqg_handle *h, const double *planar, const double *mag,
+                 const double *magdist, const double *probs, int K, int U,
+                 double mindist, double itime);
+int oqg_host_end(oqg_handle *h, float *map, unsigned long long *pairs_kept);
+
 /* ---- rupture generation of point sources on the device --
  * replaces PointSource.get_planar / get_planin (source/point.py:192-289) and
  * build_planar / _build_corners (geo/surface/planar.py:107-251) for a batch

@@ -85,6 +85,11 @@ def lib():
             H, c_void, c_void, c_void, c_void, C.c_int, C.c_int,
             C.POINTER(OqgSites), C.c_int, C.c_double, C.c_double, C.c_int,
             c_void, C.POINTER(C.c_ulonglong)]),
+        'oqg_host_begin': (C.c_int, [H, C.POINTER(OqgSites), C.c_int,
+                                     C.c_int, c_void]),
+        'oqg_host_add': (C.c_int, [H, c_void, c_void, c_void, c_void,
+                                   C.c_int, C.c_int, C.c_double, C.c_double]),
+        'oqg_host_end': (C.c_int, [H, c_void, C.POINTER(C.c_ulonglong)]),
         'oqg_point_ruptures': (C.c_int, [H, c_void, C.c_int, C.c_int64,
                                          c_void, c_void, c_void, c_void]),
         'oqg_fused_planar': (C.c_int, [

@@ -113,6 +113,13 @@ struct oqg_handle {
   // columns (oqg_set_post_grouping), the kernel path of the last call
   bool post_grouping = true;
   int last_post_path = -1, last_post_groups = 0;
+  // oqg_host_begin / add / end: sites and map resident, two rupture slots
+  Buf hs_site[7], hs_map, hs_slot[2][4];
+  cudaStream_t hs_copy = nullptr;
+  cudaEvent_t hs_copied[2], hs_used[2];
+  bool hs_rec[2] = {false, false}, hs_open = false;
+  int hs_N = 0, hs_rates = 0, hs_n = 0;
+  oqg_sites hs_sd;
   // oqg_truncnorm_rvs: the jump table in stage[11] belongs to this increment
   bool pcg_tab_ok = false;
   uint64_t pcg_inc[2] = {0, 0};
@@ -1376,6 +1383,16 @@ void oqg_destroy(oqg_handle *h) {
                  &h->sg_par[3], &h->sg_sidx})
     if (b->p) cudaFree(b->p);
   for (auto &b : h->stage) if (b.p) cudaFree(b.p);
+  for (auto &b : h->hs_site) if (b.p) cudaFree(b.p);
+  for (auto &sl : h->hs_slot) for (auto &b : sl) if (b.p) cudaFree(b.p);
+  if (h->hs_map.p) cudaFree(h->hs_map.p);
+  if (h->hs_copy) {
+    cudaStreamDestroy(h->hs_copy);
+    for (int i = 0; i < 2; i++) {
+      cudaEventDestroy(h->hs_copied[i]);
+      cudaEventDestroy(h->hs_used[i]);
+    }
+  }
   if (h->flag_dev) cudaFree(h->flag_dev);
   for (auto &ev : h->ev) cudaEventDestroy(ev);
   {
@@ -2932,6 +2949,114 @@ int oqg_hazard_planar_host(oqg_handle *h, const double *planar,
   CK(cudaMemcpyAsync(map, map_dev, mbytes, cudaMemcpyDeviceToHost, h->stream));
   if (pairs_kept)
     CK(cudaMemcpyAsync(pairs_kept, cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+__global__ void k_fill_f32(float *p, size_t n, float v) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- a stream of sources from host memory: begin / add / end ----------------
+// oqg_hazard_planar_host pays, per call, the upload of the sites and of the
+// map, the download of the map and a synchronisation.  For a loop over many
+// small sources (the reference's `for src in sources: cmaker.update(pmap,
+// ...)`, contexts.py:1548-1579) the session keeps sites and map on the device
+// and double-buffers the ruptures: the copy of source k + 1 (copy stream)
+// overlaps the kernels of source k (compute stream); `add` returns as soon
+// as ITS copy is done -- the caller may then reuse its buffers -- not when
+// the kernels are.
+int oqg_host_begin(oqg_handle *h, const oqg_sites *s, int N, int rates_mode,
+                   const float *map) {
+  CK(cudaSetDevice(h->device));
+  if (!h->G || !h->L1) return fail(h, "set_gsims / set_levels not called");
+  if (h->hs_open) return fail(h, "host_begin: a session is already open");
+  if (!s || N <= 0) return fail(h, "host_begin: no sites");
+  if (!h->hs_copy) {
+    CK(cudaStreamCreateWithFlags(&h->hs_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&h->hs_copied[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->hs_used[i], cudaEventDisableTiming));
+    }
+  }
+  const void *d[7];
+  if (h2d(h, h->hs_site[0], s->lon, (size_t)N * 8, &d[0])) return 1;
+  if (h2d(h, h->hs_site[1], s->lat, (size_t)N * 8, &d[1])) return 1;
+  if (h2d(h, h->hs_site[2], s->depth, (size_t)N * 8, &d[2])) return 1;
+  if (h2d(h, h->hs_site[3], s->vs30, (size_t)N * 8, &d[3])) return 1;
+  if (h2d(h, h->hs_site[4], s->z1pt0, (size_t)N * 8, &d[4])) return 1;
+  if (h2d(h, h->hs_site[5], s->z2pt5, (size_t)N * 8, &d[5])) return 1;
+  if (h2d(h, h->hs_site[6], s->vs30measured, (size_t)N, &d[6])) return 1;
+  h->hs_sd.lon = (const double *)d[0]; h->hs_sd.lat = (const double *)d[1];
+  h->hs_sd.depth = (const double *)d[2]; h->hs_sd.vs30 = (const double *)d[3];
+  h->hs_sd.z1pt0 = (const double *)d[4]; h->hs_sd.z2pt5 = (const double *)d[5];
+  h->hs_sd.vs30measured = (const uint8_t *)d[6];
+  const size_t n = (size_t)N * h->M * h->L1 * h->G, mbytes = n * 4;
+  if (reserve(h, h->hs_map, mbytes + 16)) return 1;
+  float *map_dev = (float *)h->hs_map.p;
+  if (map) {
+    CK(cudaMemcpyAsync(map_dev, map, mbytes, cudaMemcpyHostToDevice, h->stream));
+  } else if (rates_mode) {
+    CK(cudaMemsetAsync(map_dev, 0, mbytes, h->stream));
+  } else {
+    k_fill_f32<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(map_dev, n, 1.f);
+    h->launches++;
+  }
+  CK(cudaMemsetAsync((char *)h->hs_map.p + (mbytes + 7) / 8 * 8, 0, 8, h->stream));
+  h->hs_N = N; h->hs_rates = rates_mode; h->hs_n = 0; h->hs_open = true;
+  h->hs_rec[0] = h->hs_rec[1] = false;
+  return 0;
+}
+
+int oqg_host_add(oqg_handle *h, const double *planar, const double *mag,
+                 const double *magdist, const double *probs, int K, int U,
+                 double mindist, double itime) {
+  CK(cudaSetDevice(h->device));
+  if (!h->hs_open) return fail(h, "host_add: no open session");
+  if (U <= 0) return 0;
+  if (!planar || !mag || !magdist) return fail(h, "host_add: missing array");
+  if (K && !probs) return fail(h, "probs_occur missing");
+  const int slot = h->hs_n++ & 1;
+  Buf *b = h->hs_slot[slot];
+  // the kernels that read this slot two calls ago must be done
+  if (h->hs_rec[slot]) CK(cudaStreamWaitEvent(h->hs_copy, h->hs_used[slot], 0));
+  const void *src[4] = {planar, mag, magdist, K ? probs : nullptr};
+  const size_t nb[4] = {(size_t)U * OQG_PLANAR_LEN * 8, (size_t)U * 8,
+                        (size_t)U * 8, (size_t)U * K * 8};
+  for (int i = 0; i < 4; i++) {
+    if (!src[i]) continue;
+    if (reserve(h, b[i], nb[i])) return 1;
+    CK(cudaMemcpyAsync(b[i].p, src[i], nb[i], cudaMemcpyHostToDevice, h->hs_copy));
+  }
+  CK(cudaEventRecord(h->hs_copied[slot], h->hs_copy));
+  CK(cudaStreamWaitEvent(h->stream, h->hs_copied[slot], 0));
+  const size_t mbytes = (size_t)h->hs_N * h->M * h->L1 * h->G * 4;
+  unsigned long long *cnt =
+      (unsigned long long *)((char *)h->hs_map.p + (mbytes + 7) / 8 * 8);
+  if (hazard_fused(h, (const double *)b[0].p, (const double *)b[1].p,
+                   (const double *)b[2].p, nullptr, nullptr, nullptr,
+                   K ? (const double *)b[3].p : nullptr, K, U, &h->hs_sd,
+                   nullptr, h->hs_N, mindist, itime, h->hs_rates,
+                   (float *)h->hs_map.p, cnt))
+    return 1;
+  CK(cudaEventRecord(h->hs_used[slot], h->stream));
+  h->hs_rec[slot] = true;
+  // the caller's buffers are free again once the copy is done
+  CK(cudaEventSynchronize(h->hs_copied[slot]));
+  return 0;
+}
+
+int oqg_host_end(oqg_handle *h, float *map, unsigned long long *pairs_kept) {
+  CK(cudaSetDevice(h->device));
+  if (!h->hs_open) return fail(h, "host_end: no open session");
+  h->hs_open = false;
+  const size_t mbytes = (size_t)h->hs_N * h->M * h->L1 * h->G * 4;
+  if (map)
+    CK(cudaMemcpyAsync(map, h->hs_map.p, mbytes, cudaMemcpyDeviceToHost, h->stream));
+  if (pairs_kept)
+    CK(cudaMemcpyAsync(pairs_kept, (char *)h->hs_map.p + (mbytes + 7) / 8 * 8, 8,
+                       cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

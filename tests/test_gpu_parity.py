@@ -433,6 +433,37 @@ def test_fused_host_entry_point(oq):
            out.ctypes.data, ctypes.byref(kept))
     assert kept.value == U * N
     np.testing.assert_array_equal(out, pmap.array)
+    # the same ruptures as a stream of 5 sources through one session
+    # (oqg_host_begin / add / end: sites and map stay on the device, the
+    # uploads are double-buffered): the calls one after the other on a map
+    # kept by the caller give the same bits
+    one = np.ones((N, cm.L, cm.G), np.float32)
+    cuts = [0, 7, 40, 41, 90, U]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        h.call('oqg_hazard_planar_host', flat[a:].ctypes.data,
+               mag[a:].ctypes.data, md[a:].ctypes.data, None, 0, b - a,
+               ctypes.byref(st), N, 0., 50., 0, one.ctypes.data, None)
+    for init in (None, np.ones((N, cm.L, cm.G), np.float32)):
+        h.call('oqg_host_begin', ctypes.byref(st), N, 0,
+               None if init is None else init.ctypes.data)
+        with pytest.raises(RuntimeError):
+            h.call('oqg_host_begin', ctypes.byref(st), N, 0, None)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            # a fresh copy per call, dropped right after: `add` returns when
+            # the caller's buffers can be reused
+            f, m, d = flat[a:b].copy(), mag[a:b].copy(), md[a:b].copy()
+            h.call('oqg_host_add', f.ctypes.data, m.ctypes.data,
+                   d.ctypes.data, None, 0, b - a, 0., 50.)
+            f[:] = m[:] = d[:] = np.nan
+        got = np.zeros((N, cm.L, cm.G), np.float32)
+        kept = ctypes.c_ulonglong(0)
+        h.call('oqg_host_end', got.ctypes.data, ctypes.byref(kept))
+        assert kept.value == U * N
+        np.testing.assert_array_equal(got, one)
+    np.testing.assert_allclose(one, pmap.array, rtol=2e-6)
+    with pytest.raises(RuntimeError):
+        h.call('oqg_host_add', flat.ctypes.data, mag.ctypes.data,
+               md.ctypes.data, None, 0, U, 0., 50.)
 
 
 def test_fused_negbin_vs_oracle(oq):
