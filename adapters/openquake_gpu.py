@@ -129,9 +129,9 @@ def _spec_akkar(kind):
     return spec
 
 
-def _spec_plain(family):
+def _spec_plain(family, flags=0):
     def spec(g):
-        return family, 0, [0., 0., 0., 0.]
+        return family, flags, [0., 0., 0., 0.]
     return spec
 
 
@@ -153,6 +153,8 @@ SUPPORTED = {
     'ChiouYoungs2008': (_spec_plain('CY08'), {'': 'COEFFS'}),
     'ToroEtAl2002': (_spec_plain('TORO02'), {'': 'COEFFS'}),
     'Campbell2003': (_spec_plain('C03'), {'': 'COEFFS'}),
+    'ToroEtAl2002SHARE': (_spec_plain('TORO02', 1), {'': 'COEFFS'}),
+    'Campbell2003SHARE': (_spec_plain('C03', 1), {'': 'COEFFS'}),
 }
 
 
@@ -177,10 +179,33 @@ def _table(gsim, attr):
     return getattr(gsim, attr)
 
 
-def _extra_fields(family, imt):
+def _share_fields(gsim, imt):
+    """The SHARE adjustment of ToroEtAl2002SHARE / Campbell2003SHARE
+    (toro_2002.py:134-142, campbell_2003.py:236-245): the faulting style term
+    of the three rake classes from the class's own COEFFS_FS_ROCK / CONSTS_FS,
+    zeros for the base classes"""
+    family = SUPPORTED[gsim.__class__.__name__][0](gsim)[0]
+    names = (('adj_ss', 'adj_rv', 'adj_nm') if family == 'TORO02'
+             else ('fs_ss', 'fs_rv', 'fs_nm', 'afrock'))
+    if not getattr(gsim, 'CONSTS_FS', None):
+        return dict.fromkeys(names, 0.)
+    from openquake.hazardlib.gsim.campbell_2003 import (
+        _compute_faulting_style_term)
+    C, K = gsim.COEFFS_FS_ROCK[imt], gsim.CONSTS_FS
+    # one rake per class: strike slip / other, reverse, normal
+    terms = _compute_faulting_style_term(
+        C['Frss'], K['pR'], K['Fnss'], K['pN'], numpy.array([0., 90., -90.]))
+    if family == 'TORO02':
+        return dict(zip(names, terms * C['AFrock']))
+    return dict(zip(names, list(terms) + [C['AFrock']]))
+
+
+def _extra_fields(family, imt, gsim=None):
     """The non-tabulated fields of a device coefficient row"""
     t = imt.period
     out = {'period': t}
+    if family in ('TORO02', 'C03') and gsim is not None:
+        out.update(_share_fields(gsim, imt))
     if family == 'ASK14':
         # _get_v1, abrahamson_2014.py:345-365
         if imt.string.startswith('SA') and t > 0.5:
@@ -205,7 +230,7 @@ def coeff_row(gsim, imt):
     if family == 'CB14' and imt.string in ('CAV', 'IA'):
         raise KeyError('%s has no device implementation' % imt.string)
     tables = SUPPORTED[gsim.__class__.__name__][1]
-    extra = _extra_fields(family, imt)
+    extra = _extra_fields(family, imt, gsim)
     recs = {}
     out = []
     for name in _lib.family_fields(family):

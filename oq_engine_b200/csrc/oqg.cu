@@ -2505,6 +2505,7 @@ static const char *missing_column(const oqg_gsim &g, const oqg_ctx *c) {
   const bool plain = f == OQG_TORO02 || f == OQG_C03;   // mag + one distance
   if (!plain && !c->vs30) return "vs30";
   if (f != OQG_AB06 && !plain && !c->rake) return "rake";
+  if (plain && (g.flags & 1) && !c->rake) return "rake";   // SHARE variants
   if (f == OQG_CY14 || f == OQG_ASK14 || f == OQG_CB14 || f == OQG_CY08) {
     if (!c->dip) return "dip";
     if (!c->ztor) return "ztor";

@@ -82,10 +82,10 @@ struct Out {
   X(sig1) X(sig2) X(sig3) X(sig4) X(period)
 #define TORO02_FIELDS(X)                                                     \
   X(c1) X(c2) X(c3) X(c4) X(c5) X(c6) X(c7) X(m50) X(m55) X(m80) X(r5)       \
-  X(r20) X(period)
+  X(r20) X(period) X(adj_ss) X(adj_rv) X(adj_nm)
 #define C03_FIELDS(X)                                                        \
   X(c1) X(c2) X(c3) X(c4) X(c5) X(c6) X(c7) X(c8) X(c9) X(c10) X(c11)        \
-  X(c12) X(c13) X(period)
+  X(c12) X(c13) X(period) X(fs_ss) X(fs_rv) X(fs_nm) X(afrock)
 
 struct Bssa14C { BSSA14_FIELDS(OQG_DECL) };
 struct Cy14C { CY14_FIELDS(OQG_DECL) };
@@ -859,7 +859,16 @@ __device__ __forceinline__ double np_interp3(double x, double x0, double x1,
   return (y2 - y1) / (x2 - x1) * (x - x1) + y1;
 }
 
-__device__ __forceinline__ Out toro02_imt(const oqg_gsim &, const Toro02C &C,
+// _compute_faulting_style_term, campbell_2003.py:272-281: the value of the
+// rake class (reverse (30, 150], normal (-120, -60], otherwise strike slip)
+__device__ __forceinline__ double share_pick(double rake, double ss, double rv,
+                                             double nm) {
+  if (rake > 30.0 && rake <= 150.0) return rv;
+  if (rake > -120.0 && rake <= -60.0) return nm;
+  return ss;
+}
+
+__device__ __forceinline__ Out toro02_imt(const oqg_gsim &g, const Toro02C &C,
                                           const Row &r) {
   // toro_2002.py:31-57
   const double md = r.mag - 6.;
@@ -881,13 +890,19 @@ __device__ __forceinline__ Out toro02_imt(const oqg_gsim &, const Toro02C &C,
   o.sig = sqrt(ale * ale + epi * epi);
   if (C.period == 3.0) o.mean /= 0.612;
   if (C.period == 4.0) o.mean /= 0.559;
+  if (g.flags & 1) {
+    // ToroEtAl2002SHARE, toro_2002.py:134-142: style of faulting and rock
+    // adjustment, log(exp(mean) * (term(rake) * AFrock)); the three products
+    // come with the coefficient row (adj_*)
+    o.mean = log(exp(o.mean) * share_pick(r.rake, C.adj_ss, C.adj_rv, C.adj_nm));
+  }
   o.tau = 0.;
   o.phi = 0.;
   return o;
 }
 
 // ====================================================================== C03
-__device__ __forceinline__ Out c03_imt(const oqg_gsim &, const C03C &C,
+__device__ __forceinline__ Out c03_imt(const oqg_gsim &g, const C03C &C,
                                        const Row &r) {
   // campbell_2003.py:39-47, 71-106 (kind "base")
   const double term1 = (C.c2 * r.mag) + C.c3 * ((8.5 - r.mag) * (8.5 - r.mag));
@@ -902,6 +917,9 @@ __device__ __forceinline__ Out c03_imt(const oqg_gsim &, const C03C &C,
   Out o;
   o.mean = C.c1 + term1 + term2 + f3;
   o.sig = r.mag < 7.16 ? C.c11 + C.c12 * r.mag : C.c13;
+  if (g.flags & 1)   // Campbell2003SHARE, campbell_2003.py:236-245
+    o.mean = log(exp(o.mean) * share_pick(r.rake, C.fs_ss, C.fs_rv, C.fs_nm) *
+                 C.afrock);
   o.tau = 0.;
   o.phi = 0.;
   return o;

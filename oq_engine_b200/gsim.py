@@ -333,6 +333,37 @@ class ToroEtAl2002(_PlainGMPE):
     family = 'TORO02'
     tables = {'': 'TORO02'}
 
+    def extra_fields(self, imt):
+        dic = super().extra_fields(imt)
+        dic.update(adj_ss=0., adj_rv=0., adj_nm=0.)     # SHARE variant only
+        return dic
+
+
+def _share_terms(Frss, pR=0.81, Fnss=0.95, pN=0.01):
+    """_compute_faulting_style_term (campbell_2003.py:272-281) for the three
+    rake classes: strike slip / other, reverse (30, 150], normal (-120, -60];
+    CONSTS_FS of both SHARE classes"""
+    return (numpy.power(Frss, -pR) * numpy.power(Fnss, -pN),
+            numpy.power(Frss, 1 - pR) * numpy.power(Fnss, -pN),
+            numpy.power(Frss, -pR) * numpy.power(Fnss, 1 - pN))
+
+
+class ToroEtAl2002SHARE(ToroEtAl2002):
+    """toro_2002.py:149-183: style of faulting and rock adjustment of the
+    SHARE project, mean = log(exp(mean) * (term(rake) * AFrock))"""
+    REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag', 'rake'})
+
+    def device_spec(self):
+        return (_lib.FAMILIES[self.family], 1, [0., 0., 0., 0.])
+
+    def extra_fields(self, imt):
+        dic = super().extra_fields(imt)
+        C = CoeffsTable.get('TORO02_FS_ROCK')[from_string(imt)]
+        ss, rv, nm = _share_terms(C['Frss'])
+        dic.update(adj_ss=ss * C['AFrock'], adj_rv=rv * C['AFrock'],
+                   adj_nm=nm * C['AFrock'])
+        return dic
+
 
 class Campbell2003(_PlainGMPE):
     """campbell_2003.py:138-212 (kind "base"; total standard deviation
@@ -343,6 +374,26 @@ class Campbell2003(_PlainGMPE):
     DEFINED_FOR_STANDARD_DEVIATION_TYPES = frozenset({'Total'})
     family = 'C03'
     tables = {'': 'C03'}
+
+    def extra_fields(self, imt):
+        dic = super().extra_fields(imt)
+        dic.update(fs_ss=0., fs_rv=0., fs_nm=0., afrock=0.)   # SHARE only
+        return dic
+
+
+class Campbell2003SHARE(Campbell2003):
+    """campbell_2003.py:215-270: mean = log(exp(mean) * term(rake) * AFrock)"""
+    REQUIRES_RUPTURE_PARAMETERS = frozenset({'mag', 'rake'})
+
+    def device_spec(self):
+        return (_lib.FAMILIES[self.family], 1, [0., 0., 0., 0.])
+
+    def extra_fields(self, imt):
+        dic = super().extra_fields(imt)
+        C = CoeffsTable.get('C03_FS_ROCK')[from_string(imt)]
+        ss, rv, nm = _share_terms(C['Frss'])
+        dic.update(fs_ss=ss, fs_rv=rv, fs_nm=nm, afrock=C['AFrock'])
+        return dic
 
 
 def get_gsim(name, **kwargs):

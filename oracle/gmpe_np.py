@@ -960,6 +960,37 @@ def campbell03(ctx, imts):
     return out
 
 
+def _share_term(Frss, rake, pR=0.81, Fnss=0.95, pN=0.01):
+    """_compute_faulting_style_term, campbell_2003.py:272-281 (CONSTS_FS of
+    both SHARE classes)"""
+    term = np.full_like(rake, np.power(Frss, -pR) * np.power(Fnss, -pN))
+    term[(rake > 30.0) & (rake <= 150.0)] = (
+        np.power(Frss, 1 - pR) * np.power(Fnss, -pN))
+    term[(rake > -120.0) & (rake <= -60.0)] = (
+        np.power(Frss, -pR) * np.power(Fnss, 1 - pN))
+    return term
+
+
+def toro02_share(ctx, imts):
+    """ToroEtAl2002SHARE, toro_2002.py:134-142 on top of toro02"""
+    out = toro02(ctx, imts)
+    for m, imt in enumerate(imts):
+        C = coeffs('TORO02_FS_ROCK', imt)
+        out[0, m] = np.log(np.exp(out[0, m]) * (
+            _share_term(C['Frss'], ctx.rake) * C['AFrock']))
+    return out
+
+
+def campbell03_share(ctx, imts):
+    """Campbell2003SHARE, campbell_2003.py:236-245 on top of campbell03"""
+    out = campbell03(ctx, imts)
+    for m, imt in enumerate(imts):
+        C = coeffs('C03_FS_ROCK', imt)
+        out[0, m] = np.log(np.exp(out[0, m]) *
+                           _share_term(C['Frss'], ctx.rake) * C['AFrock'])
+    return out
+
+
 # --------------------------------------------------------------------- #
 #                              registry                                  #
 # --------------------------------------------------------------------- #
@@ -979,6 +1010,8 @@ MODELS = {
     'ChiouYoungs2008': cy08,
     'ToroEtAl2002': toro02,
     'Campbell2003': campbell03,
+    'ToroEtAl2002SHARE': toro02_share,
+    'Campbell2003SHARE': campbell03_share,
 }
 
 

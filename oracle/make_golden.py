@@ -98,6 +98,14 @@ GMPE_CASES = {
     'c03': ('Campbell2003', '[Campbell2003]', {},
             ['PGA', 'SA(0.02)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)', 'SA(1.0)',
              'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
+    # the SHARE variants (style of faulting and rock adjustment); the first
+    # is the model of the reference manual's ContextMaker example
+    'toro02_share': ('ToroEtAl2002SHARE', '[ToroEtAl2002SHARE]', {},
+                     ['PGA', 'SA(0.04)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)',
+                      'SA(1.0)', 'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
+    'c03_share': ('Campbell2003SHARE', '[Campbell2003SHARE]', {},
+                  ['PGA', 'SA(0.02)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)',
+                   'SA(1.0)', 'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
 }
 
 

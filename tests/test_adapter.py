@@ -45,6 +45,7 @@ CASES = [
     ('AkkarEtAlRjb2014', {}), ('AkkarEtAlRepi2014', {}),
     ('AkkarEtAlRhyp2014', dict(adjustment_factor=1.2)),
     ('ChiouYoungs2008', {}), ('ToroEtAl2002', {}), ('Campbell2003', {}),
+    ('ToroEtAl2002SHARE', {}), ('Campbell2003SHARE', {}),
 ]
 IMTS = ['PGA', 'SA(0.1)', 'SA(0.27)', 'SA(1.0)', 'SA(3.0)']
 
@@ -87,7 +88,7 @@ def test_packing_is_byte_identical_to_the_mirror(ref, name, kw):
 def test_error_mapping(ref):
     og, avail = ref
     with pytest.raises(NotImplementedError, match='no device implementation'):
-        og.pack_gsims([avail['ToroEtAl2002SHARE']()], ['PGA'])
+        og.pack_gsims([avail['SadighEtAl1997']()], ['PGA'])
     with pytest.raises(NotImplementedError, match='usgs_basin_scaling'):
         og.pack_gsims([avail['BooreEtAl2014'](
             region='CAL', usgs_basin_scaling=True)], ['PGA'])
@@ -102,7 +103,7 @@ def test_error_mapping(ref):
         og.pack_gsims([avail['CampbellBozorgnia2014']()], ['IA'])
     # a GpuContextMaker refuses at construction, not at first use
     with pytest.raises(NotImplementedError):
-        og.GpuContextMaker('*', [avail['ToroEtAl2002SHARE']()],
+        og.GpuContextMaker('*', [avail['SadighEtAl1997']()],
                            dict(imtls={'PGA': [0.1]}))
 
 

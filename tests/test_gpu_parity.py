@@ -733,6 +733,31 @@ def test_reference_known_ask14_stddevs(oq):
     np.testing.assert_allclose(ms[1], .79162428, rtol=1e-8)
 
 
+def test_reference_known_planar_distances(oq):
+    """The reference's own known answers for the planar distances,
+    contexts_test.py:327-360 (PlanarDistancesTestCase): a point source of
+    magnitude 7 at (0, 0), strike 90, dip 90, hypocentral depth 10 km, WC1994,
+    aspect ratio 1, seismogenic layer 0 - 20 km, sites at (0.25, 0) and
+    (0.35, 0), built and measured entirely on the device path"""
+    src = oq.PointSource('ps', 0., 0., oq.ArbitraryMFD([7.0], [1.]), 'WC1994',
+                         1.0, 0., 20., [(1.0, 90., 90., 90.)], [(1.0, 10.)])
+    sc = oq.SiteCollection.from_points(
+        [0.25, 0.35], [0., 0.], [0., 0.],
+        dict(vs30=760., vs30measured=True, z1pt0=48., z2pt5=0.6))
+    # models that together require every distance of the reference's test
+    cm = oq.ContextMaker('*', [oq.AbrahamsonEtAl2014(), oq.AkkarEtAlRepi2014(),
+                               oq.AkkarEtAlRhyp2014()],
+                         dict(imtls={'PGA': [0.01]}, truncation_level=3.))
+    [ctx] = cm.get_ctxs(src, sc)
+    aac = np.testing.assert_allclose
+    aac(ctx.rrup, [9.32409196, 20.44343079], rtol=1e-7)
+    aac(ctx.rx, [0., 0.], atol=1e-9)
+    aac(ctx.ry0, [9.26597563, 20.38546829], rtol=1e-7)
+    aac(ctx.rjb, [9.26597481, 20.3854596], rtol=1e-7)
+    aac(ctx.rhypo, [29.54267222, 40.18243627], rtol=1e-7)
+    aac(ctx.repi, [27.79873166, 38.91822433], rtol=1e-7)
+
+
 def test_sharding_groups_with_their_own_gsims(oq):
     """groups with different gsim sets occupy different columns
     of the map (gid): combining the ranks is a concatenation on the G axis,

@@ -490,3 +490,53 @@ def test_recarray_of_no_contexts_is_empty():
                          dict(imtls={'PGA': [0.1]}))
     ctx = cm.recarray([])
     assert len(ctx) == 0 and 'rjb' in ctx.dtype.names
+
+
+@pytest.mark.gpu
+def test_reference_manual_contextmaker_example(oq):
+    """The ContextMaker example of the reference's manual
+    (doc/contributing/developing-with-the-engine.rst:196-333), whose printed
+    values are known answers of the whole path: area source 126 (incremental
+    MFD of 15 magnitudes, one nodal plane, one depth) -> 47 point sources ->
+    705 ruptures, one site at (15.0, 45.2), ToroEtAl2002SHARE, truncation
+    level 99, 200 km, 50 years:
+        len(ctx) == 705, ctx.mag[0] == 4.7, round(ctx.rrup[0], 1) == 106.4,
+        round(ctx.rjb[0], 1) == 105.9, get_pmap(ctx).array == [[[0.00507998]]]
+    Polygon discretisation on the host (area.py), everything else on the
+    device: contexts through from_srcs, the map through get_pmap AND through
+    the fused pass."""
+    rates = [1.4731083E-02, 9.2946848E-03, 5.8645496E-03, 3.7002807E-03,
+             2.3347193E-03, 1.4731083E-03, 9.2946848E-04, 5.8645496E-04,
+             3.7002807E-04, 2.3347193E-04, 1.4731083E-04, 9.2946848E-05,
+             1.7588460E-05, 1.1097568E-05, 2.3340307E-06]
+    lons = [1.5026169E+01, 1.5650548E+01, 1.6273108E+01, 1.6398742E+01,
+            1.5947759E+01, 1.5677179E+01]
+    lats = [4.5773603E+01, 4.6176279E+01, 4.6083465E+01, 4.6024744E+01,
+            4.5648318E+01, 4.5422577E+01]
+    src = oq.AreaSource(
+        '126', lons, lats, 10., oq.EvenlyDiscretizedMFD(4.7, .2, rates),
+        'WC1994', 1., 0., 30., [(1., 6.9033586E+01, 5.7596810E+01, 0.)],
+        [(1., 1.0200000E+01)])
+    srcs = list(src)
+    assert len(srcs) == 47
+    assert len(src.mfd.get_annual_occurrence_rates()) == 15
+    sc = oq.SiteCollection.from_points(
+        [15.0], [45.2], [0.], dict(vs30=600., vs30measured=True))
+    cm = oq.ContextMaker('*', [oq.get_gsim('ToroEtAl2002SHARE')], dict(
+        imtls={'PGA': [0.1]}, truncation_level=99., investigation_time=50.,
+        maximum_distance=oq.IntegrationDistance.new('200.0')))
+    ctx = cm.from_srcs(srcs, sc)
+    assert len(ctx) == 705
+    assert float(ctx.mag[0]) == 4.7
+    assert float(round(ctx.rrup[0], 1)) == 106.4
+    assert float(round(ctx.rjb[0], 1)) == 105.9
+    np.testing.assert_array_equal(np.unique(ctx.sids), [0])
+    mean, sig, tau, phi = cm.get_mean_stds([ctx])
+    assert mean.shape == sig.shape == (1, 1, 705)
+    got = cm.get_pmap(ctx).array
+    assert got.shape == (1, 1, 1) and got.dtype == np.float32
+    np.testing.assert_allclose(got, [[[0.00507998]]], rtol=2e-6)
+    # the fused pass over the same sources
+    pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1.)
+    assert cm.hazard_point_sources(pmap, srcs, sc, count=True) == 705
+    np.testing.assert_allclose((~pmap).array, [[[0.00507998]]], rtol=2e-5)

@@ -32,8 +32,10 @@ from openquake.hazardlib.gsim.atkinson_boore_2006 import (  # noqa
 from openquake.hazardlib.gsim.akkar_2014 import (  # noqa
     AkkarEtAlRjb2014, AkkarEtAlRepi2014, AkkarEtAlRhyp2014)
 from openquake.hazardlib.gsim.chiou_youngs_2008 import ChiouYoungs2008  # noqa
-from openquake.hazardlib.gsim.toro_2002 import ToroEtAl2002  # noqa
-from openquake.hazardlib.gsim.campbell_2003 import Campbell2003  # noqa
+from openquake.hazardlib.gsim.toro_2002 import (  # noqa
+    ToroEtAl2002, ToroEtAl2002SHARE)
+from openquake.hazardlib.gsim.campbell_2003 import (  # noqa
+    Campbell2003, Campbell2003SHARE)
 
 TABLES = {
     'BSSA14': BooreEtAl2014.COEFFS,
@@ -51,6 +53,8 @@ TABLES = {
     'CY08': ChiouYoungs2008.COEFFS,
     'TORO02': ToroEtAl2002.COEFFS,
     'C03': Campbell2003.COEFFS,
+    'TORO02_FS_ROCK': ToroEtAl2002SHARE.COEFFS_FS_ROCK,
+    'C03_FS_ROCK': Campbell2003SHARE.COEFFS_FS_ROCK,
 }
 
 
