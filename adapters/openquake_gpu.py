@@ -155,6 +155,9 @@ SUPPORTED = {
     'Campbell2003': (_spec_plain('C03'), {'': 'COEFFS'}),
     'ToroEtAl2002SHARE': (_spec_plain('TORO02', 1), {'': 'COEFFS'}),
     'Campbell2003SHARE': (_spec_plain('C03', 1), {'': 'COEFFS'}),
+    'SadighEtAl1997': (_spec_plain('SADIGH97'), {
+        'lo_': 'COEFFS_ROCK_LOWMAG', 'hi_': 'COEFFS_ROCK_HIMAG',
+        'sd_': 'COEFFS_ROCK_STDDERR', 'so_': 'COEFFS_SOIL'}),
 }
 
 

@@ -53,7 +53,8 @@ enum {
   OQG_CY08 = 7,    /* gsim/chiou_youngs_2008.py ChiouYoungs2008 */
   OQG_TORO02 = 8,  /* gsim/toro_2002.py ToroEtAl2002 */
   OQG_C03 = 9,     /* gsim/campbell_2003.py Campbell2003 */
-  OQG_NFAMILIES = 10
+  OQG_SADIGH97 = 10, /* gsim/sadigh_1997.py SadighEtAl1997 */
+  OQG_NFAMILIES = 11
 };
 
 /* distance metrics: bit positions for masks and order of output planes */
@@ -88,7 +89,9 @@ enum {
  *  AB06   : flags bit0-1 mag_eq (0 NA, 1 Mblg87, 2 Mblg96); par[0] scale_fac
  *  AKKAR14: flags bit0-1 distance (0 rjb, 1 repi, 2 rhypo);
  *           par[0] log(adjustment_factor)
- *  CY08, TORO02, C03: - (the models of the LogicTreeCase2ClassicalPSHA demo)
+ *  CY08: - ; TORO02, C03: flags bit0 the SHARE variant (style of faulting and
+ *           rock adjustment, its factors in the coefficient row)
+ *  SADIGH97: - (the model of the PEER verification tests)
  */
 typedef struct {
   int32_t family;
@@ -281,7 +284,8 @@ int oqg_host_end(oqg_handle *h, float *map, unsigned long long *pairs_kept);
  * reference; rup_off[s] is the index of the first rupture of source s,
  * rup_off[S] = U = sum of mag_cnt * np_cnt * hd_cnt. */
 enum { OQG_MSR_WC1994 = 0,   /* scalerel/wc1994.py get_median_area */
-       OQG_MSR_POINT = 1 };  /* scalerel/point.py PointMSR */
+       OQG_MSR_POINT = 1,    /* scalerel/point.py PointMSR */
+       OQG_MSR_PEER = 2 };   /* scalerel/peer.py PeerMSR: 10 ** (mag - 4) */
 typedef struct {
   const double *lon, *lat;            /* [S] location, degrees */
   const double *usd, *lsd, *rar;      /* [S] upper / lower seismogenic depth

@@ -11,7 +11,7 @@ from .gsim import (  # noqa
     CampbellBozorgnia2014, BooreAtkinson2008, AtkinsonBoore2006,
     AkkarEtAlRjb2014, AkkarEtAlRepi2014, AkkarEtAlRhyp2014, ChiouYoungs2008,
     ToroEtAl2002, Campbell2003, ToroEtAl2002SHARE, Campbell2003SHARE,
-    get_gsim,
+    SadighEtAl1997, get_gsim,
     registry)
 from .tom import PoissonTOM, NegativeBinomialTOM  # noqa
 from .map_array import MapArray  # noqa

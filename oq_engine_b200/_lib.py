@@ -10,7 +10,8 @@ LIBPATH = os.environ.get('OQG_LIB') or os.path.join(HERE, 'liboqg.so')
 KMAX = 56
 PLANAR_LEN = 42
 FAMILIES = {'BSSA14': 0, 'CY14': 1, 'ASK14': 2, 'CB14': 3, 'BA08': 4,
-            'AB06': 5, 'AKKAR14': 6, 'CY08': 7, 'TORO02': 8, 'C03': 9}
+            'AB06': 5, 'AKKAR14': 6, 'CY08': 7, 'TORO02': 8, 'C03': 9,
+            'SADIGH97': 10}
 DIST = ['rrup', 'rjb', 'rx', 'ry0', 'repi', 'rhypo', 'azimuth', 'clon',
         'clat']
 

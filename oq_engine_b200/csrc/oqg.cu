@@ -730,7 +730,7 @@ template <int F> struct DistMask {
           ? (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_RX)
       : F == OQG_ASK14
           ? (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_RX) | (1 << OQG_RY0)
-      : F == OQG_AB06 || F == OQG_C03 ? (1 << OQG_RRUP)
+      : F == OQG_AB06 || F == OQG_C03 || F == OQG_SADIGH97 ? (1 << OQG_RRUP)
       : (1 << OQG_RRUP) | (1 << OQG_RJB) | (1 << OQG_REPI) | (1 << OQG_RHYPO);
 };
 __host__ __device__ constexpr int popc_below(int mask, int k) {   // planes before distance k
@@ -1437,6 +1437,7 @@ const char *oqg_family_fields(int family) {
     case OQG_CY08: return Fam<OQG_CY08>::fields();
     case OQG_TORO02: return Fam<OQG_TORO02>::fields();
     case OQG_C03: return Fam<OQG_C03>::fields();
+    case OQG_SADIGH97: return Fam<OQG_SADIGH97>::fields();
   }
   return nullptr;
 }
@@ -2424,7 +2425,8 @@ int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        double *magdist, double *aux) {
   CK(cudaSetDevice(h->device));
   if (S <= 0 || U <= 0) return 0;
-  if (src->msr != OQG_MSR_WC1994 && src->msr != OQG_MSR_POINT)
+  if (src->msr != OQG_MSR_WC1994 && src->msr != OQG_MSR_POINT &&
+      src->msr != OQG_MSR_PEER)
     return fail(h, "unsupported magnitude-scaling relationship (no fallback)");
   if (!src->lon || !src->lat || !src->usd || !src->lsd || !src->rar ||
       !src->mag_beg || !src->mag_cnt || !src->np_beg || !src->np_cnt ||
@@ -2543,6 +2545,7 @@ int oqg_mean_stds(oqg_handle *h, const oqg_ctx *ctx, int64_t P, double *out) {
       case OQG_CY08: launch_mean_stds<OQG_CY08>(h, g, ctx, P, out); break;
       case OQG_TORO02: launch_mean_stds<OQG_TORO02>(h, g, ctx, P, out); break;
       case OQG_C03: launch_mean_stds<OQG_C03>(h, g, ctx, P, out); break;
+      case OQG_SADIGH97: launch_mean_stds<OQG_SADIGH97>(h, g, ctx, P, out); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -2582,6 +2585,7 @@ int oqg_mean_stds_staged(oqg_handle *h, const oqg_ctx *ctx, int64_t P,
       case OQG_CY08: launch_mean_stds_staged<OQG_CY08>(h, g, ctx, P, out); break;
       case OQG_TORO02: launch_mean_stds_staged<OQG_TORO02>(h, g, ctx, P, out); break;
       case OQG_C03: launch_mean_stds_staged<OQG_C03>(h, g, ctx, P, out); break;
+      case OQG_SADIGH97: launch_mean_stds_staged<OQG_SADIGH97>(h, g, ctx, P, out); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -2877,6 +2881,7 @@ static int hazard_fused(oqg_handle *h, const double *planar,
       case OQG_CY08: LF(OQG_CY08); break;
       case OQG_TORO02: LF(OQG_TORO02); break;
       case OQG_C03: LF(OQG_C03); break;
+      case OQG_SADIGH97: LF(OQG_SADIGH97); break;
     }
 #undef LF
     h->last_subs = A.subs;

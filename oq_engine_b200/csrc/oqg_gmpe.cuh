@@ -17,6 +17,7 @@
 //   CY08     gsim/chiou_youngs_2008.py:29-167, 204-228
 //   TORO02   gsim/toro_2002.py:31-57, 103-128
 //   C03      gsim/campbell_2003.py:39-47, 71-106, 178-189
+//   SADIGH97 gsim/sadigh_1997.py:47-108, 134-161
 //   epistemic sigma: gsim/abrahamson_2014.py:440-464
 //
 // Coefficient rows are arrays of OQG_KMAX doubles laid out by the *_FIELDS
@@ -87,6 +88,12 @@ struct Out {
   X(c1) X(c2) X(c3) X(c4) X(c5) X(c6) X(c7) X(c8) X(c9) X(c10) X(c11)        \
   X(c12) X(c13) X(period) X(fs_ss) X(fs_rv) X(fs_nm) X(afrock)
 
+#define SADIGH97_FIELDS(X)                                                   \
+  X(lo_c1) X(lo_c2) X(lo_c3) X(lo_c4) X(lo_c5) X(lo_c6) X(lo_c7) X(hi_c1)    \
+  X(hi_c2) X(hi_c3) X(hi_c4) X(hi_c5) X(hi_c6) X(hi_c7) X(sd_sigma0)         \
+  X(sd_magfactor) X(sd_maxsigma) X(sd_maxmag) X(so_c6r) X(so_c6ss) X(so_c7)  \
+  X(so_sigma0) X(so_magfactor) X(period)
+
 struct Bssa14C { BSSA14_FIELDS(OQG_DECL) };
 struct Cy14C { CY14_FIELDS(OQG_DECL) };
 struct Ask14C { ASK14_FIELDS(OQG_DECL) };
@@ -97,6 +104,7 @@ struct Akkar14C { AKKAR14_FIELDS(OQG_DECL) };
 struct Cy08C { CY08_FIELDS(OQG_DECL) };
 struct Toro02C { TORO02_FIELDS(OQG_DECL) };
 struct C03C { C03_FIELDS(OQG_DECL) };
+struct Sadigh97C { SADIGH97_FIELDS(OQG_DECL) };
 
 // the last OQG_KMAX - OQG_DER doubles of a row hold constants derived on the
 // host from the packed coefficients (oqg_set_gsims; read by oqg_fast.cuh)
@@ -925,6 +933,41 @@ __device__ __forceinline__ Out c03_imt(const oqg_gsim &g, const C03C &C,
   return o;
 }
 
+// ================================================================= SADIGH97
+__device__ __forceinline__ Out sadigh97_imt(const oqg_gsim &,
+                                            const Sadigh97C &C, const Row &r) {
+  // sadigh_1997.py:134-161: rock above 750 m/s, deep soil otherwise; total
+  // standard deviation only
+  const bool reverse = 45. <= r.rake && r.rake <= 135.;
+  const bool lowmag = r.mag <= 6.5;             // NEAR_FIELD_SATURATION_MAG
+  const double mag = fmin(r.mag, 8.5);
+  Out o;
+  if (r.vs30 > 750.) {
+    // get_mean_rock :71-87, get_stddev_rock :90-97
+    const double c1 = lowmag ? C.lo_c1 : C.hi_c1, c2 = lowmag ? C.lo_c2 : C.hi_c2,
+                 c3 = lowmag ? C.lo_c3 : C.hi_c3, c4 = lowmag ? C.lo_c4 : C.hi_c4,
+                 c5 = lowmag ? C.lo_c5 : C.hi_c5, c6 = lowmag ? C.lo_c6 : C.hi_c6,
+                 c7 = lowmag ? C.lo_c7 : C.hi_c7;
+    o.mean = c1 + c2 * mag + c3 * pow(8.5 - mag, 2.5) +
+             c4 * log(r.rrup + exp(c5 + c6 * mag)) + c7 * log(r.rrup + 2.);
+    if (reverse) o.mean += 0.1823215567939546;   // log(1.2)
+    o.sig = r.mag > C.sd_maxmag ? C.sd_maxsigma
+                                : C.sd_sigma0 + C.sd_magfactor * r.mag;
+  } else {
+    // get_mean_deep_soil :47-68 (COEFFS_SOIL_IMT_INDEPENDENT),
+    // get_stddev_deep_soil :100-107
+    const double c1 = reverse ? -1.92 : -2.17;
+    const double c4 = lowmag ? 2.1863 : 0.3825, c5 = lowmag ? 0.32 : 0.5882;
+    const double c6 = reverse ? C.so_c6r : C.so_c6ss;
+    o.mean = c1 + 1.0 * mag + c6 + C.so_c7 * pow(8.5 - mag, 2.5) -
+             1.7 * log(r.rrup + c4 * exp(c5 * mag));
+    o.sig = C.so_sigma0 + C.so_magfactor * fmin(r.mag, 7.);
+  }
+  o.tau = 0.;
+  o.phi = 0.;
+  return o;
+}
+
 // ================================================================ dispatch
 // Fam<F>: the coefficient row type, the per-row state and the two stages
 template <int F> struct Fam;
@@ -966,6 +1009,8 @@ OQG_FAM(OQG_TORO02, Toro02C, NoRow, no_row_t<Toro02C>,
         ((void)s, toro02_imt(g, c, r)), TORO02_FIELDS)
 OQG_FAM(OQG_C03, C03C, NoRow, no_row_t<C03C>, ((void)s, c03_imt(g, c, r)),
         C03_FIELDS)
+OQG_FAM(OQG_SADIGH97, Sadigh97C, NoRow, no_row_t<Sadigh97C>,
+        ((void)s, sadigh97_imt(g, c, r)), SADIGH97_FIELDS)
 
 // distances a model reads (REQUIRES_DISTANCES of the reference classes,
 // SURVEY.md appendix B) as a mask of 1 << OQG_R*
@@ -986,6 +1031,7 @@ __host__ __device__ inline int required_distances(const oqg_gsim &g) {
     case OQG_CY08: return RRUP | RJB | RX;
     case OQG_TORO02: return RJB;
     case OQG_C03: return RRUP;
+    case OQG_SADIGH97: return RRUP;
   }
   return 0;
 }

@@ -233,7 +233,7 @@ class SimpleFaultSource(object):
         `rupture_mesh_spacing` km -- SimpleFaultSurface.from_fault_data(...)
         .mesh in the reference
     :param mfd: an object with get_annual_occurrence_rates()
-    :param msr: 'WC1994' or 'PointMSR'
+    :param msr: 'WC1994', 'PointMSR' or 'PeerMSR'
     """
     def __init__(self, source_id, mesh, mfd, rupture_mesh_spacing,
                  msr='WC1994', rupture_aspect_ratio=1.0, rake=0.,
@@ -268,6 +268,8 @@ class SimpleFaultSource(object):
     def _median_area(self, mag):
         if self.msr == 'WC1994':
             return float(wc1994_median_area(mag, self.rake))
+        if self.msr == 'PeerMSR':         # scalerel/peer.py:32-36
+            return 10 ** (mag - 4.0)
         return 1e-4   # PointMSR (scalerel/point.py)
 
     def _get_rupture_dimensions(self, fault_length, fault_width, mag):

@@ -396,6 +396,18 @@ class Campbell2003SHARE(Campbell2003):
         return dic
 
 
+class SadighEtAl1997(_PlainGMPE):
+    """sadigh_1997.py:110-161 (rock above 750 m/s, deep soil otherwise; total
+    standard deviation only): the model of the PEER verification tests"""
+    REQUIRES_DISTANCES = frozenset({'rrup'})
+    REQUIRES_RUPTURE_PARAMETERS = frozenset({'rake', 'mag'})
+    REQUIRES_SITES_PARAMETERS = frozenset({'vs30'})
+    DEFINED_FOR_STANDARD_DEVIATION_TYPES = frozenset({'Total'})
+    family = 'SADIGH97'
+    tables = {'lo_': 'SADIGH97_ROCK_LOWMAG', 'hi_': 'SADIGH97_ROCK_HIMAG',
+              'sd_': 'SADIGH97_ROCK_STDDERR', 'so_': 'SADIGH97_SOIL'}
+
+
 def get_gsim(name, **kwargs):
     """Instantiate a supported model by class name (like valid.gsim); an
     unsupported model is a hard error: there is no CPU fallback"""

@@ -16,7 +16,7 @@ import numpy
 
 from . import _lib
 
-MSR = {'WC1994': 0, 'PointMSR': 1}
+MSR = {'WC1994': 0, 'PointMSR': 1, 'PeerMSR': 2}
 
 
 def _round(x):
@@ -92,7 +92,7 @@ class PointSource(object):
     source/point.py PointSource, the attributes the rupture generation reads.
 
     :param mfd: an object with get_annual_occurrence_rates()
-    :param msr: 'WC1994' or 'PointMSR' (anything else is an error: there is
+    :param msr: 'WC1994', 'PointMSR' or 'PeerMSR' (anything else is an error: there is
         no device implementation to fall back from)
     :param nodal_plane_distribution: [(prob, strike, dip, rake), ...]
     :param hypocenter_distribution: [(prob, depth), ...]

@@ -960,6 +960,40 @@ def campbell03(ctx, imts):
     return out
 
 
+def sadigh97(ctx, imts):
+    """SadighEtAl1997.compute, sadigh_1997.py:134-161 with get_mean_rock
+    :71-87, get_mean_deep_soil :47-68 and the two standard deviations
+    :90-107 (total only)"""
+    out = _out(len(imts), len(ctx.mag))
+    mag, rrup = ctx.mag, ctx.rrup
+    reverse = (45 <= ctx.rake) & (ctx.rake <= 135)
+    rock = ctx.vs30 > 750
+    low = mag <= 6.5
+    mc = np.clip(mag, None, 8.5)
+    for m, imt in enumerate(imts):
+        lo = coeffs('SADIGH97_ROCK_LOWMAG', imt)
+        hi = coeffs('SADIGH97_ROCK_HIMAG', imt)
+        sd = coeffs('SADIGH97_ROCK_STDDERR', imt)
+        so = coeffs('SADIGH97_SOIL', imt)
+        C = {k: np.where(low, lo[k], hi[k]) for k in lo}
+        mean_r = (C['c1'] + C['c2'] * mc + C['c3'] * ((8.5 - mc) ** 2.5)
+                  + C['c4'] * np.log(rrup + np.exp(C['c5'] + C['c6'] * mc))
+                  + C['c7'] * np.log(rrup + 2))
+        mean_r = np.where(reverse, mean_r + 0.1823215567939546, mean_r)
+        sig_r = np.where(mag > sd['maxmag'], sd['maxsigma'],
+                         sd['sigma0'] + sd['magfactor'] * mag)
+        c1 = np.where(reverse, -1.92, -2.17)
+        c4 = np.where(low, 2.1863, 0.3825)
+        c5 = np.where(low, 0.32, 0.5882)
+        c6 = np.where(reverse, so['c6r'], so['c6ss'])
+        mean_s = (c1 + 1.0 * mc + c6 + so['c7'] * ((8.5 - mc) ** 2.5)
+                  - 1.7 * np.log(rrup + c4 * np.exp(c5 * mc)))
+        sig_s = so['sigma0'] + so['magfactor'] * np.clip(mag, None, 7)
+        out[0, m] = np.where(rock, mean_r, mean_s)
+        out[1, m] = np.where(rock, sig_r, sig_s)
+    return out
+
+
 def _share_term(Frss, rake, pR=0.81, Fnss=0.95, pN=0.01):
     """_compute_faulting_style_term, campbell_2003.py:272-281 (CONSTS_FS of
     both SHARE classes)"""
@@ -1012,6 +1046,7 @@ MODELS = {
     'Campbell2003': campbell03,
     'ToroEtAl2002SHARE': toro02_share,
     'Campbell2003SHARE': campbell03_share,
+    'SadighEtAl1997': sadigh97,
 }
 
 

@@ -103,6 +103,10 @@ GMPE_CASES = {
     'toro02_share': ('ToroEtAl2002SHARE', '[ToroEtAl2002SHARE]', {},
                      ['PGA', 'SA(0.04)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)',
                       'SA(1.0)', 'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
+    # the model of the PEER verification tests (acceptance/peer_test.py)
+    'sadigh97': ('SadighEtAl1997', '[SadighEtAl1997]', {},
+                 ['PGA', 'SA(0.075)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)',
+                  'SA(1.0)', 'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
     'c03_share': ('Campbell2003SHARE', '[Campbell2003SHARE]', {},
                   ['PGA', 'SA(0.02)', 'SA(0.1)', 'SA(0.27)', 'SA(0.7)',
                    'SA(1.0)', 'SA(2.0)', 'SA(3.0)', 'SA(4.0)']),
@@ -438,6 +442,10 @@ KAT = {  # reference verification tables (hazardlib/tests/gsim/data) ->
                           'CY08_INTRA_EVENT_SIGMA.csv']),
     'toro02': ('TORO02', ['T02_MEAN.csv', 'T02_STD_TOTAL.csv']),
     'c03': ('C03', ['C03_MEAN.csv', 'C03_STD_TOTAL.csv']),
+    'sadigh97': ('SADIGH97', ['SADIGH1997_ROCK_MEAN.csv',
+                              'SADIGH1997_ROCK_STD_TOTAL.csv',
+                              'SADIGH1997_SOIL_MEAN.csv',
+                              'SADIGH1997_SOIL_STD_TOTAL.csv']),
 }
 
 

@@ -42,6 +42,8 @@ def median_area(msr, mag, rake):
     """scalerel/wc1994.py get_median_area, scalerel/point.py:40-52"""
     if msr == 'PointMSR':
         return 1e-4
+    if msr == 'PeerMSR':         # scalerel/peer.py:32-36
+        return 10 ** (mag - 4.0)
     assert msr == 'WC1994', msr
     if abs(rake) <= 45 or abs(rake) >= 135:
         return 10.0 ** (-3.42 + 0.90 * mag)

@@ -104,7 +104,8 @@ def read_kat(fname):
     for j, h in enumerate(header):
         if h == 'result_type':
             rtype = body[0, j]
-        elif h == 'damping' or h.startswith('Unnamed') or not h:
+        elif h in ('damping', 'component_type') or \
+                h.startswith('Unnamed') or not h:
             continue
         elif h.startswith(('rup_', 'site_', 'dist_')):
             name = h.split('_', 1)[1]

@@ -88,7 +88,7 @@ def test_packing_is_byte_identical_to_the_mirror(ref, name, kw):
 def test_error_mapping(ref):
     og, avail = ref
     with pytest.raises(NotImplementedError, match='no device implementation'):
-        og.pack_gsims([avail['SadighEtAl1997']()], ['PGA'])
+        og.pack_gsims([avail['ZhaoEtAl2006Asc']()], ['PGA'])
     with pytest.raises(NotImplementedError, match='usgs_basin_scaling'):
         og.pack_gsims([avail['BooreEtAl2014'](
             region='CAL', usgs_basin_scaling=True)], ['PGA'])
@@ -103,7 +103,7 @@ def test_error_mapping(ref):
         og.pack_gsims([avail['CampbellBozorgnia2014']()], ['IA'])
     # a GpuContextMaker refuses at construction, not at first use
     with pytest.raises(NotImplementedError):
-        og.GpuContextMaker('*', [avail['SadighEtAl1997']()],
+        og.GpuContextMaker('*', [avail['ZhaoEtAl2006Asc']()],
                            dict(imtls={'PGA': [0.1]}))
 
 

@@ -26,13 +26,13 @@ KAT_MODEL = {'bssa14': 'BooreEtAl2014', 'cy14': 'ChiouYoungs2014',
              'ask14': 'AbrahamsonEtAl2014', 'cb14': 'CampbellBozorgnia2014',
              'ba08': 'BooreAtkinson2008', 'akkar14_rjb': 'AkkarEtAlRjb2014',
              'cy08': 'ChiouYoungs2008', 'toro02': 'ToroEtAl2002',
-             'c03': 'Campbell2003'}
+             'c03': 'Campbell2003', 'sadigh97': 'SadighEtAl1997'}
 KAT_ROW = {'MEAN': 0, 'TOTAL_STDDEV': 1, 'INTER_EVENT_STDDEV': 2,
            'INTRA_EVENT_STDDEV': 3}
 # the reference's own tolerances in percent
 KAT_TOL = {'bssa14': 2.0, 'cy14': 0.05, 'ask14': 0.1, 'cb14': 0.1,
            'ba08': 0.6, 'akkar14_rjb': 0.1, 'cy08': 0.05, 'toro02': 0.1,
-           'c03': 0.1}
+           'c03': 0.1, 'sadigh97': 0.5}
 
 
 def kat_files():

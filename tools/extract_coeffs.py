@@ -37,6 +37,8 @@ from openquake.hazardlib.gsim.toro_2002 import (  # noqa
 from openquake.hazardlib.gsim.campbell_2003 import (  # noqa
     Campbell2003, Campbell2003SHARE)
 
+from openquake.hazardlib.gsim.sadigh_1997 import SadighEtAl1997  # noqa
+
 TABLES = {
     'BSSA14': BooreEtAl2014.COEFFS,
     'CY14': ChiouYoungs2014.COEFFS,
@@ -55,6 +57,10 @@ TABLES = {
     'C03': Campbell2003.COEFFS,
     'TORO02_FS_ROCK': ToroEtAl2002SHARE.COEFFS_FS_ROCK,
     'C03_FS_ROCK': Campbell2003SHARE.COEFFS_FS_ROCK,
+    'SADIGH97_ROCK_LOWMAG': SadighEtAl1997.COEFFS_ROCK_LOWMAG,
+    'SADIGH97_ROCK_HIMAG': SadighEtAl1997.COEFFS_ROCK_HIMAG,
+    'SADIGH97_ROCK_STDDERR': SadighEtAl1997.COEFFS_ROCK_STDDERR,
+    'SADIGH97_SOIL': SadighEtAl1997.COEFFS_SOIL,
 }
 
 
