@@ -409,6 +409,16 @@ def planar_of_source(src, shift_hypo=False, cmaker=None, sitecol=None):
 
 
 # ------------------------------------------------------------ ContextMaker
+def _msr_name(msr):
+    """The name of a reference magnitude-scaling relationship as the device
+    sources take it (WC1994, PointMSR, PeerMSR, 'CScalingMSR.C = <C>'), None
+    if it has no device implementation"""
+    name = msr.__class__.__name__
+    if name == 'CScalingMSR':
+        return 'CScalingMSR.C = %r' % float(msr.C)
+    return name if name in ('WC1994', 'PointMSR', 'PeerMSR') else None
+
+
 def fault_of_source(src):
     """
     The device-side description of a reference SimpleFaultSource
@@ -419,10 +429,9 @@ def fault_of_source(src):
     """
     from openquake.hazardlib.geo.surface.simple_fault import (
         SimpleFaultSurface)
-    msr = src.magnitude_scaling_relationship.__class__.__name__
+    msr = _msr_name(src.magnitude_scaling_relationship)
     _no(src, hypo_list=len(src.hypo_list), slip_list=len(src.slip_list),
-        hypo_depth_list=len(src.hypo_depth_list),
-        msr=msr not in ('WC1994', 'PointMSR'),
+        hypo_depth_list=len(src.hypo_depth_list), msr=msr is None,
         magnitude_dependent_aspect_ratio=not isinstance(
             src.rupture_aspect_ratio, (int, float)))
     mesh = SimpleFaultSurface.from_fault_data(

@@ -285,7 +285,9 @@ int oqg_host_end(oqg_handle *h, float *map, unsigned long long *pairs_kept);
  * rup_off[S] = U = sum of mag_cnt * np_cnt * hd_cnt. */
 enum { OQG_MSR_WC1994 = 0,   /* scalerel/wc1994.py get_median_area */
        OQG_MSR_POINT = 1,    /* scalerel/point.py PointMSR */
-       OQG_MSR_PEER = 2 };   /* scalerel/peer.py PeerMSR: 10 ** (mag - 4) */
+       OQG_MSR_PEER = 2,     /* scalerel/peer.py PeerMSR: 10 ** (mag - 4) */
+       OQG_MSR_CSCALING = 3 }; /* scalerel/cscaling.py CScalingMSR:
+                                  10 ** (mag - msr_par) */
 typedef struct {
   const double *lon, *lat;            /* [S] location, degrees */
   const double *usd, *lsd, *rar;      /* [S] upper / lower seismogenic depth
@@ -317,6 +319,7 @@ typedef struct {
    * 1 near, 2 far, 3 none) -- the all-or-nothing rule of the reference for
    * few sites (contexts.py:358-362) is decided by the caller */
   const uint8_t *mode;
+  double msr_par;                     /* C of OQG_MSR_CSCALING */
 } oqg_point_sources;
 
 #define OQG_AUX_LEN 5 /* per rupture: x, y, z of the source location (km),

@@ -310,7 +310,7 @@ __global__ void k_point_ruptures(const oqg_point_sources P, int S, int64_t U,
   }
   double pl[OQG_PLANAR_LEN];
   build_planar_rupture(P.usd[s], P.lsd[s], P.rar[s],
-                       median_area(P.msr, mag, rake), strike, dip, rake,
+                       median_area(P.msr, P.msr_par, mag, rake), strike, dip, rake,
                        P.lon[s], P.lat[s], dep, frac, P.mag_rate[im] * weight,
                        P.shift_hypo, pl);
   for (int k = 0; k < OQG_PLANAR_LEN; k++) s_rec[threadIdx.x][k] = pl[k];
@@ -334,7 +334,7 @@ __global__ void k_point_ruptures(const oqg_point_sources P, int S, int64_t U,
         const int il = P.np_beg[s] + N - 1;
         double len, wproj;
         rupture_dims(P.usd[s], P.lsd[s], P.rar[s],
-                     median_area(P.msr, mag, P.np_rake[il]), P.np_dip[il], len,
+                     median_area(P.msr, P.msr_par, mag, P.np_rake[il]), P.np_dip[il], len,
                      wproj);
         radius = sqrt(len * len + wproj * wproj) / 2.0;
       }
@@ -2425,8 +2425,7 @@ int oqg_point_ruptures(oqg_handle *h, const oqg_point_sources *src, int S,
                        double *magdist, double *aux) {
   CK(cudaSetDevice(h->device));
   if (S <= 0 || U <= 0) return 0;
-  if (src->msr != OQG_MSR_WC1994 && src->msr != OQG_MSR_POINT &&
-      src->msr != OQG_MSR_PEER)
+  if (src->msr < OQG_MSR_WC1994 || src->msr > OQG_MSR_CSCALING)
     return fail(h, "unsupported magnitude-scaling relationship (no fallback)");
   if (!src->lon || !src->lat || !src->usd || !src->lsd || !src->rar ||
       !src->mag_beg || !src->mag_cnt || !src->np_beg || !src->np_cnt ||

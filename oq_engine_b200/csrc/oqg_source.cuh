@@ -42,10 +42,11 @@ __device__ __forceinline__ void point_at(double lon, double lat, double azimuth,
   olat = asin(sin_lats) * OQG_R2D;
 }
 
-__device__ __forceinline__ double median_area(int msr, double mag,
+__device__ __forceinline__ double median_area(int msr, double par, double mag,
                                               double rake) {
   if (msr == OQG_MSR_POINT) return 1e-4;
   if (msr == OQG_MSR_PEER) return pow(10.0, mag - 4.0);
+  if (msr == OQG_MSR_CSCALING) return pow(10.0, mag - par);
   // WC1994: strike slip |rake| <= 45 or >= 135; reverse rake > 0; normal
   if (fabs(rake) <= 45. || fabs(rake) >= 135.)
     return pow(10.0, -3.42 + 0.90 * mag);

@@ -22,8 +22,8 @@ SimpleFaultSurface.from_fault_data).
 """
 import math
 import numpy
-from .planar import wc1994_median_area
-from .source import MSR
+from .planar import wc1994_median_area  # noqa: re-exported
+from .source import parse_msr, median_area
 
 EARTH_RADIUS = 6371.0
 
@@ -233,7 +233,7 @@ class SimpleFaultSource(object):
         `rupture_mesh_spacing` km -- SimpleFaultSurface.from_fault_data(...)
         .mesh in the reference
     :param mfd: an object with get_annual_occurrence_rates()
-    :param msr: 'WC1994', 'PointMSR' or 'PeerMSR'
+    :param msr: 'WC1994', 'PointMSR', 'PeerMSR' or 'CScalingMSR.C = <C>'
     """
     def __init__(self, source_id, mesh, mfd, rupture_mesh_spacing,
                  msr='WC1994', rupture_aspect_ratio=1.0, rake=0.,
@@ -245,9 +245,7 @@ class SimpleFaultSource(object):
                              'length and width.')
         self.mfd = mfd
         self.rupture_mesh_spacing = float(rupture_mesh_spacing)
-        if msr not in MSR:
-            raise NotImplementedError('magnitude-scaling relationship %s'
-                                      % msr)
+        parse_msr(msr)      # NotImplementedError if unsupported
         self.msr = msr
         self.rupture_aspect_ratio = float(rupture_aspect_ratio)
         self.rake = float(rake)
@@ -266,11 +264,7 @@ class SimpleFaultSource(object):
         return self.mfd.get_annual_occurrence_rates()
 
     def _median_area(self, mag):
-        if self.msr == 'WC1994':
-            return float(wc1994_median_area(mag, self.rake))
-        if self.msr == 'PeerMSR':         # scalerel/peer.py:32-36
-            return 10 ** (mag - 4.0)
-        return 1e-4   # PointMSR (scalerel/point.py)
+        return float(median_area(self.msr, mag, self.rake))
 
     def _get_rupture_dimensions(self, fault_length, fault_width, mag):
         area = self._median_area(mag)

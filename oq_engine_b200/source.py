@@ -16,7 +16,41 @@ import numpy
 
 from . import _lib
 
-MSR = {'WC1994': 0, 'PointMSR': 1, 'PeerMSR': 2}
+MSR = {'WC1994': 0, 'PointMSR': 1, 'PeerMSR': 2, 'CScalingMSR': 3}
+
+
+def parse_msr(msr):
+    """(name, parameter) of a magnitude-scaling relationship given as the
+    reference writes it in the source model: 'WC1994', 'PointMSR', 'PeerMSR'
+    or the TOML form 'CScalingMSR.C = 3.90' (scalerel/cscaling.py:36-40).
+    Anything else is an error: there is no device implementation to fall
+    back from."""
+    name, _, rest = str(msr).partition('.')
+    name = name.strip()
+    if name not in MSR or (rest and name != 'CScalingMSR'):
+        raise NotImplementedError(
+            'magnitude-scaling relationship %s has no device '
+            'implementation' % msr)
+    if name == 'CScalingMSR':
+        key, _, val = rest.partition('=')
+        if key.strip() != 'C' or not val.strip():
+            raise ValueError('expected "CScalingMSR.C = <value>", got %r'
+                             % msr)
+        return name, float(val)
+    return name, 4.0 if name == 'PeerMSR' else 0.
+
+
+def median_area(msr, mags, rake):
+    """get_median_area of the supported relationships (scalerel/wc1994.py,
+    point.py:40-52, peer.py:32-36, cscaling.py:33-34)"""
+    from .planar import wc1994_median_area
+    name, par = parse_msr(msr)
+    mags = numpy.asarray(mags, float)
+    if name == 'WC1994':
+        return wc1994_median_area(mags, numpy.full(mags.shape, rake))
+    if name == 'PointMSR':
+        return numpy.full(mags.shape, 1e-4)
+    return 10. ** (mags - par)
 
 
 def _round(x):
@@ -92,8 +126,9 @@ class PointSource(object):
     source/point.py PointSource, the attributes the rupture generation reads.
 
     :param mfd: an object with get_annual_occurrence_rates()
-    :param msr: 'WC1994', 'PointMSR' or 'PeerMSR' (anything else is an error: there is
-        no device implementation to fall back from)
+    :param msr: 'WC1994', 'PointMSR', 'PeerMSR' or 'CScalingMSR.C = <C>'
+        (anything else is an error: there is no device implementation to
+        fall back from)
     :param nodal_plane_distribution: [(prob, strike, dip, rake), ...]
     :param hypocenter_distribution: [(prob, depth), ...]
     :param hypo_dip_fracs: optional, one down-dip fraction per depth
@@ -102,10 +137,7 @@ class PointSource(object):
                  upper_seismogenic_depth, lower_seismogenic_depth,
                  nodal_plane_distribution, hypocenter_distribution,
                  hypo_dip_fracs=None, tectonic_region_type='*'):
-        if msr not in MSR:
-            raise NotImplementedError(
-                'magnitude-scaling relationship %s has no device '
-                'implementation' % msr)
+        parse_msr(msr)      # NotImplementedError if unsupported
         if not lower_seismogenic_depth > upper_seismogenic_depth:
             raise ValueError('lower seismogenic depth must be below '
                              'upper seismogenic depth')
@@ -151,7 +183,8 @@ class OqgPointSources(ctypes.Structure):
         'hd_prob', 'hd_frac')] + [('msr', ctypes.c_int32),
                                   ('shift_hypo', ctypes.c_int32),
                                   ('pointsource_distance', ctypes.c_double),
-                                  ('mode', ctypes.c_void_p)]
+                                  ('mode', ctypes.c_void_p),
+                                  ('msr_par', ctypes.c_double)]
 
 
 class PointSourceBatch(object):
@@ -178,7 +211,9 @@ class PointSourceBatch(object):
         if len(msrs) != 1:
             raise ValueError('one magnitude-scaling relationship per batch, '
                              'got %s' % sorted(msrs))
-        self.msr = MSR[msrs.pop()]
+        self.msr_name = msrs.pop()
+        name, self.msr_par = parse_msr(self.msr_name)
+        self.msr = MSR[name]
         S = self.S = len(sources)
         f = lambda name: numpy.array([getattr(s, name) for s in sources],  # noqa
                                      float)
@@ -266,7 +301,7 @@ class PointSourceBatch(object):
             if self.msr == MSR['PointMSR']:
                 radius = numpy.zeros(mc)
             else:
-                area = wc1994_median_area(mags, numpy.full(mc, self.np_rake[last]))
+                area = median_area(self.msr_name, mags, self.np_rake[last])
                 rdip = numpy.radians(self.np_dip[last])
                 max_width = (self.lsd[s] - self.usd[s]) / numpy.sin(rdip)
                 length = numpy.sqrt(area * self.rar[s])
@@ -329,6 +364,7 @@ class PointSourceBatch(object):
             setattr(st, k + '_cnt', up(k + '_cnt', self.cnt[k]))
         st.mag_dist = up('mag_dist', mag_dist)
         st.msr = self.msr
+        st.msr_par = self.msr_par
         st.shift_hypo = int(bool(shift_hypo))
         st.pointsource_distance = self.pointsource_distance
         st.mode = up('mode', mode)

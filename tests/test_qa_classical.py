@@ -1,0 +1,68 @@
+"""Engine-level known answers: the expected hazard
+curves of the reference's QA test classical/case_01
+(openquake/qa_tests_data/classical/case_01/expected/*.csv, checked by
+calculators/tests/classical_test.py:73-76 at delta 1e-5) reproduced by the
+device path from the QA test's own inputs (oracle/make_golden_qa.py reads its
+job.ini and source model)."""
+import os
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+D = np.load(os.path.join(GOLDEN, 'qa_classical_case_01.npz'))
+
+
+def test_fixture():
+    assert str(D['msr']) == 'CScalingMSR.C = 3.90'
+    assert D['sites'].shape == (4, 3) and D['npd'].shape == (3, 4)
+    assert D['expected_PGA'].shape == D['expected_SA(0.1)'].shape == (4, 3)
+
+
+def test_msr_names():
+    import oq_engine_b200 as oq
+    from oq_engine_b200.source import parse_msr, median_area
+    assert parse_msr('CScalingMSR.C = 3.90') == ('CScalingMSR', 3.9)
+    assert parse_msr('PeerMSR') == ('PeerMSR', 4.0)
+    np.testing.assert_allclose(median_area('CScalingMSR.C = 4.0', [6.], 0.),
+                               median_area('PeerMSR', [6.], 0.), rtol=0)
+    np.testing.assert_allclose(median_area('PeerMSR', [6.5], 0.),
+                               10 ** 2.5, rtol=1e-15)
+    for bad in ('Leonard2014_SCR', 'PeerMSR.C = 1', 'CScalingMSR'):
+        with pytest.raises((NotImplementedError, ValueError)):
+            oq.PointSource('x', 0., 0., oq.ArbitraryMFD([5.], [1.]), bad,
+                           1., 0., 10., [(1., 0., 90., 0.)], [(1., 5.)])
+
+
+@pytest.mark.gpu
+def test_qa_classical_case_01():
+    import oq_engine_b200 as oq
+    oq._lib.lib()
+    trt = str(D['trt'])
+    src = oq.PointSource(
+        '1', float(D['lon']), float(D['lat']),
+        oq.EvenlyDiscretizedMFD(float(D['min_mag']), float(D['bin_width']),
+                                list(D['occur_rates'])),
+        str(D['msr']), float(D['rar']), float(D['usd']), float(D['lsd']),
+        [tuple(r) for r in D['npd']], [tuple(r) for r in D['hdd']],
+        tectonic_region_type=trt)
+    assert src.count_ruptures() == 3      # the engine collapses the equal planes
+    S = D['sites']
+    sc = oq.SiteCollection.from_points(
+        S[:, 0], S[:, 1], S[:, 2],
+        dict(vs30=float(D['vs30']), vs30measured=True,
+             z1pt0=float(D['z1pt0']), z2pt5=float(D['z2pt5'])))
+    imtls = {str(imt): lev for imt, lev in zip(D['imts'], D['levels'])}
+    curves = oq.calc_hazard_curves(
+        [src], sc, imtls, {trt: oq.SadighEtAl1997()},
+        float(D['truncation_level']),
+        investigation_time=float(D['investigation_time']),
+        maximum_distance=oq.IntegrationDistance.new(
+            str(float(D['maximum_distance']))),
+        pointsource_distance=100.)        # the engine's default
+    for imt in imtls:
+        exp = D['expected_' + imt]
+        # the files hold 7 significant digits; delta 1e-5 of the QA test
+        np.testing.assert_allclose(curves[imt], exp, rtol=1e-5, atol=1e-7,
+                                   err_msg=imt)
+        assert (curves[imt][exp == 0] == 0).all()
