@@ -203,27 +203,6 @@ __device__ __forceinline__ double post_key_value(unsigned long long k) {
   return __longlong_as_double((long long)(k & ~((1ull << (2 * IB)) - 1)));
 }
 
-// one stage of the bitonic network: compare-exchange of key[i] and key[i ^ J]
-// for all i; the direction of element i in the merge of size k is
-// (i & k) == 0 -> ascending.  Five instantiations (J = 16 .. 1) executed by
-// a rolled (k, j) loop keep the code at ~1 100 SASS instructions: the fully
-// unrolled network (15 stages) made the kernel instruction-fetch bound.
-template <int RP, int J>
-__device__ __forceinline__ void bitonic_stage(unsigned long long (&key)[RP],
-                                              int k) {
-#pragma unroll
-  for (int i = 0; i < RP; i++) {
-    const int p = i ^ J;
-    if (p > i) {
-      const bool up = (i & k) == 0;
-      const unsigned long long a = key[i], b = key[p];
-      const bool sw = (a > b) == up;
-      key[i] = sw ? b : a;
-      key[p] = sw ? a : b;
-    }
-  }
-}
-
 // RP <= 32: TPB = 128 threads, keys sorted in registers; RP = 64 .. 256: TPB =
 // 64 threads, the same network on the keys in shared memory ([RP][TPB],
 // conflict free: consecutive threads, consecutive 8-byte words).  A.R is the
@@ -288,14 +267,26 @@ k_postclassical_reg(const PostRegArgs A) {
 #pragma unroll 1
   for (int r = 0; r < R; r++) {
     double x = 0.;
+    // (short trip counts: unrolled by the compiler these two loops cost more
+    // in prologue / remainder code than their bodies)
+#pragma unroll 1
     for (const int kend = s_off[r + 1]; kc < kend; kc++)
       x += (double)row[s_gs[kc]];
     double v = 1. - fast_exp(fmax(-x, -700.));   // to_probs
     if (out_e) {
       // the curve of every realization of the group (uniform offsets)
       const float vf = (float)v;
-      for (const int mend = s_moff[r + 1]; km < mend; km++)
-        out_e[__ldg(A.m_pos + km)] = vf;
+      const int mend = s_moff[r + 1];
+      if (mend - km >= 8) {           // sampled logic trees: long lists
+#pragma unroll 4
+        for (; km + 4 <= mend; km += 4) {
+          const int64_t p0 = __ldg(A.m_pos + km), p1 = __ldg(A.m_pos + km + 1),
+                        p2 = __ldg(A.m_pos + km + 2), p3 = __ldg(A.m_pos + km + 3);
+          out_e[p0] = vf; out_e[p1] = vf; out_e[p2] = vf; out_e[p3] = vf;
+        }
+      }
+#pragma unroll 1
+      for (; km < mend; km++) out_e[__ldg(A.m_pos + km)] = vf;
     }
     if (A.use_rates) v = to_rate(v);
     if (r == 0) v0 = v;
@@ -343,51 +334,75 @@ k_postclassical_reg(const PostRegArgs A) {
           }
         }
   } else {
-    constexpr int RR = RP <= 32 ? RP : 4;   // register network: RP <= 32
-    unsigned long long key[RR];
+    // register network, RP <= 32.  The keys are bit patterns of non negative
+    // doubles (value bits | rank | group: the order of the patterns is the
+    // order of the doubles, denormals included), so a compare-exchange is
+    // one DSETP on the FP64 pipe and four selects (sm_100 has no DMNMX:
+    // fmin / fmax expand to more than that); the network is the bitonic
+    // sorter in its direction-free form (first step of a merge of size k:
+    // partner i ^ (k - 1), then half cleaners i ^ j), so no direction logic
+    // is executed; fully unrolled: 240 compare-exchanges of 5 instructions
+    // for 32 keys.
+    constexpr int RR = RP <= 32 ? RP : 4;
+    double key[RR];
 #pragma unroll
-    for (int r = 0; r < RR; r++)
-      key[r] = r < R ? s_key[r * TPB] : ~0ull;   // padding sorts last
-#pragma unroll 1
+    for (int r = 0; r < RR; r++)     // padding (+inf) sorts last
+      key[r] = r < R ? __longlong_as_double((long long)s_key[r * TPB])
+                     : __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
     for (int k = 2; k <= RR; k <<= 1) {
-#pragma unroll 1
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        switch (j) {
-          case 16: if (RR > 16) bitonic_stage<RR, (RR > 16 ? 16 : 1)>(key, k); break;
-          case 8: if (RR > 8) bitonic_stage<RR, (RR > 8 ? 8 : 1)>(key, k); break;
-          case 4: if (RR > 4) bitonic_stage<RR, (RR > 4 ? 4 : 1)>(key, k); break;
-          case 2: if (RR > 2) bitonic_stage<RR, (RR > 2 ? 2 : 1)>(key, k); break;
-          default: bitonic_stage<RR, 1>(key, k); break;
+#pragma unroll
+      for (int i = 0; i < RR; i++) {
+        const int p = i ^ (k - 1);
+        if (p > i) {
+          const double a = key[i], b = key[p];
+          const bool sw = a > b;
+          key[i] = sw ? b : a;
+          key[p] = sw ? a : b;
+        }
+      }
+#pragma unroll
+      for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < RR; i++) {
+          const int p = i ^ j;
+          if (p > i) {
+            const double a = key[i], b = key[p];
+            const bool sw = a > b;
+            key[i] = sw ? b : a;
+            key[p] = sw ? a : b;
+          }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RR; r++) s_key[r * TPB] = key[r];
+    for (int r = 0; r < RR; r++)
+      s_key[r * TPB] = (unsigned long long)__double_as_longlong(key[r]);
   }
   // numpy.interp(q, cumsum(w sorted), v sorted) for all the quantiles in one
   // scan of the sorted groups: group j covers (cum, cum + W_j]; up to
   // cum + w_j the curve ramps from the previous value, then it is flat
   int qi = 0;
+  double qcur = A.qsorted[0];
   double cum = 0., prev_v = 0.;
 #pragma unroll 1
-  for (int j = 0; j < R && qi < A.nq; j++) {
+  for (int j = 0; j < R; j++) {
     const unsigned long long kj = s_key[j * TPB];
     const double vk = post_key_value<IB>(kj);
-    const int g = (int)(kj & ((1u << IB) - 1));
-    const double2 wg = ww[g];
-    const double c1 = cum + wg.y, c2 = cum + wg.x;
-    while (qi < A.nq) {
-      const double q = A.qsorted[qi];
-      double res;
-      if (q < c1)
-        res = j == 0 ? vk : prev_v + (q - cum) * ((vk - prev_v) / (c1 - cum));
-      else if (q < c2 || j == R - 1)
-        res = vk;
-      else
-        break;
-      if (A.use_rates) res = 1. - exp(-res);
-      A.stat_out[(int64_t)A.qstat[qi] * A.n_elems + e] = (float)res;
-      qi++;
+    const double2 wg = ww[(int)(kj & ((1u << IB) - 1))];
+    const double c2 = cum + wg.x;
+    const bool last = j == R - 1;
+    if (qcur < c2 || last) {          // at most nq times in the whole scan
+      const double c1 = cum + wg.y;
+      do {
+        double res = vk;
+        if (qcur < c1 && j > 0)
+          res = prev_v + (qcur - cum) * ((vk - prev_v) / (c1 - cum));
+        if (A.use_rates) res = 1. - exp(-res);
+        A.stat_out[(int64_t)A.qstat[qi] * A.n_elems + e] = (float)res;
+        if (++qi == A.nq) return;     // the scan is the end of the kernel
+        qcur = A.qsorted[qi];
+      } while (qcur < c2 || last);
     }
     cum = c2;
     prev_v = vk;
