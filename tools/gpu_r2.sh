@@ -3,6 +3,8 @@
 # (--import-source) and full-size per-launch metrics of the fused kernels + the build fingerprint
 # the metrics belong to.
 #   gpurun --timeout 2400 -- 'bash tools/gpu_r2.sh TAG'
+# (gpurun copies back at most 64 MiB: the post-processing capture is a call of its own,
+#  tools/gpu_post.sh)
 TAG=${1:-r2}
 mkdir -p gpurun_out
 python -c "from oq_engine_b200 import _build; print(_build.kernel_fingerprint())" > gpurun_out/${TAG}_fingerprint.txt
@@ -21,6 +23,6 @@ python tools/bench_mesh.py > gpurun_out/${TAG}_bench_mesh.json 2>/dev/null
 python tools/bench_sources.py > gpurun_out/${TAG}_bench_sources.json 2>/dev/null
 python tools/bench_post.py --sites 10000 --rlzs 1000 > gpurun_out/${TAG}_bench_post_r1000.json 2>/dev/null
 python tools/bench_host_stream.py > gpurun_out/${TAG}_host_stream.json 2>/dev/null
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_postclassical_reg|k_hazard_maps" -c 2 --launch-skip 2 -o gpurun_out/${TAG}_post -f python tools/bench_post.py --steps 1 > gpurun_out/${TAG}_ncu_post.log 2>&1
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_postproc.py tests/test_gmf.py -m gpu -x -q > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -2 gpurun_out/${TAG}_memcheck.log
+du -sh gpurun_out; ls -la gpurun_out | sort -k5 -n | tail -4
 cut -c1-260 gpurun_out/${TAG}_bench.json; cut -c1-200 gpurun_out/${TAG}_bench_reference.json
