@@ -74,5 +74,134 @@ def main():
     print({k: (v if np.ndim(v) == 0 else np.shape(v)) for k, v in out.items()})
 
 
+def logscale(x_min, x_max, n):
+    """valid.logscale of the reference's job.ini parser"""
+    return np.logspace(np.log10(x_min), np.log10(x_max), int(n))
+
+
+def reference_case_24(d, imtls):
+    """The same calculation with the reference's hazardlib of THIS version
+    (the expected files were written by engine 3.20 and are compared at delta
+    1e-3): AreaSource -> point sources -> ContextMaker.get_ctxs -> update of
+    a map of rates (RmapMaker's mode) -> 1 - exp(-rates); (N, M, L1)"""
+    import sys
+    sys.path.insert(0, HERE)
+    # bootstraps the reference and installs the ray-casting Polygon.contains
+    # in place of shapely's (absent here), as for BASELINE configs[0]
+    import make_golden_sources  # noqa
+    import types
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, Polygon, NodalPlane
+    from openquake.hazardlib.pmf import PMF
+    from openquake.hazardlib.mfd import TruncatedGRMFD
+    from openquake.hazardlib.scalerel import WC1994
+    from openquake.hazardlib.source import AreaSource
+    from openquake.hazardlib.tom import PoissonTOM
+    from openquake.hazardlib.site import SiteCollection
+    from openquake.hazardlib.contexts import ContextMaker
+    from openquake.hazardlib.calc.filters import IntegrationDistance
+    from openquake.hazardlib.map_array import MapArray
+    tom = PoissonTOM(d['investigation_time'])
+    mn, mx, a, b = d['gr']
+    area = AreaSource(
+        '1', 'Area Source', 'Active Shallow Crust',
+        TruncatedGRMFD(mn, mx, d['width_of_mfd_bin'], a, b), 5., WC1994(),
+        d['rar'], tom, d['usd'], d['lsd'],
+        PMF([(p, NodalPlane(s, dip, r)) for p, s, dip, r in d['npd']]),
+        PMF([(p, dep) for p, dep in d['hdd']]),
+        Polygon([Point(x, y) for x, y in zip(d['poly_lons'],
+                                             d['poly_lats'])]),
+        d['area_discretization'])
+    levels = {imt: list(v) for imt, v in imtls.items()}
+    cm = ContextMaker('Active Shallow Crust', [valid.gsim(
+        '[BooreAtkinson2008]')], dict(
+        imtls=levels, truncation_level=d['truncation_level'],
+        investigation_time=d['investigation_time'],
+        maximum_distance=IntegrationDistance.new(
+            str(d['maximum_distance']))))
+    cm.tom = tom
+    S = d['sites']
+    sitecol = SiteCollection.from_points(
+        S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
+            reference_vs30_value=d['vs30'], reference_vs30_type='measured',
+            reference_depth_to_1pt0km_per_sec=d['z1pt0'],
+            reference_depth_to_2pt5km_per_sec=d['z2pt5']))
+    M, L1 = len(levels), len(next(iter(levels.values())))
+    rmap = MapArray(sitecol.sids, M * L1, 1, rates=True).fill(0)
+    nrup = 0
+    for src in area:
+        src.id = 0
+        nrup += src.count_ruptures()
+        for ctx in cm.get_ctxs(src, sitecol):
+            cm.update(rmap, ctx)
+    assert nrup == d['num_ruptures'], nrup
+    return (1. - np.exp(-rmap.array[:, :, 0].astype(float))).reshape(
+        len(S), M, L1)
+
+
+def case_24():
+    """classical/case_24 (calculators/tests/classical_test.py:355-366, delta
+    1e-3): the area source of the AreaSourceClassicalPSHA demo with three
+    hypocentral depths, BooreAtkinson2008, PGV + PGA + 7 SA x 45 levels, two
+    sites, pointsource_distance = 1000 (no approximation), 780 ruptures"""
+    case = os.path.join(os.path.dirname(CASE), 'case_24')
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(case, 'job.ini'))
+    sites = np.array([[float(x) for x in s.split()]
+                      for s in ini['geometry']['sites'].split(',')])
+    imtls = eval(ini['calculation']['intensity_measure_types_and_levels'],
+                 {'logscale': logscale})
+    out = dict(
+        sites=sites, imts=np.array(list(imtls)),
+        levels=np.array([np.asarray(imtls[i], float) for i in imtls]),
+        vs30=float(ini['site_params']['reference_vs30_value']),
+        z1pt0=float(ini['site_params']['reference_depth_to_1pt0km_per_sec']),
+        z2pt5=float(ini['site_params']['reference_depth_to_2pt5km_per_sec']),
+        investigation_time=float(ini['calculation']['investigation_time']),
+        truncation_level=float(ini['calculation']['truncation_level']),
+        maximum_distance=float(ini['calculation']['maximum_distance']),
+        pointsource_distance=float(ini['calculation']['pointsource_distance']),
+        width_of_mfd_bin=float(ini['erf']['width_of_mfd_bin']),
+        area_discretization=float(ini['erf']['area_source_discretization']))
+    root = ET.parse(os.path.join(case, 'source_model.xml')).getroot()
+    [src] = root.findall('.//n:areaSource', NS)
+    pos = [float(x) for x in src.find('.//gml:posList', NS).text.split()]
+    mfd = src.find('n:truncGutenbergRichterMFD', NS)
+    out.update(
+        poly_lons=np.array(pos[0::2]), poly_lats=np.array(pos[1::2]),
+        trt=src.get('tectonicRegion'),
+        usd=float(src.find('.//n:upperSeismoDepth', NS).text),
+        lsd=float(src.find('.//n:lowerSeismoDepth', NS).text),
+        msr=src.find('n:magScaleRel', NS).text.strip(),
+        rar=float(src.find('n:ruptAspectRatio', NS).text),
+        gr=np.array([float(mfd.get(k)) for k in ('minMag', 'maxMag', 'aValue',
+                                                 'bValue')]),
+        npd=np.array([[float(n.get(k)) for k in (
+            'probability', 'strike', 'dip', 'rake')]
+            for n in src.findall('.//n:nodalPlane', NS)]),
+        hdd=np.array([[float(n.get(k)) for k in ('probability', 'depth')]
+                      for n in src.findall('.//n:hypoDepth', NS)]),
+        num_ruptures=780)
+    for imt in imtls:
+        with open(os.path.join(case, 'expected',
+                               'hazard_curve-%s.csv' % imt)) as f:
+            rows = [r for r in csv.reader(f) if not r[0].startswith('#')]
+        body = np.array(rows[1:], float)
+        np.testing.assert_allclose(body[:, :2], sites)
+        out['expected_' + imt] = body[:, 3:]
+    out['ref_poes'] = reference_case_24(out, imtls)
+    for m, imt in enumerate(imtls):
+        exp, ref = out['expected_' + imt], out['ref_poes'][:, m]
+        print('case_24 %-10s reference (this version) vs expected file: max '
+              'abs %.1e, max rel (PoE >= 1e-4) %.1e' % (
+                  imt, np.abs(ref - exp).max(),
+                  np.abs(ref / exp - 1)[exp >= 1e-4].max()))
+    np.savez_compressed(os.path.join(GOLDEN, 'qa_classical_case_24.npz'),
+                        **out)
+    print('case_24', {k: np.shape(v) for k, v in out.items()
+                      if k.startswith('expected')})
+
+
 if __name__ == '__main__':
     main()
+    case_24()
