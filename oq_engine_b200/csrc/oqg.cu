@@ -113,6 +113,7 @@ struct oqg_handle {
   // columns (oqg_set_post_grouping), the kernel path of the last call
   bool post_grouping = true;
   int last_post_path = -1, last_post_groups = 0;
+  bool wave_fit = true;        // OQG_WAVE_FIT=0: the first guess of the chunks
   // oqg_host_begin / add / end: sites and map resident, two rupture slots
   Buf hs_site[7], hs_map, hs_slot[2][4];
   cudaStream_t hs_copy = nullptr;
@@ -1367,6 +1368,7 @@ int oqg_create(oqg_handle **out, int device) {
   cudaMemset(h->flag_dev, 0, sizeof(int));
   // tuning knobs for A/B measurements (oqg_set_site_grouping)
   if (const char *e = getenv("OQG_SITE_GROUPING")) h->site_grouping = atoi(e) != 0;
+  if (const char *e = getenv("OQG_WAVE_FIT")) h->wave_fit = atoi(e) != 0;
   if (const char *e = getenv("OQG_SITE_CELL"))
     if (atof(e) > 0.) h->site_cell_deg = atof(e);
   *out = h;
@@ -2670,20 +2672,47 @@ static cudaError_t launch_fused2(const FusedArgs &A, dim3 grid, int threads,
 // many as fit into the shared memory of an SM; otherwise the one-work-item
 // CTAs with the plain table (4 per SM).  cfg[0] forces subs (0 = automatic),
 // cfg[1] != 0 forces the plain table.
+// sub-CTAs per CTA of a model (1 = the one-work-item CTAs)
+template <int F>
+static int fused_subs(const FusedArgs &A, const int *cfg) {
+  const bool fast = A.ptab != nullptr && A.K == 0;
+  if (!(fast && !cfg[1] && A.pt_nodes == 256)) return 1;
+  const size_t tab1 = (size_t)A.pt_nodes * PT_STRIDE * 4;
+  const size_t sub = FusedLayout<F, false, true>::SIZE * 8;
+  int subs = (int)((OQG_SMEM_SM - 8 * tab1) / sub);
+  subs = std::min(subs, OQG_SUBS_MAX);
+  if (cfg[0]) subs = std::min(subs, cfg[0]);
+  if (subs * A.nw > 32) subs = 32 / A.nw;
+  return std::max(subs, 1);
+}
+
+static int fused_subs_of(int family, const FusedArgs &A, const int *cfg) {
+  switch (family) {
+    case OQG_BSSA14: return fused_subs<OQG_BSSA14>(A, cfg);
+    case OQG_CY14: return fused_subs<OQG_CY14>(A, cfg);
+    case OQG_ASK14: return fused_subs<OQG_ASK14>(A, cfg);
+    case OQG_CB14: return fused_subs<OQG_CB14>(A, cfg);
+    case OQG_BA08: return fused_subs<OQG_BA08>(A, cfg);
+    case OQG_AB06: return fused_subs<OQG_AB06>(A, cfg);
+    case OQG_AKKAR14: return fused_subs<OQG_AKKAR14>(A, cfg);
+    case OQG_CY08: return fused_subs<OQG_CY08>(A, cfg);
+    case OQG_TORO02: return fused_subs<OQG_TORO02>(A, cfg);
+    case OQG_C03: return fused_subs<OQG_C03>(A, cfg);
+    case OQG_SADIGH97: return fused_subs<OQG_SADIGH97>(A, cfg);
+  }
+  return 1;
+}
+
 template <int F>
 static cudaError_t launch_fused(FusedArgs &A, int tiles, int rc, int ugroups,
                                 const int *cfg, cudaStream_t st) {
   const bool fast = A.ptab != nullptr && A.K == 0;
   A.ntiles = tiles;
   const size_t tab1 = fast ? (size_t)A.pt_nodes * PT_STRIDE * 4 : 0;
-  int subs = 1;
-  if (fast && !cfg[1] && A.pt_nodes == 256) {
+  int subs = fused_subs<F>(A, cfg);
+  if (subs > 1) {
     const size_t sub = FusedLayout<F, false, true>::SIZE * 8;
-    subs = (int)((OQG_SMEM_SM - 8 * tab1) / sub);
-    subs = std::min(subs, OQG_SUBS_MAX);
-    if (cfg[0]) subs = std::min(subs, cfg[0]);
-    if (subs * A.nw > 32) subs = 32 / A.nw;
-    if (subs > 1) {
+    {
       A.subs = subs;
       A.pt_bias = 0u - 0x4b000000u * (unsigned)(PT_STRIDE * 4 * 8);
       dim3 grid((tiles + subs - 1) / subs, rc, ugroups);
@@ -2836,6 +2865,31 @@ static int hazard_fused(oqg_handle *h, const double *planar,
                ((int64_t)tiles * ugroups);
   int64_t max_rc = (U + RT - 1) / RT;
   rc = std::max<int64_t>(1, std::min<int64_t>(rc, std::min<int64_t>(max_rc, 64)));
+  if (h->wave_fit) {
+    // Wave quantisation: the CTAs of a launch take about the same time (same
+    // ruptures, 32 sites each), so a grid of 8.5 waves costs 9.  Among the
+    // chunk counts around the first guess pick the one with the smallest
+    // waves x tiles-per-chunk summed over the models (cfg3: 16 chunks = 1264
+    // CTAs = 8.54 waves of 148 -> 13 chunks = 1027 CTAs = 6.94 waves).
+    A.nw = nw;
+    const int64_t lo = std::max<int64_t>(1, rc / 2);
+    const int64_t hi = std::min<int64_t>(std::min<int64_t>(max_rc, 64), rc * 2);
+    int64_t best_rc = rc;
+    double best_cost = 1e300;
+    for (int64_t c = lo; c <= hi; c++) {
+      const int64_t tiles_per_chunk = ((U + c - 1) / c + RT - 1) / RT;
+      double cost = 0.;
+      for (int g = 0; g < G; g++) {
+        const int subs = fused_subs_of(h->gsims[g].family, A, h->fused_cfg);
+        const int64_t ctas = (int64_t)((tiles + subs - 1) / subs) * c * ugroups;
+        const int64_t slots = (int64_t)h->sm_count * (subs > 1 ? 1 : MINB);
+        cost += (double)((ctas + slots - 1) / slots) * (double)tiles_per_chunk;
+      }
+      // prefer the first guess, then fewer chunks, on (near) ties
+      if (cost < best_cost * (1. - 1e-3)) { best_cost = cost; best_rc = c; }
+    }
+    rc = best_rc;
+  }
   int64_t rpc = (U + rc - 1) / rc;
   rpc = (rpc + RT - 1) / RT * RT;
   rc = (U + rpc - 1) / rpc;

@@ -24,6 +24,14 @@
 
 namespace oqg {
 
+// min of two doubles as one DSETP and two selects: fmin() on sm_100 is a
+// DSETP.MIN plus NaN handling and moves, 8 instructions (there is no DMNMX).
+// A NaN second argument is ignored like in fmin(); the first one must not be
+// NaN (a running minimum).
+__device__ __forceinline__ double dmin(double a, double b) {
+  return b < a ? b : a;
+}
+
 #define OQG_EARTH_RADIUS 6371.0  // geodetic.py:32
 #define OQG_R2D 57.29577951308232
 
@@ -214,7 +222,7 @@ __device__ __forceinline__ void pair_distances(RupPtr rup, int rs,
     if (mask & (1 << OQG_RX)) d.rx = asin(s[1]) * OQG_EARTH_RADIUS;
     bool same23 = (s[2] > 0.) == (s[3] > 0.) && (s[2] < 0.) == (s[3] < 0.);
     if (mask & (1 << OQG_RY0)) {
-      d.ry0 = same23 ? asin(fmin(fabs(s[2]), fabs(s[3]))) * OQG_EARTH_RADIUS
+      d.ry0 = same23 ? asin(dmin(fabs(s[2]), fabs(s[3]))) * OQG_EARTH_RADIUS
                      : 0.;
     }
     if (mask & (1 << OQG_RJB)) {
@@ -226,13 +234,13 @@ __device__ __forceinline__ void pair_distances(RupPtr rup, int rs,
         for (int c = 0; c < 4; c++) {
           double e0 = sx[0] - RUP(RF_CS + 3 * c), e1 = sx[1] - RUP(RF_CS + 3 * c + 1),
                  e2 = sx[2] - RUP(RF_CS + 3 * c + 2);
-          best = fmin(best, e0 * e0 + e1 * e1 + e2 * e2);
+          best = dmin(best, e0 * e0 + e1 * e1 + e2 * e2);
         }
         d.rjb = sqrt(best);
       } else if (same01) {
-        d.rjb = asin(fmin(fabs(s[0]), fabs(s[1]))) * OQG_EARTH_RADIUS;
+        d.rjb = asin(dmin(fabs(s[0]), fabs(s[1]))) * OQG_EARTH_RADIUS;
       } else if (same23) {
-        d.rjb = asin(fmin(fabs(s[2]), fabs(s[3]))) * OQG_EARTH_RADIUS;
+        d.rjb = asin(dmin(fabs(s[2]), fabs(s[3]))) * OQG_EARTH_RADIUS;
       } else {
         d.rjb = 0.;
       }
@@ -315,7 +323,7 @@ k_mesh_min_distance(const double *__restrict__ pts, int64_t P,
       const double px = sx[i], py = sy[i], pz = sz[i], pp = sp[i];
 #pragma unroll
       for (int k = 0; k < MESH_SPT; k++)
-        best[k] = fmin(best[k], fma(qx[k], px, fma(qy[k], py, fma(qz[k], pz, pp))));
+        best[k] = dmin(best[k], fma(qx[k], px, fma(qy[k], py, fma(qz[k], pz, pp))));
     }
   }
 #pragma unroll
