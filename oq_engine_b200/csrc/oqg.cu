@@ -114,6 +114,7 @@ struct oqg_handle {
   bool post_grouping = true;
   int last_post_path = -1, last_post_groups = 0;
   bool wave_fit = true;        // OQG_WAVE_FIT=0: the first guess of the chunks
+  int force_chunks = 0;        // OQG_CHUNKS=n: exactly n rupture chunks
   // oqg_host_begin / add / end: sites and map resident, two rupture slots
   Buf hs_site[7], hs_map, hs_slot[2][4];
   cudaStream_t hs_copy = nullptr;
@@ -1369,6 +1370,7 @@ int oqg_create(oqg_handle **out, int device) {
   // tuning knobs for A/B measurements (oqg_set_site_grouping)
   if (const char *e = getenv("OQG_SITE_GROUPING")) h->site_grouping = atoi(e) != 0;
   if (const char *e = getenv("OQG_WAVE_FIT")) h->wave_fit = atoi(e) != 0;
+  if (const char *e = getenv("OQG_CHUNKS")) h->force_chunks = atoi(e);
   if (const char *e = getenv("OQG_SITE_CELL"))
     if (atof(e) > 0.) h->site_cell_deg = atof(e);
   *out = h;
@@ -2870,7 +2872,8 @@ static int hazard_fused(oqg_handle *h, const double *planar,
     // ruptures, 32 sites each), so a grid of 8.5 waves costs 9.  Among the
     // chunk counts around the first guess pick the one with the smallest
     // waves x tiles-per-chunk summed over the models (cfg3: 16 chunks = 1264
-    // CTAs = 8.54 waves of 148 -> 13 chunks = 1027 CTAs = 6.94 waves).
+    // CTAs = 8.54 waves of 148, 303.9 ms -> 28 chunks = 2212 CTAs = 14.95
+    // waves, 290.6 ms).
     A.nw = nw;
     const int64_t lo = std::max<int64_t>(1, rc / 2);
     const int64_t hi = std::min<int64_t>(std::min<int64_t>(max_rc, 64), rc * 2);
@@ -2883,13 +2886,19 @@ static int hazard_fused(oqg_handle *h, const double *planar,
         const int subs = fused_subs_of(h->gsims[g].family, A, h->fused_cfg);
         const int64_t ctas = (int64_t)((tiles + subs - 1) / subs) * c * ugroups;
         const int64_t slots = (int64_t)h->sm_count * (subs > 1 ? 1 : MINB);
-        cost += (double)((ctas + slots - 1) / slots) * (double)tiles_per_chunk;
+        // + half a wave: the CTAs do not finish in lockstep, the tail of a
+        // launch costs about half a CTA time whatever the wave count
+        // (measured on cfg3: 13 chunks 293.8 ms, 28: 290.6, 43: 288.8)
+        cost += ((double)((ctas + slots - 1) / slots) + 0.5) *
+                (double)tiles_per_chunk;
       }
       // prefer the first guess, then fewer chunks, on (near) ties
       if (cost < best_cost * (1. - 1e-3)) { best_cost = cost; best_rc = c; }
     }
     rc = best_rc;
   }
+  if (h->force_chunks > 0)     // OQG_CHUNKS: experiments
+    rc = std::max<int64_t>(1, std::min<int64_t>(h->force_chunks, max_rc));
   int64_t rpc = (U + rc - 1) / rc;
   rpc = (rpc + RT - 1) / RT * RT;
   rc = (U + rpc - 1) / rpc;
