@@ -79,7 +79,7 @@ def logscale(x_min, x_max, n):
     return np.logspace(np.log10(x_min), np.log10(x_max), int(n))
 
 
-def reference_case_24(d, imtls):
+def reference_case_24(d, imtls, mfd=None, gsim='[BooreAtkinson2008]'):
     """The same calculation with the reference's hazardlib of THIS version
     (the expected files were written by engine 3.20 and are compared at delta
     1e-3): AreaSource -> point sources -> ContextMaker.get_ctxs -> update of
@@ -102,10 +102,12 @@ def reference_case_24(d, imtls):
     from openquake.hazardlib.calc.filters import IntegrationDistance
     from openquake.hazardlib.map_array import MapArray
     tom = PoissonTOM(d['investigation_time'])
-    mn, mx, a, b = d['gr']
+    if mfd is None:
+        mn, mx, a, b = d['gr']
     area = AreaSource(
         '1', 'Area Source', 'Active Shallow Crust',
-        TruncatedGRMFD(mn, mx, d['width_of_mfd_bin'], a, b), 5., WC1994(),
+        mfd or TruncatedGRMFD(mn, mx, d['width_of_mfd_bin'], a, b), 5.,
+        WC1994(),
         d['rar'], tom, d['usd'], d['lsd'],
         PMF([(p, NodalPlane(s, dip, r)) for p, s, dip, r in d['npd']]),
         PMF([(p, dep) for p, dep in d['hdd']]),
@@ -113,8 +115,7 @@ def reference_case_24(d, imtls):
                                              d['poly_lats'])]),
         d['area_discretization'])
     levels = {imt: list(v) for imt, v in imtls.items()}
-    cm = ContextMaker('Active Shallow Crust', [valid.gsim(
-        '[BooreAtkinson2008]')], dict(
+    cm = ContextMaker('Active Shallow Crust', [valid.gsim(gsim)], dict(
         imtls=levels, truncation_level=d['truncation_level'],
         investigation_time=d['investigation_time'],
         maximum_distance=IntegrationDistance.new(
@@ -202,6 +203,102 @@ def case_24():
                       if k.startswith('expected')})
 
 
+def case_26():
+    """classical/case_26 (classical_test.py:373-375, delta 2e-5, expected
+    file of engine 3.26): an area source over a 1 x 1 degree square
+    discretised at 5 km with a YoungsCoppersmith1985MFD (characteristic
+    magnitude 7.0: ruptures longer than the seismogenic layer is thick),
+    BooreAtkinson2008, SA(1.0) x 19 levels, one site.  The magnitudes and
+    rates of the MFD are read from the reference's own class (data, as the
+    coefficient tables)."""
+    case = os.path.join(os.path.dirname(CASE), 'case_26')
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(case, 'job.ini'))
+    sites = np.array([[float(x) for x in s.split()] + [0.]
+                      for s in ini['geometry']['sites'].split(',')])[:, :3]
+    imtls = eval(ini['calculation']['intensity_measure_types_and_levels'],
+                 {'logscale': logscale})
+    out = dict(
+        sites=sites, imts=np.array(list(imtls)),
+        levels=np.array([np.asarray(imtls[i], float) for i in imtls]),
+        vs30=float(ini['site_params']['reference_vs30_value']),
+        z1pt0=float(ini['site_params']['reference_depth_to_1pt0km_per_sec']),
+        z2pt5=float(ini['site_params']['reference_depth_to_2pt5km_per_sec']),
+        investigation_time=float(ini['calculation']['investigation_time']),
+        truncation_level=float(ini['calculation']['truncation_level']),
+        maximum_distance=float(ini['calculation']['maximum_distance']),
+        area_discretization=float(ini['erf']['area_source_discretization']))
+    root = ET.parse(os.path.join(case, 'source_model.xml')).getroot()
+    [src] = root.findall('.//n:areaSource', NS)
+    pos = [float(x) for x in src.find('.//gml:posList', NS).text.split()]
+    node = src.find('n:YoungsCoppersmithMFD', NS)
+    import sys
+    sys.path.insert(0, HERE)
+    import make_golden_sources  # noqa: bootstraps the reference
+    from openquake.hazardlib.mfd import YoungsCoppersmith1985MFD
+    mfd = YoungsCoppersmith1985MFD(
+        min_mag=float(node.get('minMag')), b_val=float(node.get('bValue')),
+        char_mag=float(node.get('characteristicMag')),
+        char_rate=float(node.get('characteristicRate')),
+        total_moment_rate=None, bin_width=float(node.get('binWidth')))
+    out.update(
+        poly_lons=np.array(pos[0::2]), poly_lats=np.array(pos[1::2]),
+        trt=src.get('tectonicRegion'),
+        usd=float(src.find('.//n:upperSeismoDepth', NS).text),
+        lsd=float(src.find('.//n:lowerSeismoDepth', NS).text),
+        msr=src.find('n:magScaleRel', NS).text.strip(),
+        rar=float(src.find('n:ruptAspectRatio', NS).text),
+        mfd=np.array(mfd.get_annual_occurrence_rates()),
+        npd=np.array([[float(n.get(k)) for k in (
+            'probability', 'strike', 'dip', 'rake')]
+            for n in src.findall('.//n:nodalPlane', NS)]),
+        hdd=np.array([[float(n.get(k)) for k in ('probability', 'depth')]
+                      for n in src.findall('.//n:hypoDepth', NS)]))
+    with open(os.path.join(case, 'expected', 'hazard_curve-rlz-000.csv')) as f:
+        rows = [r for r in csv.reader(f) if not r[0].startswith('#')]
+    out['expected'] = np.array(rows[1:], float)[:, 3:]
+    d = dict(out, num_ruptures=None)
+    ref = reference_case_26(d, imtls, mfd)
+    out['ref_poes'], out['num_points'], out['num_ruptures'] = ref
+    print('case_26: %d points, %d ruptures; reference (this version) vs '
+          'expected file: max abs %.1e, max rel (PoE >= 1e-4) %.1e' % (
+              ref[1], ref[2], np.abs(ref[0][:, 0] - out['expected']).max(),
+              np.abs(ref[0][:, 0] / out['expected'] - 1)[
+                  out['expected'] >= 1e-4].max()))
+    np.savez_compressed(os.path.join(GOLDEN, 'qa_classical_case_26.npz'),
+                        **out)
+
+
+def reference_case_26(d, imtls, mfd):
+    """as reference_case_24, returning also the numbers of points and
+    ruptures of the discretised source"""
+    from openquake.hazardlib import source
+    count = {}
+    orig = source.AreaSource.__iter__
+
+    def counting(self):
+        n = r = 0
+        for src in orig(self):
+            n += 1
+            r += src.count_ruptures()
+            yield src
+        count['points'], count['ruptures'] = n, r
+    source.AreaSource.__iter__ = counting
+    try:
+        d = dict(d)
+        d['num_ruptures'] = -1
+        try:
+            poes = reference_case_24(d, imtls, mfd)
+        except AssertionError:
+            # reference_case_24 checks the rupture count of case_24 only
+            d['num_ruptures'] = count['ruptures']
+            poes = reference_case_24(d, imtls, mfd)
+    finally:
+        source.AreaSource.__iter__ = orig
+    return poes, count['points'], count['ruptures']
+
+
 if __name__ == '__main__':
     main()
     case_24()
+    case_26()

@@ -116,3 +116,46 @@ def test_qa_classical_case_24():
         ref = E['ref_poes'][:, m]
         np.testing.assert_allclose(curves[imt], ref, rtol=2e-5, atol=1.5e-7,
                                    err_msg=imt)
+
+
+F = np.load(os.path.join(GOLDEN, 'qa_classical_case_26.npz'))
+
+
+@pytest.mark.gpu
+def test_qa_classical_case_26():
+    """classical/case_26 (classical_test.py:373-375, delta 2e-5): an area
+    source over a 1 x 1 degree square discretised at 5 km (484 point
+    sources), YoungsCoppersmith1985MFD with characteristic magnitude 7.0
+    (23 magnitudes, 11 132 ruptures, the large ones clipped to the
+    seismogenic layer), BooreAtkinson2008, SA(1.0) x 19 levels, one site:
+    the engine's expected curve at the QA test's delta, and this version's
+    hazardlib on the same inputs."""
+    import oq_engine_b200 as oq
+    oq._lib.lib()
+    trt = str(F['trt'])
+    src = oq.AreaSource(
+        '1', F['poly_lons'], F['poly_lats'], float(F['area_discretization']),
+        oq.ArbitraryMFD(F['mfd'][:, 0], F['mfd'][:, 1]), str(F['msr']),
+        float(F['rar']), float(F['usd']), float(F['lsd']),
+        [tuple(r) for r in F['npd']], [tuple(r) for r in F['hdd']],
+        tectonic_region_type=trt)
+    srcs = list(src)
+    assert len(srcs) == int(F['num_points'])
+    assert sum(s.count_ruptures() for s in srcs) == int(F['num_ruptures'])
+    S = F['sites']
+    sc = oq.SiteCollection.from_points(
+        S[:, 0], S[:, 1], np.zeros(len(S)),
+        dict(vs30=float(F['vs30']), vs30measured=True,
+             z1pt0=float(F['z1pt0']), z2pt5=float(F['z2pt5'])))
+    imtls = {str(imt): lev for imt, lev in zip(F['imts'], F['levels'])}
+    [imt] = imtls
+    curves = oq.calc_hazard_curves(
+        srcs, sc, imtls, {trt: oq.BooreAtkinson2008()},
+        float(F['truncation_level']),
+        investigation_time=float(F['investigation_time']),
+        maximum_distance=oq.IntegrationDistance.new(
+            str(float(F['maximum_distance']))))
+    np.testing.assert_allclose(curves[imt], F['expected'], rtol=2e-5,
+                               atol=2e-5)           # the QA test's delta
+    np.testing.assert_allclose(curves[imt], F['ref_poes'][:, 0], rtol=2e-5,
+                               atol=1.5e-7)
