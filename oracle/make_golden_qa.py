@@ -298,7 +298,161 @@ def reference_case_26(d, imtls, mfd):
     return poes, count['points'], count['ruptures']
 
 
+def case_31():
+    """classical/case_31 (classical_test.py:472-474, default delta 1e-5,
+    expected file of engine 3.26): an area source, a point source and a
+    multi-point source, dipping reverse ruptures (dip 60, rake 90) with three
+    hypocentral depths each carrying its own fixedDipFrac, ChiouYoungs2014
+    (hanging-wall terms), PGA x 6 levels, one site, the engine's default
+    pointsource_distance of 100 km (the far sites of a source see the average
+    rupture of its depths, contexts.py:321-370)."""
+    case = os.path.join(os.path.dirname(CASE), 'case_31')
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(case, 'job.ini'))
+    sites = np.array([[float(x) for x in s.split()]
+                      for s in ini['geometry']['sites'].split(',')])
+    imtls = eval(ini['calculation']['intensity_measure_types_and_levels'])
+    binw = float(ini['erf']['width_of_mfd_bin'])
+    out = dict(
+        sites=sites, imts=np.array(list(imtls)),
+        levels=np.array([np.asarray(imtls[i], float) for i in imtls]),
+        vs30=float(ini['site_params']['reference_vs30_value']),
+        z1pt0=float(ini['site_params']['reference_depth_to_1pt0km_per_sec']),
+        z2pt5=float(ini['site_params']['reference_depth_to_2pt5km_per_sec']),
+        investigation_time=float(ini['calculation']['investigation_time']),
+        truncation_level=float(ini['calculation']['truncation_level']),
+        maximum_distance=float(ini['calculation']['maximum_distance']),
+        area_discretization=float(ini['erf']['area_source_discretization']),
+        width_of_mfd_bin=binw, pointsource_distance=100.)   # openquake.cfg
+    root = ET.parse(os.path.join(case, 'source_model.xml')).getroot()
+
+    def common(src):
+        return dict(
+            usd=float(src.find('.//n:upperSeismoDepth', NS).text),
+            lsd=float(src.find('.//n:lowerSeismoDepth', NS).text),
+            msr=src.find('n:magScaleRel', NS).text.strip(),
+            rar=float(src.find('n:ruptAspectRatio', NS).text),
+            npd=np.array([[float(n.get(k)) for k in (
+                'probability', 'strike', 'dip', 'rake')]
+                for n in src.findall('.//n:nodalPlane', NS)]),
+            hdd=np.array([[float(n.get(k)) for k in (
+                'probability', 'depth', 'fixedDipFrac')]
+                for n in src.findall('.//n:hypoDepth', NS)]))
+    [area] = root.findall('.//n:areaSource', NS)
+    [point] = root.findall('.//n:pointSource', NS)
+    [multi] = root.findall('.//n:multiPointSource', NS)
+    com = common(area)
+    for other in (point, multi):      # the three sources share everything
+        for k, v in common(other).items():
+            np.testing.assert_array_equal(v, com[k])
+    out.update(com)
+    out['trt'] = area.get('tectonicRegion')
+    pos = [float(x) for x in area.find('.//gml:posList', NS).text.split()]
+    out['poly_lons'], out['poly_lats'] = np.array(pos[0::2]), np.array(pos[1::2])
+    g = area.find('n:truncGutenbergRichterMFD', NS)
+    out['gr'] = np.array([float(g.get(k)) for k in ('minMag', 'maxMag',
+                                                    'aValue', 'bValue')])
+    g2 = point.find('n:truncGutenbergRichterMFD', NS)
+    assert [g2.get(k) for k in ('minMag', 'maxMag', 'aValue', 'bValue')] == [
+        g.get(k) for k in ('minMag', 'maxMag', 'aValue', 'bValue')]
+    out['point'] = np.array([float(x) for x in point.find(
+        './/gml:pos', NS).text.split()])
+    mp = [float(x) for x in multi.find('.//gml:posList', NS).text.split()]
+    out['multi_points'] = np.array(mp).reshape(-1, 2)
+    mm = multi.find('n:multiMFD', NS)
+    assert mm.get('kind') == 'truncGutenbergRichterMFD'
+    a_vals = [float(x) for x in mm.find('n:a_val', NS).text.split()]
+    assert (float(mm.find('n:b_val', NS).text),
+            float(mm.find('n:min_mag', NS).text),
+            float(mm.find('n:max_mag', NS).text)) == (
+                out['gr'][3], out['gr'][0], out['gr'][1])
+    out['multi_a_vals'] = np.array(a_vals)
+    with open(os.path.join(case, 'expected', 'hazard_curve-mean-PGA.csv')) as f:
+        rows = [r for r in csv.reader(f) if not r[0].startswith('#')]
+    out['expected'] = np.array(rows[1:], float)[:, 3:]
+    ref = reference_case_31(out, imtls)
+    out['ref_poes'], out['num_ruptures'], out['num_rows'] = ref
+    print('case_31: %d ruptures, %d context rows; reference (this version) '
+          'vs expected file: max abs %.1e, max rel %.1e' % (
+              ref[1], ref[2], np.abs(ref[0] - out['expected']).max(),
+              np.abs(ref[0] / out['expected'] - 1).max()))
+    np.savez_compressed(os.path.join(GOLDEN, 'qa_classical_case_31.npz'),
+                        **out)
+
+
+def reference_case_31(d, imtls):
+    """this version's hazardlib on the inputs of case_31: the three sources
+    through ContextMaker.get_ctxs (with pointsource_distance) -> update of a
+    map of rates -> 1 - exp(-rates)"""
+    import sys
+    sys.path.insert(0, HERE)
+    import make_golden_sources  # noqa: bootstrap + polygon shim
+    import types
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, Polygon, NodalPlane
+    from openquake.hazardlib.pmf import PMF
+    from openquake.hazardlib.mfd import TruncatedGRMFD
+    from openquake.hazardlib.scalerel import WC1994
+    from openquake.hazardlib.source import AreaSource, PointSource
+    from openquake.hazardlib.tom import PoissonTOM
+    from openquake.hazardlib.site import SiteCollection
+    from openquake.hazardlib.contexts import ContextMaker
+    from openquake.hazardlib.calc.filters import IntegrationDistance
+    from openquake.hazardlib.map_array import MapArray
+    tom = PoissonTOM(d['investigation_time'])
+    mn, mx, a, b = d['gr']
+    npd = PMF([(p, NodalPlane(s, dip, r)) for p, s, dip, r in d['npd']])
+
+    def hdd():
+        pmf = PMF([(p, dep) for p, dep, _f in d['hdd']])
+        pmf.hypo_dip_fracs = tuple(f for _p, _dep, f in d['hdd'])
+        return pmf
+
+    def mfd(a_val):
+        return TruncatedGRMFD(mn, mx, d['width_of_mfd_bin'], a_val, b)
+    trt = 'Active Shallow Crust'
+    srcs = list(AreaSource(
+        '1', 'Area Source', trt, mfd(a), 5., WC1994(), d['rar'], tom,
+        d['usd'], d['lsd'], npd, hdd(),
+        Polygon([Point(x, y) for x, y in zip(d['poly_lons'],
+                                             d['poly_lats'])]),
+        d['area_discretization']))
+    srcs.append(PointSource(
+        '2', 'Point Source', trt, mfd(a), 5., WC1994(), d['rar'], tom,
+        d['usd'], d['lsd'], Point(*d['point']), npd, hdd()))
+    for i, ((x, y), av) in enumerate(zip(d['multi_points'],
+                                         d['multi_a_vals'])):
+        srcs.append(PointSource(
+            '3:%d' % i, 'Multi-Point Source', trt, mfd(av), 5., WC1994(),
+            d['rar'], tom, d['usd'], d['lsd'], Point(x, y), npd, hdd()))
+    levels = {imt: list(v) for imt, v in imtls.items()}
+    cm = ContextMaker(trt, [valid.gsim('[ChiouYoungs2014]')], dict(
+        imtls=levels, truncation_level=d['truncation_level'],
+        investigation_time=d['investigation_time'],
+        pointsource_distance={'default': d['pointsource_distance']},
+        maximum_distance=IntegrationDistance.new(
+            str(d['maximum_distance']))))
+    cm.tom = tom
+    S = d['sites']
+    sitecol = SiteCollection.from_points(
+        S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
+            reference_vs30_value=d['vs30'], reference_vs30_type='measured',
+            reference_depth_to_1pt0km_per_sec=d['z1pt0'],
+            reference_depth_to_2pt5km_per_sec=d['z2pt5']))
+    L = sum(len(v) for v in levels.values())
+    rmap = MapArray(sitecol.sids, L, 1, rates=True).fill(0)
+    nrup = nrows = 0
+    for src in srcs:
+        src.id = 0
+        nrup += src.count_ruptures()
+        for ctx in cm.get_ctxs(src, sitecol):
+            nrows += len(ctx)
+            cm.update(rmap, ctx)
+    return (1. - np.exp(-rmap.array[:, :, 0].astype(float)), nrup, nrows)
+
+
 if __name__ == '__main__':
     main()
     case_24()
     case_26()
+    case_31()

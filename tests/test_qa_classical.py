@@ -159,3 +159,56 @@ def test_qa_classical_case_26():
                                atol=2e-5)           # the QA test's delta
     np.testing.assert_allclose(curves[imt], F['ref_poes'][:, 0], rtol=2e-5,
                                atol=1.5e-7)
+
+
+H = np.load(os.path.join(GOLDEN, 'qa_classical_case_31.npz'))
+
+
+@pytest.mark.gpu
+def test_qa_classical_case_31():
+    """classical/case_31 (classical_test.py:472-474, delta 1e-5): an area
+    source, a point source and a multi-point source with dipping reverse
+    ruptures, three hypocentral depths each with its own fixedDipFrac
+    (hypo_dip_fracs), ChiouYoungs2014 with its hanging-wall terms, the
+    engine's default pointsource_distance: 6 075 ruptures on one site, the
+    engine's expected mean curve and this version's hazardlib."""
+    import oq_engine_b200 as oq
+    oq._lib.lib()
+    trt = str(H['trt'])
+    mn, mx, a, b = H['gr']
+    binw = float(H['width_of_mfd_bin'])
+    npd = [tuple(r) for r in H['npd']]
+    hdd = [(p, dep) for p, dep, _f in H['hdd']]
+    fracs = [f for _p, _dep, f in H['hdd']]
+    args = (str(H['msr']), float(H['rar']), float(H['usd']), float(H['lsd']),
+            npd, hdd, fracs)
+    srcs = list(oq.AreaSource(
+        '1', H['poly_lons'], H['poly_lats'], float(H['area_discretization']),
+        oq.TruncatedGRMFD(mn, mx, binw, a, b), *args,
+        tectonic_region_type=trt))
+    srcs.append(oq.PointSource('2', H['point'][0], H['point'][1],
+                               oq.TruncatedGRMFD(mn, mx, binw, a, b), *args,
+                               tectonic_region_type=trt))
+    for i, ((x, y), av) in enumerate(zip(H['multi_points'],
+                                         H['multi_a_vals'])):
+        srcs.append(oq.PointSource('3:%d' % i, x, y,
+                                   oq.TruncatedGRMFD(mn, mx, binw, av, b),
+                                   *args, tectonic_region_type=trt))
+    assert sum(s.count_ruptures() for s in srcs) == int(H['num_ruptures'])
+    S = H['sites']
+    sc = oq.SiteCollection.from_points(
+        S[:, 0], S[:, 1], np.zeros(len(S)),
+        dict(vs30=float(H['vs30']), vs30measured=True,
+             z1pt0=float(H['z1pt0']), z2pt5=float(H['z2pt5'])))
+    imtls = {str(imt): lev for imt, lev in zip(H['imts'], H['levels'])}
+    curves = oq.calc_hazard_curves(
+        srcs, sc, imtls, {trt: oq.ChiouYoungs2014()},
+        float(H['truncation_level']),
+        investigation_time=float(H['investigation_time']),
+        maximum_distance=oq.IntegrationDistance.new(
+            str(float(H['maximum_distance']))),
+        pointsource_distance=float(H['pointsource_distance']))
+    np.testing.assert_allclose(curves['PGA'], H['expected'], rtol=1e-5,
+                               atol=1e-5)           # the QA test's delta
+    np.testing.assert_allclose(curves['PGA'], H['ref_poes'], rtol=2e-5,
+                               atol=1.5e-7)
