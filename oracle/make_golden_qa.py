@@ -451,8 +451,123 @@ def reference_case_31(d, imtls):
     return (1. - np.exp(-rmap.array[:, :, 0].astype(float)), nrup, nrows)
 
 
+def case_28():
+    """classical/case_28 (classical_test.py:406-408, delta 1e-5, expected
+    file of engine 3.26): a dipping simple fault (dip 60, rake 90, 0 - 20
+    km, 5 km mesh) with a hypoDepthDist, ChiouYoungs2014, PGA x 6 levels, one
+    site 57 km away.  The hypocentral depth distribution splits every
+    floating rupture into copies with renormalised weights
+    (source/simple_fault.py:204-268) and ChiouYoungs2014 reads nothing of the
+    hypocentre, so the curve is that of the plain fault: the device path runs
+    the fault without the distribution, the reference run below WITH it."""
+    case = os.path.join(os.path.dirname(CASE), 'case_28')
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(case, 'job.ini'))
+    sites = np.array([[float(x) for x in s.split()]
+                      for s in ini['geometry']['sites'].split(',')])
+    imtls = eval(ini['calculation']['intensity_measure_types_and_levels'])
+    out = dict(
+        sites=sites, imts=np.array(list(imtls)),
+        levels=np.array([np.asarray(imtls[i], float) for i in imtls]),
+        vs30=float(ini['site_params']['reference_vs30_value']),
+        z1pt0=float(ini['site_params']['reference_depth_to_1pt0km_per_sec']),
+        z2pt5=float(ini['site_params']['reference_depth_to_2pt5km_per_sec']),
+        investigation_time=float(ini['calculation']['investigation_time']),
+        truncation_level=float(ini['calculation']['truncation_level']),
+        maximum_distance=float(ini['calculation']['maximum_distance']),
+        spacing=float(ini['erf']['rupture_mesh_spacing']),
+        width_of_mfd_bin=float(ini['erf']['width_of_mfd_bin']))
+    root = ET.parse(os.path.join(case, 'source_model.xml')).getroot()
+    [src] = root.findall('.//n:simpleFaultSource', NS)
+    pos = [float(x) for x in src.find('.//gml:posList', NS).text.split()]
+    g = src.find('n:truncGutenbergRichterMFD', NS)
+    out.update(
+        trace=np.array(pos).reshape(-1, 2), trt=src.get('tectonicRegion'),
+        dip=float(src.find('.//n:dip', NS).text),
+        usd=float(src.find('.//n:upperSeismoDepth', NS).text),
+        lsd=float(src.find('.//n:lowerSeismoDepth', NS).text),
+        msr=src.find('n:magScaleRel', NS).text.strip(),
+        rar=float(src.find('n:ruptAspectRatio', NS).text),
+        rake=float(src.find('n:rake', NS).text),
+        gr=np.array([float(g.get(k)) for k in ('minMag', 'maxMag', 'aValue',
+                                               'bValue')]),
+        hdd=np.array([[float(n.get(k)) for k in ('probability', 'depth')]
+                      for n in src.findall('.//n:hypoDepth', NS)]))
+    with open(os.path.join(case, 'expected', 'hazard_curve-mean-PGA.csv')) as f:
+        rows = [r for r in csv.reader(f) if not r[0].startswith('#')]
+    out['expected'] = np.array(rows[1:], float)[:, 3:]
+    import sys
+    sys.path.insert(0, HERE)
+    import make_golden_sources  # noqa: bootstraps the reference
+    import types
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, Line
+    from openquake.hazardlib.geo.surface import SimpleFaultSurface
+    from openquake.hazardlib.mfd import TruncatedGRMFD
+    from openquake.hazardlib.scalerel import WC1994
+    from openquake.hazardlib.source import SimpleFaultSource
+    from openquake.hazardlib.tom import PoissonTOM
+    from openquake.hazardlib.site import SiteCollection
+    from openquake.hazardlib.contexts import ContextMaker
+    from openquake.hazardlib.calc.filters import IntegrationDistance
+    from openquake.hazardlib.map_array import MapArray
+    tom = PoissonTOM(out['investigation_time'])
+    mn, mx, a, b = out['gr']
+    trace = Line([Point(x, y) for x, y in out['trace']])
+    hypo_data = types.SimpleNamespace(
+        hypo_list=(), slip_list=(),
+        depth_list=[(p, dep) for p, dep in out['hdd']])
+    mfd = TruncatedGRMFD(mn, mx, out['width_of_mfd_bin'], a, b)
+    fault = SimpleFaultSource(
+        '1', 'Simple Fault Source', 'Active Shallow Crust', mfd,
+        out['spacing'], WC1994(), out['rar'], tom, out['usd'], out['lsd'],
+        trace, out['dip'], out['rake'], hypo_data)
+    plain = SimpleFaultSource(
+        '1', 'Simple Fault Source', 'Active Shallow Crust', mfd,
+        out['spacing'], WC1994(), out['rar'], tom, out['usd'], out['lsd'],
+        trace, out['dip'], out['rake'])
+    mesh = SimpleFaultSurface.from_fault_data(
+        trace, out['usd'], out['lsd'], out['dip'], out['spacing']).mesh
+    out['mesh_lons'], out['mesh_lats'] = mesh.lons, mesh.lats
+    out['mesh_deps'] = mesh.depths
+    out['mfd'] = np.array(mfd.get_annual_occurrence_rates())
+    out['num_ruptures_plain'] = plain.count_ruptures()
+    levels = {imt: list(v) for imt, v in imtls.items()}
+    S = out['sites']
+    sitecol = SiteCollection.from_points(
+        S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
+            reference_vs30_value=out['vs30'], reference_vs30_type='measured',
+            reference_depth_to_1pt0km_per_sec=out['z1pt0'],
+            reference_depth_to_2pt5km_per_sec=out['z2pt5']))
+    res = {}
+    for tag, src_ in (('hdd', fault), ('plain', plain)):
+        cm = ContextMaker('Active Shallow Crust', [valid.gsim(
+            '[ChiouYoungs2014]')], dict(
+            imtls=levels, truncation_level=out['truncation_level'],
+            investigation_time=out['investigation_time'],
+            maximum_distance=IntegrationDistance.new(
+                str(out['maximum_distance']))))
+        cm.tom = tom
+        src_.id = 0
+        rmap = MapArray(sitecol.sids, 6, 1, rates=True).fill(0)
+        n = 0
+        for ctx in cm.get_ctxs(src_, sitecol):
+            n += len(ctx)
+            cm.update(rmap, ctx)
+        res[tag] = 1. - np.exp(-rmap.array[:, :, 0].astype(float))
+        print('case_28 %-5s %5d context rows; reference (this version) vs '
+              'expected file: max abs %.1e, max rel (PoE > 0) %.1e' % (
+                  tag, n, np.abs(res[tag] - out['expected']).max(),
+                  np.abs(res[tag] / out['expected'] - 1)[
+                      out['expected'] > 0].max()))
+    out['ref_poes'], out['ref_poes_plain'] = res['hdd'], res['plain']
+    np.savez_compressed(os.path.join(GOLDEN, 'qa_classical_case_28.npz'),
+                        **out)
+
+
 if __name__ == '__main__':
     main()
     case_24()
     case_26()
     case_31()
+    case_28()

@@ -212,3 +212,51 @@ def test_qa_classical_case_31():
                                atol=1e-5)           # the QA test's delta
     np.testing.assert_allclose(curves['PGA'], H['ref_poes'], rtol=2e-5,
                                atol=1.5e-7)
+
+
+K = np.load(os.path.join(GOLDEN, 'qa_classical_case_28.npz'))
+
+
+def test_case_28_hypo_depth_dist_does_not_change_the_curve():
+    # the reference with and without the hypoDepthDist (renormalised weights,
+    # a model that reads nothing of the hypocentre): the same curve
+    np.testing.assert_allclose(K['ref_poes'], K['ref_poes_plain'], rtol=1e-6,
+                               atol=1e-12)
+    np.testing.assert_allclose(K['ref_poes'], K['expected'], rtol=1e-5,
+                               atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_qa_classical_case_28():
+    """classical/case_28 (classical_test.py:406-408, delta 1e-5): a dipping
+    simple fault (dip 60, reverse), floating ruptures over the 5 km mesh,
+    ChiouYoungs2014 (rrup, rjb, rx, ztor, dip of mesh ruptures: the mesh
+    kernels + oqg_hazard_dist), one site at 57 km: the engine's expected
+    mean curve and this version's hazardlib.  The hypoDepthDist of the source
+    does not change the curve (see the test above), the device path runs
+    the plain fault."""
+    import oq_engine_b200 as oq
+    oq._lib.lib()
+    trt = str(K['trt'])
+    src = oq.SimpleFaultSource(
+        '1', (K['mesh_lons'], K['mesh_lats'], K['mesh_deps']),
+        oq.ArbitraryMFD(K['mfd'][:, 0], K['mfd'][:, 1]), float(K['spacing']),
+        str(K['msr']), float(K['rar']), float(K['rake']),
+        tectonic_region_type=trt)
+    assert len(src.ruptures()) == int(K['num_ruptures_plain'])
+    S = K['sites']
+    sc = oq.SiteCollection.from_points(
+        S[:, 0], S[:, 1], np.zeros(len(S)),
+        dict(vs30=float(K['vs30']), vs30measured=True,
+             z1pt0=float(K['z1pt0']), z2pt5=float(K['z2pt5'])))
+    imtls = {str(imt): lev for imt, lev in zip(K['imts'], K['levels'])}
+    curves = oq.calc_hazard_curves(
+        [src], sc, imtls, {trt: oq.ChiouYoungs2014()},
+        float(K['truncation_level']),
+        investigation_time=float(K['investigation_time']),
+        maximum_distance=oq.IntegrationDistance.new(
+            str(float(K['maximum_distance']))))
+    np.testing.assert_allclose(curves['PGA'], K['expected'], rtol=1e-5,
+                               atol=1e-5)           # the QA test's delta
+    np.testing.assert_allclose(curves['PGA'], K['ref_poes_plain'], rtol=2e-5,
+                               atol=1.5e-7)
