@@ -20,7 +20,7 @@ from .site import SiteCollection  # noqa
 from .contexts import ContextMaker, IntegrationDistance, PlanarRuptures  # noqa
 from .source import (  # noqa
     PointSource, PointSourceBatch, TruncatedGRMFD, EvenlyDiscretizedMFD,
-    ArbitraryMFD, point_ruptures_device)
+    ArbitraryMFD, MultiPointSource, point_ruptures_device)
 from .postproc import (  # noqa
     postclassical, compute_hazard_maps, compute_hmaps, calc_mean_rates,
     rates_to_records, rates_dt)

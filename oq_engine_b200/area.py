@@ -222,3 +222,6 @@ class AreaSource(object):
         for i, (lon, lat) in enumerate(zip(lons, lats)):
             yield PointSource('%s:%d' % (self.source_id, i), lon, lat, mfd,
                               self.msr, *self.args)
+
+    def count_ruptures(self):
+        return sum(src.count_ruptures() for src in self)

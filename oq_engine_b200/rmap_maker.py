@@ -60,6 +60,15 @@ class RmapMaker(object):
             self.sources = list(group)
         if not self.sources:
             raise ValueError('no sources')
+        # distributed sources are split into their point sources first, like
+        # the engine does (split_source) before the calculation
+        from .area import AreaSource
+        from .source import MultiPointSource
+        if not getattr(group, 'src_interdep', None) == 'mutex':
+            self.sources = [
+                s for src in self.sources for s in (
+                    src if isinstance(src, (AreaSource, MultiPointSource))
+                    else [src])]
         self.src_mutex = getattr(group, 'src_interdep', None) == 'mutex'
         if getattr(group, 'rup_interdep', None) == 'mutex':
             raise NotImplementedError(

@@ -175,6 +175,53 @@ class PointSource(object):
         return len(self.get_annual_occurrence_rates()) * self.count_nphc()
 
 
+class MultiPointSource(object):
+    """
+    source/multi_point.py: point sources sharing everything but location and
+    MFD.  Iterating yields them (as the engine's split_source does before the
+    calculation).
+
+    :param lons, lats: the locations
+    :param mfds: one MFD per point (a MultiMFD of the reference is a list of
+        MFDs of one kind, mfd/multi_mfd.py), or a single MFD for all
+    """
+    def __init__(self, source_id, lons, lats, mfds, msr, rupture_aspect_ratio,
+                 upper_seismogenic_depth, lower_seismogenic_depth,
+                 nodal_plane_distribution, hypocenter_distribution,
+                 hypo_dip_fracs=None, tectonic_region_type='*'):
+        self.source_id = source_id
+        self.lons = numpy.asarray(lons, float)
+        self.lats = numpy.asarray(lats, float)
+        if len(self.lons) != len(self.lats) or len(self.lons) == 0:
+            raise ValueError('lons and lats must have the same, non zero '
+                             'length')
+        if hasattr(mfds, 'get_annual_occurrence_rates'):
+            mfds = [mfds] * len(self.lons)
+        self.mfds = list(mfds)
+        if len(self.mfds) != len(self.lons):
+            raise ValueError('expected %d MFDs, got %d' % (
+                len(self.lons), len(self.mfds)))
+        parse_msr(msr)
+        self.msr = msr
+        self.args = (rupture_aspect_ratio, upper_seismogenic_depth,
+                     lower_seismogenic_depth, list(nodal_plane_distribution),
+                     list(hypocenter_distribution), hypo_dip_fracs,
+                     tectonic_region_type)
+        self.tectonic_region_type = tectonic_region_type
+
+    def __iter__(self):
+        for i, (lon, lat, mfd) in enumerate(zip(self.lons, self.lats,
+                                                self.mfds)):
+            yield PointSource('%s:%d' % (self.source_id, i), lon, lat, mfd,
+                              self.msr, *self.args)
+
+    def __len__(self):
+        return len(self.lons)
+
+    def count_ruptures(self):
+        return sum(src.count_ruptures() for src in self)
+
+
 class OqgPointSources(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         'lon', 'lat', 'usd', 'lsd', 'rar', 'mag_beg', 'mag_cnt', 'np_beg',

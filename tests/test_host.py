@@ -255,3 +255,24 @@ def test_monitors_have_the_reference_names():
     cm2 = oq.ContextMaker('*', [oq.BooreEtAl2014()], dict(
         imtls={'PGA': [.1, .2]}, truncation_level=3.))
     assert cm2.gmf_mon.operation == 'computing mean_std'
+
+
+def test_multi_point_source_splits_into_point_sources():
+    """source/multi_point.py: one point source per location with its own MFD"""
+    mfds = [oq.TruncatedGRMFD(5.5, 7.0, 0.1, a, 0.9) for a in (3.0, 3.2)]
+    mps = oq.MultiPointSource('3', [0.2, 0.8], [-0.3, -0.3], mfds, 'WC1994',
+                              1.5, 0., 20., [(1., 0., 60., 90.)],
+                              [(.25, 5.), (.5, 10.), (.25, 15.)],
+                              [0.5, 0.6667, 0.75])
+    pts = list(mps)
+    assert [p.source_id for p in pts] == ['3:0', '3:1'] and len(mps) == 2
+    assert (pts[1].lon, pts[1].lat) == (0.8, -0.3)
+    assert pts[0].mfd is mfds[0] and pts[1].mfd is mfds[1]
+    assert pts[0].hypo_dip_fracs == [0.5, 0.6667, 0.75]
+    assert mps.count_ruptures() == 2 * 15 * 3
+    with pytest.raises(ValueError):
+        oq.MultiPointSource('x', [0.], [0., 1.], mfds, 'WC1994', 1., 0., 10.,
+                            [(1., 0., 90., 0.)], [(1., 5.)])
+    with pytest.raises(NotImplementedError):
+        oq.MultiPointSource('x', [0.], [0.], mfds[:1], 'Leonard2014_SCR', 1.,
+                            0., 10., [(1., 0., 90., 0.)], [(1., 5.)])

@@ -182,18 +182,20 @@ def test_qa_classical_case_31():
     fracs = [f for _p, _dep, f in H['hdd']]
     args = (str(H['msr']), float(H['rar']), float(H['usd']), float(H['lsd']),
             npd, hdd, fracs)
-    srcs = list(oq.AreaSource(
-        '1', H['poly_lons'], H['poly_lats'], float(H['area_discretization']),
-        oq.TruncatedGRMFD(mn, mx, binw, a, b), *args,
-        tectonic_region_type=trt))
-    srcs.append(oq.PointSource('2', H['point'][0], H['point'][1],
-                               oq.TruncatedGRMFD(mn, mx, binw, a, b), *args,
-                               tectonic_region_type=trt))
-    for i, ((x, y), av) in enumerate(zip(H['multi_points'],
-                                         H['multi_a_vals'])):
-        srcs.append(oq.PointSource('3:%d' % i, x, y,
-                                   oq.TruncatedGRMFD(mn, mx, binw, av, b),
-                                   *args, tectonic_region_type=trt))
+    # the three sources as objects: the area and the multi-point source are
+    # split into their point sources by the RmapMaker, as the engine does
+    srcs = [
+        oq.AreaSource('1', H['poly_lons'], H['poly_lats'],
+                      float(H['area_discretization']),
+                      oq.TruncatedGRMFD(mn, mx, binw, a, b), *args,
+                      tectonic_region_type=trt),
+        oq.PointSource('2', H['point'][0], H['point'][1],
+                       oq.TruncatedGRMFD(mn, mx, binw, a, b), *args,
+                       tectonic_region_type=trt),
+        oq.MultiPointSource(
+            '3', H['multi_points'][:, 0], H['multi_points'][:, 1],
+            [oq.TruncatedGRMFD(mn, mx, binw, av, b)
+             for av in H['multi_a_vals']], *args, tectonic_region_type=trt)]
     assert sum(s.count_ruptures() for s in srcs) == int(H['num_ruptures'])
     S = H['sites']
     sc = oq.SiteCollection.from_points(
