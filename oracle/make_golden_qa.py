@@ -22,6 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get('OQ_REFERENCE', '/root/reference')
 CASE = os.path.join(REF, 'openquake', 'qa_tests_data', 'classical', 'case_01')
 GOLDEN = os.path.join(HERE, '..', 'tests', 'golden')
+# SiteCollection.from_points sets z1pt0 / z2pt5 only when they are required
+REQ_SITE_PARAMS = ('vs30', 'vs30measured', 'z1pt0', 'z2pt5')
 NS = {'n': 'http://openquake.org/xmlns/nrml/0.4',
       'gml': 'http://www.opengis.net/gml'}
 
@@ -126,7 +128,8 @@ def reference_case_24(d, imtls, mfd=None, gsim='[BooreAtkinson2008]'):
         S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
             reference_vs30_value=d['vs30'], reference_vs30_type='measured',
             reference_depth_to_1pt0km_per_sec=d['z1pt0'],
-            reference_depth_to_2pt5km_per_sec=d['z2pt5']))
+            reference_depth_to_2pt5km_per_sec=d['z2pt5']),
+        req_site_params=REQ_SITE_PARAMS)
     M, L1 = len(levels), len(next(iter(levels.values())))
     rmap = MapArray(sitecol.sids, M * L1, 1, rates=True).fill(0)
     nrup = 0
@@ -438,7 +441,8 @@ def reference_case_31(d, imtls):
         S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
             reference_vs30_value=d['vs30'], reference_vs30_type='measured',
             reference_depth_to_1pt0km_per_sec=d['z1pt0'],
-            reference_depth_to_2pt5km_per_sec=d['z2pt5']))
+            reference_depth_to_2pt5km_per_sec=d['z2pt5']),
+        req_site_params=REQ_SITE_PARAMS)
     L = sum(len(v) for v in levels.values())
     rmap = MapArray(sitecol.sids, L, 1, rates=True).fill(0)
     nrup = nrows = 0
@@ -538,7 +542,8 @@ def case_28():
         S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
             reference_vs30_value=out['vs30'], reference_vs30_type='measured',
             reference_depth_to_1pt0km_per_sec=out['z1pt0'],
-            reference_depth_to_2pt5km_per_sec=out['z2pt5']))
+            reference_depth_to_2pt5km_per_sec=out['z2pt5']),
+        req_site_params=REQ_SITE_PARAMS)
     res = {}
     for tag, src_ in (('hdd', fault), ('plain', plain)):
         cm = ContextMaker('Active Shallow Crust', [valid.gsim(
@@ -565,9 +570,146 @@ def case_28():
                         **out)
 
 
+def case_78():
+    """classical/case_78 (classical_test.py:1014-1020, delta 1e-5, expected
+    file of engine 3.26): a point source and a dipping simple fault, each
+    with its own NegativeBinomialTOM (mu, alpha: non-Poissonian probs_occur
+    per rupture, tom.py:220-319), AbrahamsonEtAl2014 (rrup, rjb, rx, ry0,
+    width, ztor of mesh ruptures; z1pt0 and the inferred vs30 matter), PGA x
+    50 levels, one site."""
+    case = os.path.join(os.path.dirname(CASE), 'case_78')
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(case, 'job.ini'))
+    sites = np.array([[float(x) for x in s.split()]
+                      for s in ini['geometry']['sites'].split(',')])
+    imtls = eval(ini['calculation']['intensity_measure_types_and_levels'],
+                 {'logscale': logscale})
+    out = dict(
+        sites=sites, imts=np.array(list(imtls)),
+        levels=np.array([np.asarray(imtls[i], float) for i in imtls]),
+        vs30=float(ini['site_params']['reference_vs30_value']),
+        vs30measured=ini['site_params']['reference_vs30_type'] == 'measured',
+        z1pt0=float(ini['site_params']['reference_depth_to_1pt0km_per_sec']),
+        z2pt5=float(ini['site_params']['reference_depth_to_2pt5km_per_sec']),
+        investigation_time=float(ini['calculation']['investigation_time']),
+        truncation_level=float(ini['calculation']['truncation_level']),
+        maximum_distance=float(ini['calculation']['maximum_distance']),
+        spacing=float(ini['erf']['rupture_mesh_spacing']),
+        width_of_mfd_bin=float(ini['erf']['width_of_mfd_bin']))
+    NS5 = {'n': 'http://openquake.org/xmlns/nrml/0.5',
+           'gml': 'http://www.opengis.net/gml'}
+    root = ET.parse(os.path.join(case, 'source_negbinom.xml')).getroot()
+    [ps] = root.findall('.//n:pointSource', NS5)
+    [fs] = root.findall('.//n:simpleFaultSource', NS5)
+    f = lambda node, tag: float(node.find(tag, NS5).text)  # noqa
+    imfd = ps.find('n:incrementalMFD', NS5)
+    g = fs.find('n:truncGutenbergRichterMFD', NS5)
+    out.update(
+        trt=root.find('.//n:sourceGroup', NS5).get('tectonicRegion'),
+        ps_tom=np.array([float(ps.get('mu')), float(ps.get('alpha'))]),
+        ps_loc=np.array([float(x) for x in ps.find(
+            './/gml:pos', NS5).text.split()]),
+        ps_usd=f(ps, './/n:upperSeismoDepth'),
+        ps_lsd=f(ps, './/n:lowerSeismoDepth'),
+        ps_msr=ps.find('n:magScaleRel', NS5).text.strip(),
+        ps_rar=f(ps, 'n:ruptAspectRatio'),
+        ps_mfd=np.array([float(imfd.get('minMag')),
+                         float(imfd.get('binWidth'))] + [
+            float(x) for x in imfd.find('n:occurRates', NS5).text.split()]),
+        ps_npd=np.array([[float(n.get(k)) for k in (
+            'probability', 'strike', 'dip', 'rake')]
+            for n in ps.findall('.//n:nodalPlane', NS5)]),
+        ps_hdd=np.array([[float(n.get(k)) for k in ('probability', 'depth')]
+                         for n in ps.findall('.//n:hypoDepth', NS5)]),
+        fs_tom=np.array([float(fs.get('mu')), float(fs.get('alpha'))]),
+        fs_trace=np.array([float(x) for x in fs.find(
+            './/gml:posList', NS5).text.split()]).reshape(-1, 2),
+        fs_dip=f(fs, './/n:dip'), fs_usd=f(fs, './/n:upperSeismoDepth'),
+        fs_lsd=f(fs, './/n:lowerSeismoDepth'),
+        fs_msr=fs.find('n:magScaleRel', NS5).text.strip(),
+        fs_rar=f(fs, 'n:ruptAspectRatio'), fs_rake=f(fs, 'n:rake'),
+        fs_gr=np.array([float(g.get(k)) for k in ('minMag', 'maxMag',
+                                                  'aValue', 'bValue')]))
+    with open(os.path.join(case, 'expected',
+                           'hazard_curve-mean-PGA_NegBinomTest.csv')) as fh:
+        rows = [r for r in csv.reader(fh) if not r[0].startswith('#')]
+    out['expected'] = np.array(rows[1:], float)[:, 3:]
+    import sys
+    sys.path.insert(0, HERE)
+    import make_golden_sources  # noqa: bootstraps the reference
+    import types
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, Line, NodalPlane
+    from openquake.hazardlib.geo.surface import SimpleFaultSurface
+    from openquake.hazardlib.pmf import PMF
+    from openquake.hazardlib.mfd import TruncatedGRMFD, EvenlyDiscretizedMFD
+    from openquake.hazardlib.scalerel import WC1994, PointMSR
+    from openquake.hazardlib.source import SimpleFaultSource, PointSource
+    from openquake.hazardlib.tom import NegativeBinomialTOM
+    from openquake.hazardlib.site import SiteCollection
+    from openquake.hazardlib.contexts import ContextMaker
+    from openquake.hazardlib.calc.filters import IntegrationDistance
+    from openquake.hazardlib.map_array import MapArray
+    T = out['investigation_time']
+    trt = 'Active Shallow Crust'
+    assert out['ps_msr'] == 'PointMSR' and out['fs_msr'] == 'WC1994'
+    point = PointSource(
+        '00000', 'point00000', trt, EvenlyDiscretizedMFD(
+            out['ps_mfd'][0], out['ps_mfd'][1], list(out['ps_mfd'][2:])),
+        out['spacing'], PointMSR(), out['ps_rar'],
+        NegativeBinomialTOM(T, *out['ps_tom']), out['ps_usd'], out['ps_lsd'],
+        Point(*out['ps_loc']),
+        PMF([(p, NodalPlane(s, d, r)) for p, s, d, r in out['ps_npd']]),
+        PMF([(p, d) for p, d in out['ps_hdd']]))
+    mn, mx, a, b = out['fs_gr']
+    trace = Line([Point(x, y) for x, y in out['fs_trace']])
+    mfd = TruncatedGRMFD(mn, mx, out['width_of_mfd_bin'], a, b)
+    fault = SimpleFaultSource(
+        '00001', 'simplefault', trt, mfd, out['spacing'], WC1994(),
+        out['fs_rar'], NegativeBinomialTOM(T, *out['fs_tom']), out['fs_usd'],
+        out['fs_lsd'], trace, out['fs_dip'], out['fs_rake'])
+    mesh = SimpleFaultSurface.from_fault_data(
+        trace, out['fs_usd'], out['fs_lsd'], out['fs_dip'],
+        out['spacing']).mesh
+    out['mesh_lons'], out['mesh_lats'] = mesh.lons, mesh.lats
+    out['mesh_deps'] = mesh.depths
+    out['fs_mfd'] = np.array(mfd.get_annual_occurrence_rates())
+    out['fs_num_ruptures'] = fault.count_ruptures()
+    levels = {imt: list(v) for imt, v in imtls.items()}
+    S = out['sites']
+    sitecol = SiteCollection.from_points(
+        S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
+            reference_vs30_value=out['vs30'],
+            reference_vs30_type='measured' if out['vs30measured']
+            else 'inferred',
+            reference_depth_to_1pt0km_per_sec=out['z1pt0'],
+            reference_depth_to_2pt5km_per_sec=out['z2pt5']),
+        req_site_params=REQ_SITE_PARAMS)
+    pmap = MapArray(sitecol.sids, 50, 1).fill(1.)
+    nrows = 0
+    for src_ in (point, fault):
+        cm = ContextMaker(trt, [valid.gsim('[AbrahamsonEtAl2014]')], dict(
+            imtls=levels, truncation_level=out['truncation_level'],
+            investigation_time=T, maximum_distance=IntegrationDistance.new(
+                str(out['maximum_distance']))))
+        cm.tom = src_.temporal_occurrence_model
+        src_.id = 0
+        for ctx in cm.get_ctxs(src_, sitecol):
+            nrows += len(ctx)
+            cm.update(pmap, ctx)
+    out['ref_poes'] = (~pmap).array[:, :, 0]
+    print('case_78: %d context rows; reference (this version) vs expected '
+          'file: max abs %.1e, max rel %.1e' % (
+              nrows, np.abs(out['ref_poes'] - out['expected']).max(),
+              np.abs(out['ref_poes'] / out['expected'] - 1).max()))
+    np.savez_compressed(os.path.join(GOLDEN, 'qa_classical_case_78.npz'),
+                        **out)
+
+
 if __name__ == '__main__':
     main()
     case_24()
     case_26()
     case_31()
     case_28()
+    case_78()

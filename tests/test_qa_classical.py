@@ -262,3 +262,54 @@ def test_qa_classical_case_28():
                                atol=1e-5)           # the QA test's delta
     np.testing.assert_allclose(curves['PGA'], K['ref_poes_plain'], rtol=2e-5,
                                atol=1.5e-7)
+
+
+Q = np.load(os.path.join(GOLDEN, 'qa_classical_case_78.npz'))
+
+
+@pytest.mark.gpu
+def test_qa_classical_case_78():
+    """classical/case_78 (classical_test.py:1014-1020, delta 1e-5): a point
+    source and a dipping simple fault, each with its own NegativeBinomialTOM
+    (non-Poissonian probs_occur per rupture), AbrahamsonEtAl2014 with an
+    inferred vs30 and a basin depth, PGA x 50 levels: the engine's expected
+    mean curve and this version's hazardlib.  Each source is a group of its
+    own because the temporal occurrence model belongs to the source."""
+    import oq_engine_b200 as oq
+    oq._lib.lib()
+    trt = str(Q['trt'])
+    T = float(Q['investigation_time'])
+    point = oq.PointSource(
+        '00000', Q['ps_loc'][0], Q['ps_loc'][1],
+        oq.EvenlyDiscretizedMFD(Q['ps_mfd'][0], Q['ps_mfd'][1],
+                                list(Q['ps_mfd'][2:])),
+        str(Q['ps_msr']), float(Q['ps_rar']), float(Q['ps_usd']),
+        float(Q['ps_lsd']), [tuple(r) for r in Q['ps_npd']],
+        [tuple(r) for r in Q['ps_hdd']], tectonic_region_type=trt)
+    point.temporal_occurrence_model = oq.NegativeBinomialTOM(T, *Q['ps_tom'])
+    fault = oq.SimpleFaultSource(
+        '00001', (Q['mesh_lons'], Q['mesh_lats'], Q['mesh_deps']),
+        oq.ArbitraryMFD(Q['fs_mfd'][:, 0], Q['fs_mfd'][:, 1]),
+        float(Q['spacing']), str(Q['fs_msr']), float(Q['fs_rar']),
+        float(Q['fs_rake']), tectonic_region_type=trt)
+    fault.temporal_occurrence_model = oq.NegativeBinomialTOM(T, *Q['fs_tom'])
+    assert len(fault.ruptures()) == int(Q['fs_num_ruptures'])
+    S = Q['sites']
+    sc = oq.SiteCollection.from_points(
+        S[:, 0], S[:, 1], np.zeros(len(S)),
+        dict(vs30=float(Q['vs30']), vs30measured=bool(Q['vs30measured']),
+             z1pt0=float(Q['z1pt0']), z2pt5=float(Q['z2pt5'])))
+    imtls = {str(imt): lev for imt, lev in zip(Q['imts'], Q['levels'])}
+    groups = [oq.SourceGroup(trt, [src], src.source_id, 'indep', 'indep')
+              for src in (point, fault)]
+    curves = oq.calc_hazard_curves(
+        groups, sc, imtls, {trt: oq.AbrahamsonEtAl2014()},
+        float(Q['truncation_level']), investigation_time=T,
+        maximum_distance=oq.IntegrationDistance.new(
+            str(float(Q['maximum_distance']))))
+    np.testing.assert_allclose(curves['PGA'], Q['expected'], rtol=1e-5,
+                               atol=1e-5)           # the QA test's delta
+    # this version's hazardlib (float32 map of probabilities: its PoEs carry
+    # an absolute 6e-8 per multiplication)
+    np.testing.assert_allclose(curves['PGA'], Q['ref_poes'], rtol=2e-5,
+                               atol=1e-6)
