@@ -122,6 +122,30 @@ class IntegrationDistance(dict):
         pairs = self.get(trt, self.get('default'))
         return magdepdist(pairs)
 
+    def cut(self, min_mag_by_trt):
+        """
+        The engine's `minimum_magnitude` (calc/filters.py:228-259, applied by
+        OqParam to maximum_distance): the (mag, dist) pairs of every tectonic
+        region type start at its minimum magnitude, with the distance
+        interpolated there, so that smaller magnitudes get distance zero and
+        their ruptures are dropped by the distance filter.  In place.
+        """
+        lower = dict(min_mag_by_trt)
+        if 'default' not in self:
+            self['default'] = max(
+                self.values(), key=lambda prs: max(d for _m, d in prs))
+        if 'default' not in lower:
+            lower['default'] = min(lower.values())
+        for trt in set(self) | set(lower):
+            mmin = lower.get(trt, lower['default'])
+            if not mmin:
+                continue
+            pairs = self.get(trt, self['default'])
+            at_min = float(magdepdist(pairs)(mmin))
+            kept = [(m, d) for m, d in pairs if m >= mmin]
+            self[trt] = kept if kept and kept[0][0] <= mmin else [
+                (mmin, at_min)] + kept
+
 
 class magdepdist(object):
     """Linear interpolation mag -> distance (calc/filters.py:183-190:

@@ -706,8 +706,127 @@ def case_78():
                         **out)
 
 
+def case_03():
+    """classical/case_03 (classical_test.py:118-120, default delta 1e-5,
+    expected file of engine 3.23): two area sources over the same polygon,
+    minimum_magnitude = 5.7 (OqParam cuts maximum_distance at it,
+    calc/filters.py:228-259: the smaller magnitudes have no integration
+    distance, the second source, maximum magnitude 5.5, contributes nothing),
+    width_of_mfd_bin = 0.2, BooreAtkinson2008, PGA x 5 levels, one site."""
+    case = os.path.join(os.path.dirname(CASE), 'case_03')
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(case, 'job.ini'))
+    sites = np.array([[float(x) for x in s.split()]
+                      for s in ini['geometry']['sites'].split(',')])
+    imtls = eval(ini['calculation']['intensity_measure_types_and_levels'],
+                 {'logscale': logscale})
+    out = dict(
+        sites=sites, imts=np.array(list(imtls)),
+        levels=np.array([np.asarray(imtls[i], float) for i in imtls]),
+        vs30=float(ini['site_params']['reference_vs30_value']),
+        z1pt0=float(ini['site_params']['reference_depth_to_1pt0km_per_sec']),
+        z2pt5=float(ini['site_params']['reference_depth_to_2pt5km_per_sec']),
+        investigation_time=float(ini['calculation']['investigation_time']),
+        truncation_level=float(ini['calculation']['truncation_level']),
+        maximum_distance=float(ini['calculation']['maximum_distance']),
+        minimum_magnitude=float(ini['calculation']['minimum_magnitude']),
+        width_of_mfd_bin=float(ini['erf']['width_of_mfd_bin']),
+        area_discretization=float(ini['erf']['area_source_discretization']))
+    NS5 = {'n': 'http://openquake.org/xmlns/nrml/0.5',
+           'gml': 'http://www.opengis.net/gml'}
+    grs = []
+    for k, fname in enumerate(('source_model.xml', 'source_model_2.xml')):
+        root = ET.parse(os.path.join(case, fname)).getroot()
+        [src] = root.findall('.//n:areaSource', NS5)
+        pos = [float(x) for x in src.find('.//gml:posList', NS5).text.split()]
+        g = src.find('n:truncGutenbergRichterMFD', NS5)
+        grs.append([float(g.get(x)) for x in ('minMag', 'maxMag', 'aValue',
+                                              'bValue')])
+        d = dict(
+            poly_lons=np.array(pos[0::2]), poly_lats=np.array(pos[1::2]),
+            trt=src.get('tectonicRegion'),
+            usd=float(src.find('.//n:upperSeismoDepth', NS5).text),
+            lsd=float(src.find('.//n:lowerSeismoDepth', NS5).text),
+            msr=src.find('n:magScaleRel', NS5).text.strip(),
+            rar=float(src.find('n:ruptAspectRatio', NS5).text),
+            npd=np.array([[float(n.get(x)) for x in (
+                'probability', 'strike', 'dip', 'rake')]
+                for n in src.findall('.//n:nodalPlane', NS5)]),
+            hdd=np.array([[float(n.get(x)) for x in ('probability', 'depth')]
+                          for n in src.findall('.//n:hypoDepth', NS5)]))
+        if k == 0:
+            out.update(d)
+        else:       # the two sources differ by the MFD only
+            for key, val in d.items():
+                np.testing.assert_array_equal(val, out[key])
+    out['grs'] = np.array(grs)
+    with open(os.path.join(case, 'expected', 'hazard_curve-PGA.csv')) as f:
+        rows = [r for r in csv.reader(f) if not r[0].startswith('#')]
+    out['expected'] = np.array(rows[1:], float)[:, 3:]
+    import sys
+    sys.path.insert(0, HERE)
+    import make_golden_sources  # noqa: bootstrap + polygon shim
+    import types
+    from openquake.hazardlib import valid
+    from openquake.hazardlib.geo import Point, Polygon, NodalPlane
+    from openquake.hazardlib.pmf import PMF
+    from openquake.hazardlib.mfd import TruncatedGRMFD
+    from openquake.hazardlib.scalerel import WC1994
+    from openquake.hazardlib.source import AreaSource
+    from openquake.hazardlib.tom import PoissonTOM
+    from openquake.hazardlib.site import SiteCollection
+    from openquake.hazardlib.contexts import ContextMaker
+    from openquake.hazardlib.calc.filters import IntegrationDistance
+    from openquake.hazardlib.map_array import MapArray
+    tom = PoissonTOM(out['investigation_time'])
+    maxdist = IntegrationDistance.new(str(out['maximum_distance']))
+    maxdist.cut({'default': out['minimum_magnitude']})
+    levels = {imt: list(v) for imt, v in imtls.items()}
+    cm = ContextMaker('Active Shallow Crust', [valid.gsim(
+        '[BooreAtkinson2008]')], dict(
+        imtls=levels, truncation_level=out['truncation_level'],
+        investigation_time=out['investigation_time'],
+        maximum_distance=maxdist))
+    cm.tom = tom
+    S = out['sites']
+    sitecol = SiteCollection.from_points(
+        S[:, 0], S[:, 1], sitemodel=types.SimpleNamespace(
+            reference_vs30_value=out['vs30'], reference_vs30_type='measured',
+            reference_depth_to_1pt0km_per_sec=out['z1pt0'],
+            reference_depth_to_2pt5km_per_sec=out['z2pt5']),
+        req_site_params=REQ_SITE_PARAMS)
+    rmap = MapArray(sitecol.sids, 5, 1, rates=True).fill(0)
+    nrup = nrows = 0
+    for mn, mx, a, b in grs:
+        if mx < out['minimum_magnitude']:
+            continue    # _filter_mag, calculators/preclassical.py:100-109
+        area = AreaSource(
+            '1', 'Area Source', 'Active Shallow Crust',
+            TruncatedGRMFD(mn, mx, out['width_of_mfd_bin'], a, b), 2.,
+            WC1994(), out['rar'], tom, out['usd'], out['lsd'],
+            PMF([(p, NodalPlane(s, dip, r)) for p, s, dip, r in out['npd']]),
+            PMF([(p, dep) for p, dep in out['hdd']]),
+            Polygon([Point(x, y) for x, y in zip(out['poly_lons'],
+                                                 out['poly_lats'])]),
+            out['area_discretization'])
+        for src in area:
+            src.id = 0
+            nrup += src.count_ruptures()
+            for ctx in cm.get_ctxs(src, sitecol):
+                nrows += len(ctx)
+                cm.update(rmap, ctx)
+    out['ref_poes'] = 1. - np.exp(-rmap.array[:, :, 0].astype(float))
+    out['num_ruptures'], out['num_rows'] = nrup, nrows
+    print('case_03: %d ruptures, %d context rows kept; reference (this '
+          'version) vs expected file: max abs %.1e' % (
+              nrup, nrows, np.abs(out['ref_poes'] - out['expected']).max()))
+    np.savez_compressed(os.path.join(GOLDEN, 'qa_classical_case_03.npz'),
+                        **out)
+
+
 if __name__ == '__main__':
     main()
+    case_03()
     case_24()
     case_26()
     case_31()

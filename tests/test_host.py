@@ -276,3 +276,17 @@ def test_multi_point_source_splits_into_point_sources():
     with pytest.raises(NotImplementedError):
         oq.MultiPointSource('x', [0.], [0.], mfds[:1], 'Leonard2014_SCR', 1.,
                             0., 10., [(1., 0., 90., 0.)], [(1., 5.)])
+
+
+def test_integration_distance_cut():
+    """IntegrationDistance.cut, the doctest values of calc/filters.py:232-240"""
+    md = oq.IntegrationDistance.new('[(4., 50), (8., 200.)]')
+    md.cut({'default': 5.})
+    assert md == {'default': [(5.0, 87.5), (8.0, 200.0)]}
+    md = oq.IntegrationDistance.new('200')
+    md.cut({"Active Shallow Crust": 5.2, "default": 4.})
+    assert md == {'default': [(4.0, 200.0), (10.2, 200)],
+                  'Active Shallow Crust': [(5.2, 200.0), (10.2, 200)]}
+    # smaller magnitudes have no integration distance: their ruptures go
+    f = md('Active Shallow Crust')
+    assert f(5.1) == 0. and f(5.2) == 200. and f(7.) == 200.

@@ -313,3 +313,45 @@ def test_qa_classical_case_78():
     # an absolute 6e-8 per multiplication)
     np.testing.assert_allclose(curves['PGA'], Q['ref_poes'], rtol=2e-5,
                                atol=1e-6)
+
+
+C3 = np.load(os.path.join(GOLDEN, 'qa_classical_case_03.npz'))
+
+
+@pytest.mark.gpu
+def test_qa_classical_case_03():
+    """classical/case_03 (classical_test.py:118-120, delta 1e-5): two area
+    sources over one polygon with minimum_magnitude = 5.7 -- the integration
+    distance is cut at it (IntegrationDistance.cut), the smaller magnitudes
+    have distance zero and their ruptures are dropped by the distance filter
+    on the device, the second source (maximum magnitude 5.5) contributes
+    nothing; MFD binned with width_of_mfd_bin = 0.2; BooreAtkinson2008."""
+    import oq_engine_b200 as oq
+    oq._lib.lib()
+    trt = str(C3['trt'])
+    binw = float(C3['width_of_mfd_bin'])
+    srcs = [oq.AreaSource(
+        str(k + 1), C3['poly_lons'], C3['poly_lats'],
+        float(C3['area_discretization']),
+        oq.TruncatedGRMFD(mn, mx, binw, a, b), str(C3['msr']),
+        float(C3['rar']), float(C3['usd']), float(C3['lsd']),
+        [tuple(r) for r in C3['npd']], [tuple(r) for r in C3['hdd']],
+        tectonic_region_type=trt)
+        for k, (mn, mx, a, b) in enumerate(C3['grs'])]
+    maxdist = oq.IntegrationDistance.new(str(float(C3['maximum_distance'])))
+    maxdist.cut({'default': float(C3['minimum_magnitude'])})
+    S = C3['sites']
+    sc = oq.SiteCollection.from_points(
+        S[:, 0], S[:, 1], np.zeros(len(S)),
+        dict(vs30=float(C3['vs30']), vs30measured=True,
+             z1pt0=float(C3['z1pt0']), z2pt5=float(C3['z2pt5'])))
+    imtls = {str(imt): lev for imt, lev in zip(C3['imts'], C3['levels'])}
+    curves = oq.calc_hazard_curves(
+        srcs, sc, imtls, {trt: oq.BooreAtkinson2008()},
+        float(C3['truncation_level']),
+        investigation_time=float(C3['investigation_time']),
+        maximum_distance=maxdist)
+    np.testing.assert_allclose(curves['PGA'], C3['expected'], rtol=1e-5,
+                               atol=1e-5)           # the QA test's delta
+    np.testing.assert_allclose(curves['PGA'], C3['ref_poes'], rtol=2e-5,
+                               atol=1.5e-7)
