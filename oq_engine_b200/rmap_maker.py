@@ -84,8 +84,32 @@ class RmapMaker(object):
         self.cmaker.tom = self.tom = tom
 
     # ----------------------------------------------------------- folding
+    @staticmethod
+    def _tom_key(tom):
+        return (type(tom).__name__, getattr(tom, 'time_span', None),
+                repr(getattr(tom, 'mu', None)),
+                repr(getattr(tom, 'alpha', None)))
+
     def _fold(self, pmap, srcs):
-        """all the ruptures of `srcs` into pmap; returns the kept pairs"""
+        """all the ruptures of `srcs` into pmap; returns the kept pairs.
+        The temporal occurrence model belongs to the source (the reference
+        reads src.temporal_occurrence_model per source, contexts.py:443-474,
+        944-953): sources with different models (e.g. NegativeBinomialTOM
+        with their own mu / alpha) are folded one model at a time."""
+        if self.cluster:
+            return self._fold_tom(pmap, srcs)
+        by_tom = {}
+        for s in srcs:
+            tom = getattr(s, 'temporal_occurrence_model', None) or self.tom
+            by_tom.setdefault(self._tom_key(tom), (tom, []))[1].append(s)
+        kept = 0
+        for tom, group in by_tom.values():
+            self.cmaker.tom = tom
+            kept += self._fold_tom(pmap, group)
+        self.cmaker.tom = self.tom
+        return kept
+
+    def _fold_tom(self, pmap, srcs):
         cm, kept = self.cmaker, 0
         points = [s for s in srcs if isinstance(s, PointSource)]
         if points:

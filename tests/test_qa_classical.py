@@ -273,8 +273,8 @@ def test_qa_classical_case_78():
     source and a dipping simple fault, each with its own NegativeBinomialTOM
     (non-Poissonian probs_occur per rupture), AbrahamsonEtAl2014 with an
     inferred vs30 and a basin depth, PGA x 50 levels: the engine's expected
-    mean curve and this version's hazardlib.  Each source is a group of its
-    own because the temporal occurrence model belongs to the source."""
+    mean curve and this version's hazardlib.  The temporal occurrence model
+    belongs to the source, not to the group."""
     import oq_engine_b200 as oq
     oq._lib.lib()
     trt = str(Q['trt'])
@@ -300,10 +300,10 @@ def test_qa_classical_case_78():
         dict(vs30=float(Q['vs30']), vs30measured=bool(Q['vs30measured']),
              z1pt0=float(Q['z1pt0']), z2pt5=float(Q['z2pt5'])))
     imtls = {str(imt): lev for imt, lev in zip(Q['imts'], Q['levels'])}
-    groups = [oq.SourceGroup(trt, [src], src.source_id, 'indep', 'indep')
-              for src in (point, fault)]
+    # one group: the RmapMaker folds the sources one temporal occurrence
+    # model at a time
     curves = oq.calc_hazard_curves(
-        groups, sc, imtls, {trt: oq.AbrahamsonEtAl2014()},
+        [point, fault], sc, imtls, {trt: oq.AbrahamsonEtAl2014()},
         float(Q['truncation_level']), investigation_time=T,
         maximum_distance=oq.IntegrationDistance.new(
             str(float(Q['maximum_distance']))))
