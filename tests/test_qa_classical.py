@@ -355,3 +355,24 @@ def test_qa_classical_case_03():
                                atol=1e-5)           # the QA test's delta
     np.testing.assert_allclose(curves['PGA'], C3['ref_poes'], rtol=2e-5,
                                atol=1.5e-7)
+
+
+@pytest.mark.parametrize('case, delta', [('03', 1e-5), ('26', 2e-5),
+                                         ('28', 1e-5), ('31', 1e-5),
+                                         ('78', 1e-5)])
+def test_fixtures_reference_run_meets_the_expected_files(case, delta):
+    """the pin of the fixtures: this version's hazardlib, run by
+    oracle/make_golden_qa.py on the inputs of each QA test, reproduces the
+    engine's expected file within the QA test's own delta (case_24 is the
+    exception: its files date from engine 3.20 and are compared at 1e-3)"""
+    d = np.load(os.path.join(GOLDEN, 'qa_classical_case_%s.npz' % case))
+    ref = d['ref_poes'].reshape(d['expected'].shape)
+    np.testing.assert_allclose(ref, d['expected'], rtol=delta, atol=delta)
+
+
+def test_fixture_case_24_drift():
+    for imt in E['imts']:
+        m = list(E['imts']).index(imt)
+        np.testing.assert_allclose(E['ref_poes'][:, m],
+                                   E['expected_' + str(imt)], rtol=1e-3,
+                                   atol=1e-3)
