@@ -125,6 +125,23 @@ def main():
                   np.abs(out[case + '_ref'] - out[case + '_poes']).max())
         except Exception as exc:      # rjb of a mesh needs shapely here
             print(case, 'reference run not possible here:', repr(exc)[:200])
+    # the non-parametric source equivalent to case 2 (peer_test.py:216-266):
+    # 6 x 12 rupture meshes of 8 x 15 nodes, each with the probabilities of
+    # 0 and 1 occurrences
+    nd = T.SET1_CASE2_SOURCE_DATA
+    lons, lats, deps, hypo = [], [], [], []
+    for i in range(nd['num_rups_dip']):
+        for j in range(nd['num_rups_strike']):
+            lons.append(nd['lons'])
+            lats.append(nd['lats'][j])
+            deps.append(nd['depths'][i])
+            hypo.append([nd['hypo_lons'][i, j], nd['hypo_lats'][i, j],
+                         nd['hypo_depths'][i, j]])
+    out['np_lons'], out['np_lats'] = np.array(lons), np.array(lats)
+    out['np_deps'], out['np_hypo'] = np.array(deps), np.array(hypo)
+    out['np_pmf'] = np.array([p for p, _n in nd['pmf'].data])
+    assert [n for _p, n in nd['pmf'].data] == [0, 1]
+    out['np_mag'], out['np_rake'] = nd['mag'], nd['rake']
     np.savez_compressed(os.path.join(GOLDEN, 'peer_set1.npz'), **out)
     print({k: np.shape(v) for k, v in out.items()})
 

@@ -92,3 +92,28 @@ def test_peer_set1_fault(oq, case):
     for s in range(7):
         np.testing.assert_allclose(got[s], D[case + '_poes'][s],
                                    atol=atols[s], rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_peer_set1_non_parametric_source(oq):
+    """peer_test.py:216-266: the non-parametric source equivalent to case 2
+    -- 72 rupture meshes of 8 x 15 nodes, each with the probabilities of 0
+    and 1 occurrences (probs_occur) instead of a rate -- against the
+    published values of case 2 with the tolerances of the reference's test"""
+    U = len(D['np_lons'])
+    assert U == 72 and D['np_lons'].shape[1:] == (8, 15)
+    rups = oq.MeshRuptures.from_meshes(
+        [(D['np_lons'][u], D['np_lats'][u], D['np_deps'][u])
+         for u in range(U)],
+        np.full(U, float(D['np_mag'])), float(D['np_rake']),
+        np.full(U, np.nan), hypo=D['np_hypo'],
+        probs_occur=np.tile(D['np_pmf'], (U, 1)))
+    group = oq.SourceGroup(TRT, [rups], 'non parametric', 'indep', 'indep')
+    curves = oq.calc_hazard_curves(
+        [group], sites(oq, D['fault_sites']), {'PGA': D['c2_imls']},
+        {TRT: oq.SadighEtAl1997()}, 0, investigation_time=1.)
+    got = curves['PGA']
+    atols = [3e-3, 2e-5, 2e-5, 1e-3, 1e-3, 1e-3, 2e-5]   # peer_test.py:253-266
+    for s in range(7):
+        np.testing.assert_allclose(got[s], D['c2_poes'][s], atol=atols[s],
+                                   rtol=1e-5)
