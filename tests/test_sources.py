@@ -540,3 +540,45 @@ def test_reference_manual_contextmaker_example(oq):
     pmap = oq.MapArray(sc.sids, cm.L, cm.G).fill(1.)
     assert cm.hazard_point_sources(pmap, srcs, sc, count=True) == 705
     np.testing.assert_allclose((~pmap).array, [[[0.00507998]]], rtol=2e-5)
+
+
+@pytest.mark.gpu
+def test_reference_known_pointsource_distance_rrups(oq):
+    """The engine QA test classical/case_48 (calculators/tests/
+    classical_test.py:647-704): a point source with 10 magnitudes, PeerMSR
+    and 2 hypocentral depths, two sites at 55 and 111 km, maximum distance
+    110 km.  The reference's test holds the rupture distances of the context
+    rows, rounded to 0.1 km: the 20 exact ones per site, and the 15 left
+    with pointsource_distance = 50 km (for the magnitudes whose psdist the
+    site is beyond, the two depths collapse into the average rupture).
+    Rupture generation, distances and the near / far selection on the
+    device."""
+    expect = np.array([
+        [54.3, 109.8], [54.1, 109.7], [53.9, 109.4], [53.7, 109.3],
+        [53.3, 108.9], [53.3, 108.8], [52.7, 108.3], [52.7, 108.2],
+        [52.0, 107.5], [51.9, 107.5], [50.5, 106.1], [50.4, 106.0],
+        [47.8, 103.2], [47.7, 103.1], [43.7, 98.8], [43.6, 98.6],
+        [38.2, 92.0], [38.0, 91.9], [33.0, 82.3], [32.8, 82.2]])
+    approx = np.array([
+        [54.2, 109.7], [53.8, 109.3], [53.3, 108.8], [52.7, 108.2],
+        [51.9, 107.5], [50.5, 106.1], [50.4, 106.0], [47.8, 103.2],
+        [47.7, 103.1], [43.7, 98.8], [43.6, 98.6], [38.2, 92.0],
+        [38.0, 91.9], [33.0, 82.3], [32.8, 82.2]])
+    src = oq.PointSource(
+        '1', 0., 0., oq.TruncatedGRMFD(5., 7., 0.2, 3., 1.), 'PeerMSR', 1.,
+        0., 10., [(1., 144., 87., -179.)],
+        [(.66666667, 3.), (.33333333, 6.)])
+    sc = oq.SiteCollection.from_points(
+        [0., 0.], [0.5, 1.], [0., 0.],
+        dict(vs30=800., vs30measured=True, z1pt0=50., z2pt5=2.5))
+    for psd, want in ((1000., expect), (50., approx)):
+        cm = oq.ContextMaker('*', [oq.SadighEtAl1997()], dict(
+            imtls={'PGA': [0.1]}, truncation_level=2., investigation_time=100.,
+            maximum_distance=oq.IntegrationDistance.new('110.0'),
+            pointsource_distance=psd))
+        ctx = cm.recarray(cm.get_ctxs(src, sc))
+        for sid in (0, 1):
+            got = np.sort(ctx.rrup[ctx.sids == sid])[::-1]
+            assert len(got) == len(want), (psd, sid, len(got))
+            np.testing.assert_allclose(got, want[:, sid], atol=.05,
+                                       err_msg='psd %s site %d' % (psd, sid))
